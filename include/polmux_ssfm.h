@@ -1,0 +1,173 @@
+/*
+ * polmux_ssfm.h -- C ABI of the B200-native split-step Fourier fiber channel.
+ *
+ * Drop-in boundary for ONE path of the Optilux/Polmux reference: the SSFM
+ * propagation loop inside fiber.m.  Every entry point names the reference
+ * interface it replaces (file:line under the reference tree).  Plain C, POD
+ * only, no exceptions cross the boundary, no torch / MATLAB types.
+ *
+ * Conventions
+ *   - all lengths in [m], times [ns], powers [mW]  (fiber.m units)
+ *   - complex samples are IEEE double (the reference's arithmetic); the
+ *     "field" is two polarizations x nfc columns x nfft samples, column-major
+ *     like GSTATE.FIELDX / GSTATE.FIELDY (reset_all.m:158-159)
+ *   - every function returns PMX_OK (0) or a negative pmx_status; the text of
+ *     the last error is available through pmx_last_error()
+ *   - a pmx_ctx owns one CUDA device, one stream and its cached tables; it is
+ *     thread-compatible (one ctx per host thread), not thread-safe
+ *   - there is NO CPU fallback: without a usable CUDA device pmx_ctx_create
+ *     fails with PMX_ERR_CUDA
+ */
+#ifndef POLMUX_SSFM_H
+#define POLMUX_SSFM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMX_VERSION 100 /* 0.1.0 */
+
+typedef enum pmx_status {
+    PMX_OK = 0,
+    PMX_ERR_INVALID = -1,      /* bad argument (message says which)                    */
+    PMX_ERR_UNSUPPORTED = -2,  /* valid in the reference, not built here (message)     */
+    PMX_ERR_CUDA = -3,         /* CUDA runtime / driver error                          */
+    PMX_ERR_PLATE_INDEX = -4,  /* trunk counter ran past nplates: the reference fails  */
+                               /* with an index error at fiber.m:910    */
+    PMX_ERR_NUMERIC = -5,      /* NaN/Inf met in step control                          */
+    PMX_ERR_XPM_VECTOR = -6    /* fiber.m:854 'The CNLSE with separate fields is not   */
+                               /* yet implemented'                                     */
+} pmx_status;
+
+typedef enum pmx_precision { PMX_F64 = 0, PMX_F32 = 1 } pmx_precision;
+
+/* Host-side layouts of a field handed across the boundary. */
+typedef enum pmx_layout {
+    PMX_PLANAR = 0,  /* four real arrays xr, xi, yr, yi -- the split storage the    */
+                     /* reference's MEX files use (mxGetPr/mxGetPi, fastexp.c:61-63)*/
+    PMX_COMPLEX = 1  /* two interleaved complex arrays x, y (re,im,re,im,...)       */
+} pmx_layout;
+
+typedef struct pmx_ctx pmx_ctx;
+typedef struct pmx_plan pmx_plan;         /* one fiber() worth of device constants */
+typedef struct pmx_devfield pmx_devfield; /* a field resident in HBM               */
+
+/* ---- context -------------------------------------------------------------- */
+int pmx_version(void);
+int pmx_device_count(void);
+int pmx_ctx_create(pmx_ctx** ctx, int device_id);
+void pmx_ctx_destroy(pmx_ctx* ctx);
+/* ctx may be NULL: returns the calling thread's last error text. */
+const char* pmx_last_error(const pmx_ctx* ctx);
+/* Blocks until all work queued on the ctx stream is done. */
+int pmx_ctx_sync(pmx_ctx* ctx);
+/* Raw cudaStream_t of the ctx, so a caller can record its own events on it. */
+void* pmx_ctx_stream(pmx_ctx* ctx);
+
+/* ---- the fiber --------------------------------------------------------------
+ * pmx_fiber_desc is the argument list of
+ *   [firstdz,ncycle,ux,uy,brf] = matrix_ssfm(ux,uy,betat,db1,dzmaxt,dphimaxt,
+ *        gam,alphalin,nfc,Lf,nplates,manakov,fls,brf)          fiber.m:459-460
+ * (the seam inside fiber.m:381-383), plus a batch axis over independent
+ * realizations.  Everything above that seam in fiber.m:126-369 is host scalar
+ * set-up and stays on the caller's side.
+ */
+typedef struct pmx_fiber_desc {
+    int64_t nfft;        /* rows of FIELDX = NSYMB*NT (fiber.m:133); power of two, 2^8..2^24 */
+    int32_t nfc;         /* columns of FIELDX (fiber.m:132)                                  */
+    int32_t batch;       /* independent realizations propagated by one call (>=1)            */
+    int32_t precision;   /* pmx_precision                                                     */
+    int32_t manakov;     /* strcmp(manakov,'yes')   fiber.m:499                               */
+    double length;       /* Lf        fiber.m:459 */
+    double alphalin;     /* [1/m]     fiber.m:302 */
+    double dzmaxt;       /* fiber.m:157-251       */
+    double dphimaxt;     /* may be +Inf (linear flags -> exactly one step) */
+    const double* gam;   /* [nfc] 1/mW/m, BEFORE the Manakov 8/9 (applied inside, fiber.m:500) */
+    int32_t fls[4];      /* [g p s x]  fiber.m:157 */
+    int32_t nplates;     /* fiber.m:297 / 265 / 272 */
+    int32_t plate_sets;  /* 1: all realizations share the plates; batch: one draw each */
+    const double* db0;     /* [plate_sets][nplates]  brf.db0      fiber.m:266,274 */
+    const double* theta;   /* [plate_sets][nplates]  brf.theta    fiber.m:267,275 */
+    const double* epsilon; /* [plate_sets][nplates]  brf.epsilon  fiber.m:268,276 */
+    const double* betat;   /* [nfc][nfft] host, fiber.m:350-356 (FFT order)        */
+    const double* db1;     /* [nfc][nfft] host, fiber.m:358; NULL means zeros      */
+} pmx_fiber_desc;
+
+typedef struct pmx_field {
+    int32_t layout;   /* pmx_layout */
+    int32_t reserved;
+    /* PMX_PLANAR : xr,xi,yr,yi each [batch][nfc][nfft] doubles; xi / yi may be
+     *              NULL on input (purely real array, as mxGetPi returns NULL);
+     *              yr may be NULL on input (FIELDY empty -> zeros, fiber.m:286).
+     * PMX_COMPLEX: xr -> complex X array, yr -> complex Y array; xi, yi unused. */
+    double* xr;
+    double* xi;
+    double* yr;
+    double* yi;
+} pmx_field;
+
+/* Per-realization outputs of matrix_ssfm that the caller prints or checks. */
+typedef struct pmx_fiber_result {
+    double* firstdz;   /* [batch]  fiber.m:516 */
+    int32_t* ncycle;   /* [batch]  fiber.m:506,536 */
+    int32_t* ntot;     /* [batch]  trunk counter after the run (== nplates when 'p') */
+    int32_t* status;   /* [batch]  0 or a pmx_status (e.g. PMX_ERR_PLATE_INDEX)      */
+    /* optional trace of the step schedule, for tests (may be NULL):
+     * trace_dz[b*trace_cap + i] = length of step i, trace_ntrunk likewise.    */
+    double* trace_dz;
+    int32_t* trace_ntrunk;
+    int32_t trace_cap;
+} pmx_fiber_result;
+
+/* One call == one fiber(x,flag) on host buffers, in place: H2D, the whole SSFM
+ * loop on the device, D2H.  Replaces the dispatch at fiber.m:381-383. */
+int pmx_fiber_run(pmx_ctx* ctx, const pmx_fiber_desc* desc, pmx_field* io, pmx_fiber_result* out);
+
+/* ---- HBM-resident API (span loops, Monte-Carlo batches, benchmarks) --------- */
+int pmx_field_create(pmx_ctx* ctx, int64_t nfft, int32_t nfc, int32_t batch, int32_t precision,
+                     pmx_devfield** f);
+void pmx_field_destroy(pmx_devfield* f);
+/* b0..b0+nb-1: realizations to transfer; host arrays hold nb realizations. */
+int pmx_field_upload(pmx_devfield* f, const pmx_field* host, int32_t b0, int32_t nb);
+int pmx_field_download(pmx_devfield* f, pmx_field* host, int32_t b0, int32_t nb);
+/* dst[b] = src[0] for all b (same Tx field for every realization). */
+int pmx_field_broadcast(pmx_devfield* dst, const pmx_devfield* src);
+/* raw device pointer of the interleaved (xr,xi,yr,yi) sample array */
+void* pmx_field_device_ptr(pmx_devfield* f);
+
+/* Uploads betat/db1/plates, builds twiddle tables (cached in ctx by nfft). */
+int pmx_plan_create(pmx_ctx* ctx, const pmx_fiber_desc* desc, pmx_plan** plan);
+void pmx_plan_destroy(pmx_plan* plan);
+/* Replace the plate angles of an existing plan (new Monte-Carlo draw). */
+int pmx_plan_set_plates(pmx_plan* plan, int32_t plate_sets, const double* db0, const double* theta,
+                        const double* epsilon);
+/* The SSFM loop on a resident field (asynchronous wrt. the host except for the
+ * step-control polling; returns after the fiber is complete). */
+int pmx_fiber_exec(pmx_plan* plan, pmx_devfield* f, pmx_fiber_result* out);
+/* Total kernel launches issued by this ctx so far (bench `gpu_launches`). */
+int64_t pmx_ctx_launch_count(const pmx_ctx* ctx);
+
+/* ---- span boundary: flat-gain amplifier with ASE --------------------------------
+ * ampliflat(x,'gain',options)  ampliflat.m:61-148.
+ *   field <- field*sqrt(gain) + sigma[c]*noise
+ * gain   : linear power gain 10^(x/10)                       ampliflat.m:62
+ * sigma  : [nfc] sqrt(mW) per column, 0 disables ASE           ampliflat.m:91-106
+ * noise  : NULL -> complex standard normals from the counter-based generator
+ *          (Philox4x32-10 + Box-Muller) keyed by (seed, realization), else a
+ *          HOST array [batch][2*nfc][nfft] complex (options.noise, :123-129,
+ *          X columns first then Y columns).
+ */
+int pmx_ampliflat_exec(pmx_ctx* ctx, pmx_devfield* f, double gain, const double* sigma,
+                       const double* noise_host, uint64_t seed);
+
+/* ---- integer error counting (ber_estimate.m:118) --------------------------------
+ * counts[b] = #{ i : pat_hat[b][i] != pat[i] } over n symbols-bits, on the device. */
+int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pat_dev, int64_t n,
+                     int32_t batch, int64_t* counts_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLMUX_SSFM_H */

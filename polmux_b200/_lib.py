@@ -1,0 +1,318 @@
+"""ctypes binding of the C ABI in include/polmux_ssfm.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
+polmux_b200/csrc``).  There is no fallback: if the library is missing or no
+B200 is visible, every compute entry point raises ``PolmuxError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libpolmux_ssfm.so')
+
+PMX_OK = 0
+PMX_ERR_INVALID, PMX_ERR_UNSUPPORTED, PMX_ERR_CUDA = -1, -2, -3
+PMX_ERR_PLATE_INDEX, PMX_ERR_NUMERIC, PMX_ERR_XPM_VECTOR = -4, -5, -6
+PMX_F64, PMX_F32 = 0, 1
+PMX_PLANAR, PMX_COMPLEX = 0, 1
+
+# every symbol include/polmux_ssfm.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    'pmx_version', 'pmx_device_count', 'pmx_ctx_create', 'pmx_ctx_destroy', 'pmx_last_error',
+    'pmx_ctx_sync', 'pmx_ctx_stream', 'pmx_fiber_run', 'pmx_field_create', 'pmx_field_destroy',
+    'pmx_field_upload', 'pmx_field_download', 'pmx_field_broadcast', 'pmx_field_device_ptr',
+    'pmx_plan_create', 'pmx_plan_destroy', 'pmx_plan_set_plates', 'pmx_fiber_exec',
+    'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors',
+]
+
+
+class PolmuxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('polmux_ssfm error %d: %s' % (code, msg))
+        self.code = code
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class FiberDesc(C.Structure):
+    _fields_ = [
+        ('nfft', C.c_int64), ('nfc', C.c_int32), ('batch', C.c_int32), ('precision', C.c_int32),
+        ('manakov', C.c_int32), ('length', C.c_double), ('alphalin', C.c_double),
+        ('dzmaxt', C.c_double), ('dphimaxt', C.c_double), ('gam', _dp), ('fls', C.c_int32 * 4),
+        ('nplates', C.c_int32), ('plate_sets', C.c_int32), ('db0', _dp), ('theta', _dp),
+        ('epsilon', _dp), ('betat', _dp), ('db1', _dp),
+    ]
+
+
+class Field(C.Structure):
+    _fields_ = [('layout', C.c_int32), ('reserved', C.c_int32), ('xr', _dp), ('xi', _dp),
+                ('yr', _dp), ('yi', _dp)]
+
+
+class FiberResult(C.Structure):
+    _fields_ = [('firstdz', _dp), ('ncycle', _ip), ('ntot', _ip), ('status', _ip),
+                ('trace_dz', _dp), ('trace_ntrunk', _ip), ('trace_cap', C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises PolmuxError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PolmuxError(PMX_ERR_CUDA, 'CUDA library %s is not built; run __graft_entry__.build() '
+                          '(there is no CPU fallback)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.pmx_version.restype = C.c_int
+    lib.pmx_device_count.restype = C.c_int
+    lib.pmx_ctx_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.pmx_ctx_destroy.argtypes = [vp]
+    lib.pmx_ctx_destroy.restype = None
+    lib.pmx_last_error.argtypes = [vp]
+    lib.pmx_last_error.restype = C.c_char_p
+    lib.pmx_ctx_sync.argtypes = [vp]
+    lib.pmx_ctx_stream.argtypes = [vp]
+    lib.pmx_ctx_stream.restype = vp
+    lib.pmx_ctx_launch_count.argtypes = [vp]
+    lib.pmx_ctx_launch_count.restype = C.c_int64
+    lib.pmx_fiber_run.argtypes = [vp, C.POINTER(FiberDesc), C.POINTER(Field), C.POINTER(FiberResult)]
+    lib.pmx_field_create.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.pmx_field_destroy.argtypes = [vp]
+    lib.pmx_field_destroy.restype = None
+    lib.pmx_field_upload.argtypes = [vp, C.POINTER(Field), C.c_int32, C.c_int32]
+    lib.pmx_field_download.argtypes = [vp, C.POINTER(Field), C.c_int32, C.c_int32]
+    lib.pmx_field_broadcast.argtypes = [vp, vp]
+    lib.pmx_field_device_ptr.argtypes = [vp]
+    lib.pmx_field_device_ptr.restype = vp
+    lib.pmx_plan_create.argtypes = [vp, C.POINTER(FiberDesc), C.POINTER(vp)]
+    lib.pmx_plan_destroy.argtypes = [vp]
+    lib.pmx_plan_destroy.restype = None
+    lib.pmx_plan_set_plates.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
+    lib.pmx_fiber_exec.argtypes = [vp, vp, C.POINTER(FiberResult)]
+    lib.pmx_ampliflat_exec.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64]
+    lib.pmx_count_errors.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+class Context:
+    """One pmx_ctx (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.pmx_ctx_create(C.byref(h), int(device))
+        if rc != PMX_OK:
+            raise PolmuxError(rc, self.lib.pmx_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != PMX_OK:
+            raise PolmuxError(rc, self.lib.pmx_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(self.lib.pmx_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.pmx_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.pmx_ctx_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.pmx_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def make_desc(nfft, nfc, batch, length, alphalin, dzmaxt, dphimaxt, gam, fls, manakov, nplates,
+              db0, theta, epsilon, betat, db1, plate_sets=1, precision=PMX_F64):
+    """Build a FiberDesc plus the list of arrays that must stay alive while it is used."""
+    keep = {}
+    keep['gam'] = _f64(np.atleast_1d(gam))
+    keep['db0'] = _f64(db0).reshape(-1)
+    keep['theta'] = _f64(theta).reshape(-1)
+    keep['epsilon'] = _f64(epsilon).reshape(-1)
+    # betat / db1 arrive as [nfft, nfc] (column-major columns) -> [nfc][nfft]
+    keep['betat'] = _f64(np.asarray(betat).reshape(nfft, nfc).T)
+    keep['db1'] = _f64(np.asarray(db1).reshape(nfft, nfc).T) if db1 is not None else None
+    d = FiberDesc()
+    d.nfft, d.nfc, d.batch, d.precision = int(nfft), int(nfc), int(batch), int(precision)
+    d.manakov = 1 if manakov else 0
+    d.length, d.alphalin, d.dzmaxt, d.dphimaxt = float(length), float(alphalin), float(dzmaxt), float(dphimaxt)
+    d.gam = _ptr(keep['gam'])
+    d.fls = (C.c_int32 * 4)(*[int(v) for v in fls])
+    d.nplates, d.plate_sets = int(nplates), int(plate_sets)
+    d.db0, d.theta, d.epsilon = _ptr(keep['db0']), _ptr(keep['theta']), _ptr(keep['epsilon'])
+    d.betat, d.db1 = _ptr(keep['betat']), _ptr(keep['db1'])
+    return d, keep
+
+
+class Result:
+    def __init__(self, batch, trace_cap=0):
+        self.firstdz = np.zeros(batch)
+        self.ncycle = np.zeros(batch, dtype=np.int32)
+        self.ntot = np.zeros(batch, dtype=np.int32)
+        self.status = np.zeros(batch, dtype=np.int32)
+        self.trace_cap = trace_cap
+        self.trace_dz = np.zeros((batch, trace_cap)) if trace_cap else None
+        self.trace_ntrunk = np.zeros((batch, trace_cap), dtype=np.int32) if trace_cap else None
+        r = FiberResult()
+        r.firstdz = _ptr(self.firstdz)
+        r.ncycle = self.ncycle.ctypes.data_as(_ip)
+        r.ntot = self.ntot.ctypes.data_as(_ip)
+        r.status = self.status.ctypes.data_as(_ip)
+        if trace_cap:
+            r.trace_dz = _ptr(self.trace_dz)
+            r.trace_ntrunk = self.trace_ntrunk.ctypes.data_as(_ip)
+        r.trace_cap = trace_cap
+        self.c = r
+
+    def schedule(self, b=0):
+        n = int(self.ncycle[b])
+        return self.trace_dz[b, :n].copy(), self.trace_ntrunk[b, :n].copy()
+
+
+def complex_field(x: np.ndarray, y):
+    """Field struct over two complex128 arrays (PMX_COMPLEX); arrays must be C-contiguous
+    [batch][nfc][nfft] and stay alive."""
+    f = Field()
+    f.layout = PMX_COMPLEX
+    f.xr = x.ctypes.data_as(_dp)
+    f.yr = y.ctypes.data_as(_dp) if y is not None else None
+    return f
+
+
+def planar_field(xr, xi, yr, yi):
+    f = Field()
+    f.layout = PMX_PLANAR
+    f.xr, f.xi, f.yr, f.yi = _ptr(xr), _ptr(xi), _ptr(yr), _ptr(yi)
+    return f
+
+
+class DeviceField:
+    """A field resident in HBM: [batch][nfc][nfft] two-polarization samples."""
+
+    def __init__(self, ctx: Context, nfft, nfc=1, batch=1, precision=PMX_F64):
+        self.ctx, self.nfft, self.nfc, self.batch = ctx, int(nfft), int(nfc), int(batch)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.pmx_field_create(ctx.h, self.nfft, self.nfc, self.batch, precision, C.byref(h)))
+        self.h = h
+
+    def _as_cols(self, a, nb):
+        # accept [nfft, nfc] (GSTATE layout) for nb == 1, or [nb, nfc, nfft]
+        a = np.asarray(a, dtype=np.complex128)
+        if a.ndim == 2 and nb == 1 and a.shape == (self.nfft, self.nfc):
+            a = a.T[None]
+        return np.ascontiguousarray(a.reshape(nb, self.nfc, self.nfft))
+
+    def upload(self, x, y=None, b0=0, nb=None):
+        nb = self.batch if nb is None else nb
+        xs = self._as_cols(x, nb)
+        ys = self._as_cols(y, nb) if y is not None else None
+        f = complex_field(xs, ys)
+        self.ctx.check(self.ctx.lib.pmx_field_upload(self.h, C.byref(f), b0, nb))
+        self.ctx.sync()  # host arrays may be temporaries
+
+    def download(self, b0=0, nb=None):
+        """-> (x, y) complex128 arrays [nb, nfc, nfft]."""
+        nb = self.batch if nb is None else nb
+        x = np.empty((nb, self.nfc, self.nfft), dtype=np.complex128)
+        y = np.empty_like(x)
+        f = complex_field(x, y)
+        self.ctx.check(self.ctx.lib.pmx_field_download(self.h, C.byref(f), b0, nb))
+        return x, y
+
+    def broadcast_from(self, src: 'DeviceField'):
+        self.ctx.check(self.ctx.lib.pmx_field_broadcast(self.h, src.h))
+
+    @property
+    def device_ptr(self):
+        return self.ctx.lib.pmx_field_device_ptr(self.h)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.ctx.lib.pmx_field_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Plan:
+    def __init__(self, ctx: Context, desc: FiberDesc, keep):
+        self.ctx, self.desc, self.keep = ctx, desc, keep
+        h = C.c_void_p()
+        ctx.check(ctx.lib.pmx_plan_create(ctx.h, C.byref(desc), C.byref(h)))
+        self.h = h
+
+    def set_plates(self, db0, theta, epsilon, plate_sets=1):
+        a, b, c = _f64(db0).reshape(-1), _f64(theta).reshape(-1), _f64(epsilon).reshape(-1)
+        self.ctx.check(self.ctx.lib.pmx_plan_set_plates(self.h, plate_sets, _ptr(a), _ptr(b), _ptr(c)))
+
+    def execute(self, field: DeviceField, trace_cap=0) -> Result:
+        res = Result(field.batch, trace_cap)
+        self.ctx.check(self.ctx.lib.pmx_fiber_exec(self.h, field.h, C.byref(res.c)))
+        return res
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.ctx.lib.pmx_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ampliflat_exec(ctx: Context, field: DeviceField, gain: float, sigma, noise=None, seed=0):
+    s = _f64(np.atleast_1d(sigma))
+    n = None
+    if noise is not None:
+        n = np.ascontiguousarray(noise, dtype=np.complex128)
+    ctx.check(ctx.lib.pmx_ampliflat_exec(ctx.h, field.h, float(gain), _ptr(s),
+                                         n.ctypes.data_as(_dp) if n is not None else None,
+                                         C.c_uint64(int(seed))))
+    if n is not None:
+        ctx.sync()

@@ -1,0 +1,846 @@
+// Host side of the C ABI (include/polmux_ssfm.h): context, tables, plans, the
+// SSFM launch loop, layout conversion, amplifier and error counting kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/polmux_ssfm.h"
+#include "pmx_kernels.cuh"
+#include "pmx_launch.h"
+
+// ---------------------------------------------------------------------------
+extern const PmxLaunchTable pmx_table_64, pmx_table_128, pmx_table_256, pmx_table_512, pmx_table_1024,
+    pmx_table_2048, pmx_table_4096;
+
+const PmxLaunchTable* pmx_get_table(int L) {
+    switch (L) {
+        case 64: return &pmx_table_64;
+        case 128: return &pmx_table_128;
+        case 256: return &pmx_table_256;
+        case 512: return &pmx_table_512;
+        case 1024: return &pmx_table_1024;
+        case 2048: return &pmx_table_2048;
+        case 4096: return &pmx_table_4096;
+        default: return nullptr;
+    }
+}
+
+static inline cpx pmx_root(long long m, long long M) {  // exp(-2*pi*i*m/M) in long double
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    // reduce to the first octant for accuracy
+    m %= M;
+    long double a = PI2 * (long double)m / (long double)M;
+    return make_double2((double)cosl(a), (double)(-sinl(a)));
+}
+
+void pmx_fill_stage_twiddles(int L, cpx* out) {
+    int ns = 1;
+    size_t o = 0;
+    while (ns < L) {
+        int R = pmx_stage_radix(L, ns);
+        if (ns > 1) {
+            for (int r = 1; r < R; ++r)
+                for (int k = 0; k < ns; ++k) out[o++] = pmx_root((long long)k * r, (long long)ns * R);
+        }
+        ns *= R;
+    }
+}
+
+// ---------------------------------------------------------------------------
+static thread_local std::string g_tls_error;
+
+struct StageTw {
+    cpx* dev = nullptr;
+};
+struct FourStepTw {
+    cpx* hi = nullptr;
+    cpx* lo = nullptr;
+    int lo_bits = 0;
+};
+
+struct pmx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    std::map<int, StageTw> stage_tw;          // by L
+    std::map<long long, FourStepTw> four_tw;  // by N
+    std::map<int, bool> setup_done;
+    StepCtl* h_ctl = nullptr;  // pinned readback buffer
+    int h_ctl_cap = 0;
+    int64_t launches = 0;
+};
+
+struct pmx_devfield {
+    pmx_ctx* ctx;
+    int64_t nfft;
+    int32_t nfc, batch, precision;
+    cpx* data;  // [batch*nfc][nfft][2]
+};
+
+struct pmx_plan {
+    pmx_ctx* ctx;
+    pmx_fiber_desc d;  // scalar copy (pointers not kept)
+    FiberConst fc;
+    int N1, N2, log2N1, log2N2;
+    const PmxLaunchTable* tA;  // passes A/C (L = N1)
+    const PmxLaunchTable* tB;  // pass B   (L = N2)
+    double* betat_p = nullptr;
+    double* db1_p = nullptr;
+    PlateConst* plates = nullptr;
+    StepCtl* ctl = nullptr;
+    double* trace_dz = nullptr;
+    int* trace_ntrunk = nullptr;
+    int trace_cap = 0;
+    bool single_step;
+};
+
+static int set_err(pmx_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_tls_error = buf;
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return set_err(ctx, PMX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                                 \
+    } while (0)
+
+extern "C" int pmx_version(void) { return PMX_VERSION; }
+
+extern "C" int pmx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" const char* pmx_last_error(const pmx_ctx* ctx) {
+    if (ctx) return ctx->error.c_str();
+    return g_tls_error.c_str();
+}
+
+extern "C" int pmx_ctx_create(pmx_ctx** out, int device_id) {
+    if (!out) return set_err(nullptr, PMX_ERR_INVALID, "pmx_ctx_create: null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(nullptr, PMX_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n)
+        return set_err(nullptr, PMX_ERR_INVALID, "device_id %d out of range [0,%d)", device_id, n);
+    pmx_ctx* c = new (std::nothrow) pmx_ctx();
+    if (!c) return set_err(nullptr, PMX_ERR_INVALID, "out of host memory");
+    c->device = device_id;
+    CK(nullptr, cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10) {
+        delete c;
+        return set_err(nullptr, PMX_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                       device_id, prop.major, prop.minor);
+    }
+    CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return PMX_OK;
+}
+
+extern "C" void pmx_ctx_destroy(pmx_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->stage_tw) cudaFree(kv.second.dev);
+    for (auto& kv : c->four_tw) {
+        cudaFree(kv.second.hi);
+        cudaFree(kv.second.lo);
+    }
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int pmx_ctx_sync(pmx_ctx* c) {
+    if (!c) return set_err(nullptr, PMX_ERR_INVALID, "null ctx");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
+extern "C" void* pmx_ctx_stream(pmx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int64_t pmx_ctx_launch_count(const pmx_ctx* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------
+static int get_stage_tw(pmx_ctx* c, int L, const cpx** dev) {
+    auto it = c->stage_tw.find(L);
+    if (it == c->stage_tw.end()) {
+        int total = pmx_tw_total(L);
+        std::vector<cpx> h((size_t)(total > 0 ? total : 1));
+        pmx_fill_stage_twiddles(L, h.data());
+        StageTw s;
+        CK(c, cudaMalloc(&s.dev, h.size() * sizeof(cpx)));
+        CK(c, cudaMemcpyAsync(s.dev, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        it = c->stage_tw.emplace(L, s).first;
+    }
+    *dev = it->second.dev;
+    return PMX_OK;
+}
+
+static int get_four_tw(pmx_ctx* c, long long N, int log2N, FourStepTw* out) {
+    auto it = c->four_tw.find(N);
+    if (it == c->four_tw.end()) {
+        FourStepTw t;
+        t.lo_bits = (log2N + 1) / 2;
+        long long nlo = 1ll << t.lo_bits, nhi = N >> t.lo_bits;
+        std::vector<cpx> lo((size_t)nlo), hi((size_t)nhi);
+        for (long long j = 0; j < nlo; ++j) lo[(size_t)j] = pmx_root(j, N);
+        for (long long j = 0; j < nhi; ++j) hi[(size_t)j] = pmx_root(j << t.lo_bits, N);
+        CK(c, cudaMalloc(&t.lo, lo.size() * sizeof(cpx)));
+        CK(c, cudaMalloc(&t.hi, hi.size() * sizeof(cpx)));
+        CK(c, cudaMemcpyAsync(t.lo, lo.data(), lo.size() * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(t.hi, hi.data(), hi.size() * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        it = c->four_tw.emplace(N, t).first;
+    }
+    *out = it->second;
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fields
+extern "C" int pmx_field_create(pmx_ctx* c, int64_t nfft, int32_t nfc, int32_t batch, int32_t precision,
+                                pmx_devfield** out) {
+    if (!c || !out) return set_err(c, PMX_ERR_INVALID, "pmx_field_create: null argument");
+    *out = nullptr;
+    if (precision != PMX_F64)
+        return set_err(c, PMX_ERR_UNSUPPORTED, "precision %d: only PMX_F64 is built in this version", precision);
+    if (nfft <= 0 || nfc <= 0 || batch <= 0) return set_err(c, PMX_ERR_INVALID, "non-positive field size");
+    CK(c, cudaSetDevice(c->device));
+    pmx_devfield* f = new (std::nothrow) pmx_devfield();
+    if (!f) return set_err(c, PMX_ERR_INVALID, "out of host memory");
+    f->ctx = c;
+    f->nfft = nfft;
+    f->nfc = nfc;
+    f->batch = batch;
+    f->precision = precision;
+    size_t bytes = (size_t)batch * nfc * nfft * 2 * sizeof(cpx);
+    cudaError_t e = cudaMalloc(&f->data, bytes);
+    if (e != cudaSuccess) {
+        delete f;
+        return set_err(c, PMX_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    *out = f;
+    return PMX_OK;
+}
+
+extern "C" void pmx_field_destroy(pmx_devfield* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->data);
+    delete f;
+}
+
+extern "C" void* pmx_field_device_ptr(pmx_devfield* f) { return f ? (void*)f->data : nullptr; }
+
+// planar / complex host layouts <-> interleaved (xr,xi,yr,yi)
+__global__ void pmx_k_pack_planar(cpx* dst, const double* xr, const double* xi, const double* yr,
+                                  const double* yi, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        dst[2 * i] = make_double2(xr[i], xi ? xi[i] : 0.0);
+        dst[2 * i + 1] = make_double2(yr ? yr[i] : 0.0, yi ? yi[i] : 0.0);
+    }
+}
+__global__ void pmx_k_unpack_planar(const cpx* src, double* xr, double* xi, double* yr, double* yi, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        cpx x = src[2 * i], y = src[2 * i + 1];
+        xr[i] = x.x;
+        xi[i] = x.y;
+        yr[i] = y.x;
+        yi[i] = y.y;
+    }
+}
+__global__ void pmx_k_pack_complex(cpx* dst, const cpx* x, const cpx* y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        dst[2 * i] = x[i];
+        dst[2 * i + 1] = y ? y[i] : make_double2(0.0, 0.0);
+    }
+}
+__global__ void pmx_k_unpack_complex(const cpx* src, cpx* x, cpx* y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        x[i] = src[2 * i];
+        y[i] = src[2 * i + 1];
+    }
+}
+
+static int check_range(pmx_devfield* f, int32_t b0, int32_t nb) {
+    if (!f) return set_err(nullptr, PMX_ERR_INVALID, "null field");
+    if (b0 < 0 || nb <= 0 || b0 + nb > f->batch)
+        return set_err(f->ctx, PMX_ERR_INVALID, "realization range [%d,%d) outside batch %d", b0, b0 + nb, f->batch);
+    return PMX_OK;
+}
+
+extern "C" int pmx_field_upload(pmx_devfield* f, const pmx_field* h, int32_t b0, int32_t nb) {
+    int rc = check_range(f, b0, nb);
+    if (rc) return rc;
+    pmx_ctx* c = f->ctx;
+    if (!h || !h->xr) return set_err(c, PMX_ERR_INVALID, "pmx_field_upload: null host field / xr");
+    CK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)nb * f->nfc * f->nfft;
+    cpx* dst = f->data + (size_t)b0 * f->nfc * f->nfft * 2;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    if (h->layout == PMX_PLANAR) {
+        double* stage = nullptr;
+        CK(c, cudaMallocAsync(&stage, 4 * n * sizeof(double), c->stream));
+        double* parts[4] = {h->xr, h->xi, h->yr, h->yi};
+        double* dparts[4];
+        for (int k = 0; k < 4; ++k) {
+            dparts[k] = parts[k] ? stage + (size_t)k * n : nullptr;
+            if (parts[k])
+                CK(c, cudaMemcpyAsync(dparts[k], parts[k], n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
+        pmx_k_pack_planar<<<blocks, 256, 0, c->stream>>>(dst, dparts[0], dparts[1], dparts[2], dparts[3], n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        CK(c, cudaFreeAsync(stage, c->stream));
+    } else if (h->layout == PMX_COMPLEX) {
+        cpx* stage = nullptr;
+        CK(c, cudaMallocAsync(&stage, 2 * n * sizeof(cpx), c->stream));
+        CK(c, cudaMemcpyAsync(stage, h->xr, n * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
+        cpx* dy = nullptr;
+        if (h->yr) {
+            dy = stage + n;
+            CK(c, cudaMemcpyAsync(dy, h->yr, n * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
+        }
+        pmx_k_pack_complex<<<blocks, 256, 0, c->stream>>>(dst, stage, dy, n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        CK(c, cudaFreeAsync(stage, c->stream));
+    } else {
+        return set_err(c, PMX_ERR_INVALID, "unknown layout %d", h->layout);
+    }
+    return PMX_OK;
+}
+
+extern "C" int pmx_field_download(pmx_devfield* f, pmx_field* h, int32_t b0, int32_t nb) {
+    int rc = check_range(f, b0, nb);
+    if (rc) return rc;
+    pmx_ctx* c = f->ctx;
+    if (!h || !h->xr || !h->yr) return set_err(c, PMX_ERR_INVALID, "pmx_field_download: null host arrays");
+    CK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)nb * f->nfc * f->nfft;
+    const cpx* src = f->data + (size_t)b0 * f->nfc * f->nfft * 2;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    if (h->layout == PMX_PLANAR) {
+        if (!h->xi || !h->yi) return set_err(c, PMX_ERR_INVALID, "planar download needs xr, xi, yr, yi");
+        double* stage = nullptr;
+        CK(c, cudaMallocAsync(&stage, 4 * n * sizeof(double), c->stream));
+        pmx_k_unpack_planar<<<blocks, 256, 0, c->stream>>>(src, stage, stage + n, stage + 2 * n, stage + 3 * n, n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        double* parts[4] = {h->xr, h->xi, h->yr, h->yi};
+        for (int k = 0; k < 4; ++k)
+            CK(c, cudaMemcpyAsync(parts[k], stage + (size_t)k * n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaFreeAsync(stage, c->stream));
+    } else if (h->layout == PMX_COMPLEX) {
+        cpx* stage = nullptr;
+        CK(c, cudaMallocAsync(&stage, 2 * n * sizeof(cpx), c->stream));
+        pmx_k_unpack_complex<<<blocks, 256, 0, c->stream>>>(src, stage, stage + n, n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        CK(c, cudaMemcpyAsync(h->xr, stage, n * sizeof(cpx), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(h->yr, stage + n, n * sizeof(cpx), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaFreeAsync(stage, c->stream));
+    } else {
+        return set_err(c, PMX_ERR_INVALID, "unknown layout %d", h->layout);
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
+extern "C" int pmx_field_broadcast(pmx_devfield* dst, const pmx_devfield* src) {
+    if (!dst || !src) return set_err(nullptr, PMX_ERR_INVALID, "null field");
+    pmx_ctx* c = dst->ctx;
+    if (dst->nfft != src->nfft || dst->nfc != src->nfc)
+        return set_err(c, PMX_ERR_INVALID, "pmx_field_broadcast: shape mismatch");
+    CK(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)src->nfc * src->nfft * 2 * sizeof(cpx);
+    for (int b = 0; b < dst->batch; ++b)
+        CK(c, cudaMemcpyAsync((char*)dst->data + (size_t)b * bytes, src->data, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// plans
+static void fill_plates(const pmx_fiber_desc& d, int sets, const double* db0, const double* theta,
+                        const double* epsilon, std::vector<PlateConst>& out) {
+    const int np = d.nplates;
+    out.resize((size_t)sets * np);
+    for (int s = 0; s < sets; ++s) {
+        for (int n = 0; n < np; ++n) {
+            PlateConst& P = out[(size_t)s * np + n];
+            const double th = theta ? theta[(size_t)s * np + n] : 0.0;
+            const double ep = epsilon ? epsilon[(size_t)s * np + n] : 0.0;
+            const double c = cos(th), sn = sin(th), ce = cos(ep), se = sin(ep);
+            // matR = [c -s; s c] * [ce i*se; i*se ce]   (fiber.m:910-912)
+            P.r11r = c * ce;  P.r11i = -sn * se;
+            P.r12r = -sn * ce; P.r12i = c * se;
+            P.r21r = sn * ce; P.r21i = c * se;
+            P.r22r = c * ce;  P.r22i = sn * se;
+            P.db0 = db0 ? db0[(size_t)s * np + n] : 0.0;
+            P.h0r = cos(-0.5 * P.db0);
+            P.h0i = sin(-0.5 * P.db0);
+            P.pad = 0.0;
+        }
+        for (int n = 0; n < np; ++n) {
+            PlateConst& P = out[(size_t)s * np + n];
+            if (n + 1 < np) {
+                const PlateConst& Q = out[(size_t)s * np + n + 1];
+                // C = Q^H * P  (2x2 complex), computed in long double
+                auto cm = [](long double ar, long double ai, long double br, long double bi, long double& rr,
+                             long double& ri) {  // conj(a)*b accumulated
+                    rr += ar * br + ai * bi;
+                    ri += ar * bi - ai * br;
+                };
+                long double r, i;
+                r = i = 0; cm(Q.r11r, Q.r11i, P.r11r, P.r11i, r, i); cm(Q.r21r, Q.r21i, P.r21r, P.r21i, r, i);
+                P.c11r = (double)r; P.c11i = (double)i;
+                r = i = 0; cm(Q.r11r, Q.r11i, P.r12r, P.r12i, r, i); cm(Q.r21r, Q.r21i, P.r22r, P.r22i, r, i);
+                P.c12r = (double)r; P.c12i = (double)i;
+                r = i = 0; cm(Q.r12r, Q.r12i, P.r11r, P.r11i, r, i); cm(Q.r22r, Q.r22i, P.r21r, P.r21i, r, i);
+                P.c21r = (double)r; P.c21i = (double)i;
+                r = i = 0; cm(Q.r12r, Q.r12i, P.r12r, P.r12i, r, i); cm(Q.r22r, Q.r22i, P.r22r, P.r22i, r, i);
+                P.c22r = (double)r; P.c22i = (double)i;
+            } else {
+                P.c11r = 1; P.c11i = 0; P.c12r = 0; P.c12i = 0; P.c21r = 0; P.c21i = 0; P.c22r = 1; P.c22i = 0;
+            }
+        }
+    }
+}
+
+extern "C" int pmx_plan_set_plates(pmx_plan* p, int32_t sets, const double* db0, const double* theta,
+                                   const double* epsilon) {
+    if (!p) return set_err(nullptr, PMX_ERR_INVALID, "null plan");
+    pmx_ctx* c = p->ctx;
+    if (sets != 1 && sets != p->d.batch)
+        return set_err(c, PMX_ERR_INVALID, "plate_sets must be 1 or batch (%d), got %d", p->d.batch, sets);
+    CK(c, cudaSetDevice(c->device));
+    std::vector<PlateConst> h;
+    fill_plates(p->d, sets, db0, theta, epsilon, h);
+    if (p->plates == nullptr || sets != p->fc.plate_sets) {
+        if (p->plates) CK(c, cudaFree(p->plates));
+        CK(c, cudaMalloc(&p->plates, h.size() * sizeof(PlateConst)));
+    }
+    p->fc.plate_sets = sets;
+    CK(c, cudaMemcpyAsync(p->plates, h.data(), h.size() * sizeof(PlateConst), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
+extern "C" void pmx_plan_destroy(pmx_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->betat_p);
+    cudaFree(p->db1_p);
+    cudaFree(p->plates);
+    cudaFree(p->ctl);
+    cudaFree(p->trace_dz);
+    cudaFree(p->trace_ntrunk);
+    delete p;
+}
+
+static int ilog2_exact(int64_t v) {
+    int l = 0;
+    while ((1ll << l) < v) ++l;
+    return ((1ll << l) == v) ? l : -1;
+}
+
+extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** out) {
+    if (!c || !d || !out) return set_err(c, PMX_ERR_INVALID, "pmx_plan_create: null argument");
+    *out = nullptr;
+    if (d->precision != PMX_F64)
+        return set_err(c, PMX_ERR_UNSUPPORTED, "precision %d: only PMX_F64 is built in this version", d->precision);
+    const int lg = ilog2_exact(d->nfft);
+    if (lg < 12 || lg > 24)
+        return set_err(c, PMX_ERR_UNSUPPORTED, "nfft=%lld: this build handles powers of two from 2^12 to 2^24",
+                       (long long)d->nfft);
+    if (d->nfc < 1 || d->nfc > PMX_MAX_NFC)
+        return set_err(c, PMX_ERR_UNSUPPORTED, "nfc=%d outside [1,%d]", d->nfc, PMX_MAX_NFC);
+    if (d->batch < 1) return set_err(c, PMX_ERR_INVALID, "batch must be >= 1");
+    if (d->nplates < 1) return set_err(c, PMX_ERR_INVALID, "nplates must be >= 1");
+    if (!(d->length > 0)) return set_err(c, PMX_ERR_INVALID, "length must be > 0");
+    if (!d->gam || !d->betat) return set_err(c, PMX_ERR_INVALID, "gam and betat are required");
+    if (d->fls[3]) return set_err(c, PMX_ERR_XPM_VECTOR, "The CNLSE with separate fields is not yet implemented");
+    if (d->plate_sets != 1 && d->plate_sets != d->batch)
+        return set_err(c, PMX_ERR_INVALID, "plate_sets must be 1 or batch");
+    if (!(d->dzmaxt > 0)) return set_err(c, PMX_ERR_INVALID, "dzmaxt must be > 0");
+    CK(c, cudaSetDevice(c->device));
+
+    pmx_plan* p = new (std::nothrow) pmx_plan();
+    if (!p) return set_err(c, PMX_ERR_INVALID, "out of host memory");
+    p->ctx = c;
+    p->d = *d;
+    p->d.gam = p->d.db0 = p->d.theta = p->d.epsilon = p->d.betat = p->d.db1 = nullptr;
+    p->log2N1 = lg / 2;
+    p->log2N2 = lg - p->log2N1;
+    p->N1 = 1 << p->log2N1;
+    p->N2 = 1 << p->log2N2;
+    p->tA = pmx_get_table(p->N1);
+    p->tB = pmx_get_table(p->N2);
+    if (!p->tA || !p->tB) {
+        delete p;
+        return set_err(c, PMX_ERR_UNSUPPORTED, "no kernel built for FFT factors %d x %d", 1 << (lg / 2), 1 << (lg - lg / 2));
+    }
+    for (const PmxLaunchTable* t : {p->tA, p->tB}) {
+        if (!c->setup_done[t->L]) {
+            cudaError_t e = t->setup();
+            if (e != cudaSuccess) {
+                delete p;
+                return set_err(c, PMX_ERR_CUDA, "kernel attribute setup (L=%d) failed: %s", t->L, cudaGetErrorString(e));
+            }
+            c->setup_done[t->L] = true;
+        }
+    }
+    FiberConst& f = p->fc;
+    memset(&f, 0, sizeof f);
+    f.Lf = d->length;
+    f.alphalin = d->alphalin;
+    f.halfalpha = 0.5 * d->alphalin;  // fiber.m:514
+    f.dzmax = d->dzmaxt;
+    f.phimax = d->dphimaxt;
+    f.lcorr = d->length / d->nplates;  // fiber.m:507
+    f.invN = 1.0 / (double)d->nfft;
+    for (int k = 0; k < d->nfc; ++k) f.gam[k] = d->manakov ? d->gam[k] * 8 / 9 : d->gam[k];  // fiber.m:500
+    f.nplates = d->nplates;
+    f.nfc = d->nfc;
+    f.spm = d->fls[2] ? 1 : 0;
+    f.manakov = d->manakov ? 1 : 0;
+    f.plate_sets = d->plate_sets;
+    // Jones product needed unless every plate is the identity with zero birefringence
+    bool pmd = false;
+    const size_t npl = (size_t)d->plate_sets * d->nplates;
+    for (size_t i = 0; i < npl && !pmd; ++i)
+        if ((d->theta && d->theta[i] != 0.0) || (d->epsilon && d->epsilon[i] != 0.0) || (d->db0 && d->db0[i] != 0.0))
+            pmd = true;
+    const size_t N = (size_t)d->nfft;
+    if (d->db1)
+        for (size_t i = 0; i < N * d->nfc && !pmd; ++i)
+            if (d->db1[i] != 0.0) pmd = true;
+    f.pmd = pmd ? 1 : 0;
+    bool gvd = false;
+    for (size_t i = 0; i < N * d->nfc && !gvd; ++i)
+        if (d->betat[i] != 0.0) gvd = true;
+    f.gvd_any = gvd ? 1 : 0;
+    p->single_step = std::isinf(d->dphimaxt) && d->dzmaxt >= d->length;
+
+    // permuted dispersion vectors: bin k1 + N1*k2 -> position k1*N2 + k2
+    {
+        std::vector<double> tmp(N * d->nfc);
+        const int N1 = p->N1, N2 = p->N2;
+        auto permute = [&](const double* src) {
+            for (int col = 0; col < d->nfc; ++col) {
+                const double* s = src + (size_t)col * N;
+                double* t = tmp.data() + (size_t)col * N;
+                for (int k2 = 0; k2 < N2; ++k2)
+                    for (int k1 = 0; k1 < N1; ++k1) t[(size_t)k1 * N2 + k2] = s[(size_t)k1 + (size_t)N1 * k2];
+            }
+        };
+        cudaError_t e = cudaMalloc(&p->betat_p, tmp.size() * sizeof(double));
+        if (e == cudaSuccess) {
+            permute(d->betat);
+            e = cudaMemcpy(p->betat_p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice);
+        }
+        if (e == cudaSuccess && pmd) {
+            e = cudaMalloc(&p->db1_p, tmp.size() * sizeof(double));
+            if (e == cudaSuccess) {
+                if (d->db1) permute(d->db1); else std::fill(tmp.begin(), tmp.end(), 0.0);
+                e = cudaMemcpy(p->db1_p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice);
+            }
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&p->ctl, (size_t)d->batch * sizeof(StepCtl));
+        if (e != cudaSuccess) {
+            pmx_plan_destroy(p);
+            return set_err(c, PMX_ERR_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
+        }
+    }
+    int rc = pmx_plan_set_plates(p, d->plate_sets, d->db0, d->theta, d->epsilon);
+    if (rc) {
+        pmx_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int ensure_hctl(pmx_ctx* c, int batch) {
+    if (c->h_ctl_cap < batch) {
+        if (c->h_ctl) cudaFreeHost(c->h_ctl);
+        c->h_ctl = nullptr;
+        CK(c, cudaMallocHost(&c->h_ctl, (size_t)batch * sizeof(StepCtl)));
+        c->h_ctl_cap = batch;
+    }
+    return PMX_OK;
+}
+
+extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* out) {
+    if (!p || !fld) return set_err(nullptr, PMX_ERR_INVALID, "pmx_fiber_exec: null argument");
+    pmx_ctx* c = p->ctx;
+    if (fld->ctx != c) return set_err(c, PMX_ERR_INVALID, "field and plan belong to different contexts");
+    if (fld->nfft != p->d.nfft || fld->nfc != p->d.nfc || fld->batch != p->d.batch)
+        return set_err(c, PMX_ERR_INVALID, "field shape (%lld,%d,%d) does not match the plan (%lld,%d,%d)",
+                       (long long)fld->nfft, fld->nfc, fld->batch, (long long)p->d.nfft, p->d.nfc, p->d.batch);
+    CK(c, cudaSetDevice(c->device));
+    const int batch = p->d.batch, nfc = p->d.nfc;
+    int rc = ensure_hctl(c, batch);
+    if (rc) return rc;
+
+    // optional schedule trace
+    int want_cap = (out && out->trace_dz && out->trace_ntrunk && out->trace_cap > 0) ? out->trace_cap : 0;
+    if (want_cap != p->trace_cap) {
+        if (p->trace_dz) cudaFree(p->trace_dz);
+        if (p->trace_ntrunk) cudaFree(p->trace_ntrunk);
+        p->trace_dz = nullptr;
+        p->trace_ntrunk = nullptr;
+        p->trace_cap = 0;
+        if (want_cap) {
+            CK(c, cudaMalloc(&p->trace_dz, (size_t)batch * want_cap * sizeof(double)));
+            CK(c, cudaMalloc(&p->trace_ntrunk, (size_t)batch * want_cap * sizeof(int)));
+            p->trace_cap = want_cap;
+        }
+    }
+    if (p->trace_cap) {
+        CK(c, cudaMemsetAsync(p->trace_dz, 0, (size_t)batch * p->trace_cap * sizeof(double), c->stream));
+        CK(c, cudaMemsetAsync(p->trace_ntrunk, 0, (size_t)batch * p->trace_cap * sizeof(int), c->stream));
+    }
+    p->fc.trace_cap = p->trace_cap;
+
+    PassParams pa;
+    memset(&pa, 0, sizeof pa);
+    pa.field = fld->data;
+    pa.ctl = p->ctl;
+    pa.betat_p = p->betat_p;
+    pa.db1_p = p->db1_p;
+    pa.plates = p->plates;
+    pa.trace_dz = p->trace_dz;
+    pa.trace_ntrunk = p->trace_ntrunk;
+    pa.N1 = p->N1;
+    pa.N2 = p->N2;
+    pa.log2N1 = p->log2N1;
+    pa.log2N2 = p->log2N2;
+    pa.batch = batch;
+    FourStepTw ft;
+    rc = get_four_tw(c, p->d.nfft, p->log2N1 + p->log2N2, &ft);
+    if (rc) return rc;
+    pa.tw_hi = ft.hi;
+    pa.tw_lo = ft.lo;
+    pa.lo_bits = ft.lo_bits;
+    const cpx *twA, *twB;
+    rc = get_stage_tw(c, p->N1, &twA);
+    if (rc) return rc;
+    rc = get_stage_tw(c, p->N2, &twB);
+    if (rc) return rc;
+    PassParams pA = pa, pB = pa;
+    pA.tw_stage = twA;
+    pB.tw_stage = twB;
+
+    CK(c, cudaMemsetAsync(p->ctl, 0, (size_t)batch * sizeof(StepCtl), c->stream));
+    {
+        dim3 g(148 * 2, batch * nfc);
+        pmx_k_init<<<g, 256, 256, c->stream>>>(pa, p->fc);
+        c->launches++;
+        CK(c, cudaGetLastError());
+    }
+    const dim3 gA(p->N2 / p->tA->cpc, batch * nfc), gB(p->N1 / p->tB->rpc, batch * nfc);
+    int chunk = p->single_step ? 1 : 8;
+    long total_steps = 0;
+    for (;;) {
+        for (int s = 0; s < chunk; ++s) {
+            p->tA->passA(gA, c->stream, pA, p->fc);
+            p->tB->passB(gB, c->stream, pB, p->fc);
+            p->tA->passC(gA, c->stream, pA, p->fc);
+            c->launches += 3;
+        }
+        total_steps += chunk;
+        CK(c, cudaGetLastError());
+        CK(c, cudaMemcpyAsync(c->h_ctl, p->ctl, (size_t)batch * sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        bool all_done = true;
+        for (int b = 0; b < batch; ++b)
+            if (c->h_ctl[b].state < PMX_ST_DONE) all_done = false;
+        if (all_done) break;
+        if (total_steps > 10000000) return set_err(c, PMX_ERR_NUMERIC, "step loop did not terminate");
+        if (chunk < 32) chunk *= 2;
+    }
+    int worst = PMX_OK;
+    for (int b = 0; b < batch; ++b) {
+        const StepCtl& s = c->h_ctl[b];
+        int st = (s.state == PMX_ST_ERROR) ? s.err : PMX_OK;
+        if (st != PMX_OK && worst == PMX_OK) worst = st;
+        if (out) {
+            if (out->firstdz) out->firstdz[b] = s.firstdz;
+            if (out->ncycle) out->ncycle[b] = s.ncycle;
+            if (out->ntot) out->ntot[b] = s.ntot + s.ntrunk - s.nmem;
+            if (out->status) out->status[b] = st;
+        }
+    }
+    if (p->trace_cap && out) {
+        CK(c, cudaMemcpy(out->trace_dz, p->trace_dz, (size_t)batch * p->trace_cap * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(c, cudaMemcpy(out->trace_ntrunk, p->trace_ntrunk, (size_t)batch * p->trace_cap * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (worst == PMX_ERR_PLATE_INDEX)
+        return set_err(c, worst, "trunk counter exceeded nplates=%d (the reference raises an index error at fiber.m:910 "
+                                 "for this length/nplates pair)", p->d.nplates);
+    if (worst != PMX_OK) return set_err(c, worst, "NaN/Inf met in the step control");
+    return PMX_OK;
+}
+
+extern "C" int pmx_fiber_run(pmx_ctx* c, const pmx_fiber_desc* d, pmx_field* io, pmx_fiber_result* out) {
+    if (!c || !d || !io) return set_err(c, PMX_ERR_INVALID, "pmx_fiber_run: null argument");
+    pmx_plan* plan = nullptr;
+    pmx_devfield* f = nullptr;
+    int rc = pmx_plan_create(c, d, &plan);
+    if (rc == PMX_OK) rc = pmx_field_create(c, d->nfft, d->nfc, d->batch, d->precision, &f);
+    if (rc == PMX_OK) rc = pmx_field_upload(f, io, 0, d->batch);
+    if (rc == PMX_OK) rc = pmx_fiber_exec(plan, f, out);
+    if (rc == PMX_OK) rc = pmx_field_download(f, io, 0, d->batch);
+    std::string keep = c->error;
+    pmx_field_destroy(f);
+    pmx_plan_destroy(plan);
+    if (rc != PMX_OK) {
+        c->error = keep;
+        g_tls_error = keep;
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// ampliflat: flat gain + ASE (ampliflat.m:78-148)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// complex standard normal (randn + i*randn): Box-Muller on two 32-bit uniforms
+__device__ __forceinline__ cpx pmx_cnormal(uint32_t a, uint32_t b) {
+    const double u1 = ((double)a + 0.5) * (1.0 / 4294967296.0);
+    const double u2 = ((double)b + 0.5) * (1.0 / 4294967296.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double s, cs;
+    sincospi(2.0 * u2, &s, &cs);
+    return make_double2(r * cs, r * s);
+}
+
+struct AmpParams {
+    cpx* field;
+    const cpx* noise;  // [batch][2*nfc][N] or null
+    double sg;         // sqrt(gain)
+    double sigma[PMX_MAX_NFC];
+    unsigned long long seed;
+    size_t N;
+    int nfc, batch;
+};
+
+__global__ void __launch_bounds__(256) pmx_k_ampliflat(AmpParams a) {
+    const int bc = blockIdx.y, b = bc / a.nfc, col = bc % a.nfc;
+    cpx* fld = a.field + (size_t)bc * a.N * 2;
+    const double sig = a.sigma[col];
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += (size_t)gridDim.x * blockDim.x) {
+        cpx x = cscale(fld[2 * n], a.sg), y = cscale(fld[2 * n + 1], a.sg);
+        if (sig != 0.0) {
+            cpx nx, ny;
+            if (a.noise) {
+                nx = a.noise[((size_t)b * 2 * a.nfc + col) * a.N + n];
+                ny = a.noise[((size_t)b * 2 * a.nfc + a.nfc + col) * a.N + n];
+            } else {
+                uint32_t r[4];
+                philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)col, (uint32_t)b, (uint32_t)a.seed,
+                              (uint32_t)(a.seed >> 32), r);
+                nx = pmx_cnormal(r[0], r[1]);
+                ny = pmx_cnormal(r[2], r[3]);
+            }
+            x.x += sig * nx.x; x.y += sig * nx.y;
+            y.x += sig * ny.x; y.y += sig * ny.y;
+        }
+        fld[2 * n] = x;
+        fld[2 * n + 1] = y;
+    }
+}
+
+extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, const double* sigma,
+                                  const double* noise_host, uint64_t seed) {
+    if (!c || !f) return set_err(c, PMX_ERR_INVALID, "pmx_ampliflat_exec: null argument");
+    if (!(gain > 0)) return set_err(c, PMX_ERR_INVALID, "gain must be > 0");
+    CK(c, cudaSetDevice(c->device));
+    AmpParams a;
+    memset(&a, 0, sizeof a);
+    a.field = f->data;
+    a.sg = sqrt(gain);  // ampliflat.m:78
+    for (int k = 0; k < f->nfc; ++k) a.sigma[k] = sigma ? sigma[k] : 0.0;
+    a.seed = seed;
+    a.N = (size_t)f->nfft;
+    a.nfc = f->nfc;
+    a.batch = f->batch;
+    cpx* dn = nullptr;
+    if (noise_host) {
+        const size_t bytes = (size_t)f->batch * 2 * f->nfc * f->nfft * sizeof(cpx);
+        CK(c, cudaMallocAsync(&dn, bytes, c->stream));
+        CK(c, cudaMemcpyAsync(dn, noise_host, bytes, cudaMemcpyHostToDevice, c->stream));
+        a.noise = dn;
+    }
+    dim3 g((unsigned)std::min<size_t>((a.N + 255) / 256, 148 * 8), f->batch * f->nfc);
+    pmx_k_ampliflat<<<g, 256, 0, c->stream>>>(a);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    if (dn) CK(c, cudaFreeAsync(dn, c->stream));
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// integer error count (ber_estimate.m:118)
+__global__ void __launch_bounds__(256) pmx_k_count(const uint8_t* hat, const uint8_t* pat, size_t n,
+                                                   unsigned long long* counts) {
+    const int b = blockIdx.y;
+    const uint8_t* h = hat + (size_t)b * n;
+    unsigned int local = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        local += (h[i] != pat[i]);
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counts[b], (unsigned long long)local);
+}
+
+extern "C" int pmx_count_errors(pmx_ctx* c, const uint8_t* hat, const uint8_t* pat, int64_t n, int32_t batch,
+                                int64_t* counts_dev) {
+    if (!c || !hat || !pat || !counts_dev || n <= 0 || batch <= 0)
+        return set_err(c, PMX_ERR_INVALID, "pmx_count_errors: bad argument");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemsetAsync(counts_dev, 0, (size_t)batch * sizeof(int64_t), c->stream));
+    dim3 g((unsigned)std::min<size_t>(((size_t)n + 255) / 256, 148 * 4), batch);
+    pmx_k_count<<<g, 256, 0, c->stream>>>(hat, pat, (size_t)n, (unsigned long long*)counts_dev);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return PMX_OK;
+}

@@ -1,0 +1,94 @@
+// Shared device-side types of the SSFM kernels (sm_100a).
+//
+// Field layout in HBM: one "Sa" = (xr, xi, yr, yi) = 4 doubles = 32 B, stored as
+// two consecutive double2 (X then Y).  field[((b*nfc + c)*N + n)*2 + pol].
+// Four-step index split: time n = n1*N2 + n2, frequency k = k1 + N1*k2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef double2 cpx;
+
+#define PMX_MAX_NFC 16
+
+enum { PMX_ST_RUN = 0, PMX_ST_LAST = 1, PMX_ST_DONE = 2, PMX_ST_ERROR = 3 };
+
+// Per-realization propagation state + the schedule of the step about to run.
+// Written by the last CTA of pass C (or by the init kernel), read by passes A/B/C.
+struct __align__(16) StepCtl {
+    // running state of matrix_ssfm (fiber.m:506-517)
+    double zprop;      // end coordinate of the step about to be taken
+    double dz;         // dz returned by the last nextstep
+    double dz_miss;    // fiber.m:508
+    double firstdz;    // fiber.m:516
+    int ntot;          // fiber.m:515
+    int ncycle;        // fiber.m:506
+    int state;         // PMX_ST_*
+    int err;           // pmx_status when state == PMX_ST_ERROR
+    // schedule of the current step
+    double dz_cur;     // dz (or last_step) used by NL, linear and attenuation
+    double leff;       // fiber.m:827-831
+    double scale;      // exp(-alpha/2*dz_cur) / N   (attenuation fused with the ifft 1/N)
+    double dzb_first;  // dzb(1)
+    double dzb_last;   // dzb(ntrunk)
+    int ntrunk;        // fiber.m:743,749
+    int nmem;          // fiber.m:742,748
+    int n_first;       // 0-based plate index of trunk k=1:  ntot + 1 - nmem - 1
+    int pad0;
+    // reduction scratch for nextstep
+    unsigned long long umax_bits[PMX_MAX_NFC];  // max over n of |ux|^2+|uy|^2, per column
+    unsigned int ticket;
+    unsigned int pad1;
+};
+
+// Per-plate constants, precomputed on the host in IEEE double.
+struct __align__(16) PlateConst {
+    // matR = Rtheta*Repsilon (fiber.m:910-912), row-major complex
+    double r11r, r11i, r12r, r12i, r21r, r21i, r22r, r22i;
+    // C = matR(next)^H * matR(this): change of PSP basis at the boundary to the next plate
+    double c11r, c11i, c12r, c12i, c21r, c21i, c22r, c22i;
+    double db0;       // brf.db0(n)
+    double h0r, h0i;  // exp(-i*db0/2): interior-plate phase factor
+    double pad;
+};
+
+// Constants of one fiber() call (kernel parameter, by value).
+struct FiberConst {
+    double Lf, alphalin, halfalpha, dzmax, phimax, lcorr, invN;
+    double gam[PMX_MAX_NFC];  // after the Manakov 8/9 (fiber.m:500)
+    int nplates, nfc, spm, manakov, pmd, gvd_any, plate_sets, trace_cap;
+};
+
+struct PassParams {
+    cpx* field;             // [batch*nfc][N][2]
+    StepCtl* ctl;           // [batch]
+    const cpx* tw_stage;    // in-CTA FFT stage twiddles for this L
+    const cpx* tw_hi;       // four-step twiddle W_N^(m) = hi[m >> lo_bits] * lo[m & lo_mask]
+    const cpx* tw_lo;
+    const double* betat_p;  // [nfc][N1][N2] permuted so that bin k1 + N1*k2 sits at k1*N2 + k2
+    const double* db1_p;    // same layout
+    const PlateConst* plates;  // [plate_sets][nplates]
+    double* trace_dz;       // [batch][trace_cap] or null
+    int* trace_ntrunk;
+    int N1, N2, log2N1, log2N2;
+    int lo_bits;
+    int batch;
+};
+
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cpx cmulc(cpx a, cpx b) {  // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cpx cscale(cpx a, double s) { return make_double2(a.x * s, a.y * s); }
+
+// |ux|^2+|uy|^2 in the reference's order, no FMA contraction (fiber.m:694)
+__device__ __forceinline__ double power_ref(cpx x, cpx y) {
+    double p = __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y));
+    p = __dadd_rn(p, __dmul_rn(y.x, y.x));
+    p = __dadd_rn(p, __dmul_rn(y.y, y.y));
+    return p;
+}

@@ -1,0 +1,151 @@
+// In-CTA Stockham FFT of length L (power of two, 8..4096) on a two-polarization
+// row, FP64.  L/8 threads cooperate on one row; each thread keeps 8 samples of
+// BOTH polarizations in registers (element q <-> index t + q*T, T = L/8) through
+// every stage, so the first stage can be fed straight from global memory, the
+// last stage leaves the spectrum in registers for the per-bin Jones product,
+// and the inverse transform starts from those same registers.  Stages are
+// radix 8, the last one radix 2 or 4 when log2(L) is not a multiple of 3;
+// between stages the data is exchanged through padded shared memory
+// (index i -> i + (i>>3), bank-conflict free for both the scattered stage
+// writes and the strided reads).
+//
+// Stage (radix R, Ns = product of earlier radices), butterfly j in [0, L/R):
+//   in : v[r] = x[j + r*L/R] * W_{Ns*R}^{(j mod Ns)*r}
+//   out: x'[(j - j mod Ns)*R + (j mod Ns) + r*Ns] = DFT_R(v)[r]
+// (natural order in, natural order out after the last stage).
+#pragma once
+#include "pmx_common.cuh"
+
+#define PMX_SQRT1_2 0.70710678118654752440
+
+__host__ __device__ constexpr int pmx_ilog2(int v) { return v <= 1 ? 0 : 1 + pmx_ilog2(v >> 1); }
+__host__ __device__ constexpr int pmx_pad(int i) { return i + (i >> 3); }
+
+// radix of the stage that starts with Ns already done
+__host__ __device__ constexpr int pmx_stage_radix(int L, int Ns) { return (L / Ns) >= 8 ? 8 : (L / Ns); }
+// offset (in cpx) of the twiddle block of the stage starting at Ns within the per-L table
+__host__ __device__ constexpr int pmx_tw_offset(int L, int Ns) {
+    int off = 0;
+    int ns = 1;
+    while (ns < Ns) {
+        int r = pmx_stage_radix(L, ns);
+        if (ns > 1) off += (r - 1) * ns;
+        ns *= r;
+    }
+    return off;
+}
+__host__ __device__ constexpr int pmx_tw_total(int L) { return pmx_tw_offset(L, L); }
+
+template <bool INV>
+__device__ __forceinline__ cpx mul_mj(cpx a) {  // forward: *(-i); inverse: *(+i)
+    return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft2(cpx& a, cpx& b) {
+    cpx t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft4(cpx& a0, cpx& a1, cpx& a2, cpx& a3) {
+    cpx t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mj<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft8(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4, cpx& a5, cpx& a6,
+                                     cpx& a7) {
+    dft4<INV>(a0, a2, a4, a6);  // even -> E0..E3 in a0,a2,a4,a6
+    dft4<INV>(a1, a3, a5, a7);  // odd  -> O0..O3 in a1,a3,a5,a7
+    // W8^k * O[k]
+    cpx o0 = a1;
+    cpx o1, o2, o3;
+    if (!INV) {
+        o1 = make_double2((a3.x + a3.y) * PMX_SQRT1_2, (a3.y - a3.x) * PMX_SQRT1_2);
+        o2 = make_double2(a5.y, -a5.x);
+        o3 = make_double2((a7.y - a7.x) * PMX_SQRT1_2, -(a7.x + a7.y) * PMX_SQRT1_2);
+    } else {
+        o1 = make_double2((a3.x - a3.y) * PMX_SQRT1_2, (a3.x + a3.y) * PMX_SQRT1_2);
+        o2 = make_double2(-a5.y, a5.x);
+        o3 = make_double2(-(a7.x + a7.y) * PMX_SQRT1_2, (a7.x - a7.y) * PMX_SQRT1_2);
+    }
+    cpx e0 = a0, e1 = a2, e2 = a4, e3 = a6;
+    a0 = cadd(e0, o0);
+    a1 = cadd(e1, o1);
+    a2 = cadd(e2, o2);
+    a3 = cadd(e3, o3);
+    a4 = csub(e0, o0);
+    a5 = csub(e1, o1);
+    a6 = csub(e2, o2);
+    a7 = csub(e3, o3);
+}
+
+template <int L, bool INV>
+struct CtaFFT {
+    static constexpr int T = L / 8;
+    static constexpr int SMEM_CPX_PER_POL = pmx_pad(L);  // padded length of one polarization
+
+    template <int NS>
+    __device__ __forceinline__ static void stage(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t,
+                                                 const cpx* __restrict__ tw) {
+        constexpr int R = pmx_stage_radix(L, NS);
+        constexpr int NB = 8 / R;
+        constexpr bool LAST = (NS * R == L);
+        constexpr int TWO = pmx_tw_offset(L, NS);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = t + b * T;
+            const int k = j & (NS - 1);
+            if constexpr (NS > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    cpx w = __ldg(&tw[TWO + (r - 1) * NS + k]);
+                    if (INV) w.y = -w.y;
+                    x[b + NB * r] = cmul(x[b + NB * r], w);
+                    y[b + NB * r] = cmul(y[b + NB * r], w);
+                }
+            }
+            if constexpr (R == 8) {
+                dft8<INV>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+                dft8<INV>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+            } else if constexpr (R == 4) {
+                dft4<INV>(x[b], x[b + 2], x[b + 4], x[b + 6]);
+                dft4<INV>(y[b], y[b + 2], y[b + 4], y[b + 6]);
+            } else {
+                dft2<INV>(x[b], x[b + 4]);
+                dft2<INV>(y[b], y[b + 4]);
+            }
+            if constexpr (!LAST) {
+                const int j0 = (j - k) * R + k;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int o = pmx_pad(j0 + r * NS);
+                    sx[o] = x[b + NB * r];
+                    sy[o] = y[b + NB * r];
+                }
+            }
+        }
+        if constexpr (!LAST) {
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int o = pmx_pad(t + q * T);
+                x[q] = sx[o];
+                y[q] = sy[o];
+            }
+            __syncthreads();
+            stage<NS * R>(x, y, sx, sy, t, tw);
+        }
+    }
+
+    // x[q], y[q] hold element t + q*T on entry and on exit (natural order).
+    __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t,
+                                               const cpx* __restrict__ tw) {
+        stage<1>(x, y, sx, sy, t, tw);
+    }
+};

@@ -1,0 +1,395 @@
+// The three HBM passes of one SSFM step (fiber.m:518-537 per iteration) and the
+// device-side step control (nextstep fiber.m:693-715, checkstep :739-758).
+//
+//   pass A  columns: NL step (matrix_nl_step :827-851) -> FFT over n1 -> W_N^(n2*k1)
+//   pass B  rows   : FFT over n2 -> per-bin Jones/dispersion product over the step's
+//                    trunks (matrix_step :907-933) -> IFFT over k2 -> conj twiddle
+//   pass C  columns: IFFT over k1 -> 1/N * exp(-alpha/2 dz) (:531-532) ->
+//                    max |u|^2 (warp shuffle + one atomicMax per CTA) -> the last CTA
+//                    of a realization runs nextstep + checkstep for the next step
+#pragma once
+#include "pmx_fft.cuh"
+
+// ---------------------------------------------------------------------------
+// step control (one thread)
+__device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bool first, int b,
+                                             double* trace_dz, int* trace_ntrunk) {
+    if (!first) {
+        if (c->state == PMX_ST_LAST) {  // the step just finished was the last one
+            c->state = PMX_ST_DONE;
+            for (int k = 0; k < f.nfc; ++k) c->umax_bits[k] = 0ull;
+            c->ticket = 0u;
+            return;
+        }
+        c->ntot += c->ntrunk - c->nmem;  // fiber.m:529
+    }
+    // ---- nextstep, fiber.m:693-715
+    double pmax = 0.0;
+    bool bad = false;
+    for (int k = 0; k < f.nfc; ++k) {
+        double um = __longlong_as_double((long long)c->umax_bits[k]);
+        if (um != um) bad = true;
+        double gp = __dmul_rn(f.gam[k], um);
+        pmax = (k == 0) ? gp : fmax(pmax, gp);
+        c->umax_bits[k] = 0ull;
+    }
+    c->ticket = 0u;
+    if (bad) {
+        c->state = PMX_ST_ERROR;
+        c->err = -5;  // PMX_ERR_NUMERIC
+        return;
+    }
+    double leff = f.phimax / pmax;
+    double dl = __dmul_rn(f.alphalin, leff);
+    double dz;
+    if (dl >= 1.0) {
+        dz = f.dzmax;
+    } else {
+        double step;
+        if (f.alphalin == 0.0)
+            step = leff;
+        else
+            step = __dmul_rn(-1.0 / f.alphalin, log(1.0 - dl));
+        dz = (step > f.dzmax) ? f.dzmax : step;
+    }
+    if (first) {
+        c->firstdz = dz;
+        c->zprop = dz;
+        c->ncycle = 1;
+        c->ntot = 0;
+        c->dz_miss = 0.0;
+    } else {
+        c->zprop = __dadd_rn(c->zprop, dz);
+        c->ncycle += 1;
+    }
+    c->dz = dz;
+    double dz_cur, zend;
+    if (c->zprop < f.Lf) {
+        dz_cur = dz;
+        zend = c->zprop;
+        c->state = PMX_ST_RUN;
+    } else {
+        dz_cur = __dadd_rn(__dadd_rn(f.Lf, -c->zprop), dz);  // fiber.m:538
+        zend = f.Lf;
+        c->state = PMX_ST_LAST;
+    }
+    c->dz_cur = dz_cur;
+    c->leff = (f.alphalin == 0.0) ? dz_cur : (1.0 - exp(-f.alphalin * dz_cur)) / f.alphalin;  // :827-831
+    c->scale = exp(-f.halfalpha * dz_cur) * f.invN;                                           // :531
+    // ---- checkstep, fiber.m:739-758
+    const double lcorr = f.lcorr;
+    double nz = zend / lcorr;
+    int nzc = (int)ceil(nz);
+    int ntrunk, nmem;
+    double dz_miss = c->dz_miss, dzb_first, dzb_last;
+    if (dz_miss == 0.0) {
+        nmem = 0;
+        ntrunk = nzc - c->ntot;
+        double dzlast = __dadd_rn(dz_cur, -__dmul_rn(lcorr, (double)(ntrunk - 1)));
+        dzb_first = (ntrunk > 1) ? lcorr : dzlast;
+        dzb_last = dzlast;
+        dz_miss = __dadd_rn(lcorr, -dzlast);
+    } else {
+        nmem = 1;
+        ntrunk = nzc - c->ntot + 1;
+        if (ntrunk == 1) {
+            dzb_first = dzb_last = dz_cur;
+            dz_miss = __dadd_rn(dz_miss, -dz_cur);
+        } else {
+            double dzlast = __dadd_rn(__dadd_rn(dz_cur, -dz_miss), -__dmul_rn(lcorr, (double)(ntrunk - 2)));
+            dzb_first = dz_miss;
+            dzb_last = dzlast;
+            dz_miss = __dadd_rn(lcorr, -dzlast);
+        }
+    }
+    c->dz_miss = dz_miss;
+    c->ntrunk = ntrunk;
+    c->nmem = nmem;
+    c->dzb_first = dzb_first;
+    c->dzb_last = dzb_last;
+    c->n_first = c->ntot - nmem;
+    if (ntrunk > 0 && (c->ntot + ntrunk - nmem > f.nplates || c->n_first < 0)) {
+        c->state = PMX_ST_ERROR;  // brf.theta(n) index error in the reference (fiber.m:910)
+        c->err = -4;              // PMX_ERR_PLATE_INDEX
+        return;
+    }
+    if (trace_dz && c->ncycle - 1 < f.trace_cap) {
+        trace_dz[(size_t)b * f.trace_cap + c->ncycle - 1] = dz_cur;
+        trace_ntrunk[(size_t)b * f.trace_cap + c->ncycle - 1] = ntrunk;
+    }
+}
+
+// Order-preserving key of a power value: non-negative doubles order like their bit
+// patterns; NaN maps above +Inf so that it wins the max and the step control flags it.
+__device__ __forceinline__ unsigned long long pmx_pow_key(double pw) {
+    return (pw != pw) ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(pw);
+}
+
+// Block-wide max (warp shuffles, then one atomicMax per CTA); the last CTA of the
+// realization (ticket) runs the step control.
+__device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, cpx* smem, StepCtl* c, int col,
+                                                      unsigned total_ctas, const FiberConst& f,
+                                                      bool first, int b, double* trace_dz,
+                                                      int* trace_ntrunk) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem);
+    __shared__ int s_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarp = (blockDim.x + 31) >> 5;
+    __syncthreads();  // smem free
+    if (lane == 0) red[warp] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = red[0];
+        for (int w = 1; w < nwarp; ++w) m = red[w] > m ? red[w] : m;
+        atomicMax(&c->umax_bits[col], m);
+        __threadfence();
+        unsigned prev = atomicAdd(&c->ticket, 1u);
+        s_last = (prev == total_ctas - 1u);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        pmx_ctl_next(c, f, first, b, trace_dz, trace_ntrunk);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Initial max |u|^2 of a resident field + first step schedule (fiber.m:512).
+static __global__ void __launch_bounds__(256) pmx_k_init(PassParams p, FiberConst f) {
+    extern __shared__ cpx smem[];
+    const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
+    const size_t N = (size_t)p.N1 * p.N2;
+    const cpx* fld = p.field + (size_t)bc * N * 2;
+    unsigned long long vmax = 0ull;
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+        cpx x = fld[2 * n], y = fld[2 * n + 1];
+        unsigned long long key = pmx_pow_key(power_ref(x, y));
+        vmax = key > vmax ? key : vmax;
+    }
+    pmx_block_max_and_ctl(vmax, smem, &p.ctl[b], col, gridDim.x * f.nfc, f, true, b, p.trace_dz,
+                          p.trace_ntrunk);
+}
+
+// smem region stride (in cpx) between the rows/columns a CTA works on: padded so
+// that lanes of different regions fall in different 16-byte bank groups.
+template <int L, int GROUP>
+struct PmxSmem {
+    static constexpr int BASE = ((2 * pmx_pad(L) + 7) / 8) * 8;
+    static constexpr int OFF = (GROUP > 1) ? ((8 / GROUP) > 0 ? (8 / GROUP) : 1) : 0;
+    static constexpr int STRIDE = BASE + OFF;
+    static constexpr size_t bytes(int groups) { return (size_t)groups * STRIDE * sizeof(cpx); }
+};
+
+__device__ __forceinline__ cpx pmx_twiddle4(const PassParams& p, unsigned m) {
+    cpx h = __ldg(&p.tw_hi[m >> p.lo_bits]);
+    cpx l = __ldg(&p.tw_lo[m & ((1u << p.lo_bits) - 1u)]);
+    return cmul(h, l);
+}
+
+// ---------------------------------------------------------------------------
+// pass A: CPC adjacent columns per CTA, thread (cl fastest, t)
+template <int L, int CPC>
+__global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passA(PassParams p, FiberConst f) {
+    constexpr int T = L / 8;
+    extern __shared__ cpx smem[];
+    const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
+    const StepCtl* c = &p.ctl[b];
+    if (c->state >= PMX_ST_DONE) return;
+    const int cl = threadIdx.x % CPC, t = threadIdx.x / CPC;
+    const int n2 = blockIdx.x * CPC + cl;
+    const size_t N = (size_t)p.N1 * p.N2;
+    cpx* base = p.field + ((size_t)bc * N + n2) * 2;
+    const size_t rs = (size_t)p.N2 * 2;  // cpx per n1 row
+    cpx x[8], y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const cpx* a = base + (size_t)(t + q * T) * rs;
+        x[q] = a[0];
+        y[q] = a[1];
+    }
+    // ---- nonlinear step, fiber.m:832-851
+    if (f.spm) {
+        const double gamleff = __dmul_rn(f.gam[col], c->leff);
+        const double ngl = -gamleff;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double pw = power_ref(x[q], y[q]);
+            double s, cs;
+            sincos(__dmul_rn(ngl, pw), &s, &cs);
+            cpx e = make_double2(cs, s);
+            x[q] = cmul(x[q], e);
+            y[q] = cmul(y[q], e);
+            if (!f.manakov) {
+                double s3 = 2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
+                double sp, cp;
+                sincos(__dmul_rn(gamleff, s3) / 3.0, &sp, &cp);
+                cpx ux = x[q], uy = y[q];
+                x[q] = make_double2(cp * ux.x + sp * uy.x, cp * ux.y + sp * uy.y);
+                y[q] = make_double2(cp * uy.x - sp * ux.x, cp * uy.y - sp * ux.y);
+            }
+        }
+    }
+    cpx* sx = smem + cl * PmxSmem<L, CPC>::STRIDE;
+    cpx* sy = sx + pmx_pad(L);
+    CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k1 = t + q * T;
+        cpx w = pmx_twiddle4(p, (unsigned)n2 * (unsigned)k1);
+        cpx* a = base + (size_t)k1 * rs;
+        a[0] = cmul(x[q], w);
+        a[1] = cmul(y[q], w);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass B: RPC rows per CTA, thread (t fastest, rl)
+template <int L, int RPC>
+__global__ void __launch_bounds__(RPC * (L / 8)) pmx_k_passB(PassParams p, FiberConst f) {
+    constexpr int T = L / 8;
+    extern __shared__ cpx smem[];
+    const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
+    const StepCtl* c = &p.ctl[b];
+    if (c->state >= PMX_ST_DONE) return;
+    const int rl = threadIdx.x / T, t = threadIdx.x % T;
+    const int k1 = blockIdx.x * RPC + rl;
+    const size_t N = (size_t)p.N1 * p.N2;
+    cpx* base = p.field + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
+    cpx x[8], y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const cpx* a = base + (size_t)(t + q * T) * 2;
+        x[q] = a[0];
+        y[q] = a[1];
+    }
+    cpx* sx = smem + rl * PmxSmem<L, RPC>::STRIDE;
+    cpx* sy = sx + pmx_pad(L);
+    CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+
+    // ---- linear step in the frequency domain, fiber.m:907-933
+    const int ntrunk = c->ntrunk;
+    if (ntrunk > 0) {
+        const double dz_cur = c->dz_cur;
+        const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
+        if (f.pmd) {
+            const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
+            const PlateConst* pl = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
+            const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k2 = t + q * T;
+                const double d1 = __ldg(&d1p[k2]);
+                // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
+                cpx vx, vy;
+                {
+                    const PlateConst& P = pl[0];
+                    cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                    cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+                    vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
+                    vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
+                }
+                double e1s, e1c;
+                bool have_e1 = false;
+                for (int k = 0; k < ntrunk; ++k) {
+                    const PlateConst& P = pl[k];
+                    const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
+                    cpx e;
+                    if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
+                        if (!have_e1) {
+                            sincos(-0.5 * d1, &e1s, &e1c);
+                            have_e1 = true;
+                        }
+                        e = cmul(make_double2(e1c, e1s), make_double2(P.h0r, P.h0i));
+                    } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+                        double delta = 0.5 * (d1 + P.db0) * dzb / lcorr;
+                        double s, cs;
+                        sincos(-delta, &s, &cs);
+                        e = make_double2(cs, s);
+                    }
+                    vx = cmul(vx, e);
+                    vy = cmulc(vy, e);
+                    if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
+                        cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
+                        cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
+                        cpx nx = cadd(cmul(c11, vx), cmul(c12, vy));
+                        cpx ny = cadd(cmul(c21, vx), cmul(c22, vy));
+                        vx = nx;
+                        vy = ny;
+                    }
+                }
+                {  // back to the laboratory basis: u = matR * uu  (:931-932)
+                    const PlateConst& P = pl[ntrunk - 1];
+                    cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                    cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+                    x[q] = cadd(cmul(r11, vx), cmul(r12, vy));
+                    y[q] = cadd(cmul(r21, vx), cmul(r22, vy));
+                }
+            }
+        }
+        if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double ph = __ldg(&bt[t + q * T]) * dz_cur;
+                double s, cs;
+                sincos(-ph, &s, &cs);
+                cpx e = make_double2(cs, s);
+                x[q] = cmul(x[q], e);
+                y[q] = cmul(y[q], e);
+            }
+        }
+    }
+
+    CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int n2 = t + q * T;
+        cpx w = pmx_twiddle4(p, (unsigned)n2 * (unsigned)k1);
+        cpx* a = base + (size_t)n2 * 2;
+        a[0] = cmulc(x[q], w);
+        a[1] = cmulc(y[q], w);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass C: like pass A, inverse transform + attenuation + max reduction + step control
+template <int L, int CPC>
+__global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passC(PassParams p, FiberConst f) {
+    constexpr int T = L / 8;
+    extern __shared__ cpx smem[];
+    const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
+    StepCtl* c = &p.ctl[b];
+    if (c->state >= PMX_ST_DONE) return;
+    const int cl = threadIdx.x % CPC, t = threadIdx.x / CPC;
+    const int n2 = blockIdx.x * CPC + cl;
+    const size_t N = (size_t)p.N1 * p.N2;
+    cpx* base = p.field + ((size_t)bc * N + n2) * 2;
+    const size_t rs = (size_t)p.N2 * 2;
+    cpx x[8], y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const cpx* a = base + (size_t)(t + q * T) * rs;
+        x[q] = a[0];
+        y[q] = a[1];
+    }
+    cpx* sx = smem + cl * PmxSmem<L, CPC>::STRIDE;
+    cpx* sy = sx + pmx_pad(L);
+    CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
+    const double sc = c->scale;
+    unsigned long long vmax = 0ull;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        x[q] = cscale(x[q], sc);
+        y[q] = cscale(y[q], sc);
+        unsigned long long key = pmx_pow_key(power_ref(x[q], y[q]));
+        vmax = key > vmax ? key : vmax;
+        cpx* a = base + (size_t)(t + q * T) * rs;
+        a[0] = x[q];
+        a[1] = y[q];
+    }
+    pmx_block_max_and_ctl(vmax, smem, c, col, gridDim.x * f.nfc, f, false, b, p.trace_dz, p.trace_ntrunk);
+}

@@ -1,0 +1,236 @@
+"""fiber(x, flag): the reference's optical-fiber operator, SSFM loop on a B200.
+
+Mirror of fiber.m: same struct fields (fiber.m:8-52), same 4-character flag
+(:54-71, :157-251), same side effects on GSTATE.FIELDX / FIELDY / DELAY / DISP
+(:286, :367-369, :376-388) and the same ``brf`` return (:384).  Everything up
+to the dispatch at fiber.m:372 is host scalar set-up and is done here in IEEE
+double; the propagation loop itself (matrix_ssfm, :459-555) runs inside the
+C-ABI CUDA library through ``pmx_fiber_run`` -- one call per fiber(), host
+buffers in, host buffers out.  There is no CPU fallback.
+
+Not built (raise, like the reference does for its own unimplemented branches):
+the scalar single-polarization path without 'p' and with FIELDY empty
+(scalar_ssfm) is routed through the same two-polarization kernels with a zero
+Y field only when no XPM is requested; the local-error adaptive step (ltol,
+scalar_a_ssfm / adaptssfm, :639-679, :938-1010) is not available.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .gstate import CONSTANTS, GSTATE, rng as _global_rng
+
+DEF_PLATES = 100  # fiber.m:131
+
+# flag -> (g, p, s, x) and whether the run is forced to a single linear step
+_FLAG_TABLE = {
+    '----': (0, 0, 0, 0), 'g---': (1, 0, 0, 0), '-p--': (0, 1, 0, 0), '--s-': (0, 0, 1, 0),
+    '---x': (0, 0, 0, 1), 'gp--': (1, 1, 0, 0), 'g-s-': (1, 0, 1, 0), 'g--x': (1, 0, 0, 1),
+    '-ps-': (0, 1, 1, 0), '-p-x': (0, 1, 0, 1), '--sx': (0, 0, 1, 1), 'g-sx': (1, 0, 1, 1),
+    '-psx': (0, 1, 1, 1), 'gps-': (1, 1, 1, 0), 'gp-x': (1, 1, 0, 1), 'gpsx': (1, 1, 1, 1),
+}
+_LINEAR = ('----', 'g---', '-p--', 'gp--')
+_X_ONLY_MULTI = ('---x', 'g--x', '-p-x', 'gp-x')      # error when nfc == 1
+_X_OPTIONAL = ('--sx', 'g-sx', '-psx', 'gpsx')         # x silently dropped when nfc == 1
+
+
+def _get(x, name, default=None):
+    if isinstance(x, dict):
+        return x.get(name, default)
+    return getattr(x, name, default)
+
+
+def _has(x, name):
+    return (name in x) if isinstance(x, dict) else hasattr(x, name)
+
+
+@dataclass
+class FiberSetup:
+    """Everything fiber.m:126-369 computes before the SSFM dispatch."""
+    nfft: int
+    nfc: int
+    fls: tuple
+    dphimaxt: float
+    dzmaxt: float
+    length: float
+    alphalin: float
+    gam: np.ndarray          # [nfc], before the Manakov 8/9
+    betat: np.ndarray        # [nfft, nfc]
+    db1: np.ndarray          # [nfft, nfc]
+    manakov: bool
+    nplates: int
+    brf: dict
+    isv: bool
+    isy: bool
+    b1: np.ndarray
+    dch: np.ndarray
+
+
+def flag_to_fls(flag: str, nfc: int, x):
+    """fiber.m:157-251 -> (fls, dphimaxt, dzmaxt)."""
+    f = flag.lower()
+    if f not in _FLAG_TABLE:
+        raise ValueError("wrong flag. E.g. flag can be 'g---','gp--','-s--', etc")
+    if f in _X_ONLY_MULTI and nfc == 1:
+        raise ValueError("flag '%s' available only for channels separated" % f)
+    g, p, s, xx = _FLAG_TABLE[f]
+    if f in _X_OPTIONAL and nfc == 1:
+        xx = 0
+    single_exact = f in ('--s-', '--sx') and nfc == 1      # exact SPM solution, :172-174, :218-220
+    if f in _LINEAR or single_exact:
+        return (g, p, s, xx), math.inf, float(_get(x, 'length'))
+    return (g, p, s, xx), float(_get(x, 'dphimax')), float(_get(x, 'dzmax'))
+
+
+def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> FiberSetup:
+    """Host part of fiber(): parameter checks, PMD plates, unit conversions."""
+    G = GSTATE
+    if flag is None:
+        raise ValueError('Missing propagation type')                        # fiber.m:137
+    nfr, nfc = G.FIELDX.shape
+    nfft = G.NSYMB * G.NT
+    length = float(_get(x, 'length'))
+    xd = {k: _get(x, k) for k in ('dzmax', 'dphimax', 'length')}
+    if not _has(x, 'dzmax') or xd['dzmax'] > length:                        # :139-141
+        xd['dzmax'] = length
+    if _has(x, 'ltol'):
+        raise NotImplementedError('local-error adaptive step (x.ltol, fiber.m:143-155,639-679) is not built')
+    fls, dphimaxt, dzmaxt = flag_to_fls(flag, nfc, xd)
+
+    isy = G.FIELDY is not None and np.size(G.FIELDY) != 0                   # :253
+    isv = bool(fls[1]) or isy
+    brf = {}
+    if fls[1]:                                                              # :255-289
+        manakov = str(_get(x, 'manakov', 'no')) == 'yes'
+        if not _has(x, 'dgd'):
+            raise ValueError('Missing DGD in fiber')
+        dgd = float(_get(x, 'dgd'))
+        given = [_has(x, k) for k in ('db0', 'theta', 'epsilon')]
+        if all(given):                                                      # PMF, :264-269
+            theta = np.atleast_1d(np.asarray(_get(x, 'theta'), dtype=np.float64)).ravel()
+            nplates = theta.size
+            brf['db0'] = np.atleast_1d(np.asarray(_get(x, 'db0'), dtype=np.float64)).ravel()
+            brf['theta'] = theta
+            brf['epsilon'] = np.atleast_1d(np.asarray(_get(x, 'epsilon'), dtype=np.float64)).ravel()
+            if brf['db0'].size != nplates or brf['epsilon'].size != nplates:
+                raise ValueError('db0, theta and epsilon must have the same length')
+            dgdrms = dgd / nplates
+        elif not any(given):                                                # random plates, :270-279
+            nplates = int(_get(x, 'nplates', DEF_PLATES))
+            r = rng if rng is not None else _global_rng()
+            brf['db0'] = r.random(nplates) * 2 * np.pi - np.pi
+            brf['theta'] = r.random(nplates) * np.pi - 0.5 * np.pi
+            brf['epsilon'] = 0.5 * np.arcsin(r.random(nplates) * 2 - 1)
+            dgdrms = math.sqrt((3 * math.pi) / 8) * dgd / math.sqrt(nplates)
+        else:
+            raise ValueError('Missing one of db0, theta or epsilon in fiber')
+        brf['dgd'] = dgd
+        dgdrms = dgdrms / G.SYMBOLRATE                                      # :284
+    else:                                                                   # :290-298
+        dgdrms, manakov, nplates = 0.0, False, 1
+        brf['db0'] = np.zeros(1)
+        brf['theta'] = np.zeros(1)
+        brf['epsilon'] = np.zeros(1)
+
+    c0 = CONSTANTS.CLIGHT
+    lam = float(_get(x, 'lambda'))
+    disp, slope = float(_get(x, 'disp')), float(_get(x, 'slope'))
+    alphalin = (math.log(10) * 1e-4) * float(_get(x, 'alphadB'))            # :302
+    b20 = -lam ** 2 / 2 / math.pi / c0 * disp * 1e-6                        # :308
+    b30 = (lam / 2 / math.pi / c0) ** 2 * (2 * lam * disp + lam ** 2 * slope) * 1e-6
+    b30 = b30 * fls[0]                                                      # :311
+    lams = np.asarray(G.LAMBDA, dtype=np.float64).reshape(-1)
+    maxl, minl = lams.max(), lams.min()
+    lamc = 2 * maxl * minl / (maxl + minl)                                  # :315
+    w_i0 = 2 * math.pi * c0 * (1.0 / lams - 1 / lam)
+    w_ic = 2 * math.pi * c0 * (1.0 / lams - 1 / lamc)
+    w_c0 = 2 * math.pi * c0 * (1.0 / lamc - 1 / lam)
+    b1 = b20 * w_ic + 0.5 * b30 * (w_i0 ** 2 - w_c0 ** 2)                   # :321
+    n2, aeff = float(_get(x, 'n2')), float(_get(x, 'aeff'))
+    if nfc == 1:                                                            # :322-329
+        beta1 = np.zeros(1)
+        w_i0 = np.array([2 * math.pi * c0 * (1.0 / lamc - 1 / lam)])
+        gam = np.array([2 * math.pi * n2 / (lamc * aeff) * 1e18])
+    else:
+        beta1 = b1
+        gam = 2 * math.pi * n2 / (lams * aeff) * 1e18
+    beta2 = (b20 + b30 * w_i0) * fls[0]                                     # :330-332
+    dch = disp + slope * (lams - lam)                                       # :336
+
+    omega = 2 * math.pi * G.SYMBOLRATE * np.asarray(G.FN, dtype=np.float64)  # :352
+    betat = np.zeros((nfft, nfc))
+    db1 = np.zeros((nfft, nfc))
+    for k in range(nfc):                                                    # :354-362
+        betat[:, k] = omega * beta1[k] + 0.5 * omega ** 2 * beta2[k] + omega ** 3 * b30 / 6
+        if fls[1]:
+            db1[:, k] = dgdrms * omega
+    return FiberSetup(nfft=nfft, nfc=nfc, fls=fls, dphimaxt=dphimaxt, dzmaxt=dzmaxt, length=length,
+                      alphalin=alphalin, gam=gam, betat=betat, db1=db1, manakov=manakov,
+                      nplates=nplates, brf=brf, isv=isv, isy=isy, b1=b1, dch=dch)
+
+
+def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, epsilon=None):
+    """FiberSetup -> (pmx_fiber_desc, keep-alive dict)."""
+    return _lib.make_desc(
+        s.nfft, s.nfc, batch, s.length, s.alphalin, s.dzmaxt, s.dphimaxt, s.gam, s.fls, s.manakov, s.nplates,
+        s.brf['db0'] if db0 is None else db0, s.brf['theta'] if theta is None else theta,
+        s.brf['epsilon'] if epsilon is None else epsilon, s.betat, s.db1 if s.fls[1] else None,
+        plate_sets=plate_sets)
+
+
+def apply_side_effects(s: FiberSetup):
+    """GSTATE.DELAY / GSTATE.DISP bookkeeping, fiber.m:367-369."""
+    G = GSTATE
+    rows = 2 if s.isy else 1
+    loc_delay = s.length * G.SYMBOLRATE * s.b1
+    G.DELAY = G.DELAY + np.ones((rows, 1)) * loc_delay[None, :]
+    G.DISP = G.DISP + np.ones((rows, 1)) * (s.fls[0] * s.dch * s.length * 1e-3)[None, :]
+
+
+LAST = {}  # firstdz / ncycle / schedule of the most recent fiber(), what the reference prints to simul_out
+
+
+def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional[_lib.Context] = None,
+          trace: bool = False):
+    """zbrf = fiber(x, flag) -- fiber.m:1.  Propagates GSTATE.FIELDX/FIELDY in place."""
+    G = GSTATE
+    s = fiber_setup(x, flag, rng)
+    if s.fls[3] and s.isv:
+        # matrix_nl_step raises at fiber.m:854 on the first step
+        raise NotImplementedError('The CNLSE with separate fields is not yet implemented')
+    if s.fls[3]:
+        raise NotImplementedError("scalar cross-phase modulation ('x' flag with separate fields, "
+                                  "fiber.m:793-799) is not built yet")
+    if s.fls[1] and not s.isy:                                              # :285-289
+        G.FIELDY = np.zeros_like(G.FIELDX)
+    apply_side_effects(s)
+    ctx = ctx or _lib.default_context()
+    desc, keep = setup_to_desc(s)
+    fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]     # [1][nfc][nfft]
+    scalar = not s.isv
+    fy = (np.zeros_like(fx) if scalar else
+          np.ascontiguousarray(np.asarray(G.FIELDY, dtype=np.complex128).T)[None])
+    io = _lib.complex_field(fx, fy)
+    res = _lib.Result(1, trace_cap=4096 if trace else 0)
+    import ctypes
+    ctx.check(ctx.lib.pmx_fiber_run(ctx.h, ctypes.byref(desc), ctypes.byref(io), ctypes.byref(res.c)))
+    G.FIELDX = np.ascontiguousarray(fx[0].T)
+    if not scalar:
+        G.FIELDY = np.ascontiguousarray(fy[0].T)
+    LAST.clear()
+    LAST.update(firstdz=float(res.firstdz[0]), ncycle=int(res.ncycle[0]), ntot=int(res.ntot[0]))
+    if trace:
+        dz, nt = res.schedule(0)
+        LAST.update(trace_dz=dz, trace_ntrunk=nt)
+    if not s.isv:
+        return None
+    brf = dict(s.brf)
+    brf['lcorr'] = s.length / s.nplates                                     # :510
+    brf['betat'] = s.betat                                                  # :553
+    brf['db1'] = s.db1                                                      # :554
+    return brf
