@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- SSFM GSa*steps/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+Workload (config.workload = "C2"): PDM-QPSK, 2^16 symbols x 16 samples = 2^20 samples per
+polarization, 10 spans of (80 km SMF, 'gps-' Manakov, 100 random waveplates, DGD 0.1 symbol)
+each followed by a 16 dB flat amplifier with ASE (noise figure 5 dB), FP64.  One "step" is
+one pass of that 10-span link over a batch of independent realizations (different plate
+draws and ASE seeds, same Tx field) resident in HBM; the batch (8 x 32 MiB = 256 MiB) is
+larger than the 126 MB L2.
+
+  value  Sum(N * ncycle) / time, fields resident in HBM, timed with CUDA events on the
+         library's stream, max over ranks
+  e2e    the same metric through the reference-facing calls fiber(x,'gps-') + ampliflat()
+         on HOST buffers (pinned), H2D and D2H of the field inside every call
+  roofline      dominant kernel (pass B) algorithmic bytes / its mean launch time (CUDA events)
+  cpu_baseline  the numpy oracle (op-for-op restatement of fiber.m) on one host core, on a
+                bounded sample of the same workload
+
+--impl reference times the CPU path (oracle port; no Octave/MATLAB exists in the image) with
+one worker process per host core, each on its own realization.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NSYMB, NT, RATE, PAVG = 1 << 16, 16, 28.0, 2.0
+NSPAN, SPAN_KM, NPLATES, DGD = 10, 80.0, 100, 0.1
+GAIN_DB, NF_DB = 16.0, 5.0
+ALG_BYTES_PER_SA_STEP = 192.0   # 3 passes x (read + write) x 32 B   
+CPU_SAMPLE_KM = 16.0            # bounded CPU sample: first 16 km (20 plates of 800 m) of span 1
+
+
+def fiber_params(length_m, nplates):
+    from polmux_b200 import synth
+    f = dict(synth.SMF)
+    f.update(length=length_m, dgd=DGD, nplates=nplates, manakov='yes')
+    return f
+
+
+def plate_draw(seed, nplates):
+    """fiber.m:274-276 with the stream of realization `seed`."""
+    r = np.random.Generator(np.random.PCG64(seed))
+    db0 = r.random(nplates) * 2 * np.pi - np.pi
+    theta = r.random(nplates) * np.pi - 0.5 * np.pi
+    eps = 0.5 * np.arcsin(r.random(nplates) * 2 - 1)
+    return db0, theta, eps
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([v.strip() for v in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i] == 'Active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_sample(seed):
+    """One bounded CPU sample: first CPU_SAMPLE_KM of span 1 at full N through the oracle.
+    -> (Sa*steps, seconds)."""
+    import oracle.fiber_oracle as orc
+    from polmux_b200 import synth
+    ex, ey, _, _ = synth.pdm_qpsk(NSYMB, NT, 1)
+    gs = orc.reset_all(NSYMB, NT, 1)
+    gs.SYMBOLRATE, gs.LAMBDA, gs.POWER = RATE, np.array([1550.0]), np.array([PAVG])
+    orc.create_field(gs, 'unique', ex, ey, power_average=True)
+    npl = int(round(NPLATES * CPU_SAMPLE_KM / SPAN_KM))
+    fib = fiber_params(CPU_SAMPLE_KM * 1e3, npl)
+    t0 = time.perf_counter()
+    orc.fiber(gs, fib, 'gps-', rng=np.random.Generator(np.random.PCG64(seed)))
+    dt = time.perf_counter() - t0
+    return float(NSYMB * NT) * gs.log['ncycle'], dt
+
+
+def _cpu_worker(seed):
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    return cpu_sample(seed)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU SSFM on all host cores (one realization per worker process)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    sample = ('first %.0f km (%d plates) of span 1, N=2^20, one realization per worker, %d workers'
+              % (CPU_SAMPLE_KM, int(round(NPLATES * CPU_SAMPLE_KM / SPAN_KM)), cores))
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            pool.map(_cpu_worker, [1000 + i for i in range(cores)])
+        t0 = time.perf_counter()
+        work = 0.0
+        for k in range(args.steps):
+            res = pool.map(_cpu_worker, [1000 + i for i in range(cores)])
+            work += sum(r[0] for r in res)
+        dt = time.perf_counter() - t0
+    val = work / dt / 1e9
+    line = {'impl': 'reference', 'metric': 'ssfm_gsa_steps_per_s', 'value': val, 'unit': 'GSa*steps/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dt / max(args.steps, 1) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args, world),
+            'cpu_baseline': {'value': val, 'unit': 'GSa*steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'GSa*steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {'workload': 'C2', 'nfft': NSYMB * NT, 'spans': NSPAN, 'span_km': SPAN_KM, 'flag': 'gps-',
+            'manakov': 'yes', 'nplates': NPLATES, 'dgd_symbols': DGD, 'ampli_gain_db': GAIN_DB, 'ampli_f_db': NF_DB,
+            'pavg_mw': PAVG, 'symbolrate_gbaud': RATE, 'realizations_per_gpu': args.batch,
+            'l2_policy': 'batch working set %d MiB > 126 MB L2' % (args.batch * 32),
+            'parallelism': 'realizations sharded over %d GPU(s), no data-path collective' % world}
+
+
+# ----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=8, help='realizations per GPU per step')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import polmux_b200 as pmx
+    from polmux_b200 import _lib, synth
+    from polmux_b200.ampliflat import ase_sigma
+    from polmux_b200.fiber import fiber_setup, setup_to_desc
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    ctx = _lib.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device('cuda', local))
+
+    # ---- Tx field (host, seeded) and fiber set-up
+    N = NSYMB * NT
+    ex, ey, _, _ = synth.pdm_qpsk(NSYMB, NT, 1)
+    pmx.reset_all(NSYMB, NT, 1)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.LAMBDA, G.POWER = RATE, np.array([1550.0]), np.array([PAVG])
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    fib = fiber_params(SPAN_KM * 1e3, NPLATES)
+    setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
+    B = args.batch
+    gain = 10 ** (GAIN_DB * 0.1)
+    sigma = ase_sigma(gain, NF_DB, 1)
+
+    # plate draws: realization r (global index), span k -> seed 1000 + r + 100000*k
+    def plates_for(span):
+        d = [plate_draw(1000 + rank * B + b + 100000 * span, NPLATES) for b in range(B)]
+        return (np.stack([x[0] for x in d]), np.stack([x[1] for x in d]), np.stack([x[2] for x in d]))
+
+    span_plates = [plates_for(k) for k in range(NSPAN)]
+    desc, keep = setup_to_desc(setup, batch=B, plate_sets=B, db0=span_plates[0][0], theta=span_plates[0][1],
+                               epsilon=span_plates[0][2])
+    plan = _lib.Plan(ctx, desc, keep)
+    tx = _lib.DeviceField(ctx, N, 1, 1)
+    tx.upload(G.FIELDX, G.FIELDY)
+    work = _lib.DeviceField(ctx, N, 1, B)
+
+    def link_step(step_id):
+        """one pass of the 10-span link over the resident batch -> Sa*steps done"""
+        work.broadcast_from(tx)
+        sa_steps = 0
+        for k in range(NSPAN):
+            plan.set_plates(*span_plates[k], plate_sets=B)
+            res = plan.execute(work)
+            sa_steps += int(res.ncycle.sum()) * N
+            _lib.ampliflat_exec(ctx, work, gain, sigma, None, seed=(step_id << 20) + (k << 8) + rank)
+        return sa_steps
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.sync()
+
+    for w in range(args.warmup):
+        link_step(w)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    total = 0
+    for k in range(args.steps):
+        total += link_step(100 + k)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = ctx.launches - launches0
+    sampler.stop_flag = True
+    t = torch.tensor([ms, float(total)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, total_all = float(tmax[0]), float(tsum[1])
+    else:
+        total_all = float(total)
+    value = total_all / (ms * 1e-3) / 1e9
+
+    # ---- per-pass timing (separate, profiled pass over one link step; events around every launch)
+    ctx.profile(True)
+    link_step(999)
+    pms, pn = ctx.profile_read()
+    ctx.profile(False)
+    roof = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    if pn[1] > 0:
+        names = ['passA', 'passB', 'passC']
+        dom = int(np.argmax(pms[:3]))
+        t_launch = pms[dom] / pn[dom] * 1e-3
+        bytes_launch = 64.0 * N * B       # one pass reads and writes every Sa of the batch once
+        ach = bytes_launch / t_launch / 1e9
+        roof = {'bound': 'hbm', 'kernel': names[dom], 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                'bytes_per_launch': bytes_launch, 'ms_per_launch': t_launch * 1e3,
+                'pass_ms_per_launch': {names[i]: (pms[i] / pn[i] if pn[i] else None) for i in range(3)},
+                'note': 'launch durations include early-exit launches of finished realizations'}
+    step_roof = {'achieved': ALG_BYTES_PER_SA_STEP * value / world, 'peak': peak, 'unit': 'GB/s',
+                 'frac': ALG_BYTES_PER_SA_STEP * value / world / peak, 'bytes_per_sa_step': ALG_BYTES_PER_SA_STEP,
+                 'per': 'GPU'}
+
+    # ---- e2e: reference-style calls on host buffers (one realization, all spans)
+    e2e = None
+    if not args.no_e2e:
+        pinx = torch.empty((N, 1), dtype=torch.complex128).pin_memory()
+        piny = torch.empty((N, 1), dtype=torch.complex128).pin_memory()
+        txx, txy = np.array(G.FIELDX_TX), np.array(G.FIELDY_TX)
+
+        def e2e_step(sid):
+            G.FIELDX, G.FIELDY = pinx.numpy(), piny.numpy()
+            G.FIELDX[...] = txx
+            G.FIELDY[...] = txy
+            G.DELAY, G.DISP = np.zeros((2, 1)), np.zeros((2, 1))
+            sa = 0
+            for k in range(NSPAN):
+                pmx.fiber(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(1000 + rank + 100000 * k)), ctx=ctx)
+                sa += pmx.FIBER_LAST['ncycle'] * N
+                pmx.ampliflat(GAIN_DB, 'gain', {'f': NF_DB}, ctx=ctx, seed=sid * 64 + k)
+            return sa
+
+        for w in range(2):
+            e2e_step(w)
+        barrier()
+        t0 = time.perf_counter()
+        sa = 0
+        ne2e = max(2, args.steps)
+        for k in range(ne2e):
+            sa += e2e_step(10 + k)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(sa)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            a = tt.clone()
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = tt.clone()
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            dt, sa = float(a[0]), float(b[1])
+        per_step_field = N * 32
+        # fiber(): field + betat + db1 up, field down; ampliflat(): field up, field down
+        e2e = {'value': sa / dt / 1e9, 'unit': 'GSa*steps/s',
+               'h2d_bytes_per_step': NSPAN * (2 * per_step_field + 2 * N * 8),
+               'd2h_bytes_per_step': NSPAN * 2 * per_step_field,
+               'api': "fiber(x,'gps-') + ampliflat(G,'gain',opt) per span on pinned host buffers, 1 realization per rank"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sa, dt = cpu_sample(1000)
+        cpu = {'value': sa / dt / 1e9, 'unit': 'GSa*steps/s', 'cores': 1, 'kind': 'port',
+               'sample': 'first %.0f km (%d plates) of span 1, N=2^20, 1 realization, numpy oracle (%.1f s)'
+                         % (CPU_SAMPLE_KM, int(round(NPLATES * CPU_SAMPLE_KM / SPAN_KM)), dt)}
+
+    if rank == 0:
+        sampler.join(timeout=2)
+        line = {'metric': 'ssfm_gsa_steps_per_s', 'value': value, 'unit': 'GSa*steps/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / max(args.steps, 1),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic', 'config': workload_config(args, world), 'clocks': sampler.summary(),
+                'e2e': e2e, 'gpu_launches': int(gpu_launches), 'roofline': roof, 'roofline_step': step_roof,
+                'cpu_baseline': cpu, 'sa_steps_per_step': total_all / max(args.steps, 1)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

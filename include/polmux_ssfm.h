@@ -149,6 +149,14 @@ int pmx_fiber_exec(pmx_plan* plan, pmx_devfield* f, pmx_fiber_result* out);
 /* Total kernel launches issued by this ctx so far (bench `gpu_launches`). */
 int64_t pmx_ctx_launch_count(const pmx_ctx* ctx);
 
+/* Per-pass device timing for benchmarks: when enabled, every pass launch is bracketed by CUDA
+ * events on the ctx stream.  ms[k] / n[k]: accumulated milliseconds and launch count of
+ * k = 0 pass A (NL + column FFT), 1 pass B (row FFT + Jones + row IFFT), 2 pass C (column IFFT +
+ * attenuation + max + step control), 3 initial max reduction.  Early-exit launches of finished
+ * realizations are included (they are launches).  Enabling resets the counters. */
+int pmx_ctx_profile(pmx_ctx* ctx, int enable);
+int pmx_ctx_profile_read(pmx_ctx* ctx, double* ms, int64_t* n);
+
 /* ---- span boundary: flat-gain amplifier with ASE --------------------------------
  * ampliflat(x,'gain',options)  ampliflat.m:61-148.
  *   field <- field*sqrt(gain) + sigma[c]*noise

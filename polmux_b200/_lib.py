@@ -26,7 +26,8 @@ EXPORTS = [
     'pmx_ctx_sync', 'pmx_ctx_stream', 'pmx_fiber_run', 'pmx_field_create', 'pmx_field_destroy',
     'pmx_field_upload', 'pmx_field_download', 'pmx_field_broadcast', 'pmx_field_device_ptr',
     'pmx_plan_create', 'pmx_plan_destroy', 'pmx_plan_set_plates', 'pmx_fiber_exec',
-    'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors',
+    'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
+    'pmx_ctx_profile_read',
 ]
 
 
@@ -85,6 +86,8 @@ def load():
     lib.pmx_ctx_stream.restype = vp
     lib.pmx_ctx_launch_count.argtypes = [vp]
     lib.pmx_ctx_launch_count.restype = C.c_int64
+    lib.pmx_ctx_profile.argtypes = [vp, C.c_int]
+    lib.pmx_ctx_profile_read.argtypes = [vp, _dp, C.POINTER(C.c_int64)]
     lib.pmx_fiber_run.argtypes = [vp, C.POINTER(FiberDesc), C.POINTER(Field), C.POINTER(FiberResult)]
     lib.pmx_field_create.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     lib.pmx_field_destroy.argtypes = [vp]
@@ -139,6 +142,15 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.pmx_ctx_launch_count(self.h))
+
+    def profile(self, enable: bool):
+        self.check(self.lib.pmx_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms = np.zeros(4)
+        n = np.zeros(4, dtype=np.int64)
+        self.check(self.lib.pmx_ctx_profile_read(self.h, _ptr(ms), n.ctypes.data_as(C.POINTER(C.c_int64))))
+        return ms, n
 
     def close(self):
         if getattr(self, 'h', None):

@@ -74,7 +74,50 @@ struct pmx_ctx {
     StepCtl* h_ctl = nullptr;  // pinned readback buffer
     int h_ctl_cap = 0;
     int64_t launches = 0;
+    // optional per-pass timing (CUDA events around every pass launch)
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_kind;  // kind of interval i (events 2i, 2i+1)
+    size_t ev_used = 0;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_n[4] = {0, 0, 0, 0};
 };
+
+struct ProfScope {  // records start/stop events around one launch when profiling is on
+    pmx_ctx* c;
+    bool on;
+    ProfScope(pmx_ctx* ctx, int kind) : c(ctx), on(ctx->profile) {
+        if (!on) return;
+        if (c->ev_used + 2 > c->ev_pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            c->ev_pool.push_back(a);
+            c->ev_pool.push_back(b);
+        }
+        c->ev_kind.resize(c->ev_pool.size() / 2);
+        c->ev_kind[c->ev_used / 2] = kind;
+        cudaEventRecord(c->ev_pool[c->ev_used], c->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(c->ev_pool[c->ev_used + 1], c->stream);
+        c->ev_used += 2;
+    }
+};
+
+static void prof_collect(pmx_ctx* c) {
+    if (!c->ev_used) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->ev_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]) == cudaSuccess) {
+            c->prof_ms[c->ev_kind[i / 2]] += ms;
+            c->prof_n[c->ev_kind[i / 2]] += 1;
+        }
+    }
+    c->ev_used = 0;
+}
 
 struct pmx_devfield {
     pmx_ctx* ctx;
@@ -154,6 +197,13 @@ extern "C" int pmx_ctx_create(pmx_ctx** out, int device_id) {
                        device_id, prop.major, prop.minor);
     }
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {  // keep freed blocks cached in the stream-ordered pool: fiber() after fiber() reuses them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     *out = c;
     return PMX_OK;
 }
@@ -162,6 +212,7 @@ extern "C" void pmx_ctx_destroy(pmx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto& kv : c->stage_tw) cudaFree(kv.second.dev);
     for (auto& kv : c->four_tw) {
         cudaFree(kv.second.hi);
@@ -176,6 +227,28 @@ extern "C" int pmx_ctx_sync(pmx_ctx* c) {
     if (!c) return set_err(nullptr, PMX_ERR_INVALID, "null ctx");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
+extern "C" int pmx_ctx_profile(pmx_ctx* c, int enable) {
+    if (!c) return set_err(nullptr, PMX_ERR_INVALID, "null ctx");
+    prof_collect(c);
+    c->profile = enable != 0;
+    if (enable)
+        for (int k = 0; k < 4; ++k) {
+            c->prof_ms[k] = 0;
+            c->prof_n[k] = 0;
+        }
+    return PMX_OK;
+}
+
+extern "C" int pmx_ctx_profile_read(pmx_ctx* c, double* ms, int64_t* n) {
+    if (!c || !ms || !n) return set_err(c, PMX_ERR_INVALID, "null argument");
+    prof_collect(c);
+    for (int k = 0; k < 4; ++k) {
+        ms[k] = c->prof_ms[k];
+        n[k] = c->prof_n[k];
+    }
     return PMX_OK;
 }
 
@@ -237,10 +310,10 @@ extern "C" int pmx_field_create(pmx_ctx* c, int64_t nfft, int32_t nfc, int32_t b
     f->batch = batch;
     f->precision = precision;
     size_t bytes = (size_t)batch * nfc * nfft * 2 * sizeof(cpx);
-    cudaError_t e = cudaMalloc(&f->data, bytes);
+    cudaError_t e = cudaMallocAsync(&f->data, bytes, c->stream);
     if (e != cudaSuccess) {
         delete f;
-        return set_err(c, PMX_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return set_err(c, PMX_ERR_CUDA, "cudaMallocAsync of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     }
     *out = f;
     return PMX_OK;
@@ -249,8 +322,7 @@ extern "C" int pmx_field_create(pmx_ctx* c, int64_t nfft, int32_t nfc, int32_t b
 extern "C" void pmx_field_destroy(pmx_devfield* f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
-    cudaStreamSynchronize(f->ctx->stream);
-    cudaFree(f->data);
+    cudaFreeAsync(f->data, f->ctx->stream);
     delete f;
 }
 
@@ -385,6 +457,21 @@ extern "C" int pmx_field_broadcast(pmx_devfield* dst, const pmx_devfield* src) {
 
 // ---------------------------------------------------------------------------
 // plans
+// dst[col][k1*N2 + k2] = src[col][k1 + N1*k2]; *any |= (some element is non-zero)
+__global__ void __launch_bounds__(256) pmx_k_permute(const double* __restrict__ src, double* __restrict__ dst,
+                                                     int log2N1, int log2N2, int nfc, int* any) {
+    const size_t N = (size_t)1 << (log2N1 + log2N2), total = N * nfc;
+    int nz = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t col = i >> (log2N1 + log2N2), o = i & (N - 1);
+        const size_t k1 = o >> log2N2, k2 = o & (((size_t)1 << log2N2) - 1);
+        const double v = src[col * N + k1 + (k2 << log2N1)];
+        nz |= (v != 0.0);
+        dst[i] = v;
+    }
+    if (any && __any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(any, 1);
+}
+
 static void fill_plates(const pmx_fiber_desc& d, int sets, const double* db0, const double* theta,
                         const double* epsilon, std::vector<PlateConst>& out) {
     const int np = d.nplates;
@@ -441,8 +528,9 @@ extern "C" int pmx_plan_set_plates(pmx_plan* p, int32_t sets, const double* db0,
     std::vector<PlateConst> h;
     fill_plates(p->d, sets, db0, theta, epsilon, h);
     if (p->plates == nullptr || sets != p->fc.plate_sets) {
-        if (p->plates) CK(c, cudaFree(p->plates));
-        CK(c, cudaMalloc(&p->plates, h.size() * sizeof(PlateConst)));
+        if (p->plates) CK(c, cudaFreeAsync(p->plates, c->stream));
+        p->plates = nullptr;
+        CK(c, cudaMallocAsync(&p->plates, h.size() * sizeof(PlateConst), c->stream));
     }
     p->fc.plate_sets = sets;
     CK(c, cudaMemcpyAsync(p->plates, h.data(), h.size() * sizeof(PlateConst), cudaMemcpyHostToDevice, c->stream));
@@ -453,13 +541,13 @@ extern "C" int pmx_plan_set_plates(pmx_plan* p, int32_t sets, const double* db0,
 extern "C" void pmx_plan_destroy(pmx_plan* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
-    cudaFree(p->betat_p);
-    cudaFree(p->db1_p);
-    cudaFree(p->plates);
-    cudaFree(p->ctl);
-    cudaFree(p->trace_dz);
-    cudaFree(p->trace_ntrunk);
+    cudaStream_t st = p->ctx->stream;
+    if (p->betat_p) cudaFreeAsync(p->betat_p, st);
+    if (p->db1_p) cudaFreeAsync(p->db1_p, st);
+    if (p->plates) cudaFreeAsync(p->plates, st);
+    if (p->ctl) cudaFreeAsync(p->ctl, st);
+    if (p->trace_dz) cudaFreeAsync(p->trace_dz, st);
+    if (p->trace_ntrunk) cudaFreeAsync(p->trace_ntrunk, st);
     delete p;
 }
 
@@ -530,52 +618,55 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     f.spm = d->fls[2] ? 1 : 0;
     f.manakov = d->manakov ? 1 : 0;
     f.plate_sets = d->plate_sets;
-    // Jones product needed unless every plate is the identity with zero birefringence
-    bool pmd = false;
-    const size_t npl = (size_t)d->plate_sets * d->nplates;
-    for (size_t i = 0; i < npl && !pmd; ++i)
-        if ((d->theta && d->theta[i] != 0.0) || (d->epsilon && d->epsilon[i] != 0.0) || (d->db0 && d->db0[i] != 0.0))
-            pmd = true;
+    // Without the 'p' flag the front-end passes identity plates and db1 = 0 (fiber.m:290-298):
+    // the Jones product is skipped altogether.
+    f.pmd = d->fls[1] ? 1 : 0;
     const size_t N = (size_t)d->nfft;
-    if (d->db1)
-        for (size_t i = 0; i < N * d->nfc && !pmd; ++i)
-            if (d->db1[i] != 0.0) pmd = true;
-    f.pmd = pmd ? 1 : 0;
-    bool gvd = false;
-    for (size_t i = 0; i < N * d->nfc && !gvd; ++i)
-        if (d->betat[i] != 0.0) gvd = true;
-    f.gvd_any = gvd ? 1 : 0;
     p->single_step = std::isinf(d->dphimaxt) && d->dzmaxt >= d->length;
 
-    // permuted dispersion vectors: bin k1 + N1*k2 -> position k1*N2 + k2
+    // dispersion vectors, permuted on the device: bin k1 + N1*k2 -> position k1*N2 + k2
     {
-        std::vector<double> tmp(N * d->nfc);
-        const int N1 = p->N1, N2 = p->N2;
-        auto permute = [&](const double* src) {
-            for (int col = 0; col < d->nfc; ++col) {
-                const double* s = src + (size_t)col * N;
-                double* t = tmp.data() + (size_t)col * N;
-                for (int k2 = 0; k2 < N2; ++k2)
-                    for (int k1 = 0; k1 < N1; ++k1) t[(size_t)k1 * N2 + k2] = s[(size_t)k1 + (size_t)N1 * k2];
-            }
-        };
-        cudaError_t e = cudaMalloc(&p->betat_p, tmp.size() * sizeof(double));
+        const size_t bytes = N * d->nfc * sizeof(double);
+        double* raw = nullptr;
+        int* d_any = nullptr;
+        cudaError_t e = cudaMallocAsync(&p->betat_p, bytes, c->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&raw, bytes, c->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&d_any, sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_any, 0, sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(raw, d->betat, bytes, cudaMemcpyHostToDevice, c->stream);
+        const int blocks = (int)std::min<size_t>((N * d->nfc + 255) / 256, 148 * 16);
         if (e == cudaSuccess) {
-            permute(d->betat);
-            e = cudaMemcpy(p->betat_p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice);
+            pmx_k_permute<<<blocks, 256, 0, c->stream>>>(raw, p->betat_p, p->log2N1, p->log2N2, d->nfc, d_any);
+            c->launches++;
+            e = cudaGetLastError();
         }
-        if (e == cudaSuccess && pmd) {
-            e = cudaMalloc(&p->db1_p, tmp.size() * sizeof(double));
+        int any = 1;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&any, d_any, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && f.pmd) {
+            e = cudaMallocAsync(&p->db1_p, bytes, c->stream);
             if (e == cudaSuccess) {
-                if (d->db1) permute(d->db1); else std::fill(tmp.begin(), tmp.end(), 0.0);
-                e = cudaMemcpy(p->db1_p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice);
+                if (d->db1) {
+                    // raw is reused: the copy is stream-ordered after the betat permute
+                    e = cudaMemcpyAsync(raw, d->db1, bytes, cudaMemcpyHostToDevice, c->stream);
+                    if (e == cudaSuccess) {
+                        pmx_k_permute<<<blocks, 256, 0, c->stream>>>(raw, p->db1_p, p->log2N1, p->log2N2, d->nfc, nullptr);
+                        c->launches++;
+                        e = cudaGetLastError();
+                    }
+                } else {
+                    e = cudaMemsetAsync(p->db1_p, 0, bytes, c->stream);
+                }
             }
         }
-        if (e == cudaSuccess) e = cudaMalloc(&p->ctl, (size_t)d->batch * sizeof(StepCtl));
+        if (e == cudaSuccess) e = cudaMallocAsync(&p->ctl, (size_t)d->batch * sizeof(StepCtl), c->stream);
+        if (raw) cudaFreeAsync(raw, c->stream);
+        if (d_any) cudaFreeAsync(d_any, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // host vectors may go away; `any` is valid
         if (e != cudaSuccess) {
             pmx_plan_destroy(p);
             return set_err(c, PMX_ERR_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
         }
+        f.gvd_any = any ? 1 : 0;
     }
     int rc = pmx_plan_set_plates(p, d->plate_sets, d->db0, d->theta, d->epsilon);
     if (rc) {
@@ -612,14 +703,14 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     // optional schedule trace
     int want_cap = (out && out->trace_dz && out->trace_ntrunk && out->trace_cap > 0) ? out->trace_cap : 0;
     if (want_cap != p->trace_cap) {
-        if (p->trace_dz) cudaFree(p->trace_dz);
-        if (p->trace_ntrunk) cudaFree(p->trace_ntrunk);
+        if (p->trace_dz) cudaFreeAsync(p->trace_dz, c->stream);
+        if (p->trace_ntrunk) cudaFreeAsync(p->trace_ntrunk, c->stream);
         p->trace_dz = nullptr;
         p->trace_ntrunk = nullptr;
         p->trace_cap = 0;
         if (want_cap) {
-            CK(c, cudaMalloc(&p->trace_dz, (size_t)batch * want_cap * sizeof(double)));
-            CK(c, cudaMalloc(&p->trace_ntrunk, (size_t)batch * want_cap * sizeof(int)));
+            CK(c, cudaMallocAsync(&p->trace_dz, (size_t)batch * want_cap * sizeof(double), c->stream));
+            CK(c, cudaMallocAsync(&p->trace_ntrunk, (size_t)batch * want_cap * sizeof(int), c->stream));
             p->trace_cap = want_cap;
         }
     }
@@ -661,6 +752,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     CK(c, cudaMemsetAsync(p->ctl, 0, (size_t)batch * sizeof(StepCtl), c->stream));
     {
         dim3 g(148 * 2, batch * nfc);
+        ProfScope ps(c, 3);
         pmx_k_init<<<g, 256, 256, c->stream>>>(pa, p->fc);
         c->launches++;
         CK(c, cudaGetLastError());
@@ -670,10 +762,11 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     long total_steps = 0;
     for (;;) {
         for (int s = 0; s < chunk; ++s) {
-            p->tA->passA(gA, c->stream, pA, p->fc);
-            p->tB->passB(gB, c->stream, pB, p->fc);
-            p->tA->passC(gA, c->stream, pA, p->fc);
+            { ProfScope ps(c, 0); p->tA->passA(gA, c->stream, pA, p->fc); }
+            { ProfScope ps(c, 1); p->tB->passB(gB, c->stream, pB, p->fc); }
+            { ProfScope ps(c, 2); p->tA->passC(gA, c->stream, pA, p->fc); }
             c->launches += 3;
+            if (c->profile && c->ev_used > 4096) prof_collect(c);
         }
         total_steps += chunk;
         CK(c, cudaGetLastError());

@@ -85,6 +85,14 @@ __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_double2(a.x + b.
 __device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ cpx cscale(cpx a, double s) { return make_double2(a.x * s, a.y * s); }
 
+// One Sa (both polarizations, 32 B) per 256-bit global access (LDG.E.256 / STG.E.256 on sm_100a).
+__device__ __forceinline__ void ld_sa(const cpx* p, cpx& x, cpx& y) {
+    asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x.x), "=d"(x.y), "=d"(y.x), "=d"(y.y) : "l"(p));
+}
+__device__ __forceinline__ void st_sa(cpx* p, cpx x, cpx y) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y) : "memory");
+}
+
 // |ux|^2+|uy|^2 in the reference's order, no FMA contraction (fiber.m:694)
 __device__ __forceinline__ double power_ref(cpx x, cpx y) {
     double p = __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y));

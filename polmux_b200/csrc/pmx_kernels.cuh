@@ -167,7 +167,8 @@ static __global__ void __launch_bounds__(256) pmx_k_init(PassParams p, FiberCons
     const cpx* fld = p.field + (size_t)bc * N * 2;
     unsigned long long vmax = 0ull;
     for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
-        cpx x = fld[2 * n], y = fld[2 * n + 1];
+        cpx x, y;
+        ld_sa(fld + 2 * n, x, y);
         unsigned long long key = pmx_pow_key(power_ref(x, y));
         vmax = key > vmax ? key : vmax;
     }
@@ -182,7 +183,8 @@ struct PmxSmem {
     static constexpr int BASE = ((2 * pmx_pad(L) + 7) / 8) * 8;
     static constexpr int OFF = (GROUP > 1) ? ((8 / GROUP) > 0 ? (8 / GROUP) : 1) : 0;
     static constexpr int STRIDE = BASE + OFF;
-    static constexpr size_t bytes(int groups) { return (size_t)groups * STRIDE * sizeof(cpx); }
+    // + [groups][8] per-row / per-column four-step twiddle factors
+    static constexpr size_t bytes(int groups) { return ((size_t)groups * STRIDE + (size_t)groups * 8) * sizeof(cpx); }
 };
 
 __device__ __forceinline__ cpx pmx_twiddle4(const PassParams& p, unsigned m) {
@@ -194,7 +196,7 @@ __device__ __forceinline__ cpx pmx_twiddle4(const PassParams& p, unsigned m) {
 // ---------------------------------------------------------------------------
 // pass A: CPC adjacent columns per CTA, thread (cl fastest, t)
 template <int L, int CPC>
-__global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passA(PassParams p, FiberConst f) {
+__global__ void __launch_bounds__(CPC * (L / 8), 512 / (CPC * (L / 8))) pmx_k_passA(PassParams p, FiberConst f) {
     constexpr int T = L / 8;
     extern __shared__ cpx smem[];
     const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
@@ -208,9 +210,7 @@ __global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passA(PassParams p, Fiber
     cpx x[8], y[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const cpx* a = base + (size_t)(t + q * T) * rs;
-        x[q] = a[0];
-        y[q] = a[1];
+        ld_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
     }
     // ---- nonlinear step, fiber.m:832-851
     if (f.spm) {
@@ -237,20 +237,28 @@ __global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passA(PassParams p, Fiber
     cpx* sx = smem + cl * PmxSmem<L, CPC>::STRIDE;
     cpx* sy = sx + pmx_pad(L);
     CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+    // four-step twiddle W_N^(n2*k1), k1 = t + q*T:  W_N^(n2*t) * g[q],  g[q] = exp(-2*pi*i*n2*q/(8*N2))
+    // (per-column constants, computed once per CTA; the per-thread base is one table look-up)
+    cpx* gtab = smem + CPC * PmxSmem<L, CPC>::STRIDE;  // [CPC][8]
+    if (threadIdx.x < CPC * 8) {
+        const int c2 = threadIdx.x >> 3, q = threadIdx.x & 7;
+        double s, cs;
+        sincospi(-2.0 * (double)((blockIdx.x * CPC + c2) * q) / (double)(8 * p.N2), &s, &cs);
+        gtab[c2 * 8 + q] = make_double2(cs, s);
+    }
+    __syncthreads();
+    const cpx wb = pmx_twiddle4(p, (unsigned)n2 * (unsigned)t);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const int k1 = t + q * T;
-        cpx w = pmx_twiddle4(p, (unsigned)n2 * (unsigned)k1);
-        cpx* a = base + (size_t)k1 * rs;
-        a[0] = cmul(x[q], w);
-        a[1] = cmul(y[q], w);
+        const cpx w = cmul(wb, gtab[cl * 8 + q]);
+        st_sa(base + (size_t)(t + q * T) * rs, cmul(x[q], w), cmul(y[q], w));
     }
 }
 
 // ---------------------------------------------------------------------------
 // pass B: RPC rows per CTA, thread (t fastest, rl)
 template <int L, int RPC>
-__global__ void __launch_bounds__(RPC * (L / 8)) pmx_k_passB(PassParams p, FiberConst f) {
+__global__ void __launch_bounds__(RPC * (L / 8), 512 / (RPC * (L / 8))) pmx_k_passB(PassParams p, FiberConst f) {
     constexpr int T = L / 8;
     extern __shared__ cpx smem[];
     const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
@@ -263,9 +271,7 @@ __global__ void __launch_bounds__(RPC * (L / 8)) pmx_k_passB(PassParams p, Fiber
     cpx x[8], y[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const cpx* a = base + (size_t)(t + q * T) * 2;
-        x[q] = a[0];
-        y[q] = a[1];
+        ld_sa(base + (size_t)(t + q * T) * 2, x[q], y[q]);
     }
     cpx* sx = smem + rl * PmxSmem<L, RPC>::STRIDE;
     cpx* sy = sx + pmx_pad(L);
@@ -345,20 +351,28 @@ __global__ void __launch_bounds__(RPC * (L / 8)) pmx_k_passB(PassParams p, Fiber
     }
 
     CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
+    // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T:  conj(W_N^(k1*t) * g[q]),
+    // g[q] = exp(-2*pi*i*k1*q/(8*N1)) per row
+    cpx* gtab = smem + RPC * PmxSmem<L, RPC>::STRIDE;  // [RPC][8]
+    if (threadIdx.x < RPC * 8) {
+        const int r2 = threadIdx.x >> 3, q = threadIdx.x & 7;
+        double s, cs;
+        sincospi(-2.0 * (double)((blockIdx.x * RPC + r2) * q) / (double)(8 * p.N1), &s, &cs);
+        gtab[r2 * 8 + q] = make_double2(cs, s);
+    }
+    __syncthreads();
+    const cpx wb = pmx_twiddle4(p, (unsigned)k1 * (unsigned)t);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const int n2 = t + q * T;
-        cpx w = pmx_twiddle4(p, (unsigned)n2 * (unsigned)k1);
-        cpx* a = base + (size_t)n2 * 2;
-        a[0] = cmulc(x[q], w);
-        a[1] = cmulc(y[q], w);
+        const cpx w = cmul(wb, gtab[rl * 8 + q]);
+        st_sa(base + (size_t)(t + q * T) * 2, cmulc(x[q], w), cmulc(y[q], w));
     }
 }
 
 // ---------------------------------------------------------------------------
 // pass C: like pass A, inverse transform + attenuation + max reduction + step control
 template <int L, int CPC>
-__global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passC(PassParams p, FiberConst f) {
+__global__ void __launch_bounds__(CPC * (L / 8), 512 / (CPC * (L / 8))) pmx_k_passC(PassParams p, FiberConst f) {
     constexpr int T = L / 8;
     extern __shared__ cpx smem[];
     const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
@@ -372,9 +386,7 @@ __global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passC(PassParams p, Fiber
     cpx x[8], y[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const cpx* a = base + (size_t)(t + q * T) * rs;
-        x[q] = a[0];
-        y[q] = a[1];
+        ld_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
     }
     cpx* sx = smem + cl * PmxSmem<L, CPC>::STRIDE;
     cpx* sy = sx + pmx_pad(L);
@@ -387,9 +399,7 @@ __global__ void __launch_bounds__(CPC * (L / 8)) pmx_k_passC(PassParams p, Fiber
         y[q] = cscale(y[q], sc);
         unsigned long long key = pmx_pow_key(power_ref(x[q], y[q]));
         vmax = key > vmax ? key : vmax;
-        cpx* a = base + (size_t)(t + q * T) * rs;
-        a[0] = x[q];
-        a[1] = y[q];
+        st_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
     }
     pmx_block_max_and_ctl(vmax, smem, c, col, gridDim.x * f.nfc, f, false, b, p.trace_dz, p.trace_ntrunk);
 }

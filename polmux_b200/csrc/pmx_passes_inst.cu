@@ -15,6 +15,10 @@ constexpr int RPC = (T >= 128) ? 1 : (128 / T);
 
 cudaError_t setup() {
     cudaError_t e;
+    // ask for the largest shared-memory carveout so that several CTAs fit per SM
+    cudaFuncSetAttribute(pmx_k_passA<L, CPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(pmx_k_passB<L, RPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(pmx_k_passC<L, CPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     e = cudaFuncSetAttribute(pmx_k_passA<L, CPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)PmxSmem<L, CPC>::bytes(CPC));
     if (e != cudaSuccess) return e;

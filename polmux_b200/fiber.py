@@ -87,6 +87,32 @@ def flag_to_fls(flag: str, nfc: int, x):
     return (g, p, s, xx), float(_get(x, 'dphimax')), float(_get(x, 'dzmax'))
 
 
+_DISP_CACHE = {}
+
+
+def _dispersion_vectors(G, nfft, nfc, beta1, beta2, b30, dgdrms, pflag):
+    """betat(omega), db1(omega) of fiber.m:350-362.  The vectors depend only on a handful of
+    scalars and the FN grid, so successive spans with the same fiber reuse them."""
+    key = (nfft, G.NSYMB, G.NT, float(G.SYMBOLRATE), tuple(np.asarray(beta1).tolist()),
+           tuple(np.asarray(beta2).tolist()), float(b30), float(dgdrms), int(pflag))
+    hit = _DISP_CACHE.get(key)
+    if hit is not None:
+        return hit
+    omega = 2 * math.pi * G.SYMBOLRATE * np.asarray(G.FN, dtype=np.float64)  # :352
+    betat = np.zeros((nfft, nfc))
+    db1 = np.zeros((nfft, nfc))
+    for k in range(nfc):                                                    # :354-362
+        betat[:, k] = omega * beta1[k] + 0.5 * omega ** 2 * beta2[k] + omega ** 3 * b30 / 6
+        if pflag:
+            db1[:, k] = dgdrms * omega
+    betat.setflags(write=False)
+    db1.setflags(write=False)
+    if len(_DISP_CACHE) > 8:
+        _DISP_CACHE.clear()
+    _DISP_CACHE[key] = (betat, db1)
+    return betat, db1
+
+
 def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> FiberSetup:
     """Host part of fiber(): parameter checks, PMD plates, unit conversions."""
     G = GSTATE
@@ -162,13 +188,7 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
     beta2 = (b20 + b30 * w_i0) * fls[0]                                     # :330-332
     dch = disp + slope * (lams - lam)                                       # :336
 
-    omega = 2 * math.pi * G.SYMBOLRATE * np.asarray(G.FN, dtype=np.float64)  # :352
-    betat = np.zeros((nfft, nfc))
-    db1 = np.zeros((nfft, nfc))
-    for k in range(nfc):                                                    # :354-362
-        betat[:, k] = omega * beta1[k] + 0.5 * omega ** 2 * beta2[k] + omega ** 3 * b30 / 6
-        if fls[1]:
-            db1[:, k] = dgdrms * omega
+    betat, db1 = _dispersion_vectors(G, nfft, nfc, beta1, beta2, b30, dgdrms, fls[1])
     return FiberSetup(nfft=nfft, nfc=nfc, fls=fls, dphimaxt=dphimaxt, dzmaxt=dzmaxt, length=length,
                       alphalin=alphalin, gam=gam, betat=betat, db1=db1, manakov=manakov,
                       nplates=nplates, brf=brf, isv=isv, isy=isy, b1=b1, dch=dch)
