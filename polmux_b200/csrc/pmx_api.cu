@@ -13,6 +13,7 @@
 #include "../../include/polmux_ssfm.h"
 #include "pmx_kernels.cuh"
 #include "pmx_launch.h"
+#include <cudaTypedefs.h>
 
 // ---------------------------------------------------------------------------
 extern const PmxLaunchTable pmx_table_64, pmx_table_128, pmx_table_256, pmx_table_512, pmx_table_1024,
@@ -54,6 +55,8 @@ void pmx_fill_stage_twiddles(int L, cpx* out) {
 
 // ---------------------------------------------------------------------------
 static thread_local std::string g_tls_error;
+struct pmx_ctx;
+static int set_err(pmx_ctx* ctx, int code, const char* fmt, ...);
 
 struct StageTw {
     cpx* dev = nullptr;
@@ -70,7 +73,10 @@ struct pmx_ctx {
     std::string error;
     std::map<int, StageTw> stage_tw;          // by L
     std::map<long long, FourStepTw> four_tw;  // by N
-    std::map<int, bool> setup_done;
+    struct Occ { int a = 0, b = 0, c = 0; };
+    std::map<int, Occ> setup_done;  // by L: resident CTAs per SM of passes A, B, C
+    int sm_count = 148;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     StepCtl* h_ctl = nullptr;  // pinned readback buffer
     int h_ctl_cap = 0;
     int64_t launches = 0;
@@ -124,7 +130,53 @@ struct pmx_devfield {
     int64_t nfft;
     int32_t nfc, batch, precision;
     cpx* data;  // [batch*nfc][nfft][2]
+    int N1 = 0, N2 = 0;
+    bool has_maps = false;
+    CUtensorMap map_cols;  // passes A, C: box {gAC*4 doubles, <=256 rows, 1}
+    CUtensorMap map_rows;  // pass B: 128-byte lines, box {16 doubles, <=256 lines, 1}
 };
+
+static int ilog2_exact(int64_t v) {
+    int l = 0;
+    while ((1ll << l) < v) ++l;
+    return ((1ll << l) == v) ? l : -1;
+}
+
+// Tensor maps over a resident field for the four-step split N = N1*N2 (see pmx_tma.cuh).
+static int build_maps(pmx_ctx* c, pmx_devfield* f) {
+    const int lg = ilog2_exact(f->nfft);
+    if (lg < 12 || lg > 24) return PMX_OK;  // not a size the SSFM kernels take; other ops still work
+    f->N1 = 1 << (lg / 2);
+    f->N2 = 1 << (lg - lg / 2);
+    const PmxLaunchTable* tA = pmx_get_table(f->N1);
+    const PmxLaunchTable* tB = pmx_get_table(f->N2);
+    if (!tA || !tB) return PMX_OK;
+    const cuuint64_t BC = (cuuint64_t)f->batch * f->nfc, N = (cuuint64_t)f->nfft;
+    const cuuint32_t ones[3] = {1, 1, 1};
+    {
+        const int G = tA->gAC;
+        cuuint64_t dims[3] = {(cuuint64_t)f->N2 * 4, (cuuint64_t)f->N1, BC};
+        cuuint64_t strides[2] = {(cuuint64_t)f->N2 * 32, N * 32};
+        cuuint32_t box[3] = {(cuuint32_t)G * 4, (cuuint32_t)std::min(f->N1, 256), 1};
+        CUtensorMapSwizzle sw = G == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : (G == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+        CUresult r = c->encode(&f->map_cols, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, f->data, dims, strides, box, ones,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_err(c, PMX_ERR_CUDA, "cuTensorMapEncodeTiled(cols) failed: CUresult %d", (int)r);
+    }
+    {
+        const int lines = tB->gB * f->N2 / 4;
+        cuuint64_t dims[3] = {16, N / 4, BC};
+        cuuint64_t strides[2] = {128, N * 32};
+        cuuint32_t box[3] = {16, (cuuint32_t)std::min(lines, 256), 1};
+        CUresult r = c->encode(&f->map_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, f->data, dims, strides, box, ones,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_err(c, PMX_ERR_CUDA, "cuTensorMapEncodeTiled(rows) failed: CUresult %d", (int)r);
+    }
+    f->has_maps = true;
+    return PMX_OK;
+}
 
 struct pmx_plan {
     pmx_ctx* ctx;
@@ -195,6 +247,17 @@ extern "C" int pmx_ctx_create(pmx_ctx** out, int device_id) {
         delete c;
         return set_err(nullptr, PMX_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
                        device_id, prop.major, prop.minor);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t ee = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (ee != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            delete c;
+            return set_err(nullptr, PMX_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        }
+        c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     }
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     {  // keep freed blocks cached in the stream-ordered pool: fiber() after fiber() reuses them
@@ -314,6 +377,12 @@ extern "C" int pmx_field_create(pmx_ctx* c, int64_t nfft, int32_t nfc, int32_t b
     if (e != cudaSuccess) {
         delete f;
         return set_err(c, PMX_ERR_CUDA, "cudaMallocAsync of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    int rc = build_maps(c, f);
+    if (rc != PMX_OK) {
+        cudaFreeAsync(f->data, c->stream);
+        delete f;
+        return rc;
     }
     *out = f;
     return PMX_OK;
@@ -551,12 +620,6 @@ extern "C" void pmx_plan_destroy(pmx_plan* p) {
     delete p;
 }
 
-static int ilog2_exact(int64_t v) {
-    int l = 0;
-    while ((1ll << l) < v) ++l;
-    return ((1ll << l) == v) ? l : -1;
-}
-
 extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** out) {
     if (!c || !d || !out) return set_err(c, PMX_ERR_INVALID, "pmx_plan_create: null argument");
     *out = nullptr;
@@ -594,13 +657,15 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
         return set_err(c, PMX_ERR_UNSUPPORTED, "no kernel built for FFT factors %d x %d", 1 << (lg / 2), 1 << (lg - lg / 2));
     }
     for (const PmxLaunchTable* t : {p->tA, p->tB}) {
-        if (!c->setup_done[t->L]) {
-            cudaError_t e = t->setup();
-            if (e != cudaSuccess) {
+        if (!c->setup_done.count(t->L)) {
+            pmx_ctx::Occ o;
+            cudaError_t e = t->setup(&o.a, &o.b, &o.c);
+            if (e != cudaSuccess || o.a < 1 || o.b < 1 || o.c < 1) {
                 delete p;
-                return set_err(c, PMX_ERR_CUDA, "kernel attribute setup (L=%d) failed: %s", t->L, cudaGetErrorString(e));
+                return set_err(c, PMX_ERR_CUDA, "kernel setup (L=%d) failed: %s (resident CTAs %d/%d/%d)", t->L,
+                               cudaGetErrorString(e), o.a, o.b, o.c);
             }
-            c->setup_done[t->L] = true;
+            c->setup_done[t->L] = o;
         }
     }
     FiberConst& f = p->fc;
@@ -757,14 +822,18 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
         c->launches++;
         CK(c, cudaGetLastError());
     }
-    const dim3 gA(p->N2 / p->tA->cpc, batch * nfc), gB(p->N1 / p->tB->rpc, batch * nfc);
+    if (!fld->has_maps) return set_err(c, PMX_ERR_INVALID, "field has no tensor maps (unsupported nfft)");
+    const pmx_ctx::Occ oA = c->setup_done[p->N1], oB = c->setup_done[p->N2];
+    const int tilesAC = (p->N2 / p->tA->gAC) * batch * nfc, tilesB = (p->N1 / p->tB->gB) * batch * nfc;
+    const int gA = std::min(tilesAC, c->sm_count * oA.a), gB = std::min(tilesB, c->sm_count * oB.b),
+              gC = std::min(tilesAC, c->sm_count * oA.c);
     int chunk = p->single_step ? 1 : 8;
     long total_steps = 0;
     for (;;) {
         for (int s = 0; s < chunk; ++s) {
-            { ProfScope ps(c, 0); p->tA->passA(gA, c->stream, pA, p->fc); }
-            { ProfScope ps(c, 1); p->tB->passB(gB, c->stream, pB, p->fc); }
-            { ProfScope ps(c, 2); p->tA->passC(gA, c->stream, pA, p->fc); }
+            { ProfScope ps(c, 0); p->tA->passA(gA, c->stream, pA, p->fc, fld->map_cols); }
+            { ProfScope ps(c, 1); p->tB->passB(gB, c->stream, pB, p->fc, fld->map_rows); }
+            { ProfScope ps(c, 2); p->tA->passC(gC, c->stream, pA, p->fc, fld->map_cols); }
             c->launches += 3;
             if (c->profile && c->ev_used > 4096) prof_collect(c);
         }

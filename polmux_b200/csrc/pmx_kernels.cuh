@@ -9,6 +9,7 @@
 //                    of a realization runs nextstep + checkstep for the next step
 #pragma once
 #include "pmx_fft.cuh"
+#include "pmx_tma.cuh"
 
 // ---------------------------------------------------------------------------
 // step control (one thread)
@@ -127,7 +128,7 @@ __device__ __forceinline__ unsigned long long pmx_pow_key(double pw) {
 
 // Block-wide max (warp shuffles, then one atomicMax per CTA); the last CTA of the
 // realization (ticket) runs the step control.
-__device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, cpx* smem, StepCtl* c, int col,
+__device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, void* scratch, StepCtl* c, int col,
                                                       unsigned total_ctas, const FiberConst& f,
                                                       bool first, int b, double* trace_dz,
                                                       int* trace_ntrunk) {
@@ -136,7 +137,7 @@ __device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, cp
         unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other > key ? other : key;
     }
-    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem);
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(scratch);  // >= 32 x 8 B
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarp = (blockDim.x + 31) >> 5;
@@ -183,9 +184,29 @@ struct PmxSmem {
     static constexpr int BASE = ((2 * pmx_pad(L) + 7) / 8) * 8;
     static constexpr int OFF = (GROUP > 1) ? ((8 / GROUP) > 0 ? (8 / GROUP) : 1) : 0;
     static constexpr int STRIDE = BASE + OFF;
-    // + [groups][8] per-row / per-column four-step twiddle factors
-    static constexpr size_t bytes(int groups) { return ((size_t)groups * STRIDE + (size_t)groups * 8) * sizeof(cpx); }
 };
+
+// Shared-memory plan of a pass CTA working on G rows (pass B) or G columns (passes A, C) of
+// length L.  PF: the next tile is prefetched by TMA into its own landing buffer while the
+// current one is computed; !PF (long rows): the tile lands in the exchange buffer itself and
+// the next load is issued as soon as the last exchange of the current tile is over.
+template <int L, int G, bool PF>
+struct PassSmem {
+    static constexpr int T = L / 8;
+    static constexpr int THREADS = G * T;
+    static constexpr int TILE_BYTES = G * L * 32;
+    static constexpr int WORK_BYTES = G * PmxSmem<L, G>::STRIDE * 16;
+    static constexpr int WORK_OFF = PF ? ((TILE_BYTES + 1023) / 1024) * 1024 : 0;
+    static constexpr int GTAB_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;
+    static constexpr int RED_OFF = GTAB_OFF + G * 8 * 16;
+    static constexpr int MBAR_OFF = RED_OFF + 32 * 8;
+    static constexpr int TOTAL = MBAR_OFF + 16 + 1024;  // + slack to align the base to 1024 B
+    static_assert(WORK_BYTES >= TILE_BYTES, "exchange buffer must hold a landed tile");
+};
+
+__device__ __forceinline__ unsigned char* pmx_align1024(unsigned char* p) {
+    return p + ((1024u - (pmx_smem_u32(p) & 1023u)) & 1023u);
+}
 
 __device__ __forceinline__ cpx pmx_twiddle4(const PassParams& p, unsigned m) {
     cpx h = __ldg(&p.tw_hi[m >> p.lo_bits]);
@@ -193,213 +214,328 @@ __device__ __forceinline__ cpx pmx_twiddle4(const PassParams& p, unsigned m) {
     return cmul(h, l);
 }
 
+#define PMX_MINB(threads, pf) ((pf) ? ((384 / (threads)) > 0 ? (384 / (threads)) : 1) : ((512 / (threads)) > 0 ? (512 / (threads)) : 1))
+
 // ---------------------------------------------------------------------------
-// pass A: CPC adjacent columns per CTA, thread (cl fastest, t)
-template <int L, int CPC>
-__global__ void __launch_bounds__(CPC * (L / 8), 512 / (CPC * (L / 8))) pmx_k_passA(PassParams p, FiberConst f) {
-    constexpr int T = L / 8;
-    extern __shared__ cpx smem[];
-    const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
-    const StepCtl* c = &p.ctl[b];
-    if (c->state >= PMX_ST_DONE) return;
-    const int cl = threadIdx.x % CPC, t = threadIdx.x / CPC;
-    const int n2 = blockIdx.x * CPC + cl;
+// pass A: G adjacent columns per tile, thread (cl fastest, t).  Persistent CTAs walk the
+// tile list (tile = realization-column bc, column group); finished realizations are skipped.
+template <int L, int G, bool PF>
+__global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
+    pmx_k_passA(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
+    using S = PassSmem<L, G, PF>;
+    constexpr int T = L / 8, PITCH = G * 32, MASK = PITCH / 16 - 1;
+    extern __shared__ unsigned char smraw[];
+    unsigned char* sm = pmx_align1024(smraw);
+    unsigned char* in = sm;  // PF: landing buffer at 0; !PF: WORK_OFF == 0, lands in the exchange buffer
+    cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
+    cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
+    const int tiles_per_bc = p.N2 / G, total = tiles_per_bc * p.batch * f.nfc;
+    const int cl = threadIdx.x % G, t = threadIdx.x / G;
     const size_t N = (size_t)p.N1 * p.N2;
-    cpx* base = p.field + ((size_t)bc * N + n2) * 2;
     const size_t rs = (size_t)p.N2 * 2;  // cpx per n1 row
-    cpx x[8], y[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        ld_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
-    }
-    // ---- nonlinear step, fiber.m:832-851
-    if (f.spm) {
-        const double gamleff = __dmul_rn(f.gam[col], c->leff);
-        const double ngl = -gamleff;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            double pw = power_ref(x[q], y[q]);
-            double s, cs;
-            sincos(__dmul_rn(ngl, pw), &s, &cs);
-            cpx e = make_double2(cs, s);
-            x[q] = cmul(x[q], e);
-            y[q] = cmul(y[q], e);
-            if (!f.manakov) {
-                double s3 = 2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
-                double sp, cp;
-                sincos(__dmul_rn(gamleff, s3) / 3.0, &sp, &cp);
-                cpx ux = x[q], uy = y[q];
-                x[q] = make_double2(cp * ux.x + sp * uy.x, cp * ux.y + sp * uy.y);
-                y[q] = make_double2(cp * uy.x - sp * ux.x, cp * uy.y - sp * ux.y);
-            }
-        }
-    }
-    cpx* sx = smem + cl * PmxSmem<L, CPC>::STRIDE;
-    cpx* sy = sx + pmx_pad(L);
-    CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
-    // four-step twiddle W_N^(n2*k1), k1 = t + q*T:  W_N^(n2*t) * g[q],  g[q] = exp(-2*pi*i*n2*q/(8*N2))
-    // (per-column constants, computed once per CTA; the per-thread base is one table look-up)
-    cpx* gtab = smem + CPC * PmxSmem<L, CPC>::STRIDE;  // [CPC][8]
-    if (threadIdx.x < CPC * 8) {
-        const int c2 = threadIdx.x >> 3, q = threadIdx.x & 7;
-        double s, cs;
-        sincospi(-2.0 * (double)((blockIdx.x * CPC + c2) * q) / (double)(8 * p.N2), &s, &cs);
-        gtab[c2 * 8 + q] = make_double2(cs, s);
+
+    auto live = [&](int tl) {
+        while (tl < total && p.ctl[(tl / tiles_per_bc) / f.nfc].state >= PMX_ST_DONE) tl += gridDim.x;
+        return tl;
+    };
+    auto issue = [&](int tl) {  // one thread
+        pmx_fence_proxy_async();
+        pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
+        const int bc = tl / tiles_per_bc, c0 = (tl % tiles_per_bc) * G;
+        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
+    };
+    if (threadIdx.x == 0) {
+        pmx_mbar_init(mbar, 1);
+        pmx_fence_mbar_init();
     }
     __syncthreads();
-    const cpx wb = pmx_twiddle4(p, (unsigned)n2 * (unsigned)t);
+    int tile = live(blockIdx.x);
+    if (threadIdx.x == 0 && tile < total) issue(tile);
+    uint32_t phase = 0;
+    while (tile < total) {
+        const int bc = tile / tiles_per_bc, b = bc / f.nfc, col = bc % f.nfc;
+        const int n2 = (tile % tiles_per_bc) * G + cl;
+        const StepCtl* c = &p.ctl[b];
+        cpx x[8], y[8];
+        pmx_mbar_wait(mbar, phase);
+        phase ^= 1u;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const cpx w = cmul(wb, gtab[cl * 8 + q]);
-        st_sa(base + (size_t)(t + q * T) * rs, cmul(x[q], w), cmul(y[q], w));
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
+            x[q] = *reinterpret_cast<const cpx*>(in + off);
+            y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
+        }
+        __syncthreads();
+        const int next = live(tile + gridDim.x);
+        if (PF && threadIdx.x == 0 && next < total) issue(next);
+        // ---- nonlinear step, fiber.m:832-851
+        if (f.spm) {
+            const double gamleff = __dmul_rn(f.gam[col], c->leff);
+            const double ngl = -gamleff;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                double pw = power_ref(x[q], y[q]);
+                double s, cs;
+                sincos(__dmul_rn(ngl, pw), &s, &cs);
+                cpx e = make_double2(cs, s);
+                x[q] = cmul(x[q], e);
+                y[q] = cmul(y[q], e);
+                if (!f.manakov) {
+                    double s3 = 2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
+                    double sp, cp;
+                    sincos(__dmul_rn(gamleff, s3) / 3.0, &sp, &cp);
+                    cpx ux = x[q], uy = y[q];
+                    x[q] = make_double2(cp * ux.x + sp * uy.x, cp * ux.y + sp * uy.y);
+                    y[q] = make_double2(cp * uy.x - sp * ux.x, cp * uy.y - sp * ux.y);
+                }
+            }
+        }
+        cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
+        cpx* sy = sx + pmx_pad(L);
+        CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+        if (!PF && threadIdx.x == 0 && next < total) issue(next);
+        // four-step twiddle W_N^(n2*k1), k1 = t + q*T:  W_N^(n2*t) * g[q],  g[q] = exp(-2*pi*i*n2*q/(8*N2))
+        if (threadIdx.x < G * 8) {
+            const int c2 = threadIdx.x >> 3, q = threadIdx.x & 7;
+            double s, cs;
+            sincospi(-2.0 * (double)(((tile % tiles_per_bc) * G + c2) * q) / (double)(8 * p.N2), &s, &cs);
+            gtab[c2 * 8 + q] = make_double2(cs, s);
+        }
+        __syncthreads();
+        const cpx wb = pmx_twiddle4(p, (unsigned)n2 * (unsigned)t);
+        cpx* base = p.field + ((size_t)bc * N + n2) * 2;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const cpx w = cmul(wb, gtab[cl * 8 + q]);
+            st_sa(base + (size_t)(t + q * T) * rs, cmul(x[q], w), cmul(y[q], w));
+        }
+        tile = next;
+        __syncthreads();  // gtab is rewritten by the next tile
     }
 }
 
 // ---------------------------------------------------------------------------
-// pass B: RPC rows per CTA, thread (t fastest, rl)
-template <int L, int RPC>
-__global__ void __launch_bounds__(RPC * (L / 8), 512 / (RPC * (L / 8))) pmx_k_passB(PassParams p, FiberConst f) {
+// pass B: G rows per tile, thread (t fastest, rl)
+template <int L, int G, bool PF>
+__global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
+    pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
+    using S = PassSmem<L, G, PF>;
     constexpr int T = L / 8;
-    extern __shared__ cpx smem[];
-    const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
-    const StepCtl* c = &p.ctl[b];
-    if (c->state >= PMX_ST_DONE) return;
+    extern __shared__ unsigned char smraw[];
+    unsigned char* sm = pmx_align1024(smraw);
+    unsigned char* in = sm;
+    cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
+    cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
+    const int tiles_per_bc = p.N1 / G, total = tiles_per_bc * p.batch * f.nfc;
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
-    const int k1 = blockIdx.x * RPC + rl;
     const size_t N = (size_t)p.N1 * p.N2;
-    cpx* base = p.field + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
-    cpx x[8], y[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        ld_sa(base + (size_t)(t + q * T) * 2, x[q], y[q]);
-    }
-    cpx* sx = smem + rl * PmxSmem<L, RPC>::STRIDE;
-    cpx* sy = sx + pmx_pad(L);
-    CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+    constexpr int LINES = G * L / 4;  // 128-byte lines per tile
 
-    // ---- linear step in the frequency domain, fiber.m:907-933
-    const int ntrunk = c->ntrunk;
-    if (ntrunk > 0) {
-        const double dz_cur = c->dz_cur;
-        const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
-        if (f.pmd) {
-            const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
-            const PlateConst* pl = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
-            const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k2 = t + q * T;
-                const double d1 = __ldg(&d1p[k2]);
-                // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
-                cpx vx, vy;
-                {
-                    const PlateConst& P = pl[0];
-                    cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                    cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
-                    vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
-                    vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
-                }
-                double e1s, e1c;
-                bool have_e1 = false;
-                for (int k = 0; k < ntrunk; ++k) {
-                    const PlateConst& P = pl[k];
-                    const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
-                    cpx e;
-                    if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
-                        if (!have_e1) {
-                            sincos(-0.5 * d1, &e1s, &e1c);
-                            have_e1 = true;
-                        }
-                        e = cmul(make_double2(e1c, e1s), make_double2(P.h0r, P.h0i));
-                    } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-                        double delta = 0.5 * (d1 + P.db0) * dzb / lcorr;
-                        double s, cs;
-                        sincos(-delta, &s, &cs);
-                        e = make_double2(cs, s);
-                    }
-                    vx = cmul(vx, e);
-                    vy = cmulc(vy, e);
-                    if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
-                        cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
-                        cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
-                        cpx nx = cadd(cmul(c11, vx), cmul(c12, vy));
-                        cpx ny = cadd(cmul(c21, vx), cmul(c22, vy));
-                        vx = nx;
-                        vy = ny;
-                    }
-                }
-                {  // back to the laboratory basis: u = matR * uu  (:931-932)
-                    const PlateConst& P = pl[ntrunk - 1];
-                    cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                    cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
-                    x[q] = cadd(cmul(r11, vx), cmul(r12, vy));
-                    y[q] = cadd(cmul(r21, vx), cmul(r22, vy));
-                }
-            }
-        }
-        if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const double ph = __ldg(&bt[t + q * T]) * dz_cur;
-                double s, cs;
-                sincos(-ph, &s, &cs);
-                cpx e = make_double2(cs, s);
-                x[q] = cmul(x[q], e);
-                y[q] = cmul(y[q], e);
-            }
-        }
-    }
-
-    CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
-    // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T:  conj(W_N^(k1*t) * g[q]),
-    // g[q] = exp(-2*pi*i*k1*q/(8*N1)) per row
-    cpx* gtab = smem + RPC * PmxSmem<L, RPC>::STRIDE;  // [RPC][8]
-    if (threadIdx.x < RPC * 8) {
-        const int r2 = threadIdx.x >> 3, q = threadIdx.x & 7;
-        double s, cs;
-        sincospi(-2.0 * (double)((blockIdx.x * RPC + r2) * q) / (double)(8 * p.N1), &s, &cs);
-        gtab[r2 * 8 + q] = make_double2(cs, s);
+    auto live = [&](int tl) {
+        while (tl < total && p.ctl[(tl / tiles_per_bc) / f.nfc].state >= PMX_ST_DONE) tl += gridDim.x;
+        return tl;
+    };
+    auto issue = [&](int tl) {
+        pmx_fence_proxy_async();
+        pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
+        const int bc = tl / tiles_per_bc, line0 = (tl % tiles_per_bc) * LINES;
+        for (int l0 = 0; l0 < LINES; l0 += 256) pmx_tma_load_3d(in + l0 * 128, &tmap, 0, line0 + l0, bc, mbar);
+    };
+    if (threadIdx.x == 0) {
+        pmx_mbar_init(mbar, 1);
+        pmx_fence_mbar_init();
     }
     __syncthreads();
-    const cpx wb = pmx_twiddle4(p, (unsigned)k1 * (unsigned)t);
+    int tile = live(blockIdx.x);
+    if (threadIdx.x == 0 && tile < total) issue(tile);
+    uint32_t phase = 0;
+    while (tile < total) {
+        const int bc = tile / tiles_per_bc, b = bc / f.nfc, col = bc % f.nfc;
+        const int k1 = (tile % tiles_per_bc) * G + rl;
+        const StepCtl* c = &p.ctl[b];
+        cpx x[8], y[8];
+        pmx_mbar_wait(mbar, phase);
+        phase ^= 1u;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const cpx w = cmul(wb, gtab[rl * 8 + q]);
-        st_sa(base + (size_t)(t + q * T) * 2, cmulc(x[q], w), cmulc(y[q], w));
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t off = pmx_swz<7>((uint32_t)((rl * L + t + q * T) * 32));
+            x[q] = *reinterpret_cast<const cpx*>(in + off);
+            y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
+        }
+        __syncthreads();
+        const int next = live(tile + gridDim.x);
+        if (PF && threadIdx.x == 0 && next < total) issue(next);
+        cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
+        cpx* sy = sx + pmx_pad(L);
+        CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+
+        // ---- linear step in the frequency domain, fiber.m:907-933
+        const int ntrunk = c->ntrunk;
+        if (ntrunk > 0) {
+            const double dz_cur = c->dz_cur;
+            const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
+            if (f.pmd) {
+                const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
+                const PlateConst* pl = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
+                const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k2 = t + q * T;
+                    const double d1 = __ldg(&d1p[k2]);
+                    // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
+                    cpx vx, vy;
+                    {
+                        const PlateConst& P = pl[0];
+                        cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                        cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+                        vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
+                        vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
+                    }
+                    double e1s, e1c;
+                    bool have_e1 = false;
+                    for (int k = 0; k < ntrunk; ++k) {
+                        const PlateConst& P = pl[k];
+                        const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
+                        cpx e;
+                        if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
+                            if (!have_e1) {
+                                sincos(-0.5 * d1, &e1s, &e1c);
+                                have_e1 = true;
+                            }
+                            e = cmul(make_double2(e1c, e1s), make_double2(P.h0r, P.h0i));
+                        } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+                            double delta = 0.5 * (d1 + P.db0) * dzb / lcorr;
+                            double s, cs;
+                            sincos(-delta, &s, &cs);
+                            e = make_double2(cs, s);
+                        }
+                        vx = cmul(vx, e);
+                        vy = cmulc(vy, e);
+                        if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
+                            cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
+                            cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
+                            cpx nx = cadd(cmul(c11, vx), cmul(c12, vy));
+                            cpx ny = cadd(cmul(c21, vx), cmul(c22, vy));
+                            vx = nx;
+                            vy = ny;
+                        }
+                    }
+                    {  // back to the laboratory basis: u = matR * uu  (:931-932)
+                        const PlateConst& P = pl[ntrunk - 1];
+                        cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                        cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+                        x[q] = cadd(cmul(r11, vx), cmul(r12, vy));
+                        y[q] = cadd(cmul(r21, vx), cmul(r22, vy));
+                    }
+                }
+            }
+            if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double ph = __ldg(&bt[t + q * T]) * dz_cur;
+                    double s, cs;
+                    sincos(-ph, &s, &cs);
+                    cpx e = make_double2(cs, s);
+                    x[q] = cmul(x[q], e);
+                    y[q] = cmul(y[q], e);
+                }
+            }
+        }
+
+        CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
+        if (!PF && threadIdx.x == 0 && next < total) issue(next);
+        // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T:  conj(W_N^(k1*t) * g[q]),
+        // g[q] = exp(-2*pi*i*k1*q/(8*N1)) per row
+        if (threadIdx.x < G * 8) {
+            const int r2 = threadIdx.x >> 3, q = threadIdx.x & 7;
+            double s, cs;
+            sincospi(-2.0 * (double)(((tile % tiles_per_bc) * G + r2) * q) / (double)(8 * p.N1), &s, &cs);
+            gtab[r2 * 8 + q] = make_double2(cs, s);
+        }
+        __syncthreads();
+        const cpx wb = pmx_twiddle4(p, (unsigned)k1 * (unsigned)t);
+        cpx* base = p.field + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const cpx w = cmul(wb, gtab[rl * 8 + q]);
+            st_sa(base + (size_t)(t + q * T) * 2, cmulc(x[q], w), cmulc(y[q], w));
+        }
+        tile = next;
+        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------
 // pass C: like pass A, inverse transform + attenuation + max reduction + step control
-template <int L, int CPC>
-__global__ void __launch_bounds__(CPC * (L / 8), 512 / (CPC * (L / 8))) pmx_k_passC(PassParams p, FiberConst f) {
-    constexpr int T = L / 8;
-    extern __shared__ cpx smem[];
-    const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
-    StepCtl* c = &p.ctl[b];
-    if (c->state >= PMX_ST_DONE) return;
-    const int cl = threadIdx.x % CPC, t = threadIdx.x / CPC;
-    const int n2 = blockIdx.x * CPC + cl;
+template <int L, int G, bool PF>
+__global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
+    pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
+    using S = PassSmem<L, G, PF>;
+    constexpr int T = L / 8, PITCH = G * 32, MASK = PITCH / 16 - 1;
+    extern __shared__ unsigned char smraw[];
+    unsigned char* sm = pmx_align1024(smraw);
+    unsigned char* in = sm;
+    cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
+    void* red = sm + S::RED_OFF;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
+    const int tiles_per_bc = p.N2 / G, total = tiles_per_bc * p.batch * f.nfc;
+    const int cl = threadIdx.x % G, t = threadIdx.x / G;
     const size_t N = (size_t)p.N1 * p.N2;
-    cpx* base = p.field + ((size_t)bc * N + n2) * 2;
     const size_t rs = (size_t)p.N2 * 2;
-    cpx x[8], y[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        ld_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
+
+    auto live = [&](int tl) {
+        while (tl < total && p.ctl[(tl / tiles_per_bc) / f.nfc].state >= PMX_ST_DONE) tl += gridDim.x;
+        return tl;
+    };
+    auto issue = [&](int tl) {
+        pmx_fence_proxy_async();
+        pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
+        const int bc = tl / tiles_per_bc, c0 = (tl % tiles_per_bc) * G;
+        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
+    };
+    if (threadIdx.x == 0) {
+        pmx_mbar_init(mbar, 1);
+        pmx_fence_mbar_init();
     }
-    cpx* sx = smem + cl * PmxSmem<L, CPC>::STRIDE;
-    cpx* sy = sx + pmx_pad(L);
-    CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
-    const double sc = c->scale;
-    unsigned long long vmax = 0ull;
+    __syncthreads();
+    int tile = live(blockIdx.x);
+    if (threadIdx.x == 0 && tile < total) issue(tile);
+    uint32_t phase = 0;
+    while (tile < total) {
+        const int bc = tile / tiles_per_bc, b = bc / f.nfc, col = bc % f.nfc;
+        const int n2 = (tile % tiles_per_bc) * G + cl;
+        StepCtl* c = &p.ctl[b];
+        cpx x[8], y[8];
+        pmx_mbar_wait(mbar, phase);
+        phase ^= 1u;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        x[q] = cscale(x[q], sc);
-        y[q] = cscale(y[q], sc);
-        unsigned long long key = pmx_pow_key(power_ref(x[q], y[q]));
-        vmax = key > vmax ? key : vmax;
-        st_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
+            x[q] = *reinterpret_cast<const cpx*>(in + off);
+            y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
+        }
+        __syncthreads();
+        const int next = live(tile + gridDim.x);
+        if (PF && threadIdx.x == 0 && next < total) issue(next);
+        cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
+        cpx* sy = sx + pmx_pad(L);
+        CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
+        if (!PF && threadIdx.x == 0 && next < total) issue(next);
+        const double sc = c->scale;
+        unsigned long long vmax = 0ull;
+        cpx* base = p.field + ((size_t)bc * N + n2) * 2;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            x[q] = cscale(x[q], sc);
+            y[q] = cscale(y[q], sc);
+            unsigned long long key = pmx_pow_key(power_ref(x[q], y[q]));
+            vmax = key > vmax ? key : vmax;
+            st_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
+        }
+        pmx_block_max_and_ctl(vmax, red, c, col, (unsigned)(tiles_per_bc * f.nfc), f, false, b, p.trace_dz,
+                              p.trace_ntrunk);
+        tile = next;
     }
-    pmx_block_max_and_ctl(vmax, smem, c, col, gridDim.x * f.nfc, f, false, b, p.trace_dz, p.trace_ntrunk);
 }

@@ -1,20 +1,23 @@
 // Per-L launch table: one translation unit per in-CTA FFT length (pmx_passes_inst.cu
 // compiled with -DPMX_L=<L>) exports its three pass launchers through this struct.
 #pragma once
+#include <cuda.h>
 #include "pmx_common.cuh"
 
 struct PmxLaunchTable {
     int L;
-    int cpc;       // columns per CTA in passes A / C
-    int rpc;       // rows per CTA in pass B
+    int gAC;       // columns per tile in passes A / C
+    int gB;        // rows per tile in pass B
+    int pfAC, pfB; // 1: next tile prefetched into its own landing buffer
     int threadsAC, threadsB;
     size_t smemAC, smemB;
     int tw_total;  // cpx entries of the stage-twiddle table for this L
-    // grid.x = tiles, grid.y = batch*nfc
-    cudaError_t (*setup)();  // opt in to > 48 KB dynamic shared memory
-    void (*passA)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
-    void (*passB)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
-    void (*passC)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
+    // opt in to the dynamic shared memory, report resident CTAs per SM of each kernel
+    cudaError_t (*setup)(int* ctasA, int* ctasB, int* ctasC);
+    // grid_x persistent CTAs
+    void (*passA)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
+    void (*passB)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& rows);
+    void (*passC)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
 };
 
 const PmxLaunchTable* pmx_get_table(int L);  // nullptr if L is not built

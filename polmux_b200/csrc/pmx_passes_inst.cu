@@ -8,40 +8,47 @@
 
 namespace {
 constexpr int L = PMX_L;
-constexpr int T = L / 8;
-// CTA shapes: >=128 threads, columns grouped for 64..512 B contiguous runs in passes A/C
-constexpr int CPC = (L <= 256) ? (128 / T) : (L == 512 ? 4 : (L <= 2048 ? 2 : 1));
-constexpr int RPC = (T >= 128) ? 1 : (128 / T);
+// Tile shapes.  Rows/columns per tile are chosen so that a tile is <= 32 KiB (1024 Sa) when
+// possible: landing buffer + exchange buffer then fit three CTAs per SM with the next tile
+// prefetched.  Longer transforms land in the exchange buffer itself (no separate prefetch).
+#ifndef PMX_GAC
+constexpr int GAC = (L >= 1024) ? 1 : (L == 512 ? 2 : 4);
+#else
+constexpr int GAC = PMX_GAC;
+#endif
+constexpr int GB = (L >= 1024) ? 1 : (L == 512 ? 2 : 4);
+constexpr bool PFAC = (GAC * L <= 1024);
+constexpr bool PFB = (GB * L <= 1024);
+using SA = PassSmem<L, GAC, PFAC>;
+using SB = PassSmem<L, GB, PFB>;
 
-cudaError_t setup() {
+cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
     cudaError_t e;
-    // ask for the largest shared-memory carveout so that several CTAs fit per SM
-    cudaFuncSetAttribute(pmx_k_passA<L, CPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(pmx_k_passB<L, RPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(pmx_k_passC<L, CPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    e = cudaFuncSetAttribute(pmx_k_passA<L, CPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)PmxSmem<L, CPC>::bytes(CPC));
+    auto prep = [](auto kern, int smem, int threads, int* ctas) -> cudaError_t {
+        cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (r != cudaSuccess) return r;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, threads, smem);
+    };
+    e = prep(pmx_k_passA<L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasA);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pmx_k_passC<L, CPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)PmxSmem<L, CPC>::bytes(CPC));
+    e = prep(pmx_k_passB<L, GB, PFB>, SB::TOTAL, SB::THREADS, ctasB);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pmx_k_passB<L, RPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)PmxSmem<L, RPC>::bytes(RPC));
-    return e;
+    return prep(pmx_k_passC<L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasC);
 }
-void passA(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f) {
-    pmx_k_passA<L, CPC><<<grid, CPC * T, PmxSmem<L, CPC>::bytes(CPC), s>>>(p, f);
+void passA(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+    pmx_k_passA<L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);
 }
-void passB(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f) {
-    pmx_k_passB<L, RPC><<<grid, RPC * T, PmxSmem<L, RPC>::bytes(RPC), s>>>(p, f);
+void passB(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+    pmx_k_passB<L, GB, PFB><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
 }
-void passC(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f) {
-    pmx_k_passC<L, CPC><<<grid, CPC * T, PmxSmem<L, CPC>::bytes(CPC), s>>>(p, f);
+void passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+    pmx_k_passC<L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);
 }
 }  // namespace
 
 #define PMX_CAT2(a, b) a##b
 #define PMX_CAT(a, b) PMX_CAT2(a, b)
 extern const PmxLaunchTable PMX_CAT(pmx_table_, PMX_L) = {
-    L, CPC, RPC, CPC * T, RPC * T, PmxSmem<L, CPC>::bytes(CPC), PmxSmem<L, RPC>::bytes(RPC),
+    L, GAC, GB, PFAC ? 1 : 0, PFB ? 1 : 0, SA::THREADS, SB::THREADS, (size_t)SA::TOTAL, (size_t)SB::TOTAL,
     pmx_tw_total(L), setup, passA, passB, passC};

@@ -1,0 +1,57 @@
+// Minimal TMA / mbarrier wrappers (inline PTX, sm_100a) used to stage field tiles
+// from HBM into shared memory ahead of the compute that consumes them.
+//
+// Tiles are described by 3-D tensor maps over the resident field buffer
+// (cuTensorMapEncodeTiled, built on the host in pmx_api.cu):
+//   rows map   {16 doubles (128 B line), N/4 lines, batch*nfc}   pass B, SWIZZLE_128B
+//   cols map   {N2*4 doubles, N1 rows (pitch N2*32 B), batch*nfc} passes A and C,
+//              box {G*4 doubles, <=256 rows, 1}, swizzle = box pitch (32/64/128 B)
+// The swizzle makes the thread-per-Sa reads of the landed tile bank-conflict free:
+// physical offset = off ^ (((off >> 7) & (pitch/16 - 1)) << 4)  (CuTe Swizzle<B,4,3>).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__device__ __forceinline__ uint32_t pmx_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void pmx_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pmx_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pmx_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pmx_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void pmx_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pmx_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pmx_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(pmx_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one box of a 3-D tiled tensor map -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void pmx_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(pmx_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(pmx_smem_u32(bar))
+        : "memory");
+}
+// swizzled byte offset inside a landed tile; MASK = pitch/16 - 1 (1, 3 or 7), 0 = no swizzle
+template <int MASK>
+__device__ __forceinline__ uint32_t pmx_swz(uint32_t off) {
+    return off ^ (((off >> 7) & MASK) << 4);
+}
