@@ -93,6 +93,53 @@ __device__ __forceinline__ void st_sa(cpx* p, cpx x, cpx y) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y) : "memory");
 }
 
+// Branch-free sin/cos for |x| < 105615 (three-term Cody-Waite reduction by pi/2 with FMAs, then
+// the fdlibm kernel polynomials on [-pi/4, pi/4]; <= ~1 ulp like the libm calls the reference
+// makes in fastexp.c:41-42).  Being branch-free lets the compiler interleave the eight
+// evaluations a thread needs.  Larger arguments take the library's Payne-Hanek path.
+__device__ __forceinline__ void pmx_sincos_fast(double x, double* sp, double* cp) {
+    const double q = rint(x * 6.3661977236758138e-01);
+    double r = fma(q, -1.5707963267948966e+00, x);
+    r = fma(q, -6.1232339957367574e-17, r);
+    r = fma(q, -1.4973849048591698e-33, r);
+    const int n = (int)q;
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sn = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double a = (n & 1) ? cs : sn, b = (n & 1) ? sn : cs;
+    *sp = (n & 2) ? -a : a;
+    *cp = ((n + 1) & 2) ? -b : b;
+}
+__device__ __forceinline__ void pmx_sincos(double x, double* sp, double* cp) {
+    if (fabs(x) < 105615.0)
+        pmx_sincos_fast(x, sp, cp);
+    else
+        sincos(x, sp, cp);
+}
+// eight at once: one (rarely taken) branch for the whole group
+__device__ __forceinline__ void pmx_sincos8(const double (&x)[8], double (&s)[8], double (&c)[8]) {
+    double m = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m = fmax(m, fabs(x[q]));
+    if (m < 105615.0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pmx_sincos_fast(x[q], &s[q], &c[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sincos(x[q], &s[q], &c[q]);
+    }
+}
+
 // |ux|^2+|uy|^2 in the reference's order, no FMA contraction (fiber.m:694)
 __device__ __forceinline__ double power_ref(cpx x, cpx y) {
     double p = __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y));

@@ -273,21 +273,28 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         if (f.spm) {
             const double gamleff = __dmul_rn(f.gam[col], c->leff);
             const double ngl = -gamleff;
+            double ph[8], sn[8], cs[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ph[q] = __dmul_rn(ngl, power_ref(x[q], y[q]));
+            pmx_sincos8(ph, sn, cs);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                double pw = power_ref(x[q], y[q]);
-                double s, cs;
-                sincos(__dmul_rn(ngl, pw), &s, &cs);
-                cpx e = make_double2(cs, s);
+                const cpx e = make_double2(cs[q], sn[q]);
                 x[q] = cmul(x[q], e);
                 y[q] = cmul(y[q], e);
-                if (!f.manakov) {
-                    double s3 = 2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
-                    double sp, cp;
-                    sincos(__dmul_rn(gamleff, s3) / 3.0, &sp, &cp);
-                    cpx ux = x[q], uy = y[q];
-                    x[q] = make_double2(cp * ux.x + sp * uy.x, cp * ux.y + sp * uy.y);
-                    y[q] = make_double2(cp * uy.x - sp * ux.x, cp * uy.y - sp * ux.y);
+            }
+            if (!f.manakov) {  // CNLSE: rotation by gamleff*s3/3 around the third Stokes axis (:841-851)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double s3 = 2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
+                    ph[q] = __dmul_rn(gamleff, s3) / 3.0;
+                }
+                pmx_sincos8(ph, sn, cs);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const cpx ux = x[q], uy = y[q];
+                    x[q] = make_double2(cs[q] * ux.x + sn[q] * uy.x, cs[q] * ux.y + sn[q] * uy.y);
+                    y[q] = make_double2(cs[q] * uy.x - sn[q] * ux.x, cs[q] * uy.y - sn[q] * ux.y);
                 }
             }
         }
@@ -380,64 +387,86 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                 const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
                 const PlateConst* pl = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
                 const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
+                double d1[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int k2 = t + q * T;
-                    const double d1 = __ldg(&d1p[k2]);
-                    // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
-                    cpx vx, vy;
-                    {
-                        const PlateConst& P = pl[0];
-                        cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                        cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
-                        vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
-                        vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
+                for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
+                {  // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
+                    const PlateConst& P = pl[0];
+                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const cpx vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
+                        const cpx vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
+                        x[q] = vx;
+                        y[q] = vy;
                     }
-                    double e1s, e1c;
-                    bool have_e1 = false;
-                    for (int k = 0; k < ntrunk; ++k) {
-                        const PlateConst& P = pl[k];
-                        const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
-                        cpx e;
-                        if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
-                            if (!have_e1) {
-                                sincos(-0.5 * d1, &e1s, &e1c);
-                                have_e1 = true;
-                            }
-                            e = cmul(make_double2(e1c, e1s), make_double2(P.h0r, P.h0i));
-                        } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-                            double delta = 0.5 * (d1 + P.db0) * dzb / lcorr;
-                            double s, cs;
-                            sincos(-delta, &s, &cs);
-                            e = make_double2(cs, s);
+                }
+                // exp(-i*db1/2): the frequency-dependent factor shared by every whole trunk
+                const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
+                double e1s[8], e1c[8];
+                if (any_full) {
+                    double a[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = -0.5 * d1[q];
+                    pmx_sincos8(a, e1s, e1c);
+                }
+                for (int k = 0; k < ntrunk; ++k) {
+                    const PlateConst& P = pl[k];
+                    const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
+                    if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
+                        const cpx h0 = make_double2(P.h0r, P.h0i);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const cpx e = cmul(make_double2(e1c[q], e1s[q]), h0);
+                            x[q] = cmul(x[q], e);
+                            y[q] = cmulc(y[q], e);
                         }
-                        vx = cmul(vx, e);
-                        vy = cmulc(vy, e);
-                        if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
-                            cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
-                            cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
-                            cpx nx = cadd(cmul(c11, vx), cmul(c12, vy));
-                            cpx ny = cadd(cmul(c21, vx), cmul(c22, vy));
-                            vx = nx;
-                            vy = ny;
+                    } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+                        double a[8], sn[8], cs[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) a[q] = -(0.5 * (d1[q] + P.db0) * dzb / lcorr);
+                        pmx_sincos8(a, sn, cs);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const cpx e = make_double2(cs[q], sn[q]);
+                            x[q] = cmul(x[q], e);
+                            y[q] = cmulc(y[q], e);
                         }
                     }
-                    {  // back to the laboratory basis: u = matR * uu  (:931-932)
-                        const PlateConst& P = pl[ntrunk - 1];
-                        cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                        cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
-                        x[q] = cadd(cmul(r11, vx), cmul(r12, vy));
-                        y[q] = cadd(cmul(r21, vx), cmul(r22, vy));
+                    if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
+                        const cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
+                        const cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const cpx nx = cadd(cmul(c11, x[q]), cmul(c12, y[q]));
+                            const cpx ny = cadd(cmul(c21, x[q]), cmul(c22, y[q]));
+                            x[q] = nx;
+                            y[q] = ny;
+                        }
+                    }
+                }
+                {  // back to the laboratory basis: u = matR * uu  (:931-932)
+                    const PlateConst& P = pl[ntrunk - 1];
+                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const cpx ux = cadd(cmul(r11, x[q]), cmul(r12, y[q]));
+                        const cpx uy = cadd(cmul(r21, x[q]), cmul(r22, y[q]));
+                        x[q] = ux;
+                        y[q] = uy;
                     }
                 }
             }
             if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
+                double a[8], sn[8], cs[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
+                pmx_sincos8(a, sn, cs);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const double ph = __ldg(&bt[t + q * T]) * dz_cur;
-                    double s, cs;
-                    sincos(-ph, &s, &cs);
-                    cpx e = make_double2(cs, s);
+                    const cpx e = make_double2(cs[q], sn[q]);
                     x[q] = cmul(x[q], e);
                     y[q] = cmul(y[q], e);
                 }
