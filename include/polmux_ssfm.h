@@ -50,6 +50,8 @@ typedef enum pmx_layout {
     PMX_COMPLEX = 1  /* two interleaved complex arrays x, y (re,im,re,im,...)       */
 } pmx_layout;
 
+typedef enum pmx_disp_mode { PMX_DISP_VECTOR = 0, PMX_DISP_SCALAR = 1 } pmx_disp_mode;
+
 typedef struct pmx_ctx pmx_ctx;
 typedef struct pmx_plan pmx_plan;         /* one fiber() worth of device constants */
 typedef struct pmx_devfield pmx_devfield; /* a field resident in HBM               */
@@ -93,6 +95,22 @@ typedef struct pmx_fiber_desc {
     const double* epsilon; /* [plate_sets][nplates]  brf.epsilon  fiber.m:268,276 */
     const double* betat;   /* [nfc][nfft] host, fiber.m:350-356 (FFT order)        */
     const double* db1;     /* [nfc][nfft] host, fiber.m:358; NULL means zeros      */
+    /* Optional scalar dispersion mode.  With disp_mode == PMX_DISP_SCALAR the library rebuilds
+     * the two vectors per bin from the scalars fiber.m:350-362 builds them from --
+     *   omega = 2*pi*symbolrate*FN,  FN = signed FFT bin / nsymb            (reset_all.m:153)
+     *   betat = omega*beta1 + 0.5*omega^2*beta2 + omega^3*b30/6,  db1 = dgdrms*omega
+     * -- and betat / db1 may be NULL: nothing but the field crosses PCIe.  omega, db1 and the
+     * first two betat terms are bit-identical to the host vectors; the cubic term may differ by
+     * one ulp (omega^3 is formed by two multiplications, b30/6 is pre-divided). */
+    int32_t disp_mode;     /* pmx_disp_mode */
+    int32_t nsymb;         /* GSTATE.NSYMB */
+    int32_t nt;            /* GSTATE.NT    */
+    int32_t reserved0;
+    double symbolrate;     /* GSTATE.SYMBOLRATE [GBaud] */
+    double b30;            /* fiber.m:309-311 [ns^3/m] */
+    double dgdrms;         /* fiber.m:269/277/284 [ns]; 0 without the 'p' flag */
+    const double* beta1;   /* [nfc] fiber.m:323/327 */
+    const double* beta2;   /* [nfc] fiber.m:330-332 */
 } pmx_fiber_desc;
 
 typedef struct pmx_field {

@@ -48,6 +48,8 @@ class FiberDesc(C.Structure):
         ('dzmaxt', C.c_double), ('dphimaxt', C.c_double), ('gam', _dp), ('fls', C.c_int32 * 4),
         ('nplates', C.c_int32), ('plate_sets', C.c_int32), ('db0', _dp), ('theta', _dp),
         ('epsilon', _dp), ('betat', _dp), ('db1', _dp),
+        ('disp_mode', C.c_int32), ('nsymb', C.c_int32), ('nt', C.c_int32), ('reserved0', C.c_int32),
+        ('symbolrate', C.c_double), ('b30', C.c_double), ('dgdrms', C.c_double), ('beta1', _dp), ('beta2', _dp),
     ]
 
 
@@ -174,16 +176,19 @@ def default_context(device: int = 0) -> Context:
 
 
 def make_desc(nfft, nfc, batch, length, alphalin, dzmaxt, dphimaxt, gam, fls, manakov, nplates,
-              db0, theta, epsilon, betat, db1, plate_sets=1, precision=PMX_F64):
-    """Build a FiberDesc plus the list of arrays that must stay alive while it is used."""
+              db0, theta, epsilon, betat, db1, plate_sets=1, precision=PMX_F64, scalar=None):
+    """Build a FiberDesc plus the list of arrays that must stay alive while it is used.
+
+    scalar: None (vector dispersion mode: betat/db1 cross the boundary) or a dict with nsymb, nt,
+    symbolrate, b30, dgdrms, beta1, beta2 (scalar dispersion mode: betat/db1 stay on the host)."""
     keep = {}
     keep['gam'] = _f64(np.atleast_1d(gam))
     keep['db0'] = _f64(db0).reshape(-1)
     keep['theta'] = _f64(theta).reshape(-1)
     keep['epsilon'] = _f64(epsilon).reshape(-1)
     # betat / db1 arrive as [nfft, nfc] (column-major columns) -> [nfc][nfft]
-    keep['betat'] = _f64(np.asarray(betat).reshape(nfft, nfc).T)
-    keep['db1'] = _f64(np.asarray(db1).reshape(nfft, nfc).T) if db1 is not None else None
+    keep['betat'] = _f64(np.asarray(betat).reshape(nfft, nfc).T) if (betat is not None and scalar is None) else None
+    keep['db1'] = _f64(np.asarray(db1).reshape(nfft, nfc).T) if (db1 is not None and scalar is None) else None
     d = FiberDesc()
     d.nfft, d.nfc, d.batch, d.precision = int(nfft), int(nfc), int(batch), int(precision)
     d.manakov = 1 if manakov else 0
@@ -193,6 +198,13 @@ def make_desc(nfft, nfc, batch, length, alphalin, dzmaxt, dphimaxt, gam, fls, ma
     d.nplates, d.plate_sets = int(nplates), int(plate_sets)
     d.db0, d.theta, d.epsilon = _ptr(keep['db0']), _ptr(keep['theta']), _ptr(keep['epsilon'])
     d.betat, d.db1 = _ptr(keep['betat']), _ptr(keep['db1'])
+    if scalar is not None:
+        keep['beta1'] = _f64(np.atleast_1d(scalar['beta1']))
+        keep['beta2'] = _f64(np.atleast_1d(scalar['beta2']))
+        d.disp_mode = 1
+        d.nsymb, d.nt = int(scalar['nsymb']), int(scalar['nt'])
+        d.symbolrate, d.b30, d.dgdrms = float(scalar['symbolrate']), float(scalar['b30']), float(scalar['dgdrms'])
+        d.beta1, d.beta2 = _ptr(keep['beta1']), _ptr(keep['beta2'])
     return d, keep
 
 

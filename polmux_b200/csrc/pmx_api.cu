@@ -634,7 +634,15 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     if (d->batch < 1) return set_err(c, PMX_ERR_INVALID, "batch must be >= 1");
     if (d->nplates < 1) return set_err(c, PMX_ERR_INVALID, "nplates must be >= 1");
     if (!(d->length > 0)) return set_err(c, PMX_ERR_INVALID, "length must be > 0");
-    if (!d->gam || !d->betat) return set_err(c, PMX_ERR_INVALID, "gam and betat are required");
+    const bool scalar = d->disp_mode == PMX_DISP_SCALAR;
+    if (!d->gam) return set_err(c, PMX_ERR_INVALID, "gam is required");
+    if (!scalar && !d->betat) return set_err(c, PMX_ERR_INVALID, "betat is required in vector dispersion mode");
+    if (scalar) {
+        if (!d->beta1 || !d->beta2) return set_err(c, PMX_ERR_INVALID, "scalar dispersion mode needs beta1 and beta2");
+        if (d->nsymb <= 0 || d->nt <= 0 || (int64_t)d->nsymb * d->nt != d->nfft)
+            return set_err(c, PMX_ERR_INVALID, "scalar dispersion mode: nsymb*nt must equal nfft");
+        if (!(d->symbolrate > 0)) return set_err(c, PMX_ERR_INVALID, "scalar dispersion mode: symbolrate must be > 0");
+    }
     if (d->fls[3]) return set_err(c, PMX_ERR_XPM_VECTOR, "The CNLSE with separate fields is not yet implemented");
     if (d->plate_sets != 1 && d->plate_sets != d->batch)
         return set_err(c, PMX_ERR_INVALID, "plate_sets must be 1 or batch");
@@ -645,7 +653,7 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     if (!p) return set_err(c, PMX_ERR_INVALID, "out of host memory");
     p->ctx = c;
     p->d = *d;
-    p->d.gam = p->d.db0 = p->d.theta = p->d.epsilon = p->d.betat = p->d.db1 = nullptr;
+    p->d.gam = p->d.db0 = p->d.theta = p->d.epsilon = p->d.betat = p->d.db1 = p->d.beta1 = p->d.beta2 = nullptr;
     p->log2N1 = lg / 2;
     p->log2N2 = lg - p->log2N1;
     p->N1 = 1 << p->log2N1;
@@ -689,6 +697,28 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     const size_t N = (size_t)d->nfft;
     p->single_step = std::isinf(d->dphimaxt) && d->dzmaxt >= d->length;
 
+    if (scalar) {
+        f.disp_scalar = 1;
+        f.w0 = 2 * M_PI * d->symbolrate;  // fiber.m:352  2*pi*GSTATE.SYMBOLRATE (*FN)
+        f.inv_nsymb = 1.0 / (double)d->nsymb;
+        f.b30_6 = d->b30 / 6;
+        f.dgdrms = f.pmd ? d->dgdrms : 0.0;
+        f.domega = f.w0 * ((double)d->nt / 8.0);
+        f.g1r = cos(0.5 * f.dgdrms * f.domega);
+        f.g1i = -sin(0.5 * f.dgdrms * f.domega);
+        bool any = d->b30 != 0.0;
+        for (int k = 0; k < d->nfc; ++k) {
+            f.beta1[k] = d->beta1[k];
+            f.beta2[k] = d->beta2[k];
+            any = any || d->beta1[k] != 0.0 || d->beta2[k] != 0.0;
+        }
+        f.gvd_any = any ? 1 : 0;
+        cudaError_t e = cudaMallocAsync(&p->ctl, (size_t)d->batch * sizeof(StepCtl), c->stream);
+        if (e != cudaSuccess) {
+            pmx_plan_destroy(p);
+            return set_err(c, PMX_ERR_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
+        }
+    } else
     // dispersion vectors, permuted on the device: bin k1 + N1*k2 -> position k1*N2 + k2
     {
         const size_t bytes = N * d->nfc * sizeof(double);

@@ -35,6 +35,9 @@ struct __align__(16) StepCtl {
     int nmem;          // fiber.m:742,748
     int n_first;       // 0-based plate index of trunk k=1:  ntot + 1 - nmem - 1
     int pad0;
+    // scalar dispersion mode: per-bin-step factors exp(-i*0.5*dgdrms*domega*dzb/lcorr) of the
+    // first / last (partial) trunk of the step, domega = spacing of a thread's bins
+    double gpf_r, gpf_i, gpl_r, gpl_i;
     // reduction scratch for nextstep
     unsigned long long umax_bits[PMX_MAX_NFC];  // max over n of |ux|^2+|uy|^2, per column
     unsigned int ticket;
@@ -57,6 +60,13 @@ struct FiberConst {
     double Lf, alphalin, halfalpha, dzmax, phimax, lcorr, invN;
     double gam[PMX_MAX_NFC];  // after the Manakov 8/9 (fiber.m:500)
     int nplates, nfc, spm, manakov, pmd, gvd_any, plate_sets, trace_cap;
+    // scalar dispersion mode (fiber.m:350-362 regenerated per bin instead of read from HBM):
+    //   omega = w0*fn, fn = kk/NSYMB (kk = signed FFT bin), betat = omega*beta1 + 0.5*omega^2*beta2
+    //   + omega^3*b30/6, db1 = dgdrms*omega
+    int disp_scalar, pad_;
+    double w0, inv_nsymb, b30_6, dgdrms, domega;  // domega = w0*NT/8: spacing of a thread's bins
+    double g1r, g1i;                              // exp(-i*0.5*dgdrms*domega)
+    double beta1[PMX_MAX_NFC], beta2[PMX_MAX_NFC];
 };
 
 struct PassParams {

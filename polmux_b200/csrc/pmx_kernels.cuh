@@ -109,6 +109,15 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
     c->dzb_first = dzb_first;
     c->dzb_last = dzb_last;
     c->n_first = c->ntot - nmem;
+    if (f.disp_scalar && f.pmd) {
+        double s, cs;
+        sincos(-(0.5 * f.dgdrms * f.domega * dzb_first / lcorr), &s, &cs);
+        c->gpf_r = cs;
+        c->gpf_i = s;
+        sincos(-(0.5 * f.dgdrms * f.domega * dzb_last / lcorr), &s, &cs);
+        c->gpl_r = cs;
+        c->gpl_i = s;
+    }
     if (ntrunk > 0 && (c->ntot + ntrunk - nmem > f.nplates || c->n_first < 0)) {
         c->state = PMX_ST_ERROR;  // brf.theta(n) index error in the reference (fiber.m:910)
         c->err = -4;              // PMX_ERR_PLATE_INDEX
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             x[q] = *reinterpret_cast<const cpx*>(in + off);
             y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
         }
+        if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
         __syncthreads();
         const int next = live(tile + gridDim.x);
         if (PF && threadIdx.x == 0 && next < total) issue(next);
@@ -301,7 +311,6 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + pmx_pad(L);
         CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
-        if (!PF && threadIdx.x == 0 && next < total) issue(next);
         // four-step twiddle W_N^(n2*k1), k1 = t + q*T:  W_N^(n2*t) * g[q],  g[q] = exp(-2*pi*i*n2*q/(8*N2))
         if (threadIdx.x < G * 8) {
             const int c2 = threadIdx.x >> 3, q = threadIdx.x & 7;
@@ -311,20 +320,34 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         __syncthreads();
         const cpx wb = pmx_twiddle4(p, (unsigned)n2 * (unsigned)t);
-        cpx* base = p.field + ((size_t)bc * N + n2) * 2;
+        // stage the tile (same swizzled layout as it landed) in the exchange buffer, TMA-store it
+        unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const cpx w = cmul(wb, gtab[cl * 8 + q]);
-            st_sa(base + (size_t)(t + q * T) * rs, cmul(x[q], w), cmul(y[q], w));
+            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
+            *reinterpret_cast<cpx*>(outb + off) = cmul(x[q], w);
+            *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = cmul(y[q], w);
+        }
+        pmx_fence_proxy_async();
+        __syncthreads();  // tile staged; gtab free for the next tile
+        if (threadIdx.x == 0) {
+            const int c0 = (tile % tiles_per_bc) * G;
+            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, bc, outb + r0 * PITCH);
+            pmx_tma_commit();
+            if (!PF && next < total) {  // the next tile lands in this same buffer
+                pmx_tma_wait_read();
+                issue(next);
+            }
         }
         tile = next;
-        __syncthreads();  // gtab is rewritten by the next tile
     }
+    if (threadIdx.x == 0) pmx_tma_wait_read();
 }
 
 // ---------------------------------------------------------------------------
 // pass B: G rows per tile, thread (t fastest, rl)
-template <int L, int G, bool PF>
+template <int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF>;
@@ -380,7 +403,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 
         // ---- linear step in the frequency domain, fiber.m:907-933
         const int ntrunk = c->ntrunk;
-        if (ntrunk > 0) {
+        if (!SC && ntrunk > 0) {
             const double dz_cur = c->dz_cur;
             const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
             if (f.pmd) {
@@ -473,6 +496,111 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             }
         }
 
+        if (SC && ntrunk > 0) {
+            // Scalar dispersion mode.  A thread's bins are k = k1 + N1*(t + q*T): q < 4 on the
+            // positive-frequency side, q >= 4 on the negative one, equally spaced by domega.
+            const double dz_cur = c->dz_cur;
+            const long long kb = (long long)k1 + (long long)p.N1 * t;
+            const double dfn = (double)((long long)p.N1 * T) * f.inv_nsymb;
+            const double fn0 = (double)kb * f.inv_nsymb;
+            const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
+            if (f.pmd) {
+                const PlateConst* pl = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
+                const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
+                const double d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
+                const double d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
+                {  // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
+                    const PlateConst& P = pl[0];
+                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const cpx vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
+                        const cpx vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
+                        x[q] = vx;
+                        y[q] = vy;
+                    }
+                }
+                // whole trunks: exp(-i*db1/2) at the two base bins, then a geometric progression
+                const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
+                cpx E0 = make_double2(1.0, 0.0), E4 = E0;
+                if (any_full) {
+                    pmx_sincos(-0.5 * d10, &E0.y, &E0.x);
+                    pmx_sincos(-0.5 * d14, &E4.y, &E4.x);
+                }
+                const cpx g1 = make_double2(f.g1r, f.g1i);
+                for (int k = 0; k < ntrunk; ++k) {
+                    const PlateConst& P = pl[k];
+                    const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
+                    cpx e0, e4, g;
+                    if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
+                        const cpx h0 = make_double2(P.h0r, P.h0i);
+                        e0 = cmul(E0, h0);
+                        e4 = cmul(E4, h0);
+                        g = g1;
+                    } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+                        pmx_sincos(-(0.5 * (d10 + P.db0) * dzb / lcorr), &e0.y, &e0.x);
+                        pmx_sincos(-(0.5 * (d14 + P.db0) * dzb / lcorr), &e4.y, &e4.x);
+                        g = (k == 0) ? make_double2(c->gpf_r, c->gpf_i) : make_double2(c->gpl_r, c->gpl_i);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        x[q] = cmul(x[q], e0);
+                        y[q] = cmulc(y[q], e0);
+                        x[q + 4] = cmul(x[q + 4], e4);
+                        y[q + 4] = cmulc(y[q + 4], e4);
+                        if (q < 3) {
+                            e0 = cmul(e0, g);
+                            e4 = cmul(e4, g);
+                        }
+                    }
+                    if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
+                        const cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
+                        const cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const cpx nx = cadd(cmul(c11, x[q]), cmul(c12, y[q]));
+                            const cpx ny = cadd(cmul(c21, x[q]), cmul(c22, y[q]));
+                            x[q] = nx;
+                            y[q] = ny;
+                        }
+                    }
+                }
+                {  // back to the laboratory basis: u = matR * uu  (:931-932)
+                    const PlateConst& P = pl[ntrunk - 1];
+                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
+                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const cpx ux = cadd(cmul(r11, x[q]), cmul(r12, y[q]));
+                        const cpx uy = cadd(cmul(r21, x[q]), cmul(r22, y[q]));
+                        x[q] = ux;
+                        y[q] = uy;
+                    }
+                }
+            }
+            if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb)), betat regenerated (:355-356)
+                const double b1 = f.beta1[col], b2 = f.beta2[col];
+                double a[8], sn[8], cs[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
+                    const double w = __dmul_rn(f.w0, fn);
+                    const double w2 = __dmul_rn(w, w);
+                    double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
+                    bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
+                    a[q] = -(bt * dz_cur);
+                }
+                pmx_sincos8(a, sn, cs);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const cpx e = make_double2(cs[q], sn[q]);
+                    x[q] = cmul(x[q], e);
+                    y[q] = cmul(y[q], e);
+                }
+            }
+        }
+
         CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
         if (!PF && threadIdx.x == 0 && next < total) issue(next);
         // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T:  conj(W_N^(k1*t) * g[q]),
@@ -545,26 +673,43 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             x[q] = *reinterpret_cast<const cpx*>(in + off);
             y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
         }
+        if (threadIdx.x == 0) pmx_tma_wait_read();
         __syncthreads();
         const int next = live(tile + gridDim.x);
         if (PF && threadIdx.x == 0 && next < total) issue(next);
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + pmx_pad(L);
         CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
-        if (!PF && threadIdx.x == 0 && next < total) issue(next);
         const double sc = c->scale;
         unsigned long long vmax = 0ull;
-        cpx* base = p.field + ((size_t)bc * N + n2) * 2;
+        unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             x[q] = cscale(x[q], sc);
             y[q] = cscale(y[q], sc);
             unsigned long long key = pmx_pow_key(power_ref(x[q], y[q]));
             vmax = key > vmax ? key : vmax;
-            st_sa(base + (size_t)(t + q * T) * rs, x[q], y[q]);
+            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
+            *reinterpret_cast<cpx*>(outb + off) = x[q];
+            *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = y[q];
         }
+        pmx_fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int c0 = (tile % tiles_per_bc) * G;
+            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, bc, outb + r0 * PITCH);
+            pmx_tma_commit();
+            if (!PF && next < total) {
+                pmx_tma_wait_read();
+                issue(next);
+            }
+        }
+        // The bulk store must be complete in global memory before the step control of the last
+        // tile lets the next kernel start?  No: kernel boundaries order it; only this CTA's smem
+        // reuse needs the wait above.
         pmx_block_max_and_ctl(vmax, red, c, col, (unsigned)(tiles_per_bc * f.nfc), f, false, b, p.trace_dz,
                               p.trace_ntrunk);
         tile = next;
     }
+    if (threadIdx.x == 0) pmx_tma_wait_read();
 }

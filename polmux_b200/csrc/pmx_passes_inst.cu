@@ -18,7 +18,12 @@ constexpr int GAC = PMX_GAC;
 #endif
 constexpr int GB = (L >= 1024) ? 1 : (L == 512 ? 2 : 4);
 constexpr bool PFAC = (GAC * L <= 1024);
-constexpr bool PFB = (GB * L <= 1024);
+#ifndef PMX_PFB
+// pass B is compute-bound: it prefers a fourth resident CTA to a separate prefetch buffer
+constexpr bool PFB = (GB * L <= 512);
+#else
+constexpr bool PFB = (PMX_PFB != 0) && (GB * L <= 1024);
+#endif
 using SA = PassSmem<L, GAC, PFAC>;
 using SB = PassSmem<L, GB, PFB>;
 
@@ -32,7 +37,9 @@ cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
     };
     e = prep(pmx_k_passA<L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasA);
     if (e != cudaSuccess) return e;
-    e = prep(pmx_k_passB<L, GB, PFB>, SB::TOTAL, SB::THREADS, ctasB);
+    e = prep(pmx_k_passB<L, GB, PFB, false>, SB::TOTAL, SB::THREADS, ctasB);
+    if (e != cudaSuccess) return e;
+    e = prep(pmx_k_passB<L, GB, PFB, true>, SB::TOTAL, SB::THREADS, ctasB);
     if (e != cudaSuccess) return e;
     return prep(pmx_k_passC<L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasC);
 }
@@ -40,7 +47,10 @@ void passA(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, con
     pmx_k_passA<L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);
 }
 void passB(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
-    pmx_k_passB<L, GB, PFB><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
+    if (f.disp_scalar)
+        pmx_k_passB<L, GB, PFB, true><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
+    else
+        pmx_k_passB<L, GB, PFB, false><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
 }
 void passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
     pmx_k_passC<L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);

@@ -50,6 +50,16 @@ __device__ __forceinline__ void pmx_tma_load_3d(void* dst, const CUtensorMap* ma
         ::"r"(pmx_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(pmx_smem_u32(bar))
         : "memory");
 }
+// shared memory -> one box of a 3-D tiled tensor map (bulk async-group completion)
+__device__ __forceinline__ void pmx_tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(pmx_smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void pmx_tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores have finished READING shared memory
+__device__ __forceinline__ void pmx_tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // swizzled byte offset inside a landed tile; MASK = pitch/16 - 1 (1, 3 or 7), 0 = no swizzle
 template <int MASK>
 __device__ __forceinline__ uint32_t pmx_swz(uint32_t off) {

@@ -69,6 +69,7 @@ class FiberSetup:
     isy: bool
     b1: np.ndarray
     dch: np.ndarray
+    scalars: dict            # beta1, beta2, b30, dgdrms, ... (scalar dispersion mode of the C ABI)
 
 
 def flag_to_fls(flag: str, nfc: int, x):
@@ -191,16 +192,23 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
     betat, db1 = _dispersion_vectors(G, nfft, nfc, beta1, beta2, b30, dgdrms, fls[1])
     return FiberSetup(nfft=nfft, nfc=nfc, fls=fls, dphimaxt=dphimaxt, dzmaxt=dzmaxt, length=length,
                       alphalin=alphalin, gam=gam, betat=betat, db1=db1, manakov=manakov,
-                      nplates=nplates, brf=brf, isv=isv, isy=isy, b1=b1, dch=dch)
+                      nplates=nplates, brf=brf, isv=isv, isy=isy, b1=b1, dch=dch,
+                      scalars=dict(nsymb=G.NSYMB, nt=G.NT, symbolrate=float(G.SYMBOLRATE), b30=float(b30),
+                                   dgdrms=float(dgdrms), beta1=np.asarray(beta1, dtype=np.float64),
+                                   beta2=np.asarray(beta2, dtype=np.float64)))
 
 
-def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, epsilon=None):
+DISP_MODE = 'scalar'   # 'scalar': only the field crosses PCIe; 'vector': betat/db1 are uploaded
+
+
+def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, epsilon=None, disp_mode=None):
     """FiberSetup -> (pmx_fiber_desc, keep-alive dict)."""
+    mode = disp_mode or DISP_MODE
     return _lib.make_desc(
         s.nfft, s.nfc, batch, s.length, s.alphalin, s.dzmaxt, s.dphimaxt, s.gam, s.fls, s.manakov, s.nplates,
         s.brf['db0'] if db0 is None else db0, s.brf['theta'] if theta is None else theta,
         s.brf['epsilon'] if epsilon is None else epsilon, s.betat, s.db1 if s.fls[1] else None,
-        plate_sets=plate_sets)
+        plate_sets=plate_sets, scalar=s.scalars if mode == 'scalar' else None)
 
 
 def apply_side_effects(s: FiberSetup):
@@ -216,7 +224,7 @@ LAST = {}  # firstdz / ncycle / schedule of the most recent fiber(), what the re
 
 
 def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional[_lib.Context] = None,
-          trace: bool = False):
+          trace: bool = False, disp_mode: Optional[str] = None):
     """zbrf = fiber(x, flag) -- fiber.m:1.  Propagates GSTATE.FIELDX/FIELDY in place."""
     G = GSTATE
     s = fiber_setup(x, flag, rng)
@@ -230,7 +238,7 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         G.FIELDY = np.zeros_like(G.FIELDX)
     apply_side_effects(s)
     ctx = ctx or _lib.default_context()
-    desc, keep = setup_to_desc(s)
+    desc, keep = setup_to_desc(s, disp_mode=disp_mode)
     fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]     # [1][nfc][nfft]
     scalar = not s.isv
     fy = (np.zeros_like(fx) if scalar else

@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
+@pytest.fixture(autouse=True, params=['scalar', 'vector'])
+def disp_mode(request, monkeypatch):
+    """every parity test runs in both dispersion modes of the C ABI"""
+    import importlib
+    fmod = importlib.import_module('polmux_b200.fiber')
+    monkeypatch.setattr(fmod, 'DISP_MODE', request.param)
+    return request.param
+
+
 def run_both(nsymb, nt, fib, flag, nch=1, ftype='unique', seed=1000, pavg=2.0, rate=28.0):
     gs = make_tx(nsymb, nt, nch, rate=rate, pavg_mw=pavg, ftype=ftype)
     brf_o = orc.fiber(gs, fib, flag, rng=np.random.Generator(np.random.PCG64(seed)))
