@@ -1,0 +1,117 @@
+"""Generate tests/golden/*.npz by EXECUTING the reference's own M source (fiber.m, fastexp.m,
+reset_all.m, create_field.m, fastshift.m, nmod.m, checkfields.m, ampliflat.m under
+/root/reference) with the minimal interpreter in oracle/mini_m.  Run in the build container
+(the reference tree does not exist on the GPU box):
+
+    python oracle/make_golden.py [/root/reference]
+
+Inputs are the seeded synthetic PDM-QPSK fields of polmux_b200.synth; random plates come
+from numpy Generator(PCG64(seed)) in the order fiber.m:274-276 draws them.  Each fixture
+stores inputs, parameters and the reference outputs, so the tests need nothing else.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.mini_m.interp import Interp, MStruct, from_m, to_m  # noqa: E402
+from polmux_b200 import synth  # noqa: E402
+
+REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+SMF = dict(synth.SMF)
+
+
+def new_interp(seed):
+    it = Interp(REF, rng=np.random.Generator(np.random.PCG64(seed)))
+    return it
+
+
+def tx_through_reference(it, nsymb, nt, nch, rate, pavg, ftype, two_pol=True, spac=0.4):
+    """reset_all.m + (lasersource/electricsource stand-ins) + create_field.m, all interpreted."""
+    ex, ey, _, _ = synth.pdm_qpsk(nsymb, nt, nch)
+    it.call('reset_all', [to_m(nsymb), to_m(nt), to_m(nch)], 0)
+    G = it.globals['GSTATE']
+    G = G.copy()
+    G['SYMBOLRATE'] = to_m(rate)                                  # electricsource.m sets it
+    G['LAMBDA'] = to_m(synth.wdm_lambdas(nch, 1550.0, spac).reshape(1, -1))   # lasersource.m:163
+    G['POWER'] = to_m(np.full((1, nch), float(pavg)))
+    it.globals['GSTATE'] = G
+    opts = MStruct({'power': 'average'})
+    args = [ftype, to_m(ex), to_m(ey) if two_pol else np.zeros((0, 0)), opts]
+    it.call('create_field', args, 0)
+    return ex, ey
+
+
+def snapshot(it):
+    G = it.globals['GSTATE']
+    out = {'FIELDX': np.array(G['FIELDX'])}
+    fy = G['FIELDY']
+    out['FIELDY'] = np.array(fy) if isinstance(fy, np.ndarray) and fy.size else np.zeros((0, 0))
+    out['DELAY'] = np.array(G['DELAY'])
+    out['DISP'] = np.array(G['DISP'])
+    out['POWER'] = np.array(G['POWER'])
+    return out
+
+
+def run_case(name, nsymb, nt, nch, ftype, fib, flag, seed=1000, rate=28.0, pavg=2.0, two_pol=True, want_brf=True,
+             amp=None):
+    it = new_interp(seed)
+    ex, ey = tx_through_reference(it, nsymb, nt, nch, rate, pavg, ftype, two_pol)
+    pre = snapshot(it)
+    x = to_m(fib)
+    res = it.call('fiber', [x, flag], 1 if want_brf else 0)
+    post = snapshot(it)
+    data = {'in_ex': ex, 'in_ey': ey, 'tx_FIELDX': pre['FIELDX'], 'tx_FIELDY': pre['FIELDY'], 'tx_POWER': pre['POWER'],
+            'out_FIELDX': post['FIELDX'], 'out_FIELDY': post['FIELDY'], 'out_DELAY': post['DELAY'],
+            'out_DISP': post['DISP']}
+    meta = {'name': name, 'nsymb': nsymb, 'nt': nt, 'nch': nch, 'ftype': ftype, 'fiber': fib, 'flag': flag,
+            'seed': seed, 'rate': rate, 'pavg': pavg, 'two_pol': two_pol, 'warnings': it.warnings}
+    if want_brf and res:
+        brf = from_m(res[0])
+        for k in ('db0', 'theta', 'epsilon'):
+            data['brf_' + k] = np.asarray(brf[k]).ravel()
+        data['brf_lcorr'] = np.asarray(brf['lcorr']).ravel()
+        data['brf_betat'] = np.asarray(brf['betat'])
+        data['brf_db1'] = np.asarray(brf['db1'])
+    if amp is not None:                       # span boundary: ampliflat with file-backed noise (options.noise)
+        g = np.random.Generator(np.random.PCG64(seed + 7))
+        n = nsymb * nt
+        nfc = post['FIELDX'].shape[1]
+        noise = (g.standard_normal((n, 2 * nfc)) + 1j * g.standard_normal((n, 2 * nfc)))
+        opt = MStruct({'f': to_m(amp['f']), 'noise': to_m(noise)})
+        it.call('ampliflat', [to_m(amp['gain']), 'gain', opt], 0)
+        a = snapshot(it)
+        data.update(amp_noise=noise, amp_FIELDX=a['FIELDX'], amp_FIELDY=a['FIELDY'])
+        meta['amp'] = amp
+    data['meta'] = np.array(json.dumps(meta))
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **data)
+    print('%-28s N=%-6d flag=%s  |out|=%.6e' % (name, nsymb * nt, flag, np.linalg.norm(post['FIELDX'])))
+
+
+def fib(**kw):
+    f = dict(SMF)
+    f.update(kw)
+    return f
+
+
+if __name__ == '__main__':
+    run_case('lin_gvd_2pol', 256, 16, 1, 'unique', fib(length=1e5), 'g---', want_brf=True)
+    run_case('lin_pmd_20plates', 256, 16, 1, 'unique', fib(length=8e4, dgd=0.5, nplates=20), 'gp--')
+    run_case('cnlse_10plates_100km', 256, 16, 1, 'unique', fib(length=1e5, dgd=1.0, nplates=10, manakov='no'), 'gps-',
+             amp={'gain': 20.0, 'f': 5.0})
+    run_case('manakov_100plates_80km', 256, 16, 1, 'unique', fib(length=8e4, dgd=0.1, nplates=100, manakov='yes'), 'gps-',
+             amp={'gain': 16.0, 'f': 5.0})
+    run_case('cnlse_nopmd', 128, 16, 1, 'unique', fib(length=5e4), 'g-s-')
+    run_case('sep3_manakov', 128, 16, 3, 'sepfields', fib(length=5e4, dgd=0.3, nplates=20, manakov='yes', slope=0.057), 'gps-')
+    run_case('wdm3_unique_manakov', 128, 64, 3, 'unique', fib(length=4e4, dgd=0.2, nplates=10, manakov='yes'), 'gps-', pavg=1.0)
+    run_case('pmf_single', 128, 16, 1, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],
+                                                     epsilon=[0.1, 0.5, -0.3]), 'gps-')
+    run_case('scalar_gs', 256, 16, 1, 'unique', fib(length=5e4), 'g-s-', two_pol=False, want_brf=False)
+    run_case('scalar_sep3_gsx', 128, 16, 3, 'sepfields', fib(length=3e4, slope=0.057), 'g-sx', two_pol=False, want_brf=False)
+    run_case('scalar_spm_exact', 128, 16, 1, 'unique', fib(length=5e4), '--s-', two_pol=False, want_brf=False)
