@@ -107,10 +107,10 @@ if __name__ == '__main__':
              amp={'gain': 20.0, 'f': 5.0})
     run_case('manakov_100plates_80km', 256, 16, 1, 'unique', fib(length=8e4, dgd=0.1, nplates=100, manakov='yes'), 'gps-',
              amp={'gain': 16.0, 'f': 5.0})
-    run_case('cnlse_nopmd', 128, 16, 1, 'unique', fib(length=5e4), 'g-s-')
-    run_case('sep3_manakov', 128, 16, 3, 'sepfields', fib(length=5e4, dgd=0.3, nplates=20, manakov='yes', slope=0.057), 'gps-')
+    run_case('cnlse_nopmd', 256, 16, 1, 'unique', fib(length=5e4), 'g-s-')
+    run_case('sep3_manakov', 256, 16, 3, 'sepfields', fib(length=5e4, dgd=0.3, nplates=20, manakov='yes', slope=0.057), 'gps-')
     run_case('wdm3_unique_manakov', 128, 64, 3, 'unique', fib(length=4e4, dgd=0.2, nplates=10, manakov='yes'), 'gps-', pavg=1.0)
-    run_case('pmf_single', 128, 16, 1, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],
+    run_case('pmf_single', 256, 16, 1, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],
                                                      epsilon=[0.1, 0.5, -0.3]), 'gps-')
     run_case('scalar_gs', 256, 16, 1, 'unique', fib(length=5e4), 'g-s-', two_pol=False, want_brf=False)
     run_case('scalar_sep3_gsx', 128, 16, 3, 'sepfields', fib(length=3e4, slope=0.057), 'g-sx', two_pol=False, want_brf=False)
