@@ -193,6 +193,19 @@ int pmx_ampliflat_exec(pmx_ctx* ctx, pmx_devfield* f, double gain, const double*
 int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pat_dev, int64_t n,
                      int32_t batch, int64_t* counts_dev);
 
+/* ---- minimal coherent decision + error count for Monte-Carlo runs -------------------------
+ * Not the reference's dsp4cohdec.m: a data-aided stand-in used only to turn a propagated (and
+ * linearly equalised, see polmux_b200/mc.py) PDM-QPSK field into the INTEGER error count that
+ * ber_estimate.m:118 feeds its recursion with.  Per realization and polarization:
+ *   r_k = field[k*nt]                                 symbol-centre sample (samp2pat.m:60-67)
+ *   phi = angle(sum_k r_k conj(s_k))                  data-aided carrier phase
+ *   bits = (Re(r_k e^{-i phi}) > 0, Im(...) > 0)      Gray QPSK decision (pat_decoder.m:68-82)
+ *   counts[b] = #bits != transmitted bits, over both polarizations
+ * sym: HOST array [2][nsymb] of transmitted symbol indices 0..3 (bit0 -> sign Re, bit1 -> sign Im).
+ * counts_dev: DEVICE pointer to [batch] int64 (e.g. the NCCL send buffer), overwritten. */
+int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t nsymb, int32_t nt,
+                   int64_t* counts_dev);
+
 #ifdef __cplusplus
 }
 #endif

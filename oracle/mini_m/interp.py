@@ -683,11 +683,15 @@ class Interp:
     def getvar(self, ws, name):
         if name in ws['__globals__']:
             return self.globals.get(name)
+        if name in ws.get('__persist__', ()):
+            return self.persist[ws['__fname__']].get(name)
         return ws.get(name)
 
     def setvar(self, ws, name, val):
         if name in ws['__globals__']:
             self.globals[name] = val
+        elif name in ws.get('__persist__', ()):
+            self.persist[ws['__fname__']][name] = val
         else:
             ws[name] = val
 
@@ -762,11 +766,12 @@ class Interp:
                 ws['__globals__'].add(nm)
                 ws.pop(nm, None)
         elif kind == 'persistent':
-            key = ws['__fname__']
-            store = self.persist.setdefault(key, {})
+            store = self.persist.setdefault(ws['__fname__'], {})
+            ws.setdefault('__persist__', set())
             for nm in s[1]:
                 store.setdefault(nm, np.zeros((0, 0)))
-            raise MError('persistent variables are not supported')
+                ws['__persist__'].add(nm)
+                ws.pop(nm, None)
         elif kind == 'return':
             raise _Return()
         elif kind == 'break':

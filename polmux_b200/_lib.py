@@ -27,7 +27,7 @@ EXPORTS = [
     'pmx_field_upload', 'pmx_field_download', 'pmx_field_broadcast', 'pmx_field_device_ptr',
     'pmx_plan_create', 'pmx_plan_destroy', 'pmx_plan_set_plates', 'pmx_fiber_exec',
     'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
-    'pmx_ctx_profile_read',
+    'pmx_ctx_profile_read', 'pmx_qpsk_count',
 ]
 
 
@@ -106,6 +106,7 @@ def load():
     lib.pmx_fiber_exec.argtypes = [vp, vp, C.POINTER(FiberResult)]
     lib.pmx_ampliflat_exec.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64]
     lib.pmx_count_errors.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
+    lib.pmx_qpsk_count.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp]
     _lib = lib
     return lib
 
@@ -340,3 +341,10 @@ def ampliflat_exec(ctx: Context, field: DeviceField, gain: float, sigma, noise=N
                                          C.c_uint64(int(seed))))
     if n is not None:
         ctx.sync()
+
+
+def qpsk_count(ctx: Context, field: DeviceField, sym, nsymb: int, nt: int, counts_dev_ptr: int):
+    """Error counts of every realization of `field` into a device int64 buffer (pmx_qpsk_count)."""
+    s = np.ascontiguousarray(sym, dtype=np.uint8).reshape(2, nsymb)
+    ctx.check(ctx.lib.pmx_qpsk_count(ctx.h, field.h, s.ctypes.data_as(C.c_void_p), int(nsymb), int(nt),
+                                     C.c_void_p(int(counts_dev_ptr))))

@@ -1036,3 +1036,79 @@ extern "C" int pmx_count_errors(pmx_ctx* c, const uint8_t* hat, const uint8_t* p
     CK(c, cudaGetLastError());
     return PMX_OK;
 }
+
+// ---------------------------------------------------------------------------
+// data-aided QPSK decision + bit-error count (see the header)
+__global__ void __launch_bounds__(256) pmx_k_qpsk_phase(const cpx* field, const uint8_t* sym, int nsymb, int nt, size_t N,
+                                                        double* acc /*[batch][2][2]*/) {
+    const int b = blockIdx.y;
+    const cpx* fld = field + (size_t)b * N * 2;
+    double ax = 0, ay = 0, bx = 0, by = 0;  // sum r conj(s) for X (ax,ay) and Y (bx,by)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nsymb; k += gridDim.x * blockDim.x) {
+        cpx rx, ry;
+        ld_sa(fld + (size_t)k * nt * 2, rx, ry);
+        const int sx = sym[k], sy = sym[nsymb + k];
+        const double sxr = (sx & 1) ? 1.0 : -1.0, sxi = (sx & 2) ? 1.0 : -1.0;
+        const double syr = (sy & 1) ? 1.0 : -1.0, syi = (sy & 2) ? 1.0 : -1.0;
+        ax += rx.x * sxr + rx.y * sxi;
+        ay += rx.y * sxr - rx.x * sxi;
+        bx += ry.x * syr + ry.y * syi;
+        by += ry.y * syr - ry.x * syi;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        bx += __shfl_xor_sync(0xffffffffu, bx, o);
+        by += __shfl_xor_sync(0xffffffffu, by, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&acc[b * 4 + 0], ax);
+        atomicAdd(&acc[b * 4 + 1], ay);
+        atomicAdd(&acc[b * 4 + 2], bx);
+        atomicAdd(&acc[b * 4 + 3], by);
+    }
+}
+
+__global__ void __launch_bounds__(256) pmx_k_qpsk_count(const cpx* field, const uint8_t* sym, int nsymb, int nt, size_t N,
+                                                        const double* acc, unsigned long long* counts) {
+    const int b = blockIdx.y;
+    const cpx* fld = field + (size_t)b * N * 2;
+    // e^{-i phi} up to a positive factor: conj of the accumulated correlation
+    const double cxr = acc[b * 4 + 0], cxi = -acc[b * 4 + 1], cyr = acc[b * 4 + 2], cyi = -acc[b * 4 + 3];
+    unsigned int errs = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nsymb; k += gridDim.x * blockDim.x) {
+        cpx rx, ry;
+        ld_sa(fld + (size_t)k * nt * 2, rx, ry);
+        const double xr = rx.x * cxr - rx.y * cxi, xi = rx.x * cxi + rx.y * cxr;
+        const double yr = ry.x * cyr - ry.y * cyi, yi = ry.x * cyi + ry.y * cyr;
+        const int dx = (xr > 0 ? 1 : 0) | (xi > 0 ? 2 : 0), dy = (yr > 0 ? 1 : 0) | (yi > 0 ? 2 : 0);
+        errs += __popc((dx ^ sym[k]) & 3) + __popc((dy ^ sym[nsymb + k]) & 3);
+    }
+    for (int o = 16; o > 0; o >>= 1) errs += __shfl_xor_sync(0xffffffffu, errs, o);
+    if ((threadIdx.x & 31) == 0 && errs) atomicAdd(&counts[b], (unsigned long long)errs);
+}
+
+extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, int32_t nsymb, int32_t nt,
+                              int64_t* counts_dev) {
+    if (!c || !f || !sym || !counts_dev) return set_err(c, PMX_ERR_INVALID, "pmx_qpsk_count: null argument");
+    if (f->nfc != 1) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_qpsk_count: single-column ('unique') fields only");
+    if ((int64_t)nsymb * nt != f->nfft) return set_err(c, PMX_ERR_INVALID, "pmx_qpsk_count: nsymb*nt must equal nfft");
+    CK(c, cudaSetDevice(c->device));
+    uint8_t* dsym = nullptr;
+    double* acc = nullptr;
+    CK(c, cudaMallocAsync(&dsym, 2 * (size_t)nsymb, c->stream));
+    CK(c, cudaMallocAsync(&acc, (size_t)f->batch * 4 * sizeof(double), c->stream));
+    CK(c, cudaMemcpyAsync(dsym, sym, 2 * (size_t)nsymb, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(acc, 0, (size_t)f->batch * 4 * sizeof(double), c->stream));
+    CK(c, cudaMemsetAsync(counts_dev, 0, (size_t)f->batch * sizeof(int64_t), c->stream));
+    dim3 g((unsigned)std::min((nsymb + 255) / 256, 148), f->batch);
+    pmx_k_qpsk_phase<<<g, 256, 0, c->stream>>>(f->data, dsym, nsymb, nt, (size_t)f->nfft, acc);
+    pmx_k_qpsk_count<<<g, 256, 0, c->stream>>>(f->data, dsym, nsymb, nt, (size_t)f->nfft, acc,
+                                                (unsigned long long*)counts_dev);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CK(c, cudaFreeAsync(dsym, c->stream));
+    CK(c, cudaFreeAsync(acc, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));  // `sym` is a host buffer of the caller
+    return PMX_OK;
+}

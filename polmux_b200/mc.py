@@ -1,0 +1,195 @@
+"""Batched Monte-Carlo over independent realizations: the one axis the path shards on.
+
+The reference runs realizations one after another in `while cond` loops
+(ex20_coherent_polmux.m:131-181) and feeds the integer error count of each block to
+ber_estimate (ber_estimate.m:118).  Here a group of realizations (same Tx field, different
+waveplate draws and ASE seeds) is resident in HBM and advances through the whole link --
+nspan x [fiber(x,'gps-') ; ampliflat(G,'gain',{f})] -- without returning to the host; groups
+are sharded contiguously over the ranks (one process per GPU) and the only collective is an
+integer all-reduce (NCCL) of the per-realization error counts.  The host then replays
+ber_estimate's order-dependent recursion in realization order, so the estimate is the same
+whatever the number of GPUs.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .ampliflat import ase_sigma
+from .fiber import FiberSetup, setup_to_desc
+
+
+def draw_plates(seed: int, nplates: int):
+    """fiber.m:274-276 with the stream of one realization/span."""
+    r = np.random.Generator(np.random.PCG64(int(seed)))
+    db0 = r.random(nplates) * 2 * np.pi - np.pi
+    theta = r.random(nplates) * np.pi - 0.5 * np.pi
+    eps = 0.5 * np.arcsin(r.random(nplates) * 2 - 1)
+    return db0, theta, eps
+
+
+def plate_seed(realization: int, span: int) -> int:
+    return 1000 + int(realization) + 100000 * int(span)
+
+
+def shard(nreal: int, rank: int, world: int):
+    """contiguous realization groups: rank g owns [floor(g*n/G), floor((g+1)*n/G))  """
+    return (rank * nreal) // world, ((rank + 1) * nreal) // world
+
+
+class Link:
+    """nspan identical spans resident on one GPU, for a batch of realizations."""
+
+    def __init__(self, ctx: _lib.Context, setup: FiberSetup, nspan: int, batch: int, gain_db: float,
+                 nf_db: Optional[float], first_realization: int = 0):
+        self.ctx, self.setup, self.nspan, self.batch = ctx, setup, nspan, batch
+        self.first = first_realization
+        self.gain = 10 ** (gain_db * 0.1)
+        self.sigma = ase_sigma(self.gain, nf_db, setup.nfc)
+        self.plates = [self._plates(k, first_realization) for k in range(nspan)]
+        desc, keep = setup_to_desc(setup, batch=batch, plate_sets=batch, db0=self.plates[0][0],
+                                   theta=self.plates[0][1], epsilon=self.plates[0][2])
+        self.plan = _lib.Plan(ctx, desc, keep)
+        self._inv = None
+
+    def _plates(self, span, first):
+        d = [draw_plates(plate_seed(first + b, span), self.setup.nplates) for b in range(self.batch)]
+        return tuple(np.stack([x[i] for x in d]) for i in range(3))
+
+    def retarget(self, first_realization: int):
+        """same link, next group of realizations (new plate draws)"""
+        self.first = first_realization
+        self.plates = [self._plates(k, first_realization) for k in range(self.nspan)]
+
+    def run(self, field: _lib.DeviceField, ase_seed: int, noise_fn=None) -> int:
+        """propagate the resident batch through every span; -> Sa*steps done.
+        noise_fn(span) -> [batch][2*nfc][nfft] complex standard normals (ampliflat's options.noise,
+        for parity runs); default: the device's counter-based generator keyed by (seed, span, realization)."""
+        n = self.setup.nfft
+        sa_steps = 0
+        self.ncycles = []
+        for k in range(self.nspan):
+            self.plan.set_plates(*self.plates[k], plate_sets=self.batch)
+            res = self.plan.execute(field)
+            self.ncycles.append(res.ncycle.copy())
+            sa_steps += int(res.ncycle.sum()) * n * self.setup.nfc
+            _lib.ampliflat_exec(self.ctx, field, self.gain, self.sigma, None if noise_fn is None else noise_fn(k),
+                                seed=self.ase_seed(ase_seed, k))
+        return sa_steps
+
+    def ase_seed(self, ase_seed: int, span: int) -> int:
+        return ((int(ase_seed) & 0xffffff) << 40) + (span << 32) + self.first
+
+    def equalize(self, field: _lib.DeviceField):
+        """Ideal linear equaliser: undo GVD and PMD of every span, last span first.  One linear
+        single-step fiber per span with the plate order reversed and every phase negated
+        (the inverse of prod_k R_k D_k R_k' is the same product with D_k -> D_k^-1 taken backwards,
+        cf. inverse_pmd.m:100-124); attenuation was already undone by the amplifiers."""
+        s = self.setup
+        if self._inv is None:
+            sc = dict(s.scalars)
+            sc.update(b30=-sc['b30'], dgdrms=-sc['dgdrms'], beta1=-np.asarray(sc['beta1']),
+                      beta2=-np.asarray(sc['beta2']))
+            inv = FiberSetup(nfft=s.nfft, nfc=s.nfc, fls=(s.fls[0], s.fls[1], 0, 0), dphimaxt=math.inf,
+                             dzmaxt=s.length, length=s.length, alphalin=0.0, gam=s.gam, betat=-s.betat, db1=-s.db1,
+                             manakov=False, nplates=s.nplates, brf=s.brf, isv=True, isy=True, b1=s.b1, dch=s.dch,
+                             scalars=sc)
+            desc, keep = setup_to_desc(inv, batch=self.batch, plate_sets=self.batch, db0=-self.plates[0][0][:, ::-1],
+                                       theta=self.plates[0][1][:, ::-1], epsilon=self.plates[0][2][:, ::-1])
+            self._inv = _lib.Plan(self.ctx, desc, keep)
+        for k in reversed(range(self.nspan)):
+            db0, th, ep = self.plates[k]
+            self._inv.set_plates(-db0[:, ::-1], th[:, ::-1], ep[:, ::-1], plate_sets=self.batch)
+            self._inv.execute(field)
+
+
+# ------------------------------------------------------------------------------------------
+@dataclass
+class BerState:
+    """persistent variables of ber_estimate.m:103 (scalar case, x.dim == 1)"""
+    n: int = 1
+    avgber: float = 0.0
+    varber: float = 0.0
+    cond: bool = True
+
+
+def ber_update(st: BerState, err: int, M: int, stop=(0.1, 68.0), nmin: int = 1):
+    """One call of mc_run, ber_estimate.m:107-142, with the integer error count of a block of M
+    bits.  -> (cond, avgber, nruns, stdber)."""
+    eps = math.sqrt(2) * _erfcinv(1 - stop[1] / 100)
+    nnew = st.n * M
+    N = (st.n - 1) * M
+    varerr = (err - err ** 2 / M) / (M - 1)
+    avgerr = err / M
+    st.varber = ((N - 1) * st.varber + (M - 1) * varerr + N * M / (N + M) * (st.avgber - avgerr) ** 2) / (N + M - 1)
+    st.avgber = ((st.n - 1) * st.avgber + avgerr) / st.n
+    stdber = math.sqrt(st.varber / (N + M))
+    if eps * stdber < stop[0] * st.avgber and st.avgber * nnew >= nmin:
+        st.cond = False
+    st.n += 1
+    return st.cond, st.avgber, (st.n - 1) * M, stdber
+
+
+def _erfcinv(x):
+    from scipy.special import erfcinv
+    return float(erfcinv(x))
+
+
+def ber_replay(counts, bits_per_realization: int, stop=(0.1, 68.0), nmin: int = 1):
+    """Feed per-realization counts to the recursion in realization order; stops where the
+    reference's `while cond` loop would."""
+    st = BerState()
+    out = None
+    for k, e in enumerate(counts):
+        out = ber_update(st, int(e), bits_per_realization, stop, nmin)
+        if not out[0]:
+            return {'avgber': out[1], 'nbits': out[2], 'stdber': out[3], 'realizations_used': k + 1, 'converged': True}
+    return {'avgber': out[1], 'nbits': out[2], 'stdber': out[3], 'realizations_used': len(counts), 'converged': False}
+
+
+def allreduce_counts(local_counts, r0: int, nreal: int, device=None):
+    """Zero-padded [nreal] int64 vector with this rank's slice filled, summed over the ranks
+    (torch.distributed: NCCL on GPUs, gloo in the CPU tests).  Integer, hence order-independent
+    and bit-exact."""
+    import torch
+    import torch.distributed as dist
+    if isinstance(local_counts, torch.Tensor):
+        full = torch.zeros(nreal, dtype=torch.int64, device=local_counts.device)
+        full[r0:r0 + local_counts.numel()] = local_counts
+    else:
+        full = torch.zeros(nreal, dtype=torch.int64, device=device or 'cpu')
+        full[r0:r0 + len(local_counts)] = torch.as_tensor(np.asarray(local_counts, dtype=np.int64))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM)
+    return full
+
+
+def run_mc(ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int, gain_db: float,
+           nf_db: float, nreal: int, batch: int, rank: int = 0, world: int = 1, ase_seed: int = 1):
+    """Monte-Carlo BER of `nreal` realizations sharded over `world` ranks.
+    -> (counts [nreal] int64 on the host, Sa*steps done by this rank)"""
+    import torch
+    r0, r1 = shard(nreal, rank, world)
+    dev = torch.device('cuda', ctx.device)
+    local = torch.zeros(max(r1 - r0, 0), dtype=torch.int64, device=dev)
+    tx = _lib.DeviceField(ctx, setup.nfft, setup.nfc, 1)
+    tx.upload(tx_x, tx_y)
+    work = _lib.DeviceField(ctx, setup.nfft, setup.nfc, batch)
+    link = Link(ctx, setup, nspan, batch, gain_db, nf_db, r0)
+    sa_steps = 0
+    buf = torch.zeros(batch, dtype=torch.int64, device=dev)
+    for g0 in range(r0, r1, batch):
+        torch.cuda.synchronize(dev)                                  # torch's stream and the library's are independent
+        nb = min(batch, r1 - g0)
+        link.retarget(g0)
+        work.broadcast_from(tx)
+        sa_steps += link.run(work, ase_seed)
+        link.equalize(work)
+        _lib.qpsk_count(ctx, work, sym, nsymb, nt, buf.data_ptr())   # the kernel writes the send buffer
+        local[g0 - r0:g0 - r0 + nb] = buf[:nb]
+    counts = allreduce_counts(local, r0, nreal)
+    return counts.cpu().numpy(), sa_steps
