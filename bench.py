@@ -12,7 +12,9 @@ larger than the 126 MB L2.
          library's stream, max over ranks
   e2e    the same metric through the reference-facing calls fiber(x,'gps-') + ampliflat()
          on HOST buffers (pinned), H2D and D2H of the field inside every call
-  roofline      dominant kernel (pass B) algorithmic bytes / its mean launch time (CUDA events)
+  roofline      dominant pass kernel: 64 algorithmic bytes per live Sa and step / its device time
+                (CUDA events around every launch of one extra, profiled link pass)
+  mc            bounded Monte-Carlo BER leg: link + equaliser + on-GPU error count + integer all-reduce
   cpu_baseline  the numpy oracle (op-for-op restatement of fiber.m) on one host core, on a
                 bounded sample of the same workload
 
@@ -44,15 +46,6 @@ def fiber_params(length_m, nplates):
     f = dict(synth.SMF)
     f.update(length=length_m, dgd=DGD, nplates=nplates, manakov='yes')
     return f
-
-
-def plate_draw(seed, nplates):
-    """fiber.m:274-276 with the stream of realization `seed`."""
-    r = np.random.Generator(np.random.PCG64(seed))
-    db0 = r.random(nplates) * 2 * np.pi - np.pi
-    theta = r.random(nplates) * np.pi - 0.5 * np.pi
-    eps = 0.5 * np.arcsin(r.random(nplates) * 2 - 1)
-    return db0, theta, eps
 
 
 class ClockSampler(threading.Thread):
@@ -153,6 +146,8 @@ def main():
     ap.add_argument('--batch', type=int, default=8, help='realizations per GPU per step')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-mc', action='store_true')
+    ap.add_argument('--mc-groups', type=int, default=1, help='Monte-Carlo leg: groups of `batch` realizations per rank')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -166,8 +161,7 @@ def main():
     import torch.distributed as dist
     import polmux_b200 as pmx
     from polmux_b200 import _lib, synth
-    from polmux_b200.ampliflat import ase_sigma
-    from polmux_b200.fiber import fiber_setup, setup_to_desc
+    from polmux_b200.fiber import fiber_setup
 
     torch.cuda.set_device(local)
     if world > 1:
@@ -177,7 +171,7 @@ def main():
 
     # ---- Tx field (host, seeded) and fiber set-up
     N = NSYMB * NT
-    ex, ey, _, _ = synth.pdm_qpsk(NSYMB, NT, 1)
+    ex, ey, symx, symy = synth.pdm_qpsk(NSYMB, NT, 1)
     pmx.reset_all(NSYMB, NT, 1)
     G = pmx.GSTATE
     G.SYMBOLRATE, G.LAMBDA, G.POWER = RATE, np.array([1550.0]), np.array([PAVG])
@@ -185,18 +179,10 @@ def main():
     fib = fiber_params(SPAN_KM * 1e3, NPLATES)
     setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
     B = args.batch
-    gain = 10 ** (GAIN_DB * 0.1)
-    sigma = ase_sigma(gain, NF_DB, 1)
 
-    # plate draws: realization r (global index), span k -> seed 1000 + r + 100000*k
-    def plates_for(span):
-        d = [plate_draw(1000 + rank * B + b + 100000 * span, NPLATES) for b in range(B)]
-        return (np.stack([x[0] for x in d]), np.stack([x[1] for x in d]), np.stack([x[2] for x in d]))
-
-    span_plates = [plates_for(k) for k in range(NSPAN)]
-    desc, keep = setup_to_desc(setup, batch=B, plate_sets=B, db0=span_plates[0][0], theta=span_plates[0][1],
-                               epsilon=span_plates[0][2])
-    plan = _lib.Plan(ctx, desc, keep)
+    # realization r (global index) of span k draws its plates from seed 1000 + r + 100000*k (polmux_b200.mc)
+    from polmux_b200 import mc
+    link = mc.Link(ctx, setup, NSPAN, B, GAIN_DB, NF_DB, first_realization=rank * B)
     tx = _lib.DeviceField(ctx, N, 1, 1)
     tx.upload(G.FIELDX, G.FIELDY)
     work = _lib.DeviceField(ctx, N, 1, B)
@@ -204,13 +190,7 @@ def main():
     def link_step(step_id):
         """one pass of the 10-span link over the resident batch -> Sa*steps done"""
         work.broadcast_from(tx)
-        sa_steps = 0
-        for k in range(NSPAN):
-            plan.set_plates(*span_plates[k], plate_sets=B)
-            res = plan.execute(work)
-            sa_steps += int(res.ncycle.sum()) * N
-            _lib.ampliflat_exec(ctx, work, gain, sigma, None, seed=(step_id << 20) + (k << 8) + rank)
-        return sa_steps
+        return link.run(work, ase_seed=step_id)
 
     def barrier():
         ctx.sync()
@@ -249,7 +229,7 @@ def main():
 
     # ---- per-pass timing (separate, profiled pass over one link step; events around every launch)
     ctx.profile(True)
-    link_step(999)
+    prof_sa_steps = link_step(999)
     pms, pn = ctx.profile_read()
     ctx.profile(False)
     roof = None
@@ -263,17 +243,40 @@ def main():
     if pn[1] > 0:
         names = ['passA', 'passB', 'passC']
         dom = int(np.argmax(pms[:3]))
-        t_launch = pms[dom] / pn[dom] * 1e-3
-        bytes_launch = 64.0 * N * B       # one pass reads and writes every Sa of the batch once
-        ach = bytes_launch / t_launch / 1e9
+        # every live Sa is read and written once per pass and per step: 64 algorithmic bytes.  Launches
+        # that find their realizations finished exit at once; they count as launches, not as bytes.
+        alg_bytes = 64.0 * prof_sa_steps
+        ach = alg_bytes / (pms[dom] * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'kernel': names[dom], 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
-                'bytes_per_launch': bytes_launch, 'ms_per_launch': t_launch * 1e3,
-                'pass_ms_per_launch': {names[i]: (pms[i] / pn[i] if pn[i] else None) for i in range(3)},
-                'note': 'launch durations include early-exit launches of finished realizations'}
+                'bytes_per_launch': alg_bytes / float(pn[dom]), 'ms_per_launch': pms[dom] / float(pn[dom]),
+                'launches_timed': int(pn[dom]),
+                'pass_share_of_step': {names[i]: float(pms[i] / pms[:3].sum()) for i in range(3)},
+                'pass_gbs': {names[i]: alg_bytes / (pms[i] * 1e-3) / 1e9 for i in range(3)}}
     step_roof = {'achieved': ALG_BYTES_PER_SA_STEP * value / world, 'peak': peak, 'unit': 'GB/s',
                  'frac': ALG_BYTES_PER_SA_STEP * value / world / peak, 'bytes_per_sa_step': ALG_BYTES_PER_SA_STEP,
                  'per': 'GPU'}
+
+    # ---- Monte-Carlo BER leg (config C5, bounded): link + linear equaliser + on-GPU error counter,
+    # counts all-reduced over the ranks (NCCL), ber_estimate's recursion replayed on the host
+    mcres = None
+    if not args.no_mc:
+        sym = np.stack([symx[:, 0], symy[:, 0]]).astype(np.uint8)
+        nreal = B * world * args.mc_groups
+        barrier()
+        t0 = time.perf_counter()
+        counts, _ = mc.run_mc(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nreal, B,
+                              rank, world, ase_seed=7)
+        barrier()
+        dt = time.perf_counter() - t0
+        tdt = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        rep = mc.ber_replay(counts, 4 * NSYMB, stop=(0.1, 68.0), nmin=100)
+        mcres = {'realizations_per_s': nreal / float(tdt[0]), 'realizations': nreal, 'seconds': float(tdt[0]),
+                 'errors_total': int(counts.sum()), 'bits_per_realization': 4 * NSYMB, 'avgber': rep['avgber'],
+                 'count_reduce': 'all_reduce(int64[%d], sum) over %d rank(s), backend %s'
+                                 % (nreal, world, 'nccl' if world > 1 else 'none (single rank)')}
 
     # ---- e2e: reference-style calls on host buffers (one realization, all spans)
     e2e = None
@@ -332,7 +335,7 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': workload_config(args, world), 'clocks': sampler.summary(),
                 'e2e': e2e, 'gpu_launches': int(gpu_launches), 'roofline': roof, 'roofline_step': step_roof,
-                'cpu_baseline': cpu, 'sa_steps_per_step': total_all / max(args.steps, 1)}
+                'cpu_baseline': cpu, 'mc': mcres, 'sa_steps_per_step': total_all / max(args.steps, 1)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

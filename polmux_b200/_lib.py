@@ -284,6 +284,16 @@ class DeviceField:
         self.ctx.check(self.ctx.lib.pmx_field_download(self.h, C.byref(f), b0, nb))
         return x, y
 
+    def download_into(self, x: np.ndarray, y: np.ndarray, b0=0, nb=None):
+        """D2H straight into caller-owned C-contiguous complex128 buffers of nb*nfc*nfft elements
+        (keeps pinned buffers pinned)."""
+        nb = self.batch if nb is None else nb
+        for a in (x, y):
+            if a.dtype != np.complex128 or not a.flags['C_CONTIGUOUS'] or a.size != nb * self.nfc * self.nfft:
+                raise ValueError('download_into needs C-contiguous complex128 buffers of the field size')
+        f = complex_field(x, y)
+        self.ctx.check(self.ctx.lib.pmx_field_download(self.h, C.byref(f), b0, nb))
+
     def broadcast_from(self, src: 'DeviceField'):
         self.ctx.check(self.ctx.lib.pmx_field_broadcast(self.h, src.h))
 

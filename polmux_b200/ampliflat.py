@@ -47,6 +47,12 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
         nz = np.asarray(options['noise'], dtype=np.complex128)
         noise = np.ascontiguousarray(nz.T)[None]                 # [1][2*nfc][nfft]
     _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed)
+    inplace = (nfc == 1 and G.FIELDY is not None and all(
+        a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and a.flags['WRITEABLE'] for a in (G.FIELDX, G.FIELDY)))
+    if inplace:          # single column: [N,1] is also [1][1][N]; results land in the caller's buffers
+        fld.download_into(G.FIELDX, G.FIELDY)
+        fld.close()
+        return
     ox, oy = fld.download()
     fld.close()
     G.FIELDX = np.ascontiguousarray(ox[0].T)

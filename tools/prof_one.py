@@ -23,7 +23,8 @@ G.SYMBOLRATE, G.LAMBDA, G.POWER = bench.RATE, np.array([1550.0]), np.array([benc
 pmx.create_field('unique', ex, ey, {'power': 'average'})
 fib = bench.fiber_params(bench.SPAN_KM * 1e3, bench.NPLATES)
 setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
-d = [bench.plate_draw(1000 + b, bench.NPLATES) for b in range(B)]
+from polmux_b200 import mc  # noqa: E402
+d = [mc.draw_plates(1000 + b, bench.NPLATES) for b in range(B)]
 pl = [np.stack([x[i] for x in d]) for i in range(3)]
 ctx = _lib.Context(0)
 desc, keep = setup_to_desc(setup, batch=B, plate_sets=B, db0=pl[0], theta=pl[1], epsilon=pl[2])
