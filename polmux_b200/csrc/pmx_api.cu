@@ -45,8 +45,8 @@ void pmx_fill_stage_twiddles(int L, cpx* out) {
     size_t o = 0;
     while (ns < L) {
         int R = pmx_stage_radix(L, ns);
-        if (ns > 1) {
-            for (int r = 1; r < R; ++r)
+        if (ns > 1) {  // radix-8 stage: W^k, W^2k, W^4k of W = exp(-2*pi*i/(8*ns))
+            for (int r = 1; r <= 4; r *= 2)
                 for (int k = 0; k < ns; ++k) out[o++] = pmx_root((long long)k * r, (long long)ns * R);
         }
         ns *= R;
@@ -312,6 +312,21 @@ extern "C" int pmx_ctx_profile_read(pmx_ctx* c, double* ms, int64_t* n) {
         ms[k] = c->prof_ms[k];
         n[k] = c->prof_n[k];
     }
+    return PMX_OK;
+}
+
+// debug: per-phase cycle counters of the pass kernels (PMX_TIMING builds); 24 x int64 device buffer
+static long long* g_dbg = nullptr;
+extern "C" int pmx_debug_timing(pmx_ctx* c, long long* out24, int reset) {
+    if (!c) return PMX_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (!g_dbg) {
+        cudaMalloc(&g_dbg, 24 * sizeof(long long));
+        cudaMemset(g_dbg, 0, 24 * sizeof(long long));
+    }
+    cudaStreamSynchronize(c->stream);
+    if (out24) cudaMemcpy(out24, g_dbg, 24 * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(g_dbg, 0, 24 * sizeof(long long));
     return PMX_OK;
 }
 
@@ -829,6 +844,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     pa.log2N1 = p->log2N1;
     pa.log2N2 = p->log2N2;
     pa.batch = batch;
+    pa.dbg = g_dbg;
     FourStepTw ft;
     rc = get_four_tw(c, p->d.nfft, p->log2N1 + p->log2N2, &ft);
     if (rc) return rc;

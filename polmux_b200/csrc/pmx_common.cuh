@@ -83,6 +83,7 @@ struct PassParams {
     int N1, N2, log2N1, log2N2;
     int lo_bits;
     int batch;
+    long long* dbg;         // optional per-CTA phase cycle counters (PMX_TIMING builds only)
 };
 
 __device__ __forceinline__ cpx cmul(cpx a, cpx b) {

@@ -1,40 +1,45 @@
-// In-CTA Stockham FFT of length L (power of two, 8..4096) on a two-polarization
+// In-CTA Stockham FFT of length L (power of two, 64..4096) on a two-polarization
 // row, FP64.  L/8 threads cooperate on one row; each thread keeps 8 samples of
 // BOTH polarizations in registers (element q <-> index t + q*T, T = L/8) through
-// every stage, so the first stage can be fed straight from global memory, the
+// every stage, so the first stage can be fed straight from the landed tile, the
 // last stage leaves the spectrum in registers for the per-bin Jones product,
-// and the inverse transform starts from those same registers.  Stages are
-// radix 8, the last one radix 2 or 4 when log2(L) is not a multiple of 3;
-// between stages the data is exchanged through padded shared memory
-// (index i -> i + (i>>3), bank-conflict free for both the scattered stage
-// writes and the strided reads).
+// and the inverse transform starts from those same registers.  The first stage
+// is radix 2 or 4 when log2(L) is not a multiple of 3 (it needs no twiddles),
+// every other stage is radix 8; between stages the data is exchanged through
+// shared memory with an XOR swizzle (index i -> i ^ ((i>>3)&7), bank-conflict
+// free for the scattered stage writes and the strided reads, no padding).
 //
 // Stage (radix R, Ns = product of earlier radices), butterfly j in [0, L/R):
 //   in : v[r] = x[j + r*L/R] * W_{Ns*R}^{(j mod Ns)*r}
 //   out: x'[(j - j mod Ns)*R + (j mod Ns) + r*Ns] = DFT_R(v)[r]
 // (natural order in, natural order out after the last stage).
+//
+// Twiddles of a radix-8 stage: W^k, W^2k, W^4k come from a shared-memory table
+// ([3][Ns] per stage, conflict-free), W^3k, W^5k, W^6k, W^7k are four products.
 #pragma once
 #include "pmx_common.cuh"
 
 #define PMX_SQRT1_2 0.70710678118654752440
 
 __host__ __device__ constexpr int pmx_ilog2(int v) { return v <= 1 ? 0 : 1 + pmx_ilog2(v >> 1); }
-__host__ __device__ constexpr int pmx_pad(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int pmx_sw(int i) { return i ^ ((i >> 3) & 7); }
 
 // radix of the stage that starts with Ns already done
-__host__ __device__ constexpr int pmx_stage_radix(int L, int Ns) { return (L / Ns) >= 8 ? 8 : (L / Ns); }
+__host__ __device__ constexpr int pmx_stage_radix(int L, int Ns) {
+    return (Ns == 1 && (pmx_ilog2(L) % 3) != 0) ? (1 << (pmx_ilog2(L) % 3)) : 8;
+}
 // offset (in cpx) of the twiddle block of the stage starting at Ns within the per-L table
 __host__ __device__ constexpr int pmx_tw_offset(int L, int Ns) {
     int off = 0;
     int ns = 1;
     while (ns < Ns) {
         int r = pmx_stage_radix(L, ns);
-        if (ns > 1) off += (r - 1) * ns;
+        if (ns > 1) off += 3 * ns;
         ns *= r;
     }
     return off;
 }
-__host__ __device__ constexpr int pmx_tw_total(int L) { return pmx_tw_offset(L, L); }
+__host__ __device__ constexpr int pmx_tw_total(int L) { return pmx_tw_offset(L, L) > 0 ? pmx_tw_offset(L, L) : 1; }
 
 template <bool INV>
 __device__ __forceinline__ cpx mul_mj(cpx a) {  // forward: *(-i); inverse: *(+i)
@@ -88,28 +93,37 @@ __device__ __forceinline__ void dft8(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4
 template <int L, bool INV>
 struct CtaFFT {
     static constexpr int T = L / 8;
-    static constexpr int SMEM_CPX_PER_POL = pmx_pad(L);  // padded length of one polarization
 
     template <int NS>
     __device__ __forceinline__ static void stage(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t,
-                                                 const cpx* __restrict__ tw) {
+                                                 const cpx* tw) {
         constexpr int R = pmx_stage_radix(L, NS);
         constexpr int NB = 8 / R;
         constexpr bool LAST = (NS * R == L);
         constexpr int TWO = pmx_tw_offset(L, NS);
+        static_assert(NS == 1 || R == 8, "only the first stage may have a small radix");
+        if constexpr (NS > 1) {
+            const int k = t & (NS - 1);
+            cpx w1 = tw[TWO + k], w2 = tw[TWO + NS + k], w4 = tw[TWO + 2 * NS + k];
+            if (INV) {
+                w1.y = -w1.y;
+                w2.y = -w2.y;
+                w4.y = -w4.y;
+            }
+            const cpx w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
+            const cpx w7 = cmul(w4, w3);
+            x[1] = cmul(x[1], w1); y[1] = cmul(y[1], w1);
+            x[2] = cmul(x[2], w2); y[2] = cmul(y[2], w2);
+            x[3] = cmul(x[3], w3); y[3] = cmul(y[3], w3);
+            x[4] = cmul(x[4], w4); y[4] = cmul(y[4], w4);
+            x[5] = cmul(x[5], w5); y[5] = cmul(y[5], w5);
+            x[6] = cmul(x[6], w6); y[6] = cmul(y[6], w6);
+            x[7] = cmul(x[7], w7); y[7] = cmul(y[7], w7);
+        }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const int j = t + b * T;
             const int k = j & (NS - 1);
-            if constexpr (NS > 1) {
-#pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    cpx w = __ldg(&tw[TWO + (r - 1) * NS + k]);
-                    if (INV) w.y = -w.y;
-                    x[b + NB * r] = cmul(x[b + NB * r], w);
-                    y[b + NB * r] = cmul(y[b + NB * r], w);
-                }
-            }
             if constexpr (R == 8) {
                 dft8<INV>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
                 dft8<INV>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
@@ -124,7 +138,7 @@ struct CtaFFT {
                 const int j0 = (j - k) * R + k;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int o = pmx_pad(j0 + r * NS);
+                    const int o = pmx_sw(j0 + r * NS);
                     sx[o] = x[b + NB * r];
                     sy[o] = y[b + NB * r];
                 }
@@ -134,7 +148,7 @@ struct CtaFFT {
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int o = pmx_pad(t + q * T);
+                const int o = pmx_sw(t + q * T);
                 x[q] = sx[o];
                 y[q] = sy[o];
             }
@@ -143,9 +157,9 @@ struct CtaFFT {
         }
     }
 
-    // x[q], y[q] hold element t + q*T on entry and on exit (natural order).
-    __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t,
-                                               const cpx* __restrict__ tw) {
+    // x[q], y[q] hold element t + q*T on entry and on exit (natural order).  tw: shared-memory
+    // copy of the per-L stage table.
+    __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t, const cpx* tw) {
         stage<1>(x, y, sx, sy, t, tw);
     }
 };

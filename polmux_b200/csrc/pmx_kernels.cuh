@@ -186,32 +186,41 @@ static __global__ void __launch_bounds__(256) pmx_k_init(PassParams p, FiberCons
                           p.trace_ntrunk);
 }
 
-// smem region stride (in cpx) between the rows/columns a CTA works on: padded so
+// smem region stride (in cpx) between the rows/columns a CTA works on: offset so
 // that lanes of different regions fall in different 16-byte bank groups.
 template <int L, int GROUP>
 struct PmxSmem {
-    static constexpr int BASE = ((2 * pmx_pad(L) + 7) / 8) * 8;
+    static constexpr int BASE = 2 * L;
     static constexpr int OFF = (GROUP > 1) ? ((8 / GROUP) > 0 ? (8 / GROUP) : 1) : 0;
     static constexpr int STRIDE = BASE + OFF;
 };
 
 // Shared-memory plan of a pass CTA working on G rows (pass B) or G columns (passes A, C) of
 // length L.  PF: the next tile is prefetched by TMA into its own landing buffer while the
-// current one is computed; !PF (long rows): the tile lands in the exchange buffer itself and
-// the next load is issued as soon as the last exchange of the current tile is over.
-template <int L, int G, bool PF>
+// current one is computed; !PF: the tile lands in the exchange buffer itself and the next load
+// is issued as soon as the last exchange of the current tile is over.
+template <int L, int G, bool PF, int NPLATE = 0>
 struct PassSmem {
     static constexpr int T = L / 8;
     static constexpr int THREADS = G * T;
     static constexpr int TILE_BYTES = G * L * 32;
     static constexpr int WORK_BYTES = G * PmxSmem<L, G>::STRIDE * 16;
     static constexpr int WORK_OFF = PF ? ((TILE_BYTES + 1023) / 1024) * 1024 : 0;
-    static constexpr int GTAB_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;
-    static constexpr int RED_OFF = GTAB_OFF + G * 8 * 16;
+    static constexpr int TW_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;   // stage twiddles
+    static constexpr int GTAB_OFF = TW_OFF + pmx_tw_total(L) * 16;
+    static constexpr int PLATE_CAP = NPLATE;                   // trunks of the step staged in smem (pass B)
+    static constexpr int PLATE_OFF = GTAB_OFF + G * 8 * 16;
+    static constexpr int RED_OFF = PLATE_OFF + PLATE_CAP * (int)sizeof(PlateConst);
     static constexpr int MBAR_OFF = RED_OFF + 32 * 8;
     static constexpr int TOTAL = MBAR_OFF + 16 + 1024;  // + slack to align the base to 1024 B
     static_assert(WORK_BYTES >= TILE_BYTES, "exchange buffer must hold a landed tile");
 };
+
+// copy the per-L stage-twiddle table into shared memory (once per persistent CTA)
+template <int L>
+__device__ __forceinline__ void pmx_load_stage_tw(cpx* dst, const cpx* __restrict__ src) {
+    for (int i = threadIdx.x; i < pmx_tw_total(L); i += blockDim.x) dst[i] = __ldg(&src[i]);
+}
 
 __device__ __forceinline__ unsigned char* pmx_align1024(unsigned char* p) {
     return p + ((1024u - (pmx_smem_u32(p) & 1023u)) & 1023u);
@@ -222,6 +231,16 @@ __device__ __forceinline__ cpx pmx_twiddle4(const PassParams& p, unsigned m) {
     cpx l = __ldg(&p.tw_lo[m & ((1u << p.lo_bits) - 1u)]);
     return cmul(h, l);
 }
+
+#ifdef PMX_TIMING
+#define PMX_T_DECL long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long t_last = clock64();
+#define PMX_T_MARK(i) { long long t_now = clock64(); t_ph[i] += t_now - t_last; t_last = t_now; }
+#define PMX_T_FLUSH(kind) if (p.dbg && threadIdx.x == 0) { for (int i = 0; i < 8; ++i) atomicAdd((unsigned long long*)&p.dbg[(kind) * 8 + i], (unsigned long long)t_ph[i]); }
+#else
+#define PMX_T_DECL
+#define PMX_T_MARK(i)
+#define PMX_T_FLUSH(kind)
+#endif
 
 #define PMX_MINB(threads, pf) ((pf) ? ((384 / (threads)) > 0 ? (384 / (threads)) : 1) : ((512 / (threads)) > 0 ? (512 / (threads)) : 1))
 
@@ -238,6 +257,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     unsigned char* in = sm;  // PF: landing buffer at 0; !PF: WORK_OFF == 0, lands in the exchange buffer
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
     cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
+    cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
     const int tiles_per_bc = p.N2 / G, total = tiles_per_bc * p.batch * f.nfc;
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
@@ -258,6 +278,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_mbar_init(mbar, 1);
         pmx_fence_mbar_init();
     }
+    pmx_load_stage_tw<L>(stw, p.tw_stage);
     __syncthreads();
     int tile = live(blockIdx.x);
     if (threadIdx.x == 0 && tile < total) issue(tile);
@@ -309,8 +330,8 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             }
         }
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
-        cpx* sy = sx + pmx_pad(L);
-        CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+        cpx* sy = sx + L;
+        CtaFFT<L, false>::run(x, y, sx, sy, t, stw);
         // four-step twiddle W_N^(n2*k1), k1 = t + q*T:  W_N^(n2*t) * g[q],  g[q] = exp(-2*pi*i*n2*q/(8*N2))
         if (threadIdx.x < G * 8) {
             const int c2 = threadIdx.x >> 3, q = threadIdx.x & 7;
@@ -347,16 +368,23 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 
 // ---------------------------------------------------------------------------
 // pass B: G rows per tile, thread (t fastest, rl)
+#ifdef PMX_B_CTAS   // experiment knob: resident 128-thread-equivalent CTAs targeted for pass B
+#define PMX_MINB_B(threads, pf) (((PMX_B_CTAS * 128) / (threads)) > 0 ? ((PMX_B_CTAS * 128) / (threads)) : 1)
+#else
+#define PMX_MINB_B(threads, pf) PMX_MINB(threads, pf)
+#endif
 template <int L, int G, bool PF, bool SC>
-__global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
+__global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
-    using S = PassSmem<L, G, PF>;
+    using S = PassSmem<L, G, PF, 32>;
     constexpr int T = L / 8;
     extern __shared__ unsigned char smraw[];
     unsigned char* sm = pmx_align1024(smraw);
     unsigned char* in = sm;
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
     cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
+    cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
+    const PlateConst* splates = reinterpret_cast<const PlateConst*>(sm + S::PLATE_OFF);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
     const int tiles_per_bc = p.N1 / G, total = tiles_per_bc * p.batch * f.nfc;
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
@@ -377,17 +405,29 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_mbar_init(mbar, 1);
         pmx_fence_mbar_init();
     }
+    pmx_load_stage_tw<L>(stw, p.tw_stage);
     __syncthreads();
     int tile = live(blockIdx.x);
     if (threadIdx.x == 0 && tile < total) issue(tile);
     uint32_t phase = 0;
+    PMX_T_DECL
     while (tile < total) {
         const int bc = tile / tiles_per_bc, b = bc / f.nfc, col = bc % f.nfc;
         const int k1 = (tile % tiles_per_bc) * G + rl;
         const StepCtl* c = &p.ctl[b];
+        const int ntrunk = c->ntrunk;
+        const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
+        if (f.pmd) {  // this step's trunks: plate constants to shared memory while the tile is in flight
+            const int nd = (ntrunk < S::PLATE_CAP ? ntrunk : S::PLATE_CAP) * (int)(sizeof(PlateConst) / sizeof(double));
+            const double* src = reinterpret_cast<const double*>(plg);
+            double* dst = reinterpret_cast<double*>(sm + S::PLATE_OFF);
+            for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        }
         cpx x[8], y[8];
+        PMX_T_MARK(0)
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
+        PMX_T_MARK(1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint32_t off = pmx_swz<7>((uint32_t)((rl * L + t + q * T) * 32));
@@ -398,23 +438,24 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         const int next = live(tile + gridDim.x);
         if (PF && threadIdx.x == 0 && next < total) issue(next);
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
-        cpx* sy = sx + pmx_pad(L);
-        CtaFFT<L, false>::run(x, y, sx, sy, t, p.tw_stage);
+        cpx* sy = sx + L;
+        PMX_T_MARK(2)
+        CtaFFT<L, false>::run(x, y, sx, sy, t, stw);
+        PMX_T_MARK(3)
 
         // ---- linear step in the frequency domain, fiber.m:907-933
-        const int ntrunk = c->ntrunk;
+        auto plate = [&](int k) -> const PlateConst& { return (k < S::PLATE_CAP) ? splates[k] : plg[k]; };
         if (!SC && ntrunk > 0) {
             const double dz_cur = c->dz_cur;
             const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
             if (f.pmd) {
                 const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
-                const PlateConst* pl = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
                 const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
                 double d1[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
                 {  // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
-                    const PlateConst& P = pl[0];
+                    const PlateConst& P = plate(0);
                     const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
                     const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
 #pragma unroll
@@ -435,7 +476,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                     pmx_sincos8(a, e1s, e1c);
                 }
                 for (int k = 0; k < ntrunk; ++k) {
-                    const PlateConst& P = pl[k];
+                    const PlateConst& P = plate(k);
                     const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
                     if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
                         const cpx h0 = make_double2(P.h0r, P.h0i);
@@ -470,7 +511,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                     }
                 }
                 {  // back to the laboratory basis: u = matR * uu  (:931-932)
-                    const PlateConst& P = pl[ntrunk - 1];
+                    const PlateConst& P = plate(ntrunk - 1);
                     const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
                     const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
 #pragma unroll
@@ -505,12 +546,11 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             const double fn0 = (double)kb * f.inv_nsymb;
             const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
             if (f.pmd) {
-                const PlateConst* pl = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
                 const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
                 const double d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
                 const double d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
                 {  // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
-                    const PlateConst& P = pl[0];
+                    const PlateConst& P = plate(0);
                     const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
                     const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
 #pragma unroll
@@ -530,7 +570,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                 }
                 const cpx g1 = make_double2(f.g1r, f.g1i);
                 for (int k = 0; k < ntrunk; ++k) {
-                    const PlateConst& P = pl[k];
+                    const PlateConst& P = plate(k);
                     const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
                     cpx e0, e4, g;
                     if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
@@ -567,7 +607,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                     }
                 }
                 {  // back to the laboratory basis: u = matR * uu  (:931-932)
-                    const PlateConst& P = pl[ntrunk - 1];
+                    const PlateConst& P = plate(ntrunk - 1);
                     const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
                     const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
 #pragma unroll
@@ -601,7 +641,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             }
         }
 
-        CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
+        PMX_T_MARK(4)
+        CtaFFT<L, true>::run(x, y, sx, sy, t, stw);
+        PMX_T_MARK(5)
         if (!PF && threadIdx.x == 0 && next < total) issue(next);
         // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T:  conj(W_N^(k1*t) * g[q]),
         // g[q] = exp(-2*pi*i*k1*q/(8*N1)) per row
@@ -621,7 +663,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         tile = next;
         __syncthreads();
+        PMX_T_MARK(6)
     }
+    PMX_T_FLUSH(1)
 }
 
 // ---------------------------------------------------------------------------
@@ -636,6 +680,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     unsigned char* in = sm;
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
     void* red = sm + S::RED_OFF;
+    cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
     const int tiles_per_bc = p.N2 / G, total = tiles_per_bc * p.batch * f.nfc;
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
@@ -656,6 +701,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_mbar_init(mbar, 1);
         pmx_fence_mbar_init();
     }
+    pmx_load_stage_tw<L>(stw, p.tw_stage);
     __syncthreads();
     int tile = live(blockIdx.x);
     if (threadIdx.x == 0 && tile < total) issue(tile);
@@ -678,8 +724,8 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         const int next = live(tile + gridDim.x);
         if (PF && threadIdx.x == 0 && next < total) issue(next);
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
-        cpx* sy = sx + pmx_pad(L);
-        CtaFFT<L, true>::run(x, y, sx, sy, t, p.tw_stage);
+        cpx* sy = sx + L;
+        CtaFFT<L, true>::run(x, y, sx, sy, t, stw);
         const double sc = c->scale;
         unsigned long long vmax = 0ull;
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);

@@ -36,7 +36,7 @@ def check_schedule(gs):
     assert L['ncycle'] == gs.log['ncycle']
     sched = gs.log['schedule']
     assert list(L['trace_ntrunk']) == [s['ntrunk'] for s in sched]
-    np.testing.assert_allclose(L['trace_dz'], [s['dz'] for s in sched], rtol=1e-12)
+    np.testing.assert_allclose(L["trace_dz"], [s["dz"] for s in sched], rtol=1e-10)  # dz = -log(1-dl)/alpha is ill-conditioned near the dzmax cap
     np.testing.assert_allclose(L['firstdz'], gs.log['firstdz'], rtol=1e-13)
 
 

@@ -1,0 +1,19 @@
+"""Accuracy of the CUDA path vs the oracle on a few cases (prints rel-L2 and step-length deviation)."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import oracle.fiber_oracle as orc
+import polmux_b200 as pmx
+from common import base_fiber, make_tx, rel_l2
+for lg, man in ((12, 'no'), (14, 'no'), (16, 'no'), (16, 'yes'), (18, 'yes')):
+    fib = base_fiber(length=1e5, dgd=1.0, nplates=10, manakov=man)
+    gs = make_tx(1 << (lg - 4), 16)
+    orc.fiber(gs, fib, 'gps-', rng=np.random.Generator(np.random.PCG64(1000)))
+    pmx.fiber(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(1000)), trace=True)
+    G = pmx.GSTATE
+    dz_o = np.array([s['dz'] for s in gs.log['schedule']])
+    dz_g = pmx.FIBER_LAST['trace_dz']
+    print('N=2^%d manakov=%s  rel_l2=%.2e  ncycle %d/%d  max|ddz/dz|=%.2e' % (
+        lg, man, rel_l2(G.FIELDX, G.FIELDY, gs.FIELDX, gs.FIELDY), pmx.FIBER_LAST['ncycle'], gs.log['ncycle'],
+        np.max(np.abs(dz_g - dz_o) / dz_o) if len(dz_g) == len(dz_o) else -1))
