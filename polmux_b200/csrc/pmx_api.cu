@@ -709,6 +709,8 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     // Without the 'p' flag the front-end passes identity plates and db1 = 0 (fiber.m:290-298):
     // the Jones product is skipped altogether.
     f.pmd = d->fls[1] ? 1 : 0;
+    f.keep_basis = (f.pmd && (f.manakov || !f.spm)) ? 1 : 0;
+    f.nfc_magic = d->nfc > 1 ? (unsigned)((0x100000000ull + d->nfc - 1) / d->nfc) : 0u;
     const size_t N = (size_t)d->nfft;
     p->single_step = std::isinf(d->dphimaxt) && d->dzmaxt >= d->length;
 

@@ -12,6 +12,13 @@ typedef double2 cpx;
 #define PMX_MAX_NFC 16
 
 enum { PMX_ST_RUN = 0, PMX_ST_LAST = 1, PMX_ST_DONE = 2, PMX_ST_ERROR = 3 };
+// Basis bookkeeping of the PMD product.  The reference goes laboratory -> PSP basis of the first trunk at the
+// start of every linear step and back at its end (fiber.m:920-921,931-932).  When the nonlinear step is a
+// scalar phase (Manakov) or absent, those constant unitary matrices commute with everything between two
+// linear steps (phase rotation, FFTs, attenuation; |ux|^2+|uy|^2 is invariant), so the field can stay in
+// the PSP basis of the trunk it is in: R(last)*...*R(first)^H of consecutive steps collapses to nothing
+// (same trunk) or to the boundary matrix of the plate just left.
+enum { PMX_BM_ENTRY_R = 1, PMX_BM_ENTRY_C = 2, PMX_BM_EXIT_R = 4 };
 
 // Per-realization propagation state + the schedule of the step about to run.
 // Written by the last CTA of pass C (or by the init kernel), read by passes A/B/C.
@@ -34,7 +41,7 @@ struct __align__(16) StepCtl {
     int ntrunk;        // fiber.m:743,749
     int nmem;          // fiber.m:742,748
     int n_first;       // 0-based plate index of trunk k=1:  ntot + 1 - nmem - 1
-    int pad0;
+    int bmode;         // PMX_BM_* : which constant basis changes pass B applies around the trunk product
     // scalar dispersion mode: per-bin-step factors exp(-i*0.5*dgdrms*domega*dzb/lcorr) of the
     // first / last (partial) trunk of the step, domega = spacing of a thread's bins
     double gpf_r, gpf_i, gpl_r, gpl_i;
@@ -60,10 +67,12 @@ struct FiberConst {
     double Lf, alphalin, halfalpha, dzmax, phimax, lcorr, invN;
     double gam[PMX_MAX_NFC];  // after the Manakov 8/9 (fiber.m:500)
     int nplates, nfc, spm, manakov, pmd, gvd_any, plate_sets, trace_cap;
+    int keep_basis, pad_;  // keep_basis: pmd && (manakov || !spm), see PMX_BM_*
     // scalar dispersion mode (fiber.m:350-362 regenerated per bin instead of read from HBM):
     //   omega = w0*fn, fn = kk/NSYMB (kk = signed FFT bin), betat = omega*beta1 + 0.5*omega^2*beta2
     //   + omega^3*b30/6, db1 = dgdrms*omega
-    int disp_scalar, pad_;
+    int disp_scalar;
+    unsigned nfc_magic;   // ceil(2^32/nfc): bc / nfc = umulhi(bc, nfc_magic) for nfc > 1
     double w0, inv_nsymb, b30_6, dgdrms, domega;  // domega = w0*NT/8: spacing of a thread's bins
     double g1r, g1i;                              // exp(-i*0.5*dgdrms*domega)
     double beta1[PMX_MAX_NFC], beta2[PMX_MAX_NFC];

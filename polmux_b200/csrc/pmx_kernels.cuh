@@ -109,6 +109,10 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
     c->dzb_first = dzb_first;
     c->dzb_last = dzb_last;
     c->n_first = c->ntot - nmem;
+    if (f.keep_basis)
+        c->bmode = (first ? PMX_BM_ENTRY_R : (nmem ? 0 : PMX_BM_ENTRY_C)) | (c->state == PMX_ST_LAST ? PMX_BM_EXIT_R : 0);
+    else
+        c->bmode = PMX_BM_ENTRY_R | PMX_BM_EXIT_R;
     if (f.disp_scalar && f.pmd) {
         double s, cs;
         sincos(-(0.5 * f.dgdrms * f.domega * dzb_first / lcorr), &s, &cs);
@@ -135,10 +139,11 @@ __device__ __forceinline__ unsigned long long pmx_pow_key(double pw) {
     return (pw != pw) ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(pw);
 }
 
-// Block-wide max (warp shuffles, then one atomicMax per CTA); the last CTA of the
-// realization (ticket) runs the step control.
+// Block-wide max (warp shuffles, then one atomicMax per CTA); `add` = number of tiles (of the
+// realization's `total_tiles` per step) this value covers; the CTA that completes the count runs the
+// step control.  scratch: >= 33 x 8 B of shared memory.
 __device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, void* scratch, StepCtl* c, int col,
-                                                      unsigned total_ctas, const FiberConst& f,
+                                                      unsigned add, unsigned total_tiles, const FiberConst& f,
                                                       bool first, int b, double* trace_dz,
                                                       int* trace_ntrunk) {
 #pragma unroll
@@ -146,11 +151,9 @@ __device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, vo
         unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other > key ? other : key;
     }
-    unsigned long long* red = reinterpret_cast<unsigned long long*>(scratch);  // >= 32 x 8 B
-    __shared__ int s_last;
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(scratch);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarp = (blockDim.x + 31) >> 5;
-    __syncthreads();  // smem free
     if (lane == 0) red[warp] = key;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -158,14 +161,13 @@ __device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, vo
         for (int w = 1; w < nwarp; ++w) m = red[w] > m ? red[w] : m;
         atomicMax(&c->umax_bits[col], m);
         __threadfence();
-        unsigned prev = atomicAdd(&c->ticket, 1u);
-        s_last = (prev == total_ctas - 1u);
+        unsigned prev = atomicAdd(&c->ticket, add);
+        if (prev + add == total_tiles) {
+            __threadfence();
+            pmx_ctl_next(c, f, first, b, trace_dz, trace_ntrunk);
+        }
     }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        pmx_ctl_next(c, f, first, b, trace_dz, trace_ntrunk);
-    }
+    __syncthreads();  // scratch free again
 }
 
 // ---------------------------------------------------------------------------
@@ -182,7 +184,7 @@ static __global__ void __launch_bounds__(256) pmx_k_init(PassParams p, FiberCons
         unsigned long long key = pmx_pow_key(power_ref(x, y));
         vmax = key > vmax ? key : vmax;
     }
-    pmx_block_max_and_ctl(vmax, smem, &p.ctl[b], col, gridDim.x * f.nfc, f, true, b, p.trace_dz,
+    pmx_block_max_and_ctl(vmax, smem, &p.ctl[b], col, 1u, gridDim.x * f.nfc, f, true, b, p.trace_dz,
                           p.trace_ntrunk);
 }
 
@@ -193,6 +195,23 @@ struct PmxSmem {
     static constexpr int BASE = 2 * L;
     static constexpr int OFF = (GROUP > 1) ? ((8 / GROUP) > 0 ? (8 / GROUP) : 1) : 0;
     static constexpr int STRIDE = BASE + OFF;
+};
+
+// Four-step twiddle of one row/column, W_N^(r*m) for m in [0, L): two-level table per tile,
+// W^(r*m) = lo[m & (2^LO-1)] * hi[m >> LO], built with exact-argument sincospi by the threads of
+// the CTA while the tile is in flight (no HBM table, no dependent global load before the store).
+template <int L>
+struct PmxTw4 {
+    static constexpr int LOG = pmx_ilog2(L);
+    static constexpr int LO = (LOG + 1) / 2, HI = LOG - LO;
+    static constexpr int NLO = 1 << LO, NHI = 1 << HI, PER = NLO + NHI;
+};
+
+// per-tile scalars of pass B, staged in shared memory at the top of a tile
+struct BStage {
+    double dz_cur, dzb_first, dzb_last, gpf_r, gpf_i, gpl_r, gpl_i, pad;
+    double E[8];   // entry matrix (row-major re,im): R(first)^H, or the boundary matrix of the plate before
+    double X[8];   // exit matrix R(last)
 };
 
 // Shared-memory plan of a pass CTA working on G rows (pass B) or G columns (passes A, C) of
@@ -207,10 +226,11 @@ struct PassSmem {
     static constexpr int WORK_BYTES = G * PmxSmem<L, G>::STRIDE * 16;
     static constexpr int WORK_OFF = PF ? ((TILE_BYTES + 1023) / 1024) * 1024 : 0;
     static constexpr int TW_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;   // stage twiddles
-    static constexpr int GTAB_OFF = TW_OFF + pmx_tw_total(L) * 16;
+    static constexpr int GTAB_OFF = TW_OFF + pmx_tw_total(L) * 16;             // four-step twiddle tables
     static constexpr int PLATE_CAP = NPLATE;                   // trunks of the step staged in smem (pass B)
-    static constexpr int PLATE_OFF = GTAB_OFF + G * 8 * 16;
-    static constexpr int RED_OFF = PLATE_OFF + PLATE_CAP * (int)sizeof(PlateConst);
+    static constexpr int PLATE_OFF = GTAB_OFF + G * PmxTw4<L>::PER * 16;
+    static constexpr int STAGE_OFF = PLATE_OFF + PLATE_CAP * (int)sizeof(PlateConst);
+    static constexpr int RED_OFF = STAGE_OFF + (NPLATE ? (int)sizeof(BStage) : 0);
     static constexpr int MBAR_OFF = RED_OFF + 32 * 8;
     static constexpr int TOTAL = MBAR_OFF + 16 + 1024;  // + slack to align the base to 1024 B
     static_assert(WORK_BYTES >= TILE_BYTES, "exchange buffer must hold a landed tile");
@@ -226,10 +246,28 @@ __device__ __forceinline__ unsigned char* pmx_align1024(unsigned char* p) {
     return p + ((1024u - (pmx_smem_u32(p) & 1023u)) & 1023u);
 }
 
-__device__ __forceinline__ cpx pmx_twiddle4(const PassParams& p, unsigned m) {
-    cpx h = __ldg(&p.tw_hi[m >> p.lo_bits]);
-    cpx l = __ldg(&p.tw_lo[m & ((1u << p.lo_bits) - 1u)]);
-    return cmul(h, l);
+// tab[g*PER + ...] for the G rows/columns r0 .. r0+G-1 of a tile; invN2 = 2/N (sincospi argument scale)
+template <int L, int G>
+__device__ __forceinline__ void pmx_fill_tw4(cpx* tab, int r0, double two_over_N) {
+    using W = PmxTw4<L>;
+    for (int i = threadIdx.x; i < G * W::PER; i += blockDim.x) {
+        const int g = i / W::PER, e = i % W::PER;
+        const int m = (e < W::NLO) ? e : ((e - W::NLO) << W::LO);
+        double s, c;
+        sincospi(-(double)((long long)(r0 + g) * m) * two_over_N, &s, &c);  // exact argument: N is a power of two
+        tab[i] = make_double2(c, s);
+    }
+}
+
+// realization / column of a flat realization-column index
+__device__ __forceinline__ void pmx_split_bc(int bc, const FiberConst& f, int& b, int& col) {
+    if (f.nfc == 1) {
+        b = bc;
+        col = 0;
+    } else {
+        b = (int)__umulhi((unsigned)bc, f.nfc_magic);
+        col = bc - b * f.nfc;
+    }
 }
 
 #ifdef PMX_TIMING
@@ -251,6 +289,7 @@ template <int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passA(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF>;
+    using W = PmxTw4<L>;
     constexpr int T = L / 8, PITCH = G * 32, MASK = PITCH / 16 - 1;
     extern __shared__ unsigned char smraw[];
     unsigned char* sm = pmx_align1024(smraw);
@@ -258,20 +297,25 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
     cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
+    double* sred = reinterpret_cast<double*>(sm + S::RED_OFF);  // [0] = leff of the tile's realization
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
-    const int tiles_per_bc = p.N2 / G, total = tiles_per_bc * p.batch * f.nfc;
+    const int ltpb = p.log2N2 - pmx_ilog2(G), tpb_mask = (1 << ltpb) - 1, total = (p.batch * f.nfc) << ltpb;
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
-    const size_t N = (size_t)p.N1 * p.N2;
-    const size_t rs = (size_t)p.N2 * 2;  // cpx per n1 row
+    const double two_over_N = 2.0 * f.invN;
 
     auto live = [&](int tl) {
-        while (tl < total && p.ctl[(tl / tiles_per_bc) / f.nfc].state >= PMX_ST_DONE) tl += gridDim.x;
+        while (tl < total) {
+            int b_, col_;
+            pmx_split_bc(tl >> ltpb, f, b_, col_);
+            if (p.ctl[b_].state < PMX_ST_DONE) break;
+            tl += gridDim.x;
+        }
         return tl;
     };
     auto issue = [&](int tl) {  // one thread
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
-        const int bc = tl / tiles_per_bc, c0 = (tl % tiles_per_bc) * G;
+        const int bc = tl >> ltpb, c0 = (tl & tpb_mask) * G;
         for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
     };
     if (threadIdx.x == 0) {
@@ -284,9 +328,13 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     if (threadIdx.x == 0 && tile < total) issue(tile);
     uint32_t phase = 0;
     while (tile < total) {
-        const int bc = tile / tiles_per_bc, b = bc / f.nfc, col = bc % f.nfc;
-        const int n2 = (tile % tiles_per_bc) * G + cl;
-        const StepCtl* c = &p.ctl[b];
+        const int bc = tile >> ltpb, c0 = (tile & tpb_mask) * G;
+        int b, col;
+        pmx_split_bc(bc, f, b, col);
+        // tile top: scalars and the four-step twiddle table while the tile is in flight
+        const int next = live(tile + gridDim.x);
+        if (threadIdx.x == 0) sred[0] = p.ctl[b].leff;
+        pmx_fill_tw4<L, G>(gtab, c0, two_over_N);
         cpx x[8], y[8];
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
@@ -298,11 +346,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
         __syncthreads();
-        const int next = live(tile + gridDim.x);
         if (PF && threadIdx.x == 0 && next < total) issue(next);
         // ---- nonlinear step, fiber.m:832-851
         if (f.spm) {
-            const double gamleff = __dmul_rn(f.gam[col], c->leff);
+            const double gamleff = __dmul_rn(f.gam[col], sred[0]);
             const double ngl = -gamleff;
             double ph[8], sn[8], cs[8];
 #pragma unroll
@@ -332,28 +379,23 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         CtaFFT<L, false>::run(x, y, sx, sy, t, stw);
-        // four-step twiddle W_N^(n2*k1), k1 = t + q*T:  W_N^(n2*t) * g[q],  g[q] = exp(-2*pi*i*n2*q/(8*N2))
-        if (threadIdx.x < G * 8) {
-            const int c2 = threadIdx.x >> 3, q = threadIdx.x & 7;
-            double s, cs;
-            sincospi(-2.0 * (double)(((tile % tiles_per_bc) * G + c2) * q) / (double)(8 * p.N2), &s, &cs);
-            gtab[c2 * 8 + q] = make_double2(cs, s);
-        }
-        __syncthreads();
-        const cpx wb = pmx_twiddle4(p, (unsigned)n2 * (unsigned)t);
-        // stage the tile (same swizzled layout as it landed) in the exchange buffer, TMA-store it
+        // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the tile's two-level table; the tile is staged
+        // (same swizzled layout as it landed) in the exchange buffer and TMA-stored
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
+        {
+            const cpx* tb = gtab + cl * W::PER;
+            const cpx wl = tb[t & (W::NLO - 1)];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const cpx w = cmul(wb, gtab[cl * 8 + q]);
-            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
-            *reinterpret_cast<cpx*>(outb + off) = cmul(x[q], w);
-            *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = cmul(y[q], w);
+            for (int q = 0; q < 8; ++q) {
+                const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
+                const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
+                *reinterpret_cast<cpx*>(outb + off) = cmul(x[q], w);
+                *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = cmul(y[q], w);
+            }
         }
         pmx_fence_proxy_async();
-        __syncthreads();  // tile staged; gtab free for the next tile
+        __syncthreads();  // tile staged; tables free for the next tile
         if (threadIdx.x == 0) {
-            const int c0 = (tile % tiles_per_bc) * G;
             for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, bc, outb + r0 * PITCH);
             pmx_tma_commit();
             if (!PF && next < total) {  // the next tile lands in this same buffer
@@ -373,10 +415,25 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 #else
 #define PMX_MINB_B(threads, pf) PMX_MINB(threads, pf)
 #endif
+
+// u <- M*u for the eight bins of a thread, M row-major (re,im) in shared memory
+__device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const double* M) {
+    const cpx m11 = make_double2(M[0], M[1]), m12 = make_double2(M[2], M[3]);
+    const cpx m21 = make_double2(M[4], M[5]), m22 = make_double2(M[6], M[7]);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const cpx nx = cadd(cmul(m11, x[q]), cmul(m12, y[q]));
+        const cpx ny = cadd(cmul(m21, x[q]), cmul(m22, y[q]));
+        x[q] = nx;
+        y[q] = ny;
+    }
+}
+
 template <int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 32>;
+    using W = PmxTw4<L>;
     constexpr int T = L / 8;
     extern __shared__ unsigned char smraw[];
     unsigned char* sm = pmx_align1024(smraw);
@@ -384,22 +441,36 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
     cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
-    const PlateConst* splates = reinterpret_cast<const PlateConst*>(sm + S::PLATE_OFF);
+    PlateConst* splates = reinterpret_cast<PlateConst*>(sm + S::PLATE_OFF);
+    BStage* st = reinterpret_cast<BStage*>(sm + S::STAGE_OFF);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
-    const int tiles_per_bc = p.N1 / G, total = tiles_per_bc * p.batch * f.nfc;
+    const int ltpb = p.log2N1 - pmx_ilog2(G), tpb_mask = (1 << ltpb) - 1, total = (p.batch * f.nfc) << ltpb;
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
     const size_t N = (size_t)p.N1 * p.N2;
+    const double two_over_N = 2.0 * f.invN;
     constexpr int LINES = G * L / 4;  // 128-byte lines per tile
+    constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
 
     auto live = [&](int tl) {
-        while (tl < total && p.ctl[(tl / tiles_per_bc) / f.nfc].state >= PMX_ST_DONE) tl += gridDim.x;
+        while (tl < total) {
+            int b_, col_;
+            pmx_split_bc(tl >> ltpb, f, b_, col_);
+            if (p.ctl[b_].state < PMX_ST_DONE) break;
+            tl += gridDim.x;
+        }
         return tl;
     };
     auto issue = [&](int tl) {
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
-        const int bc = tl / tiles_per_bc, line0 = (tl % tiles_per_bc) * LINES;
+        const int bc = tl >> ltpb, line0 = (tl & tpb_mask) * LINES;
         for (int l0 = 0; l0 < LINES; l0 += 256) pmx_tma_load_3d(in + l0 * 128, &tmap, 0, line0 + l0, bc, mbar);
+    };
+    // stage `n` plates starting at global plate pointer `src` into shared memory
+    auto stage_plates = [&](const PlateConst* src, int n) {
+        const double* s_ = reinterpret_cast<const double*>(src);
+        double* d_ = reinterpret_cast<double*>(splates);
+        for (int i = threadIdx.x; i < n * PLD; i += blockDim.x) d_[i] = __ldg(&s_[i]);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -412,17 +483,43 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     uint32_t phase = 0;
     PMX_T_DECL
     while (tile < total) {
-        const int bc = tile / tiles_per_bc, b = bc / f.nfc, col = bc % f.nfc;
-        const int k1 = (tile % tiles_per_bc) * G + rl;
+        // ---- tile top: everything that comes from global memory besides the tile itself is fetched
+        // here, while the TMA load is in flight, and parked in shared memory.
+        const int bc = tile >> ltpb;
+        int b, col;
+        pmx_split_bc(bc, f, b, col);
+        const int row0 = (tile & tpb_mask) * G, k1 = row0 + rl;
         const StepCtl* c = &p.ctl[b];
-        const int ntrunk = c->ntrunk;
-        const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + c->n_first;
-        if (f.pmd) {  // this step's trunks: plate constants to shared memory while the tile is in flight
-            const int nd = (ntrunk < S::PLATE_CAP ? ntrunk : S::PLATE_CAP) * (int)(sizeof(PlateConst) / sizeof(double));
-            const double* src = reinterpret_cast<const double*>(plg);
-            double* dst = reinterpret_cast<double*>(sm + S::PLATE_OFF);
-            for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        const int2 sched = *reinterpret_cast<const int2*>(&c->ntrunk);     // ntrunk, nmem
+        const int2 sched2 = *reinterpret_cast<const int2*>(&c->n_first);   // n_first, bmode
+        const int ntrunk = sched.x, bmode = f.pmd ? sched2.y : 0;
+        const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + sched2.x;
+        const int next = live(tile + gridDim.x);
+        if (f.pmd) {
+            stage_plates(plg, ntrunk < S::PLATE_CAP ? ntrunk : S::PLATE_CAP);
+            if (threadIdx.x < 8) {
+                const double* sc_ = &c->dz_cur;  // dz_cur leff scale dzb_first dzb_last | gpf_r gpf_i gpl_r gpl_i
+                const int src = (threadIdx.x == 0) ? 0 : (threadIdx.x < 3 ? threadIdx.x + 2 : threadIdx.x + 4);
+                if (threadIdx.x < 7) (&st->dz_cur)[threadIdx.x] = sc_[src];
+            } else if (threadIdx.x < 16) {  // entry matrix
+                const int i = threadIdx.x - 8;
+                double v = (i == 0 || i == 6) ? 1.0 : 0.0;
+                if (bmode & PMX_BM_ENTRY_R) {  // R^H: element (r,c) = conj(R(c,r))
+                    const int r = i >> 2, cc = (i >> 1) & 1, im = i & 1;
+                    v = (&plg[0].r11r)[(cc * 2 + r) * 2 + im];
+                    if (im) v = -v;
+                } else if (bmode & PMX_BM_ENTRY_C) {
+                    v = (&plg[-1].c11r)[i];
+                }
+                st->E[i] = v;
+            } else if (threadIdx.x < 24) {  // exit matrix
+                const int i = threadIdx.x - 16;
+                st->X[i] = (&plg[ntrunk - 1].r11r)[i];
+            }
+        } else if (threadIdx.x == 0) {
+            st->dz_cur = c->dz_cur;
         }
+        pmx_fill_tw4<L, G>(gtab, row0, two_over_N);
         cpx x[8], y[8];
         PMX_T_MARK(0)
         pmx_mbar_wait(mbar, phase);
@@ -435,7 +532,6 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
             y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
         }
         __syncthreads();
-        const int next = live(tile + gridDim.x);
         if (PF && threadIdx.x == 0 && next < total) issue(next);
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
@@ -444,192 +540,117 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         PMX_T_MARK(3)
 
         // ---- linear step in the frequency domain, fiber.m:907-933
-        auto plate = [&](int k) -> const PlateConst& { return (k < S::PLATE_CAP) ? splates[k] : plg[k]; };
-        if (!SC && ntrunk > 0) {
-            const double dz_cur = c->dz_cur;
-            const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
-            if (f.pmd) {
-                const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
-                const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
-                double d1[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
-                {  // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
-                    const PlateConst& P = plate(0);
-                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const cpx vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
-                        const cpx vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
-                        x[q] = vx;
-                        y[q] = vy;
-                    }
-                }
-                // exp(-i*db1/2): the frequency-dependent factor shared by every whole trunk
-                const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
-                double e1s[8], e1c[8];
-                if (any_full) {
-                    double a[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) a[q] = -0.5 * d1[q];
-                    pmx_sincos8(a, e1s, e1c);
-                }
-                for (int k = 0; k < ntrunk; ++k) {
-                    const PlateConst& P = plate(k);
-                    const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
-                    if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
-                        const cpx h0 = make_double2(P.h0r, P.h0i);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const cpx e = cmul(make_double2(e1c[q], e1s[q]), h0);
-                            x[q] = cmul(x[q], e);
-                            y[q] = cmulc(y[q], e);
-                        }
-                    } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-                        double a[8], sn[8], cs[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) a[q] = -(0.5 * (d1[q] + P.db0) * dzb / lcorr);
-                        pmx_sincos8(a, sn, cs);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const cpx e = make_double2(cs[q], sn[q]);
-                            x[q] = cmul(x[q], e);
-                            y[q] = cmulc(y[q], e);
-                        }
-                    }
-                    if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
-                        const cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
-                        const cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const cpx nx = cadd(cmul(c11, x[q]), cmul(c12, y[q]));
-                            const cpx ny = cadd(cmul(c21, x[q]), cmul(c22, y[q]));
-                            x[q] = nx;
-                            y[q] = ny;
-                        }
-                    }
-                }
-                {  // back to the laboratory basis: u = matR * uu  (:931-932)
-                    const PlateConst& P = plate(ntrunk - 1);
-                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const cpx ux = cadd(cmul(r11, x[q]), cmul(r12, y[q]));
-                        const cpx uy = cadd(cmul(r21, x[q]), cmul(r22, y[q]));
-                        x[q] = ux;
-                        y[q] = uy;
-                    }
-                }
-            }
-            if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
-                double a[8], sn[8], cs[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
-                pmx_sincos8(a, sn, cs);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const cpx e = make_double2(cs[q], sn[q]);
-                    x[q] = cmul(x[q], e);
-                    y[q] = cmul(y[q], e);
-                }
-            }
-        }
-
-        if (SC && ntrunk > 0) {
-            // Scalar dispersion mode.  A thread's bins are k = k1 + N1*(t + q*T): q < 4 on the
-            // positive-frequency side, q >= 4 on the negative one, equally spaced by domega.
-            const double dz_cur = c->dz_cur;
+        if (ntrunk > 0) {
+            const double dz_cur = st->dz_cur;
+            // Scalar dispersion mode: a thread's bins are k = k1 + N1*(t + q*T): q < 4 on the positive-
+            // frequency side, q >= 4 on the negative one, equally spaced by domega.
             const long long kb = (long long)k1 + (long long)p.N1 * t;
             const double dfn = (double)((long long)p.N1 * T) * f.inv_nsymb;
             const double fn0 = (double)kb * f.inv_nsymb;
             const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
             if (f.pmd) {
-                const double lcorr = f.lcorr, dzb_first = c->dzb_first, dzb_last = c->dzb_last;
-                const double d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
-                const double d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
-                {  // to the PSP basis of the first trunk: uu = matR' * u  (:920-921)
-                    const PlateConst& P = plate(0);
-                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const cpx vx = cadd(cmulc(x[q], r11), cmulc(y[q], r21));
-                        const cpx vy = cadd(cmulc(x[q], r12), cmulc(y[q], r22));
-                        x[q] = vx;
-                        y[q] = vy;
-                    }
-                }
-                // whole trunks: exp(-i*db1/2) at the two base bins, then a geometric progression
+                const double lcorr = f.lcorr, dzb_first = st->dzb_first, dzb_last = st->dzb_last;
+                if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
                 const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
+                // whole trunks share exp(-i*db1/2) per bin
+                double d1[SC ? 1 : 8], e1s[SC ? 1 : 8], e1c[SC ? 1 : 8];
+                double d10 = 0.0, d14 = 0.0;
                 cpx E0 = make_double2(1.0, 0.0), E4 = E0;
-                if (any_full) {
-                    pmx_sincos(-0.5 * d10, &E0.y, &E0.x);
-                    pmx_sincos(-0.5 * d14, &E4.y, &E4.x);
-                }
-                const cpx g1 = make_double2(f.g1r, f.g1i);
-                for (int k = 0; k < ntrunk; ++k) {
-                    const PlateConst& P = plate(k);
-                    const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
-                    cpx e0, e4, g;
-                    if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
-                        const cpx h0 = make_double2(P.h0r, P.h0i);
-                        e0 = cmul(E0, h0);
-                        e4 = cmul(E4, h0);
-                        g = g1;
-                    } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-                        pmx_sincos(-(0.5 * (d10 + P.db0) * dzb / lcorr), &e0.y, &e0.x);
-                        pmx_sincos(-(0.5 * (d14 + P.db0) * dzb / lcorr), &e4.y, &e4.x);
-                        g = (k == 0) ? make_double2(c->gpf_r, c->gpf_i) : make_double2(c->gpl_r, c->gpl_i);
+                if constexpr (SC) {
+                    d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
+                    d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
+                    if (any_full) {
+                        pmx_sincos(-0.5 * d10, &E0.y, &E0.x);
+                        pmx_sincos(-0.5 * d14, &E4.y, &E4.x);
                     }
+                } else {
+                    const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        x[q] = cmul(x[q], e0);
-                        y[q] = cmulc(y[q], e0);
-                        x[q + 4] = cmul(x[q + 4], e4);
-                        y[q + 4] = cmulc(y[q + 4], e4);
-                        if (q < 3) {
-                            e0 = cmul(e0, g);
-                            e4 = cmul(e4, g);
-                        }
-                    }
-                    if (k < ntrunk - 1) {  // basis change matR(n+1)' * matR(n)
-                        const cpx c11 = make_double2(P.c11r, P.c11i), c12 = make_double2(P.c12r, P.c12i);
-                        const cpx c21 = make_double2(P.c21r, P.c21i), c22 = make_double2(P.c22r, P.c22i);
+                    for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
+                    if (any_full) {
+                        double a[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const cpx nx = cadd(cmul(c11, x[q]), cmul(c12, y[q]));
-                            const cpx ny = cadd(cmul(c21, x[q]), cmul(c22, y[q]));
-                            x[q] = nx;
-                            y[q] = ny;
-                        }
+                        for (int q = 0; q < 8; ++q) a[q] = -0.5 * d1[q];
+                        pmx_sincos8(a, e1s, e1c);
                     }
                 }
-                {  // back to the laboratory basis: u = matR * uu  (:931-932)
-                    const PlateConst& P = plate(ntrunk - 1);
-                    const cpx r11 = make_double2(P.r11r, P.r11i), r12 = make_double2(P.r12r, P.r12i);
-                    const cpx r21 = make_double2(P.r21r, P.r21i), r22 = make_double2(P.r22r, P.r22i);
+                for (int k0 = 0; k0 < ntrunk; k0 += S::PLATE_CAP) {
+                    if (k0 > 0) {  // more trunks than the staging area holds (one-step 'gp--' runs): next chunk
+                        __syncthreads();
+                        stage_plates(plg + k0, (ntrunk - k0) < S::PLATE_CAP ? (ntrunk - k0) : S::PLATE_CAP);
+                        __syncthreads();
+                    }
+                    const int kend = (ntrunk - k0) < S::PLATE_CAP ? ntrunk : k0 + S::PLATE_CAP;
+                    for (int k = k0; k < kend; ++k) {
+                        const PlateConst& P = splates[k - k0];
+                        const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
+                        if constexpr (SC) {
+                            cpx e0, e4, g;
+                            if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
+                                const cpx h0 = make_double2(P.h0r, P.h0i);
+                                e0 = cmul(E0, h0);
+                                e4 = cmul(E4, h0);
+                                g = make_double2(f.g1r, f.g1i);
+                            } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+                                pmx_sincos(-(0.5 * (d10 + P.db0) * dzb / lcorr), &e0.y, &e0.x);
+                                pmx_sincos(-(0.5 * (d14 + P.db0) * dzb / lcorr), &e4.y, &e4.x);
+                                g = (k == 0) ? make_double2(st->gpf_r, st->gpf_i) : make_double2(st->gpl_r, st->gpl_i);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                x[q] = cmul(x[q], e0);
+                                y[q] = cmulc(y[q], e0);
+                                x[q + 4] = cmul(x[q + 4], e4);
+                                y[q + 4] = cmulc(y[q + 4], e4);
+                                if (q < 3) {
+                                    e0 = cmul(e0, g);
+                                    e4 = cmul(e4, g);
+                                }
+                            }
+                        } else {
+                            if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
+                                const cpx h0 = make_double2(P.h0r, P.h0i);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const cpx e = cmul(make_double2(e1c[q], e1s[q]), h0);
+                                    x[q] = cmul(x[q], e);
+                                    y[q] = cmulc(y[q], e);
+                                }
+                            } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+                                double a[8], sn[8], cs[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) a[q] = -(0.5 * (d1[q] + P.db0) * dzb / lcorr);
+                                pmx_sincos8(a, sn, cs);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const cpx e = make_double2(cs[q], sn[q]);
+                                    x[q] = cmul(x[q], e);
+                                    y[q] = cmulc(y[q], e);
+                                }
+                            }
+                        }
+                        if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);  // basis change matR(n+1)' * matR(n)
+                    }
+                }
+                if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
+            }
+            if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
+                double a[8], sn[8], cs[8];
+                if constexpr (SC) {  // betat regenerated per bin (:355-356)
+                    const double b1 = f.beta1[col], b2 = f.beta2[col];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const cpx ux = cadd(cmul(r11, x[q]), cmul(r12, y[q]));
-                        const cpx uy = cadd(cmul(r21, x[q]), cmul(r22, y[q]));
-                        x[q] = ux;
-                        y[q] = uy;
+                        const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
+                        const double w = __dmul_rn(f.w0, fn);
+                        const double w2 = __dmul_rn(w, w);
+                        double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
+                        bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
+                        a[q] = -(bt * dz_cur);
                     }
-                }
-            }
-            if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb)), betat regenerated (:355-356)
-                const double b1 = f.beta1[col], b2 = f.beta2[col];
-                double a[8], sn[8], cs[8];
+                } else {
+                    const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
-                    const double w = __dmul_rn(f.w0, fn);
-                    const double w2 = __dmul_rn(w, w);
-                    double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
-                    bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
-                    a[q] = -(bt * dz_cur);
+                    for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
                 }
                 pmx_sincos8(a, sn, cs);
 #pragma unroll
@@ -645,31 +666,28 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         CtaFFT<L, true>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(5)
         if (!PF && threadIdx.x == 0 && next < total) issue(next);
-        // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T:  conj(W_N^(k1*t) * g[q]),
-        // g[q] = exp(-2*pi*i*k1*q/(8*N1)) per row
-        if (threadIdx.x < G * 8) {
-            const int r2 = threadIdx.x >> 3, q = threadIdx.x & 7;
-            double s, cs;
-            sincospi(-2.0 * (double)(((tile % tiles_per_bc) * G + r2) * q) / (double)(8 * p.N1), &s, &cs);
-            gtab[r2 * 8 + q] = make_double2(cs, s);
-        }
-        __syncthreads();
-        const cpx wb = pmx_twiddle4(p, (unsigned)k1 * (unsigned)t);
-        cpx* base = p.field + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
+        // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T, from the tile's two-level table
+        {
+            const cpx* tb = gtab + rl * W::PER;
+            const cpx wl = tb[t & (W::NLO - 1)];
+            cpx* base = p.field + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const cpx w = cmul(wb, gtab[rl * 8 + q]);
-            st_sa(base + (size_t)(t + q * T) * 2, cmulc(x[q], w), cmulc(y[q], w));
+            for (int q = 0; q < 8; ++q) {
+                const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
+                st_sa(base + (size_t)(t + q * T) * 2, cmulc(x[q], w), cmulc(y[q], w));
+            }
         }
         tile = next;
-        __syncthreads();
+        __syncthreads();  // staging areas free for the next tile
         PMX_T_MARK(6)
     }
     PMX_T_FLUSH(1)
 }
 
 // ---------------------------------------------------------------------------
-// pass C: like pass A, inverse transform + attenuation + max reduction + step control
+// pass C: like pass A, inverse transform + attenuation + max reduction + step control.  The running
+// maximum stays in registers across the tiles a CTA handles for one realization-column and is
+// published (one atomicMax + one ticket add per CTA) when the CTA moves on to another one.
 template <int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
@@ -679,22 +697,25 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     unsigned char* sm = pmx_align1024(smraw);
     unsigned char* in = sm;
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
-    void* red = sm + S::RED_OFF;
+    double* sred = reinterpret_cast<double*>(sm + S::RED_OFF);  // [0] = scale of the tile; [1..] reduction scratch
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
-    const int tiles_per_bc = p.N2 / G, total = tiles_per_bc * p.batch * f.nfc;
+    const int ltpb = p.log2N2 - pmx_ilog2(G), tpb_mask = (1 << ltpb) - 1, total = (p.batch * f.nfc) << ltpb;
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
-    const size_t N = (size_t)p.N1 * p.N2;
-    const size_t rs = (size_t)p.N2 * 2;
 
     auto live = [&](int tl) {
-        while (tl < total && p.ctl[(tl / tiles_per_bc) / f.nfc].state >= PMX_ST_DONE) tl += gridDim.x;
+        while (tl < total) {
+            int b_, col_;
+            pmx_split_bc(tl >> ltpb, f, b_, col_);
+            if (p.ctl[b_].state < PMX_ST_DONE) break;
+            tl += gridDim.x;
+        }
         return tl;
     };
     auto issue = [&](int tl) {
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
-        const int bc = tl / tiles_per_bc, c0 = (tl % tiles_per_bc) * G;
+        const int bc = tl >> ltpb, c0 = (tl & tpb_mask) * G;
         for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
     };
     if (threadIdx.x == 0) {
@@ -706,10 +727,15 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     int tile = live(blockIdx.x);
     if (threadIdx.x == 0 && tile < total) issue(tile);
     uint32_t phase = 0;
+    unsigned long long vmax = 0ull;  // running max of this thread for the current realization-column
+    unsigned ntiles = 0;             // tiles it covers
     while (tile < total) {
-        const int bc = tile / tiles_per_bc, b = bc / f.nfc, col = bc % f.nfc;
-        const int n2 = (tile % tiles_per_bc) * G + cl;
+        const int bc = tile >> ltpb, c0 = (tile & tpb_mask) * G;
+        int b, col;
+        pmx_split_bc(bc, f, b, col);
         StepCtl* c = &p.ctl[b];
+        const int next = live(tile + gridDim.x);
+        if (threadIdx.x == 0) sred[0] = c->scale;
         cpx x[8], y[8];
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
@@ -721,13 +747,11 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         if (threadIdx.x == 0) pmx_tma_wait_read();
         __syncthreads();
-        const int next = live(tile + gridDim.x);
         if (PF && threadIdx.x == 0 && next < total) issue(next);
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         CtaFFT<L, true>::run(x, y, sx, sy, t, stw);
-        const double sc = c->scale;
-        unsigned long long vmax = 0ull;
+        const double sc = sred[0];
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -739,10 +763,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             *reinterpret_cast<cpx*>(outb + off) = x[q];
             *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = y[q];
         }
+        ++ntiles;
         pmx_fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int c0 = (tile % tiles_per_bc) * G;
             for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, bc, outb + r0 * PITCH);
             pmx_tma_commit();
             if (!PF && next < total) {
@@ -750,11 +774,14 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                 issue(next);
             }
         }
-        // The bulk store must be complete in global memory before the step control of the last
-        // tile lets the next kernel start?  No: kernel boundaries order it; only this CTA's smem
-        // reuse needs the wait above.
-        pmx_block_max_and_ctl(vmax, red, c, col, (unsigned)(tiles_per_bc * f.nfc), f, false, b, p.trace_dz,
-                              p.trace_ntrunk);
+        // Kernel boundaries order the bulk stores against the next pass; the step control of the last
+        // CTA only needs every CTA's maximum, which the ticket counts.
+        if (next >= total || (next >> ltpb) != bc) {
+            pmx_block_max_and_ctl(vmax, sred + 1, c, col, ntiles, (unsigned)((1 << ltpb) * f.nfc), f, false, b,
+                                  p.trace_dz, p.trace_ntrunk);
+            vmax = 0ull;
+            ntiles = 0;
+        }
         tile = next;
     }
     if (threadIdx.x == 0) pmx_tma_wait_read();
