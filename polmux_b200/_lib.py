@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libpolmux_ssfm.so')
+# POLMUX_SSFM_LIB: another build of the same CUDA library (kernel-tuning variants, tools/build_variant.sh)
+LIB_PATH = os.environ.get('POLMUX_SSFM_LIB') or os.path.join(_HERE, 'lib', 'libpolmux_ssfm.so')
 
 PMX_OK = 0
 PMX_ERR_INVALID, PMX_ERR_UNSUPPORTED, PMX_ERR_CUDA = -1, -2, -3

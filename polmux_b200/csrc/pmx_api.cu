@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -142,12 +143,21 @@ static int ilog2_exact(int64_t v) {
     return ((1ll << l) == v) ? l : -1;
 }
 
+// Four-step split N = N1*N2: log2(N1).  PMX_SPLIT_SHIFT (tuning knob) moves it off the balanced choice.
+static int split_log2N1(int lg) {
+    int l1 = lg / 2;
+    if (const char* e = getenv("PMX_SPLIT_SHIFT")) l1 += atoi(e);
+    if (l1 < 6) l1 = 6;
+    if (lg - l1 < 6) l1 = lg - 6;
+    return l1;
+}
+
 // Tensor maps over a resident field for the four-step split N = N1*N2 (see pmx_tma.cuh).
 static int build_maps(pmx_ctx* c, pmx_devfield* f) {
     const int lg = ilog2_exact(f->nfft);
     if (lg < 12 || lg > 24) return PMX_OK;  // not a size the SSFM kernels take; other ops still work
-    f->N1 = 1 << (lg / 2);
-    f->N2 = 1 << (lg - lg / 2);
+    f->N1 = 1 << split_log2N1(lg);
+    f->N2 = 1 << (lg - split_log2N1(lg));
     const PmxLaunchTable* tA = pmx_get_table(f->N1);
     const PmxLaunchTable* tB = pmx_get_table(f->N2);
     if (!tA || !tB) return PMX_OK;
@@ -669,7 +679,7 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     p->ctx = c;
     p->d = *d;
     p->d.gam = p->d.db0 = p->d.theta = p->d.epsilon = p->d.betat = p->d.db1 = p->d.beta1 = p->d.beta2 = nullptr;
-    p->log2N1 = lg / 2;
+    p->log2N1 = split_log2N1(lg);
     p->log2N2 = lg - p->log2N1;
     p->N1 = 1 << p->log2N1;
     p->N2 = 1 << p->log2N2;
@@ -689,6 +699,9 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
                                cudaGetErrorString(e), o.a, o.b, o.c);
             }
             c->setup_done[t->L] = o;
+            if (getenv("PMX_VERBOSE"))
+                fprintf(stderr, "[pmx] L=%d: resident CTAs/SM passA %d passB %d passC %d (smem %zu / %zu B)\n", t->L, o.a, o.b, o.c,
+                        t->smemAC, t->smemB);
         }
     }
     FiberConst& f = p->fc;

@@ -207,9 +207,13 @@ struct PmxTw4 {
     static constexpr int NLO = 1 << LO, NHI = 1 << HI, PER = NLO + NHI;
 };
 
+#ifndef PMX_PLATE_CAP
+#define PMX_PLATE_CAP 32   // trunks of a step whose plate constants are staged in shared memory at once
+#endif
+
 // per-tile scalars of pass B, staged in shared memory at the top of a tile
 struct BStage {
-    double dz_cur, dzb_first, dzb_last, gpf_r, gpf_i, gpl_r, gpl_i, pad;
+    double dz_cur, dzb_first, dzb_last, gpf_r, gpf_i, gpl_r, gpl_i, db0_last;
     double E[8];   // entry matrix (row-major re,im): R(first)^H, or the boundary matrix of the plate before
     double X[8];   // exit matrix R(last)
 };
@@ -432,7 +436,7 @@ __device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const dou
 template <int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
-    using S = PassSmem<L, G, PF, 32>;
+    using S = PassSmem<L, G, PF, PMX_PLATE_CAP>;
     using W = PmxTw4<L>;
     constexpr int T = L / 8;
     extern __shared__ unsigned char smraw[];
@@ -500,7 +504,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
             if (threadIdx.x < 8) {
                 const double* sc_ = &c->dz_cur;  // dz_cur leff scale dzb_first dzb_last | gpf_r gpf_i gpl_r gpl_i
                 const int src = (threadIdx.x == 0) ? 0 : (threadIdx.x < 3 ? threadIdx.x + 2 : threadIdx.x + 4);
-                if (threadIdx.x < 7) (&st->dz_cur)[threadIdx.x] = sc_[src];
+                if (threadIdx.x < 7)
+                    (&st->dz_cur)[threadIdx.x] = sc_[src];
+                else
+                    st->db0_last = plg[ntrunk > 0 ? ntrunk - 1 : 0].db0;
             } else if (threadIdx.x < 16) {  // entry matrix
                 const int i = threadIdx.x - 8;
                 double v = (i == 0 || i == 6) ? 1.0 : 0.0;
@@ -556,12 +563,30 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                 double d1[SC ? 1 : 8], e1s[SC ? 1 : 8], e1c[SC ? 1 : 8];
                 double d10 = 0.0, d14 = 0.0;
                 cpx E0 = make_double2(1.0, 0.0), E4 = E0;
+                cpx pf0, pf4, pl0, pl4;  // scalar mode: phases of the step's first / last trunk at the two base bins
                 if constexpr (SC) {
                     d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
                     d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
                     if (any_full) {
                         pmx_sincos(-0.5 * d10, &E0.y, &E0.x);
                         pmx_sincos(-0.5 * d14, &E4.y, &E4.x);
+                    }
+                    // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
+                    // independent and interleave
+                    const double db0f = splates[0].db0, db0l = st->db0_last;
+                    double a4[4] = {-(0.5 * (d10 + db0f) * dzb_first / lcorr), -(0.5 * (d14 + db0f) * dzb_first / lcorr),
+                                    -(0.5 * (d10 + db0l) * dzb_last / lcorr), -(0.5 * (d14 + db0l) * dzb_last / lcorr)};
+                    double m4 = fmax(fmax(fabs(a4[0]), fabs(a4[1])), fmax(fabs(a4[2]), fabs(a4[3])));
+                    if (m4 < 105615.0) {
+                        pmx_sincos_fast(a4[0], &pf0.y, &pf0.x);
+                        pmx_sincos_fast(a4[1], &pf4.y, &pf4.x);
+                        pmx_sincos_fast(a4[2], &pl0.y, &pl0.x);
+                        pmx_sincos_fast(a4[3], &pl4.y, &pl4.x);
+                    } else {
+                        sincos(a4[0], &pf0.y, &pf0.x);
+                        sincos(a4[1], &pf4.y, &pf4.x);
+                        sincos(a4[2], &pl0.y, &pl0.x);
+                        sincos(a4[3], &pl4.y, &pl4.x);
                     }
                 } else {
                     const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
@@ -591,21 +616,23 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                                 e0 = cmul(E0, h0);
                                 e4 = cmul(E4, h0);
                                 g = make_double2(f.g1r, f.g1i);
-                            } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-                                pmx_sincos(-(0.5 * (d10 + P.db0) * dzb / lcorr), &e0.y, &e0.x);
-                                pmx_sincos(-(0.5 * (d14 + P.db0) * dzb / lcorr), &e4.y, &e4.x);
+                            } else {  // partial trunk (first or last of the step)
+                                e0 = (k == 0) ? pf0 : pl0;
+                                e4 = (k == 0) ? pf4 : pl4;
                                 g = (k == 0) ? make_double2(st->gpf_r, st->gpf_i) : make_double2(st->gpl_r, st->gpl_i);
                             }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                x[q] = cmul(x[q], e0);
-                                y[q] = cmulc(y[q], e0);
-                                x[q + 4] = cmul(x[q + 4], e4);
-                                y[q + 4] = cmulc(y[q + 4], e4);
-                                if (q < 3) {
-                                    e0 = cmul(e0, g);
-                                    e4 = cmul(e4, g);
-                                }
+                            const cpx g2 = cmul(g, g);
+                            {
+                                const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
+                                const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
+                                x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
+                                x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
+                                x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
+                                x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
+                                x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
+                                x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
+                                x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
+                                x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
                             }
                         } else {
                             if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)

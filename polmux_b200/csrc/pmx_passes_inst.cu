@@ -25,7 +25,7 @@ constexpr bool PFB = (GB * L <= 512);
 constexpr bool PFB = (PMX_PFB != 0) && (GB * L <= 1024);
 #endif
 using SA = PassSmem<L, GAC, PFAC>;
-using SB = PassSmem<L, GB, PFB, 32>;
+using SB = PassSmem<L, GB, PFB, PMX_PLATE_CAP>;
 
 cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
     cudaError_t e;

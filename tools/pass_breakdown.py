@@ -1,5 +1,5 @@
 """Per-pass device time for different flag sets (what each part of a pass costs).
-Usage: python tools/pass_breakdown.py [batch] [log2N]"""
+Usage: python tools/pass_breakdown.py [batch] [log2N] [number of flag sets]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,11 +11,12 @@ from polmux_b200.fiber import fiber_setup, setup_to_desc
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 LG = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+NF = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 nsymb, nt = 1 << (LG - 4), 16
 N = nsymb * nt
 ex, ey, _, _ = synth.pdm_qpsk(nsymb, nt, 1)
 ctx = _lib.Context(0)
-for flag, man in (('gps-', 'yes'), ('gps-', 'no'), ('g-s-', 'no'), ('--s-', 'no'), ('g---', 'no'), ('gp--', 'no')):
+for flag, man in (('gps-', 'yes'), ('gps-', 'no'), ('g-s-', 'no'), ('--s-', 'no'), ('g---', 'no'), ('gp--', 'no'))[:NF]:
     pmx.reset_all(nsymb, nt, 1)
     G = pmx.GSTATE
     G.SYMBOLRATE, G.LAMBDA, G.POWER = bench.RATE, np.array([1550.0]), np.array([bench.PAVG])
