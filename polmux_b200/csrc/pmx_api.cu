@@ -880,7 +880,8 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
         dim3 g(148 * 2, batch * nfc);
         ProfScope ps(c, 3);
         pmx_k_init<<<g, 256, 256, c->stream>>>(pa, p->fc);
-        c->launches++;
+        pmx_k_ctl<<<(batch + 127) / 128, 128, 0, c->stream>>>(pa, p->fc, 1);
+        c->launches += 2;
         CK(c, cudaGetLastError());
     }
     if (!fld->has_maps) return set_err(c, PMX_ERR_INVALID, "field has no tensor maps (unsupported nfft)");
@@ -895,7 +896,8 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
             { ProfScope ps(c, 0); p->tA->passA(gA, c->stream, pA, p->fc, fld->map_cols); }
             { ProfScope ps(c, 1); p->tB->passB(gB, c->stream, pB, p->fc, fld->map_rows); }
             { ProfScope ps(c, 2); p->tA->passC(gC, c->stream, pA, p->fc, fld->map_cols); }
-            c->launches += 3;
+            pmx_k_ctl<<<(batch + 127) / 128, 128, 0, c->stream>>>(pa, p->fc, 0);
+            c->launches += 4;
             if (c->profile && c->ev_used > 4096) prof_collect(c);
         }
         total_steps += chunk;

@@ -47,7 +47,7 @@ struct __align__(16) StepCtl {
     double gpf_r, gpf_i, gpl_r, gpl_i;
     // reduction scratch for nextstep
     unsigned long long umax_bits[PMX_MAX_NFC];  // max over n of |ux|^2+|uy|^2, per column
-    unsigned int ticket;
+    unsigned int pad_ticket;
     unsigned int pad1;
 };
 

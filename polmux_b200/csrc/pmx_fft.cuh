@@ -12,7 +12,7 @@
 // Stage (radix R, Ns = product of earlier radices), butterfly j in [0, L/R):
 //   in : v[r] = x[j + r*L/R] * W_{Ns*R}^{(j mod Ns)*r}
 //   out: x'[(j - j mod Ns)*R + (j mod Ns) + r*Ns] = DFT_R(v)[r]
-// (natural order in, natural order out after the last stage).
+// (natural order in, natural order out after the last stage).  Stages: first R0 = 2^(log2 L mod 3) (or 8), then radix 8.
 //
 // Twiddles of a radix-8 stage: W^k, W^2k, W^4k come from a shared-memory table
 // ([3][Ns] per stage, conflict-free), W^3k, W^5k, W^6k, W^7k are four products.
@@ -90,61 +90,50 @@ __device__ __forceinline__ void dft8(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4
     a7 = csub(e3, o3);
 }
 
-template <int L, bool INV>
+// Forward transform only: the inverse is conj o forward o conj, and the callers fold the two
+// conjugations into operations they perform anyway (sign of an operand), so one copy of the
+// butterfly code serves both directions.  The radix-8 stages after the first run as a loop over
+// the stage size (one copy of the stage body; pass B calls the transform from a two-iteration loop),
+// which keeps the pass kernels within the instruction cache.
+template <int L>
 struct CtaFFT {
     static constexpr int T = L / 8;
+    static constexpr int R0 = pmx_stage_radix(L, 1);  // radix of the first stage (2, 4 or 8), no twiddles
 
-    template <int NS>
-    __device__ __forceinline__ static void stage(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t,
-                                                 const cpx* tw) {
-        constexpr int R = pmx_stage_radix(L, NS);
-        constexpr int NB = 8 / R;
-        constexpr bool LAST = (NS * R == L);
-        constexpr int TWO = pmx_tw_offset(L, NS);
-        static_assert(NS == 1 || R == 8, "only the first stage may have a small radix");
-        if constexpr (NS > 1) {
-            const int k = t & (NS - 1);
-            cpx w1 = tw[TWO + k], w2 = tw[TWO + NS + k], w4 = tw[TWO + 2 * NS + k];
-            if (INV) {
-                w1.y = -w1.y;
-                w2.y = -w2.y;
-                w4.y = -w4.y;
-            }
-            const cpx w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
-            const cpx w7 = cmul(w4, w3);
-            x[1] = cmul(x[1], w1); y[1] = cmul(y[1], w1);
-            x[2] = cmul(x[2], w2); y[2] = cmul(y[2], w2);
-            x[3] = cmul(x[3], w3); y[3] = cmul(y[3], w3);
-            x[4] = cmul(x[4], w4); y[4] = cmul(y[4], w4);
-            x[5] = cmul(x[5], w5); y[5] = cmul(y[5], w5);
-            x[6] = cmul(x[6], w6); y[6] = cmul(y[6], w6);
-            x[7] = cmul(x[7], w7); y[7] = cmul(y[7], w7);
-        }
+    // x[q], y[q] hold element t + q*T on entry and on exit (natural order).  tw: shared-memory
+    // copy of the per-L stage table.
+    __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t, const cpx* tw) {
+        constexpr int NB = 8 / R0;
+        // ---- first stage
+        if constexpr (R0 == 8) {
+            dft8<false>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            dft8<false>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+        } else {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const int j = t + b * T;
-            const int k = j & (NS - 1);
-            if constexpr (R == 8) {
-                dft8<INV>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-                dft8<INV>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
-            } else if constexpr (R == 4) {
-                dft4<INV>(x[b], x[b + 2], x[b + 4], x[b + 6]);
-                dft4<INV>(y[b], y[b + 2], y[b + 4], y[b + 6]);
-            } else {
-                dft2<INV>(x[b], x[b + 4]);
-                dft2<INV>(y[b], y[b + 4]);
-            }
-            if constexpr (!LAST) {
-                const int j0 = (j - k) * R + k;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int o = pmx_sw(j0 + r * NS);
-                    sx[o] = x[b + NB * r];
-                    sy[o] = y[b + NB * r];
+            for (int b = 0; b < NB; ++b) {
+                if constexpr (R0 == 4) {
+                    dft4<false>(x[b], x[b + 2], x[b + 4], x[b + 6]);
+                    dft4<false>(y[b], y[b + 2], y[b + 4], y[b + 6]);
+                } else {
+                    dft2<false>(x[b], x[b + 4]);
+                    dft2<false>(y[b], y[b + 4]);
                 }
             }
         }
-        if constexpr (!LAST) {
+        if constexpr (R0 == L) return;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j0 = (t + b * T) * R0;
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const int o = pmx_sw(j0 + r);
+                sx[o] = x[b + NB * r];
+                sy[o] = y[b + NB * r];
+            }
+        }
+        int ns = R0, two = 0;
+#pragma unroll 1
+        for (;;) {
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -152,14 +141,35 @@ struct CtaFFT {
                 x[q] = sx[o];
                 y[q] = sy[o];
             }
-            __syncthreads();
-            stage<NS * R>(x, y, sx, sy, t, tw);
+            __syncthreads();  // everyone has read the exchange buffer: free for the next stage / the caller
+            // ---- radix-8 stage with ns sub-transforms done
+            const int k = t & (ns - 1);
+            {
+                const cpx w1 = tw[two + k], w2 = tw[two + ns + k], w4 = tw[two + 2 * ns + k];
+                const cpx w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
+                const cpx w7 = cmul(w4, w3);
+                x[1] = cmul(x[1], w1); y[1] = cmul(y[1], w1);
+                x[2] = cmul(x[2], w2); y[2] = cmul(y[2], w2);
+                x[3] = cmul(x[3], w3); y[3] = cmul(y[3], w3);
+                x[4] = cmul(x[4], w4); y[4] = cmul(y[4], w4);
+                x[5] = cmul(x[5], w5); y[5] = cmul(y[5], w5);
+                x[6] = cmul(x[6], w6); y[6] = cmul(y[6], w6);
+                x[7] = cmul(x[7], w7); y[7] = cmul(y[7], w7);
+            }
+            dft8<false>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            dft8<false>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+            if (ns * 8 >= L) break;
+            const int j0 = (t - k) * 8 + k;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int o = pmx_sw(j0 + r * ns);
+                sx[o] = x[r];
+                sy[o] = y[r];
+            }
+            two += 3 * ns;
+            ns *= 8;
         }
     }
-
-    // x[q], y[q] hold element t + q*T on entry and on exit (natural order).  tw: shared-memory
-    // copy of the per-L stage table.
-    __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t, const cpx* tw) {
-        stage<1>(x, y, sx, sy, t, tw);
-    }
 };
+
+__device__ __forceinline__ cpx cconj(cpx a) { return make_double2(a.x, -a.y); }

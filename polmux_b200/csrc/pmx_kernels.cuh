@@ -5,8 +5,8 @@
 //   pass B  rows   : FFT over n2 -> per-bin Jones/dispersion product over the step's
 //                    trunks (matrix_step :907-933) -> IFFT over k2 -> conj twiddle
 //   pass C  columns: IFFT over k1 -> 1/N * exp(-alpha/2 dz) (:531-532) ->
-//                    max |u|^2 (warp shuffle + one atomicMax per CTA) -> the last CTA
-//                    of a realization runs nextstep + checkstep for the next step
+//                    max |u|^2 (warp shuffle + one atomicMax per CTA and realization)
+//   ctl     one thread per realization: nextstep + checkstep for the next step
 #pragma once
 #include "pmx_fft.cuh"
 #include "pmx_tma.cuh"
@@ -19,7 +19,6 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
         if (c->state == PMX_ST_LAST) {  // the step just finished was the last one
             c->state = PMX_ST_DONE;
             for (int k = 0; k < f.nfc; ++k) c->umax_bits[k] = 0ull;
-            c->ticket = 0u;
             return;
         }
         c->ntot += c->ntrunk - c->nmem;  // fiber.m:529
@@ -34,7 +33,6 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
         pmax = (k == 0) ? gp : fmax(pmax, gp);
         c->umax_bits[k] = 0ull;
     }
-    c->ticket = 0u;
     if (bad) {
         c->state = PMX_ST_ERROR;
         c->err = -5;  // PMX_ERR_NUMERIC
@@ -139,13 +137,11 @@ __device__ __forceinline__ unsigned long long pmx_pow_key(double pw) {
     return (pw != pw) ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(pw);
 }
 
-// Block-wide max (warp shuffles, then one atomicMax per CTA); `add` = number of tiles (of the
-// realization's `total_tiles` per step) this value covers; the CTA that completes the count runs the
-// step control.  scratch: >= 33 x 8 B of shared memory.
-__device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, void* scratch, StepCtl* c, int col,
-                                                      unsigned add, unsigned total_tiles, const FiberConst& f,
-                                                      bool first, int b, double* trace_dz,
-                                                      int* trace_ntrunk) {
+// Block-wide max (warp shuffles, then one fire-and-forget atomicMax per CTA).  The step control that
+// consumes the maxima runs in its own one-thread-per-realization kernel (pmx_k_ctl) after the pass, so
+// no CTA waits on an atomic's return value or on a fence.  scratch: >= 32 x 8 B of shared memory that
+// is not rewritten before the CTA's next __syncthreads().
+__device__ __forceinline__ void pmx_block_max(unsigned long long key, void* scratch, StepCtl* c, int col) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
@@ -160,14 +156,17 @@ __device__ __forceinline__ void pmx_block_max_and_ctl(unsigned long long key, vo
         unsigned long long m = red[0];
         for (int w = 1; w < nwarp; ++w) m = red[w] > m ? red[w] : m;
         atomicMax(&c->umax_bits[col], m);
-        __threadfence();
-        unsigned prev = atomicAdd(&c->ticket, add);
-        if (prev + add == total_tiles) {
-            __threadfence();
-            pmx_ctl_next(c, f, first, b, trace_dz, trace_ntrunk);
-        }
     }
-    __syncthreads();  // scratch free again
+}
+
+// Step control, one thread per realization: nextstep + checkstep for the step about to run
+// (first: fiber.m:512; afterwards :534-536), from the per-column maxima the previous kernel left.
+static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst f, int first) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    StepCtl* c = &p.ctl[b];
+    if (!first && c->state >= PMX_ST_DONE) return;
+    pmx_ctl_next(c, f, first != 0, b, p.trace_dz, p.trace_ntrunk);
 }
 
 // ---------------------------------------------------------------------------
@@ -184,8 +183,7 @@ static __global__ void __launch_bounds__(256) pmx_k_init(PassParams p, FiberCons
         unsigned long long key = pmx_pow_key(power_ref(x, y));
         vmax = key > vmax ? key : vmax;
     }
-    pmx_block_max_and_ctl(vmax, smem, &p.ctl[b], col, 1u, gridDim.x * f.nfc, f, true, b, p.trace_dz,
-                          p.trace_ntrunk);
+    pmx_block_max(vmax, smem, &p.ctl[b], col);
 }
 
 // smem region stride (in cpx) between the rows/columns a CTA works on: offset so
@@ -382,7 +380,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
-        CtaFFT<L, false>::run(x, y, sx, sy, t, stw);
+        CtaFFT<L>::run(x, y, sx, sy, t, stw);
         // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the tile's two-level table; the tile is staged
         // (same swizzled layout as it landed) in the exchange buffer and TMA-stored
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
@@ -543,154 +541,164 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(2)
-        CtaFFT<L, false>::run(x, y, sx, sy, t, stw);
-        PMX_T_MARK(3)
+        // forward transform, per-bin product, inverse transform (= conj o forward o conj): one copy of
+        // the transform code, run twice
+#pragma unroll 1
+        for (int dir = 0; dir < 2; ++dir) {
+            CtaFFT<L>::run(x, y, sx, sy, t, stw);
+            if (dir == 1) break;
+            PMX_T_MARK(3)
 
-        // ---- linear step in the frequency domain, fiber.m:907-933
-        if (ntrunk > 0) {
-            const double dz_cur = st->dz_cur;
-            // Scalar dispersion mode: a thread's bins are k = k1 + N1*(t + q*T): q < 4 on the positive-
-            // frequency side, q >= 4 on the negative one, equally spaced by domega.
-            const long long kb = (long long)k1 + (long long)p.N1 * t;
-            const double dfn = (double)((long long)p.N1 * T) * f.inv_nsymb;
-            const double fn0 = (double)kb * f.inv_nsymb;
-            const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
-            if (f.pmd) {
-                const double lcorr = f.lcorr, dzb_first = st->dzb_first, dzb_last = st->dzb_last;
-                if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
-                const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
-                // whole trunks share exp(-i*db1/2) per bin
-                double d1[SC ? 1 : 8], e1s[SC ? 1 : 8], e1c[SC ? 1 : 8];
-                double d10 = 0.0, d14 = 0.0;
-                cpx E0 = make_double2(1.0, 0.0), E4 = E0;
-                cpx pf0, pf4, pl0, pl4;  // scalar mode: phases of the step's first / last trunk at the two base bins
-                if constexpr (SC) {
-                    d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
-                    d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
-                    if (any_full) {
-                        pmx_sincos(-0.5 * d10, &E0.y, &E0.x);
-                        pmx_sincos(-0.5 * d14, &E4.y, &E4.x);
-                    }
-                    // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
-                    // independent and interleave
-                    const double db0f = splates[0].db0, db0l = st->db0_last;
-                    double a4[4] = {-(0.5 * (d10 + db0f) * dzb_first / lcorr), -(0.5 * (d14 + db0f) * dzb_first / lcorr),
-                                    -(0.5 * (d10 + db0l) * dzb_last / lcorr), -(0.5 * (d14 + db0l) * dzb_last / lcorr)};
-                    double m4 = fmax(fmax(fabs(a4[0]), fabs(a4[1])), fmax(fabs(a4[2]), fabs(a4[3])));
-                    if (m4 < 105615.0) {
-                        pmx_sincos_fast(a4[0], &pf0.y, &pf0.x);
-                        pmx_sincos_fast(a4[1], &pf4.y, &pf4.x);
-                        pmx_sincos_fast(a4[2], &pl0.y, &pl0.x);
-                        pmx_sincos_fast(a4[3], &pl4.y, &pl4.x);
-                    } else {
-                        sincos(a4[0], &pf0.y, &pf0.x);
-                        sincos(a4[1], &pf4.y, &pf4.x);
-                        sincos(a4[2], &pl0.y, &pl0.x);
-                        sincos(a4[3], &pl4.y, &pl4.x);
-                    }
-                } else {
-                    const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
-                    if (any_full) {
-                        double a[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) a[q] = -0.5 * d1[q];
-                        pmx_sincos8(a, e1s, e1c);
-                    }
-                }
-                for (int k0 = 0; k0 < ntrunk; k0 += S::PLATE_CAP) {
-                    if (k0 > 0) {  // more trunks than the staging area holds (one-step 'gp--' runs): next chunk
-                        __syncthreads();
-                        stage_plates(plg + k0, (ntrunk - k0) < S::PLATE_CAP ? (ntrunk - k0) : S::PLATE_CAP);
-                        __syncthreads();
-                    }
-                    const int kend = (ntrunk - k0) < S::PLATE_CAP ? ntrunk : k0 + S::PLATE_CAP;
-                    for (int k = k0; k < kend; ++k) {
-                        const PlateConst& P = splates[k - k0];
-                        const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
-                        if constexpr (SC) {
-                            cpx e0, e4, g;
-                            if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
-                                const cpx h0 = make_double2(P.h0r, P.h0i);
-                                e0 = cmul(E0, h0);
-                                e4 = cmul(E4, h0);
-                                g = make_double2(f.g1r, f.g1i);
-                            } else {  // partial trunk (first or last of the step)
-                                e0 = (k == 0) ? pf0 : pl0;
-                                e4 = (k == 0) ? pf4 : pl4;
-                                g = (k == 0) ? make_double2(st->gpf_r, st->gpf_i) : make_double2(st->gpl_r, st->gpl_i);
-                            }
-                            const cpx g2 = cmul(g, g);
-                            {
-                                const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
-                                const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
-                                x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
-                                x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
-                                x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
-                                x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
-                                x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
-                                x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
-                                x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
-                                x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
-                            }
-                        } else {
-                            if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
-                                const cpx h0 = make_double2(P.h0r, P.h0i);
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const cpx e = cmul(make_double2(e1c[q], e1s[q]), h0);
-                                    x[q] = cmul(x[q], e);
-                                    y[q] = cmulc(y[q], e);
-                                }
-                            } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-                                double a[8], sn[8], cs[8];
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) a[q] = -(0.5 * (d1[q] + P.db0) * dzb / lcorr);
-                                pmx_sincos8(a, sn, cs);
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const cpx e = make_double2(cs[q], sn[q]);
-                                    x[q] = cmul(x[q], e);
-                                    y[q] = cmulc(y[q], e);
-                                }
-                            }
+            // ---- linear step in the frequency domain, fiber.m:907-933
+            if (ntrunk > 0) {
+                const double dz_cur = st->dz_cur;
+                // Scalar dispersion mode: a thread's bins are k = k1 + N1*(t + q*T): q < 4 on the positive-
+                // frequency side, q >= 4 on the negative one, equally spaced by domega.
+                const long long kb = (long long)k1 + (long long)p.N1 * t;
+                const double dfn = (double)((long long)p.N1 * T) * f.inv_nsymb;
+                const double fn0 = (double)kb * f.inv_nsymb;
+                const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
+                if (f.pmd) {
+                    const double lcorr = f.lcorr, dzb_first = st->dzb_first, dzb_last = st->dzb_last;
+                    if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
+                    const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
+                    // whole trunks share exp(-i*db1/2) per bin
+                    double d1[SC ? 1 : 8], e1s[SC ? 1 : 8], e1c[SC ? 1 : 8];
+                    double d10 = 0.0, d14 = 0.0;
+                    cpx E0 = make_double2(1.0, 0.0), E4 = E0;
+                    cpx pf0, pf4, pl0, pl4;  // scalar mode: phases of the step's first / last trunk at the two base bins
+                    if constexpr (SC) {
+                        d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
+                        d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
+                        if (any_full) {
+                            pmx_sincos(-0.5 * d10, &E0.y, &E0.x);
+                            pmx_sincos(-0.5 * d14, &E4.y, &E4.x);
                         }
-                        if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);  // basis change matR(n+1)' * matR(n)
+                        // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
+                        // independent and interleave
+                        const double db0f = splates[0].db0, db0l = st->db0_last;
+                        double a4[4] = {-(0.5 * (d10 + db0f) * dzb_first / lcorr), -(0.5 * (d14 + db0f) * dzb_first / lcorr),
+                                        -(0.5 * (d10 + db0l) * dzb_last / lcorr), -(0.5 * (d14 + db0l) * dzb_last / lcorr)};
+                        double m4 = fmax(fmax(fabs(a4[0]), fabs(a4[1])), fmax(fabs(a4[2]), fabs(a4[3])));
+                        if (m4 < 105615.0) {
+                            pmx_sincos_fast(a4[0], &pf0.y, &pf0.x);
+                            pmx_sincos_fast(a4[1], &pf4.y, &pf4.x);
+                            pmx_sincos_fast(a4[2], &pl0.y, &pl0.x);
+                            pmx_sincos_fast(a4[3], &pl4.y, &pl4.x);
+                        } else {
+                            sincos(a4[0], &pf0.y, &pf0.x);
+                            sincos(a4[1], &pf4.y, &pf4.x);
+                            sincos(a4[2], &pl0.y, &pl0.x);
+                            sincos(a4[3], &pl4.y, &pl4.x);
+                        }
+                    } else {
+                        const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
+    #pragma unroll
+                        for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
+                        if (any_full) {
+                            double a[8];
+    #pragma unroll
+                            for (int q = 0; q < 8; ++q) a[q] = -0.5 * d1[q];
+                            pmx_sincos8(a, e1s, e1c);
+                        }
                     }
+                    for (int k0 = 0; k0 < ntrunk; k0 += S::PLATE_CAP) {
+                        if (k0 > 0) {  // more trunks than the staging area holds (one-step 'gp--' runs): next chunk
+                            __syncthreads();
+                            stage_plates(plg + k0, (ntrunk - k0) < S::PLATE_CAP ? (ntrunk - k0) : S::PLATE_CAP);
+                            __syncthreads();
+                        }
+                        const int kend = (ntrunk - k0) < S::PLATE_CAP ? ntrunk : k0 + S::PLATE_CAP;
+                        for (int k = k0; k < kend; ++k) {
+                            const PlateConst& P = splates[k - k0];
+                            const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
+                            if constexpr (SC) {
+                                cpx e0, e4, g;
+                                if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
+                                    const cpx h0 = make_double2(P.h0r, P.h0i);
+                                    e0 = cmul(E0, h0);
+                                    e4 = cmul(E4, h0);
+                                    g = make_double2(f.g1r, f.g1i);
+                                } else {  // partial trunk (first or last of the step)
+                                    e0 = (k == 0) ? pf0 : pl0;
+                                    e4 = (k == 0) ? pf4 : pl4;
+                                    g = (k == 0) ? make_double2(st->gpf_r, st->gpf_i) : make_double2(st->gpl_r, st->gpl_i);
+                                }
+                                const cpx g2 = cmul(g, g);
+                                {
+                                    const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
+                                    const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
+                                    x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
+                                    x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
+                                    x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
+                                    x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
+                                    x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
+                                    x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
+                                    x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
+                                    x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
+                                }
+                            } else {
+                                if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
+                                    const cpx h0 = make_double2(P.h0r, P.h0i);
+    #pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        const cpx e = cmul(make_double2(e1c[q], e1s[q]), h0);
+                                        x[q] = cmul(x[q], e);
+                                        y[q] = cmulc(y[q], e);
+                                    }
+                                } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+                                    double a[8], sn[8], cs[8];
+    #pragma unroll
+                                    for (int q = 0; q < 8; ++q) a[q] = -(0.5 * (d1[q] + P.db0) * dzb / lcorr);
+                                    pmx_sincos8(a, sn, cs);
+    #pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        const cpx e = make_double2(cs[q], sn[q]);
+                                        x[q] = cmul(x[q], e);
+                                        y[q] = cmulc(y[q], e);
+                                    }
+                                }
+                            }
+                            if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);  // basis change matR(n+1)' * matR(n)
+                        }
+                    }
+                    if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
                 }
-                if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
-            }
-            if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
-                double a[8], sn[8], cs[8];
-                if constexpr (SC) {  // betat regenerated per bin (:355-356)
-                    const double b1 = f.beta1[col], b2 = f.beta2[col];
-#pragma unroll
+                if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
+                    double a[8], sn[8], cs[8];
+                    if constexpr (SC) {  // betat regenerated per bin (:355-356)
+                        const double b1 = f.beta1[col], b2 = f.beta2[col];
+    #pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
+                            const double w = __dmul_rn(f.w0, fn);
+                            const double w2 = __dmul_rn(w, w);
+                            double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
+                            bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
+                            a[q] = -(bt * dz_cur);
+                        }
+                    } else {
+                        const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
+    #pragma unroll
+                        for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
+                    }
+                    pmx_sincos8(a, sn, cs);
+    #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
-                        const double w = __dmul_rn(f.w0, fn);
-                        const double w2 = __dmul_rn(w, w);
-                        double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
-                        bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
-                        a[q] = -(bt * dz_cur);
+                        const cpx e = make_double2(cs[q], sn[q]);
+                        x[q] = cmul(x[q], e);
+                        y[q] = cmul(y[q], e);
                     }
-                } else {
-                    const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
-                }
-                pmx_sincos8(a, sn, cs);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const cpx e = make_double2(cs[q], sn[q]);
-                    x[q] = cmul(x[q], e);
-                    y[q] = cmul(y[q], e);
                 }
             }
-        }
 
-        PMX_T_MARK(4)
-        CtaFFT<L, true>::run(x, y, sx, sy, t, stw);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                x[q] = cconj(x[q]);
+                y[q] = cconj(y[q]);
+            }
+            PMX_T_MARK(4)
+        }
         PMX_T_MARK(5)
         if (!PF && threadIdx.x == 0 && next < total) issue(next);
         // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T, from the tile's two-level table
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
-                st_sa(base + (size_t)(t + q * T) * 2, cmulc(x[q], w), cmulc(y[q], w));
+                st_sa(base + (size_t)(t + q * T) * 2, cconj(cmul(x[q], w)), cconj(cmul(y[q], w)));
             }
         }
         tile = next;
@@ -714,7 +722,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
 // ---------------------------------------------------------------------------
 // pass C: like pass A, inverse transform + attenuation + max reduction + step control.  The running
 // maximum stays in registers across the tiles a CTA handles for one realization-column and is
-// published (one atomicMax + one ticket add per CTA) when the CTA moves on to another one.
+// published (one atomicMax per CTA) when the CTA moves on to another one.
 template <int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
@@ -755,7 +763,6 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     if (threadIdx.x == 0 && tile < total) issue(tile);
     uint32_t phase = 0;
     unsigned long long vmax = 0ull;  // running max of this thread for the current realization-column
-    unsigned ntiles = 0;             // tiles it covers
     while (tile < total) {
         const int bc = tile >> ltpb, c0 = (tile & tpb_mask) * G;
         int b, col;
@@ -769,28 +776,27 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
-            x[q] = *reinterpret_cast<const cpx*>(in + off);
-            y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
+            x[q] = cconj(*reinterpret_cast<const cpx*>(in + off));   // inverse transform = conj o forward o conj
+            y[q] = cconj(*reinterpret_cast<const cpx*>(in + (off ^ 16u)));
         }
         if (threadIdx.x == 0) pmx_tma_wait_read();
         __syncthreads();
         if (PF && threadIdx.x == 0 && next < total) issue(next);
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
-        CtaFFT<L, true>::run(x, y, sx, sy, t, stw);
-        const double sc = sred[0];
+        CtaFFT<L>::run(x, y, sx, sy, t, stw);
+        const double sc = sred[0], nsc = -sc;
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            x[q] = cscale(x[q], sc);
-            y[q] = cscale(y[q], sc);
+            x[q] = make_double2(x[q].x * sc, x[q].y * nsc);
+            y[q] = make_double2(y[q].x * sc, y[q].y * nsc);
             unsigned long long key = pmx_pow_key(power_ref(x[q], y[q]));
             vmax = key > vmax ? key : vmax;
             const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
             *reinterpret_cast<cpx*>(outb + off) = x[q];
             *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = y[q];
         }
-        ++ntiles;
         pmx_fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -801,13 +807,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                 issue(next);
             }
         }
-        // Kernel boundaries order the bulk stores against the next pass; the step control of the last
-        // CTA only needs every CTA's maximum, which the ticket counts.
-        if (next >= total || (next >> ltpb) != bc) {
-            pmx_block_max_and_ctl(vmax, sred + 1, c, col, ntiles, (unsigned)((1 << ltpb) * f.nfc), f, false, b,
-                                  p.trace_dz, p.trace_ntrunk);
+        if (next >= total || (next >> ltpb) != bc) {  // moving on: publish the maximum (pmx_k_ctl consumes it)
+            pmx_block_max(vmax, sred + 1, c, col);
             vmax = 0ull;
-            ntiles = 0;
         }
         tile = next;
     }
