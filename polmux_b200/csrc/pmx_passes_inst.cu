@@ -17,7 +17,11 @@ constexpr int GAC = (L >= 1024) ? 1 : (L == 512 ? 2 : 4);
 constexpr int GAC = PMX_GAC;
 #endif
 constexpr int GB = (L >= 1024) ? 1 : (L == 512 ? 2 : 4);
+#ifndef PMX_PFAC
 constexpr bool PFAC = (GAC * L <= 1024);
+#else
+constexpr bool PFAC = (PMX_PFAC != 0) && (GAC * L <= 1024);
+#endif
 #ifndef PMX_PFB
 // pass B is compute-bound: it prefers a fourth resident CTA to a separate prefetch buffer
 constexpr bool PFB = (GB * L <= 512);
