@@ -62,10 +62,8 @@ static int set_err(pmx_ctx* ctx, int code, const char* fmt, ...);
 struct StageTw {
     cpx* dev = nullptr;
 };
-struct FourStepTw {
-    cpx* hi = nullptr;
-    cpx* lo = nullptr;
-    int lo_bits = 0;
+struct FourStepTw {  // per-row two-level four-step twiddle table (PmxTw4<L> layout), see pmx_k_fill_tw4
+    cpx* rows = nullptr;
 };
 
 struct pmx_ctx {
@@ -199,6 +197,7 @@ struct pmx_plan {
     double* db1_p = nullptr;
     PlateConst* plates = nullptr;
     StepCtl* ctl = nullptr;
+    StepPkg* pkg = nullptr;  // [batch] step packages written by pmx_k_ctl
     double* trace_dz = nullptr;
     int* trace_ntrunk = nullptr;
     int trace_cap = 0;
@@ -288,8 +287,7 @@ extern "C" void pmx_ctx_destroy(pmx_ctx* c) {
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (auto& kv : c->stage_tw) cudaFree(kv.second.dev);
     for (auto& kv : c->four_tw) {
-        cudaFree(kv.second.hi);
-        cudaFree(kv.second.lo);
+        cudaFree(kv.second.rows);
     }
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     cudaStreamDestroy(c->stream);
@@ -360,23 +358,22 @@ static int get_stage_tw(pmx_ctx* c, int L, const cpx** dev) {
     return PMX_OK;
 }
 
-static int get_four_tw(pmx_ctx* c, long long N, int log2N, FourStepTw* out) {
-    auto it = c->four_tw.find(N);
+// W_N^(r*m) rows for a pass whose in-CTA transform has length L (table of that L gives the row layout) and
+// whose tiles are indexed by r in [0, rows): rows * per entries, built on the device once per (N, L).
+static int get_four_tw(pmx_ctx* c, long long N, const PmxLaunchTable* t, int rows, const cpx** out) {
+    const long long key = N * 8192 + t->L;
+    auto it = c->four_tw.find(key);
     if (it == c->four_tw.end()) {
-        FourStepTw t;
-        t.lo_bits = (log2N + 1) / 2;
-        long long nlo = 1ll << t.lo_bits, nhi = N >> t.lo_bits;
-        std::vector<cpx> lo((size_t)nlo), hi((size_t)nhi);
-        for (long long j = 0; j < nlo; ++j) lo[(size_t)j] = pmx_root(j, N);
-        for (long long j = 0; j < nhi; ++j) hi[(size_t)j] = pmx_root(j << t.lo_bits, N);
-        CK(c, cudaMalloc(&t.lo, lo.size() * sizeof(cpx)));
-        CK(c, cudaMalloc(&t.hi, hi.size() * sizeof(cpx)));
-        CK(c, cudaMemcpyAsync(t.lo, lo.data(), lo.size() * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
-        CK(c, cudaMemcpyAsync(t.hi, hi.data(), hi.size() * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
-        CK(c, cudaStreamSynchronize(c->stream));
-        it = c->four_tw.emplace(N, t).first;
+        FourStepTw tw;
+        const size_t n = (size_t)rows * t->tw4_per;
+        CK(c, cudaMalloc(&tw.rows, n * sizeof(cpx)));
+        pmx_k_fill_tw4<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, c->stream>>>(tw.rows, rows, t->tw4_lo_bits,
+                                                                                           t->tw4_per, 2.0 / (double)N);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        it = c->four_tw.emplace(key, tw).first;
     }
-    *out = it->second;
+    *out = it->second.rows;
     return PMX_OK;
 }
 
@@ -640,6 +637,7 @@ extern "C" void pmx_plan_destroy(pmx_plan* p) {
     if (p->db1_p) cudaFreeAsync(p->db1_p, st);
     if (p->plates) cudaFreeAsync(p->plates, st);
     if (p->ctl) cudaFreeAsync(p->ctl, st);
+    if (p->pkg) cudaFreeAsync(p->pkg, st);
     if (p->trace_dz) cudaFreeAsync(p->trace_dz, st);
     if (p->trace_ntrunk) cudaFreeAsync(p->trace_ntrunk, st);
     delete p;
@@ -744,6 +742,7 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
         }
         f.gvd_any = any ? 1 : 0;
         cudaError_t e = cudaMallocAsync(&p->ctl, (size_t)d->batch * sizeof(StepCtl), c->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&p->pkg, (size_t)d->batch * sizeof(StepPkg), c->stream);
         if (e != cudaSuccess) {
             pmx_plan_destroy(p);
             return set_err(c, PMX_ERR_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
@@ -784,6 +783,7 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
             }
         }
         if (e == cudaSuccess) e = cudaMallocAsync(&p->ctl, (size_t)d->batch * sizeof(StepCtl), c->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&p->pkg, (size_t)d->batch * sizeof(StepPkg), c->stream);
         if (raw) cudaFreeAsync(raw, c->stream);
         if (d_any) cudaFreeAsync(d_any, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // host vectors may go away; `any` is valid
@@ -860,12 +860,12 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     pa.log2N2 = p->log2N2;
     pa.batch = batch;
     pa.dbg = g_dbg;
-    FourStepTw ft;
-    rc = get_four_tw(c, p->d.nfft, p->log2N1 + p->log2N2, &ft);
+    pa.pkg = p->pkg;
+    const cpx *tw4A, *tw4B;
+    rc = get_four_tw(c, p->d.nfft, p->tA, p->N2, &tw4A);  // pass A: one row per column n2, W_N^(n2*k1), k1 < N1
     if (rc) return rc;
-    pa.tw_hi = ft.hi;
-    pa.tw_lo = ft.lo;
-    pa.lo_bits = ft.lo_bits;
+    rc = get_four_tw(c, p->d.nfft, p->tB, p->N1, &tw4B);  // pass B: one row per k1, W_N^(k1*n2), n2 < N2
+    if (rc) return rc;
     const cpx *twA, *twB;
     rc = get_stage_tw(c, p->N1, &twA);
     if (rc) return rc;
@@ -874,13 +874,16 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     PassParams pA = pa, pB = pa;
     pA.tw_stage = twA;
     pB.tw_stage = twB;
+    pA.tw4 = tw4A;
+    pB.tw4 = tw4B;
 
     CK(c, cudaMemsetAsync(p->ctl, 0, (size_t)batch * sizeof(StepCtl), c->stream));
+    CK(c, cudaMemsetAsync(p->pkg, 0, (size_t)batch * sizeof(StepPkg), c->stream));
     {
         dim3 g(148 * 2, batch * nfc);
         ProfScope ps(c, 3);
         pmx_k_init<<<g, 256, 256, c->stream>>>(pa, p->fc);
-        pmx_k_ctl<<<(batch + 127) / 128, 128, 0, c->stream>>>(pa, p->fc, 1);
+        pmx_k_ctl<<<batch, 128, 0, c->stream>>>(pa, p->fc, 1);
         c->launches += 2;
         CK(c, cudaGetLastError());
     }
@@ -890,13 +893,19 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     const int gA = std::min(tilesAC, c->sm_count * oA.a), gB = std::min(tilesB, c->sm_count * oB.b),
               gC = std::min(tilesAC, c->sm_count * oA.c);
     int chunk = p->single_step ? 1 : 8;
+    int rev = 1;
+    static const bool serp = !getenv("PMX_NO_SERPENTINE");
     long total_steps = 0;
     for (;;) {
         for (int s = 0; s < chunk; ++s) {
+            // serpentine tile order: consecutive passes walk the realizations in opposite directions
+            pA.reverse = serp ? (rev ^= 1) : 0;
             { ProfScope ps(c, 0); p->tA->passA(gA, c->stream, pA, p->fc, fld->map_cols); }
+            pB.reverse = serp ? (rev ^= 1) : 0;
             { ProfScope ps(c, 1); p->tB->passB(gB, c->stream, pB, p->fc, fld->map_rows); }
+            pA.reverse = serp ? (rev ^= 1) : 0;
             { ProfScope ps(c, 2); p->tA->passC(gC, c->stream, pA, p->fc, fld->map_cols); }
-            pmx_k_ctl<<<(batch + 127) / 128, 128, 0, c->stream>>>(pa, p->fc, 0);
+            pmx_k_ctl<<<batch, 128, 0, c->stream>>>(pa, p->fc, 0);
             c->launches += 4;
             if (c->profile && c->ev_used > 4096) prof_collect(c);
         }

@@ -62,6 +62,19 @@ struct __align__(16) PlateConst {
     double pad;
 };
 
+// What the pass kernels need to know about the step in flight, per realization: written by the step-control
+// kernel (pmx_k_ctl) once per step, fetched by every tile with ONE bulk copy (cp.async.bulk, same mbarrier as the
+// tile itself), so no pass thread ever waits on a dependent global load of step state.
+#define PMX_PKG_PLATES 16
+struct __align__(16) StepPkg {
+    double dz_cur, leff, scale, dzb_first, dzb_last, gpf_r, gpf_i, gpl_r, gpl_i, db0_last;
+    int ntrunk, n_first, bmode, state;  // -- 96-byte header: all passes
+    double E[8];   // pass B entry matrix (row-major re,im): R(first)^H, or the boundary matrix of the plate before
+    double X[8];   // pass B exit matrix R(last)
+    PlateConst plates[PMX_PKG_PLATES];  // the first trunks of the step (more are read from the plate array)
+};
+#define PMX_PKG_HEAD 96
+
 // Constants of one fiber() call (kernel parameter, by value).
 struct FiberConst {
     double Lf, alphalin, halfalpha, dzmax, phimax, lcorr, invN;
@@ -82,16 +95,17 @@ struct PassParams {
     cpx* field;             // [batch*nfc][N][2]
     StepCtl* ctl;           // [batch]
     const cpx* tw_stage;    // in-CTA FFT stage twiddles for this L
-    const cpx* tw_hi;       // four-step twiddle W_N^(m) = hi[m >> lo_bits] * lo[m & lo_mask]
-    const cpx* tw_lo;
     const double* betat_p;  // [nfc][N1][N2] permuted so that bin k1 + N1*k2 sits at k1*N2 + k2
     const double* db1_p;    // same layout
     const PlateConst* plates;  // [plate_sets][nplates]
+    StepPkg* pkg;           // [batch]
+    const cpx* tw4;         // four-step twiddle rows for this pass: [rows][PmxTw4<L>::PER], see pmx_kernels.cuh
     double* trace_dz;       // [batch][trace_cap] or null
     int* trace_ntrunk;
     int N1, N2, log2N1, log2N2;
-    int lo_bits;
     int batch;
+    int reverse;            // walk the tile list backwards (alternates from pass to pass: the tiles the previous
+                            // pass wrote last are still in L2 when this pass reads them first)
     long long* dbg;         // optional per-CTA phase cycle counters (PMX_TIMING builds only)
 };
 

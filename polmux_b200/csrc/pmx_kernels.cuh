@@ -159,14 +159,60 @@ __device__ __forceinline__ void pmx_block_max(unsigned long long key, void* scra
     }
 }
 
-// Step control, one thread per realization: nextstep + checkstep for the step about to run
-// (first: fiber.m:512; afterwards :534-536), from the per-column maxima the previous kernel left.
+// Step control, one CTA per realization: thread 0 runs nextstep + checkstep for the step about to run
+// (first: fiber.m:512; afterwards :534-536) from the per-column maxima the previous kernel left, then the
+// CTA writes the step package the pass kernels fetch with their tiles.
 static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst f, int first) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.batch) return;
+    const int b = blockIdx.x;
     StepCtl* c = &p.ctl[b];
-    if (!first && c->state >= PMX_ST_DONE) return;
-    pmx_ctl_next(c, f, first != 0, b, p.trace_dz, p.trace_ntrunk);
+    StepPkg* g = &p.pkg[b];
+    __shared__ int s_go;
+    if (threadIdx.x == 0) {
+        const int go = first || c->state < PMX_ST_DONE;
+        if (go) pmx_ctl_next(c, f, first != 0, b, p.trace_dz, p.trace_ntrunk);
+        g->state = c->state;
+        s_go = go && c->state < PMX_ST_DONE;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    const int ntrunk = c->ntrunk, n_first = c->n_first;
+    const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + n_first;
+    if (threadIdx.x == 0) {
+        g->dz_cur = c->dz_cur;
+        g->leff = c->leff;
+        g->scale = c->scale;
+        g->dzb_first = c->dzb_first;
+        g->dzb_last = c->dzb_last;
+        g->gpf_r = c->gpf_r;
+        g->gpf_i = c->gpf_i;
+        g->gpl_r = c->gpl_r;
+        g->gpl_i = c->gpl_i;
+        g->db0_last = (f.pmd && ntrunk > 0) ? plg[ntrunk - 1].db0 : 0.0;
+        g->ntrunk = ntrunk;
+        g->n_first = n_first;
+        g->bmode = f.pmd ? c->bmode : 0;
+    }
+    if (!f.pmd || ntrunk <= 0) return;
+    if (threadIdx.x >= 32 && threadIdx.x < 40) {  // entry matrix
+        const int i = threadIdx.x - 32;
+        double v = (i == 0 || i == 6) ? 1.0 : 0.0;
+        if (c->bmode & PMX_BM_ENTRY_R) {  // R^H: element (r,cc) = conj(R(cc,r))
+            const int r = i >> 2, cc = (i >> 1) & 1, im = i & 1;
+            v = (&plg[0].r11r)[(cc * 2 + r) * 2 + im];
+            if (im) v = -v;
+        } else if (c->bmode & PMX_BM_ENTRY_C) {
+            v = (&plg[-1].c11r)[i];
+        }
+        g->E[i] = v;
+    } else if (threadIdx.x >= 40 && threadIdx.x < 48) {  // exit matrix
+        const int i = threadIdx.x - 40;
+        g->X[i] = (&plg[ntrunk - 1].r11r)[i];
+    }
+    constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
+    const int n = (ntrunk < PMX_PKG_PLATES ? ntrunk : PMX_PKG_PLATES) * PLD;
+    const double* src = reinterpret_cast<const double*>(plg);
+    double* dst = reinterpret_cast<double*>(g->plates);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -195,9 +241,10 @@ struct PmxSmem {
     static constexpr int STRIDE = BASE + OFF;
 };
 
-// Four-step twiddle of one row/column, W_N^(r*m) for m in [0, L): two-level table per tile,
-// W^(r*m) = lo[m & (2^LO-1)] * hi[m >> LO], built with exact-argument sincospi by the threads of
-// the CTA while the tile is in flight (no HBM table, no dependent global load before the store).
+// Four-step twiddle of one row/column, W_N^(r*m) for m in [0, L): two-level table per row,
+// W^(r*m) = lo[m & (2^LO-1)] * hi[m >> LO].  The rows live in a per-plan table in global memory
+// ([rows][PER], built once with exact-argument sincospi, L2-resident) and reach shared memory with the
+// tile's bulk copy: no per-tile trigonometry, no dependent global load before the store.
 template <int L>
 struct PmxTw4 {
     static constexpr int LOG = pmx_ilog2(L);
@@ -205,22 +252,15 @@ struct PmxTw4 {
     static constexpr int NLO = 1 << LO, NHI = 1 << HI, PER = NLO + NHI;
 };
 
-#ifndef PMX_PLATE_CAP
-#define PMX_PLATE_CAP 32   // trunks of a step whose plate constants are staged in shared memory at once
-#endif
-
-// per-tile scalars of pass B, staged in shared memory at the top of a tile
-struct BStage {
-    double dz_cur, dzb_first, dzb_last, gpf_r, gpf_i, gpl_r, gpl_i, db0_last;
-    double E[8];   // entry matrix (row-major re,im): R(first)^H, or the boundary matrix of the plate before
-    double X[8];   // exit matrix R(last)
-};
+#define PMX_LIVE_CAP 256    // realizations whose done-flags a CTA caches in shared memory
 
 // Shared-memory plan of a pass CTA working on G rows (pass B) or G columns (passes A, C) of
 // length L.  PF: the next tile is prefetched by TMA into its own landing buffer while the
 // current one is computed; !PF: the tile lands in the exchange buffer itself and the next load
-// is issued as soon as the last exchange of the current tile is over.
-template <int L, int G, bool PF, int NPLATE = 0>
+// is issued as soon as the last exchange of the current tile is over.  KIND: 0 = pass A, 1 = B, 2 = C.
+// The per-tile auxiliary data (step package of the realization + four-step twiddle rows) is
+// double-buffered: tile i uses aux[i & 1] while the bulk copies for tile i+1 land in the other one.
+template <int L, int G, bool PF, int KIND>
 struct PassSmem {
     static constexpr int T = L / 8;
     static constexpr int THREADS = G * T;
@@ -228,14 +268,18 @@ struct PassSmem {
     static constexpr int WORK_BYTES = G * PmxSmem<L, G>::STRIDE * 16;
     static constexpr int WORK_OFF = PF ? ((TILE_BYTES + 1023) / 1024) * 1024 : 0;
     static constexpr int TW_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;   // stage twiddles
-    static constexpr int GTAB_OFF = TW_OFF + pmx_tw_total(L) * 16;             // four-step twiddle tables
-    static constexpr int PLATE_CAP = NPLATE;                   // trunks of the step staged in smem (pass B)
-    static constexpr int PLATE_OFF = GTAB_OFF + G * PmxTw4<L>::PER * 16;
-    static constexpr int STAGE_OFF = PLATE_OFF + PLATE_CAP * (int)sizeof(PlateConst);
-    static constexpr int RED_OFF = STAGE_OFF + (NPLATE ? (int)sizeof(BStage) : 0);
-    static constexpr int MBAR_OFF = RED_OFF + 32 * 8;
-    static constexpr int TOTAL = MBAR_OFF + 16 + 1024;  // + slack to align the base to 1024 B
+    static constexpr int PKG_BYTES = (KIND == 1) ? (int)sizeof(StepPkg) : PMX_PKG_HEAD;
+    static constexpr int TAB_BYTES = (KIND == 2) ? 0 : G * PmxTw4<L>::PER * 16;
+    static constexpr int AUX_BYTES = PKG_BYTES + TAB_BYTES;
+    static constexpr int AUX_OFF = TW_OFF + pmx_tw_total(L) * 16;
+    static constexpr int PLATE_OFF = AUX_OFF + 2 * AUX_BYTES;               // pass B: chunks of trunks beyond the package
+    static constexpr int RED_OFF = PLATE_OFF + ((KIND == 1) ? PMX_PKG_PLATES * (int)sizeof(PlateConst) : 0);
+    static constexpr int LIVE_OFF = RED_OFF + 32 * 8;
+    static constexpr int MBAR_OFF = LIVE_OFF + PMX_LIVE_CAP;
+    static constexpr int TOTAL = MBAR_OFF + 16;  // the dynamic shared array is declared 1024-byte aligned
+    static constexpr int LOAD_BYTES = TILE_BYTES + AUX_BYTES;  // bytes one tile's mbarrier phase expects
     static_assert(WORK_BYTES >= TILE_BYTES, "exchange buffer must hold a landed tile");
+    static_assert(sizeof(StepPkg) % 16 == 0 && PMX_PKG_HEAD % 16 == 0, "bulk copies move multiples of 16 bytes");
 };
 
 // copy the per-L stage-twiddle table into shared memory (once per persistent CTA)
@@ -244,21 +288,33 @@ __device__ __forceinline__ void pmx_load_stage_tw(cpx* dst, const cpx* __restric
     for (int i = threadIdx.x; i < pmx_tw_total(L); i += blockDim.x) dst[i] = __ldg(&src[i]);
 }
 
-__device__ __forceinline__ unsigned char* pmx_align1024(unsigned char* p) {
-    return p + ((1024u - (pmx_smem_u32(p) & 1023u)) & 1023u);
+// the swizzled TMA landing buffers need a 1024-byte aligned base; the extern array is declared so
+__device__ __forceinline__ unsigned char* pmx_checked1024(unsigned char* p) {
+    if (pmx_smem_u32(p) & 1023u) __trap();
+    return p;
 }
 
-// tab[g*PER + ...] for the G rows/columns r0 .. r0+G-1 of a tile; invN2 = 2/N (sincospi argument scale)
-template <int L, int G>
-__device__ __forceinline__ void pmx_fill_tw4(cpx* tab, int r0, double two_over_N) {
-    using W = PmxTw4<L>;
-    for (int i = threadIdx.x; i < G * W::PER; i += blockDim.x) {
-        const int g = i / W::PER, e = i % W::PER;
-        const int m = (e < W::NLO) ? e : ((e - W::NLO) << W::LO);
-        double s, c;
-        sincospi(-(double)((long long)(r0 + g) * m) * two_over_N, &s, &c);  // exact argument: N is a power of two
-        tab[i] = make_double2(c, s);
+// Per-plan four-step twiddle rows: tab[r*PER + e] = W_N^(r*m(e)), m(e) = e for e < NLO, (e-NLO) << LO above.
+static __global__ void pmx_k_fill_tw4(cpx* tab, int rows, int lo_bits, int per, double two_over_N) {
+    const int nlo = 1 << lo_bits;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * per;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / per), e = (int)(i % per);
+        const int m = (e < nlo) ? e : ((e - nlo) << lo_bits);
+        double sn, cs;
+        sincospi(-(double)((long long)r * m) * two_over_N, &sn, &cs);  // exact argument: N is a power of two
+        tab[i] = make_double2(cs, sn);
     }
+}
+
+// done-flags of the realizations, cached per CTA (the step control runs between passes, so they are
+// constant while a pass runs)
+__device__ __forceinline__ void pmx_cache_live(unsigned char* sdone, const PassParams& p) {
+    if (p.batch <= PMX_LIVE_CAP)
+        for (int i = threadIdx.x; i < p.batch; i += blockDim.x) sdone[i] = p.pkg[i].state >= PMX_ST_DONE ? 1 : 0;
+}
+__device__ __forceinline__ bool pmx_is_done(const unsigned char* sdone, const PassParams& p, int b) {
+    return (p.batch <= PMX_LIVE_CAP) ? (sdone[b] != 0) : (p.pkg[b].state >= PMX_ST_DONE);
 }
 
 // realization / column of a flat realization-column index
@@ -285,61 +341,81 @@ __device__ __forceinline__ void pmx_split_bc(int bc, const FiberConst& f, int& b
 #define PMX_MINB(threads, pf) ((pf) ? ((384 / (threads)) > 0 ? (384 / (threads)) : 1) : ((512 / (threads)) > 0 ? (512 / (threads)) : 1))
 
 // ---------------------------------------------------------------------------
-// pass A: G adjacent columns per tile, thread (cl fastest, t).  Persistent CTAs walk the
-// tile list (tile = realization-column bc, column group); finished realizations are skipped.
+// Tile walk shared by the three passes (persistent CTAs): tile -> (realization-column bc, group inside it),
+// serpentine direction, skipping finished realizations.
+struct PmxWalk {
+    int ltpb, tpb_mask, total, reverse;
+    __device__ __forceinline__ int phys(int tl) const { return reverse ? total - 1 - tl : tl; }
+};
+
+// ---------------------------------------------------------------------------
+// pass A: G adjacent columns per tile, thread (cl fastest, t).
 template <int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passA(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
-    using S = PassSmem<L, G, PF>;
+    using S = PassSmem<L, G, PF, 0>;
     using W = PmxTw4<L>;
     constexpr int T = L / 8, PITCH = G * 32, MASK = PITCH / 16 - 1;
-    extern __shared__ unsigned char smraw[];
-    unsigned char* sm = pmx_align1024(smraw);
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;  // PF: landing buffer at 0; !PF: WORK_OFF == 0, lands in the exchange buffer
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
-    cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
-    double* sred = reinterpret_cast<double*>(sm + S::RED_OFF);  // [0] = leff of the tile's realization
+    unsigned char* aux0 = sm + S::AUX_OFF;
+    unsigned char* sdone = sm + S::LIVE_OFF;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
-    const int ltpb = p.log2N2 - pmx_ilog2(G), tpb_mask = (1 << ltpb) - 1, total = (p.batch * f.nfc) << ltpb;
+    PmxWalk wk;
+    wk.ltpb = p.log2N2 - pmx_ilog2(G);
+    wk.tpb_mask = (1 << wk.ltpb) - 1;
+    wk.total = (p.batch * f.nfc) << wk.ltpb;
+    wk.reverse = p.reverse;
+    const int total = wk.total;
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
-    const double two_over_N = 2.0 * f.invN;
 
     auto live = [&](int tl) {
         while (tl < total) {
             int b_, col_;
-            pmx_split_bc(tl >> ltpb, f, b_, col_);
-            if (p.ctl[b_].state < PMX_ST_DONE) break;
+            pmx_split_bc(wk.phys(tl) >> wk.ltpb, f, b_, col_);
+            if (!pmx_is_done(sdone, p, b_)) break;
             tl += gridDim.x;
         }
         return tl;
     };
-    auto issue = [&](int tl) {  // one thread
+    auto issue = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
-        pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
-        const int bc = tl >> ltpb, c0 = (tl & tpb_mask) * G;
+        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
         for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
+        int b_, col_;
+        pmx_split_bc(bc, f, b_, col_);
+        unsigned char* a = aux0 + buf * S::AUX_BYTES;
+        pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
+        pmx_bulk_load(a + S::PKG_BYTES, p.tw4 + (size_t)c0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
         pmx_fence_mbar_init();
     }
     pmx_load_stage_tw<L>(stw, p.tw_stage);
+    pmx_cache_live(sdone, p);
     __syncthreads();
-    int tile = live(blockIdx.x);
-    if (threadIdx.x == 0 && tile < total) issue(tile);
+    int tile = live(blockIdx.x), it = 0;
+    if (threadIdx.x == 0 && tile < total) issue(tile, 0);
     uint32_t phase = 0;
+    PMX_T_DECL
     while (tile < total) {
-        const int bc = tile >> ltpb, c0 = (tile & tpb_mask) * G;
+        const int tt = wk.phys(tile), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
-        // tile top: scalars and the four-step twiddle table while the tile is in flight
+        const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
+        const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
+        const cpx* gtab = reinterpret_cast<const cpx*>(aux + S::PKG_BYTES);
         const int next = live(tile + gridDim.x);
-        if (threadIdx.x == 0) sred[0] = p.ctl[b].leff;
-        pmx_fill_tw4<L, G>(gtab, c0, two_over_N);
         cpx x[8], y[8];
+        PMX_T_MARK(0)
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
+        PMX_T_MARK(1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
@@ -348,10 +424,11 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
         __syncthreads();
-        if (PF && threadIdx.x == 0 && next < total) issue(next);
+        if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+        PMX_T_MARK(2)
         // ---- nonlinear step, fiber.m:832-851
         if (f.spm) {
-            const double gamleff = __dmul_rn(f.gam[col], sred[0]);
+            const double gamleff = __dmul_rn(f.gam[col], st->leff);
             const double ngl = -gamleff;
             double ph[8], sn[8], cs[8];
 #pragma unroll
@@ -380,8 +457,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
+        PMX_T_MARK(3)
         CtaFFT<L>::run(x, y, sx, sy, t, stw);
-        // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the tile's two-level table; the tile is staged
+        PMX_T_MARK(4)
+        // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the column's two-level table; the tile is staged
         // (same swizzled layout as it landed) in the exchange buffer and TMA-stored
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
         {
@@ -395,18 +474,22 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                 *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = cmul(y[q], w);
             }
         }
+        PMX_T_MARK(5)
         pmx_fence_proxy_async();
-        __syncthreads();  // tile staged; tables free for the next tile
+        __syncthreads();  // tile staged
         if (threadIdx.x == 0) {
             for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, bc, outb + r0 * PITCH);
             pmx_tma_commit();
             if (!PF && next < total) {  // the next tile lands in this same buffer
                 pmx_tma_wait_read();
-                issue(next);
+                issue(next, (it + 1) & 1);
             }
         }
         tile = next;
+        ++it;
+        PMX_T_MARK(6)
     }
+    PMX_T_FLUSH(0)
     if (threadIdx.x == 0) pmx_tma_wait_read();
 }
 
@@ -434,97 +517,70 @@ __device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const dou
 template <int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
-    using S = PassSmem<L, G, PF, PMX_PLATE_CAP>;
+    using S = PassSmem<L, G, PF, 1>;
     using W = PmxTw4<L>;
     constexpr int T = L / 8;
-    extern __shared__ unsigned char smraw[];
-    unsigned char* sm = pmx_align1024(smraw);
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
-    cpx* gtab = reinterpret_cast<cpx*>(sm + S::GTAB_OFF);
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
-    PlateConst* splates = reinterpret_cast<PlateConst*>(sm + S::PLATE_OFF);
-    BStage* st = reinterpret_cast<BStage*>(sm + S::STAGE_OFF);
+    unsigned char* aux0 = sm + S::AUX_OFF;
+    PlateConst* schunk = reinterpret_cast<PlateConst*>(sm + S::PLATE_OFF);
+    unsigned char* sdone = sm + S::LIVE_OFF;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
-    const int ltpb = p.log2N1 - pmx_ilog2(G), tpb_mask = (1 << ltpb) - 1, total = (p.batch * f.nfc) << ltpb;
+    PmxWalk wk;
+    wk.ltpb = p.log2N1 - pmx_ilog2(G);
+    wk.tpb_mask = (1 << wk.ltpb) - 1;
+    wk.total = (p.batch * f.nfc) << wk.ltpb;
+    wk.reverse = p.reverse;
+    const int total = wk.total;
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
     const size_t N = (size_t)p.N1 * p.N2;
-    const double two_over_N = 2.0 * f.invN;
     constexpr int LINES = G * L / 4;  // 128-byte lines per tile
     constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
 
     auto live = [&](int tl) {
         while (tl < total) {
             int b_, col_;
-            pmx_split_bc(tl >> ltpb, f, b_, col_);
-            if (p.ctl[b_].state < PMX_ST_DONE) break;
+            pmx_split_bc(wk.phys(tl) >> wk.ltpb, f, b_, col_);
+            if (!pmx_is_done(sdone, p, b_)) break;
             tl += gridDim.x;
         }
         return tl;
     };
-    auto issue = [&](int tl) {
+    auto issue = [&](int tl, int buf) {
         pmx_fence_proxy_async();
-        pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
-        const int bc = tl >> ltpb, line0 = (tl & tpb_mask) * LINES;
-        for (int l0 = 0; l0 < LINES; l0 += 256) pmx_tma_load_3d(in + l0 * 128, &tmap, 0, line0 + l0, bc, mbar);
-    };
-    // stage `n` plates starting at global plate pointer `src` into shared memory
-    auto stage_plates = [&](const PlateConst* src, int n) {
-        const double* s_ = reinterpret_cast<const double*>(src);
-        double* d_ = reinterpret_cast<double*>(splates);
-        for (int i = threadIdx.x; i < n * PLD; i += blockDim.x) d_[i] = __ldg(&s_[i]);
+        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
+        for (int l0 = 0; l0 < LINES; l0 += 256)
+            pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, bc, mbar);
+        int b_, col_;
+        pmx_split_bc(bc, f, b_, col_);
+        unsigned char* a = aux0 + buf * S::AUX_BYTES;
+        pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
+        pmx_bulk_load(a + S::PKG_BYTES, p.tw4 + (size_t)row0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
         pmx_fence_mbar_init();
     }
     pmx_load_stage_tw<L>(stw, p.tw_stage);
+    pmx_cache_live(sdone, p);
     __syncthreads();
-    int tile = live(blockIdx.x);
-    if (threadIdx.x == 0 && tile < total) issue(tile);
+    int tile = live(blockIdx.x), it = 0;
+    if (threadIdx.x == 0 && tile < total) issue(tile, 0);
     uint32_t phase = 0;
     PMX_T_DECL
     while (tile < total) {
-        // ---- tile top: everything that comes from global memory besides the tile itself is fetched
-        // here, while the TMA load is in flight, and parked in shared memory.
-        const int bc = tile >> ltpb;
+        const int tt = wk.phys(tile), bc = tt >> wk.ltpb;
         int b, col;
         pmx_split_bc(bc, f, b, col);
-        const int row0 = (tile & tpb_mask) * G, k1 = row0 + rl;
-        const StepCtl* c = &p.ctl[b];
-        const int2 sched = *reinterpret_cast<const int2*>(&c->ntrunk);     // ntrunk, nmem
-        const int2 sched2 = *reinterpret_cast<const int2*>(&c->n_first);   // n_first, bmode
-        const int ntrunk = sched.x, bmode = f.pmd ? sched2.y : 0;
-        const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + sched2.x;
+        const int k1 = (tt & wk.tpb_mask) * G + rl;
+        const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
+        const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
+        const cpx* gtab = reinterpret_cast<const cpx*>(aux + S::PKG_BYTES);
         const int next = live(tile + gridDim.x);
-        if (f.pmd) {
-            stage_plates(plg, ntrunk < S::PLATE_CAP ? ntrunk : S::PLATE_CAP);
-            if (threadIdx.x < 8) {
-                const double* sc_ = &c->dz_cur;  // dz_cur leff scale dzb_first dzb_last | gpf_r gpf_i gpl_r gpl_i
-                const int src = (threadIdx.x == 0) ? 0 : (threadIdx.x < 3 ? threadIdx.x + 2 : threadIdx.x + 4);
-                if (threadIdx.x < 7)
-                    (&st->dz_cur)[threadIdx.x] = sc_[src];
-                else
-                    st->db0_last = plg[ntrunk > 0 ? ntrunk - 1 : 0].db0;
-            } else if (threadIdx.x < 16) {  // entry matrix
-                const int i = threadIdx.x - 8;
-                double v = (i == 0 || i == 6) ? 1.0 : 0.0;
-                if (bmode & PMX_BM_ENTRY_R) {  // R^H: element (r,c) = conj(R(c,r))
-                    const int r = i >> 2, cc = (i >> 1) & 1, im = i & 1;
-                    v = (&plg[0].r11r)[(cc * 2 + r) * 2 + im];
-                    if (im) v = -v;
-                } else if (bmode & PMX_BM_ENTRY_C) {
-                    v = (&plg[-1].c11r)[i];
-                }
-                st->E[i] = v;
-            } else if (threadIdx.x < 24) {  // exit matrix
-                const int i = threadIdx.x - 16;
-                st->X[i] = (&plg[ntrunk - 1].r11r)[i];
-            }
-        } else if (threadIdx.x == 0) {
-            st->dz_cur = c->dz_cur;
-        }
-        pmx_fill_tw4<L, G>(gtab, row0, two_over_N);
         cpx x[8], y[8];
         PMX_T_MARK(0)
         pmx_mbar_wait(mbar, phase);
@@ -536,8 +592,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
             x[q] = *reinterpret_cast<const cpx*>(in + off);
             y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
         }
+        const int ntrunk = st->ntrunk, bmode = st->bmode;
         __syncthreads();
-        if (PF && threadIdx.x == 0 && next < total) issue(next);
+        if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(2)
@@ -576,7 +633,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                         }
                         // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
                         // independent and interleave
-                        const double db0f = splates[0].db0, db0l = st->db0_last;
+                        const double db0f = st->plates[0].db0, db0l = st->db0_last;
                         double a4[4] = {-(0.5 * (d10 + db0f) * dzb_first / lcorr), -(0.5 * (d14 + db0f) * dzb_first / lcorr),
                                         -(0.5 * (d10 + db0l) * dzb_last / lcorr), -(0.5 * (d14 + db0l) * dzb_last / lcorr)};
                         double m4 = fmax(fmax(fabs(a4[0]), fabs(a4[1])), fmax(fabs(a4[2]), fabs(a4[3])));
@@ -593,24 +650,30 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                         }
                     } else {
                         const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
-    #pragma unroll
+#pragma unroll
                         for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
                         if (any_full) {
                             double a[8];
-    #pragma unroll
+#pragma unroll
                             for (int q = 0; q < 8; ++q) a[q] = -0.5 * d1[q];
                             pmx_sincos8(a, e1s, e1c);
                         }
                     }
-                    for (int k0 = 0; k0 < ntrunk; k0 += S::PLATE_CAP) {
-                        if (k0 > 0) {  // more trunks than the staging area holds (one-step 'gp--' runs): next chunk
+                    for (int k0 = 0; k0 < ntrunk; k0 += PMX_PKG_PLATES) {
+                        const PlateConst* pl = st->plates;
+                        if (k0 > 0) {  // more trunks than the package holds (one-step 'gp--' runs): next chunk
                             __syncthreads();
-                            stage_plates(plg + k0, (ntrunk - k0) < S::PLATE_CAP ? (ntrunk - k0) : S::PLATE_CAP);
+                            const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + st->n_first + k0;
+                            const int n = ((ntrunk - k0) < PMX_PKG_PLATES ? (ntrunk - k0) : PMX_PKG_PLATES) * PLD;
+                            const double* s_ = reinterpret_cast<const double*>(plg);
+                            double* d_ = reinterpret_cast<double*>(schunk);
+                            for (int i = threadIdx.x; i < n; i += blockDim.x) d_[i] = __ldg(&s_[i]);
                             __syncthreads();
+                            pl = schunk;
                         }
-                        const int kend = (ntrunk - k0) < S::PLATE_CAP ? ntrunk : k0 + S::PLATE_CAP;
+                        const int kend = (ntrunk - k0) < PMX_PKG_PLATES ? ntrunk : k0 + PMX_PKG_PLATES;
                         for (int k = k0; k < kend; ++k) {
-                            const PlateConst& P = splates[k - k0];
+                            const PlateConst& P = pl[k - k0];
                             const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
                             if constexpr (SC) {
                                 cpx e0, e4, g;
@@ -625,22 +688,20 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                                     g = (k == 0) ? make_double2(st->gpf_r, st->gpf_i) : make_double2(st->gpl_r, st->gpl_i);
                                 }
                                 const cpx g2 = cmul(g, g);
-                                {
-                                    const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
-                                    const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
-                                    x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
-                                    x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
-                                    x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
-                                    x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
-                                    x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
-                                    x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
-                                    x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
-                                    x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
-                                }
+                                const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
+                                const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
+                                x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
+                                x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
+                                x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
+                                x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
+                                x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
+                                x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
+                                x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
+                                x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
                             } else {
                                 if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
                                     const cpx h0 = make_double2(P.h0r, P.h0i);
-    #pragma unroll
+#pragma unroll
                                     for (int q = 0; q < 8; ++q) {
                                         const cpx e = cmul(make_double2(e1c[q], e1s[q]), h0);
                                         x[q] = cmul(x[q], e);
@@ -648,10 +709,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                                     }
                                 } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
                                     double a[8], sn[8], cs[8];
-    #pragma unroll
+#pragma unroll
                                     for (int q = 0; q < 8; ++q) a[q] = -(0.5 * (d1[q] + P.db0) * dzb / lcorr);
                                     pmx_sincos8(a, sn, cs);
-    #pragma unroll
+#pragma unroll
                                     for (int q = 0; q < 8; ++q) {
                                         const cpx e = make_double2(cs[q], sn[q]);
                                         x[q] = cmul(x[q], e);
@@ -668,7 +729,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                     double a[8], sn[8], cs[8];
                     if constexpr (SC) {  // betat regenerated per bin (:355-356)
                         const double b1 = f.beta1[col], b2 = f.beta2[col];
-    #pragma unroll
+#pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
                             const double w = __dmul_rn(f.w0, fn);
@@ -679,11 +740,11 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                         }
                     } else {
                         const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
-    #pragma unroll
+#pragma unroll
                         for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
                     }
                     pmx_sincos8(a, sn, cs);
-    #pragma unroll
+#pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const cpx e = make_double2(cs[q], sn[q]);
                         x[q] = cmul(x[q], e);
@@ -691,7 +752,6 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                     }
                 }
             }
-
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 x[q] = cconj(x[q]);
@@ -700,8 +760,8 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
             PMX_T_MARK(4)
         }
         PMX_T_MARK(5)
-        if (!PF && threadIdx.x == 0 && next < total) issue(next);
-        // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T, from the tile's two-level table
+        if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+        // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T, from the row's two-level table
         {
             const cpx* tb = gtab + rl * W::PER;
             const cpx wl = tb[t & (W::NLO - 1)];
@@ -713,79 +773,96 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
             }
         }
         tile = next;
-        __syncthreads();  // staging areas free for the next tile
+        ++it;
+        __syncthreads();  // everyone is done with this tile's auxiliary buffer and plate chunk
         PMX_T_MARK(6)
     }
     PMX_T_FLUSH(1)
 }
 
 // ---------------------------------------------------------------------------
-// pass C: like pass A, inverse transform + attenuation + max reduction + step control.  The running
-// maximum stays in registers across the tiles a CTA handles for one realization-column and is
-// published (one atomicMax per CTA) when the CTA moves on to another one.
+// pass C: like pass A, inverse transform + attenuation + max reduction.  The running maximum stays in
+// registers across the tiles a CTA handles for one realization-column and is published (one atomicMax
+// per CTA) when the CTA moves on to another one.
 template <int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
-    using S = PassSmem<L, G, PF>;
+    using S = PassSmem<L, G, PF, 2>;
     constexpr int T = L / 8, PITCH = G * 32, MASK = PITCH / 16 - 1;
-    extern __shared__ unsigned char smraw[];
-    unsigned char* sm = pmx_align1024(smraw);
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;
     cpx* work = reinterpret_cast<cpx*>(sm + S::WORK_OFF);
-    double* sred = reinterpret_cast<double*>(sm + S::RED_OFF);  // [0] = scale of the tile; [1..] reduction scratch
+    void* sred = sm + S::RED_OFF;
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
+    unsigned char* aux0 = sm + S::AUX_OFF;
+    unsigned char* sdone = sm + S::LIVE_OFF;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
-    const int ltpb = p.log2N2 - pmx_ilog2(G), tpb_mask = (1 << ltpb) - 1, total = (p.batch * f.nfc) << ltpb;
+    PmxWalk wk;
+    wk.ltpb = p.log2N2 - pmx_ilog2(G);
+    wk.tpb_mask = (1 << wk.ltpb) - 1;
+    wk.total = (p.batch * f.nfc) << wk.ltpb;
+    wk.reverse = p.reverse;
+    const int total = wk.total;
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
 
     auto live = [&](int tl) {
         while (tl < total) {
             int b_, col_;
-            pmx_split_bc(tl >> ltpb, f, b_, col_);
-            if (p.ctl[b_].state < PMX_ST_DONE) break;
+            pmx_split_bc(wk.phys(tl) >> wk.ltpb, f, b_, col_);
+            if (!pmx_is_done(sdone, p, b_)) break;
             tl += gridDim.x;
         }
         return tl;
     };
-    auto issue = [&](int tl) {
+    auto issue = [&](int tl, int buf) {
         pmx_fence_proxy_async();
-        pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
-        const int bc = tl >> ltpb, c0 = (tl & tpb_mask) * G;
+        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
         for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
+        int b_, col_;
+        pmx_split_bc(bc, f, b_, col_);
+        pmx_bulk_load(aux0 + buf * S::AUX_BYTES, &p.pkg[b_], S::PKG_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
         pmx_fence_mbar_init();
     }
     pmx_load_stage_tw<L>(stw, p.tw_stage);
+    pmx_cache_live(sdone, p);
     __syncthreads();
-    int tile = live(blockIdx.x);
-    if (threadIdx.x == 0 && tile < total) issue(tile);
+    int tile = live(blockIdx.x), it = 0;
+    if (threadIdx.x == 0 && tile < total) issue(tile, 0);
     uint32_t phase = 0;
     unsigned long long vmax = 0ull;  // running max of this thread for the current realization-column
+    PMX_T_DECL
     while (tile < total) {
-        const int bc = tile >> ltpb, c0 = (tile & tpb_mask) * G;
+        const int tt = wk.phys(tile), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
-        StepCtl* c = &p.ctl[b];
+        const StepPkg* st = reinterpret_cast<const StepPkg*>(aux0 + (it & 1) * S::AUX_BYTES);
         const int next = live(tile + gridDim.x);
-        if (threadIdx.x == 0) sred[0] = c->scale;
         cpx x[8], y[8];
+        PMX_T_MARK(0)
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
+        PMX_T_MARK(1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
             x[q] = cconj(*reinterpret_cast<const cpx*>(in + off));   // inverse transform = conj o forward o conj
             y[q] = cconj(*reinterpret_cast<const cpx*>(in + (off ^ 16u)));
         }
+        const double sc = st->scale, nsc = -sc;
         if (threadIdx.x == 0) pmx_tma_wait_read();
         __syncthreads();
-        if (PF && threadIdx.x == 0 && next < total) issue(next);
+        if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+        PMX_T_MARK(2)
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
+        PMX_T_MARK(3)
         CtaFFT<L>::run(x, y, sx, sy, t, stw);
-        const double sc = sred[0], nsc = -sc;
+        PMX_T_MARK(4)
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -797,6 +874,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             *reinterpret_cast<cpx*>(outb + off) = x[q];
             *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = y[q];
         }
+        PMX_T_MARK(5)
         pmx_fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -804,14 +882,17 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             pmx_tma_commit();
             if (!PF && next < total) {
                 pmx_tma_wait_read();
-                issue(next);
+                issue(next, (it + 1) & 1);
             }
         }
-        if (next >= total || (next >> ltpb) != bc) {  // moving on: publish the maximum (pmx_k_ctl consumes it)
-            pmx_block_max(vmax, sred + 1, c, col);
+        if (next >= total || (wk.phys(next) >> wk.ltpb) != bc) {  // moving on: publish the maximum (pmx_k_ctl consumes it)
+            pmx_block_max(vmax, sred, &p.ctl[b], col);
             vmax = 0ull;
         }
         tile = next;
+        ++it;
+        PMX_T_MARK(6)
     }
+    PMX_T_FLUSH(2)
     if (threadIdx.x == 0) pmx_tma_wait_read();
 }

@@ -12,6 +12,7 @@ struct PmxLaunchTable {
     int threadsAC, threadsB;
     size_t smemAC, smemB;
     int tw_total;  // cpx entries of the stage-twiddle table for this L
+    int tw4_lo_bits, tw4_per;  // four-step twiddle row layout (PmxTw4<L>)
     // opt in to the dynamic shared memory, report resident CTAs per SM of each kernel
     cudaError_t (*setup)(int* ctasA, int* ctasB, int* ctasC);
     // grid_x persistent CTAs

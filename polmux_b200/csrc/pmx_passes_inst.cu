@@ -28,8 +28,9 @@ constexpr bool PFB = (GB * L <= 512);
 #else
 constexpr bool PFB = (PMX_PFB != 0) && (GB * L <= 1024);
 #endif
-using SA = PassSmem<L, GAC, PFAC>;
-using SB = PassSmem<L, GB, PFB, PMX_PLATE_CAP>;
+using SA = PassSmem<L, GAC, PFAC, 0>;
+using SB = PassSmem<L, GB, PFB, 1>;
+using SC = PassSmem<L, GAC, PFAC, 2>;
 
 cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
     cudaError_t e;
@@ -45,7 +46,7 @@ cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
     if (e != cudaSuccess) return e;
     e = prep(pmx_k_passB<L, GB, PFB, true>, SB::TOTAL, SB::THREADS, ctasB);
     if (e != cudaSuccess) return e;
-    return prep(pmx_k_passC<L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasC);
+    return prep(pmx_k_passC<L, GAC, PFAC>, SC::TOTAL, SC::THREADS, ctasC);
 }
 void passA(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
     pmx_k_passA<L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);
@@ -57,7 +58,7 @@ void passB(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, con
         pmx_k_passB<L, GB, PFB, false><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
 }
 void passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
-    pmx_k_passC<L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);
+    pmx_k_passC<L, GAC, PFAC><<<gx, SC::THREADS, SC::TOTAL, s>>>(p, f, m);
 }
 }  // namespace
 
@@ -65,4 +66,4 @@ void passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, con
 #define PMX_CAT(a, b) PMX_CAT2(a, b)
 extern const PmxLaunchTable PMX_CAT(pmx_table_, PMX_L) = {
     L, GAC, GB, PFAC ? 1 : 0, PFB ? 1 : 0, SA::THREADS, SB::THREADS, (size_t)SA::TOTAL, (size_t)SB::TOTAL,
-    pmx_tw_total(L), setup, passA, passB, passC};
+    pmx_tw_total(L), PmxTw4<L>::LO, PmxTw4<L>::PER, setup, passA, passB, passC};

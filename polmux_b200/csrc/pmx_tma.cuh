@@ -50,6 +50,13 @@ __device__ __forceinline__ void pmx_tma_load_3d(void* dst, const CUtensorMap* ma
         ::"r"(pmx_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(pmx_smem_u32(bar))
         : "memory");
 }
+// contiguous global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void pmx_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pmx_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(pmx_smem_u32(bar))
+                 : "memory");
+}
 // shared memory -> one box of a 3-D tiled tensor map (bulk async-group completion)
 __device__ __forceinline__ void pmx_tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
