@@ -69,6 +69,8 @@ struct FourStepTw {  // per-row two-level four-step twiddle table (PmxTw4<L> lay
 struct pmx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t gstream[3] = {nullptr, nullptr, nullptr};  // streams of the other realization groups (pmx_fiber_exec)
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     std::string error;
     std::map<int, StageTw> stage_tw;          // by L
     std::map<long long, FourStepTw> four_tw;  // by N
@@ -290,6 +292,11 @@ extern "C" void pmx_ctx_destroy(pmx_ctx* c) {
         cudaFree(kv.second.rows);
     }
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    for (int g = 0; g < 3; ++g) {
+        if (c->gstream[g]) cudaStreamDestroy(c->gstream[g]);
+        if (c->ev_join[g]) cudaEventDestroy(c->ev_join[g]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -889,28 +896,80 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     }
     if (!fld->has_maps) return set_err(c, PMX_ERR_INVALID, "field has no tensor maps (unsupported nfft)");
     const pmx_ctx::Occ oA = c->setup_done[p->N1], oB = c->setup_done[p->N2];
-    const int tilesAC = (p->N2 / p->tA->gAC) * batch * nfc, tilesB = (p->N1 / p->tB->gB) * batch * nfc;
-    const int gA = std::min(tilesAC, c->sm_count * oA.a), gB = std::min(tilesB, c->sm_count * oB.b),
-              gC = std::min(tilesAC, c->sm_count * oA.c);
-    int chunk = p->single_step ? 1 : 8;
-    int rev = 1;
+    // Realization groups.  The batch is split into groups that run on their own streams with full-size persistent
+    // grids: while the last CTAs of one group's pass drain (tile-count quantisation, stragglers, the launch gap and
+    // the one-CTA-per-realization step control), the other group's pass already fills the freed SM slots.
+    static const int want_groups = getenv("PMX_GROUPS") ? atoi(getenv("PMX_GROUPS")) : 2;
+    const int ngroups = c->profile ? 1 : std::max(1, std::min(std::min(want_groups, 4), batch));
+    static const double grid_mul = getenv("PMX_GRID_MUL") ? atof(getenv("PMX_GRID_MUL")) : 1.0;  // tuning knob
+    for (int g = 1; g < ngroups; ++g)
+        if (!c->gstream[g - 1]) {
+            CK(c, cudaStreamCreateWithFlags(&c->gstream[g - 1], cudaStreamNonBlocking));
+            CK(c, cudaEventCreateWithFlags(&c->ev_join[g - 1], cudaEventDisableTiming));
+            if (!c->ev_fork) CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        }
+    struct Grp {
+        cudaStream_t st;
+        PassParams pA, pB, pc;
+        FiberConst fc;
+        int nb, gA, gB, gC;
+    } grp[4];
+    static const int grid_div = getenv("PMX_GRID_DIV") ? std::max(1, atoi(getenv("PMX_GRID_DIV"))) : 1;  // tuning knob
+    const size_t N = (size_t)p->d.nfft;
+    for (int g = 0; g < ngroups; ++g) {
+        Grp& G = grp[g];
+        const int b0 = (int)((long long)g * batch / ngroups);
+        G.nb = (int)((long long)(g + 1) * batch / ngroups) - b0;
+        G.st = g == 0 ? c->stream : c->gstream[g - 1];
+        G.fc = p->fc;
+        for (PassParams* q : {&G.pA, &G.pB, &G.pc}) {
+            *q = (q == &G.pA) ? pA : (q == &G.pB ? pB : pa);
+            q->field = pa.field + (size_t)b0 * nfc * N * 2;
+            q->ctl = pa.ctl + b0;
+            q->pkg = pa.pkg + b0;
+            if (p->fc.plate_sets > 1) q->plates = pa.plates + (size_t)b0 * p->fc.nplates;
+            if (pa.trace_dz) {
+                q->trace_dz = pa.trace_dz + (size_t)b0 * p->trace_cap;
+                q->trace_ntrunk = pa.trace_ntrunk + (size_t)b0 * p->trace_cap;
+            }
+            q->batch = G.nb;
+            q->bc0 = b0 * nfc;
+        }
+        const int tilesAC = (p->N2 / p->tA->gAC) * G.nb * nfc, tilesB = (p->N1 / p->tB->gB) * G.nb * nfc;
+        G.gA = std::min(tilesAC, (int)(std::max(1, oA.a / grid_div) * c->sm_count * grid_mul));
+        G.gB = std::min(tilesB, (int)(std::max(1, oB.b / grid_div) * c->sm_count * grid_mul));
+        G.gC = std::min(tilesAC, (int)(std::max(1, oA.c / grid_div) * c->sm_count * grid_mul));
+    }
     static const bool serp = !getenv("PMX_NO_SERPENTINE");
+    int chunk = p->single_step ? 1 : 8;
+    int rev[4] = {1, 1, 1, 1};
     long total_steps = 0;
     for (;;) {
+        if (ngroups > 1) {  // the other streams start after everything queued on the first one so far
+            CK(c, cudaEventRecord(c->ev_fork, c->stream));
+            for (int g = 1; g < ngroups; ++g) CK(c, cudaStreamWaitEvent(c->gstream[g - 1], c->ev_fork, 0));
+        }
         for (int s = 0; s < chunk; ++s) {
-            // serpentine tile order: consecutive passes walk the realizations in opposite directions
-            pA.reverse = serp ? (rev ^= 1) : 0;
-            { ProfScope ps(c, 0); p->tA->passA(gA, c->stream, pA, p->fc, fld->map_cols); }
-            pB.reverse = serp ? (rev ^= 1) : 0;
-            { ProfScope ps(c, 1); p->tB->passB(gB, c->stream, pB, p->fc, fld->map_rows); }
-            pA.reverse = serp ? (rev ^= 1) : 0;
-            { ProfScope ps(c, 2); p->tA->passC(gC, c->stream, pA, p->fc, fld->map_cols); }
-            pmx_k_ctl<<<batch, 128, 0, c->stream>>>(pa, p->fc, 0);
-            c->launches += 4;
+            for (int gi = 0; gi < ngroups; ++gi) {
+                Grp& G = grp[gi];
+                // serpentine tile order: consecutive passes walk the realizations in opposite directions
+                G.pA.reverse = serp ? (rev[gi] ^= 1) : 0;
+                { ProfScope ps(c, 0); p->tA->passA(G.gA, G.st, G.pA, G.fc, fld->map_cols); }
+                G.pB.reverse = serp ? (rev[gi] ^= 1) : 0;
+                { ProfScope ps(c, 1); p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_rows); }
+                G.pA.reverse = serp ? (rev[gi] ^= 1) : 0;
+                { ProfScope ps(c, 2); p->tA->passC(G.gC, G.st, G.pA, G.fc, fld->map_cols); }
+                pmx_k_ctl<<<G.nb, 128, 0, G.st>>>(G.pc, G.fc, 0);
+                c->launches += 4;
+            }
             if (c->profile && c->ev_used > 4096) prof_collect(c);
         }
         total_steps += chunk;
         CK(c, cudaGetLastError());
+        for (int g = 1; g < ngroups; ++g) {
+            CK(c, cudaEventRecord(c->ev_join[g - 1], c->gstream[g - 1]));
+            CK(c, cudaStreamWaitEvent(c->stream, c->ev_join[g - 1], 0));
+        }
         CK(c, cudaMemcpyAsync(c->h_ctl, p->ctl, (size_t)batch * sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         bool all_done = true;

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
-        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
+        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_fence_proxy_async();
         __syncthreads();  // tile staged
         if (threadIdx.x == 0) {
-            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, bc, outb + r0 * PITCH);
+            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, p.bc0 + bc, outb + r0 * PITCH);
             pmx_tma_commit();
             if (!PF && next < total) {  // the next tile lands in this same buffer
                 pmx_tma_wait_read();
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         const int tt = wk.phys(tl), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
         for (int l0 = 0; l0 < LINES; l0 += 256)
-            pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, bc, mbar);
+            pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
-        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, bc, mbar);
+        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         pmx_bulk_load(aux0 + buf * S::AUX_BYTES, &p.pkg[b_], S::PKG_BYTES, mbar);
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, bc, outb + r0 * PITCH);
+            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, p.bc0 + bc, outb + r0 * PITCH);
             pmx_tma_commit();
             if (!PF && next < total) {
                 pmx_tma_wait_read();
