@@ -908,6 +908,8 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
             CK(c, cudaEventCreateWithFlags(&c->ev_join[g - 1], cudaEventDisableTiming));
             if (!c->ev_fork) CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         }
+    static const int stagB = getenv("PMX_STAGGER_B") ? atoi(getenv("PMX_STAGGER_B")) : 0;
+    static const int stagAC = getenv("PMX_STAGGER_AC") ? atoi(getenv("PMX_STAGGER_AC")) : 0;
     struct Grp {
         cudaStream_t st;
         PassParams pA, pB, pc;
@@ -934,6 +936,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
             }
             q->batch = G.nb;
             q->bc0 = b0 * nfc;
+            q->stagger = (q == &G.pB) ? stagB : stagAC;
         }
         const int tilesAC = (p->N2 / p->tA->gAC) * G.nb * nfc, tilesB = (p->N1 / p->tB->gB) * G.nb * nfc;
         G.gA = std::min(tilesAC, (int)(std::max(1, oA.a / grid_div) * c->sm_count * grid_mul));

@@ -105,6 +105,7 @@ struct PassParams {
     int N1, N2, log2N1, log2N2;
     int batch;
     int bc0;                // first realization-column of this launch inside the field (tensor-map coordinate offset)
+    int stagger;            // cycles by which the CTAs sharing an SM start apart (de-phases their load / exchange / math phases)
     int reverse;            // walk the tile list backwards (alternates from pass to pass: the tiles the previous
                             // pass wrote last are still in L2 when this pass reads them first)
     long long* dbg;         // optional per-CTA phase cycle counters (PMX_TIMING builds only)

@@ -317,6 +317,19 @@ __device__ __forceinline__ bool pmx_is_done(const unsigned char* sdone, const Pa
     return (p.batch <= PMX_LIVE_CAP) ? (sdone[b] != 0) : (p.pkg[b].state >= PMX_ST_DONE);
 }
 
+// CTAs that share an SM would otherwise run their phases (tile load, shared-memory exchanges, FP64 math) in
+// lockstep and queue on one resource at a time while the others idle: start them apart.  Blocks are placed
+// round-robin over the SMs, so blockIdx.x / #SM is the slot of a CTA on its SM.
+__device__ __forceinline__ void pmx_stagger(const PassParams& p) {
+    if (p.stagger > 0) {
+        unsigned nsm;
+        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        const long long d = (long long)(blockIdx.x / nsm) * p.stagger, t0 = clock64();
+        while (clock64() - t0 < d) {
+        }
+    }
+}
+
 // realization / column of a flat realization-column index
 __device__ __forceinline__ void pmx_split_bc(int bc, const FiberConst& f, int& b, int& col) {
     if (f.nfc == 1) {
@@ -401,6 +414,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;
     if (threadIdx.x == 0 && tile < total) issue(tile, 0);
+    pmx_stagger(p);
     uint32_t phase = 0;
     PMX_T_DECL
     while (tile < total) {
@@ -570,6 +584,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;
     if (threadIdx.x == 0 && tile < total) issue(tile, 0);
+    pmx_stagger(p);
     uint32_t phase = 0;
     PMX_T_DECL
     while (tile < total) {
@@ -725,7 +740,11 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                     }
                     if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
                 }
+#ifdef PMX_EXP_NO_COMMON
+                if (false) {
+#else
                 if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
+#endif
                     double a[8], sn[8], cs[8];
                     if constexpr (SC) {  // betat regenerated per bin (:355-356)
                         const double b1 = f.beta1[col], b2 = f.beta2[col];
@@ -833,6 +852,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;
     if (threadIdx.x == 0 && tile < total) issue(tile, 0);
+    pmx_stagger(p);
     uint32_t phase = 0;
     unsigned long long vmax = 0ull;  // running max of this thread for the current realization-column
     PMX_T_DECL
