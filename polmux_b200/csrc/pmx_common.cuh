@@ -129,16 +129,18 @@ __device__ __forceinline__ void st_sa(cpx* p, cpx x, cpx y) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y) : "memory");
 }
 
-// Branch-free sin/cos for |x| < 105615 (three-term Cody-Waite reduction by pi/2 with FMAs, then
-// the fdlibm kernel polynomials on [-pi/4, pi/4]; <= ~1 ulp like the libm calls the reference
-// makes in fastexp.c:41-42).  Being branch-free lets the compiler interleave the eight
-// evaluations a thread needs.  Larger arguments take the library's Payne-Hanek path.
+// Branch-free sin/cos: three-term Cody-Waite reduction by pi/2 carried out with FMAs (each product q*c is
+// exact inside the FMA, so the reduction stays accurate far beyond the |x| < 105615 range of the library's own
+// fast path: the absolute error of the reduced argument is about 2^-53 * |x| * 6e-17, i.e. below one ulp of
+// the result for |x| up to ~1e9 rad and never worse than the spacing of the doubles around x), then the fdlibm
+// kernel polynomials on [-pi/4, pi/4]; <= ~1 ulp like the libm calls the reference makes in fastexp.c:41-42.
+// No slow path and no branch: the compiler interleaves the evaluations a thread needs.
 __device__ __forceinline__ void pmx_sincos_fast(double x, double* sp, double* cp) {
     const double q = rint(x * 6.3661977236758138e-01);
     double r = fma(q, -1.5707963267948966e+00, x);
     r = fma(q, -6.1232339957367574e-17, r);
     r = fma(q, -1.4973849048591698e-33, r);
-    const int n = (int)q;
+    const int n = (int)(long long)q;
     const double z = r * r;
     double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
     ps = fma(z, ps, 2.75573137070700676789e-06);
@@ -156,24 +158,10 @@ __device__ __forceinline__ void pmx_sincos_fast(double x, double* sp, double* cp
     *sp = (n & 2) ? -a : a;
     *cp = ((n + 1) & 2) ? -b : b;
 }
-__device__ __forceinline__ void pmx_sincos(double x, double* sp, double* cp) {
-    if (fabs(x) < 105615.0)
-        pmx_sincos_fast(x, sp, cp);
-    else
-        sincos(x, sp, cp);
-}
-// eight at once: one (rarely taken) branch for the whole group
+__device__ __forceinline__ void pmx_sincos(double x, double* sp, double* cp) { pmx_sincos_fast(x, sp, cp); }
 __device__ __forceinline__ void pmx_sincos8(const double (&x)[8], double (&s)[8], double (&c)[8]) {
-    double m = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) m = fmax(m, fabs(x[q]));
-    if (m < 105615.0) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pmx_sincos_fast(x[q], &s[q], &c[q]);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) sincos(x[q], &s[q], &c[q]);
-    }
+    for (int q = 0; q < 8; ++q) pmx_sincos_fast(x[q], &s[q], &c[q]);
 }
 
 // |ux|^2+|uy|^2 in the reference's order, no FMA contraction (fiber.m:694)

@@ -651,18 +651,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                         const double db0f = st->plates[0].db0, db0l = st->db0_last;
                         double a4[4] = {-(0.5 * (d10 + db0f) * dzb_first / lcorr), -(0.5 * (d14 + db0f) * dzb_first / lcorr),
                                         -(0.5 * (d10 + db0l) * dzb_last / lcorr), -(0.5 * (d14 + db0l) * dzb_last / lcorr)};
-                        double m4 = fmax(fmax(fabs(a4[0]), fabs(a4[1])), fmax(fabs(a4[2]), fabs(a4[3])));
-                        if (m4 < 105615.0) {
-                            pmx_sincos_fast(a4[0], &pf0.y, &pf0.x);
-                            pmx_sincos_fast(a4[1], &pf4.y, &pf4.x);
-                            pmx_sincos_fast(a4[2], &pl0.y, &pl0.x);
-                            pmx_sincos_fast(a4[3], &pl4.y, &pl4.x);
-                        } else {
-                            sincos(a4[0], &pf0.y, &pf0.x);
-                            sincos(a4[1], &pf4.y, &pf4.x);
-                            sincos(a4[2], &pl0.y, &pl0.x);
-                            sincos(a4[3], &pl4.y, &pl4.x);
-                        }
+                        pmx_sincos_fast(a4[0], &pf0.y, &pf0.x);
+                        pmx_sincos_fast(a4[1], &pf4.y, &pf4.x);
+                        pmx_sincos_fast(a4[2], &pl0.y, &pl0.x);
+                        pmx_sincos_fast(a4[3], &pl4.y, &pl4.x);
                     } else {
                         const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
 #pragma unroll
