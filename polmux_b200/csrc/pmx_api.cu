@@ -19,16 +19,19 @@
 // ---------------------------------------------------------------------------
 extern const PmxLaunchTable pmx_table_64, pmx_table_128, pmx_table_256, pmx_table_512, pmx_table_1024,
     pmx_table_2048, pmx_table_4096;
+extern const PmxLaunchTable pmx_table_f32_64, pmx_table_f32_128, pmx_table_f32_256, pmx_table_f32_512, pmx_table_f32_1024,
+    pmx_table_f32_2048, pmx_table_f32_4096;
 
-const PmxLaunchTable* pmx_get_table(int L) {
+const PmxLaunchTable* pmx_get_table(int L, int precision) {
+    const bool f32 = precision == PMX_F32;
     switch (L) {
-        case 64: return &pmx_table_64;
-        case 128: return &pmx_table_128;
-        case 256: return &pmx_table_256;
-        case 512: return &pmx_table_512;
-        case 1024: return &pmx_table_1024;
-        case 2048: return &pmx_table_2048;
-        case 4096: return &pmx_table_4096;
+        case 64: return f32 ? &pmx_table_f32_64 : &pmx_table_64;
+        case 128: return f32 ? &pmx_table_f32_128 : &pmx_table_128;
+        case 256: return f32 ? &pmx_table_f32_256 : &pmx_table_256;
+        case 512: return f32 ? &pmx_table_f32_512 : &pmx_table_512;
+        case 1024: return f32 ? &pmx_table_f32_1024 : &pmx_table_1024;
+        case 2048: return f32 ? &pmx_table_f32_2048 : &pmx_table_2048;
+        case 4096: return f32 ? &pmx_table_f32_4096 : &pmx_table_4096;
         default: return nullptr;
     }
 }
@@ -63,7 +66,7 @@ struct StageTw {
     cpx* dev = nullptr;
 };
 struct FourStepTw {  // per-row two-level four-step twiddle table (PmxTw4<L> layout), see pmx_k_fill_tw4
-    cpx* rows = nullptr;
+    void* rows = nullptr;
 };
 
 struct pmx_ctx {
@@ -130,7 +133,8 @@ struct pmx_devfield {
     pmx_ctx* ctx;
     int64_t nfft;
     int32_t nfc, batch, precision;
-    cpx* data;  // [batch*nfc][nfft][2]
+    cpx* data;  // [batch*nfc][nfft][2]; float2 elements behind this pointer when precision == PMX_F32
+    size_t cbytes() const { return precision == PMX_F32 ? sizeof(float2) : sizeof(double2); }
     int N1 = 0, N2 = 0;
     bool has_maps = false;
     CUtensorMap map_cols;  // passes A, C: box {gAC*4 doubles, <=256 rows, 1}
@@ -158,28 +162,35 @@ static int build_maps(pmx_ctx* c, pmx_devfield* f) {
     if (lg < 12 || lg > 24) return PMX_OK;  // not a size the SSFM kernels take; other ops still work
     f->N1 = 1 << split_log2N1(lg);
     f->N2 = 1 << (lg - split_log2N1(lg));
-    const PmxLaunchTable* tA = pmx_get_table(f->N1);
-    const PmxLaunchTable* tB = pmx_get_table(f->N2);
+    const PmxLaunchTable* tA = pmx_get_table(f->N1, f->precision);
+    const PmxLaunchTable* tB = pmx_get_table(f->N2, f->precision);
     if (!tA || !tB) return PMX_OK;
     const cuuint64_t BC = (cuuint64_t)f->batch * f->nfc, N = (cuuint64_t)f->nfft;
+    const bool f32 = f->precision == PMX_F32;
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const cuuint64_t SAB = f32 ? 16 : 32;  // bytes per Sa (4 reals)
     const cuuint32_t ones[3] = {1, 1, 1};
     {
         const int G = tA->gAC;
         cuuint64_t dims[3] = {(cuuint64_t)f->N2 * 4, (cuuint64_t)f->N1, BC};
-        cuuint64_t strides[2] = {(cuuint64_t)f->N2 * 32, N * 32};
+        cuuint64_t strides[2] = {(cuuint64_t)f->N2 * SAB, N * SAB};
         cuuint32_t box[3] = {(cuuint32_t)G * 4, (cuuint32_t)std::min(f->N1, 256), 1};
-        CUtensorMapSwizzle sw = G == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : (G == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
-        CUresult r = c->encode(&f->map_cols, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, f->data, dims, strides, box, ones,
+        const int pitch = G * (int)SAB;  // bytes of one box row = swizzle span (16: none)
+        CUtensorMapSwizzle sw = pitch <= 16 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                            : (pitch == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                           : (pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
+        CUresult r = c->encode(&f->map_cols, dt, 3, f->data, dims, strides, box, ones,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return set_err(c, PMX_ERR_CUDA, "cuTensorMapEncodeTiled(cols) failed: CUresult %d", (int)r);
     }
     {
-        const int lines = tB->gB * f->N2 / 4;
-        cuuint64_t dims[3] = {16, N / 4, BC};
-        cuuint64_t strides[2] = {128, N * 32};
-        cuuint32_t box[3] = {16, (cuuint32_t)std::min(lines, 256), 1};
-        CUresult r = c->encode(&f->map_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, f->data, dims, strides, box, ones,
+        const int sa_per_line = (int)(128 / SAB);  // a 128-byte line holds 4 (FP64) or 8 (FP32) Sa
+        const int lines = tB->gB * f->N2 / sa_per_line;
+        cuuint64_t dims[3] = {(cuuint64_t)(f32 ? 32 : 16), N / sa_per_line, BC};
+        cuuint64_t strides[2] = {128, N * SAB};
+        cuuint32_t box[3] = {(cuuint32_t)(f32 ? 32 : 16), (cuuint32_t)std::min(lines, 256), 1};
+        CUresult r = c->encode(&f->map_rows, dt, 3, f->data, dims, strides, box, ones,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return set_err(c, PMX_ERR_CUDA, "cuTensorMapEncodeTiled(rows) failed: CUresult %d", (int)r);
@@ -349,17 +360,26 @@ extern "C" void* pmx_ctx_stream(pmx_ctx* c) { return c ? (void*)c->stream : null
 extern "C" int64_t pmx_ctx_launch_count(const pmx_ctx* c) { return c ? c->launches : 0; }
 
 // ---------------------------------------------------------------------------
-static int get_stage_tw(pmx_ctx* c, int L, const cpx** dev) {
-    auto it = c->stage_tw.find(L);
+static int get_stage_tw(pmx_ctx* c, int L, int precision, const void** dev) {
+    const int key = L + 65536 * precision;
+    auto it = c->stage_tw.find(key);
     if (it == c->stage_tw.end()) {
         int total = pmx_tw_total(L);
         std::vector<cpx> h((size_t)(total > 0 ? total : 1));
         pmx_fill_stage_twiddles(L, h.data());
         StageTw s;
-        CK(c, cudaMalloc(&s.dev, h.size() * sizeof(cpx)));
-        CK(c, cudaMemcpyAsync(s.dev, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
-        CK(c, cudaStreamSynchronize(c->stream));
-        it = c->stage_tw.emplace(L, s).first;
+        if (precision == PMX_F32) {  // same table, rounded once from the long-double values
+            std::vector<float2> hf(h.size());
+            for (size_t i = 0; i < h.size(); ++i) hf[i] = make_float2((float)h[i].x, (float)h[i].y);
+            CK(c, cudaMalloc(&s.dev, hf.size() * sizeof(float2)));
+            CK(c, cudaMemcpyAsync(s.dev, hf.data(), hf.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+        } else {
+            CK(c, cudaMalloc(&s.dev, h.size() * sizeof(cpx)));
+            CK(c, cudaMemcpyAsync(s.dev, h.data(), h.size() * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+        }
+        it = c->stage_tw.emplace(key, s).first;
     }
     *dev = it->second.dev;
     return PMX_OK;
@@ -367,15 +387,14 @@ static int get_stage_tw(pmx_ctx* c, int L, const cpx** dev) {
 
 // W_N^(r*m) rows for a pass whose in-CTA transform has length L (table of that L gives the row layout) and
 // whose tiles are indexed by r in [0, rows): rows * per entries, built on the device once per (N, L).
-static int get_four_tw(pmx_ctx* c, long long N, const PmxLaunchTable* t, int rows, const cpx** out) {
-    const long long key = N * 8192 + t->L;
+static int get_four_tw(pmx_ctx* c, long long N, const PmxLaunchTable* t, int rows, const void** out) {
+    const long long key = (N * 8192 + t->L) * 2 + t->precision;
     auto it = c->four_tw.find(key);
     if (it == c->four_tw.end()) {
         FourStepTw tw;
         const size_t n = (size_t)rows * t->tw4_per;
-        CK(c, cudaMalloc(&tw.rows, n * sizeof(cpx)));
-        pmx_k_fill_tw4<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, c->stream>>>(tw.rows, rows, t->tw4_lo_bits,
-                                                                                           t->tw4_per, 2.0 / (double)N);
+        CK(c, cudaMalloc(&tw.rows, n * t->cpx_bytes));
+        t->fill_tw4(tw.rows, rows, 2.0 / (double)N, c->stream);
         c->launches++;
         CK(c, cudaGetLastError());
         it = c->four_tw.emplace(key, tw).first;
@@ -390,8 +409,7 @@ extern "C" int pmx_field_create(pmx_ctx* c, int64_t nfft, int32_t nfc, int32_t b
                                 pmx_devfield** out) {
     if (!c || !out) return set_err(c, PMX_ERR_INVALID, "pmx_field_create: null argument");
     *out = nullptr;
-    if (precision != PMX_F64)
-        return set_err(c, PMX_ERR_UNSUPPORTED, "precision %d: only PMX_F64 is built in this version", precision);
+    if (precision != PMX_F64 && precision != PMX_F32) return set_err(c, PMX_ERR_INVALID, "unknown precision %d", precision);
     if (nfft <= 0 || nfc <= 0 || batch <= 0) return set_err(c, PMX_ERR_INVALID, "non-positive field size");
     CK(c, cudaSetDevice(c->device));
     pmx_devfield* f = new (std::nothrow) pmx_devfield();
@@ -401,7 +419,7 @@ extern "C" int pmx_field_create(pmx_ctx* c, int64_t nfft, int32_t nfc, int32_t b
     f->nfc = nfc;
     f->batch = batch;
     f->precision = precision;
-    size_t bytes = (size_t)batch * nfc * nfft * 2 * sizeof(cpx);
+    size_t bytes = (size_t)batch * nfc * nfft * 2 * f->cbytes();
     cudaError_t e = cudaMallocAsync(&f->data, bytes, c->stream);
     if (e != cudaSuccess) {
         delete f;
@@ -426,33 +444,44 @@ extern "C" void pmx_field_destroy(pmx_devfield* f) {
 
 extern "C" void* pmx_field_device_ptr(pmx_devfield* f) { return f ? (void*)f->data : nullptr; }
 
-// planar / complex host layouts <-> interleaved (xr,xi,yr,yi)
-__global__ void pmx_k_pack_planar(cpx* dst, const double* xr, const double* xi, const double* yr,
+// planar / complex host layouts (always double) <-> interleaved (xr,xi,yr,yi) in the field's precision
+template <typename T2>
+__device__ __forceinline__ T2 pmx_mk2(double a, double b);
+template <>
+__device__ __forceinline__ double2 pmx_mk2<double2>(double a, double b) { return make_double2(a, b); }
+template <>
+__device__ __forceinline__ float2 pmx_mk2<float2>(double a, double b) { return make_float2((float)a, (float)b); }
+
+template <typename T2>
+__global__ void pmx_k_pack_planar(T2* dst, const double* xr, const double* xi, const double* yr,
                                   const double* yi, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        dst[2 * i] = make_double2(xr[i], xi ? xi[i] : 0.0);
-        dst[2 * i + 1] = make_double2(yr ? yr[i] : 0.0, yi ? yi[i] : 0.0);
+        dst[2 * i] = pmx_mk2<T2>(xr[i], xi ? xi[i] : 0.0);
+        dst[2 * i + 1] = pmx_mk2<T2>(yr ? yr[i] : 0.0, yi ? yi[i] : 0.0);
     }
 }
-__global__ void pmx_k_unpack_planar(const cpx* src, double* xr, double* xi, double* yr, double* yi, size_t n) {
+template <typename T2>
+__global__ void pmx_k_unpack_planar(const T2* src, double* xr, double* xi, double* yr, double* yi, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        cpx x = src[2 * i], y = src[2 * i + 1];
+        T2 x = src[2 * i], y = src[2 * i + 1];
         xr[i] = x.x;
         xi[i] = x.y;
         yr[i] = y.x;
         yi[i] = y.y;
     }
 }
-__global__ void pmx_k_pack_complex(cpx* dst, const cpx* x, const cpx* y, size_t n) {
+template <typename T2>
+__global__ void pmx_k_pack_complex(T2* dst, const double2* x, const double2* y, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        dst[2 * i] = x[i];
-        dst[2 * i + 1] = y ? y[i] : make_double2(0.0, 0.0);
+        dst[2 * i] = pmx_mk2<T2>(x[i].x, x[i].y);
+        dst[2 * i + 1] = y ? pmx_mk2<T2>(y[i].x, y[i].y) : pmx_mk2<T2>(0.0, 0.0);
     }
 }
-__global__ void pmx_k_unpack_complex(const cpx* src, cpx* x, cpx* y, size_t n) {
+template <typename T2>
+__global__ void pmx_k_unpack_complex(const T2* src, double2* x, double2* y, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        x[i] = src[2 * i];
-        y[i] = src[2 * i + 1];
+        x[i] = make_double2(src[2 * i].x, src[2 * i].y);
+        y[i] = make_double2(src[2 * i + 1].x, src[2 * i + 1].y);
     }
 }
 
@@ -470,7 +499,8 @@ extern "C" int pmx_field_upload(pmx_devfield* f, const pmx_field* h, int32_t b0,
     if (!h || !h->xr) return set_err(c, PMX_ERR_INVALID, "pmx_field_upload: null host field / xr");
     CK(c, cudaSetDevice(c->device));
     const size_t n = (size_t)nb * f->nfc * f->nfft;
-    cpx* dst = f->data + (size_t)b0 * f->nfc * f->nfft * 2;
+    char* dstb = (char*)f->data + (size_t)b0 * f->nfc * f->nfft * 2 * f->cbytes();
+    const bool f32 = f->precision == PMX_F32;
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
     if (h->layout == PMX_PLANAR) {
         double* stage = nullptr;
@@ -482,7 +512,10 @@ extern "C" int pmx_field_upload(pmx_devfield* f, const pmx_field* h, int32_t b0,
             if (parts[k])
                 CK(c, cudaMemcpyAsync(dparts[k], parts[k], n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         }
-        pmx_k_pack_planar<<<blocks, 256, 0, c->stream>>>(dst, dparts[0], dparts[1], dparts[2], dparts[3], n);
+        if (f32)
+            pmx_k_pack_planar<float2><<<blocks, 256, 0, c->stream>>>((float2*)dstb, dparts[0], dparts[1], dparts[2], dparts[3], n);
+        else
+            pmx_k_pack_planar<double2><<<blocks, 256, 0, c->stream>>>((double2*)dstb, dparts[0], dparts[1], dparts[2], dparts[3], n);
         c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaFreeAsync(stage, c->stream));
@@ -495,7 +528,10 @@ extern "C" int pmx_field_upload(pmx_devfield* f, const pmx_field* h, int32_t b0,
             dy = stage + n;
             CK(c, cudaMemcpyAsync(dy, h->yr, n * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
         }
-        pmx_k_pack_complex<<<blocks, 256, 0, c->stream>>>(dst, stage, dy, n);
+        if (f32)
+            pmx_k_pack_complex<float2><<<blocks, 256, 0, c->stream>>>((float2*)dstb, stage, dy, n);
+        else
+            pmx_k_pack_complex<double2><<<blocks, 256, 0, c->stream>>>((double2*)dstb, stage, dy, n);
         c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaFreeAsync(stage, c->stream));
@@ -512,13 +548,17 @@ extern "C" int pmx_field_download(pmx_devfield* f, pmx_field* h, int32_t b0, int
     if (!h || !h->xr || !h->yr) return set_err(c, PMX_ERR_INVALID, "pmx_field_download: null host arrays");
     CK(c, cudaSetDevice(c->device));
     const size_t n = (size_t)nb * f->nfc * f->nfft;
-    const cpx* src = f->data + (size_t)b0 * f->nfc * f->nfft * 2;
+    const char* srcb = (const char*)f->data + (size_t)b0 * f->nfc * f->nfft * 2 * f->cbytes();
+    const bool f32 = f->precision == PMX_F32;
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
     if (h->layout == PMX_PLANAR) {
         if (!h->xi || !h->yi) return set_err(c, PMX_ERR_INVALID, "planar download needs xr, xi, yr, yi");
         double* stage = nullptr;
         CK(c, cudaMallocAsync(&stage, 4 * n * sizeof(double), c->stream));
-        pmx_k_unpack_planar<<<blocks, 256, 0, c->stream>>>(src, stage, stage + n, stage + 2 * n, stage + 3 * n, n);
+        if (f32)
+            pmx_k_unpack_planar<float2><<<blocks, 256, 0, c->stream>>>((const float2*)srcb, stage, stage + n, stage + 2 * n, stage + 3 * n, n);
+        else
+            pmx_k_unpack_planar<double2><<<blocks, 256, 0, c->stream>>>((const double2*)srcb, stage, stage + n, stage + 2 * n, stage + 3 * n, n);
         c->launches++;
         CK(c, cudaGetLastError());
         double* parts[4] = {h->xr, h->xi, h->yr, h->yi};
@@ -528,7 +568,10 @@ extern "C" int pmx_field_download(pmx_devfield* f, pmx_field* h, int32_t b0, int
     } else if (h->layout == PMX_COMPLEX) {
         cpx* stage = nullptr;
         CK(c, cudaMallocAsync(&stage, 2 * n * sizeof(cpx), c->stream));
-        pmx_k_unpack_complex<<<blocks, 256, 0, c->stream>>>(src, stage, stage + n, n);
+        if (f32)
+            pmx_k_unpack_complex<float2><<<blocks, 256, 0, c->stream>>>((const float2*)srcb, stage, stage + n, n);
+        else
+            pmx_k_unpack_complex<double2><<<blocks, 256, 0, c->stream>>>((const double2*)srcb, stage, stage + n, n);
         c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaMemcpyAsync(h->xr, stage, n * sizeof(cpx), cudaMemcpyDeviceToHost, c->stream));
@@ -544,10 +587,10 @@ extern "C" int pmx_field_download(pmx_devfield* f, pmx_field* h, int32_t b0, int
 extern "C" int pmx_field_broadcast(pmx_devfield* dst, const pmx_devfield* src) {
     if (!dst || !src) return set_err(nullptr, PMX_ERR_INVALID, "null field");
     pmx_ctx* c = dst->ctx;
-    if (dst->nfft != src->nfft || dst->nfc != src->nfc)
-        return set_err(c, PMX_ERR_INVALID, "pmx_field_broadcast: shape mismatch");
+    if (dst->nfft != src->nfft || dst->nfc != src->nfc || dst->precision != src->precision)
+        return set_err(c, PMX_ERR_INVALID, "pmx_field_broadcast: shape or precision mismatch");
     CK(c, cudaSetDevice(c->device));
-    const size_t bytes = (size_t)src->nfc * src->nfft * 2 * sizeof(cpx);
+    const size_t bytes = (size_t)src->nfc * src->nfft * 2 * src->cbytes();
     for (int b = 0; b < dst->batch; ++b)
         CK(c, cudaMemcpyAsync((char*)dst->data + (size_t)b * bytes, src->data, bytes, cudaMemcpyDeviceToDevice, c->stream));
     return PMX_OK;
@@ -653,8 +696,8 @@ extern "C" void pmx_plan_destroy(pmx_plan* p) {
 extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** out) {
     if (!c || !d || !out) return set_err(c, PMX_ERR_INVALID, "pmx_plan_create: null argument");
     *out = nullptr;
-    if (d->precision != PMX_F64)
-        return set_err(c, PMX_ERR_UNSUPPORTED, "precision %d: only PMX_F64 is built in this version", d->precision);
+    if (d->precision != PMX_F64 && d->precision != PMX_F32)
+        return set_err(c, PMX_ERR_INVALID, "unknown precision %d", d->precision);
     const int lg = ilog2_exact(d->nfft);
     if (lg < 12 || lg > 24)
         return set_err(c, PMX_ERR_UNSUPPORTED, "nfft=%lld: this build handles powers of two from 2^12 to 2^24",
@@ -688,14 +731,14 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     p->log2N2 = lg - p->log2N1;
     p->N1 = 1 << p->log2N1;
     p->N2 = 1 << p->log2N2;
-    p->tA = pmx_get_table(p->N1);
-    p->tB = pmx_get_table(p->N2);
+    p->tA = pmx_get_table(p->N1, d->precision);
+    p->tB = pmx_get_table(p->N2, d->precision);
     if (!p->tA || !p->tB) {
         delete p;
         return set_err(c, PMX_ERR_UNSUPPORTED, "no kernel built for FFT factors %d x %d", 1 << (lg / 2), 1 << (lg - lg / 2));
     }
     for (const PmxLaunchTable* t : {p->tA, p->tB}) {
-        if (!c->setup_done.count(t->L)) {
+        if (!c->setup_done.count(t->L + 65536 * t->precision)) {
             pmx_ctx::Occ o;
             cudaError_t e = t->setup(&o.a, &o.b, &o.c);
             if (e != cudaSuccess || o.a < 1 || o.b < 1 || o.c < 1) {
@@ -703,7 +746,7 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
                 return set_err(c, PMX_ERR_CUDA, "kernel setup (L=%d) failed: %s (resident CTAs %d/%d/%d)", t->L,
                                cudaGetErrorString(e), o.a, o.b, o.c);
             }
-            c->setup_done[t->L] = o;
+            c->setup_done[t->L + 65536 * t->precision] = o;
             if (getenv("PMX_VERBOSE"))
                 fprintf(stderr, "[pmx] L=%d: resident CTAs/SM passA %d passB %d passC %d (smem %zu / %zu B)\n", t->L, o.a, o.b, o.c,
                         t->smemAC, t->smemB);
@@ -824,6 +867,8 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     if (!p || !fld) return set_err(nullptr, PMX_ERR_INVALID, "pmx_fiber_exec: null argument");
     pmx_ctx* c = p->ctx;
     if (fld->ctx != c) return set_err(c, PMX_ERR_INVALID, "field and plan belong to different contexts");
+    if (fld->precision != p->d.precision)
+        return set_err(c, PMX_ERR_INVALID, "field precision %d does not match the plan's %d", fld->precision, p->d.precision);
     if (fld->nfft != p->d.nfft || fld->nfc != p->d.nfc || fld->batch != p->d.batch)
         return set_err(c, PMX_ERR_INVALID, "field shape (%lld,%d,%d) does not match the plan (%lld,%d,%d)",
                        (long long)fld->nfft, fld->nfc, fld->batch, (long long)p->d.nfft, p->d.nfc, p->d.batch);
@@ -868,15 +913,15 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     pa.batch = batch;
     pa.dbg = g_dbg;
     pa.pkg = p->pkg;
-    const cpx *tw4A, *tw4B;
+    const void *tw4A, *tw4B;
     rc = get_four_tw(c, p->d.nfft, p->tA, p->N2, &tw4A);  // pass A: one row per column n2, W_N^(n2*k1), k1 < N1
     if (rc) return rc;
     rc = get_four_tw(c, p->d.nfft, p->tB, p->N1, &tw4B);  // pass B: one row per k1, W_N^(k1*n2), n2 < N2
     if (rc) return rc;
-    const cpx *twA, *twB;
-    rc = get_stage_tw(c, p->N1, &twA);
+    const void *twA, *twB;
+    rc = get_stage_tw(c, p->N1, p->d.precision, &twA);
     if (rc) return rc;
-    rc = get_stage_tw(c, p->N2, &twB);
+    rc = get_stage_tw(c, p->N2, p->d.precision, &twB);
     if (rc) return rc;
     PassParams pA = pa, pB = pa;
     pA.tw_stage = twA;
@@ -889,13 +934,13 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     {
         dim3 g(148 * 2, batch * nfc);
         ProfScope ps(c, 3);
-        pmx_k_init<<<g, 256, 256, c->stream>>>(pa, p->fc);
+        p->tA->init_max(g, c->stream, pa, p->fc);
         pmx_k_ctl<<<batch, 128, 0, c->stream>>>(pa, p->fc, 1);
         c->launches += 2;
         CK(c, cudaGetLastError());
     }
     if (!fld->has_maps) return set_err(c, PMX_ERR_INVALID, "field has no tensor maps (unsupported nfft)");
-    const pmx_ctx::Occ oA = c->setup_done[p->N1], oB = c->setup_done[p->N2];
+    const pmx_ctx::Occ oA = c->setup_done[p->N1 + 65536 * p->d.precision], oB = c->setup_done[p->N2 + 65536 * p->d.precision];
     // Realization groups.  The batch is split into groups that run on their own streams with full-size persistent
     // grids: while the last CTAs of one group's pass drain (tile-count quantisation, stragglers, the launch gap and
     // the one-CTA-per-realization step control), the other group's pass already fills the freed SM slots.
@@ -926,7 +971,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
         G.fc = p->fc;
         for (PassParams* q : {&G.pA, &G.pB, &G.pc}) {
             *q = (q == &G.pA) ? pA : (q == &G.pB ? pB : pa);
-            q->field = pa.field + (size_t)b0 * nfc * N * 2;
+            q->field = (char*)pa.field + (size_t)b0 * nfc * N * 2 * fld->cbytes();
             q->ctl = pa.ctl + b0;
             q->pkg = pa.pkg + b0;
             if (p->fc.plate_sets > 1) q->plates = pa.plates + (size_t)b0 * p->fc.nplates;
@@ -1090,6 +1135,7 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
                                   const double* noise_host, uint64_t seed) {
     if (!c || !f) return set_err(c, PMX_ERR_INVALID, "pmx_ampliflat_exec: null argument");
     if (!(gain > 0)) return set_err(c, PMX_ERR_INVALID, "gain must be > 0");
+    if (f->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_ampliflat_exec: FP64 fields only");
     CK(c, cudaSetDevice(c->device));
     AmpParams a;
     memset(&a, 0, sizeof a);
@@ -1196,6 +1242,7 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
                               int64_t* counts_dev) {
     if (!c || !f || !sym || !counts_dev) return set_err(c, PMX_ERR_INVALID, "pmx_qpsk_count: null argument");
     if (f->nfc != 1) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_qpsk_count: single-column ('unique') fields only");
+    if (f->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_qpsk_count: FP64 fields only");
     if ((int64_t)nsymb * nt != f->nfft) return set_err(c, PMX_ERR_INVALID, "pmx_qpsk_count: nsymb*nt must equal nfft");
     CK(c, cudaSetDevice(c->device));
     uint8_t* dsym = nullptr;

@@ -1,13 +1,34 @@
 // Shared device-side types of the SSFM kernels (sm_100a).
 //
-// Field layout in HBM: one "Sa" = (xr, xi, yr, yi) = 4 doubles = 32 B, stored as
-// two consecutive double2 (X then Y).  field[((b*nfc + c)*N + n)*2 + pol].
+// Field layout in HBM: one "Sa" = (xr, xi, yr, yi) = 4 reals (32 B in FP64, 16 B in FP32), stored as
+// two consecutive complex numbers (X then Y).  field[((b*nfc + c)*N + n)*2 + pol].
 // Four-step index split: time n = n1*N2 + n2, frequency k = k1 + N1*k2.
+//
+// Precision: the kernel translation units are compiled twice, without and with -DPMX_F32.  `real`/`cpx` are
+// the field's arithmetic type in that translation unit; step control, plate constants and every phase
+// ARGUMENT stay in double in both builds (phases reach 1e3..1e5 rad: their reduction needs the 53 bits).
+// The structs shared with the host (StepCtl, StepPkg, PlateConst, FiberConst, PassParams) are the same in
+// both builds; the kernels carry the real type as a template parameter so that the two builds do not collide.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifdef PMX_F32
+typedef float real;
+typedef float2 cpx;
+#define PMX_PRECISION 1
+__host__ __device__ __forceinline__ cpx mkc(real a, real b) { return make_float2(a, b); }
+#define R_MUL(a, b) __fmul_rn(a, b)
+#define R_ADD(a, b) __fadd_rn(a, b)
+#else
+typedef double real;
 typedef double2 cpx;
+#define PMX_PRECISION 0
+__host__ __device__ __forceinline__ cpx mkc(real a, real b) { return make_double2(a, b); }
+#define R_MUL(a, b) __dmul_rn(a, b)
+#define R_ADD(a, b) __dadd_rn(a, b)
+#endif
+#define PMX_SA_BYTES (4 * (int)sizeof(real))
 
 #define PMX_MAX_NFC 16
 
@@ -92,14 +113,14 @@ struct FiberConst {
 };
 
 struct PassParams {
-    cpx* field;             // [batch*nfc][N][2]
+    void* field;            // cpx [batch*nfc][N][2] in the precision of the launch
     StepCtl* ctl;           // [batch]
-    const cpx* tw_stage;    // in-CTA FFT stage twiddles for this L
+    const void* tw_stage;   // cpx: in-CTA FFT stage twiddles for this L
     const double* betat_p;  // [nfc][N1][N2] permuted so that bin k1 + N1*k2 sits at k1*N2 + k2
     const double* db1_p;    // same layout
     const PlateConst* plates;  // [plate_sets][nplates]
     StepPkg* pkg;           // [batch]
-    const cpx* tw4;         // four-step twiddle rows for this pass: [rows][PmxTw4<L>::PER], see pmx_kernels.cuh
+    const void* tw4;        // cpx: four-step twiddle rows for this pass: [rows][PmxTw4<L>::PER], see pmx_kernels.cuh
     double* trace_dz;       // [batch][trace_cap] or null
     int* trace_ntrunk;
     int N1, N2, log2N1, log2N2;
@@ -111,22 +132,51 @@ struct PassParams {
     long long* dbg;         // optional per-CTA phase cycle counters (PMX_TIMING builds only)
 };
 
-__device__ __forceinline__ cpx cmul(cpx a, cpx b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) { return mkc(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ cpx cmulc(cpx a, cpx b) {  // a * conj(b)
-    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+    return mkc(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
-__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ cpx cscale(cpx a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return mkc(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return mkc(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cpx cscale(cpx a, real s) { return mkc(a.x * s, a.y * s); }
+__device__ __forceinline__ cpx cconj(cpx a) { return mkc(a.x, -a.y); }
 
-// One Sa (both polarizations, 32 B) per 256-bit global access (LDG.E.256 / STG.E.256 on sm_100a).
+// One Sa (both polarizations) per vector global access: 256-bit in FP64 (LDG.E.256 / STG.E.256 on sm_100a),
+// 128-bit in FP32.
+#ifdef PMX_F32
+__device__ __forceinline__ void ld_sa(const cpx* p, cpx& x, cpx& y) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    x = make_float2(v.x, v.y);
+    y = make_float2(v.z, v.w);
+}
+__device__ __forceinline__ void st_sa(cpx* p, cpx x, cpx y) { *reinterpret_cast<float4*>(p) = make_float4(x.x, x.y, y.x, y.y); }
+#else
 __device__ __forceinline__ void ld_sa(const cpx* p, cpx& x, cpx& y) {
     asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x.x), "=d"(x.y), "=d"(y.x), "=d"(y.y) : "l"(p));
 }
 __device__ __forceinline__ void st_sa(cpx* p, cpx x, cpx y) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y) : "memory");
+}
+#endif
+// One Sa of a landed / staged tile in shared memory at (swizzled) byte offset `off`.  FP64: X at off, Y at
+// off ^ 16 (two 128-bit accesses); FP32: both in one 128-bit access.
+__device__ __forceinline__ void lds_sa(const unsigned char* base, uint32_t off, cpx& x, cpx& y) {
+#ifdef PMX_F32
+    const float4 v = *reinterpret_cast<const float4*>(base + off);
+    x = make_float2(v.x, v.y);
+    y = make_float2(v.z, v.w);
+#else
+    x = *reinterpret_cast<const cpx*>(base + off);
+    y = *reinterpret_cast<const cpx*>(base + (off ^ 16u));
+#endif
+}
+__device__ __forceinline__ void sts_sa(unsigned char* base, uint32_t off, cpx x, cpx y) {
+#ifdef PMX_F32
+    *reinterpret_cast<float4*>(base + off) = make_float4(x.x, x.y, y.x, y.y);
+#else
+    *reinterpret_cast<cpx*>(base + off) = x;
+    *reinterpret_cast<cpx*>(base + (off ^ 16u)) = y;
+#endif
 }
 
 // Branch-free sin/cos: three-term Cody-Waite reduction by pi/2 carried out with FMAs (each product q*c is
@@ -164,10 +214,52 @@ __device__ __forceinline__ void pmx_sincos8(const double (&x)[8], double (&s)[8]
     for (int q = 0; q < 8; ++q) pmx_sincos_fast(x[q], &s[q], &c[q]);
 }
 
+// exp(i*a) in the field's precision for a phase argument given in double
+#ifdef PMX_F32
+__device__ __forceinline__ cpx pmx_cis(double a) {
+    const double q = rint(a * 6.3661977236758138e-01);  // the reduction needs the double: |a| reaches 1e5 rad
+    double r = fma(q, -1.5707963267948966e+00, a);
+    r = fma(q, -6.1232339957367574e-17, r);
+    const int n = (int)(long long)q;
+    const float rf = (float)r, z = rf * rf;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(z, ps, -1.6666654611e-1f);
+    const float sn = fmaf(z * rf, ps, rf);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(z, pc, 4.166664568298827e-2f);
+    const float cs = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+    const float u = (n & 1) ? cs : sn, v = (n & 1) ? sn : cs;
+    return make_float2(((n + 1) & 2) ? -v : v, (n & 2) ? -u : u);
+}
+// ... and for an argument already in the field's precision (nonlinear phase rotation: small angles)
+__device__ __forceinline__ cpx pmx_cis_r(float a) {
+    const float q = rintf(a * 6.3661977e-01f);
+    float rf = fmaf(q, -1.5707963705062866e+00f, a);
+    rf = fmaf(q, 4.3711388286737929e-08f, rf);
+    const int n = (int)q;
+    const float z = rf * rf;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(z, ps, -1.6666654611e-1f);
+    const float sn = fmaf(z * rf, ps, rf);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(z, pc, 4.166664568298827e-2f);
+    const float cs = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+    const float u = (n & 1) ? cs : sn, v = (n & 1) ? sn : cs;
+    return make_float2(((n + 1) & 2) ? -v : v, (n & 2) ? -u : u);
+}
+#else
+__device__ __forceinline__ cpx pmx_cis(double a) {
+    cpx e;
+    pmx_sincos_fast(a, &e.y, &e.x);
+    return e;
+}
+__device__ __forceinline__ cpx pmx_cis_r(double a) { return pmx_cis(a); }
+#endif
+
 // |ux|^2+|uy|^2 in the reference's order, no FMA contraction (fiber.m:694)
-__device__ __forceinline__ double power_ref(cpx x, cpx y) {
-    double p = __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y));
-    p = __dadd_rn(p, __dmul_rn(y.x, y.x));
-    p = __dadd_rn(p, __dmul_rn(y.y, y.y));
+__device__ __forceinline__ real power_ref(cpx x, cpx y) {
+    real p = R_ADD(R_MUL(x.x, x.x), R_MUL(x.y, x.y));
+    p = R_ADD(p, R_MUL(y.x, y.x));
+    p = R_ADD(p, R_MUL(y.y, y.y));
     return p;
 }

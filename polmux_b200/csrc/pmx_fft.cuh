@@ -19,7 +19,7 @@
 #pragma once
 #include "pmx_common.cuh"
 
-#define PMX_SQRT1_2 0.70710678118654752440
+#define PMX_SQRT1_2 ((real)0.70710678118654752440)
 
 __host__ __device__ constexpr int pmx_ilog2(int v) { return v <= 1 ? 0 : 1 + pmx_ilog2(v >> 1); }
 __host__ __device__ constexpr int pmx_sw(int i) { return i ^ ((i >> 3) & 7); }
@@ -43,7 +43,7 @@ __host__ __device__ constexpr int pmx_tw_total(int L) { return pmx_tw_offset(L, 
 
 template <bool INV>
 __device__ __forceinline__ cpx mul_mj(cpx a) {  // forward: *(-i); inverse: *(+i)
-    return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+    return INV ? mkc(-a.y, a.x) : mkc(a.y, -a.x);
 }
 
 template <bool INV>
@@ -71,13 +71,13 @@ __device__ __forceinline__ void dft8(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4
     cpx o0 = a1;
     cpx o1, o2, o3;
     if (!INV) {
-        o1 = make_double2((a3.x + a3.y) * PMX_SQRT1_2, (a3.y - a3.x) * PMX_SQRT1_2);
-        o2 = make_double2(a5.y, -a5.x);
-        o3 = make_double2((a7.y - a7.x) * PMX_SQRT1_2, -(a7.x + a7.y) * PMX_SQRT1_2);
+        o1 = mkc((a3.x + a3.y) * PMX_SQRT1_2, (a3.y - a3.x) * PMX_SQRT1_2);
+        o2 = mkc(a5.y, -a5.x);
+        o3 = mkc((a7.y - a7.x) * PMX_SQRT1_2, -(a7.x + a7.y) * PMX_SQRT1_2);
     } else {
-        o1 = make_double2((a3.x - a3.y) * PMX_SQRT1_2, (a3.x + a3.y) * PMX_SQRT1_2);
-        o2 = make_double2(-a5.y, a5.x);
-        o3 = make_double2(-(a7.x + a7.y) * PMX_SQRT1_2, (a7.x - a7.y) * PMX_SQRT1_2);
+        o1 = mkc((a3.x - a3.y) * PMX_SQRT1_2, (a3.x + a3.y) * PMX_SQRT1_2);
+        o2 = mkc(-a5.y, a5.x);
+        o3 = mkc(-(a7.x + a7.y) * PMX_SQRT1_2, (a7.x - a7.y) * PMX_SQRT1_2);
     }
     cpx e0 = a0, e1 = a2, e2 = a4, e3 = a6;
     a0 = cadd(e0, o0);
@@ -95,7 +95,7 @@ __device__ __forceinline__ void dft8(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4
 // butterfly code serves both directions.  The radix-8 stages after the first run as a loop over
 // the stage size (one copy of the stage body; pass B calls the transform from a two-iteration loop),
 // which keeps the pass kernels within the instruction cache.
-template <int L>
+template <typename R, int L>
 struct CtaFFT {
     static constexpr int T = L / 8;
     static constexpr int R0 = pmx_stage_radix(L, 1);  // radix of the first stage (2, 4 or 8), no twiddles
@@ -172,4 +172,3 @@ struct CtaFFT {
     }
 };
 
-__device__ __forceinline__ cpx cconj(cpx a) { return make_double2(a.x, -a.y); }

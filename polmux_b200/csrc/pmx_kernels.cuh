@@ -221,7 +221,7 @@ static __global__ void __launch_bounds__(256) pmx_k_init(PassParams p, FiberCons
     extern __shared__ cpx smem[];
     const int bc = blockIdx.y, b = bc / f.nfc, col = bc % f.nfc;
     const size_t N = (size_t)p.N1 * p.N2;
-    const cpx* fld = p.field + (size_t)bc * N * 2;
+    const cpx* fld = reinterpret_cast<const cpx*>(p.field) + (size_t)bc * N * 2;
     unsigned long long vmax = 0ull;
     for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
         cpx x, y;
@@ -264,14 +264,14 @@ template <int L, int G, bool PF, int KIND>
 struct PassSmem {
     static constexpr int T = L / 8;
     static constexpr int THREADS = G * T;
-    static constexpr int TILE_BYTES = G * L * 32;
-    static constexpr int WORK_BYTES = G * PmxSmem<L, G>::STRIDE * 16;
+    static constexpr int TILE_BYTES = G * L * PMX_SA_BYTES;
+    static constexpr int WORK_BYTES = G * PmxSmem<L, G>::STRIDE * (int)sizeof(cpx);
     static constexpr int WORK_OFF = PF ? ((TILE_BYTES + 1023) / 1024) * 1024 : 0;
     static constexpr int TW_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;   // stage twiddles
     static constexpr int PKG_BYTES = (KIND == 1) ? (int)sizeof(StepPkg) : PMX_PKG_HEAD;
-    static constexpr int TAB_BYTES = (KIND == 2) ? 0 : G * PmxTw4<L>::PER * 16;
+    static constexpr int TAB_BYTES = (KIND == 2) ? 0 : ((G * PmxTw4<L>::PER * (int)sizeof(cpx) + 15) / 16) * 16;
     static constexpr int AUX_BYTES = PKG_BYTES + TAB_BYTES;
-    static constexpr int AUX_OFF = TW_OFF + pmx_tw_total(L) * 16;
+    static constexpr int AUX_OFF = TW_OFF + ((pmx_tw_total(L) * (int)sizeof(cpx) + 15) / 16) * 16;
     static constexpr int PLATE_OFF = AUX_OFF + 2 * AUX_BYTES;               // pass B: chunks of trunks beyond the package
     static constexpr int RED_OFF = PLATE_OFF + ((KIND == 1) ? PMX_PKG_PLATES * (int)sizeof(PlateConst) : 0);
     static constexpr int LIVE_OFF = RED_OFF + 32 * 8;
@@ -284,7 +284,8 @@ struct PassSmem {
 
 // copy the per-L stage-twiddle table into shared memory (once per persistent CTA)
 template <int L>
-__device__ __forceinline__ void pmx_load_stage_tw(cpx* dst, const cpx* __restrict__ src) {
+__device__ __forceinline__ void pmx_load_stage_tw(cpx* dst, const void* src_) {
+    const cpx* __restrict__ src = reinterpret_cast<const cpx*>(src_);
     for (int i = threadIdx.x; i < pmx_tw_total(L); i += blockDim.x) dst[i] = __ldg(&src[i]);
 }
 
@@ -295,7 +296,7 @@ __device__ __forceinline__ unsigned char* pmx_checked1024(unsigned char* p) {
 }
 
 // Per-plan four-step twiddle rows: tab[r*PER + e] = W_N^(r*m(e)), m(e) = e for e < NLO, (e-NLO) << LO above.
-static __global__ void pmx_k_fill_tw4(cpx* tab, int rows, int lo_bits, int per, double two_over_N) {
+static __global__ void pmx_k_fill_tw4(cpx* tab, int rows, int lo_bits, int per, int row_stride, double two_over_N) {
     const int nlo = 1 << lo_bits;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * per;
          i += (long long)gridDim.x * blockDim.x) {
@@ -303,7 +304,7 @@ static __global__ void pmx_k_fill_tw4(cpx* tab, int rows, int lo_bits, int per, 
         const int m = (e < nlo) ? e : ((e - nlo) << lo_bits);
         double sn, cs;
         sincospi(-(double)((long long)r * m) * two_over_N, &sn, &cs);  // exact argument: N is a power of two
-        tab[i] = make_double2(cs, sn);
+        tab[(size_t)r * row_stride + e] = mkc((real)cs, (real)sn);
     }
 }
 
@@ -351,7 +352,9 @@ __device__ __forceinline__ void pmx_split_bc(int bc, const FiberConst& f, int& b
 #define PMX_T_FLUSH(kind)
 #endif
 
-#define PMX_MINB(threads, pf) ((pf) ? ((384 / (threads)) > 0 ? (384 / (threads)) : 1) : ((512 / (threads)) > 0 ? (512 / (threads)) : 1))
+// resident-CTA target of the launch bounds: 384 (prefetching) / 512 threads per SM in FP64, 768 in FP32
+#define PMX_TBUDGET(pf) ((PMX_SA_BYTES == 32) ? ((pf) ? 384 : 512) : 768)
+#define PMX_MINB(threads, pf) ((PMX_TBUDGET(pf) / (threads)) > 0 ? (PMX_TBUDGET(pf) / (threads)) : 1)
 
 // ---------------------------------------------------------------------------
 // Tile walk shared by the three passes (persistent CTAs): tile -> (realization-column bc, group inside it),
@@ -363,12 +366,12 @@ struct PmxWalk {
 
 // ---------------------------------------------------------------------------
 // pass A: G adjacent columns per tile, thread (cl fastest, t).
-template <int L, int G, bool PF>
+template <typename R, int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passA(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 0>;
     using W = PmxTw4<L>;
-    constexpr int T = L / 8, PITCH = G * 32, MASK = PITCH / 16 - 1;
+    constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;  // PF: landing buffer at 0; !PF: WORK_OFF == 0, lands in the exchange buffer
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
         pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
-        pmx_bulk_load(a + S::PKG_BYTES, p.tw4 + (size_t)c0 * W::PER, S::TAB_BYTES, mbar);
+        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)c0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -432,9 +435,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         PMX_T_MARK(1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
-            x[q] = *reinterpret_cast<const cpx*>(in + off);
-            y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
+            lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
         }
         if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
         __syncthreads();
@@ -442,37 +443,35 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         PMX_T_MARK(2)
         // ---- nonlinear step, fiber.m:832-851
         if (f.spm) {
-            const double gamleff = __dmul_rn(f.gam[col], st->leff);
-            const double ngl = -gamleff;
-            double ph[8], sn[8], cs[8];
+            const real gamleff = (real)__dmul_rn(f.gam[col], st->leff);
+            const real ngl = -gamleff;
+            cpx e[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) ph[q] = __dmul_rn(ngl, power_ref(x[q], y[q]));
-            pmx_sincos8(ph, sn, cs);
+            for (int q = 0; q < 8; ++q) e[q] = pmx_cis_r(R_MUL(ngl, power_ref(x[q], y[q])));
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const cpx e = make_double2(cs[q], sn[q]);
-                x[q] = cmul(x[q], e);
-                y[q] = cmul(y[q], e);
+                x[q] = cmul(x[q], e[q]);
+                y[q] = cmul(y[q], e[q]);
             }
             if (!f.manakov) {  // CNLSE: rotation by gamleff*s3/3 around the third Stokes axis (:841-851)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const double s3 = 2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
-                    ph[q] = __dmul_rn(gamleff, s3) / 3.0;
+                    const real s3 = (real)2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
+                    e[q] = pmx_cis_r(R_MUL(gamleff, s3) / (real)3.0);
                 }
-                pmx_sincos8(ph, sn, cs);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const cpx ux = x[q], uy = y[q];
-                    x[q] = make_double2(cs[q] * ux.x + sn[q] * uy.x, cs[q] * ux.y + sn[q] * uy.y);
-                    y[q] = make_double2(cs[q] * uy.x - sn[q] * ux.x, cs[q] * uy.y - sn[q] * ux.y);
+                    const real cs = e[q].x, sn = e[q].y;
+                    x[q] = mkc(cs * ux.x + sn * uy.x, cs * ux.y + sn * uy.y);
+                    y[q] = mkc(cs * uy.x - sn * ux.x, cs * uy.y - sn * ux.y);
                 }
             }
         }
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
-        CtaFFT<L>::run(x, y, sx, sy, t, stw);
+        CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
         // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the column's two-level table; the tile is staged
         // (same swizzled layout as it landed) in the exchange buffer and TMA-stored
@@ -483,9 +482,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
-                const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
-                *reinterpret_cast<cpx*>(outb + off) = cmul(x[q], w);
-                *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = cmul(y[q], w);
+                sts_sa(outb, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), cmul(x[q], w), cmul(y[q], w));
             }
         }
         PMX_T_MARK(5)
@@ -510,15 +507,15 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 // ---------------------------------------------------------------------------
 // pass B: G rows per tile, thread (t fastest, rl)
 #ifdef PMX_B_CTAS   // experiment knob: resident 128-thread-equivalent CTAs targeted for pass B
-#define PMX_MINB_B(threads, pf) (((PMX_B_CTAS * 128) / (threads)) > 0 ? ((PMX_B_CTAS * 128) / (threads)) : 1)
+#define PMX_MINB_B(threads, pf) (((PMX_B_CTAS * 128 * (32 / PMX_SA_BYTES)) / (threads)) > 0 ? ((PMX_B_CTAS * 128 * (32 / PMX_SA_BYTES)) / (threads)) : 1)
 #else
 #define PMX_MINB_B(threads, pf) PMX_MINB(threads, pf)
 #endif
 
 // u <- M*u for the eight bins of a thread, M row-major (re,im) in shared memory
 __device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const double* M) {
-    const cpx m11 = make_double2(M[0], M[1]), m12 = make_double2(M[2], M[3]);
-    const cpx m21 = make_double2(M[4], M[5]), m22 = make_double2(M[6], M[7]);
+    const cpx m11 = mkc((real)M[0], (real)M[1]), m12 = mkc((real)M[2], (real)M[3]);
+    const cpx m21 = mkc((real)M[4], (real)M[5]), m22 = mkc((real)M[6], (real)M[7]);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const cpx nx = cadd(cmul(m11, x[q]), cmul(m12, y[q]));
@@ -528,7 +525,7 @@ __device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const dou
     }
 }
 
-template <int L, int G, bool PF, bool SC>
+template <typename R, int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 1>;
@@ -551,7 +548,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     const int total = wk.total;
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
     const size_t N = (size_t)p.N1 * p.N2;
-    constexpr int LINES = G * L / 4;  // 128-byte lines per tile
+    constexpr int LINES = G * L * PMX_SA_BYTES / 128;  // 128-byte lines per tile
     constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
 
     auto live = [&](int tl) {
@@ -573,7 +570,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
         pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
-        pmx_bulk_load(a + S::PKG_BYTES, p.tw4 + (size_t)row0 * W::PER, S::TAB_BYTES, mbar);
+        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)row0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -603,9 +600,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         PMX_T_MARK(1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint32_t off = pmx_swz<7>((uint32_t)((rl * L + t + q * T) * 32));
-            x[q] = *reinterpret_cast<const cpx*>(in + off);
-            y[q] = *reinterpret_cast<const cpx*>(in + (off ^ 16u));
+            lds_sa(in, pmx_swz<7>((uint32_t)((rl * L + t + q * T) * PMX_SA_BYTES)), x[q], y[q]);
         }
         const int ntrunk = st->ntrunk, bmode = st->bmode;
         __syncthreads();
@@ -617,7 +612,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         // the transform code, run twice
 #pragma unroll 1
         for (int dir = 0; dir < 2; ++dir) {
-            CtaFFT<L>::run(x, y, sx, sy, t, stw);
+            CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
             if (dir == 1) break;
             PMX_T_MARK(3)
 
@@ -635,35 +630,55 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                     if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
                     const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
                     // whole trunks share exp(-i*db1/2) per bin
-                    double d1[SC ? 1 : 8], e1s[SC ? 1 : 8], e1c[SC ? 1 : 8];
+                    double d1[SC ? 1 : 8];
+                    cpx e1[SC ? 1 : 8];
                     double d10 = 0.0, d14 = 0.0;
-                    cpx E0 = make_double2(1.0, 0.0), E4 = E0;
+                    cpx E0 = mkc((real)1.0, (real)0.0), E4 = E0;
                     cpx pf0, pf4, pl0, pl4;  // scalar mode: phases of the step's first / last trunk at the two base bins
+#ifdef PMX_F32
+                    // FP32: the whole-trunk factor exp(-i*db1/2) of a bin is the same for every whole trunk of the
+                    // step, so a float-rounded copy (or a float progression) would repeat the SAME phase error in
+                    // each of up to nplates factors.  It is kept in double; each trunk's exp(-i*(db1+db0)/2) is
+                    // formed in double and rounded once, which makes the per-trunk errors independent.
+                    double2 Ed[8];
+#endif
                     if constexpr (SC) {
                         d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
                         d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
                         if (any_full) {
-                            pmx_sincos(-0.5 * d10, &E0.y, &E0.x);
-                            pmx_sincos(-0.5 * d14, &E4.y, &E4.x);
+#ifdef PMX_F32
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;
+                                pmx_sincos_fast(-0.5 * __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn)), &Ed[q].y, &Ed[q].x);
+                            }
+#else
+                            E0 = pmx_cis(-0.5 * d10);
+                            E4 = pmx_cis(-0.5 * d14);
+#endif
                         }
                         // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
                         // independent and interleave
                         const double db0f = st->plates[0].db0, db0l = st->db0_last;
                         double a4[4] = {-(0.5 * (d10 + db0f) * dzb_first / lcorr), -(0.5 * (d14 + db0f) * dzb_first / lcorr),
                                         -(0.5 * (d10 + db0l) * dzb_last / lcorr), -(0.5 * (d14 + db0l) * dzb_last / lcorr)};
-                        pmx_sincos_fast(a4[0], &pf0.y, &pf0.x);
-                        pmx_sincos_fast(a4[1], &pf4.y, &pf4.x);
-                        pmx_sincos_fast(a4[2], &pl0.y, &pl0.x);
-                        pmx_sincos_fast(a4[3], &pl4.y, &pl4.x);
+                        pf0 = pmx_cis(a4[0]);
+                        pf4 = pmx_cis(a4[1]);
+                        pl0 = pmx_cis(a4[2]);
+                        pl4 = pmx_cis(a4[3]);
                     } else {
                         const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
                         if (any_full) {
-                            double a[8];
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) a[q] = -0.5 * d1[q];
-                            pmx_sincos8(a, e1s, e1c);
+                            for (int q = 0; q < 8; ++q) {
+#ifdef PMX_F32
+                                pmx_sincos_fast(-0.5 * d1[q], &Ed[q].y, &Ed[q].x);
+#else
+                                e1[q] = pmx_cis(-0.5 * d1[q]);
+#endif
+                            }
                         }
                     }
                     for (int k0 = 0; k0 < ntrunk; k0 += PMX_PKG_PLATES) {
@@ -684,15 +699,27 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                             const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
                             if constexpr (SC) {
                                 cpx e0, e4, g;
+#ifdef PMX_F32
+                                if (dzb == lcorr) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        const cpx e = mkc((real)(Ed[q].x * P.h0r - Ed[q].y * P.h0i), (real)(Ed[q].x * P.h0i + Ed[q].y * P.h0r));
+                                        x[q] = cmul(x[q], e);
+                                        y[q] = cmulc(y[q], e);
+                                    }
+                                    if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);
+                                    continue;
+                                }
+#endif
                                 if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
-                                    const cpx h0 = make_double2(P.h0r, P.h0i);
+                                    const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
                                     e0 = cmul(E0, h0);
                                     e4 = cmul(E4, h0);
-                                    g = make_double2(f.g1r, f.g1i);
+                                    g = mkc((real)f.g1r, (real)f.g1i);
                                 } else {  // partial trunk (first or last of the step)
                                     e0 = (k == 0) ? pf0 : pl0;
                                     e4 = (k == 0) ? pf4 : pl4;
-                                    g = (k == 0) ? make_double2(st->gpf_r, st->gpf_i) : make_double2(st->gpl_r, st->gpl_i);
+                                    g = (k == 0) ? mkc((real)st->gpf_r, (real)st->gpf_i) : mkc((real)st->gpl_r, (real)st->gpl_i);
                                 }
                                 const cpx g2 = cmul(g, g);
                                 const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
@@ -707,21 +734,22 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                                 x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
                             } else {
                                 if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
-                                    const cpx h0 = make_double2(P.h0r, P.h0i);
+                                    const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) {
-                                        const cpx e = cmul(make_double2(e1c[q], e1s[q]), h0);
+#ifdef PMX_F32
+                                        const cpx e = mkc((real)(Ed[q].x * P.h0r - Ed[q].y * P.h0i), (real)(Ed[q].x * P.h0i + Ed[q].y * P.h0r));
+                                        (void)h0;
+#else
+                                        const cpx e = cmul(e1[q], h0);
+#endif
                                         x[q] = cmul(x[q], e);
                                         y[q] = cmulc(y[q], e);
                                     }
                                 } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-                                    double a[8], sn[8], cs[8];
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) a[q] = -(0.5 * (d1[q] + P.db0) * dzb / lcorr);
-                                    pmx_sincos8(a, sn, cs);
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) {
-                                        const cpx e = make_double2(cs[q], sn[q]);
+                                        const cpx e = pmx_cis(-(0.5 * (d1[q] + P.db0) * dzb / lcorr));
                                         x[q] = cmul(x[q], e);
                                         y[q] = cmulc(y[q], e);
                                     }
@@ -737,7 +765,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
 #else
                 if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
 #endif
-                    double a[8], sn[8], cs[8];
+                    double a[8];
                     if constexpr (SC) {  // betat regenerated per bin (:355-356)
                         const double b1 = f.beta1[col], b2 = f.beta2[col];
 #pragma unroll
@@ -754,12 +782,13 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
 #pragma unroll
                         for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
                     }
-                    pmx_sincos8(a, sn, cs);
+                    cpx e[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) e[q] = pmx_cis(a[q]);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const cpx e = make_double2(cs[q], sn[q]);
-                        x[q] = cmul(x[q], e);
-                        y[q] = cmul(y[q], e);
+                        x[q] = cmul(x[q], e[q]);
+                        y[q] = cmul(y[q], e[q]);
                     }
                 }
             }
@@ -776,7 +805,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         {
             const cpx* tb = gtab + rl * W::PER;
             const cpx wl = tb[t & (W::NLO - 1)];
-            cpx* base = p.field + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
+            cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
@@ -795,11 +824,11 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
 // pass C: like pass A, inverse transform + attenuation + max reduction.  The running maximum stays in
 // registers across the tiles a CTA handles for one realization-column and is published (one atomicMax
 // per CTA) when the CTA moves on to another one.
-template <int L, int G, bool PF>
+template <typename R, int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 2>;
-    constexpr int T = L / 8, PITCH = G * 32, MASK = PITCH / 16 - 1;
+    constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;
@@ -861,11 +890,11 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         PMX_T_MARK(1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
-            x[q] = cconj(*reinterpret_cast<const cpx*>(in + off));   // inverse transform = conj o forward o conj
-            y[q] = cconj(*reinterpret_cast<const cpx*>(in + (off ^ 16u)));
+            lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
+            x[q] = cconj(x[q]);  // inverse transform = conj o forward o conj
+            y[q] = cconj(y[q]);
         }
-        const double sc = st->scale, nsc = -sc;
+        const real sc = (real)st->scale, nsc = -sc;
         if (threadIdx.x == 0) pmx_tma_wait_read();
         __syncthreads();
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
@@ -873,18 +902,16 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
-        CtaFFT<L>::run(x, y, sx, sy, t, stw);
+        CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            x[q] = make_double2(x[q].x * sc, x[q].y * nsc);
-            y[q] = make_double2(y[q].x * sc, y[q].y * nsc);
-            unsigned long long key = pmx_pow_key(power_ref(x[q], y[q]));
+            x[q] = mkc(x[q].x * sc, x[q].y * nsc);
+            y[q] = mkc(y[q].x * sc, y[q].y * nsc);
+            unsigned long long key = pmx_pow_key((double)power_ref(x[q], y[q]));
             vmax = key > vmax ? key : vmax;
-            const uint32_t off = pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * 32));
-            *reinterpret_cast<cpx*>(outb + off) = x[q];
-            *reinterpret_cast<cpx*>(outb + (off ^ 16u)) = y[q];
+            sts_sa(outb, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
         }
         PMX_T_MARK(5)
         pmx_fence_proxy_async();

@@ -13,15 +13,20 @@ struct PmxLaunchTable {
     size_t smemAC, smemB;
     int tw_total;  // cpx entries of the stage-twiddle table for this L
     int tw4_lo_bits, tw4_per;  // four-step twiddle row layout (PmxTw4<L>)
+    int precision;             // 0 = FP64, 1 = FP32 (pmx_precision)
+    int cpx_bytes;             // sizeof one complex number of that precision
     // opt in to the dynamic shared memory, report resident CTAs per SM of each kernel
     cudaError_t (*setup)(int* ctasA, int* ctasB, int* ctasC);
     // grid_x persistent CTAs
     void (*passA)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
     void (*passB)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& rows);
     void (*passC)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
+    // first max |u|^2 of a resident field (pmx_k_init) and the four-step twiddle rows, in this precision
+    void (*init_max)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
+    void (*fill_tw4)(void* tab, int rows, double two_over_N, cudaStream_t s);
 };
 
-const PmxLaunchTable* pmx_get_table(int L);  // nullptr if L is not built
+const PmxLaunchTable* pmx_get_table(int L, int precision = 0);  // nullptr if L is not built
 
 // Host: fill the stage-twiddle table of length L (layout documented in pmx_fft.cuh).
 void pmx_fill_stage_twiddles(int L, cpx* out);

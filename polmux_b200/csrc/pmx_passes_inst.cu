@@ -1,4 +1,5 @@
-// Instantiates the three pass kernels for one in-CTA FFT length (-DPMX_L=<L>).
+// Instantiates the pass kernels for one in-CTA FFT length (-DPMX_L=<L>) in one precision
+// (FP64, or FP32 with -DPMX_F32) and exports their launchers through a PmxLaunchTable.
 #include "pmx_kernels.cuh"
 #include "pmx_launch.h"
 
@@ -8,26 +9,30 @@
 
 namespace {
 constexpr int L = PMX_L;
-// Tile shapes.  Rows/columns per tile are chosen so that a tile is <= 32 KiB (1024 Sa) when
-// possible: landing buffer + exchange buffer then fit three CTAs per SM with the next tile
-// prefetched.  Longer transforms land in the exchange buffer itself (no separate prefetch).
+// Tile shapes.  Rows/columns per tile are chosen so that a tile is <= 32 KiB when possible (1024 Sa in FP64,
+// 2048 Sa in FP32: the FP32 tiles have twice the rows/columns, i.e. the same bytes and the same TMA box rows):
+// landing buffer + exchange buffer then fit three CTAs per SM with the next tile prefetched.  Longer
+// transforms land in the exchange buffer itself (no separate prefetch).
+constexpr int PSCALE = 32 / PMX_SA_BYTES;  // 1 (FP64) or 2 (FP32)
 #ifndef PMX_GAC
-constexpr int GAC = (L >= 1024) ? 1 : (L == 512 ? 2 : 4);
+constexpr int GAC = PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4));
 #else
 constexpr int GAC = PMX_GAC;
 #endif
-constexpr int GB = (L >= 1024) ? 1 : (L == 512 ? 2 : 4);
+constexpr int GB = (PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4)) * (L / 8) > 1024) ? 1 : PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4));
+constexpr int TILE_CAP = 32 * 1024;
 #ifndef PMX_PFAC
-constexpr bool PFAC = (GAC * L <= 1024);
+constexpr bool PFAC = (GAC * L * PMX_SA_BYTES <= TILE_CAP);
 #else
-constexpr bool PFAC = (PMX_PFAC != 0) && (GAC * L <= 1024);
+constexpr bool PFAC = (PMX_PFAC != 0) && (GAC * L * PMX_SA_BYTES <= TILE_CAP);
 #endif
 #ifndef PMX_PFB
 // pass B is compute-bound: it prefers a fourth resident CTA to a separate prefetch buffer
-constexpr bool PFB = (GB * L <= 512);
+constexpr bool PFB = (GB * L * PMX_SA_BYTES <= TILE_CAP / 2);
 #else
-constexpr bool PFB = (PMX_PFB != 0) && (GB * L <= 1024);
+constexpr bool PFB = (PMX_PFB != 0) && (GB * L * PMX_SA_BYTES <= TILE_CAP);
 #endif
+static_assert(GAC * (L / 8) <= 1024 && GB * (L / 8) <= 1024, "CTA too large");
 using SA = PassSmem<L, GAC, PFAC, 0>;
 using SB = PassSmem<L, GB, PFB, 1>;
 using SC = PassSmem<L, GAC, PFAC, 2>;
@@ -40,30 +45,46 @@ cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, threads, smem);
     };
-    e = prep(pmx_k_passA<L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasA);
+    e = prep(pmx_k_passA<real, L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasA);
     if (e != cudaSuccess) return e;
-    e = prep(pmx_k_passB<L, GB, PFB, false>, SB::TOTAL, SB::THREADS, ctasB);
+    e = prep(pmx_k_passB<real, L, GB, PFB, false>, SB::TOTAL, SB::THREADS, ctasB);
     if (e != cudaSuccess) return e;
-    e = prep(pmx_k_passB<L, GB, PFB, true>, SB::TOTAL, SB::THREADS, ctasB);
+    e = prep(pmx_k_passB<real, L, GB, PFB, true>, SB::TOTAL, SB::THREADS, ctasB);
     if (e != cudaSuccess) return e;
-    return prep(pmx_k_passC<L, GAC, PFAC>, SC::TOTAL, SC::THREADS, ctasC);
+    return prep(pmx_k_passC<real, L, GAC, PFAC>, SC::TOTAL, SC::THREADS, ctasC);
 }
 void passA(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
-    pmx_k_passA<L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);
+    pmx_k_passA<real, L, GAC, PFAC><<<gx, SA::THREADS, SA::TOTAL, s>>>(p, f, m);
 }
 void passB(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
     if (f.disp_scalar)
-        pmx_k_passB<L, GB, PFB, true><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
+        pmx_k_passB<real, L, GB, PFB, true><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
     else
-        pmx_k_passB<L, GB, PFB, false><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
+        pmx_k_passB<real, L, GB, PFB, false><<<gx, SB::THREADS, SB::TOTAL, s>>>(p, f, m);
 }
 void passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
-    pmx_k_passC<L, GAC, PFAC><<<gx, SC::THREADS, SC::TOTAL, s>>>(p, f, m);
+    pmx_k_passC<real, L, GAC, PFAC><<<gx, SC::THREADS, SC::TOTAL, s>>>(p, f, m);
+}
+// precision-dependent helpers that do not depend on L (every table carries them)
+void init_max(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f) {
+    pmx_k_init<<<grid, 256, 256, s>>>(p, f);
+}
+void fill_tw4(void* tab, int rows, double two_over_N, cudaStream_t s) {
+    const size_t n = (size_t)rows * PmxTw4<L>::PER;
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    pmx_k_fill_tw4<<<blocks, 256, 0, s>>>(reinterpret_cast<cpx*>(tab), rows, PmxTw4<L>::LO, PmxTw4<L>::PER, PmxTw4<L>::PER,
+                                          two_over_N);
 }
 }  // namespace
 
 #define PMX_CAT2(a, b) a##b
 #define PMX_CAT(a, b) PMX_CAT2(a, b)
-extern const PmxLaunchTable PMX_CAT(pmx_table_, PMX_L) = {
+#ifdef PMX_F32
+#define PMX_TABLE_NAME PMX_CAT(pmx_table_f32_, PMX_L)
+#else
+#define PMX_TABLE_NAME PMX_CAT(pmx_table_, PMX_L)
+#endif
+extern const PmxLaunchTable PMX_TABLE_NAME = {
     L, GAC, GB, PFAC ? 1 : 0, PFB ? 1 : 0, SA::THREADS, SB::THREADS, (size_t)SA::TOTAL, (size_t)SB::TOTAL,
-    pmx_tw_total(L), PmxTw4<L>::LO, PmxTw4<L>::PER, setup, passA, passB, passC};
+    pmx_tw_total(L), PmxTw4<L>::LO, PmxTw4<L>::PER, PMX_PRECISION, (int)sizeof(cpx),
+    setup, passA, passB, passC, init_max, fill_tw4};

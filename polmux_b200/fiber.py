@@ -201,14 +201,19 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
 DISP_MODE = 'scalar'   # 'scalar': only the field crosses PCIe; 'vector': betat/db1 are uploaded
 
 
-def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, epsilon=None, disp_mode=None):
+PRECISION = 'f64'   # arithmetic of the device path: 'f64' (default, the reference's) or 'f32' (reported separately)
+
+
+def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, epsilon=None, disp_mode=None,
+                  precision=None):
     """FiberSetup -> (pmx_fiber_desc, keep-alive dict)."""
     mode = disp_mode or DISP_MODE
+    prec = {'f64': _lib.PMX_F64, 'f32': _lib.PMX_F32}[precision or PRECISION]
     return _lib.make_desc(
         s.nfft, s.nfc, batch, s.length, s.alphalin, s.dzmaxt, s.dphimaxt, s.gam, s.fls, s.manakov, s.nplates,
         s.brf['db0'] if db0 is None else db0, s.brf['theta'] if theta is None else theta,
         s.brf['epsilon'] if epsilon is None else epsilon, s.betat, s.db1 if s.fls[1] else None,
-        plate_sets=plate_sets, scalar=s.scalars if mode == 'scalar' else None)
+        plate_sets=plate_sets, precision=prec, scalar=s.scalars if mode == 'scalar' else None)
 
 
 def apply_side_effects(s: FiberSetup):
@@ -224,8 +229,9 @@ LAST = {}  # firstdz / ncycle / schedule of the most recent fiber(), what the re
 
 
 def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional[_lib.Context] = None,
-          trace: bool = False, disp_mode: Optional[str] = None):
-    """zbrf = fiber(x, flag) -- fiber.m:1.  Propagates GSTATE.FIELDX/FIELDY in place."""
+          trace: bool = False, disp_mode: Optional[str] = None, precision: Optional[str] = None):
+    """zbrf = fiber(x, flag) -- fiber.m:1.  Propagates GSTATE.FIELDX/FIELDY in place.
+    precision: 'f64' (default) or 'f32' -- arithmetic of the device path; host arrays stay complex128."""
     G = GSTATE
     s = fiber_setup(x, flag, rng)
     if s.fls[3] and s.isv:
@@ -238,7 +244,7 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         G.FIELDY = np.zeros_like(G.FIELDX)
     apply_side_effects(s)
     ctx = ctx or _lib.default_context()
-    desc, keep = setup_to_desc(s, disp_mode=disp_mode)
+    desc, keep = setup_to_desc(s, disp_mode=disp_mode, precision=precision)
     fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]     # [1][nfc][nfft]
     scalar = not s.isv
     fy = (np.zeros_like(fx) if scalar else
