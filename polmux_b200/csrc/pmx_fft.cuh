@@ -95,6 +95,28 @@ __device__ __forceinline__ void dft8(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4
 // butterfly code serves both directions.  The radix-8 stages after the first run as a loop over
 // the stage size (one copy of the stage body; pass B calls the transform from a two-iteration loop),
 // which keeps the pass kernels within the instruction cache.
+// one point of both polarizations to / from the exchange buffers.  FP64: two arrays (sx, sy) of 16-byte complex
+// numbers; FP32: ONE array of float4 (x, y of a point side by side) at sx, so that an exchange moves 16 bytes per
+// shared-memory instruction in both precisions.
+__device__ __forceinline__ void pmx_ex_st(cpx* sx, cpx* sy, int o, cpx x, cpx y) {
+#ifdef PMX_F32
+    reinterpret_cast<float4*>(sx)[o] = make_float4(x.x, x.y, y.x, y.y);
+#else
+    sx[o] = x;
+    sy[o] = y;
+#endif
+}
+__device__ __forceinline__ void pmx_ex_ld(const cpx* sx, const cpx* sy, int o, cpx& x, cpx& y) {
+#ifdef PMX_F32
+    const float4 v = reinterpret_cast<const float4*>(sx)[o];
+    x = make_float2(v.x, v.y);
+    y = make_float2(v.z, v.w);
+#else
+    x = sx[o];
+    y = sy[o];
+#endif
+}
+
 template <typename R, int L>
 struct CtaFFT {
     static constexpr int T = L / 8;
@@ -126,9 +148,7 @@ struct CtaFFT {
             const int j0 = (t + b * T) * R0;
 #pragma unroll
             for (int r = 0; r < R0; ++r) {
-                const int o = pmx_sw(j0 + r);
-                sx[o] = x[b + NB * r];
-                sy[o] = y[b + NB * r];
+                pmx_ex_st(sx, sy, pmx_sw(j0 + r), x[b + NB * r], y[b + NB * r]);
             }
         }
         int ns = R0, two = 0;
@@ -137,9 +157,7 @@ struct CtaFFT {
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int o = pmx_sw(t + q * T);
-                x[q] = sx[o];
-                y[q] = sy[o];
+                pmx_ex_ld(sx, sy, pmx_sw(t + q * T), x[q], y[q]);
             }
             __syncthreads();  // everyone has read the exchange buffer: free for the next stage / the caller
             // ---- radix-8 stage with ns sub-transforms done
@@ -162,9 +180,7 @@ struct CtaFFT {
             const int j0 = (t - k) * 8 + k;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const int o = pmx_sw(j0 + r * ns);
-                sx[o] = x[r];
-                sy[o] = y[r];
+                pmx_ex_st(sx, sy, pmx_sw(j0 + r * ns), x[r], y[r]);
             }
             two += 3 * ns;
             ns *= 8;

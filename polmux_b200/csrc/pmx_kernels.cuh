@@ -237,7 +237,11 @@ static __global__ void __launch_bounds__(256) pmx_k_init(PassParams p, FiberCons
 template <int L, int GROUP>
 struct PmxSmem {
     static constexpr int BASE = 2 * L;
+#ifdef PMX_F32
+    static constexpr int OFF = (GROUP > 1) ? 2 : 0;  // FP32 exchanges float4 points: keep every region 16-byte aligned
+#else
     static constexpr int OFF = (GROUP > 1) ? ((8 / GROUP) > 0 ? (8 / GROUP) : 1) : 0;
+#endif
     static constexpr int STRIDE = BASE + OFF;
 };
 

@@ -12,6 +12,9 @@ from polmux_b200.fiber import fiber_setup, setup_to_desc
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 LG = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 NF = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+PREC = sys.argv[4] if len(sys.argv) > 4 else 'f64'
+PC = {'f64': _lib.PMX_F64, 'f32': _lib.PMX_F32}[PREC]
+SAB = 32 if PREC == 'f64' else 16
 nsymb, nt = 1 << (LG - 4), 16
 N = nsymb * nt
 ex, ey, _, _ = synth.pdm_qpsk(nsymb, nt, 1)
@@ -32,11 +35,11 @@ for flag, man in (('gps-', 'yes'), ('gps-', 'no'), ('g-s-', 'no'), ('--s-', 'no'
     bb = max(1, B // nfc)
     d = [mc.draw_plates(1000 + b, setup.nplates) for b in range(bb)]
     pl = [np.stack([x[i] for x in d]) for i in range(3)]
-    desc, keep = setup_to_desc(setup, batch=bb, plate_sets=bb, db0=pl[0], theta=pl[1], epsilon=pl[2])
+    desc, keep = setup_to_desc(setup, batch=bb, plate_sets=bb, db0=pl[0], theta=pl[1], epsilon=pl[2], precision=PREC)
     plan = _lib.Plan(ctx, desc, keep)
-    tx = _lib.DeviceField(ctx, N, nfc, 1)
+    tx = _lib.DeviceField(ctx, N, nfc, 1, precision=PC)
     tx.upload(G.FIELDX, G.FIELDY)
-    work = _lib.DeviceField(ctx, N, nfc, bb)
+    work = _lib.DeviceField(ctx, N, nfc, bb, precision=PC)
     for rep in range(2):
         work.broadcast_from(tx)
         ctx.profile(rep == 1)
@@ -45,5 +48,5 @@ for flag, man in (('gps-', 'yes'), ('gps-', 'no'), ('g-s-', 'no'), ('--s-', 'no'
     ctx.profile(False)
     sa = float(res.ncycle.sum()) * N * nfc
     print('%s manakov=%-3s nfc=%d ncycle=%3d  GB/s: A %6.0f  B %6.0f  C %6.0f   ps/Sa: A %.1f B %.1f C %.1f' % (
-        flag, man, nfc, int(res.ncycle[0]), *[64 * sa / (ms[i] * 1e-3) / 1e9 for i in range(3)],
+        flag, man, nfc, int(res.ncycle[0]), *[2 * SAB * sa / (ms[i] * 1e-3) / 1e9 for i in range(3)],
         *[ms[i] * 1e-3 / sa * 1e12 for i in range(3)]))
