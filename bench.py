@@ -38,6 +38,10 @@ NSYMB, NT, RATE, PAVG = 1 << 16, 16, 28.0, 2.0
 NSPAN, SPAN_KM, NPLATES, DGD = 10, 80.0, 100, 0.1
 GAIN_DB, NF_DB = 16.0, 5.0
 ALG_BYTES_PER_SA_STEP = 192.0   # 3 passes x (read + write) x 32 B   
+# dram__bytes_read.sum + dram__bytes_write.sum per Sa of a launch, from the ncu --set full capture summarised in
+# profiles/r1_ncu_v7_summary.txt (4 realizations of 2^20 Sa per launch): pass A (135.8+80.6) MB, B (136.1+93.8) MB,
+# C (134.3+80.6) MB  ->  bytes per Sa; below the 64 algorithmic bytes because part of the writes stays in L2
+NCU_DRAM_BYTES_PER_SA = {'passA': 216.4e6 / (4 << 20), 'passB': 229.9e6 / (4 << 20), 'passC': 214.9e6 / (4 << 20)}
 CPU_SAMPLE_KM = 16.0            # bounded CPU sample: first 16 km (20 plates of 800 m) of span 1
 
 
@@ -147,6 +151,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-mc', action='store_true')
+    ap.add_argument('--no-fp32', action='store_true', help='skip the separately reported FP32 leg')
     ap.add_argument('--mc-groups', type=int, default=1, help='Monte-Carlo leg: groups of `batch` realizations per rank')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -161,7 +166,7 @@ def main():
     import torch.distributed as dist
     import polmux_b200 as pmx
     from polmux_b200 import _lib, synth
-    from polmux_b200.fiber import fiber_setup
+    from polmux_b200.fiber import fiber_setup, setup_to_desc
 
     torch.cuda.set_device(local)
     if world > 1:
@@ -248,7 +253,9 @@ def main():
         alg_bytes = 64.0 * prof_sa_steps
         ach = alg_bytes / (pms[dom] * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'kernel': names[dom], 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': ach / peak, 'traffic': NCU_DRAM_BYTES_PER_SA[names[dom]] * prof_sa_steps / float(pn[dom]),
+                'traffic_source': 'ncu --set full, profiles/r1_ncu_v7_summary.txt, scaled to the Sa of a launch',
+                'peak_source': peak_src,
                 'bytes_per_launch': alg_bytes / float(pn[dom]), 'ms_per_launch': pms[dom] / float(pn[dom]),
                 'launches_timed': int(pn[dom]),
                 'pass_share_of_step': {names[i]: float(pms[i] / pms[:3].sum()) for i in range(3)},
@@ -256,6 +263,58 @@ def main():
     step_roof = {'achieved': ALG_BYTES_PER_SA_STEP * value / world, 'peak': peak, 'unit': 'GB/s',
                  'frac': ALG_BYTES_PER_SA_STEP * value / world / peak, 'bytes_per_sa_step': ALG_BYTES_PER_SA_STEP,
                  'per': 'GPU'}
+
+    # ---- FP32 mode, reported separately (north_star): same link, fields and arithmetic in float
+    fp32 = None
+    if not args.no_fp32:
+        link32 = mc.Link(ctx, setup, NSPAN, B, GAIN_DB, NF_DB, first_realization=rank * B, precision='f32')
+        tx32 = _lib.DeviceField(ctx, N, 1, 1, precision=_lib.PMX_F32)
+        tx32.upload(G.FIELDX, G.FIELDY)
+        work32 = _lib.DeviceField(ctx, N, 1, B, precision=_lib.PMX_F32)
+
+        def link32_step(step_id):
+            work32.broadcast_from(tx32)
+            return link32.run(work32, ase_seed=step_id)
+
+        for w in range(min(args.warmup, 2)):
+            link32_step(w)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        tot32 = 0
+        for k in range(args.steps):
+            tot32 += link32_step(100 + k)
+        f1.record(stream)
+        barrier()
+        t32 = torch.tensor([f0.elapsed_time(f1), float(tot32)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            a = t32.clone()
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = t32.clone()
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            t32 = torch.stack([a[0], b[1]])
+        v32 = float(t32[1]) / (float(t32[0]) * 1e-3) / 1e9
+        # accuracy of the mode on this workload: span 1 (no ASE) of realization 0, FP32 against FP64
+        one64 = _lib.DeviceField(ctx, N, 1, 1)
+        one32 = _lib.DeviceField(ctx, N, 1, 1, precision=_lib.PMX_F32)
+        one64.upload(G.FIELDX, G.FIELDY)
+        one32.upload(G.FIELDX, G.FIELDY)
+        pl0 = mc.draw_plates(mc.plate_seed(0, 0), NPLATES)
+        errs = []
+        outs = []
+        for prec, fld in (('f64', one64), ('f32', one32)):
+            d1, k1 = setup_to_desc(setup, batch=1, plate_sets=1, db0=pl0[0][None], theta=pl0[1][None], epsilon=pl0[2][None],
+                                   precision=prec)
+            pl = _lib.Plan(ctx, d1, k1)
+            pl.execute(fld)
+            outs.append(fld.download())
+            pl.close()
+        num = np.sqrt(np.sum(np.abs(outs[1][0] - outs[0][0]) ** 2) + np.sum(np.abs(outs[1][1] - outs[0][1]) ** 2))
+        den = np.sqrt(np.sum(np.abs(outs[0][0]) ** 2) + np.sum(np.abs(outs[0][1]) ** 2))
+        fp32 = {'value': v32, 'unit': 'GSa*steps/s', 'dtype': 'f32', 'ms_per_step': float(t32[0]) / max(args.steps, 1),
+                'bytes_per_sa_step': ALG_BYTES_PER_SA_STEP / 2, 'roofline_step_frac': ALG_BYTES_PER_SA_STEP / 2 * v32 / world / peak,
+                'rel_l2_vs_f64_one_span': float(num / den), 'tolerance': 1e-5}
+        del link32, work32, tx32, one64, one32
 
     # ---- Monte-Carlo BER leg (config C5, bounded): link + linear equaliser + on-GPU error counter,
     # counts all-reduced over the ranks (NCCL), ber_estimate's recursion replayed on the host
@@ -335,7 +394,7 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': workload_config(args, world), 'clocks': sampler.summary(),
                 'e2e': e2e, 'gpu_launches': int(gpu_launches), 'roofline': roof, 'roofline_step': step_roof,
-                'cpu_baseline': cpu, 'mc': mcres, 'sa_steps_per_step': total_all / max(args.steps, 1)}
+                'cpu_baseline': cpu, 'mc': mcres, 'fp32': fp32, 'sa_steps_per_step': total_all / max(args.steps, 1)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1096,7 +1096,7 @@ __device__ __forceinline__ cpx pmx_cnormal(uint32_t a, uint32_t b) {
 }
 
 struct AmpParams {
-    cpx* field;
+    void* field;       // double2 or float2 elements (field precision)
     const cpx* noise;  // [batch][2*nfc][N] or null
     double sg;         // sqrt(gain)
     double sigma[PMX_MAX_NFC];
@@ -1105,12 +1105,13 @@ struct AmpParams {
     int nfc, batch;
 };
 
+template <typename T2>  // the gain and the noise are evaluated in double in both field precisions
 __global__ void __launch_bounds__(256) pmx_k_ampliflat(AmpParams a) {
     const int bc = blockIdx.y, b = bc / a.nfc, col = bc % a.nfc;
-    cpx* fld = a.field + (size_t)bc * a.N * 2;
+    T2* fld = reinterpret_cast<T2*>(a.field) + (size_t)bc * a.N * 2;
     const double sig = a.sigma[col];
     for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += (size_t)gridDim.x * blockDim.x) {
-        cpx x = cscale(fld[2 * n], a.sg), y = cscale(fld[2 * n + 1], a.sg);
+        cpx x = make_double2(fld[2 * n].x * a.sg, fld[2 * n].y * a.sg), y = make_double2(fld[2 * n + 1].x * a.sg, fld[2 * n + 1].y * a.sg);
         if (sig != 0.0) {
             cpx nx, ny;
             if (a.noise) {
@@ -1126,8 +1127,8 @@ __global__ void __launch_bounds__(256) pmx_k_ampliflat(AmpParams a) {
             x.x += sig * nx.x; x.y += sig * nx.y;
             y.x += sig * ny.x; y.y += sig * ny.y;
         }
-        fld[2 * n] = x;
-        fld[2 * n + 1] = y;
+        fld[2 * n] = pmx_mk2<T2>(x.x, x.y);
+        fld[2 * n + 1] = pmx_mk2<T2>(y.x, y.y);
     }
 }
 
@@ -1135,7 +1136,6 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
                                   const double* noise_host, uint64_t seed) {
     if (!c || !f) return set_err(c, PMX_ERR_INVALID, "pmx_ampliflat_exec: null argument");
     if (!(gain > 0)) return set_err(c, PMX_ERR_INVALID, "gain must be > 0");
-    if (f->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_ampliflat_exec: FP64 fields only");
     CK(c, cudaSetDevice(c->device));
     AmpParams a;
     memset(&a, 0, sizeof a);
@@ -1154,7 +1154,10 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
         a.noise = dn;
     }
     dim3 g((unsigned)std::min<size_t>((a.N + 255) / 256, 148 * 8), f->batch * f->nfc);
-    pmx_k_ampliflat<<<g, 256, 0, c->stream>>>(a);
+    if (f->precision == PMX_F32)
+        pmx_k_ampliflat<float2><<<g, 256, 0, c->stream>>>(a);
+    else
+        pmx_k_ampliflat<double2><<<g, 256, 0, c->stream>>>(a);
     c->launches++;
     CK(c, cudaGetLastError());
     if (dn) CK(c, cudaFreeAsync(dn, c->stream));

@@ -45,14 +45,15 @@ class Link:
     """nspan identical spans resident on one GPU, for a batch of realizations."""
 
     def __init__(self, ctx: _lib.Context, setup: FiberSetup, nspan: int, batch: int, gain_db: float,
-                 nf_db: Optional[float], first_realization: int = 0):
+                 nf_db: Optional[float], first_realization: int = 0, precision: str = 'f64'):
         self.ctx, self.setup, self.nspan, self.batch = ctx, setup, nspan, batch
+        self.precision = precision
         self.first = first_realization
         self.gain = 10 ** (gain_db * 0.1)
         self.sigma = ase_sigma(self.gain, nf_db, setup.nfc)
         self.plates = [self._plates(k, first_realization) for k in range(nspan)]
         desc, keep = setup_to_desc(setup, batch=batch, plate_sets=batch, db0=self.plates[0][0],
-                                   theta=self.plates[0][1], epsilon=self.plates[0][2])
+                                   theta=self.plates[0][1], epsilon=self.plates[0][2], precision=precision)
         self.plan = _lib.Plan(ctx, desc, keep)
         self._inv = None
 

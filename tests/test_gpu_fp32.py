@@ -60,9 +60,26 @@ def test_fp32_sepfields_spm():
     assert err < TOL32
 
 
-def test_fp32_ampliflat_is_fp64_only():
+def test_fp32_ampliflat_gain_and_injected_noise():
+    """ampliflat on an FP32 field: u*sqrt(G) + sigma*noise (ampliflat.m:78-148) against numpy, float rounding only."""
+    from polmux_b200 import _lib
+    ctx = _lib.default_context()
+    n = 1 << 12
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((1, 1, n)) + 1j * rng.standard_normal((1, 1, n)))
+    y = (rng.standard_normal((1, 1, n)) + 1j * rng.standard_normal((1, 1, n)))
+    noise = (rng.standard_normal((1, 2, n)) + 1j * rng.standard_normal((1, 2, n)))
+    f = _lib.DeviceField(ctx, n, 1, 1, precision=_lib.PMX_F32)
+    f.upload(x, y)
+    _lib.ampliflat_exec(ctx, f, 4.0, [0.25], noise=noise)
+    gx, gy = f.download()
+    np.testing.assert_allclose(gx[0, 0], 2.0 * x[0, 0] + 0.25 * noise[0, 0], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(gy[0, 0], 2.0 * y[0, 0] + 0.25 * noise[0, 1], rtol=0, atol=2e-6)
+
+
+def test_fp32_qpsk_count_is_fp64_only():
     from polmux_b200 import _lib
     ctx = _lib.default_context()
     f = _lib.DeviceField(ctx, 1 << 12, 1, 1, precision=_lib.PMX_F32)
     with pytest.raises(_lib.PolmuxError):
-        _lib.ampliflat_exec(ctx, f, 2.0, [0.0])
+        _lib.qpsk_count(ctx, f, np.zeros((2, 256), dtype=np.uint8), 256, 16, 0)
