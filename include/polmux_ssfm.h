@@ -105,7 +105,8 @@ typedef struct pmx_fiber_desc {
     int32_t disp_mode;     /* pmx_disp_mode */
     int32_t nsymb;         /* GSTATE.NSYMB */
     int32_t nt;            /* GSTATE.NT    */
-    int32_t reserved0;
+    int32_t scalar_field;  /* 1: the scalar path of fiber.m:372-380 (FIELDY empty, no 'p' flag): Y is absent and the
+                            * 'x' flag couples the columns (nl_step, fiber.m:793-799); 0: matrix_ssfm            */
     double symbolrate;     /* GSTATE.SYMBOLRATE [GBaud] */
     double b30;            /* fiber.m:309-311 [ns^3/m] */
     double dgdrms;         /* fiber.m:269/277/284 [ns]; 0 without the 'p' flag */

@@ -113,5 +113,6 @@ if __name__ == '__main__':
     run_case('pmf_single', 256, 16, 1, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],
                                                      epsilon=[0.1, 0.5, -0.3]), 'gps-')
     run_case('scalar_gs', 256, 16, 1, 'unique', fib(length=5e4), 'g-s-', two_pol=False, want_brf=False)
-    run_case('scalar_sep3_gsx', 128, 16, 3, 'sepfields', fib(length=3e4, slope=0.057), 'g-sx', two_pol=False, want_brf=False)
-    run_case('scalar_spm_exact', 128, 16, 1, 'unique', fib(length=5e4), '--s-', two_pol=False, want_brf=False)
+    run_case('scalar_sep3_gsx', 256, 16, 3, 'sepfields', fib(length=3e4, slope=0.057), 'g-sx', two_pol=False, want_brf=False)
+    run_case('scalar_sep3_xonly', 256, 16, 3, 'sepfields', fib(length=2e4, slope=0.057), 'g--x', two_pol=False, want_brf=False)
+    run_case('scalar_spm_exact', 256, 16, 1, 'unique', fib(length=5e4), '--s-', two_pol=False, want_brf=False)

@@ -49,7 +49,7 @@ class FiberDesc(C.Structure):
         ('dzmaxt', C.c_double), ('dphimaxt', C.c_double), ('gam', _dp), ('fls', C.c_int32 * 4),
         ('nplates', C.c_int32), ('plate_sets', C.c_int32), ('db0', _dp), ('theta', _dp),
         ('epsilon', _dp), ('betat', _dp), ('db1', _dp),
-        ('disp_mode', C.c_int32), ('nsymb', C.c_int32), ('nt', C.c_int32), ('reserved0', C.c_int32),
+        ('disp_mode', C.c_int32), ('nsymb', C.c_int32), ('nt', C.c_int32), ('scalar_field', C.c_int32),
         ('symbolrate', C.c_double), ('b30', C.c_double), ('dgdrms', C.c_double), ('beta1', _dp), ('beta2', _dp),
     ]
 
@@ -178,7 +178,7 @@ def default_context(device: int = 0) -> Context:
 
 
 def make_desc(nfft, nfc, batch, length, alphalin, dzmaxt, dphimaxt, gam, fls, manakov, nplates,
-              db0, theta, epsilon, betat, db1, plate_sets=1, precision=PMX_F64, scalar=None):
+              db0, theta, epsilon, betat, db1, plate_sets=1, precision=PMX_F64, scalar=None, scalar_field=False):
     """Build a FiberDesc plus the list of arrays that must stay alive while it is used.
 
     scalar: None (vector dispersion mode: betat/db1 cross the boundary) or a dict with nsymb, nt,
@@ -194,6 +194,7 @@ def make_desc(nfft, nfc, batch, length, alphalin, dzmaxt, dphimaxt, gam, fls, ma
     d = FiberDesc()
     d.nfft, d.nfc, d.batch, d.precision = int(nfft), int(nfc), int(batch), int(precision)
     d.manakov = 1 if manakov else 0
+    d.scalar_field = 1 if scalar_field else 0   # scalar_ssfm dispatch (fiber.m:372-380)
     d.length, d.alphalin, d.dzmaxt, d.dphimaxt = float(length), float(alphalin), float(dzmaxt), float(dphimaxt)
     d.gam = _ptr(keep['gam'])
     d.fls = (C.c_int32 * 4)(*[int(v) for v in fls])

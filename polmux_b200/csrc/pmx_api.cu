@@ -716,7 +716,9 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
             return set_err(c, PMX_ERR_INVALID, "scalar dispersion mode: nsymb*nt must equal nfft");
         if (!(d->symbolrate > 0)) return set_err(c, PMX_ERR_INVALID, "scalar dispersion mode: symbolrate must be > 0");
     }
-    if (d->fls[3]) return set_err(c, PMX_ERR_XPM_VECTOR, "The CNLSE with separate fields is not yet implemented");
+    if (d->fls[3] && !d->scalar_field)  // matrix_nl_step raises at fiber.m:853-854
+        return set_err(c, PMX_ERR_XPM_VECTOR, "The CNLSE with separate fields is not yet implemented");
+    if (d->scalar_field && d->fls[1]) return set_err(c, PMX_ERR_INVALID, "scalar_field excludes the 'p' flag (fiber.m:253-254)");
     if (d->plate_sets != 1 && d->plate_sets != d->batch)
         return set_err(c, PMX_ERR_INVALID, "plate_sets must be 1 or batch");
     if (!(d->dzmaxt > 0)) return set_err(c, PMX_ERR_INVALID, "dzmaxt must be > 0");
@@ -771,6 +773,8 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     // the Jones product is skipped altogether.
     f.pmd = d->fls[1] ? 1 : 0;
     f.keep_basis = (f.pmd && (f.manakov || !f.spm)) ? 1 : 0;
+    f.scalar_field = d->scalar_field ? 1 : 0;
+    f.xpm = (d->scalar_field && d->fls[3]) ? 1 : 0;
     f.nfc_magic = d->nfc > 1 ? (unsigned)((0x100000000ull + d->nfc - 1) / d->nfc) : 0u;
     const size_t N = (size_t)d->nfft;
     p->single_step = std::isinf(d->dphimaxt) && d->dzmaxt >= d->length;
@@ -1002,6 +1006,10 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
                 Grp& G = grp[gi];
                 // serpentine tile order: consecutive passes walk the realizations in opposite directions
                 G.pA.reverse = serp ? (rev[gi] ^= 1) : 0;
+                if (G.fc.xpm) {  // row sums of |u|^2 over the columns, parked in the (empty) Y slots for pass A
+                    p->tA->xpm_sum(dim3((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), G.nb), G.st, G.pA, G.fc);
+                    c->launches++;
+                }
                 { ProfScope ps(c, 0); p->tA->passA(G.gA, G.st, G.pA, G.fc, fld->map_cols); }
                 G.pB.reverse = serp ? (rev[gi] ^= 1) : 0;
                 { ProfScope ps(c, 1); p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_rows); }

@@ -101,7 +101,9 @@ struct FiberConst {
     double Lf, alphalin, halfalpha, dzmax, phimax, lcorr, invN;
     double gam[PMX_MAX_NFC];  // after the Manakov 8/9 (fiber.m:500)
     int nplates, nfc, spm, manakov, pmd, gvd_any, plate_sets, trace_cap;
-    int keep_basis, pad_;  // keep_basis: pmd && (manakov || !spm), see PMX_BM_*
+    int keep_basis;        // pmd && (manakov || !spm), see PMX_BM_*
+    int scalar_field;      // scalar_ssfm dispatch (fiber.m:372-380): Y absent; nl_step's operation order
+    int xpm;               // scalar path with the 'x' flag: cross-phase modulation between the columns (:793-799)
     // scalar dispersion mode (fiber.m:350-362 regenerated per bin instead of read from HBM):
     //   omega = w0*fn, fn = kk/NSYMB (kk = signed FFT bin), betat = omega*beta1 + 0.5*omega^2*beta2
     //   + omega^3*b30/6, db1 = dgdrms*omega

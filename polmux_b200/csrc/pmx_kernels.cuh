@@ -361,6 +361,26 @@ __device__ __forceinline__ void pmx_split_bc(int bc, const FiberConst& f, int& b
 #define PMX_MINB(threads, pf) ((PMX_TBUDGET(pf) / (threads)) > 0 ? (PMX_TBUDGET(pf) / (threads)) : 1)
 
 // ---------------------------------------------------------------------------
+// Scalar path with the 'x' flag (nl_step, fiber.m:786-799): the nonlinear phase of column k needs
+// sum_j |u_j|^2 of the same sample.  The scalar path has no Y polarization, so the row sum is parked in the
+// (zero) Y slot of every column's Sa, where pass A finds it with the sample it already loads; pass A
+// clears the slot again.  One read + a 16-byte write per Sa and step.
+static __global__ void __launch_bounds__(256) pmx_k_xpm_sum(PassParams p, FiberConst f) {
+    const int b = blockIdx.y;
+    if (p.pkg[b].state >= PMX_ST_DONE) return;
+    const size_t N = (size_t)p.N1 * p.N2;
+    cpx* fld = reinterpret_cast<cpx*>(p.field) + (size_t)b * f.nfc * N * 2;
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+        real sum = (real)0;
+        for (int k = 0; k < f.nfc; ++k) {  // sum(pow,2), left to right
+            const cpx x = fld[((size_t)k * N + n) * 2];
+            sum = R_ADD(sum, R_ADD(R_MUL(x.x, x.x), R_MUL(x.y, x.y)));
+        }
+        for (int k = 0; k < f.nfc; ++k) fld[((size_t)k * N + n) * 2 + 1] = mkc(sum, (real)0);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Tile walk shared by the three passes (persistent CTAs): tile -> (realization-column bc, group inside it),
 // serpentine direction, skipping finished realizations.
 struct PmxWalk {
@@ -446,7 +466,22 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
         PMX_T_MARK(2)
         // ---- nonlinear step, fiber.m:832-851
-        if (f.spm) {
+        if (f.scalar_field) {  // nl_step (fiber.m:786-803): u .* fastexp(-gam.*pow*leff), Y absent
+            if (f.spm || f.xpm) {
+                const real ngam = (real)(-f.gam[col]), leff = (real)st->leff;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    real pw = R_ADD(R_MUL(x[q].x, x[q].x), R_MUL(x[q].y, x[q].y));
+                    if (f.xpm) {  // y.x holds sum(pow,2) of this sample (pmx_k_xpm_sum)
+                        const real two_s = R_MUL((real)2, y[q].x);
+                        pw = f.spm ? R_ADD(two_s, -pw) : R_MUL((real)2, R_ADD(y[q].x, -pw));
+                    }
+                    x[q] = cmul(x[q], pmx_cis_r(R_MUL(R_MUL(ngam, pw), leff)));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) y[q] = mkc((real)0, (real)0);
+        } else if (f.spm) {
             const real gamleff = (real)__dmul_rn(f.gam[col], st->leff);
             const real ngl = -gamleff;
             cpx e[8];

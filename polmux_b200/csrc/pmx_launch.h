@@ -24,6 +24,8 @@ struct PmxLaunchTable {
     // first max |u|^2 of a resident field (pmx_k_init) and the four-step twiddle rows, in this precision
     void (*init_max)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
     void (*fill_tw4)(void* tab, int rows, double two_over_N, cudaStream_t s);
+    // scalar XPM: sum over the columns of |u|^2 per sample, written to the Y slot of every column (grid.y = realizations)
+    void (*xpm_sum)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
 };
 
 const PmxLaunchTable* pmx_get_table(int L, int precision = 0);  // nullptr if L is not built

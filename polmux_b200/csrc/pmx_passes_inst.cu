@@ -69,6 +69,7 @@ void passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, con
 void init_max(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f) {
     pmx_k_init<<<grid, 256, 256, s>>>(p, f);
 }
+void xpm_sum(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f) { pmx_k_xpm_sum<<<grid, 256, 0, s>>>(p, f); }
 void fill_tw4(void* tab, int rows, double two_over_N, cudaStream_t s) {
     const size_t n = (size_t)rows * PmxTw4<L>::PER;
     const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
@@ -87,4 +88,4 @@ void fill_tw4(void* tab, int rows, double two_over_N, cudaStream_t s) {
 extern const PmxLaunchTable PMX_TABLE_NAME = {
     L, GAC, GB, PFAC ? 1 : 0, PFB ? 1 : 0, SA::THREADS, SB::THREADS, (size_t)SA::TOTAL, (size_t)SB::TOTAL,
     pmx_tw_total(L), PmxTw4<L>::LO, PmxTw4<L>::PER, PMX_PRECISION, (int)sizeof(cpx),
-    setup, passA, passB, passC, init_max, fill_tw4};
+    setup, passA, passB, passC, init_max, fill_tw4, xpm_sum};

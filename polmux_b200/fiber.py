@@ -213,7 +213,8 @@ def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, ep
         s.nfft, s.nfc, batch, s.length, s.alphalin, s.dzmaxt, s.dphimaxt, s.gam, s.fls, s.manakov, s.nplates,
         s.brf['db0'] if db0 is None else db0, s.brf['theta'] if theta is None else theta,
         s.brf['epsilon'] if epsilon is None else epsilon, s.betat, s.db1 if s.fls[1] else None,
-        plate_sets=plate_sets, precision=prec, scalar=s.scalars if mode == 'scalar' else None)
+        plate_sets=plate_sets, precision=prec, scalar=s.scalars if mode == 'scalar' else None,
+        scalar_field=not s.isv)
 
 
 def apply_side_effects(s: FiberSetup):
@@ -237,9 +238,6 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
     if s.fls[3] and s.isv:
         # matrix_nl_step raises at fiber.m:854 on the first step
         raise NotImplementedError('The CNLSE with separate fields is not yet implemented')
-    if s.fls[3]:
-        raise NotImplementedError("scalar cross-phase modulation ('x' flag with separate fields, "
-                                  "fiber.m:793-799) is not built yet")
     if s.fls[1] and not s.isy:                                              # :285-289
         G.FIELDY = np.zeros_like(G.FIELDX)
     apply_side_effects(s)

@@ -94,3 +94,26 @@ def test_cuda_matches_reference_source(name):
     if 'amp_FIELDX' in z.files:
         pmx.ampliflat(m['amp']['gain'], 'gain', {'f': m['amp']['f'], 'noise': z['amp_noise']})
         assert orc.rel_l2(G.FIELDX, G.FIELDY, z['amp_FIELDX'], z['amp_FIELDY']) < 1e-10
+
+
+SCALAR_CASES = [c for c in CASES if c.startswith('scalar_')]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', SCALAR_CASES)
+def test_cuda_scalar_path_matches_reference_source(name):
+    """The scalar path (scalar_ssfm: FIELDY empty, no 'p' flag; nl_step with SPM and cross-column XPM,
+    fiber.m:557-636,786-803) on the device against the interpreted reference: <= 1e-10 rel L2 (FP64)."""
+    z, m = load(name)
+    if m['fiber'].get('ltol') is not None or 'ltol' in m['fiber']:
+        pytest.skip('local-error adaptive step (scalar_a_ssfm) is not built')
+    pmx.reset_all(m['nsymb'], m['nt'], m['nch'])
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.POWER, G.LAMBDA = m['rate'], np.full(m['nch'], float(m['pavg'])), synth.wdm_lambdas(m['nch'])
+    pmx.create_field(m['ftype'], z['in_ex'], None, {'power': 'average'})
+    pmx.fiber(m['fiber'], m['flag'], rng=np.random.Generator(np.random.PCG64(m['seed'])))
+    err = float(np.linalg.norm(G.FIELDX - z['out_FIELDX']) / np.linalg.norm(z['out_FIELDX']))
+    assert err < 1e-10, err
+    assert G.FIELDY is None or np.size(G.FIELDY) == 0
+    np.testing.assert_allclose(G.DELAY, z['out_DELAY'], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(G.DISP, z['out_DISP'], rtol=1e-13, atol=1e-13)
