@@ -103,7 +103,7 @@ def _cpu_worker(seed):
     return cpu_sample(seed)
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out=sys.stdout):
     """--impl reference: the CPU SSFM on all host cores (one realization per worker process)."""
     if rank != 0:
         return
@@ -129,7 +129,8 @@ def run_reference(args, rank, world):
             'config': workload_config(args, world),
             'cpu_baseline': {'value': val, 'unit': 'GSa*steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'GSa*steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def workload_config(args, world):
@@ -141,7 +142,17 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Keep stdout for the one JSON line: libraries (NCCL's version banner, torchrun notices) that write to
+    file descriptor 1 are redirected to stderr; returns a writer bound to the original stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, 'w')
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
@@ -158,7 +169,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -395,7 +406,8 @@ def main():
                 'data': 'synthetic', 'config': workload_config(args, world), 'clocks': sampler.summary(),
                 'e2e': e2e, 'gpu_launches': int(gpu_launches), 'roofline': roof, 'roofline_step': step_roof,
                 'cpu_baseline': cpu, 'mc': mcres, 'fp32': fp32, 'sa_steps_per_step': total_all / max(args.steps, 1)}
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + '\n')
+        out.flush()
     if world > 1:
         dist.destroy_process_group()
 
