@@ -556,11 +556,12 @@ __device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const dou
     const cpx m11 = mkc((real)M[0], (real)M[1]), m12 = mkc((real)M[2], (real)M[3]);
     const cpx m21 = mkc((real)M[4], (real)M[5]), m22 = mkc((real)M[6], (real)M[7]);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const cpx nx = cadd(cmul(m11, x[q]), cmul(m12, y[q]));
-        const cpx ny = cadd(cmul(m21, x[q]), cmul(m22, y[q]));
-        x[q] = nx;
-        y[q] = ny;
+    for (int q = 0; q < 8; ++q) {  // four-term FMA chains: 16 instructions per bin instead of 20
+        const cpx a = x[q], b = y[q];
+        x[q] = mkc(fma(-m12.y, b.y, fma(m12.x, b.x, fma(-m11.y, a.y, m11.x * a.x))),
+                   fma(m12.y, b.x, fma(m12.x, b.y, fma(m11.y, a.x, m11.x * a.y))));
+        y[q] = mkc(fma(-m22.y, b.y, fma(m22.x, b.x, fma(-m21.y, a.y, m21.x * a.x))),
+                   fma(m22.y, b.x, fma(m22.x, b.y, fma(m21.y, a.x, m21.x * a.y))));
     }
 }
 
