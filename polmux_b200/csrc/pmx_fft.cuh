@@ -95,6 +95,41 @@ __device__ __forceinline__ void dft8(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4
 // butterfly code serves both directions.  The radix-8 stages after the first run as a loop over
 // the stage size (one copy of the stage body; pass B calls the transform from a two-iteration loop),
 // which keeps the pass kernels within the instruction cache.
+// a + w*b as two FMAs per component, and a - w*b = 2a - (a + w*b) as one more: a twiddled radix-2 butterfly in
+// 6 instructions instead of 8 (complex product, add, subtract)
+__device__ __forceinline__ void bfly_tw(cpx a, cpx w, cpx b, cpx& s, cpx& d) {
+    s = mkc(fma(-w.y, b.y, fma(w.x, b.x, a.x)), fma(w.y, b.x, fma(w.x, b.y, a.y)));
+    d = mkc(fma((real)2, a.x, -s.x), fma((real)2, a.y, -s.y));
+}
+
+// Forward radix-8 butterfly with the stage twiddles w1..w7 folded into its first layer: inputs a1..a7 are the
+// UNtwiddled points, the result is DFT_8(a0, w1*a1, ..., w7*a7).
+__device__ __forceinline__ void dft8_tw(cpx& a0, cpx& a1, cpx& a2, cpx& a3, cpx& a4, cpx& a5, cpx& a6, cpx& a7, cpx w1,
+                                        cpx w2, cpx w3, cpx w4, cpx w5, cpx w6, cpx w7) {
+    // first layer: pairs (0,4) (2,6) (1,5) (3,7)
+    cpx s04, d04, s26, d26, s15, d15, s37, d37;
+    bfly_tw(a0, w4, a4, s04, d04);
+    bfly_tw(cmul(w2, a2), w6, a6, s26, d26);
+    bfly_tw(cmul(w1, a1), w5, a5, s15, d15);
+    bfly_tw(cmul(w3, a3), w7, a7, s37, d37);
+    // rest of the two radix-4 butterflies (forward: * -i)
+    const cpx d26r = mkc(d26.y, -d26.x), d37r = mkc(d37.y, -d37.x);
+    const cpx e0 = cadd(s04, s26), e2 = csub(s04, s26), e1 = cadd(d04, d26r), e3 = csub(d04, d26r);
+    const cpx o0 = cadd(s15, s37), o2r = csub(s15, s37), o1r = cadd(d15, d37r), o3r = csub(d15, d37r);
+    // W8^k * O[k]
+    const cpx o1 = mkc((o1r.x + o1r.y) * PMX_SQRT1_2, (o1r.y - o1r.x) * PMX_SQRT1_2);
+    const cpx o2 = mkc(o2r.y, -o2r.x);
+    const cpx o3 = mkc((o3r.y - o3r.x) * PMX_SQRT1_2, -(o3r.x + o3r.y) * PMX_SQRT1_2);
+    a0 = cadd(e0, o0);
+    a1 = cadd(e1, o1);
+    a2 = cadd(e2, o2);
+    a3 = cadd(e3, o3);
+    a4 = csub(e0, o0);
+    a5 = csub(e1, o1);
+    a6 = csub(e2, o2);
+    a7 = csub(e3, o3);
+}
+
 // one point of both polarizations to / from the exchange buffers.  FP64: two arrays (sx, sy) of 16-byte complex
 // numbers; FP32: ONE array of float4 (x, y of a point side by side) at sx, so that an exchange moves 16 bytes per
 // shared-memory instruction in both precisions.
@@ -166,16 +201,9 @@ struct CtaFFT {
                 const cpx w1 = tw[two + k], w2 = tw[two + ns + k], w4 = tw[two + 2 * ns + k];
                 const cpx w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
                 const cpx w7 = cmul(w4, w3);
-                x[1] = cmul(x[1], w1); y[1] = cmul(y[1], w1);
-                x[2] = cmul(x[2], w2); y[2] = cmul(y[2], w2);
-                x[3] = cmul(x[3], w3); y[3] = cmul(y[3], w3);
-                x[4] = cmul(x[4], w4); y[4] = cmul(y[4], w4);
-                x[5] = cmul(x[5], w5); y[5] = cmul(y[5], w5);
-                x[6] = cmul(x[6], w6); y[6] = cmul(y[6], w6);
-                x[7] = cmul(x[7], w7); y[7] = cmul(y[7], w7);
+                dft8_tw(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], w1, w2, w3, w4, w5, w6, w7);
+                dft8_tw(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], w1, w2, w3, w4, w5, w6, w7);
             }
-            dft8<false>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-            dft8<false>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
             if (ns * 8 >= L) break;
             const int j0 = (t - k) * 8 + k;
 #pragma unroll
