@@ -273,7 +273,7 @@ struct PassSmem {
     static constexpr int WORK_OFF = PF ? ((TILE_BYTES + 1023) / 1024) * 1024 : 0;
     static constexpr int TW_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;   // stage twiddles
     static constexpr int PKG_BYTES = (KIND == 1) ? (int)sizeof(StepPkg) : PMX_PKG_HEAD;
-    static constexpr int TAB_BYTES = (KIND == 2) ? 0 : ((G * PmxTw4<L>::PER * (int)sizeof(cpx) + 15) / 16) * 16;
+    static constexpr int TAB_BYTES = (KIND == 1) ? 0 : ((G * PmxTw4<L>::PER * (int)sizeof(cpx) + 15) / 16) * 16;
     static constexpr int AUX_BYTES = PKG_BYTES + TAB_BYTES;
     static constexpr int AUX_OFF = TW_OFF + ((pmx_tw_total(L) * (int)sizeof(cpx) + 15) / 16) * 16;
     static constexpr int PLATE_OFF = AUX_OFF + 2 * AUX_BYTES;               // pass B: chunks of trunks beyond the package
@@ -603,14 +603,13 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     auto issue = [&](int tl, int buf) {
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
-        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb;
         for (int l0 = 0; l0 < LINES; l0 += 256)
             pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
         pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
-        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)row0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -631,7 +630,6 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         const int k1 = (tt & wk.tpb_mask) * G + rl;
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
         const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
-        const cpx* gtab = reinterpret_cast<const cpx*>(aux + S::PKG_BYTES);
         const int next = live(tile + gridDim.x);
         cpx x[8], y[8];
         PMX_T_MARK(0)
@@ -841,16 +839,12 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         }
         PMX_T_MARK(5)
         if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
-        // conj four-step twiddle W_N^(-n2*k1), n2 = t + q*T, from the row's two-level table
+        // the second transform was run on conj(spectrum): conj(result) is the inverse transform.  Its four-step
+        // twiddle W_N^(-n2*k1) is applied by pass C when it loads the sample (pass C has FP64 slots to spare).
         {
-            const cpx* tb = gtab + rl * W::PER;
-            const cpx wl = tb[t & (W::NLO - 1)];
             cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
-                st_sa(base + (size_t)(t + q * T) * 2, cconj(cmul(x[q], w)), cconj(cmul(y[q], w)));
-            }
+            for (int q = 0; q < 8; ++q) st_sa(base + (size_t)(t + q * T) * 2, cconj(x[q]), cconj(y[q]));
         }
         tile = next;
         ++it;
@@ -868,6 +862,7 @@ template <typename R, int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 2>;
+    using W = PmxTw4<L>;
     constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
@@ -902,7 +897,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
-        pmx_bulk_load(aux0 + buf * S::AUX_BYTES, &p.pkg[b_], S::PKG_BYTES, mbar);
+        unsigned char* a = aux0 + buf * S::AUX_BYTES;
+        pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
+        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)c0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -921,7 +918,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         const int tt = wk.phys(tile), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
-        const StepPkg* st = reinterpret_cast<const StepPkg*>(aux0 + (it & 1) * S::AUX_BYTES);
+        const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
+        const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
+        const cpx* gtab = reinterpret_cast<const cpx*>(aux + S::PKG_BYTES);
         const int next = live(tile + gridDim.x);
         cpx x[8], y[8];
         PMX_T_MARK(0)
@@ -931,8 +930,17 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
-            x[q] = cconj(x[q]);  // inverse transform = conj o forward o conj
-            y[q] = cconj(y[q]);
+        }
+        {   // Pass B left v = conj(z), z = its transform output before the four-step twiddle W_N^(-n2*k1), k1 = t + q*T.
+            // The inverse transform over k1 = conj o forward o conj applied to conj(z)*conj(W): its input is z*W.
+            const cpx* tb = gtab + cl * W::PER;
+            const cpx wl = tb[t & (W::NLO - 1)];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
+                x[q] = cmul(cconj(x[q]), w);
+                y[q] = cmul(cconj(y[q]), w);
+            }
         }
         const real sc = (real)st->scale, nsc = -sc;
         if (threadIdx.x == 0) pmx_tma_wait_read();
