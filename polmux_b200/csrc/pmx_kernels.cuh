@@ -671,8 +671,15 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                     double d1[SC ? 1 : 8];
                     cpx e1[SC ? 1 : 8];
                     double d10 = 0.0, d14 = 0.0;
-                    cpx E0 = mkc((real)1.0, (real)0.0), E4 = E0;
-                    cpx pf0, pf4, pl0, pl4;  // scalar mode: phases of the step's first / last trunk at the two base bins
+                    cpx E0 = mkc((real)1.0, (real)0.0);
+                    // scalar mode: phases of the step's first / last trunk at the thread's first bin.  Its bins
+                    // q = 0..3 (positive frequencies) and 4..7 (negative) are equally spaced, bin 4 lying four spacings
+                    // BELOW bin 0, and db1 is linear in omega: with g = exp(-i*0.5*dgdrms*domega*dzb/lcorr) the phase
+                    // factors of bins 1..3 are e0*g^q and those of bins 4..7 are e0*conj(g)^4*g^(q-4).
+                    cpx pf0, pl0;
+#ifdef PMX_F32
+                    cpx pf4, pl4;  // FP32: g^4 in float would cost 2e-7 of phase per trunk; evaluate both base bins
+#endif
 #ifdef PMX_F32
                     // FP32: the whole-trunk factor exp(-i*db1/2) of a bin is the same for every whole trunk of the
                     // step, so a float-rounded copy (or a float progression) would repeat the SAME phase error in
@@ -692,18 +699,17 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                             }
 #else
                             E0 = pmx_cis(-0.5 * d10);
-                            E4 = pmx_cis(-0.5 * d14);
 #endif
                         }
                         // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
                         // independent and interleave
                         const double db0f = st->plates[0].db0, db0l = st->db0_last;
-                        double a4[4] = {-(0.5 * (d10 + db0f) * dzb_first / lcorr), -(0.5 * (d14 + db0f) * dzb_first / lcorr),
-                                        -(0.5 * (d10 + db0l) * dzb_last / lcorr), -(0.5 * (d14 + db0l) * dzb_last / lcorr)};
-                        pf0 = pmx_cis(a4[0]);
-                        pf4 = pmx_cis(a4[1]);
-                        pl0 = pmx_cis(a4[2]);
-                        pl4 = pmx_cis(a4[3]);
+                        pf0 = pmx_cis(-(0.5 * (d10 + db0f) * dzb_first / lcorr));
+                        pl0 = pmx_cis(-(0.5 * (d10 + db0l) * dzb_last / lcorr));
+#ifdef PMX_F32
+                        pf4 = pmx_cis(-(0.5 * (d14 + db0f) * dzb_first / lcorr));
+                        pl4 = pmx_cis(-(0.5 * (d14 + db0l) * dzb_last / lcorr));
+#endif
                     } else {
                         const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
 #pragma unroll
@@ -752,14 +758,17 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                                 if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
                                     const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
                                     e0 = cmul(E0, h0);
-                                    e4 = cmul(E4, h0);
                                     g = mkc((real)f.g1r, (real)f.g1i);
                                 } else {  // partial trunk (first or last of the step)
                                     e0 = (k == 0) ? pf0 : pl0;
-                                    e4 = (k == 0) ? pf4 : pl4;
                                     g = (k == 0) ? mkc((real)st->gpf_r, (real)st->gpf_i) : mkc((real)st->gpl_r, (real)st->gpl_i);
                                 }
                                 const cpx g2 = cmul(g, g);
+#ifdef PMX_F32
+                                e4 = (k == 0) ? pf4 : pl4;  // (whole trunks took the double-phasor path above)
+#else
+                                e4 = cmulc(e0, cmul(g2, g2));
+#endif
                                 const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
                                 const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
                                 x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
