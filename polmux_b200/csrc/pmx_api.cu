@@ -1033,7 +1033,21 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
             if (c->h_ctl[b].state < PMX_ST_DONE) all_done = false;
         if (all_done) break;
         if (total_steps > 10000000) return set_err(c, PMX_ERR_NUMERIC, "step loop did not terminate");
-        if (chunk < 32) chunk *= 2;
+        // Size the next chunk from what is left: steps beyond the last one of every realization are launches that
+        // exit at once (a few microseconds each), a chunk that ends early costs one more read-back.  With
+        // attenuation the step grows like exp(alpha*z) while it is bounded by the nonlinear phase, so
+        // (1 - exp(-alpha*r)) / (alpha*dz) steps remain over the length r; r/dz is the bound for constant steps.
+        double est = 1.0;
+        for (int b = 0; b < batch; ++b) {
+            const StepCtl& sc = c->h_ctl[b];
+            if (sc.state >= PMX_ST_DONE || !(sc.dz > 0)) continue;
+            const double r = std::max(0.0, p->fc.Lf - sc.zprop) + sc.dz;
+            const double lin = r / sc.dz;
+            const double a = p->fc.alphalin;
+            const double ex = (a > 0) ? (1.0 - exp(-a * r)) / (a * sc.dz) : lin;
+            est = std::max(est, 0.5 * (lin + ex));
+        }
+        chunk = (int)std::min(32.0, std::max(1.0, ceil(0.85 * est)));
     }
     int worst = PMX_OK;
     for (int b = 0; b < batch; ++b) {
