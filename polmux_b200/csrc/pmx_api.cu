@@ -136,9 +136,10 @@ struct pmx_devfield {
     cpx* data;  // [batch*nfc][nfft][2]; float2 elements behind this pointer when precision == PMX_F32
     size_t cbytes() const { return precision == PMX_F32 ? sizeof(float2) : sizeof(double2); }
     int N1 = 0, N2 = 0;
+    int log2N1 = 0, log2N2 = 0;  // time sample n = n1*N2 + n2 is stored at n2*N1 + n1 (0/0: natural order, no SSFM)
     bool has_maps = false;
-    CUtensorMap map_cols;  // passes A, C: box {gAC*4 doubles, <=256 rows, 1}
-    CUtensorMap map_rows;  // pass B: 128-byte lines, box {16 doubles, <=256 lines, 1}
+    CUtensorMap map_cols;  // pass B: box {gB*4 reals, <=256 rows, 1} of the [N2][N1] matrix
+    CUtensorMap map_rows;  // passes A, C: 128-byte lines, box {one line, <=256 lines, 1}
 };
 
 static int ilog2_exact(int64_t v) {
@@ -170,11 +171,13 @@ static int build_maps(pmx_ctx* c, pmx_devfield* f) {
     const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     const cuuint64_t SAB = f32 ? 16 : 32;  // bytes per Sa (4 reals)
     const cuuint32_t ones[3] = {1, 1, 1};
-    {
-        const int G = tA->gAC;
-        cuuint64_t dims[3] = {(cuuint64_t)f->N2 * 4, (cuuint64_t)f->N1, BC};
-        cuuint64_t strides[2] = {(cuuint64_t)f->N2 * SAB, N * SAB};
-        cuuint32_t box[3] = {(cuuint32_t)G * 4, (cuuint32_t)std::min(f->N1, 256), 1};
+    // The field is stored transposed in time (sample n1*N2 + n2 at n2*N1 + n1, see pmx_kernels.cuh): an [N2][N1]
+    // matrix of Sa per realization-column.
+    {   // pass B: gB adjacent columns (k1), all N2 rows
+        const int G = tB->gB;
+        cuuint64_t dims[3] = {(cuuint64_t)f->N1 * 4, (cuuint64_t)f->N2, BC};
+        cuuint64_t strides[2] = {(cuuint64_t)f->N1 * SAB, N * SAB};
+        cuuint32_t box[3] = {(cuuint32_t)G * 4, (cuuint32_t)std::min(f->N2, 256), 1};
         const int pitch = G * (int)SAB;  // bytes of one box row = swizzle span (16: none)
         CUtensorMapSwizzle sw = pitch <= 16 ? CU_TENSOR_MAP_SWIZZLE_NONE
                                             : (pitch == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
@@ -184,9 +187,9 @@ static int build_maps(pmx_ctx* c, pmx_devfield* f) {
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return set_err(c, PMX_ERR_CUDA, "cuTensorMapEncodeTiled(cols) failed: CUresult %d", (int)r);
     }
-    {
+    {   // passes A and C: gAC adjacent rows (n2) of N1 Sa = contiguous 128-byte lines
         const int sa_per_line = (int)(128 / SAB);  // a 128-byte line holds 4 (FP64) or 8 (FP32) Sa
-        const int lines = tB->gB * f->N2 / sa_per_line;
+        const int lines = tA->gAC * f->N1 / sa_per_line;
         cuuint64_t dims[3] = {(cuuint64_t)(f32 ? 32 : 16), N / sa_per_line, BC};
         cuuint64_t strides[2] = {128, N * SAB};
         cuuint32_t box[3] = {(cuuint32_t)(f32 ? 32 : 16), (cuuint32_t)std::min(lines, 256), 1};
@@ -195,6 +198,8 @@ static int build_maps(pmx_ctx* c, pmx_devfield* f) {
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return set_err(c, PMX_ERR_CUDA, "cuTensorMapEncodeTiled(rows) failed: CUresult %d", (int)r);
     }
+    f->log2N1 = split_log2N1(lg);
+    f->log2N2 = lg - f->log2N1;
     f->has_maps = true;
     return PMX_OK;
 }
@@ -444,7 +449,13 @@ extern "C" void pmx_field_destroy(pmx_devfield* f) {
 
 extern "C" void* pmx_field_device_ptr(pmx_devfield* f) { return f ? (void*)f->data : nullptr; }
 
-// planar / complex host layouts (always double) <-> interleaved (xr,xi,yr,yi) in the field's precision
+// position of time sample n of a column in the resident field (transposed four-step layout, or natural order)
+__host__ __device__ __forceinline__ size_t pmx_mem_index(size_t n, int log2N1, int log2N2) {
+    return ((n & (((size_t)1 << log2N2) - 1)) << log2N1) + (n >> log2N2);
+}
+
+// planar / complex host layouts (always double) <-> interleaved (xr,xi,yr,yi) in the field's precision;
+// i runs over [columns][nfft] in host (time) order, the device side is permuted within each column
 template <typename T2>
 __device__ __forceinline__ T2 pmx_mk2(double a, double b);
 template <>
@@ -452,18 +463,21 @@ __device__ __forceinline__ double2 pmx_mk2<double2>(double a, double b) { return
 template <>
 __device__ __forceinline__ float2 pmx_mk2<float2>(double a, double b) { return make_float2((float)a, (float)b); }
 
+#define PMX_DEV_INDEX(i) ((((i) >> lg) << lg) + pmx_mem_index((i) & (((size_t)1 << lg) - 1), l1, lg - l1))
 template <typename T2>
 __global__ void pmx_k_pack_planar(T2* dst, const double* xr, const double* xi, const double* yr,
-                                  const double* yi, size_t n) {
+                                  const double* yi, size_t n, int lg, int l1) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        dst[2 * i] = pmx_mk2<T2>(xr[i], xi ? xi[i] : 0.0);
-        dst[2 * i + 1] = pmx_mk2<T2>(yr ? yr[i] : 0.0, yi ? yi[i] : 0.0);
+        const size_t m = PMX_DEV_INDEX(i);
+        dst[2 * m] = pmx_mk2<T2>(xr[i], xi ? xi[i] : 0.0);
+        dst[2 * m + 1] = pmx_mk2<T2>(yr ? yr[i] : 0.0, yi ? yi[i] : 0.0);
     }
 }
 template <typename T2>
-__global__ void pmx_k_unpack_planar(const T2* src, double* xr, double* xi, double* yr, double* yi, size_t n) {
+__global__ void pmx_k_unpack_planar(const T2* src, double* xr, double* xi, double* yr, double* yi, size_t n, int lg, int l1) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        T2 x = src[2 * i], y = src[2 * i + 1];
+        const size_t m = PMX_DEV_INDEX(i);
+        T2 x = src[2 * m], y = src[2 * m + 1];
         xr[i] = x.x;
         xi[i] = x.y;
         yr[i] = y.x;
@@ -471,17 +485,19 @@ __global__ void pmx_k_unpack_planar(const T2* src, double* xr, double* xi, doubl
     }
 }
 template <typename T2>
-__global__ void pmx_k_pack_complex(T2* dst, const double2* x, const double2* y, size_t n) {
+__global__ void pmx_k_pack_complex(T2* dst, const double2* x, const double2* y, size_t n, int lg, int l1) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        dst[2 * i] = pmx_mk2<T2>(x[i].x, x[i].y);
-        dst[2 * i + 1] = y ? pmx_mk2<T2>(y[i].x, y[i].y) : pmx_mk2<T2>(0.0, 0.0);
+        const size_t m = PMX_DEV_INDEX(i);
+        dst[2 * m] = pmx_mk2<T2>(x[i].x, x[i].y);
+        dst[2 * m + 1] = y ? pmx_mk2<T2>(y[i].x, y[i].y) : pmx_mk2<T2>(0.0, 0.0);
     }
 }
 template <typename T2>
-__global__ void pmx_k_unpack_complex(const T2* src, double2* x, double2* y, size_t n) {
+__global__ void pmx_k_unpack_complex(const T2* src, double2* x, double2* y, size_t n, int lg, int l1) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        x[i] = make_double2(src[2 * i].x, src[2 * i].y);
-        y[i] = make_double2(src[2 * i + 1].x, src[2 * i + 1].y);
+        const size_t m = PMX_DEV_INDEX(i);
+        x[i] = make_double2(src[2 * m].x, src[2 * m].y);
+        y[i] = make_double2(src[2 * m + 1].x, src[2 * m + 1].y);
     }
 }
 
@@ -513,9 +529,9 @@ extern "C" int pmx_field_upload(pmx_devfield* f, const pmx_field* h, int32_t b0,
                 CK(c, cudaMemcpyAsync(dparts[k], parts[k], n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         }
         if (f32)
-            pmx_k_pack_planar<float2><<<blocks, 256, 0, c->stream>>>((float2*)dstb, dparts[0], dparts[1], dparts[2], dparts[3], n);
+            pmx_k_pack_planar<float2><<<blocks, 256, 0, c->stream>>>((float2*)dstb, dparts[0], dparts[1], dparts[2], dparts[3], n, f->log2N1 + f->log2N2, f->log2N1);
         else
-            pmx_k_pack_planar<double2><<<blocks, 256, 0, c->stream>>>((double2*)dstb, dparts[0], dparts[1], dparts[2], dparts[3], n);
+            pmx_k_pack_planar<double2><<<blocks, 256, 0, c->stream>>>((double2*)dstb, dparts[0], dparts[1], dparts[2], dparts[3], n, f->log2N1 + f->log2N2, f->log2N1);
         c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaFreeAsync(stage, c->stream));
@@ -529,9 +545,9 @@ extern "C" int pmx_field_upload(pmx_devfield* f, const pmx_field* h, int32_t b0,
             CK(c, cudaMemcpyAsync(dy, h->yr, n * sizeof(cpx), cudaMemcpyHostToDevice, c->stream));
         }
         if (f32)
-            pmx_k_pack_complex<float2><<<blocks, 256, 0, c->stream>>>((float2*)dstb, stage, dy, n);
+            pmx_k_pack_complex<float2><<<blocks, 256, 0, c->stream>>>((float2*)dstb, stage, dy, n, f->log2N1 + f->log2N2, f->log2N1);
         else
-            pmx_k_pack_complex<double2><<<blocks, 256, 0, c->stream>>>((double2*)dstb, stage, dy, n);
+            pmx_k_pack_complex<double2><<<blocks, 256, 0, c->stream>>>((double2*)dstb, stage, dy, n, f->log2N1 + f->log2N2, f->log2N1);
         c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaFreeAsync(stage, c->stream));
@@ -556,9 +572,9 @@ extern "C" int pmx_field_download(pmx_devfield* f, pmx_field* h, int32_t b0, int
         double* stage = nullptr;
         CK(c, cudaMallocAsync(&stage, 4 * n * sizeof(double), c->stream));
         if (f32)
-            pmx_k_unpack_planar<float2><<<blocks, 256, 0, c->stream>>>((const float2*)srcb, stage, stage + n, stage + 2 * n, stage + 3 * n, n);
+            pmx_k_unpack_planar<float2><<<blocks, 256, 0, c->stream>>>((const float2*)srcb, stage, stage + n, stage + 2 * n, stage + 3 * n, n, f->log2N1 + f->log2N2, f->log2N1);
         else
-            pmx_k_unpack_planar<double2><<<blocks, 256, 0, c->stream>>>((const double2*)srcb, stage, stage + n, stage + 2 * n, stage + 3 * n, n);
+            pmx_k_unpack_planar<double2><<<blocks, 256, 0, c->stream>>>((const double2*)srcb, stage, stage + n, stage + 2 * n, stage + 3 * n, n, f->log2N1 + f->log2N2, f->log2N1);
         c->launches++;
         CK(c, cudaGetLastError());
         double* parts[4] = {h->xr, h->xi, h->yr, h->yi};
@@ -569,9 +585,9 @@ extern "C" int pmx_field_download(pmx_devfield* f, pmx_field* h, int32_t b0, int
         cpx* stage = nullptr;
         CK(c, cudaMallocAsync(&stage, 2 * n * sizeof(cpx), c->stream));
         if (f32)
-            pmx_k_unpack_complex<float2><<<blocks, 256, 0, c->stream>>>((const float2*)srcb, stage, stage + n, n);
+            pmx_k_unpack_complex<float2><<<blocks, 256, 0, c->stream>>>((const float2*)srcb, stage, stage + n, n, f->log2N1 + f->log2N2, f->log2N1);
         else
-            pmx_k_unpack_complex<double2><<<blocks, 256, 0, c->stream>>>((const double2*)srcb, stage, stage + n, n);
+            pmx_k_unpack_complex<double2><<<blocks, 256, 0, c->stream>>>((const double2*)srcb, stage, stage + n, n, f->log2N1 + f->log2N2, f->log2N1);
         c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaMemcpyAsync(h->xr, stage, n * sizeof(cpx), cudaMemcpyDeviceToHost, c->stream));
@@ -1010,11 +1026,11 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
                     p->tA->xpm_sum(dim3((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), G.nb), G.st, G.pA, G.fc);
                     c->launches++;
                 }
-                { ProfScope ps(c, 0); p->tA->passA(G.gA, G.st, G.pA, G.fc, fld->map_cols); }
+                { ProfScope ps(c, 0); p->tA->passA(G.gA, G.st, G.pA, G.fc, fld->map_rows); }
                 G.pB.reverse = serp ? (rev[gi] ^= 1) : 0;
-                { ProfScope ps(c, 1); p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_rows); }
+                { ProfScope ps(c, 1); p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_cols); }
                 G.pA.reverse = serp ? (rev[gi] ^= 1) : 0;
-                { ProfScope ps(c, 2); p->tA->passC(G.gC, G.st, G.pA, G.fc, fld->map_cols); }
+                { ProfScope ps(c, 2); p->tA->passC(G.gC, G.st, G.pA, G.fc, fld->map_rows); }
                 pmx_k_ctl<<<G.nb, 128, 0, G.st>>>(G.pc, G.fc, 0);
                 c->launches += 4;
             }
@@ -1125,6 +1141,7 @@ struct AmpParams {
     unsigned long long seed;
     size_t N;
     int nfc, batch;
+    int l1, l2;        // field layout: time sample n1*N2 + n2 at n2*N1 + n1 (log2 N1, log2 N2; 0/0 = natural order)
 };
 
 template <typename T2>  // the gain and the noise are evaluated in double in both field precisions
@@ -1132,8 +1149,9 @@ __global__ void __launch_bounds__(256) pmx_k_ampliflat(AmpParams a) {
     const int bc = blockIdx.y, b = bc / a.nfc, col = bc % a.nfc;
     T2* fld = reinterpret_cast<T2*>(a.field) + (size_t)bc * a.N * 2;
     const double sig = a.sigma[col];
-    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += (size_t)gridDim.x * blockDim.x) {
-        cpx x = make_double2(fld[2 * n].x * a.sg, fld[2 * n].y * a.sg), y = make_double2(fld[2 * n + 1].x * a.sg, fld[2 * n + 1].y * a.sg);
+    for (size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x; m < a.N; m += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = ((m & (((size_t)1 << a.l1) - 1)) << a.l2) + (m >> a.l1);  // time index of memory position m
+        cpx x = make_double2(fld[2 * m].x * a.sg, fld[2 * m].y * a.sg), y = make_double2(fld[2 * m + 1].x * a.sg, fld[2 * m + 1].y * a.sg);
         if (sig != 0.0) {
             cpx nx, ny;
             if (a.noise) {
@@ -1149,8 +1167,8 @@ __global__ void __launch_bounds__(256) pmx_k_ampliflat(AmpParams a) {
             x.x += sig * nx.x; x.y += sig * nx.y;
             y.x += sig * ny.x; y.y += sig * ny.y;
         }
-        fld[2 * n] = pmx_mk2<T2>(x.x, x.y);
-        fld[2 * n + 1] = pmx_mk2<T2>(y.x, y.y);
+        fld[2 * m] = pmx_mk2<T2>(x.x, x.y);
+        fld[2 * m + 1] = pmx_mk2<T2>(y.x, y.y);
     }
 }
 
@@ -1168,6 +1186,8 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
     a.N = (size_t)f->nfft;
     a.nfc = f->nfc;
     a.batch = f->batch;
+    a.l1 = f->log2N1;
+    a.l2 = f->log2N2;
     cpx* dn = nullptr;
     if (noise_host) {
         const size_t bytes = (size_t)f->batch * 2 * f->nfc * f->nfft * sizeof(cpx);
@@ -1215,13 +1235,13 @@ extern "C" int pmx_count_errors(pmx_ctx* c, const uint8_t* hat, const uint8_t* p
 // ---------------------------------------------------------------------------
 // data-aided QPSK decision + bit-error count (see the header)
 __global__ void __launch_bounds__(256) pmx_k_qpsk_phase(const cpx* field, const uint8_t* sym, int nsymb, int nt, size_t N,
-                                                        double* acc /*[batch][2][2]*/) {
+                                                        int l1, int l2, double* acc /*[batch][2][2]*/) {
     const int b = blockIdx.y;
     const cpx* fld = field + (size_t)b * N * 2;
     double ax = 0, ay = 0, bx = 0, by = 0;  // sum r conj(s) for X (ax,ay) and Y (bx,by)
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nsymb; k += gridDim.x * blockDim.x) {
         cpx rx, ry;
-        ld_sa(fld + (size_t)k * nt * 2, rx, ry);
+        ld_sa(fld + pmx_mem_index((size_t)k * nt, l1, l2) * 2, rx, ry);
         const int sx = sym[k], sy = sym[nsymb + k];
         const double sxr = (sx & 1) ? 1.0 : -1.0, sxi = (sx & 2) ? 1.0 : -1.0;
         const double syr = (sy & 1) ? 1.0 : -1.0, syi = (sy & 2) ? 1.0 : -1.0;
@@ -1245,7 +1265,7 @@ __global__ void __launch_bounds__(256) pmx_k_qpsk_phase(const cpx* field, const 
 }
 
 __global__ void __launch_bounds__(256) pmx_k_qpsk_count(const cpx* field, const uint8_t* sym, int nsymb, int nt, size_t N,
-                                                        const double* acc, unsigned long long* counts) {
+                                                        int l1, int l2, const double* acc, unsigned long long* counts) {
     const int b = blockIdx.y;
     const cpx* fld = field + (size_t)b * N * 2;
     // e^{-i phi} up to a positive factor: conj of the accumulated correlation
@@ -1253,7 +1273,7 @@ __global__ void __launch_bounds__(256) pmx_k_qpsk_count(const cpx* field, const 
     unsigned int errs = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nsymb; k += gridDim.x * blockDim.x) {
         cpx rx, ry;
-        ld_sa(fld + (size_t)k * nt * 2, rx, ry);
+        ld_sa(fld + pmx_mem_index((size_t)k * nt, l1, l2) * 2, rx, ry);
         const double xr = rx.x * cxr - rx.y * cxi, xi = rx.x * cxi + rx.y * cxr;
         const double yr = ry.x * cyr - ry.y * cyi, yi = ry.x * cyi + ry.y * cyr;
         const int dx = (xr > 0 ? 1 : 0) | (xi > 0 ? 2 : 0), dy = (yr > 0 ? 1 : 0) | (yi > 0 ? 2 : 0);
@@ -1278,8 +1298,8 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
     CK(c, cudaMemsetAsync(acc, 0, (size_t)f->batch * 4 * sizeof(double), c->stream));
     CK(c, cudaMemsetAsync(counts_dev, 0, (size_t)f->batch * sizeof(int64_t), c->stream));
     dim3 g((unsigned)std::min((nsymb + 255) / 256, 148), f->batch);
-    pmx_k_qpsk_phase<<<g, 256, 0, c->stream>>>(f->data, dsym, nsymb, nt, (size_t)f->nfft, acc);
-    pmx_k_qpsk_count<<<g, 256, 0, c->stream>>>(f->data, dsym, nsymb, nt, (size_t)f->nfft, acc,
+    pmx_k_qpsk_phase<<<g, 256, 0, c->stream>>>(f->data, dsym, nsymb, nt, (size_t)f->nfft, f->log2N1, f->log2N2, acc);
+    pmx_k_qpsk_count<<<g, 256, 0, c->stream>>>(f->data, dsym, nsymb, nt, (size_t)f->nfft, f->log2N1, f->log2N2, acc,
                                                 (unsigned long long*)counts_dev);
     c->launches += 2;
     CK(c, cudaGetLastError());

@@ -389,13 +389,23 @@ struct PmxWalk {
 };
 
 // ---------------------------------------------------------------------------
-// pass A: G adjacent columns per tile, thread (cl fastest, t).
+// The field lives in HBM TRANSPOSED with respect to time: sample n = n1*N2 + n2 sits at n2*N1 + n1 (the
+// upload / download kernels do the permutation once per fiber() call).  The two passes that touch the time
+// domain (A and C) therefore work on CONTIGUOUS rows (fixed n2, all n1) and only pass B, which has the
+// arithmetic to hide it, walks columns (fixed k1, all n2) through narrow TMA boxes:
+//   memory [n2][n1] --A: FFT over n1, in place--> [n2][k1] --B: column k1, FFT over n2 / Jones / IFFT over k2,
+//   in place--> [n2][k1] --C: IFFT over k1, in place--> [n2][n1].
+// (Measured on B200: a TMA copy of 32-byte-wide column tiles runs at 4.4 TB/s, contiguous tiles at 6.5 TB/s.)
+//
+// pass A: G adjacent rows per tile, thread (t fastest, rl).  Persistent CTAs walk the tile list
+// (tile = realization-column bc, row group); finished realizations are skipped.
 template <typename R, int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passA(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 0>;
     using W = PmxTw4<L>;
-    constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
+    constexpr int T = L / 8;
+    constexpr int LINES = G * L * PMX_SA_BYTES / 128;  // 128-byte lines per tile
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;  // PF: landing buffer at 0; !PF: WORK_OFF == 0, lands in the exchange buffer
@@ -404,13 +414,14 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     unsigned char* aux0 = sm + S::AUX_OFF;
     unsigned char* sdone = sm + S::LIVE_OFF;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
+    const int rl = threadIdx.x / T, t = threadIdx.x % T;
+    const size_t N = (size_t)p.N1 * p.N2;
     PmxWalk wk;
     wk.ltpb = p.log2N2 - pmx_ilog2(G);
     wk.tpb_mask = (1 << wk.ltpb) - 1;
     wk.total = (p.batch * f.nfc) << wk.ltpb;
     wk.reverse = p.reverse;
     const int total = wk.total;
-    const int cl = threadIdx.x % G, t = threadIdx.x / G;
 
     auto live = [&](int tl) {
         while (tl < total) {
@@ -421,16 +432,18 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         return tl;
     };
+    // a tile = G adjacent rows of the [N2][N1] time-domain matrix = G*L contiguous Sa
     auto issue = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
-        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
-        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
+        for (int l0 = 0; l0 < LINES; l0 += 256)
+            pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
         pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
-        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)c0 * W::PER, S::TAB_BYTES, mbar);
+        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)row0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -445,7 +458,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     uint32_t phase = 0;
     PMX_T_DECL
     while (tile < total) {
-        const int tt = wk.phys(tile), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
+        const int tt = wk.phys(tile), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
@@ -458,10 +471,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         phase ^= 1u;
         PMX_T_MARK(1)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
-        }
-        if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
+        for (int q = 0; q < 8; ++q) lds_sa(in, pmx_swz<7>((uint32_t)((rl * L + t + q * T) * PMX_SA_BYTES)), x[q], y[q]);
         __syncthreads();
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
         PMX_T_MARK(2)
@@ -507,44 +517,35 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
                 }
             }
         }
-        cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
+        cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
         CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
-        // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the column's two-level table; the tile is staged
-        // (same swizzled layout as it landed) in the exchange buffer and TMA-stored
-        unsigned char* outb = reinterpret_cast<unsigned char*>(work);
+        if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);  // the exchange buffer is free again
+        // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the row's two-level table; straight to HBM (the row is
+        // contiguous: 32 lanes x 32 B per store instruction)
         {
-            const cpx* tb = gtab + cl * W::PER;
+            const cpx* tb = gtab + rl * W::PER;
             const cpx wl = tb[t & (W::NLO - 1)];
+            cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)(row0 + rl) * L) * 2;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const cpx w = cmul(wl, tb[W::NLO + ((t + q * T) >> W::LO)]);
-                sts_sa(outb, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), cmul(x[q], w), cmul(y[q], w));
+                st_sa(base + (size_t)(t + q * T) * 2, cmul(x[q], w), cmul(y[q], w));
             }
         }
         PMX_T_MARK(5)
-        pmx_fence_proxy_async();
-        __syncthreads();  // tile staged
-        if (threadIdx.x == 0) {
-            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, p.bc0 + bc, outb + r0 * PITCH);
-            pmx_tma_commit();
-            if (!PF && next < total) {  // the next tile lands in this same buffer
-                pmx_tma_wait_read();
-                issue(next, (it + 1) & 1);
-            }
-        }
         tile = next;
         ++it;
+        __syncthreads();  // everyone is done with this tile's auxiliary buffer
         PMX_T_MARK(6)
     }
     PMX_T_FLUSH(0)
-    if (threadIdx.x == 0) pmx_tma_wait_read();
 }
 
 // ---------------------------------------------------------------------------
-// pass B: G rows per tile, thread (t fastest, rl)
+// pass B: G adjacent columns (k1) of the [n2][k1] matrix per tile, thread (cl fastest, t)
 #ifdef PMX_B_CTAS   // experiment knob: resident 128-thread-equivalent CTAs targeted for pass B
 #define PMX_MINB_B(threads, pf) (((PMX_B_CTAS * 128 * (32 / PMX_SA_BYTES)) / (threads)) > 0 ? ((PMX_B_CTAS * 128 * (32 / PMX_SA_BYTES)) / (threads)) : 1)
 #else
@@ -569,8 +570,7 @@ template <typename R, int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 1>;
-    using W = PmxTw4<L>;
-    constexpr int T = L / 8;
+    constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;
@@ -580,16 +580,15 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     PlateConst* schunk = reinterpret_cast<PlateConst*>(sm + S::PLATE_OFF);
     unsigned char* sdone = sm + S::LIVE_OFF;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
+    const int cl = threadIdx.x % G, t = threadIdx.x / G;
+    const size_t N = (size_t)p.N1 * p.N2;
+    constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
     PmxWalk wk;
     wk.ltpb = p.log2N1 - pmx_ilog2(G);
     wk.tpb_mask = (1 << wk.ltpb) - 1;
     wk.total = (p.batch * f.nfc) << wk.ltpb;
     wk.reverse = p.reverse;
     const int total = wk.total;
-    const int rl = threadIdx.x / T, t = threadIdx.x % T;
-    const size_t N = (size_t)p.N1 * p.N2;
-    constexpr int LINES = G * L * PMX_SA_BYTES / 128;  // 128-byte lines per tile
-    constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
 
     auto live = [&](int tl) {
         while (tl < total) {
@@ -600,16 +599,14 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         }
         return tl;
     };
-    auto issue = [&](int tl, int buf) {
+    auto issue = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
-        const int tt = wk.phys(tl), bc = tt >> wk.ltpb;
-        for (int l0 = 0; l0 < LINES; l0 += 256)
-            pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, p.bc0 + bc, mbar);
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
+        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
-        unsigned char* a = aux0 + buf * S::AUX_BYTES;
-        pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
+        pmx_bulk_load(aux0 + buf * S::AUX_BYTES, &p.pkg[b_], S::PKG_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -624,10 +621,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     uint32_t phase = 0;
     PMX_T_DECL
     while (tile < total) {
-        const int tt = wk.phys(tile), bc = tt >> wk.ltpb;
+        const int tt = wk.phys(tile), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
-        const int k1 = (tt & wk.tpb_mask) * G + rl;
+        const int k1 = c0 + cl;
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
         const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
         const int next = live(tile + gridDim.x);
@@ -637,13 +634,12 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         phase ^= 1u;
         PMX_T_MARK(1)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            lds_sa(in, pmx_swz<7>((uint32_t)((rl * L + t + q * T) * PMX_SA_BYTES)), x[q], y[q]);
-        }
+        for (int q = 0; q < 8; ++q) lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
         const int ntrunk = st->ntrunk, bmode = st->bmode;
+        if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
         __syncthreads();
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
-        cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
+        cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(2)
         // forward transform, per-bin product, inverse transform (= conj o forward o conj): one copy of
@@ -847,32 +843,42 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
             PMX_T_MARK(4)
         }
         PMX_T_MARK(5)
-        if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
         // the second transform was run on conj(spectrum): conj(result) is the inverse transform.  Its four-step
         // twiddle W_N^(-n2*k1) is applied by pass C when it loads the sample (pass C has FP64 slots to spare).
-        {
-            cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)k1 * p.N2) * 2;
+        // The column tile is staged (same swizzled layout as it landed) in the exchange buffer and TMA-stored.
+        unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) st_sa(base + (size_t)(t + q * T) * 2, cconj(x[q]), cconj(y[q]));
+        for (int q = 0; q < 8; ++q)
+            sts_sa(outb, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), cconj(x[q]), cconj(y[q]));
+        pmx_fence_proxy_async();
+        __syncthreads();  // tile staged; everyone is done with this tile's auxiliary buffer and plate chunk
+        if (threadIdx.x == 0) {
+            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, p.bc0 + bc, outb + r0 * PITCH);
+            pmx_tma_commit();
+            if (!PF && next < total) {  // the next tile lands in this same buffer
+                pmx_tma_wait_read();
+                issue(next, (it + 1) & 1);
+            }
         }
         tile = next;
         ++it;
-        __syncthreads();  // everyone is done with this tile's auxiliary buffer and plate chunk
         PMX_T_MARK(6)
     }
     PMX_T_FLUSH(1)
+    if (threadIdx.x == 0) pmx_tma_wait_read();
 }
 
 // ---------------------------------------------------------------------------
-// pass C: like pass A, inverse transform + attenuation + max reduction.  The running maximum stays in
-// registers across the tiles a CTA handles for one realization-column and is published (one atomicMax
-// per CTA) when the CTA moves on to another one.
+// pass C: rows like pass A: four-step twiddle, inverse transform over k1, attenuation, max reduction.  The
+// running maximum stays in registers across the tiles a CTA handles for one realization-column and is published
+// (one atomicMax per CTA) when the CTA moves on to another one.
 template <typename R, int L, int G, bool PF>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 2>;
     using W = PmxTw4<L>;
-    constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
+    constexpr int T = L / 8;
+    constexpr int LINES = G * L * PMX_SA_BYTES / 128;
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;
@@ -882,13 +888,14 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     unsigned char* aux0 = sm + S::AUX_OFF;
     unsigned char* sdone = sm + S::LIVE_OFF;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
+    const int rl = threadIdx.x / T, t = threadIdx.x % T;
+    const size_t N = (size_t)p.N1 * p.N2;
     PmxWalk wk;
     wk.ltpb = p.log2N2 - pmx_ilog2(G);
     wk.tpb_mask = (1 << wk.ltpb) - 1;
     wk.total = (p.batch * f.nfc) << wk.ltpb;
     wk.reverse = p.reverse;
     const int total = wk.total;
-    const int cl = threadIdx.x % G, t = threadIdx.x / G;
 
     auto live = [&](int tl) {
         while (tl < total) {
@@ -899,16 +906,18 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         }
         return tl;
     };
-    auto issue = [&](int tl, int buf) {
+    // a tile = G adjacent rows of the [N2][N1] time-domain matrix = G*L contiguous Sa
+    auto issue = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
         pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
-        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
-        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
+        for (int l0 = 0; l0 < LINES; l0 += 256)
+            pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
         pmx_bulk_load(a, &p.pkg[b_], S::PKG_BYTES, mbar);
-        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)c0 * W::PER, S::TAB_BYTES, mbar);
+        pmx_bulk_load(a + S::PKG_BYTES, reinterpret_cast<const cpx*>(p.tw4) + (size_t)row0 * W::PER, S::TAB_BYTES, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -924,7 +933,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     unsigned long long vmax = 0ull;  // running max of this thread for the current realization-column
     PMX_T_DECL
     while (tile < total) {
-        const int tt = wk.phys(tile), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
+        const int tt = wk.phys(tile), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
@@ -937,12 +946,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         phase ^= 1u;
         PMX_T_MARK(1)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
-        }
+        for (int q = 0; q < 8; ++q) lds_sa(in, pmx_swz<7>((uint32_t)((rl * L + t + q * T) * PMX_SA_BYTES)), x[q], y[q]);
         {   // Pass B left v = conj(z), z = its transform output before the four-step twiddle W_N^(-n2*k1), k1 = t + q*T.
             // The inverse transform over k1 = conj o forward o conj applied to conj(z)*conj(W): its input is z*W.
-            const cpx* tb = gtab + cl * W::PER;
+            const cpx* tb = gtab + rl * W::PER;
             const cpx wl = tb[t & (W::NLO - 1)];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -952,43 +959,35 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
             }
         }
         const real sc = (real)st->scale, nsc = -sc;
-        if (threadIdx.x == 0) pmx_tma_wait_read();
         __syncthreads();
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
         PMX_T_MARK(2)
-        cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
+        cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
         CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
-        unsigned char* outb = reinterpret_cast<unsigned char*>(work);
+        if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+        {
+            cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)(row0 + rl) * L) * 2;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            x[q] = mkc(x[q].x * sc, x[q].y * nsc);
-            y[q] = mkc(y[q].x * sc, y[q].y * nsc);
-            unsigned long long key = pmx_pow_key((double)power_ref(x[q], y[q]));
-            vmax = key > vmax ? key : vmax;
-            sts_sa(outb, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
-        }
-        PMX_T_MARK(5)
-        pmx_fence_proxy_async();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_store_3d(&tmap, c0 * 4, r0, p.bc0 + bc, outb + r0 * PITCH);
-            pmx_tma_commit();
-            if (!PF && next < total) {
-                pmx_tma_wait_read();
-                issue(next, (it + 1) & 1);
+            for (int q = 0; q < 8; ++q) {
+                x[q] = mkc(x[q].x * sc, x[q].y * nsc);
+                y[q] = mkc(y[q].x * sc, y[q].y * nsc);
+                unsigned long long key = pmx_pow_key((double)power_ref(x[q], y[q]));
+                vmax = key > vmax ? key : vmax;
+                st_sa(base + (size_t)(t + q * T) * 2, x[q], y[q]);
             }
         }
+        PMX_T_MARK(5)
         if (next >= total || (wk.phys(next) >> wk.ltpb) != bc) {  // moving on: publish the maximum (pmx_k_ctl consumes it)
             pmx_block_max(vmax, sred, &p.ctl[b], col);
             vmax = 0ull;
         }
         tile = next;
         ++it;
+        __syncthreads();  // everyone is done with this tile's auxiliary buffer
         PMX_T_MARK(6)
     }
     PMX_T_FLUSH(2)
-    if (threadIdx.x == 0) pmx_tma_wait_read();
 }
