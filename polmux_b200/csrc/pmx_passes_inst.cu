@@ -22,7 +22,10 @@ constexpr int GAC = PMX_GAC;
 constexpr int GB = (PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4)) * (L / 8) > 1024) ? 1 : PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4));
 constexpr int TILE_CAP = 32 * 1024;
 #ifndef PMX_PFAC
-constexpr bool PFAC = (GAC * L * PMX_SA_BYTES <= TILE_CAP);
+// Since passes A and C read and write contiguous rows straight from / to registers they no longer stage a
+// tile for a TMA store, and a fourth resident CTA (the tile lands in the exchange buffer, 42 KB per CTA) beats a
+// separate prefetch buffer with three (measured 49.0 against 50.3 ps per Sa and step at N = 2^20).
+constexpr bool PFAC = false;
 #else
 constexpr bool PFAC = (PMX_PFAC != 0) && (GAC * L * PMX_SA_BYTES <= TILE_CAP);
 #endif
