@@ -111,6 +111,8 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
         c->bmode = (first ? PMX_BM_ENTRY_R : (nmem ? 0 : PMX_BM_ENTRY_C)) | (c->state == PMX_ST_LAST ? PMX_BM_EXIT_R : 0);
     else
         c->bmode = PMX_BM_ENTRY_R | PMX_BM_EXIT_R;
+    // largest nonlinear phase of the step: gam*leff*max|u|^2 (the CNLSE rotation angle is at most a third of it)
+    if (f.spm && !f.xpm && pmax * c->leff < 0.015625) c->bmode |= PMX_BM_NL_SMALL;
     if (f.disp_scalar && f.pmd) {
         double s, cs;
         sincos(-(0.5 * f.dgdrms * f.domega * dzb_first / lcorr), &s, &cs);
@@ -190,7 +192,7 @@ static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst
         g->db0_last = (f.pmd && ntrunk > 0) ? plg[ntrunk - 1].db0 : 0.0;
         g->ntrunk = ntrunk;
         g->n_first = n_first;
-        g->bmode = f.pmd ? c->bmode : 0;
+        g->bmode = f.pmd ? c->bmode : (c->bmode & PMX_BM_NL_SMALL);
     }
     if (!f.pmd || ntrunk <= 0) return;
     if (threadIdx.x >= 32 && threadIdx.x < 40) {  // entry matrix
@@ -494,9 +496,15 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         } else if (f.spm) {
             const real gamleff = (real)__dmul_rn(f.gam[col], st->leff);
             const real ngl = -gamleff;
+            const bool nl_small = (st->bmode & PMX_BM_NL_SMALL) != 0;  // uniform for the tile
             cpx e[8];
+            if (nl_small) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) e[q] = pmx_cis_r(R_MUL(ngl, power_ref(x[q], y[q])));
+                for (int q = 0; q < 8; ++q) e[q] = pmx_cis_small(R_MUL(ngl, power_ref(x[q], y[q])));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) e[q] = pmx_cis_r(R_MUL(ngl, power_ref(x[q], y[q])));
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 x[q] = cmul(x[q], e[q]);
@@ -506,7 +514,8 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const real s3 = (real)2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
-                    e[q] = pmx_cis_r(R_MUL(gamleff, s3) / (real)3.0);
+                    const real a3 = R_MUL(gamleff, s3) / (real)3.0;
+                    e[q] = nl_small ? pmx_cis_small(a3) : pmx_cis_r(a3);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
