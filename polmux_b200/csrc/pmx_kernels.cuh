@@ -881,8 +881,13 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
 // pass C: rows like pass A: four-step twiddle, inverse transform over k1, attenuation, max reduction.  The
 // running maximum stays in registers across the tiles a CTA handles for one realization-column and is published
 // (one atomicMax per CTA) when the CTA moves on to another one.
+#ifdef PMX_C_CTAS
+#define PMX_MINB_C(threads, pf) (((PMX_C_CTAS * 128 * (32 / PMX_SA_BYTES)) / (threads)) > 0 ? ((PMX_C_CTAS * 128 * (32 / PMX_SA_BYTES)) / (threads)) : 1)
+#else
+#define PMX_MINB_C(threads, pf) PMX_MINB(threads, pf)
+#endif
 template <typename R, int L, int G, bool PF>
-__global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
+__global__ void __launch_bounds__(G*(L / 8), PMX_MINB_C(G*(L / 8), PF))
     pmx_k_passC(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 2>;
     using W = PmxTw4<L>;
