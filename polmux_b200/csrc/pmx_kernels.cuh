@@ -437,10 +437,14 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     // a tile = G adjacent rows of the [N2][N1] time-domain matrix = G*L contiguous Sa
     auto issue = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
-        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         const int tt = wk.phys(tl), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
+#ifdef PMX_AC_LDG
+        pmx_mbar_expect_tx(mbar, S::AUX_BYTES);
+#else
+        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         for (int l0 = 0; l0 < LINES; l0 += 256)
             pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, p.bc0 + bc, mbar);
+#endif
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
@@ -469,6 +473,17 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         const int next = live(tile + gridDim.x);
         cpx x[8], y[8];
         PMX_T_MARK(0)
+#ifdef PMX_AC_LDG
+        {   // the row is contiguous: 32 lanes x 32 B per load instruction, straight into registers
+            const cpx* src = reinterpret_cast<const cpx*>(p.field) + ((size_t)bc * N + (size_t)(row0 + rl) * L) * 2;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ld_sa(src + (size_t)(t + q * T) * 2, x[q], y[q]);
+        }
+        pmx_mbar_wait(mbar, phase);
+        phase ^= 1u;
+        __syncthreads();  // every thread has seen this phase complete before the barrier is armed again
+        if (threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+#else
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
         PMX_T_MARK(1)
@@ -476,6 +491,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         for (int q = 0; q < 8; ++q) lds_sa(in, pmx_swz<7>((uint32_t)((rl * L + t + q * T) * PMX_SA_BYTES)), x[q], y[q]);
         __syncthreads();
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+#endif
         PMX_T_MARK(2)
         // ---- nonlinear step, fiber.m:832-851
         if (f.scalar_field) {  // nl_step (fiber.m:786-803): u .* fastexp(-gam.*pow*leff), Y absent
@@ -531,7 +547,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         PMX_T_MARK(3)
         CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
+#ifndef PMX_AC_LDG
         if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);  // the exchange buffer is free again
+#endif
         // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the row's two-level table; straight to HBM (the row is
         // contiguous: 32 lanes x 32 B per store instruction)
         {
@@ -923,10 +941,14 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_C(G*(L / 8), PF))
     // a tile = G adjacent rows of the [N2][N1] time-domain matrix = G*L contiguous Sa
     auto issue = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
-        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         const int tt = wk.phys(tl), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
+#ifdef PMX_AC_LDG
+        pmx_mbar_expect_tx(mbar, S::AUX_BYTES);
+#else
+        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         for (int l0 = 0; l0 < LINES; l0 += 256)
             pmx_tma_load_3d(in + l0 * 128, &tmap, 0, (tt & wk.tpb_mask) * LINES + l0, p.bc0 + bc, mbar);
+#endif
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         unsigned char* a = aux0 + buf * S::AUX_BYTES;
@@ -956,11 +978,20 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_C(G*(L / 8), PF))
         const int next = live(tile + gridDim.x);
         cpx x[8], y[8];
         PMX_T_MARK(0)
+#ifdef PMX_AC_LDG
+        {
+            const cpx* src = reinterpret_cast<const cpx*>(p.field) + ((size_t)bc * N + (size_t)(row0 + rl) * L) * 2;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ld_sa(src + (size_t)(t + q * T) * 2, x[q], y[q]);
+        }
+#endif
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
         PMX_T_MARK(1)
+#ifndef PMX_AC_LDG
 #pragma unroll
         for (int q = 0; q < 8; ++q) lds_sa(in, pmx_swz<7>((uint32_t)((rl * L + t + q * T) * PMX_SA_BYTES)), x[q], y[q]);
+#endif
         {   // Pass B left v = conj(z), z = its transform output before the four-step twiddle W_N^(-n2*k1), k1 = t + q*T.
             // The inverse transform over k1 = conj o forward o conj applied to conj(z)*conj(W): its input is z*W.
             const cpx* tb = gtab + rl * W::PER;
@@ -973,15 +1004,21 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_C(G*(L / 8), PF))
             }
         }
         const real sc = (real)st->scale, nsc = -sc;
-        __syncthreads();
+        __syncthreads();  // every thread has seen this phase complete before the barrier is armed again
+#ifdef PMX_AC_LDG
+        if (threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+#else
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+#endif
         PMX_T_MARK(2)
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
         CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
+#ifndef PMX_AC_LDG
         if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+#endif
         {
             cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)(row0 + rl) * L) * 2;
 #pragma unroll
