@@ -153,7 +153,11 @@ int pmx_field_upload(pmx_devfield* f, const pmx_field* host, int32_t b0, int32_t
 int pmx_field_download(pmx_devfield* f, pmx_field* host, int32_t b0, int32_t nb);
 /* dst[b] = src[0] for all b (same Tx field for every realization). */
 int pmx_field_broadcast(pmx_devfield* dst, const pmx_devfield* src);
-/* raw device pointer of the interleaved (xr,xi,yr,yi) sample array */
+/* Raw device pointer of the interleaved (xr,xi,yr,yi) sample array (doubles, or floats for PMX_F32 fields).
+ * Layout inside a column: for nfft = 2^m in [2^12, 2^24] the samples are stored TRANSPOSED with respect to the
+ * four-step split N1 = 2^floor(m/2), N2 = nfft/N1 -- time sample n1*N2 + n2 at position n2*N1 + n1 -- so that the
+ * time-domain passes of the SSFM stream contiguous rows; other sizes are in natural order.  pmx_field_upload /
+ * pmx_field_download convert from / to time order. */
 void* pmx_field_device_ptr(pmx_devfield* f);
 
 /* Uploads betat/db1/plates, builds twiddle tables (cached in ctx by nfft). */
