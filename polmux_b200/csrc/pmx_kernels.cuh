@@ -240,7 +240,9 @@ template <int L, int GROUP>
 struct PmxSmem {
     static constexpr int BASE = 2 * L;
 #ifdef PMX_F32
-    static constexpr int OFF = (GROUP > 1) ? 2 : 0;  // FP32 exchanges float4 points: keep every region 16-byte aligned
+    // FP32 exchanges float4 points (16 B = two cpx): the GROUP regions a warp touches at once are offset by 128/GROUP
+    // bytes so that their lanes fall in different 16-byte bank groups (and every region stays 16-byte aligned)
+    static constexpr int OFF = (GROUP > 1) ? ((16 / GROUP) > 2 ? (16 / GROUP) : 2) : 0;
 #else
     static constexpr int OFF = (GROUP > 1) ? ((8 / GROUP) > 0 ? (8 / GROUP) : 1) : 0;
 #endif

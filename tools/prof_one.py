@@ -13,6 +13,7 @@ from polmux_b200 import _lib, synth  # noqa: E402
 from polmux_b200.fiber import fiber_setup, setup_to_desc  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+PREC = sys.argv[3] if len(sys.argv) > 3 else "f64"
 LG = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 nsymb, nt = 1 << (LG - 4), 16
 N = nsymb * nt
@@ -27,11 +28,12 @@ from polmux_b200 import mc  # noqa: E402
 d = [mc.draw_plates(1000 + b, bench.NPLATES) for b in range(B)]
 pl = [np.stack([x[i] for x in d]) for i in range(3)]
 ctx = _lib.Context(0)
-desc, keep = setup_to_desc(setup, batch=B, plate_sets=B, db0=pl[0], theta=pl[1], epsilon=pl[2])
+desc, keep = setup_to_desc(setup, batch=B, plate_sets=B, db0=pl[0], theta=pl[1], epsilon=pl[2], precision=PREC)
+PC = {'f64': _lib.PMX_F64, 'f32': _lib.PMX_F32}[PREC]
 plan = _lib.Plan(ctx, desc, keep)
-tx = _lib.DeviceField(ctx, N, 1, 1)
+tx = _lib.DeviceField(ctx, N, 1, 1, precision=PC)
 tx.upload(G.FIELDX, G.FIELDY)
-work = _lib.DeviceField(ctx, N, 1, B)
+work = _lib.DeviceField(ctx, N, 1, B, precision=PC)
 work.broadcast_from(tx)
 res = plan.execute(work)
 ctx.sync()
