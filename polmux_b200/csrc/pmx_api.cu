@@ -44,7 +44,15 @@ static inline cpx pmx_root(long long m, long long M) {  // exp(-2*pi*i*m/M) in l
     return make_double2((double)cosl(a), (double)(-sinl(a)));
 }
 
-void pmx_fill_stage_twiddles(int L, cpx* out) {
+void pmx_fill_stage_twiddles(int L, cpx* out, int layout) {
+    if (layout == 1) {  // L = 1024 as 8 * 16 * 8 (CtaFFT<R, 1024>): [15][8] of W_128^(k*r), then [3][128] of W_1024^(k*{1,2,4})
+        size_t o = 0;
+        for (int r = 1; r <= 15; ++r)
+            for (int k = 0; k < 8; ++k) out[o++] = pmx_root((long long)k * r, 128);
+        for (int r = 1; r <= 4; r *= 2)
+            for (int k = 0; k < 128; ++k) out[o++] = pmx_root((long long)k * r, 1024);
+        return;
+    }
     int ns = 1;
     size_t o = 0;
     while (ns < L) {
@@ -365,13 +373,14 @@ extern "C" void* pmx_ctx_stream(pmx_ctx* c) { return c ? (void*)c->stream : null
 extern "C" int64_t pmx_ctx_launch_count(const pmx_ctx* c) { return c ? c->launches : 0; }
 
 // ---------------------------------------------------------------------------
-static int get_stage_tw(pmx_ctx* c, int L, int precision, const void** dev) {
+static int get_stage_tw(pmx_ctx* c, const PmxLaunchTable* t, const void** dev) {
+    const int L = t->L, precision = t->precision;
     const int key = L + 65536 * precision;
     auto it = c->stage_tw.find(key);
     if (it == c->stage_tw.end()) {
-        int total = pmx_tw_total(L);
+        const int total = t->tw_total;
         std::vector<cpx> h((size_t)(total > 0 ? total : 1));
-        pmx_fill_stage_twiddles(L, h.data());
+        pmx_fill_stage_twiddles(L, h.data(), t->tw_layout);
         StageTw s;
         if (precision == PMX_F32) {  // same table, rounded once from the long-double values
             std::vector<float2> hf(h.size());
@@ -939,9 +948,9 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     rc = get_four_tw(c, p->d.nfft, p->tB, p->N1, &tw4B);  // pass B: one row per k1, W_N^(k1*n2), n2 < N2
     if (rc) return rc;
     const void *twA, *twB;
-    rc = get_stage_tw(c, p->N1, p->d.precision, &twA);
+    rc = get_stage_tw(c, p->tA, &twA);
     if (rc) return rc;
-    rc = get_stage_tw(c, p->N2, p->d.precision, &twB);
+    rc = get_stage_tw(c, p->tB, &twB);
     if (rc) return rc;
     PassParams pA = pa, pB = pa;
     pA.tw_stage = twA;

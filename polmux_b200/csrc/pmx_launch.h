@@ -12,6 +12,7 @@ struct PmxLaunchTable {
     int threadsAC, threadsB;
     size_t smemAC, smemB;
     int tw_total;  // cpx entries of the stage-twiddle table for this L
+    int tw_layout; // 0: first stage 2/4/8 then radix-8 stages; 1: L = 1024 as 8 * 16 * 8 (pmx_fft.cuh)
     int tw4_lo_bits, tw4_per;  // four-step twiddle row layout (PmxTw4<L>)
     int precision;             // 0 = FP64, 1 = FP32 (pmx_precision)
     int cpx_bytes;             // sizeof one complex number of that precision
@@ -31,4 +32,4 @@ struct PmxLaunchTable {
 const PmxLaunchTable* pmx_get_table(int L, int precision = 0);  // nullptr if L is not built
 
 // Host: fill the stage-twiddle table of length L (layout documented in pmx_fft.cuh).
-void pmx_fill_stage_twiddles(int L, cpx* out);
+void pmx_fill_stage_twiddles(int L, cpx* out, int layout);

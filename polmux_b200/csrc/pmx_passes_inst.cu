@@ -90,5 +90,5 @@ void fill_tw4(void* tab, int rows, double two_over_N, cudaStream_t s) {
 #endif
 extern const PmxLaunchTable PMX_TABLE_NAME = {
     L, GAC, GB, PFAC ? 1 : 0, PFB ? 1 : 0, SA::THREADS, SB::THREADS, (size_t)SA::TOTAL, (size_t)SB::TOTAL,
-    pmx_tw_total(L), PmxTw4<L>::LO, PmxTw4<L>::PER, PMX_PRECISION, (int)sizeof(cpx),
+    pmx_tw_total(L), pmx_tw_layout(L), PmxTw4<L>::LO, PmxTw4<L>::PER, PMX_PRECISION, (int)sizeof(cpx),
     setup, passA, passB, passC, init_max, fill_tw4, xpm_sum};
