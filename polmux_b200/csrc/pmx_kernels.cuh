@@ -874,6 +874,17 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         PMX_T_MARK(5)
         // the second transform was run on conj(spectrum): conj(result) is the inverse transform.  Its four-step
         // twiddle W_N^(-n2*k1) is applied by pass C when it loads the sample (pass C has FP64 slots to spare).
+#ifdef PMX_B_STG
+        // direct scattered stores (one 32-byte sector per lane): the exchange buffer is free for the next tile's load
+        // as soon as the last exchange is read out
+        if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+        {
+            cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)k1) * 2;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) st_sa(base + (size_t)(t + q * T) * p.N1 * 2, cconj(x[q]), cconj(y[q]));
+        }
+        __syncthreads();  // everyone is done with this tile's auxiliary buffer and plate chunk
+#else
         // The column tile is staged (same swizzled layout as it landed) in the exchange buffer and TMA-stored.
         unsigned char* outb = reinterpret_cast<unsigned char*>(work);
 #pragma unroll
@@ -889,6 +900,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                 issue(next, (it + 1) & 1);
             }
         }
+#endif
         tile = next;
         ++it;
         PMX_T_MARK(6)
