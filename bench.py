@@ -39,9 +39,9 @@ NSPAN, SPAN_KM, NPLATES, DGD = 10, 80.0, 100, 0.1
 GAIN_DB, NF_DB = 16.0, 5.0
 ALG_BYTES_PER_SA_STEP = 192.0   # 3 passes x (read + write) x 32 B   
 # dram__bytes_read.sum + dram__bytes_write.sum per Sa of a launch, from the ncu --set full capture summarised in
-# profiles/r1_ncu_v11_summary.txt (4 realizations of 2^20 Sa per launch): pass A (135.7+76.0) MB, B (134.3+85.5) MB,
-# C (135.5+76.1) MB  ->  bytes per Sa; below the 64 algorithmic bytes because part of the writes stays in L2
-NCU_DRAM_BYTES_PER_SA = {'passA': 211.7e6 / (4 << 20), 'passB': 219.8e6 / (4 << 20), 'passC': 211.6e6 / (4 << 20)}
+# profiles/r1_ncu_v13_summary.txt (4 realizations of 2^20 Sa per launch): pass A (135.9+76.8) MB, B (134.3+82.7) MB,
+# C (135.8+75.6) MB  ->  bytes per Sa; below the 64 algorithmic bytes because part of the writes stays in L2
+NCU_DRAM_BYTES_PER_SA = {'passA': 212.7e6 / (4 << 20), 'passB': 217.0e6 / (4 << 20), 'passC': 211.4e6 / (4 << 20)}
 CPU_SAMPLE_KM = 16.0            # bounded CPU sample: first 16 km (20 plates of 800 m) of span 1
 
 
@@ -265,7 +265,7 @@ def main():
         ach = alg_bytes / (pms[dom] * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'kernel': names[dom], 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach / peak, 'traffic': NCU_DRAM_BYTES_PER_SA[names[dom]] * prof_sa_steps / float(pn[dom]),
-                'traffic_source': 'ncu --set full, profiles/r1_ncu_v11_summary.txt, scaled to the Sa of a launch',
+                'traffic_source': 'ncu --set full, profiles/r1_ncu_v13_summary.txt, scaled to the Sa of a launch',
                 'peak_source': peak_src,
                 'bytes_per_launch': alg_bytes / float(pn[dom]), 'ms_per_launch': pms[dom] / float(pn[dom]),
                 'launches_timed': int(pn[dom]),
