@@ -984,6 +984,10 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
         }
     static const int stagB = getenv("PMX_STAGGER_B") ? atoi(getenv("PMX_STAGGER_B")) : 0;
     static const int stagAC = getenv("PMX_STAGGER_AC") ? atoi(getenv("PMX_STAGGER_AC")) : 0;
+    // programmatic dependent launch pays when nothing else fills the gap between two kernels of a stream, i.e. with a
+    // single realization group (a batch of one: the reference-style fiber() call); PMX_PDL=0/1 overrides
+    static const int pdl_env = getenv("PMX_PDL") ? atoi(getenv("PMX_PDL")) : -1;
+    const int use_pdl = (pdl_env >= 0) ? pdl_env : (ngroups == 1 && !c->profile && !p->fc.xpm ? 1 : 0);
     struct Grp {
         cudaStream_t st;
         PassParams pA, pB, pc;
@@ -1011,6 +1015,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
             q->batch = G.nb;
             q->bc0 = b0 * nfc;
             q->stagger = (q == &G.pB) ? stagB : stagAC;
+            q->pdl = use_pdl;
         }
         const int tilesAC = (p->N2 / p->tA->gAC) * G.nb * nfc, tilesB = (p->N1 / p->tB->gB) * G.nb * nfc;
         G.gA = std::min(tilesAC, (int)(std::max(1, oA.a / grid_div) * c->sm_count * grid_mul));
@@ -1040,7 +1045,20 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
                 { ProfScope ps(c, 1); p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_cols); }
                 G.pA.reverse = serp ? (rev[gi] ^= 1) : 0;
                 { ProfScope ps(c, 2); p->tA->passC(G.gC, G.st, G.pA, G.fc, fld->map_rows); }
-                pmx_k_ctl<<<G.nb, 128, 0, G.st>>>(G.pc, G.fc, 0);
+                if (use_pdl) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(G.nb);
+                    cfg.blockDim = dim3(128);
+                    cfg.stream = G.st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    cudaLaunchKernelEx(&cfg, pmx_k_ctl, G.pc, G.fc, 0);
+                } else {
+                    pmx_k_ctl<<<G.nb, 128, 0, G.st>>>(G.pc, G.fc, 0);
+                }
                 c->launches += 4;
             }
             if (c->profile && c->ev_used > 4096) prof_collect(c);

@@ -169,6 +169,10 @@ static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst
     StepCtl* c = &p.ctl[b];
     StepPkg* g = &p.pkg[b];
     __shared__ int s_go;
+    if (p.pdl) {
+        pmx_pdl_launch_dependents();
+        pmx_pdl_wait();
+    }
     if (threadIdx.x == 0) {
         const int go = first || c->state < PMX_ST_DONE;
         if (go) pmx_ctl_next(c, f, first != 0, b, p.trace_dz, p.trace_ntrunk);
@@ -458,6 +462,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_fence_mbar_init();
     }
     pmx_load_stage_tw<L>(stw, p.tw_stage);
+    if (p.pdl) {  // everything above is independent of the previous kernel of the stream
+        pmx_pdl_launch_dependents();
+        pmx_pdl_wait();
+    }
     pmx_cache_live(sdone, p);
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;
@@ -642,6 +650,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         pmx_fence_mbar_init();
     }
     pmx_load_stage_tw<L>(stw, p.tw_stage);
+    if (p.pdl) {  // everything above is independent of the previous kernel of the stream
+        pmx_pdl_launch_dependents();
+        pmx_pdl_wait();
+    }
     pmx_cache_live(sdone, p);
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;
@@ -974,6 +986,10 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_C(G*(L / 8), PF))
         pmx_fence_mbar_init();
     }
     pmx_load_stage_tw<L>(stw, p.tw_stage);
+    if (p.pdl) {  // everything above is independent of the previous kernel of the stream
+        pmx_pdl_launch_dependents();
+        pmx_pdl_wait();
+    }
     pmx_cache_live(sdone, p);
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;

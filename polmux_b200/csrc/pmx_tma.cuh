@@ -50,6 +50,10 @@ __device__ __forceinline__ void pmx_tma_load_3d(void* dst, const CUtensorMap* ma
         ::"r"(pmx_smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(pmx_smem_u32(bar))
         : "memory");
 }
+// Programmatic dependent launch: let the next kernel of the stream be scheduled early / wait for the previous one.
+__device__ __forceinline__ void pmx_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pmx_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // contiguous global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned)
 __device__ __forceinline__ void pmx_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
