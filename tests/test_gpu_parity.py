@@ -110,3 +110,46 @@ def test_plate_index_error():
     with pytest.raises(pmx.PolmuxError) as e:
         pmx.fiber(fib, 'gp--', rng=np.random.Generator(np.random.PCG64(1)))
     assert e.value.code == -4
+
+
+def test_batch_of_realizations_matches_oracle_each(disp_mode):
+    """A resident batch (5 realizations, own plate draw each; run as two realization groups on two streams,
+    ragged step counts) against one oracle run per realization: field <= 1e-10, ncycle equal."""
+    from polmux_b200 import _lib, mc
+    from polmux_b200.fiber import fiber_setup, setup_to_desc
+    nsymb, nt, batch = 1 << 10, 16, 5
+    n = nsymb * nt
+    fib = base_fiber(length=6e4, dgd=0.4, nplates=12, manakov='yes')
+    gs0 = make_tx(nsymb, nt)
+    G = pmx.GSTATE
+    setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
+    draws = [mc.draw_plates(2000 + b, setup.nplates) for b in range(batch)]
+    pl = [np.stack([d[i] for d in draws]) for i in range(3)]
+    ctx = _lib.default_context()
+    desc, keep = setup_to_desc(setup, batch=batch, plate_sets=batch, db0=pl[0], theta=pl[1], epsilon=pl[2])
+    plan = _lib.Plan(ctx, desc, keep)
+    tx = _lib.DeviceField(ctx, n, 1, 1)
+    # realization b gets the Tx field scaled by (1 + b/10): different peak power -> different step schedule
+    work = _lib.DeviceField(ctx, n, 1, batch)
+    xs = np.stack([(1 + b / 10) * np.asarray(G.FIELDX).T for b in range(batch)])
+    ys = np.stack([(1 + b / 10) * np.asarray(G.FIELDY).T for b in range(batch)])
+    work.upload(xs, ys)
+    res = plan.execute(work)
+    gx, gy = work.download()
+    ncycles = []
+    for b in range(batch):
+        gs = make_tx(nsymb, nt)
+        gs.FIELDX = gs.FIELDX * (1 + b / 10)
+        gs.FIELDY = gs.FIELDY * (1 + b / 10)
+        f = dict(fib)
+        f.update(db0=draws[b][0], theta=draws[b][1], epsilon=draws[b][2])
+        # user-given plates go through the PMF branch: dgdrms = dgd/nplates there, sqrt(3*pi/8)*dgd/sqrt(nplates) for
+        # random plates (fiber.m:269 vs :277, SURVEY 8c): rescale the DGD so that both sides see the same dgdrms
+        f['dgd'] = np.sqrt(3 * np.pi / 8) * fib['dgd'] * np.sqrt(setup.nplates)
+        orc.fiber(gs, f, 'gps-')
+        err = rel_l2(gx[b].T, gy[b].T, gs.FIELDX, gs.FIELDY)
+        assert err < TOL, (b, err)
+        assert int(res.ncycle[b]) == gs.log['ncycle']
+        ncycles.append(gs.log['ncycle'])
+    assert len(set(ncycles)) > 1   # the batch really is ragged
+    tx.close() if hasattr(tx, 'close') else None
