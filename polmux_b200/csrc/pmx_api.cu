@@ -973,7 +973,11 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     // Realization groups.  The batch is split into groups that run on their own streams with full-size persistent
     // grids: while the last CTAs of one group's pass drain (tile-count quantisation, stragglers, the launch gap and
     // the one-CTA-per-realization step control), the other group's pass already fills the freed SM slots.
-    static const int want_groups = getenv("PMX_GROUPS") ? atoi(getenv("PMX_GROUPS")) : 2;
+    static const int env_groups = getenv("PMX_GROUPS") ? atoi(getenv("PMX_GROUPS")) : 0;
+    // two groups pay once a pass has more than about two rounds of tiles; below that a single group with
+    // programmatic dependent launches (prologue of the next kernel under the tail of the current one) is faster
+    const long tiles_all = (long)(p->N2 / p->tA->gAC) * batch * nfc;
+    const int want_groups = env_groups ? env_groups : (tiles_all > 2L * c->sm_count * oA.a ? 2 : 1);
     const int ngroups = c->profile ? 1 : std::max(1, std::min(std::min(want_groups, 4), batch));
     static const double grid_mul = getenv("PMX_GRID_MUL") ? atof(getenv("PMX_GRID_MUL")) : 1.0;  // tuning knob
     for (int g = 1; g < ngroups; ++g)
