@@ -1,7 +1,7 @@
 """Accuracy of the CUDA path vs the oracle on a few cases (prints rel-L2 and step-length deviation)."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this script lives in tests/: it uses the oracle as checker)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import oracle.fiber_oracle as orc
 import polmux_b200 as pmx
