@@ -1,12 +1,14 @@
 // The three HBM passes of one SSFM step (fiber.m:518-537 per iteration) and the
 // device-side step control (nextstep fiber.m:693-715, checkstep :739-758).
+// The resident field is stored transposed in time (sample n1*N2 + n2 at n2*N1 + n1), see pass A below.
 //
-//   pass A  columns: NL step (matrix_nl_step :827-851) -> FFT over n1 -> W_N^(n2*k1)
-//   pass B  rows   : FFT over n2 -> per-bin Jones/dispersion product over the step's
-//                    trunks (matrix_step :907-933) -> IFFT over k2 -> conj twiddle
-//   pass C  columns: IFFT over k1 -> 1/N * exp(-alpha/2 dz) (:531-532) ->
-//                    max |u|^2 (warp shuffle + one atomicMax per CTA and realization)
-//   ctl     one thread per realization: nextstep + checkstep for the next step
+//   pass A  rows    : NL step (matrix_nl_step :827-851, or nl_step :786-803 on the scalar path) -> FFT over n1
+//                     -> four-step twiddle W_N^(n2*k1)
+//   pass B  columns : FFT over n2 -> per-bin Jones/dispersion product over the step's trunks
+//                     (matrix_step :907-933) -> IFFT over k2
+//   pass C  rows    : W_N^(-n2*k1) -> IFFT over k1 -> 1/N * exp(-alpha/2 dz) (:531-532) ->
+//                     max |u|^2 (warp shuffle + one atomicMax per CTA and realization)
+//   ctl     one CTA per realization: nextstep + checkstep for the next step, step package for the passes
 #pragma once
 #include "pmx_fft.cuh"
 #include "pmx_tma.cuh"

@@ -3,9 +3,10 @@
 //
 // Tiles are described by 3-D tensor maps over the resident field buffer
 // (cuTensorMapEncodeTiled, built on the host in pmx_api.cu):
-//   rows map   {16 doubles (128 B line), N/4 lines, batch*nfc}   pass B, SWIZZLE_128B
-//   cols map   {N2*4 doubles, N1 rows (pitch N2*32 B), batch*nfc} passes A and C,
-//              box {G*4 doubles, <=256 rows, 1}, swizzle = box pitch (32/64/128 B)
+// (the field is an [N2][N1] matrix of Sa per realization-column, see pmx_kernels.cuh; FP32 fields: floats, 16-byte Sa)
+//   rows map   {128-byte line, N*SA/128 lines, batch*nfc}, SWIZZLE_128B            passes A and C (contiguous rows)
+//   cols map   {N1*4 reals, N2 rows (pitch N1*SA bytes), batch*nfc}                 pass B (columns k1),
+//              box {G*4 reals, <=256 rows, 1}, swizzle = box pitch (32/64/128 B)
 // The swizzle makes the thread-per-Sa reads of the landed tile bank-conflict free:
 // physical offset = off ^ (((off >> 7) & (pitch/16 - 1)) << 4)  (CuTe Swizzle<B,4,3>).
 #pragma once
