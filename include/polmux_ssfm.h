@@ -211,6 +211,24 @@ int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pa
 int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t nsymb, int32_t nt,
                    int64_t* counts_dev);
 
+/* ---- building blocks of the local-error adaptive step (scalar path only) -------------------------
+ * scalar_a_ssfm / adaptssfm, fiber.m:639-679,938-1010: one symmetric step against two half steps, local error
+ * max|u - uh|/dz, Richardson extrapolation 4/3*uh - 1/3*u, step proposal safety*sqrt(err/est_err)*dz.  The loop itself
+ * is host logic (polmux_b200/fiber.py, as it is interpreter code in the reference); the field never leaves the
+ * device.  FP64 fields, X polarization (the scalar path has no Y).
+ *   pmx_scalar_nl_exec : u_k <- u_k .* fastexp(-gam_k .* pow * leff) * atten   nl_step (:786-803, pow with the
+ *                        SPM / XPM rules of :792-799) followed by u*exp(-halfalpha*dz) (:971,976,...)
+ *   pmx_plan_set_length: a plan of a linear flag ('g---': one step) then applies lin_step(betat*length, u) (:762-773)
+ *   pmx_field_max_power: umax[b*nfc+c] = max_n |ux|^2 + |uy|^2 (nextstep's Umax, :693-698)
+ *   pmx_field_maxdiff2 : *out = max over samples and columns of |a - b|^2 of the X polarization (:996)
+ *   pmx_field_lincomb  : dst <- ca*a - cb*b (X and Y), products rounded separately as the interpreter does (:1003) */
+int pmx_scalar_nl_exec(pmx_ctx* ctx, pmx_devfield* f, const double* gam, double leff, double atten, int32_t spm,
+                       int32_t xpm);
+int pmx_plan_set_length(pmx_plan* plan, double length);
+int pmx_field_max_power(pmx_ctx* ctx, pmx_devfield* f, double* umax);
+int pmx_field_maxdiff2(pmx_ctx* ctx, pmx_devfield* a, pmx_devfield* b, double* out);
+int pmx_field_lincomb(pmx_ctx* ctx, pmx_devfield* dst, double ca, pmx_devfield* a, double cb, pmx_devfield* b);
+
 #ifdef __cplusplus
 }
 #endif

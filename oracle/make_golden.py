@@ -116,3 +116,8 @@ if __name__ == '__main__':
     run_case('scalar_sep3_gsx', 256, 16, 3, 'sepfields', fib(length=3e4, slope=0.057), 'g-sx', two_pol=False, want_brf=False)
     run_case('scalar_sep3_xonly', 256, 16, 3, 'sepfields', fib(length=2e4, slope=0.057), 'g--x', two_pol=False, want_brf=False)
     run_case('scalar_spm_exact', 256, 16, 1, 'unique', fib(length=5e4), '--s-', two_pol=False, want_brf=False)
+    # local-error adaptive step (x.ltol -> scalar_a_ssfm / adaptssfm, fiber.m:639-679,938-1010): 24 accepted and 4
+    # rejected steps in the first case
+    run_case('scalar_ltol_gs', 256, 16, 1, 'unique', fib(length=3e4, ltol=1e-6), 'g-s-', two_pol=False, want_brf=False)
+    run_case('scalar_ltol_sep3_gsx', 256, 16, 3, 'sepfields', fib(length=2e4, ltol=2e-6, slope=0.057), 'g-sx', two_pol=False,
+             want_brf=False)

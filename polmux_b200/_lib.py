@@ -28,7 +28,8 @@ EXPORTS = [
     'pmx_field_upload', 'pmx_field_download', 'pmx_field_broadcast', 'pmx_field_device_ptr',
     'pmx_plan_create', 'pmx_plan_destroy', 'pmx_plan_set_plates', 'pmx_fiber_exec',
     'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
-    'pmx_ctx_profile_read', 'pmx_qpsk_count',
+    'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
+    'pmx_field_maxdiff2', 'pmx_field_lincomb',
 ]
 
 
@@ -108,6 +109,11 @@ def load():
     lib.pmx_ampliflat_exec.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64]
     lib.pmx_count_errors.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     lib.pmx_qpsk_count.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp]
+    lib.pmx_scalar_nl_exec.argtypes = [vp, vp, _dp, C.c_double, C.c_double, C.c_int32, C.c_int32]
+    lib.pmx_plan_set_length.argtypes = [vp, C.c_double]
+    lib.pmx_field_max_power.argtypes = [vp, vp, _dp]
+    lib.pmx_field_maxdiff2.argtypes = [vp, vp, vp, _dp]
+    lib.pmx_field_lincomb.argtypes = [vp, vp, C.c_double, vp, C.c_double, vp]
     _lib = lib
     return lib
 
@@ -326,6 +332,10 @@ class Plan:
         a, b, c = _f64(db0).reshape(-1), _f64(theta).reshape(-1), _f64(epsilon).reshape(-1)
         self.ctx.check(self.ctx.lib.pmx_plan_set_plates(self.h, plate_sets, _ptr(a), _ptr(b), _ptr(c)))
 
+    def set_length(self, length: float):
+        """one-step (linear-flag) plans: the next execute applies lin_step(betat*length, u)"""
+        self.ctx.check(self.ctx.lib.pmx_plan_set_length(self.h, float(length)))
+
     def execute(self, field: DeviceField, trace_cap=0) -> Result:
         res = Result(field.batch, trace_cap)
         self.ctx.check(self.ctx.lib.pmx_fiber_exec(self.h, field.h, C.byref(res.c)))
@@ -341,6 +351,30 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+def scalar_nl_exec(ctx: Context, field: DeviceField, gam, leff: float, atten: float, spm: bool, xpm: bool):
+    """nl_step (fiber.m:786-803) followed by the attenuation factor of the same sub-step"""
+    g = _f64(np.atleast_1d(gam))
+    ctx.check(ctx.lib.pmx_scalar_nl_exec(ctx.h, field.h, _ptr(g), float(leff), float(atten), int(bool(spm)), int(bool(xpm))))
+
+
+def field_max_power(ctx: Context, field: DeviceField) -> np.ndarray:
+    """max_n |ux|^2 + |uy|^2 per realization and column -> [batch, nfc] (nextstep's Umax, fiber.m:693-698)"""
+    out = np.zeros(field.batch * field.nfc)
+    ctx.check(ctx.lib.pmx_field_max_power(ctx.h, field.h, _ptr(out)))
+    return out.reshape(field.batch, field.nfc)
+
+
+def field_maxdiff2(ctx: Context, a: DeviceField, b: DeviceField) -> float:
+    out = np.zeros(1)
+    ctx.check(ctx.lib.pmx_field_maxdiff2(ctx.h, a.h, b.h, _ptr(out)))
+    return float(out[0])
+
+
+def field_lincomb(ctx: Context, dst: DeviceField, ca: float, a: DeviceField, cb: float, b: DeviceField):
+    """dst <- ca*a - cb*b"""
+    ctx.check(ctx.lib.pmx_field_lincomb(ctx.h, dst.h, float(ca), a.h, float(cb), b.h))
 
 
 def ampliflat_exec(ctx: Context, field: DeviceField, gain: float, sigma, noise=None, seed=0):

@@ -1339,3 +1339,165 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
     CK(c, cudaStreamSynchronize(c->stream));  // `sym` is a host buffer of the caller
     return PMX_OK;
 }
+
+// ---------------------------------------------------------------------------
+// building blocks of the local-error adaptive step (scalar path, fiber.m:639-679,938-1010); FP64
+__global__ void __launch_bounds__(256) pmx_k_scalar_nl(cpx* field, size_t N, int nfc, const double* gam /*[nfc], device*/,
+                                                       double leff, double atten, int spm, int xpm) {
+    const int b = blockIdx.y;
+    cpx* fld = field + (size_t)b * nfc * N * 2;
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+        double sum = 0.0;
+        if (xpm)
+            for (int k = 0; k < nfc; ++k) {  // sum(pow,2)
+                const cpx x = fld[((size_t)k * N + n) * 2];
+                sum = __dadd_rn(sum, __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y)));
+            }
+        for (int k = 0; k < nfc; ++k) {
+            cpx x = fld[((size_t)k * N + n) * 2];
+            if (spm || xpm) {
+                double pw = __dadd_rn(__dmul_rn(x.x, x.x), __dmul_rn(x.y, x.y));
+                if (xpm) pw = spm ? __dadd_rn(__dmul_rn(2.0, sum), -pw) : __dmul_rn(2.0, __dadd_rn(sum, -pw));
+                double sn, cs;
+                pmx_sincos_fast(__dmul_rn(__dmul_rn(-gam[k], pw), leff), &sn, &cs);
+                x = cmul(x, make_double2(cs, sn));
+            }
+            fld[((size_t)k * N + n) * 2] = make_double2(__dmul_rn(x.x, atten), __dmul_rn(x.y, atten));
+        }
+    }
+}
+
+static int need_f64(pmx_ctx* c, const pmx_devfield* f, const char* who) {
+    if (!c || !f) return set_err(c, PMX_ERR_INVALID, "%s: null argument", who);
+    if (f->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "%s: FP64 fields only", who);
+    return PMX_OK;
+}
+
+extern "C" int pmx_scalar_nl_exec(pmx_ctx* c, pmx_devfield* f, const double* gam, double leff, double atten, int32_t spm,
+                                  int32_t xpm) {
+    int rc = need_f64(c, f, "pmx_scalar_nl_exec");
+    if (rc) return rc;
+    if (!gam) return set_err(c, PMX_ERR_INVALID, "pmx_scalar_nl_exec: gam is required");
+    CK(c, cudaSetDevice(c->device));
+    double* dg = nullptr;
+    CK(c, cudaMallocAsync(&dg, f->nfc * sizeof(double), c->stream));
+    CK(c, cudaMemcpyAsync(dg, gam, f->nfc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dim3 g((unsigned)std::min<size_t>(((size_t)f->nfft + 255) / 256, 148 * 8), f->batch);
+    pmx_k_scalar_nl<<<g, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->nfc, dg, leff, atten, spm, xpm);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaFreeAsync(dg, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));  // gam is a host buffer of the caller
+    return PMX_OK;
+}
+
+extern "C" int pmx_plan_set_length(pmx_plan* p, double length) {
+    if (!p) return set_err(nullptr, PMX_ERR_INVALID, "null plan");
+    if (!(length > 0)) return set_err(p->ctx, PMX_ERR_INVALID, "length must be > 0");
+    if (!p->single_step) return set_err(p->ctx, PMX_ERR_INVALID, "pmx_plan_set_length: only for plans of a one-step (linear) flag");
+    p->d.length = length;
+    p->d.dzmaxt = length;
+    p->fc.Lf = length;
+    p->fc.dzmax = length;
+    p->fc.lcorr = length / p->d.nplates;
+    return PMX_OK;
+}
+
+__global__ void __launch_bounds__(256) pmx_k_max_power(const cpx* field, size_t N, unsigned long long* out) {
+    const int bc = blockIdx.y;
+    const cpx* fld = field + (size_t)bc * N * 2;
+    unsigned long long vmax = 0ull;
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+        cpx x, y;
+        ld_sa(fld + 2 * n, x, y);
+        const unsigned long long key = pmx_pow_key(power_ref(x, y));
+        vmax = key > vmax ? key : vmax;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, vmax, o);
+        vmax = other > vmax ? other : vmax;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(&out[bc], vmax);
+}
+
+extern "C" int pmx_field_max_power(pmx_ctx* c, pmx_devfield* f, double* umax) {
+    int rc = need_f64(c, f, "pmx_field_max_power");
+    if (rc) return rc;
+    if (!umax) return set_err(c, PMX_ERR_INVALID, "pmx_field_max_power: null output");
+    CK(c, cudaSetDevice(c->device));
+    const int nbc = f->batch * f->nfc;
+    unsigned long long* d = nullptr;
+    CK(c, cudaMallocAsync(&d, nbc * sizeof(unsigned long long), c->stream));
+    CK(c, cudaMemsetAsync(d, 0, nbc * sizeof(unsigned long long), c->stream));
+    dim3 g((unsigned)std::min<size_t>(((size_t)f->nfft + 255) / 256, 148 * 8), nbc);
+    pmx_k_max_power<<<g, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, d);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(umax, d, nbc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));  // key == bit pattern
+    CK(c, cudaFreeAsync(d, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
+__global__ void __launch_bounds__(256) pmx_k_maxdiff2(const cpx* a, const cpx* b, size_t n_sa, unsigned long long* out) {
+    unsigned long long vmax = 0ull;
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_sa; n += (size_t)gridDim.x * blockDim.x) {
+        const cpx x = a[2 * n], z = b[2 * n];
+        const double dr = __dadd_rn(x.x, -z.x), di = __dadd_rn(x.y, -z.y);
+        const unsigned long long key = pmx_pow_key(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(di, di)));
+        vmax = key > vmax ? key : vmax;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, vmax, o);
+        vmax = other > vmax ? other : vmax;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, vmax);
+}
+
+static int same_shape(pmx_ctx* c, const pmx_devfield* a, const pmx_devfield* b, const char* who) {
+    if (a->nfft != b->nfft || a->nfc != b->nfc || a->batch != b->batch || a->precision != b->precision)
+        return set_err(c, PMX_ERR_INVALID, "%s: fields differ in shape or precision", who);
+    return PMX_OK;
+}
+
+extern "C" int pmx_field_maxdiff2(pmx_ctx* c, pmx_devfield* a, pmx_devfield* b, double* out) {
+    int rc = need_f64(c, a, "pmx_field_maxdiff2");
+    if (rc == PMX_OK) rc = need_f64(c, b, "pmx_field_maxdiff2");
+    if (rc == PMX_OK) rc = same_shape(c, a, b, "pmx_field_maxdiff2");
+    if (rc) return rc;
+    if (!out) return set_err(c, PMX_ERR_INVALID, "pmx_field_maxdiff2: null output");
+    CK(c, cudaSetDevice(c->device));
+    unsigned long long* d = nullptr;
+    CK(c, cudaMallocAsync(&d, sizeof(unsigned long long), c->stream));
+    CK(c, cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
+    const size_t n_sa = (size_t)a->batch * a->nfc * a->nfft;
+    pmx_k_maxdiff2<<<(unsigned)std::min<size_t>((n_sa + 255) / 256, 148 * 8), 256, 0, c->stream>>>(a->data, b->data, n_sa, d);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaFreeAsync(d, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
+__global__ void __launch_bounds__(256) pmx_k_lincomb(cpx* dst, double ca, const cpx* a, double cb, const cpx* b, size_t n_cpx) {
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_cpx; n += (size_t)gridDim.x * blockDim.x) {
+        const cpx x = a[n], z = b[n];
+        dst[n] = make_double2(__dadd_rn(__dmul_rn(ca, x.x), -__dmul_rn(cb, z.x)), __dadd_rn(__dmul_rn(ca, x.y), -__dmul_rn(cb, z.y)));
+    }
+}
+
+extern "C" int pmx_field_lincomb(pmx_ctx* c, pmx_devfield* dst, double ca, pmx_devfield* a, double cb, pmx_devfield* b) {
+    int rc = need_f64(c, dst, "pmx_field_lincomb");
+    if (rc == PMX_OK) rc = need_f64(c, a, "pmx_field_lincomb");
+    if (rc == PMX_OK) rc = need_f64(c, b, "pmx_field_lincomb");
+    if (rc == PMX_OK) rc = same_shape(c, dst, a, "pmx_field_lincomb");
+    if (rc == PMX_OK) rc = same_shape(c, dst, b, "pmx_field_lincomb");
+    if (rc) return rc;
+    CK(c, cudaSetDevice(c->device));
+    const size_t n_cpx = (size_t)dst->batch * dst->nfc * dst->nfft * 2;
+    pmx_k_lincomb<<<(unsigned)std::min<size_t>((n_cpx + 255) / 256, 148 * 8), 256, 0, c->stream>>>(dst->data, ca, a->data, cb, b->data, n_cpx);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return PMX_OK;
+}

@@ -26,6 +26,7 @@ from . import _lib
 from .gstate import CONSTANTS, GSTATE, rng as _global_rng
 
 DEF_PLATES = 100  # fiber.m:131
+SAFETYFCT = 0.9   # fiber.m:130: safety step-reduction factor of the adaptive step
 
 # flag -> (g, p, s, x) and whether the run is forced to a single linear step
 _FLAG_TABLE = {
@@ -70,6 +71,8 @@ class FiberSetup:
     b1: np.ndarray
     dch: np.ndarray
     scalars: dict            # beta1, beta2, b30, dgdrms, ... (scalar dispersion mode of the C ABI)
+    tolflag: int = 0         # 2: local-error adaptive step (x.ltol), fiber.m:143-155
+    trg: Optional[dict] = None
 
 
 def flag_to_fls(flag: str, nfc: int, x):
@@ -125,8 +128,13 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
     xd = {k: _get(x, k) for k in ('dzmax', 'dphimax', 'length')}
     if not _has(x, 'dzmax') or xd['dzmax'] > length:                        # :139-141
         xd['dzmax'] = length
-    if _has(x, 'ltol'):
-        raise NotImplementedError('local-error adaptive step (x.ltol, fiber.m:143-155,639-679) is not built')
+    tolflag, trg = 0, None
+    if _has(x, 'ltol'):                                                     # :143-155
+        if not _has(x, 'dphimax'):
+            xd['dphimax'] = math.inf
+        if _has(x, 'dphiadapt') and _get(x, 'dphiadapt'):
+            raise NotImplementedError('x.dphiadapt (adaptive first step only, fiber.m:588-611) is not built')
+        tolflag, trg = 2, {'err': float(_get(x, 'ltol')), 'safety': SAFETYFCT}
     fls, dphimaxt, dzmaxt = flag_to_fls(flag, nfc, xd)
 
     isy = G.FIELDY is not None and np.size(G.FIELDY) != 0                   # :253
@@ -195,7 +203,8 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
                       nplates=nplates, brf=brf, isv=isv, isy=isy, b1=b1, dch=dch,
                       scalars=dict(nsymb=G.NSYMB, nt=G.NT, symbolrate=float(G.SYMBOLRATE), b30=float(b30),
                                    dgdrms=float(dgdrms), beta1=np.asarray(beta1, dtype=np.float64),
-                                   beta2=np.asarray(beta2, dtype=np.float64)))
+                                   beta2=np.asarray(beta2, dtype=np.float64)),
+                      tolflag=tolflag, trg=trg)
 
 
 DISP_MODE = 'scalar'   # 'scalar': only the field crosses PCIe; 'vector': betat/db1 are uploaded
@@ -229,6 +238,84 @@ def apply_side_effects(s: FiberSetup):
 LAST = {}  # firstdz / ncycle / schedule of the most recent fiber(), what the reference prints to simul_out
 
 
+def _nextstep_host(dzmax, phimax, gam, alphalin, umax):
+    """nextstep (fiber.m:693-715) from the per-column maxima of |u|^2."""
+    with np.errstate(divide='ignore', invalid='ignore'):
+        pmax = np.max(np.asarray(gam, dtype=np.float64) * np.asarray(umax, dtype=np.float64))
+        leff = np.float64(phimax) / pmax
+        dl = np.float64(alphalin) * leff
+        if dl >= 1:
+            return float(dzmax)
+        step = leff if alphalin == 0 else np.float64(-1.0) / np.float64(alphalin) * np.log(np.float64(1.0) - dl)
+        return float(dzmax) if step > dzmax else float(step)
+
+
+def _scalar_a_ssfm(s: FiberSetup, ctx: _lib.Context, disp_mode=None):
+    """scalar_a_ssfm + adaptssfm (fiber.m:639-679, 938-1010): symmetric SSFM with the step chosen from the local
+    error (one full step against two half steps, Richardson extrapolation).  The loop is host logic as in the
+    reference; nl_step, lin_step, the error norm and the extrapolation run on the resident field."""
+    G = GSTATE
+    n, nfc = s.nfft, s.nfc
+    fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]
+    u = _lib.DeviceField(ctx, n, nfc, 1)
+    uh = _lib.DeviceField(ctx, n, nfc, 1)
+    ustack = _lib.DeviceField(ctx, n, nfc, 1)
+    u.upload(fx, None)
+    # lin_step(betat*dz, u) = ifft(fft(u).*fastexp(-betat*dz)): a one-step plan of the same dispersion, no loss
+    lin = FiberSetup(nfft=n, nfc=nfc, fls=(s.fls[0], 0, 0, 0), dphimaxt=math.inf, dzmaxt=s.length, length=s.length,
+                     alphalin=0.0, gam=s.gam, betat=s.betat, db1=s.db1, manakov=False, nplates=1, brf=s.brf,
+                     isv=False, isy=False, b1=s.b1, dch=s.dch, scalars=s.scalars)
+    desc, keep = setup_to_desc(lin, disp_mode=disp_mode)
+    plan = _lib.Plan(ctx, desc, keep)
+    gam, alphalin, halfalpha = np.asarray(s.gam, dtype=np.float64), s.alphalin, 0.5 * s.alphalin
+    spm, xpm = bool(s.fls[2]), bool(s.fls[3])
+
+    def nl(f, dz):                                                          # nl_step + u*exp(-halfalpha*dz)
+        leff = dz if alphalin == 0 else (1 - math.exp(-alphalin * dz)) / alphalin
+        _lib.scalar_nl_exec(ctx, f, gam, leff, math.exp(-halfalpha * dz), spm, xpm)
+
+    def lin_step(f, dz):
+        plan.set_length(dz)
+        plan.execute(f)
+
+    ncycle = 1                                                              # :664-668
+    dz = _nextstep_host(s.dzmaxt, s.dphimaxt, gam, alphalin, _lib.field_max_power(ctx, u)[0])
+    firstdz, zdone, nrej = dz, 0.0, 0
+    err, safety = s.trg['err'], s.trg['safety']
+    while zdone < s.length:                                                 # :670-678
+        if zdone + dz > s.length:
+            dz = s.length - zdone
+        dz2, dz4 = 0.5 * dz, 0.25 * dz                                      # adaptssfm :966-1009
+        ustack.broadcast_from(u)
+        uh.broadcast_from(u)
+        nl(u, dz2)
+        lin_step(u, dz)
+        nl(u, dz2)
+        nl(uh, dz4)
+        lin_step(uh, dz2)
+        nl(uh, dz2)
+        lin_step(uh, dz2)
+        nl(uh, dz4)
+        est_err = math.sqrt(_lib.field_maxdiff2(ctx, u, uh)) / dz
+        with np.errstate(divide='ignore'):
+            prop = safety * float(np.sqrt(np.float64(err) / np.float64(est_err))) * dz
+        if est_err > err:                                                   # reject the step
+            dz = prop
+            u.broadcast_from(ustack)
+            nrej += 1
+        else:                                                               # accept: Richardson extrapolation
+            _lib.field_lincomb(ctx, u, 4.0 / 3.0, uh, 1.0 / 3.0, u)
+            zdone = zdone + dz
+            dz = prop
+            ncycle += 1
+        if dz > s.dzmaxt:
+            dz = s.dzmaxt
+    gx, _ = u.download()
+    G.FIELDX = np.ascontiguousarray(gx[0].T)
+    plan.close()
+    return firstdz, ncycle
+
+
 def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional[_lib.Context] = None,
           trace: bool = False, disp_mode: Optional[str] = None, precision: Optional[str] = None):
     """zbrf = fiber(x, flag) -- fiber.m:1.  Propagates GSTATE.FIELDX/FIELDY in place.
@@ -240,8 +327,17 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         raise NotImplementedError('The CNLSE with separate fields is not yet implemented')
     if s.fls[1] and not s.isy:                                              # :285-289
         G.FIELDY = np.zeros_like(G.FIELDX)
+    if s.tolflag == 2 and s.isv:                                            # :372-374
+        raise ValueError('adaptive step available in absence of polarization effects')
     apply_side_effects(s)
     ctx = ctx or _lib.default_context()
+    if s.tolflag == 2:                                                      # :375-378
+        if (precision or PRECISION) != 'f64':
+            raise NotImplementedError('the local-error adaptive step runs in FP64 only')
+        firstdz, ncycle = _scalar_a_ssfm(s, ctx, disp_mode)
+        LAST.clear()
+        LAST.update(firstdz=firstdz, ncycle=ncycle, ntot=0)
+        return None
     desc, keep = setup_to_desc(s, disp_mode=disp_mode, precision=precision)
     fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]     # [1][nfc][nfft]
     scalar = not s.isv

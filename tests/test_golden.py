@@ -103,10 +103,9 @@ SCALAR_CASES = [c for c in CASES if c.startswith('scalar_')]
 @pytest.mark.parametrize('name', SCALAR_CASES)
 def test_cuda_scalar_path_matches_reference_source(name):
     """The scalar path (scalar_ssfm: FIELDY empty, no 'p' flag; nl_step with SPM and cross-column XPM,
-    fiber.m:557-636,786-803) on the device against the interpreted reference: <= 1e-10 rel L2 (FP64)."""
+    fiber.m:557-636,786-803; with x.ltol the local-error adaptive step scalar_a_ssfm / adaptssfm, :639-679,938-1010)
+    on the device against the interpreted reference: <= 1e-10 rel L2 (FP64)."""
     z, m = load(name)
-    if m['fiber'].get('ltol') is not None or 'ltol' in m['fiber']:
-        pytest.skip('local-error adaptive step (scalar_a_ssfm) is not built')
     pmx.reset_all(m['nsymb'], m['nt'], m['nch'])
     G = pmx.GSTATE
     G.SYMBOLRATE, G.POWER, G.LAMBDA = m['rate'], np.full(m['nch'], float(m['pavg'])), synth.wdm_lambdas(m['nch'])
