@@ -1,0 +1,52 @@
+"""inverse_pmd(brf) -- inverse_pmd.m:1.  Undoes the GVD and PMD of a chain of fibers on GSTATE.FIELDX/FIELDY.
+
+The reference builds U(omega) = prod_fibers R_last * prod_k [D_k * R_k' R_(k-1)] * R_1' * exp(-i*betat*L) on the
+host and multiplies the spectrum by inv(U) (inverse_pmd.m:91-141).  inv(R_n D_n R_n' ... R_1 D_1 R_1') is the same
+product taken backwards with every phase negated, i.e. the linear step of a fiber with the plates in reverse
+order, db0 -> -db0, db1 -> -db1, betat -> -betat and no loss: one single-step run of the SSFM kernels per fiber
+(pass B applies the whole-trunk Jones product), the field staying on the device in between.
+options.mat / options.theta (a change of reference system before the inversion) are not built."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _lib
+from .fiber import FiberSetup, setup_to_desc
+from .gstate import GSTATE
+
+
+def inverse_pmd(brf, options=None, ctx=None):
+    G = GSTATE
+    if options:
+        raise NotImplementedError('inverse_pmd options (mat, theta; inverse_pmd.m:73-89) are not built')
+    brfs = [brf] if isinstance(brf, dict) else list(brf)
+    nfr, nfc = np.shape(G.FIELDX)
+    if nfc != 1:
+        raise NotImplementedError('inverse_pmd: single-column (unique) fields only')
+    n = G.NSYMB * G.NT
+    ctx = ctx or _lib.default_context()
+    fld = _lib.DeviceField(ctx, n, 1, 1)
+    fld.upload(np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None],
+               np.ascontiguousarray(np.asarray(G.FIELDY, dtype=np.complex128).T)[None])
+    for b in reversed(brfs):
+        th = np.asarray(b['theta'], dtype=np.float64).ravel()
+        ep = np.asarray(b['epsilon'], dtype=np.float64).ravel()
+        db0 = np.asarray(b['db0'], dtype=np.float64).ravel()
+        ntr = th.size
+        length = float(b['lcorr']) * ntr
+        betat = -np.asarray(b['betat'], dtype=np.float64).reshape(n, 1)
+        db1 = -np.asarray(b['db1'], dtype=np.float64).reshape(n, 1)
+        inv = FiberSetup(nfft=n, nfc=1, fls=(1, 1, 0, 0), dphimaxt=math.inf, dzmaxt=length, length=length,
+                         alphalin=0.0, gam=np.zeros(1), betat=betat, db1=db1, manakov=False, nplates=ntr,
+                         brf={'db0': -db0[::-1], 'theta': th[::-1], 'epsilon': ep[::-1]}, isv=True, isy=True,
+                         b1=np.zeros(1), dch=np.zeros(1), scalars={})
+        desc, keep = setup_to_desc(inv, disp_mode='vector')
+        plan = _lib.Plan(ctx, desc, keep)
+        plan.execute(fld)
+        plan.close()
+    gx, gy = fld.download()
+    G.FIELDX = np.ascontiguousarray(gx[0].T)
+    G.FIELDY = np.ascontiguousarray(gy[0].T)
+    G.DISP = np.zeros((2, G.NCH))                         # inverse_pmd.m:141

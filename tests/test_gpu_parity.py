@@ -153,3 +153,24 @@ def test_batch_of_realizations_matches_oracle_each(disp_mode):
         ncycles.append(gs.log['ncycle'])
     assert len(set(ncycles)) > 1   # the batch really is ragged
     tx.close() if hasattr(tx, 'close') else None
+
+
+def test_inverse_pmd_on_device(disp_mode):
+    """inverse_pmd.m: fiber('gp--') followed by inverse_pmd(brf) gives the transmitted field back (self-check
+    4), and equals the oracle's inverse_pmd applied to the same propagated field."""
+    gs = make_tx(1 << 10, 16)
+    tx_x, tx_y = np.array(pmx.GSTATE.FIELDX), np.array(pmx.GSTATE.FIELDY)
+    fib = base_fiber(length=5e4, dgd=0.6, nplates=15, alphadB=0.0)
+    brf_o = orc.fiber(gs, fib, 'gp--', rng=np.random.Generator(np.random.PCG64(11)))
+    brf_g = pmx.fiber(fib, 'gp--', rng=np.random.Generator(np.random.PCG64(11)))
+    orc.inverse_pmd(gs, [brf_o])
+    pmx.inverse_pmd(brf_g)
+    G = pmx.GSTATE
+    assert rel_l2(G.FIELDX, G.FIELDY, gs.FIELDX, gs.FIELDY) < TOL
+    assert rel_l2(G.FIELDX, G.FIELDY, tx_x, tx_y) < 1e-9
+    # two fibers in a row, inverted together
+    gs = make_tx(1 << 10, 16)
+    b1 = pmx.fiber(fib, 'gp--', rng=np.random.Generator(np.random.PCG64(12)))
+    b2 = pmx.fiber(fib, 'gp--', rng=np.random.Generator(np.random.PCG64(13)))
+    pmx.inverse_pmd([b1, b2])
+    assert rel_l2(pmx.GSTATE.FIELDX, pmx.GSTATE.FIELDY, tx_x, tx_y) < 1e-9
