@@ -264,6 +264,7 @@ class DeviceField:
 
     def __init__(self, ctx: Context, nfft, nfc=1, batch=1, precision=PMX_F64):
         self.ctx, self.nfft, self.nfc, self.batch = ctx, int(nfft), int(nfc), int(batch)
+        self.precision = int(precision)
         h = C.c_void_p()
         ctx.check(ctx.lib.pmx_field_create(ctx.h, self.nfft, self.nfc, self.batch, precision, C.byref(h)))
         self.h = h

@@ -25,7 +25,7 @@ def ase_sigma(gain: float, f_db, nfc: int) -> np.ndarray:
 
 
 def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
-    """Host-buffer form, like the reference: GSTATE.FIELDX/FIELDY in place.
+    """ampliflat(x,'gain',options) on GSTATE.FIELDX/FIELDY, like the reference.
 
     options: {'f': noise figure [dB], 'noise': [Nfft, 2*nfc] complex standard normals}.
     Without options.noise the ASE comes from the device's counter-based generator (seed)."""
@@ -35,28 +35,31 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
     options = dict(options or {})
     if 'onepol' in options:
         raise NotImplementedError('ampliflat: options.onepol is not built')
-    nfr, nfc = G.FIELDX.shape
+    nfr, nfc = G.field_shape()
     gain = 10 ** (x * 0.1)
     sigma = ase_sigma(gain, options.get('f'), nfc) if options else np.zeros(nfc)
     ctx = ctx or _lib.default_context()
-    fld = _lib.DeviceField(ctx, nfr, nfc, 1)
-    fy = G.FIELDY if G.FIELDY is not None else np.zeros_like(G.FIELDX)
-    fld.upload(G.FIELDX, fy)
     noise = None
     if np.any(sigma) and 'noise' in options:
         nz = np.asarray(options['noise'], dtype=np.complex128)
         noise = np.ascontiguousarray(nz.T)[None]                 # [1][2*nfc][nfft]
-    _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed)
-    inplace = (nfc == 1 and G.FIELDY is not None and all(
-        a.dtype == np.complex128 and a.flags['C_CONTIGUOUS'] and a.flags['WRITEABLE'] for a in (G.FIELDX, G.FIELDY)))
-    if inplace:          # single column: [N,1] is also [1][1][N]; results land in the caller's buffers
-        fld.download_into(G.FIELDX, G.FIELDY)
-        fld.close()
+    if G.has_y():
+        # two polarizations: works on the field fiber() left in HBM (or uploads it) and leaves it there
+        fld, hx, hy = G.take_device(ctx)
+        try:
+            _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed)
+        except Exception:
+            fld.close()
+            raise
+        G.put_device(fld, hx, hy)
         return
+    # single polarization: host buffers in, host buffers out (ASE creates FIELDY, ampliflat.m:132-146)
+    fld = _lib.DeviceField(ctx, nfr, nfc, 1)
+    fld.upload(G.FIELDX, np.zeros_like(G.FIELDX))
+    _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed)
     ox, oy = fld.download()
     fld.close()
     G.FIELDX = np.ascontiguousarray(ox[0].T)
-    if G.FIELDY is not None or np.any(sigma):
-        if G.FIELDY is None:
-            G.DELAY = np.vstack([G.DELAY[:1], np.zeros((1, G.NCH))])          # ampliflat.m:144
+    if np.any(sigma):
+        G.DELAY = np.vstack([G.DELAY[:1], np.zeros((1, G.NCH))])              # ampliflat.m:144
         G.FIELDY = np.ascontiguousarray(oy[0].T)

@@ -122,7 +122,7 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
     G = GSTATE
     if flag is None:
         raise ValueError('Missing propagation type')                        # fiber.m:137
-    nfr, nfc = G.FIELDX.shape
+    nfr, nfc = G.field_shape()
     nfft = G.NSYMB * G.NT
     length = float(_get(x, 'length'))
     xd = {k: _get(x, k) for k in ('dzmax', 'dphimax', 'length')}
@@ -137,7 +137,7 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
         tolflag, trg = 2, {'err': float(_get(x, 'ltol')), 'safety': SAFETYFCT}
     fls, dphimaxt, dzmaxt = flag_to_fls(flag, nfc, xd)
 
-    isy = G.FIELDY is not None and np.size(G.FIELDY) != 0                   # :253
+    isy = G.has_y()                                                         # :253
     isv = bool(fls[1]) or isy
     brf = {}
     if fls[1]:                                                              # :255-289
@@ -339,17 +339,31 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         LAST.update(firstdz=firstdz, ncycle=ncycle, ntot=0)
         return None
     desc, keep = setup_to_desc(s, disp_mode=disp_mode, precision=precision)
-    fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]     # [1][nfc][nfft]
     scalar = not s.isv
-    fy = (np.zeros_like(fx) if scalar else
-          np.ascontiguousarray(np.asarray(G.FIELDY, dtype=np.complex128).T)[None])
-    io = _lib.complex_field(fx, fy)
-    res = _lib.Result(1, trace_cap=4096 if trace else 0)
-    import ctypes
-    ctx.check(ctx.lib.pmx_fiber_run(ctx.h, ctypes.byref(desc), ctypes.byref(io), ctypes.byref(res.c)))
-    G.FIELDX = np.ascontiguousarray(fx[0].T)
-    if not scalar:
-        G.FIELDY = np.ascontiguousarray(fy[0].T)
+    if scalar:
+        # single-polarization path (fiber.m:372-380): one call on host buffers, H2D + loop + D2H
+        fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]     # [1][nfc][nfft]
+        fy = np.zeros_like(fx)
+        io = _lib.complex_field(fx, fy)
+        res = _lib.Result(1, trace_cap=4096 if trace else 0)
+        import ctypes
+        ctx.check(ctx.lib.pmx_fiber_run(ctx.h, ctypes.byref(desc), ctypes.byref(io), ctypes.byref(res.c)))
+        G.FIELDX = np.ascontiguousarray(fx[0].T)
+    else:
+        # two polarizations: the field of the previous in-line device if it is still in HBM, else an upload; the
+        # result stays there until GSTATE.FIELDX / FIELDY are read (gstate.RESIDENT)
+        fld, hx, hy = G.take_device(ctx, desc.precision)
+        plan = None
+        try:
+            plan = _lib.Plan(ctx, desc, keep)
+            res = plan.execute(fld, trace_cap=4096 if trace else 0)
+        except Exception:
+            fld.close()
+            raise
+        finally:
+            if plan is not None:
+                plan.close()
+        G.put_device(fld, hx, hy)
     LAST.clear()
     LAST.update(firstdz=float(res.firstdz[0]), ncycle=int(res.ncycle[0]), ntot=int(res.ntot[0]))
     if trace:

@@ -24,8 +24,121 @@ class _Constants(_Struct):
     KBOLTZMANN = 1.3806504e-23    # Boltzmann's constant [J/K]           reset_all.m:112
 
 
+# True: FIELDX/FIELDY stay in HBM between the in-line devices (fiber, ampliflat, inverse_pmd) of a two-polarization
+# link and reach the host when somebody reads them; False: every call copies the field up and down, as a MEX call does
+RESIDENT = True
+
+
+class _Resident:
+    """A two-polarization field living in HBM after an in-line device ran, plus the host arrays it came from
+    (results land in those again when they can, as the reference overwrites GSTATE.FIELDX/FIELDY)."""
+
+    def __init__(self, field, hostx, hosty):
+        self.field, self.hostx, self.hosty = field, hostx, hosty
+
+
+class _GState(_Struct):
+    """GSTATE (reset_all.m:152-174).  FIELDX / FIELDY read and assign like the reference's arrays.  Behind them the
+    field of a two-polarization link may be resident on the device: fiber() -> ampliflat() -> fiber() ... chains of
+    the reference's span loops (ex06_ber.m:110-115, ex20_coherent_polmux.m) then cross PCIe once in and once out
+    instead of twice per call.  Reading either attribute downloads the field and gives the device copy up (the host
+    array is handed out and may be written in place); assigning does the same before it replaces the array."""
+
+    def __repr__(self):
+        return 'GSTATE(%s)' % ', '.join(sorted(k for k in self.__dict__ if not k.startswith('_')) + ['FIELDX', 'FIELDY'])
+
+    # -- host view
+    def _materialize(self):
+        res = self.__dict__.pop('_res', None)
+        if res is None:
+            return
+        fld = res.field
+        n, nfc = fld.nfft, fld.nfc
+        bufs = (res.hostx, res.hosty)
+        if nfc == 1 and all(isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.shape == (n, 1)
+                            and a.flags['C_CONTIGUOUS'] and a.flags['WRITEABLE'] for a in bufs):
+            fld.download_into(res.hostx, res.hosty)              # [N,1] is also [1][1][N]; pinned stays pinned
+            hx, hy = res.hostx, res.hosty
+        else:
+            ox, oy = fld.download()
+            hx, hy = np.ascontiguousarray(ox[0].T), np.ascontiguousarray(oy[0].T)
+        fld.close()
+        self.__dict__['_hx'], self.__dict__['_hy'] = hx, hy
+
+    @property
+    def FIELDX(self):
+        self._materialize()
+        return self.__dict__.get('_hx')
+
+    @FIELDX.setter
+    def FIELDX(self, value):
+        self._materialize()
+        self.__dict__['_hx'] = value
+
+    @property
+    def FIELDY(self):
+        self._materialize()
+        return self.__dict__.get('_hy')
+
+    @FIELDY.setter
+    def FIELDY(self, value):
+        self._materialize()
+        self.__dict__['_hy'] = value
+
+    # -- what the in-line devices use (no transfer just to look at the shape)
+    def field_shape(self):
+        res = self.__dict__.get('_res')
+        if res is not None:
+            return res.field.nfft, res.field.nfc
+        return np.shape(self.__dict__.get('_hx'))
+
+    def has_y(self):
+        """~isempty(GSTATE.FIELDY) (fiber.m:253)"""
+        if self.__dict__.get('_res') is not None:
+            return True
+        hy = self.__dict__.get('_hy')
+        return hy is not None and np.size(hy) != 0
+
+    def is_resident(self):
+        return self.__dict__.get('_res') is not None
+
+    def take_device(self, ctx, precision=None):
+        """-> (DeviceField [1][nfc][N] holding FIELDX/FIELDY, hostx, hosty): the resident copy when there is one on
+        this context in this precision (None: whatever is resident, FP64 for an upload), else an upload of the host
+        arrays.  The caller owns the field until it hands it back with put_device()."""
+        from . import _lib
+        res = self.__dict__.get('_res')
+        if res is not None and (res.field.ctx is not ctx or (precision is not None and res.field.precision != precision)):
+            self._materialize()
+            res = None
+        if res is not None:
+            del self.__dict__['_res']
+            return res.field, res.hostx, res.hosty
+        hx, hy = self.__dict__.get('_hx'), self.__dict__.get('_hy')
+        n, nfc = np.shape(hx)
+        fld = _lib.DeviceField(ctx, n, nfc, 1, precision=_lib.PMX_F64 if precision is None else precision)
+        try:
+            fld.upload(hx, hy)
+        except Exception:
+            fld.close()
+            raise
+        return fld, hx, hy
+
+    def put_device(self, fld, hostx, hosty):
+        """The field an in-line device leaves behind.  With RESIDENT it stays in HBM until it is read."""
+        self.__dict__['_res'] = _Resident(fld, hostx, hosty)
+        self.__dict__['_hx'] = self.__dict__['_hy'] = None
+        if not RESIDENT:
+            self._materialize()
+
+    def drop_device(self):
+        res = self.__dict__.pop('_res', None)
+        if res is not None:
+            res.field.close()
+
+
 CONSTANTS = _Constants()
-GSTATE = _Struct()
+GSTATE = _GState()
 
 # stream standing in for the interpreter's global rand/randn state
 _rng = np.random.default_rng(0)
@@ -47,8 +160,9 @@ def reset_all(Nsymb: int, Nt: int, Nch: int, *opts):
     Printing to simul_out is not built (GSTATE.PRINT is always False)."""
     if len(opts) > 2:
         raise ValueError('Invalid number of inputs')
+    GSTATE.drop_device()
     for k in list(GSTATE.__dict__):
-        delattr(GSTATE, k)
+        del GSTATE.__dict__[k]
     GSTATE.PRINT = False
     if opts:
         if not isinstance(opts[0], str):

@@ -22,14 +22,14 @@ def inverse_pmd(brf, options=None, ctx=None):
     if options:
         raise NotImplementedError('inverse_pmd options (mat, theta; inverse_pmd.m:73-89) are not built')
     brfs = [brf] if isinstance(brf, dict) else list(brf)
-    nfr, nfc = np.shape(G.FIELDX)
+    nfr, nfc = G.field_shape()
     if nfc != 1:
         raise NotImplementedError('inverse_pmd: single-column (unique) fields only')
+    if not G.has_y():
+        raise ValueError('inverse_pmd needs both polarizations')
     n = G.NSYMB * G.NT
     ctx = ctx or _lib.default_context()
-    fld = _lib.DeviceField(ctx, n, 1, 1)
-    fld.upload(np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None],
-               np.ascontiguousarray(np.asarray(G.FIELDY, dtype=np.complex128).T)[None])
+    fld, hx, hy = G.take_device(ctx, _lib.PMX_F64)      # the field fiber() left in HBM, or an upload
     for b in reversed(brfs):
         th = np.asarray(b['theta'], dtype=np.float64).ravel()
         ep = np.asarray(b['epsilon'], dtype=np.float64).ravel()
@@ -46,7 +46,5 @@ def inverse_pmd(brf, options=None, ctx=None):
         plan = _lib.Plan(ctx, desc, keep)
         plan.execute(fld)
         plan.close()
-    gx, gy = fld.download()
-    G.FIELDX = np.ascontiguousarray(gx[0].T)
-    G.FIELDY = np.ascontiguousarray(gy[0].T)
+    G.put_device(fld, hx, hy)
     G.DISP = np.zeros((2, G.NCH))                         # inverse_pmd.m:141

@@ -142,3 +142,65 @@ def test_synth_is_deterministic_and_unit_power():
     # symbol centres carry the symbols
     c = ex[0::16, 0] * np.sqrt(2)
     np.testing.assert_allclose(np.sign(c.real), 2 * (sx[:, 0] & 1) - 1)
+
+
+class _FakeDeviceField:
+    """stands in for _lib.DeviceField in the residency bookkeeping of GSTATE (no GPU here)"""
+
+    def __init__(self, x, y):
+        self.nfft, self.nfc, self.batch, self.ctx, self.precision = x.shape[0], x.shape[1], 1, 'ctx', _lib.PMX_F64
+        self.x, self.y, self.closed, self.downloads = x.copy(), y.copy(), False, 0
+
+    def download(self):
+        self.downloads += 1
+        return np.ascontiguousarray(self.x.T)[None], np.ascontiguousarray(self.y.T)[None]
+
+    def download_into(self, x, y):
+        self.downloads += 1
+        x[...] = self.x
+        y[...] = self.y
+
+    def close(self):
+        self.closed = True
+
+
+def test_gstate_resident_field_reads_like_the_host_arrays():
+    """GSTATE.FIELDX/FIELDY of a two-polarization link may live in HBM between in-line devices (gstate.RESIDENT):
+    reading or assigning either downloads once, lands in the arrays the field came from, and gives the device copy up"""
+    from polmux_b200 import gstate
+    pmx.reset_all(8, 4, 1)
+    G = pmx.GSTATE
+    hx = np.zeros((32, 1), dtype=np.complex128)
+    hy = np.zeros((32, 1), dtype=np.complex128)
+    G.FIELDX, G.FIELDY = hx, hy
+    assert G.FIELDX is hx and G.has_y() and G.field_shape() == (32, 1) and not G.is_resident()
+    fake = _FakeDeviceField(hx + 1.0, hy + 2.0j)
+    G.put_device(fake, hx, hy)
+    assert G.is_resident() and G.field_shape() == (32, 1) and G.has_y() and fake.downloads == 0
+    assert G.take_device('ctx', _lib.PMX_F64)[0] is fake and not G.is_resident()    # the next device finds it there
+    G.put_device(fake, hx, hy)
+    assert G.FIELDY is hy and fake.downloads == 1 and fake.closed and not G.is_resident()  # in place, as the reference
+    assert np.all(hx == 1.0) and np.all(hy == 2.0j) and G.FIELDX is hx and fake.downloads == 1
+    # assigning one polarization keeps the other
+    fake2 = _FakeDeviceField(hx + 4.0, hy + 4.0)
+    G.put_device(fake2, None, None)
+    G.FIELDX = np.full((32, 1), 7.0 + 0j)
+    assert fake2.closed and np.all(G.FIELDY == 4.0 + 2.0j) and np.all(G.FIELDX == 7.0)
+    # multi-column fields come back as [N, nfc]
+    x3 = np.arange(96, dtype=np.complex128).reshape(32, 3)
+    G.put_device(_FakeDeviceField(x3, -x3), None, None)
+    assert G.field_shape() == (32, 3) and np.array_equal(G.FIELDX, x3) and np.array_equal(G.FIELDY, -x3)
+    # per-call mode: nothing stays behind
+    old = gstate.RESIDENT
+    try:
+        gstate.RESIDENT = False
+        fake3 = _FakeDeviceField(hx, hy)
+        G.put_device(fake3, hx, hy)
+        assert not G.is_resident() and fake3.closed
+    finally:
+        gstate.RESIDENT = old
+    # reset_all drops a resident field
+    fake4 = _FakeDeviceField(hx, hy)
+    G.put_device(fake4, hx, hy)
+    pmx.reset_all(8, 4, 1)
+    assert fake4.closed and pmx.GSTATE.FIELDX is None and not pmx.GSTATE.has_y()

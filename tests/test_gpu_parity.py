@@ -174,3 +174,37 @@ def test_inverse_pmd_on_device(disp_mode):
     b2 = pmx.fiber(fib, 'gp--', rng=np.random.Generator(np.random.PCG64(13)))
     pmx.inverse_pmd([b1, b2])
     assert rel_l2(pmx.GSTATE.FIELDX, pmx.GSTATE.FIELDY, tx_x, tx_y) < 1e-9
+
+
+def test_resident_chain_equals_per_call_chain(disp_mode):
+    """fiber -> ampliflat -> fiber with the field left in HBM between the calls (gstate.RESIDENT, the default) gives
+    the bits of the same chain with a download and an upload at every call; the result lands in the caller's arrays"""
+    from polmux_b200 import gstate
+    fib = base_fiber(length=2e4, dgd=0.3, nplates=12, manakov='yes')
+    outs = []
+    for resident in (True, False):
+        old = gstate.RESIDENT
+        gstate.RESIDENT = resident
+        try:
+            gs = make_tx(1 << 10, 16)
+            G = pmx.GSTATE
+            hx, hy = G.FIELDX, G.FIELDY
+            noise = np.random.Generator(np.random.PCG64(5)).standard_normal((1 << 14, 4)).view(np.complex128).copy()
+            pmx.fiber(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(21)))
+            assert G.is_resident() == resident
+            pmx.ampliflat(4.0, 'gain', {'f': 5.0, 'noise': noise})
+            assert G.is_resident() == resident
+            pmx.fiber(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(22)))
+            assert G.field_shape() == (1 << 14, 1) and G.has_y()
+            assert G.is_resident() == resident
+            assert G.FIELDX is hx and G.FIELDY is hy and not G.is_resident()
+            outs.append((np.array(hx), np.array(hy)))
+            # the oracle on the same chain
+            if resident:
+                orc.fiber(gs, fib, 'gps-', rng=np.random.Generator(np.random.PCG64(21)))
+                orc.ampliflat(gs, 4.0, 5.0, noise=noise)
+                orc.fiber(gs, fib, 'gps-', rng=np.random.Generator(np.random.PCG64(22)))
+                assert rel_l2(hx, hy, gs.FIELDX, gs.FIELDY) < TOL
+        finally:
+            gstate.RESIDENT = old
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
