@@ -193,6 +193,30 @@ int pmx_ctx_profile_read(pmx_ctx* ctx, double* ms, int64_t* n);
 int pmx_ampliflat_exec(pmx_ctx* ctx, pmx_devfield* f, double gain, const double* sigma,
                        const double* noise_host, uint64_t seed);
 
+/* ---- span loop: nspan x [ fiber ; ampliflat ] without returning to the host ---------------
+ * The loop every multi-span script of the reference writes around its in-line devices
+ *   for k=1:Nspan, fiber(x,flag); ampliflat(Gerbio,'gain',opt); end        ex06_ber.m:110-115
+ * as one call: the field stays in HBM between the fibers and the amplifiers.  The fiber of every span is the one
+ * the plan / pmx_fiber_desc describes; the waveplates may change from span to span (fiber.m:274-276 draws new
+ * ones at every call). */
+typedef struct pmx_link_desc {
+    int32_t nspan;
+    int32_t plate_sets;      /* 1 or batch: plate draws per span handed in below                                  */
+    const double* db0;       /* [nspan][plate_sets][nplates], or NULL: every span keeps the plates of the plan    */
+    const double* theta;     /* same shape */
+    const double* epsilon;   /* same shape */
+    double gain;             /* linear power gain of the amplifier after every span (ampliflat.m:62); 0: none     */
+    const double* sigma;     /* [nfc] ASE sigma per column (ampliflat.m:91-106); NULL or zeros: no ASE            */
+    const double* noise;     /* NULL: device generator keyed by seeds[k]; else HOST [nspan][batch][2*nfc][nfft]   */
+                             /* complex standard normals, options.noise of span k (ampliflat.m:123-129)            */
+    const uint64_t* seeds;   /* [nspan] ASE seed of every span, or NULL: seed k                                   */
+} pmx_link_desc;
+/* Resident form.  out (may be NULL): arrays of nspan*batch entries, span-major ([k*batch + b]); no trace. */
+int pmx_link_exec(pmx_plan* plan, pmx_devfield* f, const pmx_link_desc* link, pmx_fiber_result* out);
+/* Host-buffer form: H2D of the transmitted field, the whole link on the device, D2H of the received field. */
+int pmx_link_run(pmx_ctx* ctx, const pmx_fiber_desc* desc, const pmx_link_desc* link, pmx_field* io,
+                 pmx_fiber_result* out);
+
 /* ---- integer error counting (ber_estimate.m:118) --------------------------------
  * counts[b] = #{ i : pat_hat[b][i] != pat[i] } over n symbols-bits, on the device. */
 int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pat_dev, int64_t n,

@@ -8,6 +8,7 @@ from .field import create_field  # noqa: F401
 from .fiber import fiber, fiber_setup, LAST as FIBER_LAST  # noqa: F401
 from .ampliflat import ampliflat  # noqa: F401
 from .inverse_pmd import inverse_pmd  # noqa: F401
+from .link import link  # noqa: F401
 from ._lib import PolmuxError, Context, DeviceField, Plan  # noqa: F401
 
 __version__ = '0.1.0'

@@ -29,7 +29,7 @@ EXPORTS = [
     'pmx_plan_create', 'pmx_plan_destroy', 'pmx_plan_set_plates', 'pmx_fiber_exec',
     'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
-    'pmx_field_maxdiff2', 'pmx_field_lincomb',
+    'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run',
 ]
 
 
@@ -63,6 +63,11 @@ class Field(C.Structure):
 class FiberResult(C.Structure):
     _fields_ = [('firstdz', _dp), ('ncycle', _ip), ('ntot', _ip), ('status', _ip),
                 ('trace_dz', _dp), ('trace_ntrunk', _ip), ('trace_cap', C.c_int32)]
+
+
+class LinkDesc(C.Structure):
+    _fields_ = [('nspan', C.c_int32), ('plate_sets', C.c_int32), ('db0', _dp), ('theta', _dp), ('epsilon', _dp),
+                ('gain', C.c_double), ('sigma', _dp), ('noise', _dp), ('seeds', C.POINTER(C.c_uint64))]
 
 
 _lib = None
@@ -114,6 +119,8 @@ def load():
     lib.pmx_field_max_power.argtypes = [vp, vp, _dp]
     lib.pmx_field_maxdiff2.argtypes = [vp, vp, vp, _dp]
     lib.pmx_field_lincomb.argtypes = [vp, vp, C.c_double, vp, C.c_double, vp]
+    lib.pmx_link_exec.argtypes = [vp, vp, C.POINTER(LinkDesc), C.POINTER(FiberResult)]
+    lib.pmx_link_run.argtypes = [vp, C.POINTER(FiberDesc), C.POINTER(LinkDesc), C.POINTER(Field), C.POINTER(FiberResult)]
     _lib = lib
     return lib
 
@@ -342,6 +349,13 @@ class Plan:
         self.ctx.check(self.ctx.lib.pmx_fiber_exec(self.h, field.h, C.byref(res.c)))
         return res
 
+    def link_exec(self, field: DeviceField, link, keep) -> 'Result':
+        """nspan x [fiber ; ampliflat] on the resident field (pmx_link_exec); -> Result with [nspan*batch] entries,
+        span-major"""
+        res = Result(field.batch * int(link.nspan))
+        self.ctx.check(self.ctx.lib.pmx_link_exec(self.h, field.h, C.byref(link), C.byref(res.c)))
+        return res
+
     def close(self):
         if getattr(self, 'h', None):
             self.ctx.lib.pmx_plan_destroy(self.h)
@@ -352,6 +366,32 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+def make_link(nspan, gain=0.0, sigma=None, plates=None, plate_sets=1, noise=None, seeds=None):
+    """-> (LinkDesc, keep-alive dict).  plates: (db0, theta, epsilon) each [nspan][plate_sets][nplates] or None;
+    noise: [nspan][batch][2*nfc][nfft] complex128 or None; seeds: [nspan] ints or None."""
+    keep = {}
+    l = LinkDesc()
+    l.nspan, l.plate_sets, l.gain = int(nspan), int(plate_sets), float(gain)
+    if plates is not None:
+        for name, a in zip(('db0', 'theta', 'epsilon'), plates):
+            keep[name] = _f64(a).reshape(-1)
+            if keep[name].size % int(nspan):
+                raise ValueError('plates must hold nspan draws')
+            setattr(l, name, _ptr(keep[name]))
+    if sigma is not None:
+        keep['sigma'] = _f64(np.atleast_1d(sigma))
+        l.sigma = _ptr(keep['sigma'])
+    if noise is not None:
+        keep['noise'] = np.ascontiguousarray(noise, dtype=np.complex128)
+        l.noise = keep['noise'].ctypes.data_as(_dp)
+    if seeds is not None:
+        keep['seeds'] = np.ascontiguousarray(seeds, dtype=np.uint64)
+        if keep['seeds'].size != int(nspan):
+            raise ValueError('one ASE seed per span')
+        l.seeds = keep['seeds'].ctypes.data_as(C.POINTER(C.c_uint64))
+    return l, keep
 
 
 def scalar_nl_exec(ctx: Context, field: DeviceField, gam, leff: float, atten: float, spm: bool, xpm: bool):

@@ -1238,6 +1238,66 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
 }
 
 // ---------------------------------------------------------------------------
+// span loop (ex06_ber.m:110-115): nspan x [ fiber ; ampliflat ] on a resident field
+extern "C" int pmx_link_exec(pmx_plan* p, pmx_devfield* f, const pmx_link_desc* l, pmx_fiber_result* out) {
+    if (!p || !f || !l) return set_err(p ? p->ctx : nullptr, PMX_ERR_INVALID, "pmx_link_exec: null argument");
+    pmx_ctx* c = p->ctx;
+    if (l->nspan < 1) return set_err(c, PMX_ERR_INVALID, "pmx_link_exec: nspan must be >= 1");
+    const bool redraw = l->db0 || l->theta || l->epsilon;
+    if (redraw && !(l->db0 && l->theta && l->epsilon))
+        return set_err(c, PMX_ERR_INVALID, "pmx_link_exec: db0, theta and epsilon come together");
+    if (redraw && l->plate_sets != 1 && l->plate_sets != p->d.batch)
+        return set_err(c, PMX_ERR_INVALID, "pmx_link_exec: plate_sets must be 1 or batch (%d), got %d", p->d.batch, l->plate_sets);
+    if (l->gain < 0 || l->gain != l->gain) return set_err(c, PMX_ERR_INVALID, "pmx_link_exec: negative gain");
+    const int batch = p->d.batch;
+    const size_t per_span = redraw ? (size_t)l->plate_sets * p->d.nplates : 0;
+    const size_t noise_span = (size_t)batch * 2 * p->d.nfc * (size_t)p->d.nfft * 2;  // doubles
+    std::vector<double> zeros((size_t)p->d.nfc, 0.0);
+    for (int k = 0; k < l->nspan; ++k) {
+        int rc = PMX_OK;
+        if (redraw)
+            rc = pmx_plan_set_plates(p, l->plate_sets, l->db0 + k * per_span, l->theta + k * per_span, l->epsilon + k * per_span);
+        if (rc != PMX_OK) return rc;
+        pmx_fiber_result r = {};
+        if (out) {
+            r.firstdz = out->firstdz ? out->firstdz + (size_t)k * batch : nullptr;
+            r.ncycle = out->ncycle ? out->ncycle + (size_t)k * batch : nullptr;
+            r.ntot = out->ntot ? out->ntot + (size_t)k * batch : nullptr;
+            r.status = out->status ? out->status + (size_t)k * batch : nullptr;
+        }
+        rc = pmx_fiber_exec(p, f, &r);
+        if (rc != PMX_OK) return rc;
+        if (l->gain > 0) {
+            rc = pmx_ampliflat_exec(c, f, l->gain, l->sigma ? l->sigma : zeros.data(),
+                                    l->noise ? l->noise + (size_t)k * noise_span : nullptr,
+                                    l->seeds ? l->seeds[k] : (uint64_t)k);
+            if (rc != PMX_OK) return rc;
+        }
+    }
+    return PMX_OK;
+}
+
+extern "C" int pmx_link_run(pmx_ctx* c, const pmx_fiber_desc* d, const pmx_link_desc* l, pmx_field* io,
+                            pmx_fiber_result* out) {
+    if (!c || !d || !l || !io) return set_err(c, PMX_ERR_INVALID, "pmx_link_run: null argument");
+    pmx_plan* plan = nullptr;
+    pmx_devfield* f = nullptr;
+    int rc = pmx_plan_create(c, d, &plan);
+    if (rc == PMX_OK) rc = pmx_field_create(c, d->nfft, d->nfc, d->batch, d->precision, &f);
+    if (rc == PMX_OK) rc = pmx_field_upload(f, io, 0, d->batch);
+    if (rc == PMX_OK) rc = pmx_link_exec(plan, f, l, out);
+    if (rc == PMX_OK) rc = pmx_field_download(f, io, 0, d->batch);
+    std::string keep = c->error;
+    pmx_field_destroy(f);
+    pmx_plan_destroy(plan);
+    if (rc != PMX_OK) {
+        c->error = keep;
+        g_tls_error = keep;
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
 // integer error count (ber_estimate.m:118)
 __global__ void __launch_bounds__(256) pmx_k_count(const uint8_t* hat, const uint8_t* pat, size_t n,
                                                    unsigned long long* counts) {

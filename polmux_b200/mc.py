@@ -71,16 +71,15 @@ class Link:
         noise_fn(span) -> [batch][2*nfc][nfft] complex standard normals (ampliflat's options.noise,
         for parity runs); default: the device's counter-based generator keyed by (seed, span, realization)."""
         n = self.setup.nfft
-        sa_steps = 0
-        self.ncycles = []
-        for k in range(self.nspan):
-            self.plan.set_plates(*self.plates[k], plate_sets=self.batch)
-            res = self.plan.execute(field)
-            self.ncycles.append(res.ncycle.copy())
-            sa_steps += int(res.ncycle.sum()) * n * self.setup.nfc
-            _lib.ampliflat_exec(self.ctx, field, self.gain, self.sigma, None if noise_fn is None else noise_fn(k),
-                                seed=self.ase_seed(ase_seed, k))
-        return sa_steps
+        noise = None if noise_fn is None else np.stack([np.asarray(noise_fn(k), dtype=np.complex128)
+                                                        for k in range(self.nspan)])
+        link, keep = _lib.make_link(
+            self.nspan, self.gain, self.sigma, plates=[np.stack([pl[i] for pl in self.plates]) for i in range(3)],
+            plate_sets=self.batch, noise=noise, seeds=[self.ase_seed(ase_seed, k) for k in range(self.nspan)])
+        res = self.plan.link_exec(field, link, keep)            # the span loop runs inside the library
+        ncyc = res.ncycle.reshape(self.nspan, self.batch)
+        self.ncycles = [ncyc[k].copy() for k in range(self.nspan)]
+        return int(ncyc.sum()) * n * self.setup.nfc
 
     def ase_seed(self, ase_seed: int, span: int) -> int:
         return ((int(ase_seed) & 0xffffff) << 40) + (span << 32) + self.first

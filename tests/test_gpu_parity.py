@@ -208,3 +208,39 @@ def test_resident_chain_equals_per_call_chain(disp_mode):
         finally:
             gstate.RESIDENT = old
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_link_call_equals_the_script_loop(disp_mode):
+    """pmx_link_run (one call: H2D, nspan x [fiber ; ampliflat] on the device, D2H) gives the bits of the loop of
+    fiber() and ampliflat() calls the reference's scripts write (ex06_ber.m:110-115), with injected and with
+    device-generated ASE; the oracle agrees on the injected-noise link"""
+    fib = base_fiber(length=2e4, dgd=0.3, nplates=12, manakov='yes')
+    nspan, n = 3, 1 << 14
+    g = np.random.Generator(np.random.PCG64(9))
+    noise = [g.standard_normal((n, 4)).view(np.complex128).copy() for _ in range(nspan)]
+    for opts_of in (lambda k: {'f': 5.0, 'noise': noise[k]}, lambda k: {'f': 5.0}):
+        gs = make_tx(1 << 10, 16)
+        G = pmx.GSTATE
+        r = np.random.Generator(np.random.PCG64(77))
+        brfs, ncyc = [], []
+        for k in range(nspan):
+            brfs.append(pmx.fiber(fib, 'gps-', rng=r))
+            ncyc.append(pmx.FIBER_LAST['ncycle'])
+            pmx.ampliflat(4.0, 'gain', opts_of(k), seed=300 + k)
+        loop = (np.array(G.FIELDX), np.array(G.FIELDY), np.array(G.DELAY), np.array(G.DISP))
+        make_tx(1 << 10, 16)
+        o = opts_of(0)
+        if 'noise' in o:
+            o['noise'] = noise
+        out = pmx.link(fib, 'gps-', nspan, 4.0, o, rng=np.random.Generator(np.random.PCG64(77)), seed=300)
+        assert np.array_equal(G.FIELDX, loop[0]) and np.array_equal(G.FIELDY, loop[1])
+        assert np.array_equal(G.DELAY, loop[2]) and np.array_equal(G.DISP, loop[3])
+        assert pmx.FIBER_LAST['ncycle_per_span'] == ncyc and len(out) == nspan
+        for a, b in zip(out, brfs):
+            assert np.array_equal(a['theta'], b['theta']) and np.array_equal(a['db0'], b['db0']) and a['lcorr'] == b['lcorr']
+        if 'noise' in o:
+            ro = np.random.Generator(np.random.PCG64(77))
+            for k in range(nspan):
+                orc.fiber(gs, fib, 'gps-', rng=ro)
+                orc.ampliflat(gs, 4.0, 5.0, noise=noise[k])
+            assert rel_l2(G.FIELDX, G.FIELDY, gs.FIELDX, gs.FIELDY) < TOL
