@@ -18,7 +18,18 @@
  *   fls        1 x 4 flag vector                      (fiber.m:157)
  *   db0,theta,epsilon   nplates x 1                   (brf.*, fiber.m:266-276)
  *   scal       optional [symbolrate nsymb nt b30 dgdrms beta1(1:nfc) beta2(1:nfc)]: the library
- *              regenerates betat/db1 on the device and the two vectors are not uploaded
+ *              regenerates betat/db1 on the device and the two vectors are not uploaded ([] to skip)
+ *
+ * Span loop in one call (the loop  for k=1:Nspan, fiber(x,flag); ampliflat(G,'gain',opt); end  of
+ * ex06_ber.m:110-115; the field crosses PCIe once in and once out, pmx_link_run):
+ *
+ *   [ux,uy,firstdz,ncycle] = ssfm_mex(..., db0,theta,epsilon, scal, amp)
+ *
+ *   db0,theta,epsilon   nplates x Nspan: column k holds the waveplates fiber.m:274-276 draws for span k
+ *   amp        [gain sigma(1:nfc) seed]: linear power gain 10^(G/10) of the amplifier after every span
+ *              (ampliflat.m:62), ASE sigma per column (ampliflat.m:91-106, 0 = noiseless) and the seed of the
+ *              device noise generator (span k uses seed+k-1); [] or absent: fibers only
+ *   firstdz    first step of span 1;  ncycle  1 x Nspan
  *
  * Build (not verifiable in the image this was written in -- it has no mex.h):
  *   mex ssfm_mex.c -I../include -L../polmux_b200/lib -lpolmux_ssfm
@@ -58,14 +69,17 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     pmx_fiber_desc d;
     pmx_field io;
     pmx_fiber_result res;
-    double firstdz = 0.0, gam_buf[16], beta_buf[32];
-    int32_t ncycle = 0, ntot = 0, status = 0;
-    size_t nfft, nfc, n, k;
-    mxArray *uy_out;
-    int rc;
+    pmx_link_desc lk;
+    double gam_buf[16], beta_buf[32], sigma_buf[16];
+    double *firstdz;
+    int32_t *ncycle, *ntot, *status;
+    uint64_t *seeds;
+    size_t nfft, nfc, n, k, nspan;
+    mxArray *uy_out, *work;
+    int rc, is_link;
 
-    if (nrhs != 16 && nrhs != 17)
-        mexErrMsgTxt("ssfm_mex: 16 or 17 input arguments expected (see the header of ssfm_mex.c).");
+    if (nrhs < 16 || nrhs > 18)
+        mexErrMsgTxt("ssfm_mex: 16 to 18 input arguments expected (see the header of ssfm_mex.c).");
     if (nlhs > 4)
         mexErrMsgTxt("ssfm_mex: at most 4 outputs [ux,uy,firstdz,ncycle].");
 
@@ -100,14 +114,20 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     for (k = 0; k < nfc; k++)
         gam_buf[k] = mxGetPr(prhs[6])[mxGetNumberOfElements(prhs[6]) == 1 ? 0 : k];
     d.gam = gam_buf;
-    if ((size_t)d.nplates != mxGetNumberOfElements(prhs[13]) || (size_t)d.nplates != mxGetNumberOfElements(prhs[14]) ||
-        (size_t)d.nplates != mxGetNumberOfElements(prhs[15]))
-        mexErrMsgTxt("ssfm_mex: db0, theta and epsilon must have nplates elements.");
+    /* one column of plates per span: a vector (either orientation) is one span */
+    nspan = (d.nplates > 0) ? mxGetNumberOfElements(prhs[14]) / (size_t)d.nplates : 0;
+    if (nspan < 1 || nspan * (size_t)d.nplates != mxGetNumberOfElements(prhs[14]) ||
+        mxGetNumberOfElements(prhs[13]) != mxGetNumberOfElements(prhs[14]) ||
+        mxGetNumberOfElements(prhs[15]) != mxGetNumberOfElements(prhs[14]))
+        mexErrMsgTxt("ssfm_mex: db0, theta and epsilon must have nplates elements (nplates x Nspan for a span loop).");
+    if (nspan > 1 && mxGetM(prhs[14]) != (size_t)d.nplates)
+        mexErrMsgTxt("ssfm_mex: span loop: db0, theta and epsilon must be nplates x Nspan.");
+    is_link = nspan > 1 || (nrhs == 18 && mxGetNumberOfElements(prhs[17]) != 0);
     d.plate_sets = 1;
     d.db0 = mxGetPr(prhs[13]);
     d.theta = mxGetPr(prhs[14]);
     d.epsilon = mxGetPr(prhs[15]);
-    if (nrhs == 17 && mxGetNumberOfElements(prhs[16]) != 0) {
+    if (nrhs >= 17 && mxGetNumberOfElements(prhs[16]) != 0) {
         const double *s = mxGetPr(prhs[16]);
         if (mxGetNumberOfElements(prhs[16]) != 5 + 2 * nfc)
             mexErrMsgTxt("ssfm_mex: scal must be [symbolrate nsymb nt b30 dgdrms beta1(1:nfc) beta2(1:nfc)].");
@@ -152,12 +172,43 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
             fail("ssfm_mex: no usable B200 (there is no CPU fallback)");
         mexAtExit(ssfm_at_exit);
     }
+    /* per-span results live in one scratch matrix owned by the interpreter (freed on error, too) */
+    work = mxCreateDoubleMatrix(4 * nspan, 1, mxREAL);
+    firstdz = mxGetPr(work);
+    ncycle = (int32_t *)(firstdz + nspan);
+    ntot = ncycle + nspan;
+    status = ntot + nspan;
+    seeds = (uint64_t *)(firstdz + 3 * nspan);
     memset(&res, 0, sizeof res);
-    res.firstdz = &firstdz;
-    res.ncycle = &ncycle;
-    res.ntot = &ntot;
-    res.status = &status;
-    rc = pmx_fiber_run(g_ctx, &d, &io, &res);
+    res.firstdz = firstdz;
+    res.ncycle = ncycle;
+    res.ntot = ntot;
+    res.status = status;
+    if (is_link) {
+        memset(&lk, 0, sizeof lk);
+        lk.nspan = (int32_t)nspan;
+        lk.plate_sets = 1;
+        lk.db0 = d.db0; /* nplates x Nspan column-major == [nspan][1][nplates] */
+        lk.theta = d.theta;
+        lk.epsilon = d.epsilon;
+        if (nrhs == 18 && mxGetNumberOfElements(prhs[17]) != 0) {
+            const double *a = mxGetPr(prhs[17]);
+            if (mxGetNumberOfElements(prhs[17]) != 2 + nfc)
+                mexErrMsgTxt("ssfm_mex: amp must be [gain sigma(1:nfc) seed].");
+            if (!(a[0] > 0.0))
+                mexErrMsgTxt("ssfm_mex: amp(1) is the linear power gain 10^(G/10) and must be positive.");
+            lk.gain = a[0];
+            for (k = 0; k < nfc; k++)
+                sigma_buf[k] = a[1 + k];
+            lk.sigma = sigma_buf;
+            for (k = 0; k < nspan; k++)
+                seeds[k] = (uint64_t)a[1 + nfc] + (uint64_t)k;
+            lk.seeds = seeds;
+        }
+        rc = pmx_link_run(g_ctx, &d, &lk, &io, &res);
+    } else {
+        rc = pmx_fiber_run(g_ctx, &d, &io, &res);
+    }
     if (nlhs > 1)
         plhs[1] = uy_out;
     else
@@ -169,10 +220,12 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 
     if (nlhs > 2) {
         plhs[2] = mxCreateDoubleMatrix(1, 1, mxREAL);
-        *mxGetPr(plhs[2]) = firstdz;
+        *mxGetPr(plhs[2]) = firstdz[0];
     }
     if (nlhs > 3) {
-        plhs[3] = mxCreateDoubleMatrix(1, 1, mxREAL);
-        *mxGetPr(plhs[3]) = (double)ncycle;
+        plhs[3] = mxCreateDoubleMatrix(1, nspan, mxREAL);
+        for (k = 0; k < nspan; k++)
+            mxGetPr(plhs[3])[k] = (double)ncycle[k];
     }
+    mxDestroyArray(work);
 }

@@ -4,10 +4,11 @@
  *
  *   test_ssfm_mex in.bin out.bin
  *
- * in.bin : int64 header {nfft, nfc, nplates, manakov, fls[4], has_uy_imag, use_scal, nscal}
+ * in.bin : int64 header {nfft, nfc, nplates, manakov, fls[4], has_uy_imag, use_scal, nscal, nspan, namp}
  *          then doubles: dzmaxt dphimaxt alphalin Lf, gam[nfc], uxr uxi uyr uyi [nfft*nfc each],
- *          betat db1 [nfft*nfc each], db0 theta epsilon [nplates each], scal[nscal]
- * out.bin: doubles {status, firstdz, ncycle}, uxr uxi uyr uyi     (status 1 = mexErrMsgTxt, message on stderr)
+ *          betat db1 [nfft*nfc each], db0 theta epsilon [nplates*nspan each, span after span], scal[nscal], amp[namp]
+ * out.bin: doubles {status, firstdz, ncycle(1)}, uxr uxi uyr uyi, ncycle[nspan]
+ *          (status 1 = mexErrMsgTxt, message on stderr)
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -31,18 +32,19 @@ static mxArray *scal(double v)
 
 int main(int argc, char **argv)
 {
-    int64_t h[11];
+    int64_t h[13];
     double s4[4];
-    const mxArray *prhs[17];
+    const mxArray *prhs[18];
     mxArray *plhs[4] = {0, 0, 0, 0};
     FILE *f, *o;
-    size_t nfft, nfc, n, np;
+    size_t nfft, nfc, n, np, nspan;
     int rc, nrhs, k;
     double hdr[3];
     if (argc != 3) return 2;
     f = fopen(argv[1], "rb");
-    if (!f || fread(h, sizeof(int64_t), 11, f) != 11) return 3;
+    if (!f || fread(h, sizeof(int64_t), 13, f) != 13) return 3;
     nfft = (size_t)h[0], nfc = (size_t)h[1], np = (size_t)h[2];
+    nspan = (size_t)h[11];
     n = nfft * nfc;
     if (fread(s4, sizeof(double), 4, f) != 4) return 3;
     {
@@ -51,9 +53,10 @@ int main(int argc, char **argv)
         mxArray *uy = vec(f, nfft, nfc, 1);
         mxArray *betat = vec(f, nfft, nfc, 0);
         mxArray *db1 = vec(f, nfft, nfc, 0);
-        mxArray *db0 = vec(f, np, 1, 0), *theta = vec(f, np, 1, 0), *eps = vec(f, np, 1, 0);
+        mxArray *db0 = vec(f, np, nspan, 0), *theta = vec(f, np, nspan, 0), *eps = vec(f, np, nspan, 0);
         mxArray *fls = mxCreateDoubleMatrix(1, 4, mxREAL);
         mxArray *sc = vec(f, 1, (size_t)h[10], 0);
+        mxArray *amp = vec(f, 1, (size_t)h[12], 0);
         if (!h[8]) { /* exercise the "purely real array has no imaginary plane" branch */
             free(uy->pi);
             uy->pi = NULL;
@@ -64,7 +67,8 @@ int main(int argc, char **argv)
         prhs[8] = scal((double)nfc); prhs[9] = scal(s4[3]); prhs[10] = scal((double)np);
         prhs[11] = scal((double)h[3]); prhs[12] = fls; prhs[13] = db0; prhs[14] = theta; prhs[15] = eps;
         prhs[16] = sc;
-        nrhs = h[9] ? 17 : 16;
+        prhs[17] = amp;
+        nrhs = h[12] ? 18 : (h[9] ? 17 : 16);
     }
     fclose(f);
     rc = mex_shim_call(4, plhs, nrhs, prhs);
@@ -81,6 +85,7 @@ int main(int argc, char **argv)
         fwrite(plhs[0]->pi, sizeof(double), n, o);
         fwrite(plhs[1]->pr, sizeof(double), n, o);
         fwrite(plhs[1]->pi, sizeof(double), n, o);
+        fwrite(plhs[3]->pr, sizeof(double), nspan, o);
     }
     fclose(o);
     mex_shim_run_at_exit();
