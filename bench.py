@@ -338,17 +338,23 @@ def main():
         # one untimed pass first: plans, tensor maps, twiddle tables and the allocator's pools are created once
         mc.run_mc(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nreal, B,
                   rank, world, ase_seed=7)
-        barrier()
-        t0 = time.perf_counter()
-        counts, _ = mc.run_mc(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nreal, B,
-                              rank, world, ase_seed=7)
-        barrier()
-        dt = time.perf_counter() - t0
-        tdt = torch.tensor([dt], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        # three timed passes, the median reported: the pass is short (0.36 s) and an occasional host-side stall of a few
+        # hundred ms in its set-up (allocations, plan creation) was seen on the shared boxes
+        mc_times = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            counts, _ = mc.run_mc(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nreal, B,
+                                  rank, world, ase_seed=7)
+            barrier()
+            tdt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+            if world > 1:
+                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            mc_times.append(float(tdt[0]))
+        tdt = torch.tensor([sorted(mc_times)[1]], dtype=torch.float64)
         rep = mc.ber_replay(counts, 4 * NSYMB, stop=(0.1, 68.0), nmin=100)
         mcres = {'realizations_per_s': nreal / float(tdt[0]), 'realizations': nreal, 'seconds': float(tdt[0]),
+                 'timing': 'median of 3 passes (max over ranks each): %s s' % ', '.join('%.3f' % v for v in mc_times),
                  'errors_total': int(counts.sum()), 'bits_per_realization': 4 * NSYMB, 'avgber': rep['avgber'],
                  'count_reduce': 'all_reduce(int64[%d], sum) over %d rank(s), backend %s'
                                  % (nreal, world, 'nccl' if world > 1 else 'none (single rank)')}
