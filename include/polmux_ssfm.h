@@ -217,6 +217,20 @@ int pmx_link_exec(pmx_plan* plan, pmx_devfield* f, const pmx_link_desc* link, pm
 int pmx_link_run(pmx_ctx* ctx, const pmx_fiber_desc* desc, const pmx_link_desc* link, pmx_field* io,
                  pmx_fiber_result* out);
 
+/* ---- create_field('unique'): the WDM multiplex on the device (create_field.m:113-149,180-199) ----------------
+ * The reference builds the single field as
+ *   FIELDX = ifft( sum_ch fastshift( fft(sigx(:,ch)), -ndfn(ch) ) ),   ndfn = round(deltafn/SYMBOLRATE/minfreq)
+ * A circular shift of the spectrum by -ndfn bins is the modulation exp(-2*pi*i*ndfn*n/nfft) in time, so the same
+ * field is  sum_ch scale(ch) * sig(mod(n - delay(ch), nfft), ch) * exp(-2*pi*i*ndfn(ch)*n/nfft)  -- one pointwise
+ * pass, no transform (the phase index ndfn*n is reduced modulo nfft in integers, the argument of sincospi is exact).
+ *   f      : batch 1, nfc 1 field to fill (either precision)
+ *   sig    : HOST arrays [nch][nfft] per polarization (PMX_COMPLEX: xr -> X, yr -> Y or NULL; PMX_PLANAR likewise)
+ *   ndfn   : [nch] frequency offsets in bins (create_field.m:183)
+ *   scale  : [nch] amplitude factors (options.power = 'average', :113-124) or NULL (ones)
+ *   delayx, delayy : [nch] integer sample delays per polarization (options.delay, :127-146) or NULL (zeros) */
+int pmx_field_mux(pmx_devfield* f, const pmx_field* sig, int32_t nch, const int64_t* ndfn, const double* scale,
+                  const int64_t* delayx, const int64_t* delayy);
+
 /* ---- integer error counting (ber_estimate.m:118) --------------------------------
  * counts[b] = #{ i : pat_hat[b][i] != pat[i] } over n symbols-bits, on the device. */
 int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pat_dev, int64_t n,

@@ -29,7 +29,7 @@ EXPORTS = [
     'pmx_plan_create', 'pmx_plan_destroy', 'pmx_plan_set_plates', 'pmx_fiber_exec',
     'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
-    'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run',
+    'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux',
 ]
 
 
@@ -119,6 +119,8 @@ def load():
     lib.pmx_field_max_power.argtypes = [vp, vp, _dp]
     lib.pmx_field_maxdiff2.argtypes = [vp, vp, vp, _dp]
     lib.pmx_field_lincomb.argtypes = [vp, vp, C.c_double, vp, C.c_double, vp]
+    lib.pmx_field_mux.argtypes = [vp, C.POINTER(Field), C.c_int32, C.POINTER(C.c_int64), _dp, C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64)]
     lib.pmx_link_exec.argtypes = [vp, vp, C.POINTER(LinkDesc), C.POINTER(FiberResult)]
     lib.pmx_link_run.argtypes = [vp, C.POINTER(FiberDesc), C.POINTER(LinkDesc), C.POINTER(Field), C.POINTER(FiberResult)]
     _lib = lib
@@ -392,6 +394,22 @@ def make_link(nspan, gain=0.0, sigma=None, plates=None, plate_sets=1, noise=None
             raise ValueError('one ASE seed per span')
         l.seeds = keep['seeds'].ctypes.data_as(C.POINTER(C.c_uint64))
     return l, keep
+
+
+def field_mux(ctx: Context, field: DeviceField, sigx, sigy, ndfn, scale=None, delayx=None, delayy=None):
+    """create_field('unique') on the device (pmx_field_mux): sigx/sigy [nfft, nch] complex (GSTATE layout)."""
+    nch = int(np.shape(sigx)[1])
+    xs = np.ascontiguousarray(np.asarray(sigx, dtype=np.complex128).T)          # [nch][nfft]
+    ys = np.ascontiguousarray(np.asarray(sigy, dtype=np.complex128).T) if sigy is not None else None
+    f = complex_field(xs, ys)
+    i64 = C.POINTER(C.c_int64)
+    nd = np.ascontiguousarray(ndfn, dtype=np.int64)
+    sc = _f64(scale) if scale is not None else None
+    dx = np.ascontiguousarray(delayx, dtype=np.int64) if delayx is not None else None
+    dy = np.ascontiguousarray(delayy, dtype=np.int64) if delayy is not None else None
+    ctx.check(ctx.lib.pmx_field_mux(field.h, C.byref(f), nch, nd.ctypes.data_as(i64), _ptr(sc),
+                                    dx.ctypes.data_as(i64) if dx is not None else None,
+                                    dy.ctypes.data_as(i64) if dy is not None else None))
 
 
 def scalar_nl_exec(ctx: Context, field: DeviceField, gam, leff: float, atten: float, spm: bool, xpm: bool):

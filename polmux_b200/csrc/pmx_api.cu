@@ -1238,6 +1238,105 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
 }
 
 // ---------------------------------------------------------------------------
+// create_field('unique') (create_field.m:180-199): sum over the channels of the modulated (and delayed, scaled)
+// channel fields, written straight into the resident layout
+#define PMX_MUX_MAXCH 64
+struct MuxParams {
+    const double2* sx;  // [nch][N]
+    const double2* sy;  // [nch][N] or null
+    void* dst;
+    long long ndfn[PMX_MUX_MAXCH], dlx[PMX_MUX_MAXCH], dly[PMX_MUX_MAXCH];
+    double scale[PMX_MUX_MAXCH];
+    size_t N;
+    int nch, lg, l1;
+};
+template <typename T2>
+__global__ void __launch_bounds__(256) pmx_k_mux(const __grid_constant__ MuxParams a) {
+    const size_t N = a.N, mask = N - 1;
+    const double inv = 2.0 / (double)N;
+    T2* dst = reinterpret_cast<T2*>(a.dst);
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+        double xr = 0.0, xi = 0.0, yr = 0.0, yi = 0.0;
+        for (int ch = 0; ch < a.nch; ++ch) {
+            // exp(-2*pi*i*ndfn*n/N): (ndfn*n) mod N in integers (N is a power of two), exact argument for sincospi
+            const unsigned long long r = ((unsigned long long)a.ndfn[ch] * (unsigned long long)n) & mask;
+            double s, c;
+            sincospi(-(double)r * inv, &s, &c);
+            const double sc = a.scale[ch];
+            const double2 vx = a.sx[(size_t)ch * N + ((n - (size_t)a.dlx[ch]) & mask)];
+            const double ar = vx.x * sc, ai = vx.y * sc;
+            xr += ar * c - ai * s;
+            xi += ar * s + ai * c;
+            if (a.sy) {
+                const double2 vy = a.sy[(size_t)ch * N + ((n - (size_t)a.dly[ch]) & mask)];
+                const double br = vy.x * sc, bi = vy.y * sc;
+                yr += br * c - bi * s;
+                yi += br * s + bi * c;
+            }
+        }
+        const size_t m = pmx_mem_index(n, a.l1, a.lg - a.l1);
+        dst[2 * m] = pmx_mk2<T2>(xr, xi);
+        dst[2 * m + 1] = pmx_mk2<T2>(yr, yi);
+    }
+}
+
+extern "C" int pmx_field_mux(pmx_devfield* f, const pmx_field* sig, int32_t nch, const int64_t* ndfn, const double* scale,
+                             const int64_t* delayx, const int64_t* delayy) {
+    if (!f) return set_err(nullptr, PMX_ERR_INVALID, "pmx_field_mux: null field");
+    pmx_ctx* c = f->ctx;
+    if (!sig || !sig->xr || !ndfn) return set_err(c, PMX_ERR_INVALID, "pmx_field_mux: null argument");
+    if (f->batch != 1 || f->nfc != 1) return set_err(c, PMX_ERR_INVALID, "pmx_field_mux: the multiplexed field has one column, batch 1");
+    if (nch < 1 || nch > PMX_MUX_MAXCH) return set_err(c, PMX_ERR_INVALID, "pmx_field_mux: 1..%d channels, got %d", PMX_MUX_MAXCH, nch);
+    const int lg = ilog2_exact(f->nfft);
+    if (lg < 0) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_field_mux: nfft must be a power of two");
+    CK(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)f->nfft, n = (size_t)nch * N;
+    MuxParams a;
+    memset(&a, 0, sizeof a);
+    const bool has_y = sig->layout == PMX_PLANAR ? (sig->yr != nullptr) : (sig->yr != nullptr);
+    double2* stage = nullptr;
+    CK(c, cudaMallocAsync(&stage, (has_y ? 2 : 1) * n * sizeof(double2), c->stream));
+    if (sig->layout == PMX_COMPLEX) {
+        CK(c, cudaMemcpyAsync(stage, sig->xr, n * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+        if (has_y) CK(c, cudaMemcpyAsync(stage + n, sig->yr, n * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    } else if (sig->layout == PMX_PLANAR) {  // interleave on the way: strided 2-D copies of the two planes
+        const double* planes[4] = {sig->xr, sig->xi, sig->yr, sig->yi};
+        CK(c, cudaMemsetAsync(stage, 0, (has_y ? 2 : 1) * n * sizeof(double2), c->stream));
+        for (int k = 0; k < (has_y ? 4 : 2); ++k)
+            if (planes[k])
+                CK(c, cudaMemcpy2DAsync((double*)(stage + (k / 2) * n) + (k & 1), sizeof(double2), planes[k], sizeof(double),
+                                        sizeof(double), n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        cudaFreeAsync(stage, c->stream);
+        return set_err(c, PMX_ERR_INVALID, "unknown layout %d", sig->layout);
+    }
+    a.sx = stage;
+    a.sy = has_y ? stage + n : nullptr;
+    a.dst = f->data;
+    a.N = N;
+    a.nch = nch;
+    a.lg = lg;
+    a.l1 = f->log2N1 + f->log2N2 == lg ? f->log2N1 : 0;
+    if (f->log2N1 + f->log2N2 != lg) a.lg = 0, a.l1 = 0;  // natural order (sizes without tensor maps)
+    for (int k = 0; k < nch; ++k) {
+        a.ndfn[k] = (long long)(((ndfn[k] % (int64_t)N) + (int64_t)N) % (int64_t)N);
+        a.scale[k] = scale ? scale[k] : 1.0;
+        a.dlx[k] = delayx ? (long long)(((delayx[k] % (int64_t)N) + (int64_t)N) % (int64_t)N) : 0;
+        a.dly[k] = delayy ? (long long)(((delayy[k] % (int64_t)N) + (int64_t)N) % (int64_t)N) : 0;
+    }
+    const int blocks = (int)std::min<size_t>((N + 255) / 256, 148 * 16);
+    if (f->precision == PMX_F32)
+        pmx_k_mux<float2><<<blocks, 256, 0, c->stream>>>(a);
+    else
+        pmx_k_mux<double2><<<blocks, 256, 0, c->stream>>>(a);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaFreeAsync(stage, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));  // the host arrays belong to the caller
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
 // span loop (ex06_ber.m:110-115): nspan x [ fiber ; ampliflat ] on a resident field
 extern "C" int pmx_link_exec(pmx_plan* p, pmx_devfield* f, const pmx_link_desc* l, pmx_fiber_result* out) {
     if (!p || !f || !l) return set_err(p ? p->ctx : nullptr, PMX_ERR_INVALID, "pmx_link_exec: null argument");

@@ -10,6 +10,11 @@ import numpy as np
 
 from .gstate import CONSTANTS, GSTATE
 
+# True: create_field('unique', ...) of a two-polarization field multiplexes the channels on the device
+# (pmx_field_mux: one pointwise modulation pass instead of the reference's fft / fastshift / ifft) and leaves
+# GSTATE.FIELDX/FIELDY resident in HBM for the first fiber().  False (default): the reference's host arithmetic.
+DEVICE_MUX = False
+
 
 def _shift(v, n):  # fastshift.m:45-58 (n > 0 delays)
     return np.roll(v, int(n), axis=0)
@@ -39,13 +44,18 @@ def create_field(ftype, sigx, sigy=None, options=None):
     if sigx.shape[1] != G.NCH:
         raise ValueError('the number of columns of sigx,sigy must be equal to the number of channels')
     power = np.asarray(G.POWER, dtype=np.float64).reshape(-1)
+    ft = ftype.lower()
+    on_device = DEVICE_MUX and ft == 'unique' and isy
+    scale = np.ones(G.NCH)
     if str(options.get('power', '')).lower() == 'average':                   # :113-124
         avge = np.mean(np.abs(sigx) ** 2 + (np.abs(sigy) ** 2 if isy else 0.0), axis=0)
-        s = np.sqrt(power / avge)
-        sigx = sigx * s[None, :]
-        if isy:
-            sigy = sigy * s[None, :]
+        scale = np.sqrt(power / avge)
+        if not on_device:
+            sigx = sigx * scale[None, :]
+            if isy:
+                sigy = sigy * scale[None, :]
         G.POWER = power * power / avge
+    tau = np.zeros((npol, G.NCH))
     if 'delay' in options:                                                   # :127-146
         if isinstance(options['delay'], str) and options['delay'] == 'rand':
             from .gstate import rng
@@ -55,15 +65,15 @@ def create_field(ftype, sigx, sigy=None, options=None):
             if d.shape != (npol, G.NCH):
                 raise ValueError('the delay must be of size [number of polarizations,number of channels]')
             tau = np.round(d * G.NT)
-        for kch in range(G.NCH):
-            sigx[:, kch] = _shift(sigx[:, kch], tau[0, kch])
-            if isy:
-                sigy[:, kch] = _shift(sigy[:, kch], tau[1, kch])
+        if not on_device:
+            for kch in range(G.NCH):
+                sigx[:, kch] = _shift(sigx[:, kch], tau[0, kch])
+                if isy:
+                    sigy[:, kch] = _shift(sigy[:, kch], tau[1, kch])
         G.DELAY = tau
     else:
         G.DELAY = np.zeros((npol, G.NCH))
     G.DISP = np.zeros((npol, G.NCH))                                         # :151
-    ft = ftype.lower()
     if ft == 'sepfields':                                                    # :156-162
         G.FIELDX_TX, G.FIELDX = sigx.copy(), sigx
         if isy:
@@ -81,6 +91,22 @@ def create_field(ftype, sigx, sigy=None, options=None):
         deltafn = CONSTANTS.CLIGHT * (1 / lamc - 1.0 / lamt)
         minfreq = G.FN[1] - G.FN[0]
         ndfn = np.round(deltafn / G.SYMBOLRATE / minfreq).astype(np.int64)
+        if on_device:
+            # fastshift(fft(sig), -ndfn) is the modulation exp(-2*pi*i*ndfn*n/Nfft) in time: one pointwise pass
+            # over the channels on the device, no transform; the field stays in HBM for the first fiber()
+            from . import _lib
+            ctx = _lib.default_context()
+            fld = _lib.DeviceField(ctx, nfft, 1, 1)
+            try:
+                _lib.field_mux(ctx, fld, sigx, sigy, ndfn, scale, tau[0], tau[1])
+                ox, oy = fld.download()
+            except Exception:
+                fld.close()
+                raise
+            G.FIELDX_TX = np.ascontiguousarray(ox[0].T)
+            G.FIELDY_TX = np.ascontiguousarray(oy[0].T)
+            G.put_device(fld, None, None)
+            return
         zx = np.fft.fft(sigx, axis=0)
         fx = np.zeros(nfft, dtype=np.complex128)
         fy = np.zeros(nfft, dtype=np.complex128) if isy else None

@@ -244,3 +244,39 @@ def test_link_call_equals_the_script_loop(disp_mode):
                 orc.fiber(gs, fib, 'gps-', rng=ro)
                 orc.ampliflat(gs, 4.0, 5.0, noise=noise[k])
             assert rel_l2(G.FIELDX, G.FIELDY, gs.FIELDX, gs.FIELDY) < TOL
+
+
+@pytest.mark.parametrize('nch,lg,delay', [(3, 14, True), (9, 16, False), (1, 13, True)])
+def test_create_field_unique_on_device(nch, lg, delay):
+    """create_field('unique') with the multiplex on the device (field.DEVICE_MUX: spectrum shift = modulation in time,
+    one pointwise pass) against the reference's fft / fastshift / ifft arithmetic on the host (create_field.m:180-199),
+    with options.power = 'average' and integer-sample delays; the field it leaves in HBM feeds fiber() directly"""
+    from polmux_b200 import field as fmod, synth
+    nt = 64
+    nsymb = (1 << lg) // nt
+    ex, ey, _, _ = synth.pdm_qpsk(nsymb, nt, nch)
+    lams = synth.wdm_lambdas(nch, 1550.0, 0.4)
+    opts = {'power': 'average'}
+    if delay:
+        opts['delay'] = np.random.Generator(np.random.PCG64(3)).random((2, nch))
+    res = {}
+    for dev in (False, True):
+        pmx.reset_all(nsymb, nt, nch)
+        G = pmx.GSTATE
+        G.SYMBOLRATE, G.LAMBDA, G.POWER = 28.0, lams.copy(), np.full(nch, 1.0)
+        old = fmod.DEVICE_MUX
+        fmod.DEVICE_MUX = dev
+        try:
+            pmx.create_field('unique', ex, ey, dict(opts))
+        finally:
+            fmod.DEVICE_MUX = old
+        assert G.is_resident() == dev
+        tx = (np.array(G.FIELDX_TX), np.array(G.FIELDY_TX))
+        pw, dl = np.array(G.POWER), np.array(G.DELAY)
+        fib = base_fiber(length=2e4, dgd=0.2, nplates=10, manakov='yes')
+        pmx.fiber(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(8)))
+        res[dev] = (tx, pw, dl, np.array(G.FIELDX), np.array(G.FIELDY), pmx.FIBER_LAST['ncycle'])
+    h, d = res[False], res[True]
+    assert rel_l2(d[0][0], d[0][1], h[0][0], h[0][1]) < 1e-13
+    assert np.array_equal(h[1], d[1]) and np.array_equal(h[2], d[2])
+    assert rel_l2(d[3], d[4], h[3], h[4]) < 1e-11 and h[5] == d[5]
