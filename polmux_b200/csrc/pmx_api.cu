@@ -1022,9 +1022,18 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
             q->pdl = use_pdl;
         }
         const int tilesAC = (p->N2 / p->tA->gAC) * G.nb * nfc, tilesB = (p->N1 / p->tB->gB) * G.nb * nfc;
-        G.gA = std::min(tilesAC, (int)(std::max(1, oA.a / grid_div) * c->sm_count * grid_mul));
-        G.gB = std::min(tilesB, (int)(std::max(1, oB.b / grid_div) * c->sm_count * grid_mul));
-        G.gC = std::min(tilesAC, (int)(std::max(1, oA.c / grid_div) * c->sm_count * grid_mul));
+        // Persistent grids of one CTA per resident slot -- except when a pass has between one and two rounds of
+        // tiles (a batch of one at N = 2^20: 1024 tiles on 592 slots): then one CTA per tile, so that the hardware
+        // hands the tiles of the partial second round to whichever slot frees first (measured +8 % at batch 1, N = 2^20;
+        // with more rounds the persistent grid is the faster one, PMX_GRID_MUL sweeps in DESIGN.md)
+        auto grid_of = [&](int tiles, int ctas_per_sm) {
+            const int slots = (int)(std::max(1, ctas_per_sm / grid_div) * c->sm_count * grid_mul);
+            if (!getenv("PMX_GRID_MUL") && tiles > slots && tiles <= 2 * slots) return tiles;
+            return std::min(tiles, slots);
+        };
+        G.gA = grid_of(tilesAC, oA.a);
+        G.gB = grid_of(tilesB, oB.b);
+        G.gC = grid_of(tilesAC, oA.c);
     }
     static const bool serp = !getenv("PMX_NO_SERPENTINE");
     int chunk = p->single_step ? 1 : 8;
