@@ -5,7 +5,7 @@ Workload (config.workload = "C2"): PDM-QPSK, 2^16 symbols x 16 samples = 2^20 sa
 polarization, 10 spans of (80 km SMF, 'gps-' Manakov, 100 random waveplates, DGD 0.1 symbol)
 each followed by a 16 dB flat amplifier with ASE (noise figure 5 dB), FP64.  One "step" is
 one pass of that 10-span link over a batch of independent realizations (different plate
-draws and ASE seeds, same Tx field) resident in HBM; the batch (8 x 32 MiB = 256 MiB) is
+draws and ASE seeds, same Tx field) resident in HBM; the batch (16 x 32 MiB = 512 MiB) is
 larger than the 126 MB L2.
 
   value  Sum(N * ncycle) / time, fields resident in HBM, timed with CUDA events on the
@@ -160,7 +160,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=8, help='realizations per GPU per step')
+    ap.add_argument('--batch', type=int, default=16, help='realizations per GPU per step')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-mc', action='store_true')
