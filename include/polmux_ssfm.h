@@ -112,6 +112,11 @@ typedef struct pmx_fiber_desc {
     double dgdrms;         /* fiber.m:269/277/284 [ns]; 0 without the 'p' flag */
     const double* beta1;   /* [nfc] fiber.m:323/327 */
     const double* beta2;   /* [nfc] fiber.m:330-332 */
+    /* Resuming a propagation part-way (scalar_ssfm with x.dphiadapt, fiber.m:588-611: the first step is taken by the
+     * local-error method on the host side of the boundary, the loop then starts at zprop = zdone + dz with the step the
+     * adaptive method proposed).  Both zero: a fresh fiber, first step from nextstep (fiber.m:512 / :585). */
+    double z_start;        /* [m] length already propagated when the loop starts */
+    double dz_first;       /* [m] first step of the loop; 0 = nextstep on the incoming field */
 } pmx_fiber_desc;
 
 typedef struct pmx_field {

@@ -121,3 +121,9 @@ if __name__ == '__main__':
     run_case('scalar_ltol_gs', 256, 16, 1, 'unique', fib(length=3e4, ltol=1e-6), 'g-s-', two_pol=False, want_brf=False)
     run_case('scalar_ltol_sep3_gsx', 256, 16, 3, 'sepfields', fib(length=2e4, ltol=2e-6, slope=0.057), 'g-sx', two_pol=False,
              want_brf=False)
+    # x.dphiadapt (scalar_ssfm with tolflag 1, fiber.m:588-611): first step by the local-error method, dphimax
+    # recalibrated from it, the rest by the phase criterion (52 steps in the first case)
+    run_case('scalar_dphiadapt_gs', 256, 16, 1, 'unique', fib(length=5e4, ltol=1e-6, dphiadapt=True), 'g-s-', two_pol=False,
+             want_brf=False)
+    run_case('scalar_dphiadapt_sep3_gsx', 256, 16, 3, 'sepfields', fib(length=3e4, ltol=2e-6, dphiadapt=True, slope=0.057),
+             'g-sx', two_pol=False, want_brf=False)

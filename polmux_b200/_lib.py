@@ -52,6 +52,7 @@ class FiberDesc(C.Structure):
         ('epsilon', _dp), ('betat', _dp), ('db1', _dp),
         ('disp_mode', C.c_int32), ('nsymb', C.c_int32), ('nt', C.c_int32), ('scalar_field', C.c_int32),
         ('symbolrate', C.c_double), ('b30', C.c_double), ('dgdrms', C.c_double), ('beta1', _dp), ('beta2', _dp),
+        ('z_start', C.c_double), ('dz_first', C.c_double),
     ]
 
 
@@ -193,7 +194,8 @@ def default_context(device: int = 0) -> Context:
 
 
 def make_desc(nfft, nfc, batch, length, alphalin, dzmaxt, dphimaxt, gam, fls, manakov, nplates,
-              db0, theta, epsilon, betat, db1, plate_sets=1, precision=PMX_F64, scalar=None, scalar_field=False):
+              db0, theta, epsilon, betat, db1, plate_sets=1, precision=PMX_F64, scalar=None, scalar_field=False,
+              z_start=0.0, dz_first=0.0):
     """Build a FiberDesc plus the list of arrays that must stay alive while it is used.
 
     scalar: None (vector dispersion mode: betat/db1 cross the boundary) or a dict with nsymb, nt,
@@ -210,6 +212,7 @@ def make_desc(nfft, nfc, batch, length, alphalin, dzmaxt, dphimaxt, gam, fls, ma
     d.nfft, d.nfc, d.batch, d.precision = int(nfft), int(nfc), int(batch), int(precision)
     d.manakov = 1 if manakov else 0
     d.scalar_field = 1 if scalar_field else 0   # scalar_ssfm dispatch (fiber.m:372-380)
+    d.z_start, d.dz_first = float(z_start), float(dz_first)   # resumed loop (x.dphiadapt, fiber.m:603-609)
     d.length, d.alphalin, d.dzmaxt, d.dphimaxt = float(length), float(alphalin), float(dzmaxt), float(dphimaxt)
     d.gam = _ptr(keep['gam'])
     d.fls = (C.c_int32 * 4)(*[int(v) for v in fls])

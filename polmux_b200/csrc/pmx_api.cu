@@ -747,6 +747,10 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     if (d->plate_sets != 1 && d->plate_sets != d->batch)
         return set_err(c, PMX_ERR_INVALID, "plate_sets must be 1 or batch");
     if (!(d->dzmaxt > 0)) return set_err(c, PMX_ERR_INVALID, "dzmaxt must be > 0");
+    if (d->z_start < 0 || d->dz_first < 0 || d->z_start != d->z_start || d->dz_first != d->dz_first)
+        return set_err(c, PMX_ERR_INVALID, "z_start and dz_first must be >= 0");
+    if ((d->z_start > 0 || d->dz_first > 0) && d->fls[1])
+        return set_err(c, PMX_ERR_UNSUPPORTED, "a resumed propagation (z_start / dz_first) is built for fibers without the 'p' flag");
     CK(c, cudaSetDevice(c->device));
 
     pmx_plan* p = new (std::nothrow) pmx_plan();
@@ -800,6 +804,8 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     f.keep_basis = (f.pmd && (f.manakov || !f.spm)) ? 1 : 0;
     f.scalar_field = d->scalar_field ? 1 : 0;
     f.xpm = (d->scalar_field && d->fls[3]) ? 1 : 0;
+    f.z_start = d->z_start;
+    f.dz_first = d->dz_first;
     f.nfc_magic = d->nfc > 1 ? (unsigned)((0x100000000ull + d->nfc - 1) / d->nfc) : 0u;
     const size_t N = (size_t)d->nfft;
     p->single_step = std::isinf(d->dphimaxt) && d->dzmaxt >= d->length;

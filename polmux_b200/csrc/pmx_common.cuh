@@ -114,6 +114,7 @@ struct FiberConst {
     double w0, inv_nsymb, b30_6, dgdrms, domega;  // domega = w0*NT/8: spacing of a thread's bins
     double g1r, g1i;                              // exp(-i*0.5*dgdrms*domega)
     double beta1[PMX_MAX_NFC], beta2[PMX_MAX_NFC];
+    double z_start, dz_first;  // loop resumed at zprop = z_start + dz_first (pmx_fiber_desc); 0/0 = fresh fiber
 };
 
 struct PassParams {

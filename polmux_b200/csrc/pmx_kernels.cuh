@@ -54,8 +54,9 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
         dz = (step > f.dzmax) ? f.dzmax : step;
     }
     if (first) {
+        if (f.dz_first > 0.0) dz = f.dz_first;  // resumed propagation: the caller hands the step in (fiber.m:603-609)
         c->firstdz = dz;
-        c->zprop = dz;
+        c->zprop = __dadd_rn(f.z_start, dz);
         c->ncycle = 1;
         c->ntot = 0;
         c->dz_miss = 0.0;

@@ -16,6 +16,7 @@ scalar_a_ssfm / adaptssfm, :639-679, :938-1010) is not available.
 """
 from __future__ import annotations
 
+import dataclasses
 import math
 from dataclasses import dataclass
 from typing import Optional
@@ -71,7 +72,8 @@ class FiberSetup:
     b1: np.ndarray
     dch: np.ndarray
     scalars: dict            # beta1, beta2, b30, dgdrms, ... (scalar dispersion mode of the C ABI)
-    tolflag: int = 0         # 2: local-error adaptive step (x.ltol), fiber.m:143-155
+    tolflag: int = 0         # x.ltol: 2 = local-error adaptive step throughout, 1 = for the first step only
+                             # (x.dphiadapt: it calibrates dphimax), fiber.m:143-155
     trg: Optional[dict] = None
 
 
@@ -132,9 +134,8 @@ def fiber_setup(x, flag: str, rng: Optional[np.random.Generator] = None) -> Fibe
     if _has(x, 'ltol'):                                                     # :143-155
         if not _has(x, 'dphimax'):
             xd['dphimax'] = math.inf
-        if _has(x, 'dphiadapt') and _get(x, 'dphiadapt'):
-            raise NotImplementedError('x.dphiadapt (adaptive first step only, fiber.m:588-611) is not built')
-        tolflag, trg = 2, {'err': float(_get(x, 'ltol')), 'safety': SAFETYFCT}
+        adapt_first = _has(x, 'dphiadapt') and bool(_get(x, 'dphiadapt'))           # :147-151
+        tolflag, trg = (1 if adapt_first else 2), {'err': float(_get(x, 'ltol')), 'safety': SAFETYFCT}
     fls, dphimaxt, dzmaxt = flag_to_fls(flag, nfc, xd)
 
     isy = G.has_y()                                                         # :253
@@ -214,7 +215,7 @@ PRECISION = 'f64'   # arithmetic of the device path: 'f64' (default, the referen
 
 
 def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, epsilon=None, disp_mode=None,
-                  precision=None):
+                  precision=None, z_start=0.0, dz_first=0.0):
     """FiberSetup -> (pmx_fiber_desc, keep-alive dict)."""
     mode = disp_mode or DISP_MODE
     prec = {'f64': _lib.PMX_F64, 'f32': _lib.PMX_F32}[precision or PRECISION]
@@ -223,7 +224,7 @@ def setup_to_desc(s: FiberSetup, batch=1, plate_sets=1, db0=None, theta=None, ep
         s.brf['db0'] if db0 is None else db0, s.brf['theta'] if theta is None else theta,
         s.brf['epsilon'] if epsilon is None else epsilon, s.betat, s.db1 if s.fls[1] else None,
         plate_sets=plate_sets, precision=prec, scalar=s.scalars if mode == 'scalar' else None,
-        scalar_field=not s.isv)
+        scalar_field=not s.isv, z_start=z_start, dz_first=dz_first)
 
 
 def apply_side_effects(s: FiberSetup):
@@ -250,70 +251,130 @@ def _nextstep_host(dzmax, phimax, gam, alphalin, umax):
         return float(dzmax) if step > dzmax else float(step)
 
 
-def _scalar_a_ssfm(s: FiberSetup, ctx: _lib.Context, disp_mode=None):
-    """scalar_a_ssfm + adaptssfm (fiber.m:639-679, 938-1010): symmetric SSFM with the step chosen from the local
-    error (one full step against two half steps, Richardson extrapolation).  The loop is host logic as in the
-    reference; nl_step, lin_step, the error norm and the extrapolation run on the resident field."""
-    G = GSTATE
-    n, nfc = s.nfft, s.nfc
-    fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]
-    u = _lib.DeviceField(ctx, n, nfc, 1)
-    uh = _lib.DeviceField(ctx, n, nfc, 1)
-    ustack = _lib.DeviceField(ctx, n, nfc, 1)
-    u.upload(fx, None)
-    # lin_step(betat*dz, u) = ifft(fft(u).*fastexp(-betat*dz)): a one-step plan of the same dispersion, no loss
-    lin = FiberSetup(nfft=n, nfc=nfc, fls=(s.fls[0], 0, 0, 0), dphimaxt=math.inf, dzmaxt=s.length, length=s.length,
-                     alphalin=0.0, gam=s.gam, betat=s.betat, db1=s.db1, manakov=False, nplates=1, brf=s.brf,
-                     isv=False, isy=False, b1=s.b1, dch=s.dch, scalars=s.scalars)
-    desc, keep = setup_to_desc(lin, disp_mode=disp_mode)
-    plan = _lib.Plan(ctx, desc, keep)
-    gam, alphalin, halfalpha = np.asarray(s.gam, dtype=np.float64), s.alphalin, 0.5 * s.alphalin
-    spm, xpm = bool(s.fls[2]), bool(s.fls[3])
+class _LocalErrorStepper:
+    """adaptssfm (fiber.m:938-1010) on a resident scalar field: one symmetric step of length dz against two half steps,
+    local error max|u - uh|/dz, Richardson extrapolation 4/3*uh - 1/3*u on acceptance.  nl_step + attenuation
+    (pmx_scalar_nl_exec), lin_step (a one-step plan whose length is set per call), the error norm and the
+    extrapolation run on the device; the accept/reject logic is host code as in the reference."""
 
-    def nl(f, dz):                                                          # nl_step + u*exp(-halfalpha*dz)
-        leff = dz if alphalin == 0 else (1 - math.exp(-alphalin * dz)) / alphalin
-        _lib.scalar_nl_exec(ctx, f, gam, leff, math.exp(-halfalpha * dz), spm, xpm)
+    def __init__(self, s: FiberSetup, ctx: _lib.Context, disp_mode=None):
+        G = GSTATE
+        n, nfc = s.nfft, s.nfc
+        self.s, self.ctx = s, ctx
+        fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]
+        self.u = _lib.DeviceField(ctx, n, nfc, 1)
+        self.uh = _lib.DeviceField(ctx, n, nfc, 1)
+        self.ustack = _lib.DeviceField(ctx, n, nfc, 1)
+        self.u.upload(fx, None)
+        # lin_step(betat*dz, u) = ifft(fft(u).*fastexp(-betat*dz)): a one-step plan of the same dispersion, no loss
+        lin = FiberSetup(nfft=n, nfc=nfc, fls=(s.fls[0], 0, 0, 0), dphimaxt=math.inf, dzmaxt=s.length, length=s.length,
+                         alphalin=0.0, gam=s.gam, betat=s.betat, db1=s.db1, manakov=False, nplates=1, brf=s.brf,
+                         isv=False, isy=False, b1=s.b1, dch=s.dch, scalars=s.scalars)
+        desc, keep = setup_to_desc(lin, disp_mode=disp_mode)
+        self.plan = _lib.Plan(ctx, desc, keep)
+        self.gam = np.asarray(s.gam, dtype=np.float64)
+        self.nrej = 0
 
-    def lin_step(f, dz):
-        plan.set_length(dz)
-        plan.execute(f)
+    def _nl(self, f, dz):                                                   # nl_step + u*exp(-halfalpha*dz)
+        a = self.s.alphalin
+        leff = dz if a == 0 else (1 - math.exp(-a * dz)) / a
+        _lib.scalar_nl_exec(self.ctx, f, self.gam, leff, math.exp(-0.5 * a * dz), bool(self.s.fls[2]), bool(self.s.fls[3]))
 
-    ncycle = 1                                                              # :664-668
-    dz = _nextstep_host(s.dzmaxt, s.dphimaxt, gam, alphalin, _lib.field_max_power(ctx, u)[0])
-    firstdz, zdone, nrej = dz, 0.0, 0
-    err, safety = s.trg['err'], s.trg['safety']
-    while zdone < s.length:                                                 # :670-678
-        if zdone + dz > s.length:
-            dz = s.length - zdone
+    def _lin(self, f, dz):
+        self.plan.set_length(dz)
+        self.plan.execute(f)
+
+    def first_step(self):
+        """nextstep on the incoming field -> (dz, per-column max |u|^2)"""
+        umax = _lib.field_max_power(self.ctx, self.u)[0]
+        return _nextstep_host(self.s.dzmaxt, self.s.dphimaxt, self.gam, self.s.alphalin, umax), umax
+
+    def try_step(self, dz):
+        """-> (accepted, proposed next step).  The field advances by dz only when the step is accepted."""
+        u, uh, ustack = self.u, self.uh, self.ustack
         dz2, dz4 = 0.5 * dz, 0.25 * dz                                      # adaptssfm :966-1009
         ustack.broadcast_from(u)
         uh.broadcast_from(u)
-        nl(u, dz2)
-        lin_step(u, dz)
-        nl(u, dz2)
-        nl(uh, dz4)
-        lin_step(uh, dz2)
-        nl(uh, dz2)
-        lin_step(uh, dz2)
-        nl(uh, dz4)
-        est_err = math.sqrt(_lib.field_maxdiff2(ctx, u, uh)) / dz
+        self._nl(u, dz2)
+        self._lin(u, dz)
+        self._nl(u, dz2)
+        self._nl(uh, dz4)
+        self._lin(uh, dz2)
+        self._nl(uh, dz2)
+        self._lin(uh, dz2)
+        self._nl(uh, dz4)
+        est_err = math.sqrt(_lib.field_maxdiff2(self.ctx, u, uh)) / dz
         with np.errstate(divide='ignore'):
-            prop = safety * float(np.sqrt(np.float64(err) / np.float64(est_err))) * dz
-        if est_err > err:                                                   # reject the step
-            dz = prop
+            prop = self.s.trg['safety'] * float(np.sqrt(np.float64(self.s.trg['err']) / np.float64(est_err))) * dz
+        if est_err > self.s.trg['err']:                                     # reject the step
             u.broadcast_from(ustack)
-            nrej += 1
-        else:                                                               # accept: Richardson extrapolation
-            _lib.field_lincomb(ctx, u, 4.0 / 3.0, uh, 1.0 / 3.0, u)
+            self.nrej += 1
+            return False, prop
+        _lib.field_lincomb(self.ctx, u, 4.0 / 3.0, uh, 1.0 / 3.0, u)        # accept: Richardson extrapolation
+        return True, prop
+
+    def close(self):
+        self.plan.close()
+        for f in (self.uh, self.ustack, self.u):
+            f.close()
+
+
+def _scalar_a_ssfm(s: FiberSetup, ctx: _lib.Context, disp_mode=None):
+    """scalar_a_ssfm (fiber.m:639-679): symmetric SSFM with every step chosen from the local error."""
+    G = GSTATE
+    st = _LocalErrorStepper(s, ctx, disp_mode)
+    ncycle = 1                                                              # :664-668
+    dz, _ = st.first_step()
+    firstdz, zdone = dz, 0.0
+    while zdone < s.length:                                                 # :670-678
+        if zdone + dz > s.length:
+            dz = s.length - zdone
+        accepted, prop = st.try_step(dz)
+        if accepted:
             zdone = zdone + dz
-            dz = prop
             ncycle += 1
+        dz = prop
         if dz > s.dzmaxt:
             dz = s.dzmaxt
-    gx, _ = u.download()
+    gx, _ = st.u.download()
     G.FIELDX = np.ascontiguousarray(gx[0].T)
-    plan.close()
+    st.close()
     return firstdz, ncycle
+
+
+def _scalar_dphiadapt_ssfm(s: FiberSetup, ctx: _lib.Context, disp_mode=None):
+    """scalar_ssfm with tolflag == 1 (x.dphiadapt, fiber.m:588-611): the first step is found by the local-error
+    method, the nonlinear phase per step is recalibrated from it (:607) and the remaining fiber runs through the
+    device loop, resumed at zprop = zdone + dz with the step the adaptive method proposed."""
+    G = GSTATE
+    if s.alphalin == 0:
+        raise ValueError('x.dphiadapt needs attenuation: fiber.m:607 divides (1-exp(-alpha*zdone)) by (1-exp(-alpha*dzini))')
+    st = _LocalErrorStepper(s, ctx, disp_mode)
+    dz, umax = st.first_step()
+    dphimaxt = s.dphimaxt
+    if dz >= s.dzmaxt:                                                      # :589-597
+        maxpow = float(np.max(st.gam * umax))
+        dphimaxt = maxpow * (1 - math.exp(-s.alphalin * dz)) / s.alphalin
+    dzini, zdone = dz, 0.0
+    while zdone == 0:                                                       # :600-603
+        accepted, prop = st.try_step(dz)
+        if accepted:
+            zdone = zdone + dz
+        dz = prop
+    if dz > s.dzmaxt:                                                       # :604
+        dz = s.dzmaxt
+    dphimaxt = dphimaxt * (1 - math.exp(-s.alphalin * zdone)) / (1 - math.exp(-s.alphalin * dzini))   # :607
+    rest = dataclasses.replace(s, dphimaxt=dphimaxt, tolflag=0, trg=None)
+    desc, keep = setup_to_desc(rest, disp_mode=disp_mode, z_start=zdone, dz_first=dz)
+    plan = _lib.Plan(ctx, desc, keep)
+    try:
+        res = plan.execute(st.u)
+    finally:
+        plan.close()
+    gx, _ = st.u.download()
+    G.FIELDX = np.ascontiguousarray(gx[0].T)
+    st.close()
+    return zdone, int(res.ncycle[0]) + 1                                    # :609-611: the adaptive step counts as one
 
 
 def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional[_lib.Context] = None,
@@ -331,10 +392,11 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         raise ValueError('adaptive step available in absence of polarization effects')
     apply_side_effects(s)
     ctx = ctx or _lib.default_context()
-    if s.tolflag == 2:                                                      # :375-378
+    # x.dphiadapt (tolflag 1) is read by scalar_ssfm only (fiber.m:386-387, :588); matrix_ssfm takes no tolflag
+    if s.tolflag == 2 or (s.tolflag == 1 and not s.isv):                    # :375-380, :386-387
         if (precision or PRECISION) != 'f64':
             raise NotImplementedError('the local-error adaptive step runs in FP64 only')
-        firstdz, ncycle = _scalar_a_ssfm(s, ctx, disp_mode)
+        firstdz, ncycle = (_scalar_a_ssfm if s.tolflag == 2 else _scalar_dphiadapt_ssfm)(s, ctx, disp_mode)
         LAST.clear()
         LAST.update(firstdz=firstdz, ncycle=ncycle, ntot=0)
         return None
