@@ -126,3 +126,20 @@ def test_c5_batch_gives_the_bits_of_single_runs_full_size():
     assert not np.array_equal(gx[0], gx[1])
     for f in (tx, work, one):
         f.close()
+
+
+def test_fp32_c2_span_prefix_against_fp64():
+    """FP32 mode at C2 size (reported separately, tolerance 1e-5): the first 16 km of the span in FP32 against the FP64
+    run of the same call (which test_c2_span_prefix_against_oracle pins on the oracle), same step count; energy ratio
+    exp(-alpha L) to FP32 accuracy"""
+    fib = base_fiber(length=16e3, dgd=0.1, nplates=20, manakov='yes')
+    out = {}
+    for prec in ('f64', 'f32'):
+        G = product_tx(1 << 16, 16)
+        e_in = energy(G)
+        pmx.fiber(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(1000)), precision=prec)
+        out[prec] = (np.array(G.FIELDX), np.array(G.FIELDY), pmx.FIBER_LAST['ncycle'], energy(G) / e_in)
+    assert rel_l2(out['f32'][0], out['f32'][1], out['f64'][0], out['f64'][1]) < 1e-5
+    assert abs(out['f32'][2] - out['f64'][2]) <= 1          # the step control sees FP32-rounded maxima
+    alphalin = math.log(10) * 1e-4 * fib['alphadB']
+    assert abs(out['f32'][3] / math.exp(-alphalin * fib['length']) - 1) < 1e-5
