@@ -94,6 +94,25 @@ def run_case(name, nsymb, nt, nch, ftype, fib, flag, seed=1000, rate=28.0, pavg=
     print('%-28s N=%-6d flag=%s  |out|=%.6e' % (name, nsymb * nt, flag, np.linalg.norm(post['FIELDX'])))
 
 
+def run_print_case(name, nsymb, nt, nch, ftype, fib, flag, seed=1000, rate=28.0, pavg=2.0, two_pol=True):
+    """the simul_out block fiber.m:392-456 writes when GSTATE.PRINT is set, captured from the interpreted reference
+    (fprintf of the mini interpreter) -> tests/golden/simul_out_<name>.json {params, firstdz/ncycle are in the text}"""
+    it = new_interp(seed)
+    tx_through_reference(it, nsymb, nt, nch, rate, pavg, ftype, two_pol)
+    G = it.globals['GSTATE'].copy()
+    G['PRINT'] = to_m(True)
+    G['DIR'] = 'sim'
+    it.globals['GSTATE'] = G
+    it.printed = []
+    it.call('fiber', [to_m(fib), flag], 0)
+    text = ''.join(it.printed)
+    meta = {'name': name, 'nsymb': nsymb, 'nt': nt, 'nch': nch, 'ftype': ftype, 'fiber': fib, 'flag': flag, 'seed': seed,
+            'rate': rate, 'pavg': pavg, 'two_pol': two_pol, 'text': text}
+    with open(os.path.join(OUT, 'simul_out_' + name + '.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+    print('simul_out_%s: %d characters' % (name, len(text)))
+
+
 def fib(**kw):
     f = dict(SMF)
     f.update(kw)
@@ -127,3 +146,8 @@ if __name__ == '__main__':
              want_brf=False)
     run_case('scalar_dphiadapt_sep3_gsx', 256, 16, 3, 'sepfields', fib(length=3e4, ltol=2e-6, dphiadapt=True, slope=0.057),
              'g-sx', two_pol=False, want_brf=False)
+    # the summary block of fiber.m:392-456 (GSTATE.PRINT)
+    run_print_case('manakov', 256, 16, 1, 'unique', fib(length=8e4, dgd=0.1, nplates=100, manakov='yes'), 'gps-')
+    run_print_case('wdm3_pmf', 128, 64, 3, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],
+                                                         epsilon=[0.1, 0.5, -0.3], manakov='no', slope=0.057), 'gps-', pavg=1.0)
+    run_print_case('scalar_sep3_ltol', 256, 16, 3, 'sepfields', fib(length=2e4, ltol=2e-6, slope=0.057), 'g-sx', two_pol=False)

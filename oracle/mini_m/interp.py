@@ -1318,6 +1318,49 @@ for _n in ('fprintf', 'disp', 'fclose', 'drawnow', 'figure', 'plot', 'hold', 'gr
            'mkdir', 'fflush'):
     BUILTINS[_n] = lambda it, a, n: [np.zeros((0, 0))]
 BUILTINS['fopen'] = lambda it, a, n: [np.array([[-1.0]])]
+
+
+def m_sprintf(fmt, args):
+    """fprintf / sprintf formatting: escapes of the format, arguments flattened column-major, the format reused
+    until the arguments are consumed (the interpreter's semantics; enough for the simul_out blocks of the reference)."""
+    fmt = fmt.replace('\\n', '\n').replace('\\t', '\t')
+    flat = []
+    for v in args:
+        if isinstance(v, str):
+            flat.append(v)
+        else:
+            flat.extend(np.real(np.asarray(v, dtype=complex)).ravel(order='F').tolist())
+    specs = re.findall(r'%[-+ 0#]*\d*(?:\.\d+)?([diuoxXfeEgGcs])', fmt.replace('%%', ''))
+    if not specs:
+        return fmt.replace('%%', '%')
+    out, i = '', 0
+    while True:
+        vals = []
+        for k, sp in enumerate(specs):
+            v = flat[i + k] if i + k < len(flat) else ('' if sp == 's' else 0.0)
+            if sp in 'diu' and not isinstance(v, str):
+                v = int(round(v))
+            vals.append(v)
+        piece = fmt % tuple(vals)
+        if any(isinstance(v, float) and not np.isfinite(v) for v in vals):    # the interpreter spells them Inf / NaN
+            piece = re.sub(r'\binf\b', 'Inf', re.sub(r'\bnan\b', 'NaN', piece))
+        out += piece
+        i += len(specs)
+        if i >= len(flat):
+            return out
+
+
+def _fprintf_capture(it, a, n):
+    """With it.printed a list: text written through fprintf(fid, fmt, ...) is appended to it (fid itself is ignored)."""
+    if getattr(it, 'printed', None) is None or not a:
+        return [np.zeros((0, 0))]
+    rest = a[1:] if not isinstance(a[0], str) else a
+    if rest and isinstance(rest[0], str):
+        it.printed.append(m_sprintf(rest[0], rest[1:]))
+    return [np.zeros((0, 0))]
+
+
+BUILTINS['fprintf'] = _fprintf_capture
 BUILTINS['input'] = lambda it, a, n: (_ for _ in ()).throw(MError('input() is interactive: not available'))
 
 

@@ -23,7 +23,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import _lib
+from . import _lib, simul_out
 from .gstate import CONSTANTS, GSTATE, rng as _global_rng
 
 DEF_PLATES = 100  # fiber.m:131
@@ -399,6 +399,7 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         firstdz, ncycle = (_scalar_a_ssfm if s.tolflag == 2 else _scalar_dphiadapt_ssfm)(s, ctx, disp_mode)
         LAST.clear()
         LAST.update(firstdz=firstdz, ncycle=ncycle, ntot=0)
+        simul_out.log_fiber(x, flag, s, firstdz, ncycle)                    # :392-456
         return None
     desc, keep = setup_to_desc(s, disp_mode=disp_mode, precision=precision)
     scalar = not s.isv
@@ -431,6 +432,7 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
     if trace:
         dz, nt = res.schedule(0)
         LAST.update(trace_dz=dz, trace_ntrunk=nt)
+    simul_out.log_fiber(x, flag, s, LAST['firstdz'], LAST['ncycle'])        # :392-456
     if not s.isv:
         return None
     brf = dict(s.brf)

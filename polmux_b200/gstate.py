@@ -157,17 +157,34 @@ def rng() -> np.random.Generator:
 def reset_all(Nsymb: int, Nt: int, Nch: int, *opts):
     """reset_all(Nsymb,Nt,Nch[,outdir[,'noprint']]) -- reset_all.m:114-174.
 
-    Printing to simul_out is not built (GSTATE.PRINT is always False)."""
+    With an output directory (and without 'noprint') GSTATE.PRINT is set and the log GSTATE.DIR/simul_out is opened
+    (reset_all.m:176-225); fiber() appends its summary block to it (polmux_b200/simul_out.py)."""
     if len(opts) > 2:
         raise ValueError('Invalid number of inputs')
     GSTATE.drop_device()
     for k in list(GSTATE.__dict__):
         del GSTATE.__dict__[k]
     GSTATE.PRINT = False
-    if opts:
+    if len(opts) == 1:                                                       # reset_all.m:125-133
         if not isinstance(opts[0], str):
             raise ValueError('directory name must be a string')
-        GSTATE.DIR = opts[1] if (len(opts) == 2 and opts[0] == 'noprint') else opts[0]
+        if opts[0] == 'noprint':
+            raise ValueError("The output directory cannot be called 'noprint'")
+        GSTATE.DIR = opts[0]
+        GSTATE.PRINT = True
+    elif len(opts) == 2:                                                     # :134-150
+        if opts[0] == 'noprint':
+            if not isinstance(opts[1], str):
+                raise ValueError('directory name must be a string')
+            if opts[1] == 'noprint':
+                raise ValueError("The output directory cannot be called 'noprint'")
+            GSTATE.DIR = opts[1]
+        else:
+            if not isinstance(opts[0], str):
+                raise ValueError('directory name must be a string')
+            GSTATE.DIR = opts[0]
+            if opts[1] != 'noprint':
+                raise ValueError("Use 'noprint' to avoid printing to file")
     stepf = 1.0 / Nsymb
     n = int(Nsymb) * int(Nt)
     # fftshift(-Nt/2 : 1/Nsymb : Nt/2-1/Nsymb)                         reset_all.m:153
@@ -184,4 +201,9 @@ def reset_all(Nsymb: int, Nt: int, Nch: int, *opts):
     GSTATE.DISP = None
     GSTATE.LAMBDA = None
     GSTATE.POWER = None
+    if GSTATE.PRINT:
+        from . import simul_out
+        if simul_out.open_log(int(Nsymb), int(Nt), int(Nch)):
+            import warnings
+            warnings.warn('The output file simul_out is very big')           # reset_all.m:220-222
     return GSTATE
