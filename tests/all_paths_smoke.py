@@ -6,7 +6,7 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))   # lives under tests/: it uses the oracle as checker
 import oracle.fiber_oracle as orc
 import polmux_b200 as pmx
 from polmux_b200 import _lib, mc, field as fmod
