@@ -197,6 +197,10 @@ int pmx_ctx_profile_read(pmx_ctx* ctx, double* ms, int64_t* n);
  */
 int pmx_ampliflat_exec(pmx_ctx* ctx, pmx_devfield* f, double gain, const double* sigma,
                        const double* noise_host, uint64_t seed);
+/* The same with the ASE on one polarization only (options.onepol = 'asex' / 'asey', ampliflat.m:107-118):
+ * asepol = 1 (X), 2 (Y), 3 (both = pmx_ampliflat_exec). */
+int pmx_ampliflat_exec_pol(pmx_ctx* ctx, pmx_devfield* f, double gain, const double* sigma,
+                           const double* noise_host, uint64_t seed, int32_t asepol);
 
 /* ---- span loop: nspan x [ fiber ; ampliflat ] without returning to the host ---------------
  * The loop every multi-span script of the reference writes around its in-line devices

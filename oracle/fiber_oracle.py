@@ -649,9 +649,9 @@ def ampliflat_sigma(gs: GState, gain_db: float, f_db: float, nfc: int):
     return gain, sigma
 
 
-def ampliflat(gs: GState, gain_db: float, f_db: Optional[float] = None, noise=None):
+def ampliflat(gs: GState, gain_db: float, f_db: Optional[float] = None, noise=None, onepol=None):
     """ampliflat.m:61-148, atype='gain'.  ``noise`` is options.noise: [N, 2*nfc]
-    complex standard normals (X columns first, then Y), :123-129."""
+    complex standard normals (X columns first, then Y), :123-129; ``onepol``: 'asex' / 'asey' (:107-118)."""
     nfr, nfc = gs.FIELDX.shape
     gain, sigma = ampliflat_sigma(gs, gain_db, f_db, nfc)
     R = np.dtype(gs.real).type
@@ -665,9 +665,14 @@ def ampliflat(gs: GState, gain_db: float, f_db: Optional[float] = None, noise=No
             raise ValueError('the oracle takes ASE noise from the caller (options.noise)')
         noise = np.asarray(noise)
         sig = sigma.astype(gs.real)[None, :]
-        gs.FIELDX = gs.FIELDX + sig * noise[:, :nfc]
-        ny = sig * noise[:, nfc:]
-        gs.FIELDY = gs.FIELDY + ny if isy else ny
+        if onepol is not None and str(onepol).lower() not in ('asex', 'asey'):
+            raise ValueError("ONEPOL, if exists, must be 'asex' or 'asey'")
+        asepol = (True, True) if onepol is None else (str(onepol).lower() == 'asex', str(onepol).lower() == 'asey')
+        if asepol[0]:
+            gs.FIELDX = gs.FIELDX + sig * noise[:, :nfc]
+        if asepol[1]:
+            ny = sig * noise[:, nfc:]
+            gs.FIELDY = gs.FIELDY + ny if isy else ny
 
 
 # --------------------------------------------------------------------------

@@ -29,7 +29,7 @@ EXPORTS = [
     'pmx_plan_create', 'pmx_plan_destroy', 'pmx_plan_set_plates', 'pmx_fiber_exec',
     'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
-    'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux',
+    'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     lib.pmx_plan_set_plates.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     lib.pmx_fiber_exec.argtypes = [vp, vp, C.POINTER(FiberResult)]
     lib.pmx_ampliflat_exec.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64]
+    lib.pmx_ampliflat_exec_pol.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64, C.c_int32]
     lib.pmx_count_errors.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     lib.pmx_qpsk_count.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp]
     lib.pmx_scalar_nl_exec.argtypes = [vp, vp, _dp, C.c_double, C.c_double, C.c_int32, C.c_int32]
@@ -439,14 +440,15 @@ def field_lincomb(ctx: Context, dst: DeviceField, ca: float, a: DeviceField, cb:
     ctx.check(ctx.lib.pmx_field_lincomb(ctx.h, dst.h, float(ca), a.h, float(cb), b.h))
 
 
-def ampliflat_exec(ctx: Context, field: DeviceField, gain: float, sigma, noise=None, seed=0):
+def ampliflat_exec(ctx: Context, field: DeviceField, gain: float, sigma, noise=None, seed=0, asepol=3):
+    """asepol: 1 = ASE on X only, 2 = on Y only, 3 = both (options.onepol, ampliflat.m:107-118)"""
     s = _f64(np.atleast_1d(sigma))
     n = None
     if noise is not None:
         n = np.ascontiguousarray(noise, dtype=np.complex128)
-    ctx.check(ctx.lib.pmx_ampliflat_exec(ctx.h, field.h, float(gain), _ptr(s),
-                                         n.ctypes.data_as(_dp) if n is not None else None,
-                                         C.c_uint64(int(seed))))
+    ctx.check(ctx.lib.pmx_ampliflat_exec_pol(ctx.h, field.h, float(gain), _ptr(s),
+                                             n.ctypes.data_as(_dp) if n is not None else None,
+                                             C.c_uint64(int(seed)), int(asepol)))
     if n is not None:
         ctx.sync()
 

@@ -27,14 +27,18 @@ def ase_sigma(gain: float, f_db, nfc: int) -> np.ndarray:
 def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
     """ampliflat(x,'gain',options) on GSTATE.FIELDX/FIELDY, like the reference.
 
-    options: {'f': noise figure [dB], 'noise': [Nfft, 2*nfc] complex standard normals}.
+    options: {'f': noise figure [dB], 'noise': [Nfft, 2*nfc] complex standard normals, 'onepol': 'asex' | 'asey'}.
     Without options.noise the ASE comes from the device's counter-based generator (seed)."""
     G = GSTATE
     if atype.lower() != 'gain':
         raise NotImplementedError("ampliflat: only atype 'gain' is built (ampliflat.m:61-63)")
     options = dict(options or {})
-    if 'onepol' in options:
-        raise NotImplementedError('ampliflat: options.onepol is not built')
+    asepol = 3
+    if 'onepol' in options:                                                  # ampliflat.m:107-118
+        pol = str(options['onepol']).lower()
+        if pol not in ('asex', 'asey'):
+            raise ValueError("ONEPOL, if exists, must be 'asex' or 'asey'")
+        asepol = 1 if pol == 'asex' else 2
     nfr, nfc = G.field_shape()
     gain = 10 ** (x * 0.1)
     sigma = ase_sigma(gain, options.get('f'), nfc) if options else np.zeros(nfc)
@@ -47,7 +51,7 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
         # two polarizations: works on the field fiber() left in HBM (or uploads it) and leaves it there
         fld, hx, hy = G.take_device(ctx)
         try:
-            _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed)
+            _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed, asepol)
         except Exception:
             fld.close()
             raise
@@ -56,10 +60,10 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
     # single polarization: host buffers in, host buffers out (ASE creates FIELDY, ampliflat.m:132-146)
     fld = _lib.DeviceField(ctx, nfr, nfc, 1)
     fld.upload(G.FIELDX, np.zeros_like(G.FIELDX))
-    _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed)
+    _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed, asepol)
     ox, oy = fld.download()
     fld.close()
     G.FIELDX = np.ascontiguousarray(ox[0].T)
-    if np.any(sigma):
+    if np.any(sigma) and (asepol & 2):
         G.DELAY = np.vstack([G.DELAY[:1], np.zeros((1, G.NCH))])              # ampliflat.m:144
         G.FIELDY = np.ascontiguousarray(oy[0].T)

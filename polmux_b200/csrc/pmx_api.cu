@@ -1188,6 +1188,7 @@ struct AmpParams {
     size_t N;
     int nfc, batch;
     int l1, l2;        // field layout: time sample n1*N2 + n2 at n2*N1 + n1 (log2 N1, log2 N2; 0/0 = natural order)
+    int asepol;        // bit 0: ASE on X, bit 1: ASE on Y (options.onepol, ampliflat.m:107-118)
 };
 
 template <typename T2>  // the gain and the noise are evaluated in double in both field precisions
@@ -1210,16 +1211,22 @@ __global__ void __launch_bounds__(256) pmx_k_ampliflat(AmpParams a) {
                 nx = pmx_cnormal(r[0], r[1]);
                 ny = pmx_cnormal(r[2], r[3]);
             }
-            x.x += sig * nx.x; x.y += sig * nx.y;
-            y.x += sig * ny.x; y.y += sig * ny.y;
+            if (a.asepol & 1) { x.x += sig * nx.x; x.y += sig * nx.y; }
+            if (a.asepol & 2) { y.x += sig * ny.x; y.y += sig * ny.y; }
         }
         fld[2 * m] = pmx_mk2<T2>(x.x, x.y);
         fld[2 * m + 1] = pmx_mk2<T2>(y.x, y.y);
     }
 }
 
+extern "C" int pmx_ampliflat_exec_pol(pmx_ctx* c, pmx_devfield* f, double gain, const double* sigma,
+                                      const double* noise_host, uint64_t seed, int32_t asepol);
 extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, const double* sigma,
                                   const double* noise_host, uint64_t seed) {
+    return pmx_ampliflat_exec_pol(c, f, gain, sigma, noise_host, seed, 3);
+}
+extern "C" int pmx_ampliflat_exec_pol(pmx_ctx* c, pmx_devfield* f, double gain, const double* sigma,
+                                      const double* noise_host, uint64_t seed, int32_t asepol) {
     if (!c || !f) return set_err(c, PMX_ERR_INVALID, "pmx_ampliflat_exec: null argument");
     if (!(gain > 0)) return set_err(c, PMX_ERR_INVALID, "gain must be > 0");
     CK(c, cudaSetDevice(c->device));
@@ -1228,6 +1235,8 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
     a.field = f->data;
     a.sg = sqrt(gain);  // ampliflat.m:78
     for (int k = 0; k < f->nfc; ++k) a.sigma[k] = sigma ? sigma[k] : 0.0;
+    if (asepol < 1 || asepol > 3) return set_err(c, PMX_ERR_INVALID, "asepol must be 1 (X), 2 (Y) or 3 (both)");
+    a.asepol = asepol;
     a.seed = seed;
     a.N = (size_t)f->nfft;
     a.nfc = f->nfc;

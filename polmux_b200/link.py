@@ -33,7 +33,7 @@ def link(x, flag: str, nspan: int, gain_db: Optional[float] = None, options=None
         raise ValueError('nspan must be at least 1')
     options = dict(options or {})
     if 'onepol' in options:
-        raise NotImplementedError('ampliflat: options.onepol is not built')
+        raise NotImplementedError('link: options.onepol goes through ampliflat() (pmx_link_desc carries no polarization mask)')
     setups = [fiber_setup(x, flag, rng) for _ in range(nspan)]          # one plate draw per span, in call order
     s = setups[0]
     if not (s.isv and G.has_y()):

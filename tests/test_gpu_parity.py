@@ -280,3 +280,19 @@ def test_create_field_unique_on_device(nch, lg, delay):
     assert rel_l2(d[0][0], d[0][1], h[0][0], h[0][1]) < 1e-13
     assert np.array_equal(h[1], d[1]) and np.array_equal(h[2], d[2])
     assert rel_l2(d[3], d[4], h[3], h[4]) < 1e-11 and h[5] == d[5]
+
+
+@pytest.mark.parametrize('pol', ['asex', 'asey'])
+def test_ampliflat_onepol(pol):
+    """options.onepol (ampliflat.m:107-118): ASE on one polarization only, the other one just amplified"""
+    gs = make_tx(1 << 9, 16)
+    G = pmx.GSTATE
+    noise = np.random.Generator(np.random.PCG64(4)).standard_normal((1 << 13, 4)).view(np.complex128).copy()
+    orc.ampliflat(gs, 7.0, 5.0, noise=noise, onepol=pol)
+    pmx.ampliflat(7.0, 'gain', {'f': 5.0, 'noise': noise, 'onepol': pol})
+    assert rel_l2(G.FIELDX, G.FIELDY, gs.FIELDX, gs.FIELDY) < 1e-14
+    quiet = G.FIELDY if pol == 'asex' else G.FIELDX
+    tx = G.FIELDY_TX if pol == 'asex' else G.FIELDX_TX
+    assert np.allclose(quiet, tx * np.sqrt(10 ** 0.7), rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):
+        pmx.ampliflat(7.0, 'gain', {'f': 5.0, 'onepol': 'both'})
