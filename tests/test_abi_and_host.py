@@ -205,3 +205,17 @@ def test_gstate_resident_field_reads_like_the_host_arrays():
     G.put_device(fake4, hx, hy)
     pmx.reset_all(8, 4, 1)
     assert fake4.closed and pmx.GSTATE.FIELDX is None and not pmx.GSTATE.has_y()
+
+
+def test_link_descriptor_checks():
+    """make_link (pmx_link_desc): one plate draw and one ASE seed per span"""
+    pl = [np.zeros((3, 1, 4))] * 3
+    l, keep = _lib.make_link(3, 2.0, [0.1], plates=pl, plate_sets=1, seeds=[5, 6, 7])
+    assert l.nspan == 3 and l.plate_sets == 1 and l.gain == 2.0 and keep['seeds'].dtype == np.uint64
+    assert keep['db0'].size == 12 and not l.noise
+    with pytest.raises(ValueError):
+        _lib.make_link(3, 2.0, [0.1], seeds=[1, 2])
+    with pytest.raises(ValueError):
+        _lib.make_link(3, 2.0, [0.1], plates=[np.zeros(10)] * 3)
+    l0, _ = _lib.make_link(2)
+    assert not l0.db0 and not l0.sigma and not l0.seeds and l0.gain == 0.0
