@@ -156,6 +156,10 @@ void pmx_field_destroy(pmx_devfield* f);
 /* b0..b0+nb-1: realizations to transfer; host arrays hold nb realizations. */
 int pmx_field_upload(pmx_devfield* f, const pmx_field* host, int32_t b0, int32_t nb);
 int pmx_field_download(pmx_devfield* f, pmx_field* host, int32_t b0, int32_t nb);
+/* 1 when `p` points into page-locked (CUDA-registered) host memory, 0 when not (or when no device is usable).  The
+ * host mirror uses it to decide whether a received field may be written back into the caller's own arrays: pinned
+ * buffers are reused in place (no staging copy), ordinary arrays are never overwritten behind the caller's back. */
+int pmx_host_is_pinned(const void* p);
 /* dst[b] = src[0] for all b (same Tx field for every realization). */
 int pmx_field_broadcast(pmx_devfield* dst, const pmx_devfield* src);
 /* Raw device pointer of the interleaved (xr,xi,yr,yi) sample array (doubles, or floats for PMX_F32 fields).

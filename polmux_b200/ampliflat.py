@@ -6,6 +6,7 @@ import math
 import numpy as np
 
 from . import _lib
+from . import gstate
 from .gstate import CONSTANTS, GSTATE
 
 
@@ -24,11 +25,13 @@ def ase_sigma(gain: float, f_db, nfc: int) -> np.ndarray:
     return np.sqrt(flin / 4 * CONSTANTS.HPLANCK * CONSTANTS.CLIGHT / lam * (gain - 1) * G.NT * G.SYMBOLRATE * 1e21)
 
 
-def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
+def ampliflat(x, atype='gain', options=None, ctx=None, seed=None):
     """ampliflat(x,'gain',options) on GSTATE.FIELDX/FIELDY, like the reference.
 
     options: {'f': noise figure [dB], 'noise': [Nfft, 2*nfc] complex standard normals, 'onepol': 'asex' | 'asey'}.
-    Without options.noise the ASE comes from the device's counter-based generator (seed)."""
+    Without options.noise the ASE comes from the device's counter-based generator, keyed by `seed`; seed=None (the
+    default) takes the next value of the global stream (gstate.seed(k) = randn('state',k)), so successive calls add
+    independent noise as the reference's randn does (ampliflat.m:132-135)."""
     G = GSTATE
     if atype.lower() != 'gain':
         raise NotImplementedError("ampliflat: only atype 'gain' is built (ampliflat.m:61-63)")
@@ -44,6 +47,8 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
     sigma = ase_sigma(gain, options.get('f'), nfc) if options else np.zeros(nfc)
     ctx = ctx or _lib.default_context()
     noise = None
+    if seed is None:
+        seed = gstate.next_ase_seed() if np.any(sigma) and 'noise' not in options else 0
     if np.any(sigma) and 'noise' in options:
         nz = np.asarray(options['noise'], dtype=np.complex128)
         noise = np.ascontiguousarray(nz.T)[None]                 # [1][2*nfc][nfft]
@@ -53,7 +58,7 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=0):
         try:
             _lib.ampliflat_exec(ctx, fld, gain, sigma, noise, seed, asepol)
         except Exception:
-            fld.close()
+            G.restore_host(fld, hx, hy)
             raise
         G.put_device(fld, hx, hy)
         return

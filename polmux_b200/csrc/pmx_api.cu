@@ -609,6 +609,16 @@ extern "C" int pmx_field_download(pmx_devfield* f, pmx_field* h, int32_t b0, int
     return PMX_OK;
 }
 
+extern "C" int pmx_host_is_pinned(const void* p) {
+    if (!p) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 extern "C" int pmx_field_broadcast(pmx_devfield* dst, const pmx_devfield* src) {
     if (!dst || !src) return set_err(nullptr, PMX_ERR_INVALID, "null field");
     pmx_ctx* c = dst->ctx;
@@ -1059,11 +1069,11 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
                     p->tA->xpm_sum(dim3((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), G.nb), G.st, G.pA, G.fc);
                     c->launches++;
                 }
-                { ProfScope ps(c, 0); p->tA->passA(G.gA, G.st, G.pA, G.fc, fld->map_rows); }
+                { ProfScope ps(c, 0); CK(c, p->tA->passA(G.gA, G.st, G.pA, G.fc, fld->map_rows)); }
                 G.pB.reverse = serp ? (rev[gi] ^= 1) : 0;
-                { ProfScope ps(c, 1); p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_cols); }
+                { ProfScope ps(c, 1); CK(c, p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_cols)); }
                 G.pA.reverse = serp ? (rev[gi] ^= 1) : 0;
-                { ProfScope ps(c, 2); p->tA->passC(G.gC, G.st, G.pA, G.fc, fld->map_rows); }
+                { ProfScope ps(c, 2); CK(c, p->tA->passC(G.gC, G.st, G.pA, G.fc, fld->map_rows)); }
                 if (use_pdl) {
                     cudaLaunchConfig_t cfg = {};
                     cfg.gridDim = dim3(G.nb);
@@ -1074,7 +1084,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
                     at[0].val.programmaticStreamSerializationAllowed = 1;
                     cfg.attrs = at;
                     cfg.numAttrs = 1;
-                    cudaLaunchKernelEx(&cfg, pmx_k_ctl, G.pc, G.fc, 0);
+                    CK(c, cudaLaunchKernelEx(&cfg, pmx_k_ctl, G.pc, G.fc, 0));
                 } else {
                     pmx_k_ctl<<<G.nb, 128, 0, G.st>>>(G.pc, G.fc, 0);
                 }

@@ -19,9 +19,10 @@ struct PmxLaunchTable {
     // opt in to the dynamic shared memory, report resident CTAs per SM of each kernel
     cudaError_t (*setup)(int* ctasA, int* ctasB, int* ctasC);
     // grid_x persistent CTAs
-    void (*passA)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
-    void (*passB)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& rows);
-    void (*passC)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
+    // (every launcher returns the launch status)
+    cudaError_t (*passA)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
+    cudaError_t (*passB)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& rows);
+    cudaError_t (*passC)(int grid_x, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& cols);
     // first max |u|^2 of a resident field (pmx_k_init) and the four-step twiddle rows, in this precision
     void (*init_max)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
     void (*fill_tw4)(void* tab, int rows, double two_over_N, cudaStream_t s);

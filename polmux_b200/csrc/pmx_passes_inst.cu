@@ -58,7 +58,7 @@ cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
 }
 // p.pdl: launch with programmatic stream serialization (the kernel's prologue then overlaps the previous kernel's tail)
 template <typename K>
-void launch(K kern, int gx, int threads, int smem, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+cudaError_t launch(K kern, int gx, int threads, int smem, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx);
     cfg.blockDim = dim3(threads);
@@ -69,19 +69,18 @@ void launch(K kern, int gx, int threads, int smem, cudaStream_t s, const PassPar
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = p.pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, p, f, m);
+    return cudaLaunchKernelEx(&cfg, kern, p, f, m);
 }
-void passA(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
-    launch(pmx_k_passA<real, L, GAC, PFAC>, gx, SA::THREADS, SA::TOTAL, s, p, f, m);
+cudaError_t passA(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+    return launch(pmx_k_passA<real, L, GAC, PFAC>, gx, SA::THREADS, SA::TOTAL, s, p, f, m);
 }
-void passB(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+cudaError_t passB(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
     if (f.disp_scalar)
-        launch(pmx_k_passB<real, L, GB, PFB, true>, gx, SB::THREADS, SB::TOTAL, s, p, f, m);
-    else
-        launch(pmx_k_passB<real, L, GB, PFB, false>, gx, SB::THREADS, SB::TOTAL, s, p, f, m);
+        return launch(pmx_k_passB<real, L, GB, PFB, true>, gx, SB::THREADS, SB::TOTAL, s, p, f, m);
+    return launch(pmx_k_passB<real, L, GB, PFB, false>, gx, SB::THREADS, SB::TOTAL, s, p, f, m);
 }
-void passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
-    launch(pmx_k_passC<real, L, GAC, PFAC>, gx, SC::THREADS, SC::TOTAL, s, p, f, m);
+cudaError_t passC(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+    return launch(pmx_k_passC<real, L, GAC, PFAC>, gx, SC::THREADS, SC::TOTAL, s, p, f, m);
 }
 // precision-dependent helpers that do not depend on L (every table carries them)
 void init_max(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f) {

@@ -8,11 +8,11 @@ double; the propagation loop itself (matrix_ssfm, :459-555) runs inside the
 C-ABI CUDA library through ``pmx_fiber_run`` -- one call per fiber(), host
 buffers in, host buffers out.  There is no CPU fallback.
 
-Not built (raise, like the reference does for its own unimplemented branches):
-the scalar single-polarization path without 'p' and with FIELDY empty
-(scalar_ssfm) is routed through the same two-polarization kernels with a zero
-Y field only when no XPM is requested; the local-error adaptive step (ltol,
-scalar_a_ssfm / adaptssfm, :639-679, :938-1010) is not available.
+The scalar single-polarization path (scalar_ssfm, nl_step incl. cross-column XPM,
+:557-636, :786-803), the local-error adaptive step (x.ltol: scalar_a_ssfm / adaptssfm,
+:639-679, :938-1010) and x.dphiadapt (:588-611) run on the device as well; what raises
+is what the reference raises for (two polarizations + 'x', :853-854; ltol with
+polarization effects, :372-374).
 """
 from __future__ import annotations
 
@@ -390,13 +390,14 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         G.FIELDY = np.zeros_like(G.FIELDX)
     if s.tolflag == 2 and s.isv:                                            # :372-374
         raise ValueError('adaptive step available in absence of polarization effects')
-    apply_side_effects(s)
     ctx = ctx or _lib.default_context()
+    # (GSTATE.DELAY / DISP, fiber.m:367-369, are updated once the propagation has succeeded)
     # x.dphiadapt (tolflag 1) is read by scalar_ssfm only (fiber.m:386-387, :588); matrix_ssfm takes no tolflag
     if s.tolflag == 2 or (s.tolflag == 1 and not s.isv):                    # :375-380, :386-387
         if (precision or PRECISION) != 'f64':
             raise NotImplementedError('the local-error adaptive step runs in FP64 only')
         firstdz, ncycle = (_scalar_a_ssfm if s.tolflag == 2 else _scalar_dphiadapt_ssfm)(s, ctx, disp_mode)
+        apply_side_effects(s)
         LAST.clear()
         LAST.update(firstdz=firstdz, ncycle=ncycle, ntot=0)
         simul_out.log_fiber(x, flag, s, firstdz, ncycle)                    # :392-456
@@ -416,17 +417,20 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
         # two polarizations: the field of the previous in-line device if it is still in HBM, else an upload; the
         # result stays there until GSTATE.FIELDX / FIELDY are read (gstate.RESIDENT)
         fld, hx, hy = G.take_device(ctx, desc.precision)
-        plan = None
         try:
             plan = _lib.Plan(ctx, desc, keep)
+        except Exception:
+            G.restore_host(fld, hx, hy)     # nothing ran: the caller's field is as it was
+            raise
+        try:
             res = plan.execute(fld, trace_cap=4096 if trace else 0)
         except Exception:
-            fld.close()
+            fld.close()                     # the device copy is part-way through the fiber: not usable
             raise
         finally:
-            if plan is not None:
-                plan.close()
+            plan.close()
         G.put_device(fld, hx, hy)
+    apply_side_effects(s)
     LAST.clear()
     LAST.update(firstdz=float(res.firstdz[0]), ncycle=int(res.ncycle[0]), ntot=int(res.ntot[0]))
     if trace:

@@ -55,8 +55,13 @@ class _GState(_Struct):
         fld = res.field
         n, nfc = fld.nfft, fld.nfc
         bufs = (res.hostx, res.hosty)
+        # Value semantics like the interpreter's: an array the caller may still hold (x0 = GSTATE.FIELDX before the
+        # fiber) is never overwritten -- unless it is PINNED memory, which a caller allocates precisely to have the
+        # transfers land in it (bench e2e; a staging copy would defeat it).
+        from . import _lib
         if nfc == 1 and all(isinstance(a, np.ndarray) and a.dtype == np.complex128 and a.shape == (n, 1)
-                            and a.flags['C_CONTIGUOUS'] and a.flags['WRITEABLE'] for a in bufs):
+                            and a.flags['C_CONTIGUOUS'] and a.flags['WRITEABLE'] and _lib.host_is_pinned(a)
+                            for a in bufs):
             fld.download_into(res.hostx, res.hosty)              # [N,1] is also [1][1][N]; pinned stays pinned
             hx, hy = res.hostx, res.hosty
         else:
@@ -113,9 +118,12 @@ class _GState(_Struct):
             res = None
         if res is not None:
             del self.__dict__['_res']
+            self.__dict__['_taken_resident'] = True
+            # the host arrays of a resident field are stale: only pinned ones are kept, as download targets
             return res.field, res.hostx, res.hosty
         hx, hy = self.__dict__.get('_hx'), self.__dict__.get('_hy')
         n, nfc = np.shape(hx)
+        self.__dict__['_taken_resident'] = False
         fld = _lib.DeviceField(ctx, n, nfc, 1, precision=_lib.PMX_F64 if precision is None else precision)
         try:
             fld.upload(hx, hy)
@@ -126,10 +134,20 @@ class _GState(_Struct):
 
     def put_device(self, fld, hostx, hosty):
         """The field an in-line device leaves behind.  With RESIDENT it stays in HBM until it is read."""
+        self.__dict__.pop('_taken_resident', None)
         self.__dict__['_res'] = _Resident(fld, hostx, hosty)
         self.__dict__['_hx'] = self.__dict__['_hy'] = None
         if not RESIDENT:
             self._materialize()
+
+    def restore_host(self, fld, hostx, hosty):
+        """An in-line device failed before it touched the field: give the caller's state back as it was (the device
+        copy stays resident when it was the only copy)."""
+        if self.__dict__.pop('_taken_resident', False):
+            self.__dict__['_res'] = _Resident(fld, hostx, hosty)
+            return
+        fld.close()
+        self.__dict__['_hx'], self.__dict__['_hy'] = hostx, hosty
 
     def drop_device(self):
         res = self.__dict__.pop('_res', None)
@@ -148,6 +166,12 @@ def seed(value: int):
     """Equivalent of rand('state',k) / randn('state',k): reseed the global stream."""
     global _rng
     _rng = np.random.Generator(np.random.PCG64(int(value)))
+
+
+def next_ase_seed() -> int:
+    """Seed of the next ASE draw when the caller names none: taken from the global stream, so that -- like randn in
+    ampliflat.m:132-135 -- every ampliflat() call adds fresh, independent noise and seed(k) makes a run repeatable."""
+    return int(_rng.integers(0, 1 << 63, dtype=np.int64))
 
 
 def rng() -> np.random.Generator:

@@ -43,8 +43,20 @@ def inverse_pmd(brf, options=None, ctx=None):
                          brf={'db0': -db0[::-1], 'theta': th[::-1], 'epsilon': ep[::-1]}, isv=True, isy=True,
                          b1=np.zeros(1), dch=np.zeros(1), scalars={})
         desc, keep = setup_to_desc(inv, disp_mode='vector')
-        plan = _lib.Plan(ctx, desc, keep)
-        plan.execute(fld)
-        plan.close()
+        try:
+            plan = _lib.Plan(ctx, desc, keep)
+        except Exception:
+            if b is brfs[-1]:
+                G.restore_host(fld, hx, hy)                 # nothing ran yet: the caller's field is as it was
+            else:
+                fld.close()
+            raise
+        try:
+            plan.execute(fld)
+        except Exception:
+            fld.close()
+            raise
+        finally:
+            plan.close()
     G.put_device(fld, hx, hy)
     G.DISP = np.zeros((2, G.NCH))                         # inverse_pmd.m:141

@@ -19,14 +19,16 @@ import numpy as np
 from . import _lib
 from .ampliflat import ase_sigma
 from .fiber import LAST, apply_side_effects, fiber_setup, setup_to_desc
+from . import gstate
 from .gstate import GSTATE
 
 
-def link(x, flag: str, nspan: int, gain_db: Optional[float] = None, options=None, rng=None, ctx=None, seed: int = 0,
+def link(x, flag: str, nspan: int, gain_db: Optional[float] = None, options=None, rng=None, ctx=None, seed: Optional[int] = None,
          disp_mode: Optional[str] = None, precision: Optional[str] = None):
     """-> list of the nspan brf structs fiber() would have returned.
     options: ampliflat's ({'f': noise figure [dB], 'noise': list of nspan arrays [Nfft, 2*nfc]}); the ASE of span k
-    comes from options['noise'][k] or from the device generator with seed `seed + k`."""
+    comes from options['noise'][k] or from the device generator with seed `seed + k` (seed=None: one fresh seed per
+    span from the global stream, as ampliflat() draws them)."""
     G = GSTATE
     nspan = int(nspan)
     if nspan < 1:
@@ -54,8 +56,13 @@ def link(x, flag: str, nspan: int, gain_db: Optional[float] = None, options=None
             if len(nz) != nspan:
                 raise ValueError('options.noise: one [Nfft, 2*nfc] array per span')
             noise = np.stack([np.ascontiguousarray(np.asarray(a, dtype=np.complex128).T)[None] for a in nz])
+    draws = gain_db is not None and sigma is not None and np.any(sigma) and noise is None
+    if seed is None:
+        seeds = [gstate.next_ase_seed() if draws else 0 for _ in range(nspan)]
+    else:
+        seeds = [int(seed) + k for k in range(nspan)]
     ldesc, lkeep = _lib.make_link(nspan, gain, sigma, plates=plates, plate_sets=1, noise=noise,
-                                  seeds=[int(seed) + k for k in range(nspan)])
+                                  seeds=seeds)
     fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]             # [1][nfc][nfft]
     fy = np.ascontiguousarray(np.asarray(G.FIELDY, dtype=np.complex128).T)[None]
     io = _lib.complex_field(fx, fy)

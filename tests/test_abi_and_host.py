@@ -165,10 +165,30 @@ class _FakeDeviceField:
         self.closed = True
 
 
-def test_gstate_resident_field_reads_like_the_host_arrays():
+def test_gstate_resident_field_reads_like_the_host_arrays(monkeypatch):
     """GSTATE.FIELDX/FIELDY of a two-polarization link may live in HBM between in-line devices (gstate.RESIDENT):
-    reading or assigning either downloads once, lands in the arrays the field came from, and gives the device copy up"""
+    reading or assigning either downloads once and gives the device copy up.  Ordinary host arrays the caller may
+    still hold are never overwritten (the interpreter's value semantics); PINNED arrays are download targets."""
     from polmux_b200 import gstate
+    pmx.reset_all(8, 4, 1)
+    G = pmx.GSTATE
+    # ordinary arrays: x0 = GSTATE.FIELDX; fiber(); x1 = GSTATE.FIELDX leaves x0 alone
+    monkeypatch.setattr(_lib, 'host_is_pinned', lambda a: False)
+    x0 = np.zeros((32, 1), dtype=np.complex128)
+    y0 = np.zeros((32, 1), dtype=np.complex128)
+    G.FIELDX, G.FIELDY = x0, y0
+    fk = _FakeDeviceField(x0 + 3.0, y0 + 5.0)
+    G.put_device(fk, x0, y0)
+    x1 = G.FIELDX
+    assert x1 is not x0 and np.all(x0 == 0) and np.all(x1 == 3.0) and np.all(G.FIELDY == 5.0) and fk.closed
+    # a failed device call gives the host arrays back untouched
+    fk = _FakeDeviceField(x0, y0)
+    G.FIELDX, G.FIELDY = x0, y0
+    G.__dict__['_taken_resident'] = False
+    G.restore_host(fk, x0, y0)
+    assert fk.closed and G.FIELDX is x0 and G.FIELDY is y0
+    # pinned arrays (from here on): results land in them
+    monkeypatch.setattr(_lib, 'host_is_pinned', lambda a: True)
     pmx.reset_all(8, 4, 1)
     G = pmx.GSTATE
     hx = np.zeros((32, 1), dtype=np.complex128)

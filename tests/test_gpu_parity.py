@@ -296,3 +296,22 @@ def test_ampliflat_onepol(pol):
     assert np.allclose(quiet, tx * np.sqrt(10 ** 0.7), rtol=1e-14, atol=0)
     with pytest.raises(ValueError):
         pmx.ampliflat(7.0, 'gain', {'f': 5.0, 'onepol': 'both'})
+
+
+def test_ampliflat_default_calls_draw_fresh_noise():
+    """ampliflat.m:132-135 draws new randn samples at every call: two calls without an explicit seed must add
+    different ASE, and reseeding the global stream (randn('state',k) -> gstate.seed(k)) must repeat a run"""
+    from polmux_b200 import gstate
+    outs = []
+    for rep in range(2):
+        gstate.seed(77)
+        got = []
+        for call in range(2):
+            make_tx(1 << 8, 16)
+            pmx.ampliflat(16.0, 'gain', {'f': 5.0})
+            got.append((np.array(pmx.GSTATE.FIELDX), np.array(pmx.GSTATE.FIELDY)))
+        outs.append(got)
+    assert not np.array_equal(outs[0][0][0], outs[0][1][0])          # successive calls: independent noise
+    assert np.array_equal(outs[0][0][0], outs[1][0][0]) and np.array_equal(outs[0][1][1], outs[1][1][1])
+    d = outs[0][0][0] - outs[0][1][0]
+    assert abs(np.vdot(d, d).real / d.size) > 0
