@@ -45,12 +45,11 @@ static inline cpx pmx_root(long long m, long long M) {  // exp(-2*pi*i*m/M) in l
 }
 
 void pmx_fill_stage_twiddles(int L, cpx* out, int layout) {
-    if (layout == 1) {  // L = 1024 as 8 * 16 * 8 (CtaFFT<R, 1024>): [15][8] of W_128^(k*r), then [3][128] of W_1024^(k*{1,2,4})
+    if (layout == 1) {  // L = 1024 as 8 * 16 * 8 (CtaFFT<R, 1024>): [15][8] of W_128^(k*r), then [128] of W_1024^k
         size_t o = 0;
         for (int r = 1; r <= 15; ++r)
             for (int k = 0; k < 8; ++k) out[o++] = pmx_root((long long)k * r, 128);
-        for (int r = 1; r <= 4; r *= 2)
-            for (int k = 0; k < 128; ++k) out[o++] = pmx_root((long long)k * r, 1024);
+        for (int k = 0; k < 128; ++k) out[o++] = pmx_root((long long)k, 1024);
         return;
     }
     int ns = 1;
@@ -666,7 +665,6 @@ static void fill_plates(const pmx_fiber_desc& d, int sets, const double* db0, co
             P.db0 = db0 ? db0[(size_t)s * np + n] : 0.0;
             P.h0r = cos(-0.5 * P.db0);
             P.h0i = sin(-0.5 * P.db0);
-            P.pad = 0.0;
         }
         for (int n = 0; n < np; ++n) {
             PlateConst& P = out[(size_t)s * np + n];
@@ -689,6 +687,15 @@ static void fill_plates(const pmx_fiber_desc& d, int sets, const double* db0, co
                 P.c22r = (double)r; P.c22i = (double)i;
             } else {
                 P.c11r = 1; P.c11i = 0; P.c12r = 0; P.c12i = 0; P.c21r = 0; P.c21i = 0; P.c22r = 1; P.c22i = 0;
+            }
+            {   // C = diag(p, p*) * [ka kb; -kb* ka]:  p = c11/|c11|, ka = |c11|, kb = conj(p)*c12
+                const long double ar = P.c11r, ai = P.c11i, m = hypotl(ar, ai);
+                const long double pr = m > 0 ? ar / m : 1.0L, pi = m > 0 ? ai / m : 0.0L;
+                P.ka = (double)m;
+                P.pr = (double)pr;
+                P.pi = (double)pi;
+                P.kbr = (double)(pr * P.c12r + pi * P.c12i);
+                P.kbi = (double)(pr * P.c12i - pi * P.c12r);
             }
         }
     }
@@ -829,6 +836,10 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
         f.domega = f.w0 * ((double)d->nt / 8.0);
         f.g1r = cos(0.5 * f.dgdrms * f.domega);
         f.g1i = -sin(0.5 * f.dgdrms * f.domega);
+        f.g2r = cos(f.dgdrms * f.domega);
+        f.g2i = -sin(f.dgdrms * f.domega);
+        f.g4r = cos(2.0 * f.dgdrms * f.domega);
+        f.g4i = -sin(2.0 * f.dgdrms * f.domega);
         bool any = d->b30 != 0.0;
         for (int k = 0; k < d->nfc; ++k) {
             f.beta1[k] = d->beta1[k];

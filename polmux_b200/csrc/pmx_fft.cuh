@@ -40,7 +40,8 @@ __host__ __device__ constexpr int pmx_tw_offset(int L, int Ns) {
     return off;
 }
 // L = 1024 in FP64 runs as 8 * 16 * 8 (two exchanges instead of the three of 2 * 8 * 8 * 8, see CtaFFT<R, 1024>):
-// its table holds [15][8] twiddles W_128^(k*r) of the radix-16 stage, then [3][128] of the last radix-8 stage.
+// its table holds [15][8] twiddles W_128^(k*r) of the radix-16 stage, then [128] W_1024^k of the last radix-8 stage (its
+// W^2k and W^4k are two squarings: 4 KB of shared memory and two 128-bit loads per thread and transform less).
 #ifndef PMX_F32
 #define PMX_FFT_8_16_8 1
 #else
@@ -48,7 +49,7 @@ __host__ __device__ constexpr int pmx_tw_offset(int L, int Ns) {
 #endif
 __host__ __device__ constexpr int pmx_tw_layout(int L) { return (PMX_FFT_8_16_8 && L == 1024) ? 1 : 0; }
 __host__ __device__ constexpr int pmx_tw_total(int L) {
-    return pmx_tw_layout(L) == 1 ? 15 * 8 + 3 * 128 : (pmx_tw_offset(L, L) > 0 ? pmx_tw_offset(L, L) : 1);
+    return pmx_tw_layout(L) == 1 ? 15 * 8 + 128 : (pmx_tw_offset(L, L) > 0 ? pmx_tw_offset(L, L) : 1);
 }
 
 template <bool INV>
@@ -316,7 +317,9 @@ struct CtaFFT<R, 1024> {
         // ---- stage C: radix 8, Ns = 128: twiddles W_1024^(t*r), natural-order output t + r*128
         {
             const cpx* tc = tw + 15 * 8;
-            const cpx w1 = tc[t], w2 = tc[128 + t], w4 = tc[256 + t];
+            const cpx w1 = tc[t];
+            const cpx w2 = mkc(fma(w1.x, w1.x, -w1.y * w1.y), (real)2 * w1.x * w1.y);
+            const cpx w4 = mkc(fma(w2.x, w2.x, -w2.y * w2.y), (real)2 * w2.x * w2.y);
             const cpx w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
             const cpx w7 = cmul(w4, w3);
             dft8_tw(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], w1, w2, w3, w4, w5, w6, w7);

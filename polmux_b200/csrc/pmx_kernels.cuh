@@ -118,12 +118,23 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
     if (f.spm && !f.xpm && pmax * c->leff < 0.015625) c->bmode |= PMX_BM_NL_SMALL;
     if (f.disp_scalar && f.pmd) {
         double s, cs;
-        sincos(-(0.5 * f.dgdrms * f.domega * dzb_first / lcorr), &s, &cs);
+        const double af = -(0.5 * f.dgdrms * f.domega * dzb_first / lcorr), al = -(0.5 * f.dgdrms * f.domega * dzb_last / lcorr);
+        sincos(af, &s, &cs);
         c->gpf_r = cs;
         c->gpf_i = s;
-        sincos(-(0.5 * f.dgdrms * f.domega * dzb_last / lcorr), &s, &cs);
+        sincos(al, &s, &cs);
         c->gpl_r = cs;
         c->gpl_i = s;
+        sincos(2.0 * af, &c->gpf2[1], &c->gpf2[0]);
+        sincos(4.0 * af, &c->gpf4[1], &c->gpf4[0]);
+        sincos(2.0 * al, &c->gpl2[1], &c->gpl2[0]);
+        sincos(4.0 * al, &c->gpl4[1], &c->gpl4[0]);
+    }
+    if (f.disp_scalar && f.gvd_any) {  // third difference of -betat*dz over bins spaced by domega: -dz*b30*domega^3
+        double s, cs;
+        sincos(-(dz_cur * (6.0 * f.b30_6) * f.domega * f.domega * f.domega), &s, &cs);
+        c->gd3_r = cs;
+        c->gd3_i = s;
     }
     if (ntrunk > 0 && (c->ntot + ntrunk - nmem > f.nplates || c->n_first < 0)) {
         c->state = PMX_ST_ERROR;  // brf.theta(n) index error in the reference (fiber.m:910)
@@ -197,6 +208,14 @@ static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst
         g->gpl_r = c->gpl_r;
         g->gpl_i = c->gpl_i;
         g->db0_last = (f.pmd && ntrunk > 0) ? plg[ntrunk - 1].db0 : 0.0;
+        g->gd3_r = c->gd3_r;
+        g->gd3_i = c->gd3_i;
+        for (int i = 0; i < 2; ++i) {
+            g->gpf2[i] = c->gpf2[i];
+            g->gpf4[i] = c->gpf4[i];
+            g->gpl2[i] = c->gpl2[i];
+            g->gpl4[i] = c->gpl4[i];
+        }
         g->ntrunk = ntrunk;
         g->n_first = n_first;
         g->bmode = f.pmd ? c->bmode : (c->bmode & PMX_BM_NL_SMALL);
@@ -267,7 +286,15 @@ struct PmxTw4 {
     static constexpr int NLO = 1 << LO, NHI = 1 << HI, PER = NLO + NHI;
 };
 
-#define PMX_LIVE_CAP 256    // realizations whose done-flags a CTA caches in shared memory
+#define PMX_LIVE_CAP 64    // realizations whose done-flags a CTA caches in shared memory
+
+// Pass B, FP64: per-thread phasors that depend on the tile's bins and the step only (not on the field) are evaluated
+// BEFORE the CTA waits for its tile and parked here while the forward transform needs the registers.
+#ifdef PMX_F32
+#define PMX_B_SCR 0
+#else
+#define PMX_B_SCR 6
+#endif
 
 // Shared-memory plan of a pass CTA working on G rows (pass B) or G columns (passes A, C) of
 // length L.  PF: the next tile is prefetched by TMA into its own landing buffer while the
@@ -283,18 +310,21 @@ struct PassSmem {
     static constexpr int WORK_BYTES = G * PmxSmem<L, G>::STRIDE * (int)sizeof(cpx);
     static constexpr int WORK_OFF = PF ? ((TILE_BYTES + 1023) / 1024) * 1024 : 0;
     static constexpr int TW_OFF = WORK_OFF + ((WORK_BYTES + 15) / 16) * 16;   // stage twiddles
-    static constexpr int PKG_BYTES = (KIND == 1) ? (int)sizeof(StepPkg) : PMX_PKG_HEAD;
+    static constexpr int PKG_BYTES = (KIND == 1) ? (int)sizeof(StepPkg) : PMX_PKG_HEAD_AC;
     static constexpr int TAB_BYTES = (KIND == 1) ? 0 : ((G * PmxTw4<L>::PER * (int)sizeof(cpx) + 15) / 16) * 16;
     static constexpr int AUX_BYTES = PKG_BYTES + TAB_BYTES;
     static constexpr int AUX_OFF = TW_OFF + ((pmx_tw_total(L) * (int)sizeof(cpx) + 15) / 16) * 16;
     static constexpr int PLATE_OFF = AUX_OFF + 2 * AUX_BYTES;               // pass B: chunks of trunks beyond the package
-    static constexpr int RED_OFF = PLATE_OFF + ((KIND == 1) ? PMX_PKG_PLATES * (int)sizeof(PlateConst) : 0);
+    static constexpr int SCR_OFF = PLATE_OFF + ((KIND == 1) ? PMX_PKG_PLATES * (int)sizeof(PlateConst) : 0);
+    static constexpr int SCR_BYTES = (KIND == 1) ? PMX_B_SCR * THREADS * (int)sizeof(cpx) : 0;   // [PMX_B_SCR][THREADS]
+    static constexpr int RED_OFF = SCR_OFF + SCR_BYTES;
     static constexpr int LIVE_OFF = RED_OFF + 32 * 8;
     static constexpr int MBAR_OFF = LIVE_OFF + PMX_LIVE_CAP;
-    static constexpr int TOTAL = MBAR_OFF + 16;  // the dynamic shared array is declared 1024-byte aligned
-    static constexpr int LOAD_BYTES = TILE_BYTES + AUX_BYTES;  // bytes one tile's mbarrier phase expects
+    static constexpr int TOTAL = MBAR_OFF + 32;  // the dynamic shared array is declared 1024-byte aligned
+    static constexpr int LOAD_BYTES = TILE_BYTES + AUX_BYTES;  // bytes one tile's mbarrier phase expects (passes A, C)
     static_assert(WORK_BYTES >= TILE_BYTES, "exchange buffer must hold a landed tile");
-    static_assert(sizeof(StepPkg) % 16 == 0 && PMX_PKG_HEAD % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static_assert(sizeof(StepPkg) % 16 == 0 && PMX_PKG_HEAD % 16 == 0 && PMX_PKG_HEAD_AC % 16 == 0,
+                  "bulk copies move multiples of 16 bytes");
 };
 
 // copy the per-L stage-twiddle table into shared memory (once per persistent CTA)
@@ -606,11 +636,117 @@ __device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const dou
     }
 }
 
+// FP64, scalar dispersion mode: what a thread of pass B knows about its eight bins before the field arrives.
+// The bins k = k1 + N1*(t + q*T) are equally spaced in frequency; in rising order they are q = 4..7 (negative
+// frequencies) then q = 0..3, so with j = (q + 4) & 7 the angular frequency is wb + j*domega.
+struct PmxBPre {
+    cpx E, D1, D2;    // common phase exp(i*phi(j)), phi = -betat*dz: value, first and second difference at j = 4
+    cpx E0, pf, pl;   // exp(-i*db1/2) (whole trunks), first / last trunk phasor (partial trunks), all at j = 0
+};
+
+#ifndef PMX_F32
+// phi(w) = -dz*(b1*w + b2/2*w^2 + b30/6*w^3) at w = wc; its forward differences over the bin spacing d are evaluated
+// from their closed forms (no cancellation):
+//   D1 = phi(w+d) - phi(w)   = -dz*d*(b1 + b2*(w + d/2) + b30_6*(3*w*(w + d) + d*d))
+//   D2 = D1(w+d) - D1(w)     = -dz*d*d*(b2 + 6*b30_6*(w + d))
+//   D3                        = -dz*6*b30_6*d^3          (per step: StepPkg.gd3)
+// The six phasors go straight to the thread's scratch slots scr[slot*stride] (PmxBPre order).
+__device__ __forceinline__ void pmx_b_pre(cpx* scr, int stride, const StepPkg* st, const FiberConst& f, int col, double fnb,
+                                          double fnc, bool any_full) {
+    const double wb = __dmul_rn(f.w0, fnb);   // lowest bin (j = 0): base of the trunk phasor progressions
+    if (f.gvd_any) {
+        const double wc = __dmul_rn(f.w0, fnc);   // middle bin (j = 4, q = 0): anchor of the common-phase recurrence
+        const double b1 = f.beta1[col], b2 = f.beta2[col], d = f.domega, dz = st->dz_cur;
+        const double w2 = __dmul_rn(wc, wc);
+        double bt = __dadd_rn(__dmul_rn(wc, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));   // betat as fiber.m:355-356
+        bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, wc), f.b30_6));
+        const double ndzd = -(dz * d);
+        const double a1 = ndzd * (b1 + fma(b2, fma(0.5, d, wc), f.b30_6 * fma(3.0 * wc, wc + d, d * d)));
+        const double a2 = ndzd * d * fma(6.0 * f.b30_6, wc + d, b2);
+        scr[0 * stride] = pmx_cis(-(bt * dz));
+        scr[1 * stride] = pmx_cis(a1);
+        scr[2 * stride] = pmx_cis(a2);
+    }
+    if (f.pmd) {
+        const double d1b = __dmul_rn(f.dgdrms, wb);  // db1 = dgdrms*omega (:358)
+        scr[3 * stride] = any_full ? pmx_cis(-0.5 * d1b) : mkc(1.0, 0.0);
+        // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+        scr[4 * stride] = pmx_cis(-(0.5 * (d1b + st->plates[0].db0) * st->dzb_first / f.lcorr));
+        scr[5 * stride] = pmx_cis(-(0.5 * (d1b + st->db0_last) * st->dzb_last / f.lcorr));
+    }
+}
+
+// One trunk in the PSP basis of its plate is diag(e, conj(e)) with e(j) = b*g^j over the thread's bins (deltabeta is
+// linear in omega).  Written as conj(e) * diag(e^2, 1): the scalar conj(e) is common to both polarizations and is
+// collected over the trunks of the step in closed form (conj(prod b) * conj(prod g)^j, folded into the common-phase
+// recurrence), so a trunk multiplies ONE polarization by e(j)^2 = b2 * g2^j.  Two interleaved chains (even / odd j)
+// advanced by g4 = g2^2: three phasors live at a time.
+__device__ __forceinline__ void pmx_b_diag2(cpx (&x)[8], cpx b2, cpx g2, cpx g4) {
+    cpx ea = b2, eo = cmul(b2, g2);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const int qa = (j + 4) & 7, qo = (j + 5) & 7;
+        x[qa] = cmul(x[qa], ea);
+        x[qo] = cmul(x[qo], eo);
+        if (j < 6) {
+            ea = cmul(ea, g4);
+            eo = cmul(eo, g4);
+        }
+    }
+}
+// u <- [ka kb; -conj(kb) ka] * u, ka real: 12 FMAs per bin
+__device__ __forceinline__ void pmx_b_applyK(cpx (&x)[8], cpx (&y)[8], double ka, double kbr, double kbi) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const cpx a = x[q], b = y[q];
+        x[q] = mkc(fma(-kbi, b.y, fma(kbr, b.x, ka * a.x)), fma(kbi, b.x, fma(kbr, b.y, ka * a.y)));
+        y[q] = mkc(fma(-kbi, a.y, fma(-kbr, a.x, ka * b.x)), fma(kbi, a.x, fma(-kbr, a.y, ka * b.y)));
+    }
+}
+
+// common phase of the eight bins by a difference recurrence anchored at the thread's MIDDLE bin (j = 4, i.e. q = 0):
+//   upwards    E(j+1) = E(j)*D1(j),        D1(j+1) = D1(j)*D2(j),        D2(j+1) = D2(j)*D3
+//   downwards  E(j-1) = E(j)*conj(D1(j-1)), D1(j-1) = D1(j)*conj(D2(j-1)), D2(j-1) = D2(j)*conj(D3)
+// three evaluations + 18 complex products instead of eight evaluations; a rounding error of the first / second
+// difference is amplified by at most 4 / 6 (binomials of the distance to the anchor).
+__device__ __forceinline__ void pmx_b_common(cpx (&x)[8], cpx (&y)[8], cpx E, cpx D1, cpx D2, cpx D3) {
+    x[0] = cmul(x[0], E);
+    y[0] = cmul(y[0], E);
+    {   // j = 5, 6, 7  <->  q = 1, 2, 3
+        cpx e = E, d1 = D1, d2 = D2;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            e = cmul(e, d1);
+            x[q] = cmul(x[q], e);
+            y[q] = cmul(y[q], e);
+            if (q < 3) d1 = cmul(d1, d2);
+            if (q < 2) d2 = cmul(d2, D3);
+        }
+    }
+    {   // j = 3, 2, 1, 0  <->  q = 7, 6, 5, 4
+        cpx e = E, d1 = D1, d2 = D2;
+#pragma unroll
+        for (int q = 7; q >= 4; --q) {
+            d2 = cmulc(d2, D3);
+            d1 = cmulc(d1, d2);
+            e = cmulc(e, d1);
+            x[q] = cmul(x[q], e);
+            y[q] = cmul(y[q], e);
+        }
+    }
+}
+#endif
+
 template <typename R, int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 1>;
     constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
+#ifdef PMX_F32
+    constexpr bool PRE = false;
+#else
+    constexpr bool PRE = SC;   // FP64 scalar dispersion mode: data-independent phasors before the tile wait
+#endif
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;
@@ -618,8 +754,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
     unsigned char* aux0 = sm + S::AUX_OFF;
     PlateConst* schunk = reinterpret_cast<PlateConst*>(sm + S::PLATE_OFF);
+    cpx* scr = reinterpret_cast<cpx*>(sm + S::SCR_OFF) + threadIdx.x;   // [slot][THREADS]
     unsigned char* sdone = sm + S::LIVE_OFF;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);      // [0]: tile, [1]: step package
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
     const size_t N = (size_t)p.N1 * p.N2;
     constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
@@ -639,17 +776,21 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         }
         return tl;
     };
+    // The step package travels on its own mbarrier: it is a few KB out of the L2 and lands long before the tile, so
+    // the threads can evaluate everything that does not depend on the field while the tile is still in flight.
     auto issue = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
-        pmx_mbar_expect_tx(mbar, S::LOAD_BYTES);
         const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
-        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
-        pmx_bulk_load(aux0 + buf * S::AUX_BYTES, &p.pkg[b_], S::PKG_BYTES, mbar);
+        pmx_mbar_expect_tx(mbar + 1, S::PKG_BYTES);
+        pmx_bulk_load(aux0 + buf * S::AUX_BYTES, &p.pkg[b_], S::PKG_BYTES, mbar + 1);
+        pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
+        for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
+        pmx_mbar_init(mbar + 1, 1);
         pmx_fence_mbar_init();
     }
     pmx_load_stage_tw<L>(stw, p.tw_stage);
@@ -674,12 +815,26 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         const int next = live(tile + gridDim.x);
         cpx x[8], y[8];
         PMX_T_MARK(0)
+        pmx_mbar_wait(mbar + 1, phase);
+        const int ntrunk = st->ntrunk, bmode = st->bmode;
+        // Scalar dispersion mode: a thread's bins are k = k1 + N1*(t + q*T): q < 4 on the positive-frequency side,
+        // q >= 4 on the negative one, equally spaced by domega; bin 4 lies four spacings BELOW bin 0.
+        const long long kb = (long long)k1 + (long long)p.N1 * t;
+        const double dfn = (double)((long long)p.N1 * T) * f.inv_nsymb;
+        const double fn0 = (double)kb * f.inv_nsymb;
+        const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
+        const bool any_full = (ntrunk > 2) || (st->dzb_first == f.lcorr) || (st->dzb_last == f.lcorr);
+#ifndef PMX_F32
+        if constexpr (PRE) {
+            if (ntrunk > 0) pmx_b_pre(scr, S::THREADS, st, f, col, fn4, fn0, any_full);
+        }
+#endif
+        PMX_T_MARK(7)
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;
         PMX_T_MARK(1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
-        const int ntrunk = st->ntrunk, bmode = st->bmode;
         if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
         __syncthreads();
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
@@ -690,65 +845,63 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         // the transform code, run twice
 #pragma unroll 1
         for (int dir = 0; dir < 2; ++dir) {
+#ifndef PMX_EXP_NO_FFT
             CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
+#endif
             if (dir == 1) break;
             PMX_T_MARK(3)
 
             // ---- linear step in the frequency domain, fiber.m:907-933
+#ifdef PMX_EXP_NO_PHYS
+            if (false) {
+#else
             if (ntrunk > 0) {
+#endif
                 const double dz_cur = st->dz_cur;
-                // Scalar dispersion mode: a thread's bins are k = k1 + N1*(t + q*T): q < 4 on the positive-
-                // frequency side, q >= 4 on the negative one, equally spaced by domega.
-                const long long kb = (long long)k1 + (long long)p.N1 * t;
-                const double dfn = (double)((long long)p.N1 * T) * f.inv_nsymb;
-                const double fn0 = (double)kb * f.inv_nsymb;
-                const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
+#ifndef PMX_F32
+                // scalar phase common to both polarizations collected over the trunks: conj(Bacc) * conj(Gacc)^j
+                cpx Bacc = mkc(1.0, 0.0), Gacc = mkc(1.0, 0.0);
+#endif
                 if (f.pmd) {
                     const double lcorr = f.lcorr, dzb_first = st->dzb_first, dzb_last = st->dzb_last;
                     if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
-                    const bool any_full = (ntrunk > 2) || (dzb_first == lcorr) || (dzb_last == lcorr);
                     // whole trunks share exp(-i*db1/2) per bin
-                    double d1[SC ? 1 : 8];
-                    cpx e1[SC ? 1 : 8];
-                    double d10 = 0.0, d14 = 0.0;
-                    cpx E0 = mkc((real)1.0, (real)0.0);
-                    // scalar mode: phases of the step's first / last trunk at the thread's first bin.  Its bins
-                    // q = 0..3 (positive frequencies) and 4..7 (negative) are equally spaced, bin 4 lying four spacings
-                    // BELOW bin 0, and db1 is linear in omega: with g = exp(-i*0.5*dgdrms*domega*dzb/lcorr) the phase
-                    // factors of bins 1..3 are e0*g^q and those of bins 4..7 are e0*conj(g)^4*g^(q-4).
-                    cpx pf0, pl0;
+                    double d1[(SC) ? 1 : 8];
+                    cpx e1[(SC) ? 1 : 8];
+                    // scalar mode: phases of the step's first / last trunk at the thread's lowest bin; db1 is linear
+                    // in omega, so the other bins follow by a geometric progression (pmx_b_diag)
 #ifdef PMX_F32
-                    cpx pf4, pl4;  // FP32: g^4 in float would cost 2e-7 of phase per trunk; evaluate both base bins
-#endif
-#ifdef PMX_F32
+                    cpx pf0, pl0, pf4, pl4;  // FP32: g^4 in float would cost 2e-7 of phase per trunk; evaluate both base bins
                     // FP32: the whole-trunk factor exp(-i*db1/2) of a bin is the same for every whole trunk of the
                     // step, so a float-rounded copy (or a float progression) would repeat the SAME phase error in
                     // each of up to nplates factors.  It is kept in double; each trunk's exp(-i*(db1+db0)/2) is
                     // formed in double and rounded once, which makes the per-trunk errors independent.
                     double2 Ed[8];
+#else
+                    cpx E0b, pfb, plb, pprev = mkc(1.0, 0.0);
 #endif
                     if constexpr (SC) {
-                        d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
-                        d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
-                        if (any_full) {
 #ifdef PMX_F32
+                        const double d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
+                        const double d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
+                        if (any_full) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;
                                 pmx_sincos_fast(-0.5 * __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn)), &Ed[q].y, &Ed[q].x);
                             }
-#else
-                            E0 = pmx_cis(-0.5 * d10);
-#endif
                         }
                         // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
                         // independent and interleave
                         const double db0f = st->plates[0].db0, db0l = st->db0_last;
                         pf0 = pmx_cis(-(0.5 * (d10 + db0f) * dzb_first / lcorr));
                         pl0 = pmx_cis(-(0.5 * (d10 + db0l) * dzb_last / lcorr));
-#ifdef PMX_F32
                         pf4 = pmx_cis(-(0.5 * (d14 + db0f) * dzb_first / lcorr));
                         pl4 = pmx_cis(-(0.5 * (d14 + db0l) * dzb_last / lcorr));
+#else
+                        E0b = scr[3 * S::THREADS];
+                        pfb = scr[4 * S::THREADS];
+                        plb = scr[5 * S::THREADS];
 #endif
                     } else {
                         const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
@@ -782,7 +935,6 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                             const PlateConst& P = pl[k - k0];
                             const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
                             if constexpr (SC) {
-                                cpx e0, e4, g;
 #ifdef PMX_F32
                                 if (dzb == lcorr) {
 #pragma unroll
@@ -794,31 +946,51 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                                     if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);
                                     continue;
                                 }
-#endif
-                                if (dzb == lcorr) {  // exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
-                                    const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
-                                    e0 = cmul(E0, h0);
-                                    g = mkc((real)f.g1r, (real)f.g1i);
-                                } else {  // partial trunk (first or last of the step)
-                                    e0 = (k == 0) ? pf0 : pl0;
-                                    g = (k == 0) ? mkc((real)st->gpf_r, (real)st->gpf_i) : mkc((real)st->gpl_r, (real)st->gpl_i);
+                                {   // partial trunk: bins 1..3 are e0*g^q, bins 5..7 e4*g^(q-4)
+                                    const cpx e0 = (k == 0) ? pf0 : pl0, e4 = (k == 0) ? pf4 : pl4;
+                                    const cpx g = (k == 0) ? mkc((real)st->gpf_r, (real)st->gpf_i) : mkc((real)st->gpl_r, (real)st->gpl_i);
+                                    const cpx g2 = cmul(g, g);
+                                    const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
+                                    const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
+                                    x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
+                                    x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
+                                    x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
+                                    x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
+                                    x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
+                                    x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
+                                    x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
+                                    x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
                                 }
-                                const cpx g2 = cmul(g, g);
-#ifdef PMX_F32
-                                e4 = (k == 0) ? pf4 : pl4;  // (whole trunks took the double-phasor path above)
 #else
-                                e4 = cmulc(e0, cmul(g2, g2));
+                                {
+                                    cpx b, g, g2, g4;
+                                    if (dzb == lcorr) {  // whole trunk: exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
+                                        b = cmul(E0b, mkc(P.h0r, P.h0i));
+                                        g = mkc(f.g1r, f.g1i);
+                                        g2 = mkc(f.g2r, f.g2i);
+                                        g4 = mkc(f.g4r, f.g4i);
+                                    } else if (k == 0) {  // partial trunk (first or last of the step)
+                                        b = pfb;
+                                        g = mkc(st->gpf_r, st->gpf_i);
+                                        g2 = mkc(st->gpf2[0], st->gpf2[1]);
+                                        g4 = mkc(st->gpf4[0], st->gpf4[1]);
+                                    } else {
+                                        b = plb;
+                                        g = mkc(st->gpl_r, st->gpl_i);
+                                        g2 = mkc(st->gpl2[0], st->gpl2[1]);
+                                        g4 = mkc(st->gpl4[0], st->gpl4[1]);
+                                    }
+                                    b = cmul(b, pprev);          // left phase of the boundary matrix just applied
+                                    Bacc = cmul(Bacc, b);
+                                    Gacc = cmul(Gacc, g);
+                                    pmx_b_diag2(x, cmul(b, b), g2, g4);
+                                    if (k < ntrunk - 1) {        // basis change matR(n+1)' * matR(n) = diag(p, p*) * K
+                                        pmx_b_applyK(x, y, P.ka, P.kbr, P.kbi);
+                                        pprev = mkc(P.pr, P.pi);
+                                    }
+                                    continue;
+                                }
 #endif
-                                const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
-                                const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
-                                x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
-                                x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
-                                x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
-                                x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
-                                x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
-                                x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
-                                x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
-                                x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
                             } else {
                                 if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
                                     const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
@@ -847,35 +1019,49 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
                     }
                     if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
                 }
+#ifndef PMX_F32
+                if constexpr (PRE) {  // common phase exp(-i*betat*sum(dzb)) (:924,927-928) times the trunks' common scalar
+                    // at the anchor bin (j = 4) the collected scalar is conj(Bacc * Gacc^4)
+                    const cpx G2 = cmul(Gacc, Gacc);
+                    const cpx S4 = cmul(Bacc, cmul(G2, G2));
+                    if (f.gvd_any)
+                        pmx_b_common(x, y, cmulc(scr[0 * S::THREADS], S4), cmulc(scr[1 * S::THREADS], Gacc),
+                                     scr[2 * S::THREADS], mkc(st->gd3_r, st->gd3_i));
+                    else if (f.pmd)
+                        pmx_b_common(x, y, cconj(S4), cconj(Gacc), mkc(1.0, 0.0), mkc(1.0, 0.0));
+                } else
+#endif
 #ifdef PMX_EXP_NO_COMMON
                 if (false) {
 #else
                 if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
 #endif
-                    double a[8];
-                    if constexpr (SC) {  // betat regenerated per bin (:355-356)
-                        const double b1 = f.beta1[col], b2 = f.beta2[col];
+                    {
+                        double a[8];
+                        if constexpr (SC) {  // betat regenerated per bin (:355-356)
+                            const double b1 = f.beta1[col], b2 = f.beta2[col];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
+                                const double w = __dmul_rn(f.w0, fn);
+                                const double w2 = __dmul_rn(w, w);
+                                double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
+                                bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
+                                a[q] = -(bt * dz_cur);
+                            }
+                        } else {
+                            const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
+                        }
+                        cpx e[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) e[q] = pmx_cis(a[q]);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
-                            const double w = __dmul_rn(f.w0, fn);
-                            const double w2 = __dmul_rn(w, w);
-                            double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
-                            bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
-                            a[q] = -(bt * dz_cur);
+                            x[q] = cmul(x[q], e[q]);
+                            y[q] = cmul(y[q], e[q]);
                         }
-                    } else {
-                        const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
-                    }
-                    cpx e[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) e[q] = pmx_cis(a[q]);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        x[q] = cmul(x[q], e[q]);
-                        y[q] = cmul(y[q], e[q]);
                     }
                 }
             }

@@ -19,7 +19,11 @@ constexpr int GAC = PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4));
 #else
 constexpr int GAC = PMX_GAC;
 #endif
+#ifdef PMX_GB
+constexpr int GB = PMX_GB;
+#else
 constexpr int GB = (PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4)) * (L / 8) > 1024) ? 1 : PSCALE * ((L >= 1024) ? 1 : (L == 512 ? 2 : 4));
+#endif
 constexpr int TILE_CAP = 32 * 1024;
 #ifndef PMX_PFAC
 // Since passes A and C read and write contiguous rows straight from / to registers they no longer stage a

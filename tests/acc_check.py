@@ -17,3 +17,15 @@ for lg, man in ((12, 'no'), (14, 'no'), (16, 'no'), (16, 'yes'), (18, 'yes')):
     print('N=2^%d manakov=%s  rel_l2=%.2e  ncycle %d/%d  max|ddz/dz|=%.2e' % (
         lg, man, rel_l2(G.FIELDX, G.FIELDY, gs.FIELDX, gs.FIELDY), pmx.FIBER_LAST['ncycle'], gs.log['ncycle'],
         np.max(np.abs(dz_g - dz_o) / dz_o) if len(dz_g) == len(dz_o) else -1))
+# extended-precision arbiter (the same restatement in np.longdouble): how far are the float64 oracle and the CUDA path from it
+for lg, man in ((12, 'no'), (14, 'yes')):
+    fib = base_fiber(length=1e5, dgd=1.0, nplates=10, manakov=man)
+    gl = make_tx(1 << (lg - 4), 16, real=np.longdouble)
+    orc.fiber(gl, fib, 'gps-', rng=np.random.Generator(np.random.PCG64(1000)))
+    gs = make_tx(1 << (lg - 4), 16)
+    orc.fiber(gs, fib, 'gps-', rng=np.random.Generator(np.random.PCG64(1000)))
+    pmx.fiber(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(1000)))
+    G = pmx.GSTATE
+    print('N=2^%d manakov=%s  vs longdouble arbiter: oracle(f64) %.2e   CUDA %.2e   (CUDA vs oracle %.2e)' % (
+        lg, man, rel_l2(gs.FIELDX, gs.FIELDY, gl.FIELDX, gl.FIELDY), rel_l2(G.FIELDX, G.FIELDY, gl.FIELDX, gl.FIELDY),
+        rel_l2(G.FIELDX, G.FIELDY, gs.FIELDX, gs.FIELDY)))

@@ -31,10 +31,10 @@ work.broadcast_from(tx); plan.execute(work)
 lib.pmx_debug_timing(ctx.h, None, 1)
 work.broadcast_from(tx); res = plan.execute(work)
 lib.pmx_debug_timing(ctx.h, buf.ctypes.data_as(ctypes.c_void_p), 0)
-namesB = ['tile top (plates, ctl, tables)', 'mbarrier wait (TMA)', 'tile LDS + barrier + issue', 'forward FFT', 'Jones + phases', 'inverse FFT', 'twiddle + store + barrier']
-namesAC = ['tile top (ctl, tables)', 'mbarrier wait (TMA)', 'tile LDS + barrier + issue', 'NL step (A) / -', 'FFT', 'twiddle/scale + staging STS', 'barrier + TMA store issue (+ max publish)']
+namesB = ['tile top (plates, ctl, tables)', 'mbarrier wait (TMA)', 'tile LDS + barrier + issue', 'forward FFT', 'Jones + phases', 'inverse FFT', 'twiddle + store + barrier', 'pkg wait + data-independent phasors (before the tile wait)']
+namesAC = ['tile top (ctl, tables)', 'mbarrier wait (TMA)', 'tile LDS + barrier + issue', 'NL step (A) / -', 'FFT', 'twiddle/scale + staging STS', 'barrier + TMA store issue (+ max publish)', '-']
 for kind, title, names in ((0, 'pass A', namesAC), (1, 'pass B', namesB), (2, 'pass C', namesAC)):
-    t = buf[8 * kind:8 * kind + 7].astype(float)
+    t = buf[8 * kind:8 * kind + 8].astype(float)
     print('%s phases, share of CTA cycles (thread 0), total %.0f Mcycles:' % (title, t.sum() / 1e6))
     for n_, v in zip(names, t):
         print('  %-44s %5.1f%%' % (n_, 100 * v / max(t.sum(), 1)))
