@@ -119,7 +119,40 @@ def fib(**kw):
     return f
 
 
+def run_c1_case(name='c1_cnlse_10plates_100km_2e16'):
+    """BASELINE config C1 at its full size (Run_my_PDM_QPSK: 2^12 symbols x 16 samples = 2^16 samples, 28 GBaud, 100 km SMF,
+    'gps-' CNLSE, 10 plates, x.dgd = 1.0 -- the value Run_my_PDM_QPSK.m:46 evaluates to) through the interpreted
+    create_field.m + fiber.m.  Stored compactly under tests/golden/big/: the outputs, the plate draw and a checksum of
+    the seeded inputs (the tests regenerate them), not the 2^16-sample inputs themselves."""
+    import hashlib
+    nsymb, nt, seed = 1 << 12, 16, 1000
+    f = fib(length=1e5, dgd=1.0, nplates=10, manakov='no')
+    it = new_interp(seed)
+    ex, ey = tx_through_reference(it, nsymb, nt, 1, 28.0, 2.0, 'unique', True)
+    pre = snapshot(it)
+    res = it.call('fiber', [to_m(f), 'gps-'], 1)
+    post = snapshot(it)
+    brf = from_m(res[0])
+    meta = {'name': name, 'nsymb': nsymb, 'nt': nt, 'nch': 1, 'ftype': 'unique', 'fiber': f, 'flag': 'gps-', 'seed': seed,
+            'rate': 28.0, 'pavg': 2.0, 'two_pol': True, 'warnings': it.warnings,
+            'sha256_in': hashlib.sha256(np.ascontiguousarray(ex).tobytes() + np.ascontiguousarray(ey).tobytes()).hexdigest(),
+            'sha256_tx': hashlib.sha256(np.ascontiguousarray(pre['FIELDX']).tobytes()
+                                        + np.ascontiguousarray(pre['FIELDY']).tobytes()).hexdigest()}
+    data = {'out_FIELDX': post['FIELDX'], 'out_FIELDY': post['FIELDY'], 'out_DELAY': post['DELAY'], 'out_DISP': post['DISP'],
+            'tx_power_sum': np.array([np.sum(np.abs(pre['FIELDX']) ** 2 + np.abs(pre['FIELDY']) ** 2)]),
+            'meta': np.array(json.dumps(meta))}
+    for k in ('db0', 'theta', 'epsilon'):
+        data['brf_' + k] = np.asarray(brf[k]).ravel()
+    data['brf_lcorr'] = np.asarray(brf['lcorr']).ravel()
+    os.makedirs(os.path.join(OUT, 'big'), exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, 'big', name + '.npz'), **data)
+    print('%-28s N=%-6d flag=gps-  |out|=%.6e' % (name, nsymb * nt, np.linalg.norm(post['FIELDX'])))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[2] == 'c1':     # only the full-size C1 case
+        run_c1_case()
+        sys.exit(0)
     run_case('lin_gvd_2pol', 256, 16, 1, 'unique', fib(length=1e5), 'g---', want_brf=True)
     run_case('lin_pmd_20plates', 256, 16, 1, 'unique', fib(length=8e4, dgd=0.5, nplates=20), 'gp--')
     run_case('cnlse_10plates_100km', 256, 16, 1, 'unique', fib(length=1e5, dgd=1.0, nplates=10, manakov='no'), 'gps-',
@@ -151,3 +184,4 @@ if __name__ == '__main__':
     run_print_case('wdm3_pmf', 128, 64, 3, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],
                                                          epsilon=[0.1, 0.5, -0.3], manakov='no', slope=0.057), 'gps-', pavg=1.0)
     run_print_case('scalar_sep3_ltol', 256, 16, 3, 'sepfields', fib(length=2e4, ltol=2e-6, slope=0.057), 'g-sx', two_pol=False)
+    run_c1_case()

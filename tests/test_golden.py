@@ -116,3 +116,50 @@ def test_cuda_scalar_path_matches_reference_source(name):
     assert G.FIELDY is None or np.size(G.FIELDY) == 0
     np.testing.assert_allclose(G.DELAY, z['out_DELAY'], rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(G.DISP, z['out_DISP'], rtol=1e-13, atol=1e-13)
+
+
+# ---- BASELINE config C1 at its full size (2^16 samples), from the interpreted reference (oracle/make_golden.py c1) ----
+BIG = os.path.join(GOLD, 'big', 'c1_cnlse_10plates_100km_2e16.npz')
+
+
+def _load_c1():
+    import hashlib
+    z = np.load(BIG)
+    m = json.loads(str(z['meta']))
+    ex, ey, _, _ = synth.pdm_qpsk(m['nsymb'], m['nt'], 1)
+    assert hashlib.sha256(np.ascontiguousarray(ex).tobytes() + np.ascontiguousarray(ey).tobytes()).hexdigest() == m['sha256_in']
+    return z, m, ex, ey
+
+
+def test_c1_full_size_oracle_matches_reference_source():
+    """C1 (Run_my_PDM_QPSK: 2^12 symbols x 16 samples, 100 km, 'gps-' CNLSE, 10 plates): numpy restatement ==
+    interpreted create_field.m + fiber.m at the configuration's own size"""
+    import hashlib
+    z, m, ex, ey = _load_c1()
+    gs = orc.reset_all(m['nsymb'], m['nt'], 1)
+    gs.SYMBOLRATE, gs.POWER, gs.LAMBDA = m['rate'], np.array([float(m['pavg'])]), synth.wdm_lambdas(1)
+    orc.create_field(gs, 'unique', ex, ey, power_average=True)
+    assert abs(np.sum(np.abs(gs.FIELDX) ** 2 + np.abs(gs.FIELDY) ** 2) / float(z['tx_power_sum'][0]) - 1) < 1e-14
+    brf = orc.fiber(gs, m['fiber'], m['flag'], rng=np.random.Generator(np.random.PCG64(m['seed'])))
+    assert orc.rel_l2(gs.FIELDX, gs.FIELDY, z['out_FIELDX'], z['out_FIELDY']) < 1e-13
+    for k in ('db0', 'theta', 'epsilon'):
+        np.testing.assert_array_equal(brf[k], z['brf_' + k])
+    np.testing.assert_allclose(gs.DELAY, z['out_DELAY'], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(gs.DISP, z['out_DISP'], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_c1_full_size_cuda_matches_reference_source():
+    """C1 at full size on the CUDA path against the interpreted reference: <= 1e-10 rel L2 (FP64)"""
+    z, m, ex, ey = _load_c1()
+    pmx.reset_all(m['nsymb'], m['nt'], 1)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.POWER, G.LAMBDA = m['rate'], np.array([float(m['pavg'])]), synth.wdm_lambdas(1)
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    brf = pmx.fiber(m['fiber'], m['flag'], rng=np.random.Generator(np.random.PCG64(m['seed'])))
+    err = orc.rel_l2(G.FIELDX, G.FIELDY, z['out_FIELDX'], z['out_FIELDY'])
+    assert err < 1e-10, err
+    for k in ('db0', 'theta', 'epsilon'):
+        np.testing.assert_array_equal(brf[k], z['brf_' + k])
+    np.testing.assert_allclose(G.DELAY, z['out_DELAY'], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(G.DISP, z['out_DISP'], rtol=1e-13, atol=1e-13)
