@@ -16,12 +16,18 @@ larger than the 126 MB L2.
          every fiber()/ampliflat() call)
   roofline      dominant pass kernel: 64 algorithmic bytes per live Sa and step / its device time
                 (CUDA events around every launch of one extra, profiled link pass)
-  mc            bounded Monte-Carlo BER leg: link + equaliser + on-GPU error count + integer all-reduce
+  mc            Monte-Carlo BER leg (BASELINE config C5): --mc-realizations (default 1024) realizations of the C2 link
+                in TOTAL, sharded over the ranks (strong scaling): link + equaliser + on-GPU error count + integer
+                all-reduce; fields, plans and buffers are created before the clock starts
+  configs       one span of every other BASELINE configuration on a resident batch, CUDA events on the library's
+                stream: C1 (batch 1 and 64), C3 ('gp--' against the FP64 roofline, and 'gps-'), C4 -- each with its
+                own roofline fraction
   cpu_baseline  the numpy oracle (op-for-op restatement of fiber.m) on one host core, on a
-                bounded sample of the same workload
+                bounded sample of the same workload: span 1 of the link (80 km, 100 plates) at full N
 
 --impl reference times the CPU path (oracle port; no Octave/MATLAB exists in the image) with
-one worker process per host core, each on its own realization.
+one worker process per host core, each on its own realization; a step is span 1 of the link
+(config.cpu_sample says so).
 """
 import argparse
 import json
@@ -45,7 +51,13 @@ ALG_BYTES_PER_SA_STEP = 192.0   # 3 passes x (read + write) x 32 B   
 # (271.3+209.3) MB, B (268.8+218.4) MB, C (271.2+211.9) MB  ->  bytes per Sa; below the 64 algorithmic bytes because
 # part of the traffic is served by the L2
 NCU_DRAM_BYTES_PER_SA = {'passA': 480.6e6 / (8 << 20), 'passB': 487.2e6 / (8 << 20), 'passC': 483.1e6 / (8 << 20)}
-CPU_SAMPLE_KM = 16.0            # bounded CPU sample: first 16 km (20 plates of 800 m) of span 1
+CPU_SAMPLE_KM = SPAN_KM         # bounded CPU sample: span 1 of the link in full (80 km, 100 plates): 15-30 s per core
+# FP64 work of one whole trunk on one Sa (both polarizations of a bin) as pass B executes it: phasor progression 1 complex
+# product, phasor on one polarization 1 complex product (2 mul + 2 fma each), boundary matrix 4 mul + 8 fma
+# ->  20 FP64 instructions = 32 flops; used for the FP64 roofline of the one-step 'gp--' run of C3
+FLOPS_PER_SA_TRUNK = 32.0
+FP64_INSTR_PER_SA_TRUNK = 20.0
+FP64_FMA_PER_CLK_SM = 64.0      # measured: tools/ubench/fp64_rate.cu, 63.9 DFMA/clk/SM on this B200
 
 
 def fiber_params(length_m, nplates):
@@ -85,7 +97,7 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------------------
 def cpu_sample(seed):
-    """One bounded CPU sample: first CPU_SAMPLE_KM of span 1 at full N through the oracle.
+    """One bounded CPU sample: span 1 (CPU_SAMPLE_KM) at full N through the oracle.
     -> (Sa*steps, seconds)."""
     import oracle.fiber_oracle as orc
     from polmux_b200 import synth
@@ -112,11 +124,11 @@ def run_reference(args, rank, world, out=sys.stdout):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    sample = ('first %.0f km (%d plates) of span 1, N=2^20, one realization per worker, %d workers'
-              % (CPU_SAMPLE_KM, int(round(NPLATES * CPU_SAMPLE_KM / SPAN_KM)), cores))
+    sample = ('span 1 of %d (%.0f km, %d plates, no amplifier) at N=2^20, one realization per worker, %d workers'
+              % (NSPAN, CPU_SAMPLE_KM, int(round(NPLATES * CPU_SAMPLE_KM / SPAN_KM)), cores))
     ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
-        for w in range(args.warmup):
+        for w in range(min(args.warmup, 1)):     # numpy has nothing to warm up beyond the first call
             pool.map(_cpu_worker, [1000 + i for i in range(cores)])
         t0 = time.perf_counter()
         work = 0.0
@@ -129,7 +141,8 @@ def run_reference(args, rank, world, out=sys.stdout):
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': dt / max(args.steps, 1) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, world),
+            'config': dict(workload_config(args, world), cpu_sample=sample, cpu_sample_spans=1, cpu_sample_km=CPU_SAMPLE_KM,
+                           realizations_per_step=cores),
             'cpu_baseline': {'value': val, 'unit': 'GSa*steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'GSa*steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     out.write(json.dumps(line) + "\n")
@@ -145,6 +158,80 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------------------
+CONFIG_CASES = [  # key, description, nsymb, nt, nch, mW per channel, fiber overrides, flag, batch
+    ('C1_batch1', 'Run_my_PDM_QPSK: 2^16 Sa, 100 km, CNLSE, 10 plates, one realization',
+     1 << 12, 16, 1, 2.0, dict(length=1e5, dgd=1.0, nplates=10, manakov='no'), 'gps-', 1),
+    ('C1_batch64', 'Run_my_PDM_QPSK, 64 realizations resident',
+     1 << 12, 16, 1, 2.0, dict(length=1e5, dgd=1.0, nplates=10, manakov='no'), 'gps-', 64),
+    ('C3_gp', "ex24_pmd with the reference's flag 'gp--': one linear step of 200 trunks, DGD 0.5 symbol, 8 realizations",
+     1 << 16, 16, 1, 2.0, dict(length=8e4, dgd=0.5, nplates=200), 'gp--', 8),
+    ('C3_gps', "ex24_pmd fiber with 'gps-' (Manakov), 200 plates per span, 8 realizations",
+     1 << 16, 16, 1, 2.0, dict(length=8e4, dgd=0.5, nplates=200, manakov='yes'), 'gps-', 8),
+    ('C4', 'nine 28-GBaud channels in one field of 2^22 Sa, 80 km Manakov, 1 mW per channel, 2 realizations',
+     1 << 16, 64, 9, 1.0, dict(length=8e4, dgd=0.1, nplates=100, manakov='yes'), 'gps-', 2),
+]
+
+
+def config_legs(ctx, stream, torch, peak, peaks):
+    """One span of every BASELINE configuration besides the headline one, on a resident batch: best of 3 runs, CUDA
+    events on the library's stream.  'gp--' (one step, 200 trunks per Sa) is bound by the FP64 pipe, not by HBM: it is
+    reported against 2*64*148*f_max flop/s (64 DFMA per clock and SM measured, tools/ubench/fp64_rate.cu)."""
+    import polmux_b200 as pmx
+    from polmux_b200 import _lib, mc, synth
+    from polmux_b200.fiber import fiber_setup, setup_to_desc
+    out = {}
+    fmax = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
+    fp64_peak = 2.0 * FP64_FMA_PER_CLK_SM * 148 * fmax / 1e12
+    for key, what, nsymb, nt, nch, pw, over, flag, B in CONFIG_CASES:
+        N = nsymb * nt
+        ex, ey, _, _ = synth.pdm_qpsk(nsymb, nt, nch)
+        pmx.reset_all(nsymb, nt, nch)
+        G = pmx.GSTATE
+        G.SYMBOLRATE, G.LAMBDA, G.POWER = RATE, synth.wdm_lambdas(nch, 1550.0, 0.4), np.full(nch, pw)
+        pmx.create_field('unique', ex, ey, {'power': 'average'})
+        fib = dict(synth.SMF)
+        fib.update(over)
+        setup = fiber_setup(fib, flag, rng=np.random.Generator(np.random.PCG64(0)))
+        d = [mc.draw_plates(1000 + b, setup.nplates) for b in range(B)]
+        pl = [np.stack([x[i] for x in d]) for i in range(3)]
+        desc, keep = setup_to_desc(setup, batch=B, plate_sets=B, db0=pl[0], theta=pl[1], epsilon=pl[2])
+        plan = _lib.Plan(ctx, desc, keep)
+        tx = _lib.DeviceField(ctx, N, 1, 1)
+        tx.upload(G.FIELDX, G.FIELDY)
+        work = _lib.DeviceField(ctx, N, 1, B)
+        best, res = None, None
+        for rep in range(4):                         # the first run is the warm-up
+            work.broadcast_from(tx)
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            res = plan.execute(work)
+            e1.record(stream)
+            ctx.sync()
+            ms = e0.elapsed_time(e1)
+            if rep > 0:
+                best = ms if best is None else min(best, ms)
+        sa = float(res.ncycle.sum()) * N
+        v = sa / (best * 1e-3) / 1e9
+        item = {'what': what, 'nfft': N, 'batch': B, 'flag': flag, 'ncycle': int(res.ncycle[0]), 'ms_per_span': best,
+                'value': v, 'unit': 'GSa*steps/s',
+                'roofline': {'bound': 'hbm', 'achieved': ALG_BYTES_PER_SA_STEP * v, 'peak': peak, 'unit': 'GB/s',
+                             'frac': ALG_BYTES_PER_SA_STEP * v / peak}}
+        if flag == 'gp--':
+            trunks = float(setup.nplates) * B * N / (best * 1e-3)
+            tf = trunks * FLOPS_PER_SA_TRUNK / 1e12
+            item['gsa_trunks_per_s'] = trunks / 1e9
+            item['roofline'] = {'bound': 'fp64', 'achieved': tf, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf / fp64_peak,
+                                'flops_per_sa_trunk': FLOPS_PER_SA_TRUNK, 'fp64_instr_per_sa_trunk': FP64_INSTR_PER_SA_TRUNK,
+                                'fp64_issue_frac': trunks * FP64_INSTR_PER_SA_TRUNK / (FP64_FMA_PER_CLK_SM * 148 * fmax),
+                                'peak_source': '2 * 64 DFMA/clk/SM (measured) * 148 SMs * sm_max_mhz'}
+        out[key] = item
+        for f in (tx, work):
+            f.close()
+        plan.close()
+    return out
+
+
 def _claim_stdout():
     """Keep stdout for the one JSON line: libraries (NCCL's version banner, torchrun notices) that write to
     file descriptor 1 are redirected to stderr; returns a writer bound to the original stdout."""
@@ -166,7 +253,9 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-mc', action='store_true')
     ap.add_argument('--no-fp32', action='store_true', help='skip the separately reported FP32 leg')
-    ap.add_argument('--mc-groups', type=int, default=1, help='Monte-Carlo leg: groups of `batch` realizations per rank')
+    ap.add_argument('--mc-realizations', type=int, default=1024,
+                    help='Monte-Carlo leg (C5): realizations in TOTAL over all ranks (strong scaling)')
+    ap.add_argument('--no-configs', action='store_true', help='skip the per-configuration legs (C1, C3, C4)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -335,27 +424,30 @@ def main():
     mcres = None
     if not args.no_mc:
         sym = np.stack([symx[:, 0], symy[:, 0]]).astype(np.uint8)
-        nreal = B * world * args.mc_groups
-        # one untimed pass first: plans, tensor maps, twiddle tables and the allocator's pools are created once
-        mc.run_mc(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nreal, B,
-                  rank, world, ase_seed=7)
-        # three timed passes, the median reported: the pass is short (0.36 s) and an occasional host-side stall of a few
-        # hundred ms in its set-up (allocations, plan creation) was seen on the shared boxes
-        mc_times = []
-        for _ in range(3):
-            barrier()
-            t0 = time.perf_counter()
-            counts, _ = mc.run_mc(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nreal, B,
-                                  rank, world, ase_seed=7)
-            barrier()
-            tdt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
-            if world > 1:
-                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-            mc_times.append(float(tdt[0]))
-        tdt = torch.tensor([sorted(mc_times)[1]], dtype=torch.float64)
+        nreal = max(int(args.mc_realizations), world)
+        # fields, the link and equaliser plans, twiddle tables and count buffers are created here, outside the clock;
+        # one untimed pass over a single group per rank warms them up
+        warm = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, B * world, B,
+                           rank, world)
+        warm.run(ase_seed=7)
+        warm.close()
+        runner = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nreal, B,
+                             rank, world)
+        runner.work.broadcast_from(runner.tx)
+        runner.link.equalize(runner.work)            # builds the equaliser plan (the field is overwritten by run())
+        barrier()
+        t0 = time.perf_counter()
+        counts, _ = runner.run(ase_seed=7)
+        barrier()
+        tdt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        runner.close()
         rep = mc.ber_replay(counts, 4 * NSYMB, stop=(0.1, 68.0), nmin=100)
         mcres = {'realizations_per_s': nreal / float(tdt[0]), 'realizations': nreal, 'seconds': float(tdt[0]),
-                 'timing': 'median of 3 passes (max over ranks each): %s s' % ', '.join('%.3f' % v for v in mc_times),
+                 'scaling': 'strong', 'realizations_per_rank': (nreal + world - 1) // world,
+                 'timing': 'one pass over all realizations, host clock between barriers, max over ranks; allocations, '
+                           'plans and a warm-up group outside',
                  'errors_total': int(counts.sum()), 'bits_per_realization': 4 * NSYMB, 'avgber': rep['avgber'],
                  'count_reduce': 'all_reduce(int64[%d], sum) over %d rank(s), backend %s'
                                  % (nreal, world, 'nccl' if world > 1 else 'none (single rank)')}
@@ -428,12 +520,18 @@ def main():
                   'h2d_bytes_per_step': NSPAN * 2 * per_field, 'd2h_bytes_per_step': NSPAN * 2 * per_field,
                   'api': 'the same calls with gstate.RESIDENT = False (H2D + D2H inside every call)'}
 
+    # ---- the other BASELINE configurations, one span each on a resident batch (every rank runs them so that the ranks
+    # stay in step, the figures are rank 0's); last of the GPU legs: they re-initialise GSTATE with their own sizes)
+    cfgs = None
+    if not args.no_configs:
+        cfgs = config_legs(ctx, stream, torch, peak, peaks)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sa, dt = cpu_sample(1000)
         cpu = {'value': sa / dt / 1e9, 'unit': 'GSa*steps/s', 'cores': 1, 'kind': 'port',
-               'sample': 'first %.0f km (%d plates) of span 1, N=2^20, 1 realization, numpy oracle (%.1f s)'
-                         % (CPU_SAMPLE_KM, int(round(NPLATES * CPU_SAMPLE_KM / SPAN_KM)), dt)}
+               'sample': 'span 1 of %d (%.0f km, %d plates, no amplifier) at N=2^20, 1 realization, numpy oracle (%.1f s)'
+                         % (NSPAN, CPU_SAMPLE_KM, int(round(NPLATES * CPU_SAMPLE_KM / SPAN_KM)), dt)}
 
     if rank == 0:
         sampler.join(timeout=2)
@@ -442,7 +540,8 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic', 'config': workload_config(args, world), 'clocks': sampler.summary(),
                 'e2e': e2e, 'e2e_per_call': e2e_pc, 'gpu_launches': int(gpu_launches), 'roofline': roof, 'roofline_step': step_roof,
-                'cpu_baseline': cpu, 'mc': mcres, 'fp32': fp32, 'sa_steps_per_step': total_all / max(args.steps, 1)}
+                'cpu_baseline': cpu, 'mc': mcres, 'configs': cfgs, 'fp32': fp32,
+                'sa_steps_per_step': total_all / max(args.steps, 1)}
         out.write(json.dumps(line) + '\n')
         out.flush()
     if world > 1:

@@ -168,28 +168,54 @@ def allreduce_counts(local_counts, r0: int, nreal: int, device=None):
     return full
 
 
+class McRunner:
+    """Monte-Carlo BER of `nreal` realizations sharded over `world` ranks.  Everything that is allocated or planned
+    once (fields, the link and equaliser plans with their tables, the count buffers) is created here; run() is
+    the job itself: plate draws of every group, broadcast of the Tx field, link, equaliser, on-GPU error count,
+    integer all-reduce."""
+
+    def __init__(self, ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int,
+                 gain_db: float, nf_db: float, nreal: int, batch: int, rank: int = 0, world: int = 1):
+        import torch
+        self.ctx, self.setup, self.sym, self.nsymb, self.nt = ctx, setup, sym, nsymb, nt
+        self.nreal, self.batch, self.rank, self.world = nreal, batch, rank, world
+        self.r0, self.r1 = shard(nreal, rank, world)
+        self.dev = torch.device('cuda', ctx.device)
+        self.local = torch.zeros(max(self.r1 - self.r0, 0), dtype=torch.int64, device=self.dev)
+        self.buf = torch.zeros(batch, dtype=torch.int64, device=self.dev)
+        self.tx = _lib.DeviceField(ctx, setup.nfft, setup.nfc, 1)
+        self.tx.upload(tx_x, tx_y)
+        self.work = _lib.DeviceField(ctx, setup.nfft, setup.nfc, batch)
+        self.link = Link(ctx, setup, nspan, batch, gain_db, nf_db, self.r0)
+
+    def run(self, ase_seed: int = 1):
+        """-> (counts [nreal] int64 on the host, Sa*steps done by this rank)"""
+        import torch
+        sa_steps = 0
+        self.local.zero_()
+        for g0 in range(self.r0, self.r1, self.batch):
+            torch.cuda.synchronize(self.dev)                         # torch's stream and the library's are independent
+            nb = min(self.batch, self.r1 - g0)
+            self.link.retarget(g0)
+            self.work.broadcast_from(self.tx)
+            sa_steps += self.link.run(self.work, ase_seed)
+            self.link.equalize(self.work)
+            _lib.qpsk_count(self.ctx, self.work, self.sym, self.nsymb, self.nt, self.buf.data_ptr())   # writes the send buffer
+            self.ctx.sync()
+            self.local[g0 - self.r0:g0 - self.r0 + nb] = self.buf[:nb]
+        counts = allreduce_counts(self.local, self.r0, self.nreal)
+        return counts.cpu().numpy(), sa_steps
+
+    def close(self):
+        for f in (self.work, self.tx):
+            f.close()
+
+
 def run_mc(ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int, gain_db: float,
            nf_db: float, nreal: int, batch: int, rank: int = 0, world: int = 1, ase_seed: int = 1):
-    """Monte-Carlo BER of `nreal` realizations sharded over `world` ranks.
-    -> (counts [nreal] int64 on the host, Sa*steps done by this rank)"""
-    import torch
-    r0, r1 = shard(nreal, rank, world)
-    dev = torch.device('cuda', ctx.device)
-    local = torch.zeros(max(r1 - r0, 0), dtype=torch.int64, device=dev)
-    tx = _lib.DeviceField(ctx, setup.nfft, setup.nfc, 1)
-    tx.upload(tx_x, tx_y)
-    work = _lib.DeviceField(ctx, setup.nfft, setup.nfc, batch)
-    link = Link(ctx, setup, nspan, batch, gain_db, nf_db, r0)
-    sa_steps = 0
-    buf = torch.zeros(batch, dtype=torch.int64, device=dev)
-    for g0 in range(r0, r1, batch):
-        torch.cuda.synchronize(dev)                                  # torch's stream and the library's are independent
-        nb = min(batch, r1 - g0)
-        link.retarget(g0)
-        work.broadcast_from(tx)
-        sa_steps += link.run(work, ase_seed)
-        link.equalize(work)
-        _lib.qpsk_count(ctx, work, sym, nsymb, nt, buf.data_ptr())   # the kernel writes the send buffer
-        local[g0 - r0:g0 - r0 + nb] = buf[:nb]
-    counts = allreduce_counts(local, r0, nreal)
-    return counts.cpu().numpy(), sa_steps
+    """One-shot form of McRunner.  -> (counts [nreal] int64 on the host, Sa*steps done by this rank)"""
+    r = McRunner(ctx, setup, tx_x, tx_y, sym, nsymb, nt, nspan, gain_db, nf_db, nreal, batch, rank, world)
+    try:
+        return r.run(ase_seed)
+    finally:
+        r.close()
