@@ -275,6 +275,13 @@ int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t ns
  *   pmx_field_lincomb  : dst <- ca*a - cb*b (X and Y), products rounded separately as the interpreter does (:1003) */
 int pmx_scalar_nl_exec(pmx_ctx* ctx, pmx_devfield* f, const double* gam, double leff, double atten, int32_t spm,
                        int32_t xpm);
+/* The whole adaptive dispatch on host buffers, for callers that are not the Python mirror (the MEX gateway):
+ *   first_only = 0: scalar_a_ssfm (fiber.m:639-679) -- every step from the local error (x.ltol);
+ *   first_only = 1: scalar_ssfm with x.dphiadapt (fiber.m:588-611) -- first step from the local error, dphimax
+ *                   recalibrated from it (:607), the rest of the fiber by the device loop.
+ * desc: scalar_field = 1, batch 1, FP64; io: X planes only (Y absent); out: firstdz[1], ncycle[1]. */
+int pmx_scalar_adaptive_run(pmx_ctx* ctx, const pmx_fiber_desc* desc, double ltol, double safety, int32_t first_only,
+                            pmx_field* io, pmx_fiber_result* out);
 int pmx_plan_set_length(pmx_plan* plan, double length);
 int pmx_field_max_power(pmx_ctx* ctx, pmx_devfield* f, double* umax);
 int pmx_field_maxdiff2(pmx_ctx* ctx, pmx_devfield* a, pmx_devfield* b, double* out);

@@ -21,6 +21,7 @@ typedef struct mxArray_tag {
     size_t m, n;
     double *pr; /* real plane, column-major */
     double *pi; /* imaginary plane or NULL */
+    char *str;  /* char row vector (1 x n) or NULL for a numeric array */
 } mxArray;
 
 mxArray *mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity flag);
@@ -31,6 +32,9 @@ size_t mxGetNumberOfElements(const mxArray *a);
 double *mxGetPr(const mxArray *a);
 double *mxGetPi(const mxArray *a);
 double mxGetScalar(const mxArray *a);
+int mxIsChar(const mxArray *a);
+int mxGetString(const mxArray *a, char *buf, mwSize buflen); /* 0 = ok, 1 = truncated / not a string */
+mxArray *mxCreateString(const char *s);
 void mexErrMsgTxt(const char *msg); /* longjmps back to the driver */
 int mexAtExit(void (*fn)(void));
 

@@ -24,6 +24,7 @@ void mxDestroyArray(mxArray *a)
     if (!a) return;
     free(a->pr);
     free(a->pi);
+    free(a->str);
     free(a);
 }
 size_t mxGetM(const mxArray *a) { return a->m; }
@@ -32,6 +33,23 @@ size_t mxGetNumberOfElements(const mxArray *a) { return a->m * a->n; }
 double *mxGetPr(const mxArray *a) { return a->pr; }
 double *mxGetPi(const mxArray *a) { return a->pi; }
 double mxGetScalar(const mxArray *a) { return (a->m * a->n != 0) ? a->pr[0] : 0.0; }
+int mxIsChar(const mxArray *a) { return a && a->str != NULL; }
+int mxGetString(const mxArray *a, char *buf, mwSize buflen)
+{
+    if (!a || !a->str || buflen == 0) return 1;
+    strncpy(buf, a->str, buflen - 1);
+    buf[buflen - 1] = 0;
+    return strlen(a->str) >= buflen;
+}
+mxArray *mxCreateString(const char *s)
+{
+    mxArray *a = (mxArray *)calloc(1, sizeof *a);
+    a->m = 1;
+    a->n = strlen(s);
+    a->str = (char *)malloc(a->n + 1);
+    memcpy(a->str, s, a->n + 1);
+    return a;
+}
 void mexErrMsgTxt(const char *msg)
 {
     strncpy(g_err, msg, sizeof g_err - 1);

@@ -31,6 +31,25 @@
  *              device noise generator (span k uses seed+k-1); [] or absent: fibers only
  *   firstdz    first step of span 1;  ncycle  1 x Nspan
  *
+ * Command interface (what matlab/fiber.m and matlab/ampliflat.m call; the first argument is a string):
+ *
+ *   [ux,uy,firstdz,ncycle] = ssfm_mex('fiber', ux, uy, betat, db1, P, gam, fls, plates, scal, opt)
+ *       P      [dzmaxt dphimaxt alphalin Lf nplates manakov]        (matrix_ssfm's scalars, fiber.m:459-460)
+ *       plates nplates x 3  [db0 theta epsilon]                      (brf.*, fiber.m:266-276); [] without the 'p' flag
+ *       scal   [] or [symbolrate nsymb nt b30 dgdrms beta1(1:nfc) beta2(1:nfc)] (betat / db1 may then be [])
+ *       opt    [scalar_field precision resident tolflag ltol safety], trailing entries optional:
+ *              scalar_field 1 = the scalar_ssfm / scalar_a_ssfm dispatches (fiber.m:372-380,386-387; uy = [] in and out)
+ *              precision    0 = FP64, 1 = FP32 arithmetic on the device (host arrays stay double)
+ *              resident     1 = keep the propagated field in HBM as well: the next in-line device call that is handed
+ *                           the very arrays this call returned (same data pointers, same fingerprint) skips its upload
+ *              tolflag      0 | 1 (x.dphiadapt: first step by the local error) | 2 (x.ltol: every step), with ltol and
+ *                           the safety factor of fiber.m:130
+ *   [ux,uy] = ssfm_mex('ampliflat', ux, uy, gain, sigma, noise, asepol, opt)
+ *       gain   linear power gain; sigma 1 x nfc; noise = Nfft x 2*nfc complex (options.noise, ampliflat.m:123-129) or a
+ *              scalar seed of the device generator; asepol 1 = X, 2 = Y, 3 = both (options.onepol); opt as above
+ *   ssfm_mex('reset')                    drops the resident field
+ *   c = ssfm_mex('stats')                [uploads downloads resident_hits] since the MEX file was loaded
+ *
  * Build (not verifiable in the image this was written in -- it has no mex.h):
  *   mex ssfm_mex.c -I../include -L../polmux_b200/lib -lpolmux_ssfm
  *   mkoctfile --mex ssfm_mex.c -I../include -L../polmux_b200/lib -lpolmux_ssfm
@@ -43,8 +62,11 @@
 
 static pmx_ctx *g_ctx = NULL; /* one device context for the life of the MEX file */
 
+static void drop_resident(void);
+
 static void ssfm_at_exit(void)
 {
+    drop_resident();
     if (g_ctx) {
         pmx_ctx_destroy(g_ctx);
         g_ctx = NULL;
@@ -64,6 +86,8 @@ static void fail(const char *what)
     mexErrMsgTxt(msg);
 }
 
+static void command(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);
+
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 {
     pmx_fiber_desc d;
@@ -78,6 +102,10 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     mxArray *uy_out, *work;
     int rc, is_link;
 
+    if (nrhs >= 1 && mxIsChar(prhs[0])) {
+        command(nlhs, plhs, nrhs, prhs);
+        return;
+    }
     if (nrhs < 16 || nrhs > 18)
         mexErrMsgTxt("ssfm_mex: 16 to 18 input arguments expected (see the header of ssfm_mex.c).");
     if (nlhs > 4)
@@ -228,4 +256,350 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
             mxGetPr(plhs[3])[k] = (double)ncycle[k];
     }
     mxDestroyArray(work);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Command interface.  The propagated field may stay in HBM between calls (opt(3) = resident): the
+ * interpreter always gets its arrays back (any M code may read GSTATE.FIELDX), but the next in-line
+ * device that is handed exactly those arrays -- same data pointers, same fingerprint -- does not
+ * upload them again. */
+static struct {
+    pmx_devfield *f;
+    size_t nfft, nfc;
+    int precision, has_y;
+    const double *p[4];   /* data pointers of the arrays handed back by the last call */
+    double fp[4];         /* fingerprints of their contents */
+} g_res;
+static double g_stats[3]; /* uploads, downloads, resident hits */
+
+static void ensure_ctx(void)
+{
+    if (!g_ctx) {
+        if (pmx_ctx_create(&g_ctx, 0) != PMX_OK)
+            fail("ssfm_mex: no usable B200 (there is no CPU fallback)");
+        mexAtExit(ssfm_at_exit);
+    }
+}
+
+static void drop_resident(void)
+{
+    if (g_res.f)
+        pmx_field_destroy(g_res.f);
+    memset(&g_res, 0, sizeof g_res);
+}
+
+/* a few hundred samples spread over the plane, combined so that an in-place edit is unlikely to go unnoticed */
+static double fingerprint(const double *v, size_t n)
+{
+    double acc = 0.0;
+    size_t k, step;
+    if (!v || n == 0)
+        return 0.0;
+    step = n / 509 + 1;
+    for (k = 0; k < n; k += step)
+        acc = acc * 1.0000001192092896 + v[k];
+    return acc + 3.0 * v[0] + 5.0 * v[n - 1] + 7.0 * v[n / 2];
+}
+
+static double opt_at(const mxArray *o, size_t k, double dflt)
+{
+    return (o && mxGetNumberOfElements(o) > k) ? mxGetPr(o)[k] : dflt;
+}
+
+/* the field of this call on the device: the resident one when the caller hands back what it was given, else an upload */
+static pmx_devfield *acquire(const mxArray *ux, const mxArray *uy, int precision)
+{
+    const size_t nfft = mxGetM(ux), nfc = mxGetN(ux), n = nfft * nfc;
+    const int has_y = uy && mxGetNumberOfElements(uy) == n;
+    const double *p[4];
+    pmx_field h;
+    pmx_devfield *f;
+    p[0] = mxGetPr(ux);
+    p[1] = mxGetPi(ux);
+    p[2] = has_y ? mxGetPr(uy) : NULL;
+    p[3] = has_y ? mxGetPi(uy) : NULL;
+    if (g_res.f && g_res.nfft == nfft && g_res.nfc == nfc && g_res.precision == precision && g_res.has_y == has_y &&
+        p[0] == g_res.p[0] && p[1] == g_res.p[1] && p[2] == g_res.p[2] && p[3] == g_res.p[3] &&
+        fingerprint(p[0], n) == g_res.fp[0] && fingerprint(p[1], n) == g_res.fp[1] &&
+        fingerprint(p[2], n) == g_res.fp[2] && fingerprint(p[3], n) == g_res.fp[3]) {
+        f = g_res.f;
+        g_res.f = NULL;
+        g_stats[2] += 1.0;
+        return f;
+    }
+    drop_resident();
+    if (pmx_field_create(g_ctx, (int64_t)nfft, (int32_t)nfc, 1, precision, &f) != PMX_OK)
+        fail("ssfm_mex: device allocation failed");
+    h.layout = PMX_PLANAR;
+    h.reserved = 0;
+    h.xr = (double *)p[0];
+    h.xi = (double *)p[1];
+    h.yr = (double *)p[2];
+    h.yi = (double *)p[3];
+    if (pmx_field_upload(f, &h, 0, 1) != PMX_OK) {
+        pmx_field_destroy(f);
+        fail("ssfm_mex: upload failed");
+    }
+    g_stats[0] += 1.0;
+    return f;
+}
+
+/* hand the field back to the interpreter (always) and keep the device copy when asked to */
+static void release(pmx_devfield *f, size_t nfft, size_t nfc, int precision, int with_y, int resident, int nlhs,
+                    mxArray *plhs[])
+{
+    const size_t n = nfft * nfc;
+    mxArray *ox = mxCreateDoubleMatrix(nfft, nfc, mxCOMPLEX);
+    mxArray *oy = mxCreateDoubleMatrix(nfft, nfc, mxCOMPLEX);
+    pmx_field h;
+    h.layout = PMX_PLANAR;
+    h.reserved = 0;
+    h.xr = mxGetPr(ox);
+    h.xi = mxGetPi(ox);
+    h.yr = mxGetPr(oy);
+    h.yi = mxGetPi(oy);
+    if (pmx_field_download(f, &h, 0, 1) != PMX_OK) {
+        pmx_field_destroy(f);
+        fail("ssfm_mex: download failed");
+    }
+    g_stats[1] += 1.0;
+    plhs[0] = ox;
+    if (with_y && nlhs > 1) {
+        plhs[1] = oy;
+    } else {
+        mxDestroyArray(oy);
+        oy = NULL;
+        if (nlhs > 1)
+            plhs[1] = mxCreateDoubleMatrix(0, 0, mxREAL);
+    }
+    if (resident && (oy || !with_y)) {
+        g_res.f = f;
+        g_res.nfft = nfft;
+        g_res.nfc = nfc;
+        g_res.precision = precision;
+        g_res.has_y = oy != NULL;
+        g_res.p[0] = mxGetPr(ox);
+        g_res.p[1] = mxGetPi(ox);
+        g_res.p[2] = oy ? mxGetPr(oy) : NULL;
+        g_res.p[3] = oy ? mxGetPi(oy) : NULL;
+        g_res.fp[0] = fingerprint(g_res.p[0], n);
+        g_res.fp[1] = fingerprint(g_res.p[1], n);
+        g_res.fp[2] = fingerprint(g_res.p[2], n);
+        g_res.fp[3] = fingerprint(g_res.p[3], n);
+    } else {
+        pmx_field_destroy(f);
+    }
+}
+
+static void cmd_fiber(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+{
+    /* prhs: 'fiber', ux, uy, betat, db1, P, gam, fls, plates, scal, opt */
+    pmx_fiber_desc d;
+    pmx_fiber_result res;
+    pmx_plan *plan = NULL;
+    pmx_devfield *f;
+    double gam_buf[16], beta_buf[32], firstdz = 0.0;
+    const double *P, *pl;
+    int32_t ncycle = 0, ntot = 0, status = 0;
+    size_t nfft, nfc, n, k, np;
+    int scalar_field, precision, resident, tolflag, rc, has_y;
+    const mxArray *opt = nrhs > 10 ? prhs[10] : NULL;
+
+    if (nrhs < 10 || nrhs > 11)
+        mexErrMsgTxt("ssfm_mex('fiber',ux,uy,betat,db1,P,gam,fls,plates,scal[,opt]): wrong number of arguments.");
+    if (nlhs > 4)
+        mexErrMsgTxt("ssfm_mex: at most 4 outputs [ux,uy,firstdz,ncycle].");
+    nfft = mxGetM(prhs[1]);
+    nfc = mxGetN(prhs[1]);
+    n = nfft * nfc;
+    if (n == 0)
+        mexErrMsgTxt("ssfm_mex: empty x field.");
+    if (nfc > 16)
+        mexErrMsgTxt("ssfm_mex: at most 16 field columns.");
+    has_y = mxGetNumberOfElements(prhs[2]) != 0;
+    if (has_y && (mxGetM(prhs[2]) != nfft || mxGetN(prhs[2]) != nfc))
+        mexErrMsgTxt("ssfm_mex: ux and uy must have the same size.");
+    if (mxGetNumberOfElements(prhs[5]) != 6)
+        mexErrMsgTxt("ssfm_mex: P must be [dzmaxt dphimaxt alphalin Lf nplates manakov].");
+    if (mxGetNumberOfElements(prhs[7]) != 4)
+        mexErrMsgTxt("ssfm_mex: fls must have 4 elements.");
+    scalar_field = opt_at(opt, 0, 0.0) != 0.0;
+    precision = opt_at(opt, 1, 0.0) != 0.0 ? PMX_F32 : PMX_F64;
+    resident = opt_at(opt, 2, 0.0) != 0.0;
+    tolflag = (int)opt_at(opt, 3, 0.0);
+    if (scalar_field && has_y)
+        mexErrMsgTxt("ssfm_mex: the scalar path takes no y field (fiber.m:253).");
+
+    P = mxGetPr(prhs[5]);
+    memset(&d, 0, sizeof d);
+    d.nfft = (int64_t)nfft;
+    d.nfc = (int32_t)nfc;
+    d.batch = 1;
+    d.precision = precision;
+    d.dzmaxt = P[0];
+    d.dphimaxt = P[1];
+    d.alphalin = P[2];
+    d.length = P[3];
+    d.nplates = (int32_t)P[4];
+    d.manakov = P[5] != 0.0;
+    d.scalar_field = scalar_field;
+    for (k = 0; k < 4; k++)
+        d.fls[k] = mxGetPr(prhs[7])[k] != 0.0;
+    for (k = 0; k < nfc; k++)
+        gam_buf[k] = mxGetPr(prhs[6])[mxGetNumberOfElements(prhs[6]) == 1 ? 0 : k];
+    d.gam = gam_buf;
+    d.plate_sets = 1;
+    np = (size_t)d.nplates;
+    if (mxGetNumberOfElements(prhs[8]) != 0) {
+        if (mxGetM(prhs[8]) != np || mxGetN(prhs[8]) != 3)
+            mexErrMsgTxt("ssfm_mex: plates must be nplates x 3 [db0 theta epsilon].");
+        pl = mxGetPr(prhs[8]);
+        d.db0 = pl;
+        d.theta = pl + np;
+        d.epsilon = pl + 2 * np;
+    } else if (d.fls[1]) {
+        mexErrMsgTxt("ssfm_mex: the 'p' flag needs the waveplates.");
+    }
+    if (mxGetNumberOfElements(prhs[9]) != 0) {
+        const double *s = mxGetPr(prhs[9]);
+        if (mxGetNumberOfElements(prhs[9]) != 5 + 2 * nfc)
+            mexErrMsgTxt("ssfm_mex: scal must be [symbolrate nsymb nt b30 dgdrms beta1(1:nfc) beta2(1:nfc)].");
+        d.disp_mode = PMX_DISP_SCALAR;
+        d.symbolrate = s[0];
+        d.nsymb = (int32_t)s[1];
+        d.nt = (int32_t)s[2];
+        d.b30 = s[3];
+        d.dgdrms = s[4];
+        for (k = 0; k < 2 * nfc; k++)
+            beta_buf[k] = s[5 + k];
+        d.beta1 = beta_buf;
+        d.beta2 = beta_buf + nfc;
+    } else {
+        if (mxGetM(prhs[3]) != nfft || mxGetN(prhs[3]) != nfc)
+            mexErrMsgTxt("ssfm_mex: betat must be Nfft x nfc.");
+        d.disp_mode = PMX_DISP_VECTOR;
+        d.betat = mxGetPr(prhs[3]);
+        d.db1 = (mxGetNumberOfElements(prhs[4]) == n) ? mxGetPr(prhs[4]) : NULL;
+    }
+    ensure_ctx();
+    memset(&res, 0, sizeof res);
+    res.firstdz = &firstdz;
+    res.ncycle = &ncycle;
+    res.ntot = &ntot;
+    res.status = &status;
+
+    if (tolflag) { /* scalar_a_ssfm (2) / scalar_ssfm with x.dphiadapt (1): host buffers in, host buffers out */
+        pmx_field io;
+        if (!scalar_field)
+            mexErrMsgTxt("adaptive step available in absence of polarization effects"); /* fiber.m:373 */
+        drop_resident();
+        plhs[0] = mxCreateDoubleMatrix(nfft, nfc, mxCOMPLEX);
+        memcpy(mxGetPr(plhs[0]), mxGetPr(prhs[1]), n * sizeof(double));
+        if (mxGetPi(prhs[1]))
+            memcpy(mxGetPi(plhs[0]), mxGetPi(prhs[1]), n * sizeof(double));
+        io.layout = PMX_PLANAR;
+        io.reserved = 0;
+        io.xr = mxGetPr(plhs[0]);
+        io.xi = mxGetPi(plhs[0]);
+        io.yr = io.yi = NULL;
+        rc = pmx_scalar_adaptive_run(g_ctx, &d, opt_at(opt, 4, 0.0), opt_at(opt, 5, 0.9), tolflag == 1, &io, &res);
+        if (rc != PMX_OK)
+            fail("ssfm_mex: adaptive propagation failed");
+        if (nlhs > 1)
+            plhs[1] = mxCreateDoubleMatrix(0, 0, mxREAL);
+    } else {
+        if (pmx_plan_create(g_ctx, &d, &plan) != PMX_OK) {
+            if (d.fls[3] && !scalar_field)
+                mexErrMsgTxt("The CNLSE with separate fields is not yet implemented"); /* fiber.m:854 */
+            fail("ssfm_mex: plan creation failed");
+        }
+        f = acquire(prhs[1], prhs[2], precision);
+        rc = pmx_fiber_exec(plan, f, &res);
+        pmx_plan_destroy(plan);
+        if (rc != PMX_OK) {
+            pmx_field_destroy(f);
+            if (rc == PMX_ERR_PLATE_INDEX)
+                fail("ssfm_mex: index out of bound; value out of bound nplates (fiber.m:910)");
+            fail("ssfm_mex: propagation failed");
+        }
+        release(f, nfft, nfc, precision, !scalar_field, resident, nlhs, plhs);
+    }
+    if (nlhs > 2) {
+        plhs[2] = mxCreateDoubleMatrix(1, 1, mxREAL);
+        *mxGetPr(plhs[2]) = firstdz;
+    }
+    if (nlhs > 3) {
+        plhs[3] = mxCreateDoubleMatrix(1, 1, mxREAL);
+        *mxGetPr(plhs[3]) = (double)ncycle;
+    }
+}
+
+static void cmd_ampliflat(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+{
+    /* prhs: 'ampliflat', ux, uy, gain, sigma, noise, asepol, opt */
+    double sigma_buf[16], *nz = NULL;
+    const mxArray *opt = nrhs > 7 ? prhs[7] : NULL;
+    pmx_devfield *f;
+    size_t nfft, nfc, n, k, c;
+    uint64_t seed = 0;
+    int precision, resident, asepol, rc;
+    mxArray *work = NULL;
+
+    if (nrhs < 7 || nrhs > 8 || nlhs != 2)
+        mexErrMsgTxt("[ux,uy] = ssfm_mex('ampliflat',ux,uy,gain,sigma,noise,asepol[,opt]): wrong number of arguments.");
+    nfft = mxGetM(prhs[1]);
+    nfc = mxGetN(prhs[1]);
+    n = nfft * nfc;
+    if (n == 0 || nfc > 16)
+        mexErrMsgTxt("ssfm_mex: bad x field.");
+    if (mxGetNumberOfElements(prhs[4]) != nfc)
+        mexErrMsgTxt("ssfm_mex: sigma must have one entry per field column.");
+    for (k = 0; k < nfc; k++)
+        sigma_buf[k] = mxGetPr(prhs[4])[k];
+    asepol = (int)mxGetScalar(prhs[6]);
+    precision = opt_at(opt, 1, 0.0) != 0.0 ? PMX_F32 : PMX_F64;
+    resident = opt_at(opt, 2, 0.0) != 0.0;
+    if (mxGetNumberOfElements(prhs[5]) == 2 * n) { /* options.noise: Nfft x 2*nfc complex -> [2*nfc][nfft] interleaved */
+        const double *re = mxGetPr(prhs[5]), *im = mxGetPi(prhs[5]);
+        work = mxCreateDoubleMatrix(4 * n, 1, mxREAL);
+        nz = mxGetPr(work);
+        for (c = 0; c < 2 * nfc; c++)
+            for (k = 0; k < nfft; k++) {
+                nz[2 * (c * nfft + k)] = re[c * nfft + k];
+                nz[2 * (c * nfft + k) + 1] = im ? im[c * nfft + k] : 0.0;
+            }
+    } else if (mxGetNumberOfElements(prhs[5]) == 1) {
+        seed = (uint64_t)mxGetScalar(prhs[5]);
+    } else if (mxGetNumberOfElements(prhs[5]) != 0) {
+        mexErrMsgTxt("ssfm_mex: noise must be Nfft x 2*nfc (options.noise) or a scalar seed.");
+    }
+    ensure_ctx();
+    f = acquire(prhs[1], prhs[2], precision);
+    rc = pmx_ampliflat_exec_pol(g_ctx, f, mxGetScalar(prhs[3]), sigma_buf, nz, seed, asepol);
+    if (work)
+        mxDestroyArray(work);
+    if (rc != PMX_OK) {
+        pmx_field_destroy(f);
+        fail("ssfm_mex: ampliflat failed");
+    }
+    release(f, nfft, nfc, precision, 1, resident, nlhs, plhs);
+}
+
+static void command(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+{
+    char cmd[32];
+    if (mxGetString(prhs[0], cmd, sizeof cmd))
+        mexErrMsgTxt("ssfm_mex: unknown command.");
+    if (!strcmp(cmd, "fiber")) {
+        cmd_fiber(nlhs, plhs, nrhs, prhs);
+    } else if (!strcmp(cmd, "ampliflat")) {
+        cmd_ampliflat(nlhs, plhs, nrhs, prhs);
+    } else if (!strcmp(cmd, "reset")) {
+        drop_resident();
+    } else if (!strcmp(cmd, "stats")) {
+        plhs[0] = mxCreateDoubleMatrix(1, 3, mxREAL);
+        memcpy(mxGetPr(plhs[0]), g_stats, sizeof g_stats);
+    } else {
+        mexErrMsgTxt("ssfm_mex: unknown command (fiber, ampliflat, reset, stats).");
+    }
 }

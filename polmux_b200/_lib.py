@@ -30,7 +30,7 @@ EXPORTS = [
     'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
-    'pmx_host_is_pinned',
+    'pmx_host_is_pinned', 'pmx_scalar_adaptive_run',
 ]
 
 
@@ -114,6 +114,8 @@ def load():
     lib.pmx_plan_set_plates.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     lib.pmx_fiber_exec.argtypes = [vp, vp, C.POINTER(FiberResult)]
     lib.pmx_host_is_pinned.argtypes = [vp]
+    lib.pmx_scalar_adaptive_run.argtypes = [vp, C.POINTER(FiberDesc), C.c_double, C.c_double, C.c_int32, C.POINTER(Field),
+                                            C.POINTER(FiberResult)]
     lib.pmx_ampliflat_exec.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64]
     lib.pmx_ampliflat_exec_pol.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64, C.c_int32]
     lib.pmx_count_errors.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]

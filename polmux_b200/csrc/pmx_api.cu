@@ -1705,3 +1705,205 @@ extern "C" int pmx_field_lincomb(pmx_ctx* c, pmx_devfield* dst, double ca, pmx_d
     CK(c, cudaGetLastError());
     return PMX_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Local-error adaptive step on the scalar path: scalar_a_ssfm / adaptssfm (fiber.m:639-679, 938-1010) and the
+// x.dphiadapt variant of scalar_ssfm (fiber.m:588-611).  The accept/reject logic is host code as in the reference;
+// nl_step + attenuation, lin_step, the error norm and the Richardson combination run on the resident field.
+namespace {
+double nextstep_host(double dzmax, double phimax, const double* gam, int nfc, double alphalin, const double* umax) {
+    double pmax = 0.0;
+    for (int k = 0; k < nfc; ++k) {                        // nextstep, fiber.m:693-715
+        const double gp = gam[k] * umax[k];
+        pmax = (k == 0) ? gp : std::max(pmax, gp);
+    }
+    const double leff = phimax / pmax, dl = alphalin * leff;
+    if (dl >= 1.0) return dzmax;
+    const double step = (alphalin == 0.0) ? leff : (-1.0 / alphalin) * log(1.0 - dl);
+    return step > dzmax ? dzmax : step;
+}
+
+struct LocalErrorStepper {
+    pmx_ctx* c;
+    const pmx_fiber_desc* d;
+    pmx_devfield *u = nullptr, *uh = nullptr, *ust = nullptr;
+    pmx_plan* lin = nullptr;
+    double err_tol, safety;
+    int nrej = 0;
+    ~LocalErrorStepper() {
+        pmx_plan_destroy(lin);
+        pmx_field_destroy(uh);
+        pmx_field_destroy(ust);
+        pmx_field_destroy(u);
+    }
+    int init(pmx_ctx* ctx, const pmx_fiber_desc* desc, const pmx_field* io, double tol, double sf) {
+        c = ctx;
+        d = desc;
+        err_tol = tol;
+        safety = sf;
+        int rc = pmx_field_create(c, d->nfft, d->nfc, 1, PMX_F64, &u);
+        if (rc == PMX_OK) rc = pmx_field_create(c, d->nfft, d->nfc, 1, PMX_F64, &uh);
+        if (rc == PMX_OK) rc = pmx_field_create(c, d->nfft, d->nfc, 1, PMX_F64, &ust);
+        if (rc != PMX_OK) return rc;
+        pmx_field h = *io;
+        h.yr = h.yi = nullptr;                             // the scalar path has no Y polarization
+        rc = pmx_field_upload(u, &h, 0, 1);
+        if (rc != PMX_OK) return rc;
+        // lin_step(betat*dz, u) = ifft(fft(u).*fastexp(-betat*dz)): a one-step plan of the same dispersion, no loss
+        pmx_fiber_desc l = *d;
+        l.batch = 1;
+        l.precision = PMX_F64;
+        l.fls[1] = l.fls[2] = l.fls[3] = 0;
+        l.dphimaxt = INFINITY;
+        l.dzmaxt = l.length;
+        l.alphalin = 0.0;
+        l.manakov = 0;
+        l.nplates = 1;
+        l.plate_sets = 1;
+        l.db0 = l.theta = l.epsilon = nullptr;
+        l.db1 = nullptr;
+        l.dgdrms = 0.0;
+        l.scalar_field = 1;
+        l.z_start = l.dz_first = 0.0;
+        return pmx_plan_create(c, &l, &lin);
+    }
+    int nl(pmx_devfield* f, double dz) {                   // nl_step + u*exp(-halfalpha*dz)
+        const double a = d->alphalin;
+        const double leff = (a == 0.0) ? dz : (1.0 - exp(-a * dz)) / a;
+        return pmx_scalar_nl_exec(c, f, d->gam, leff, exp(-0.5 * a * dz), d->fls[2], d->fls[3]);
+    }
+    int lstep(pmx_devfield* f, double dz) {
+        int rc = pmx_plan_set_length(lin, dz);
+        return rc != PMX_OK ? rc : pmx_fiber_exec(lin, f, nullptr);
+    }
+    int first_step(double* dz, double* umax) {
+        int rc = pmx_field_max_power(c, u, umax);
+        if (rc == PMX_OK) *dz = nextstep_host(d->dzmaxt, d->dphimaxt, d->gam, d->nfc, d->alphalin, umax);
+        return rc;
+    }
+    // adaptssfm (:966-1009): one step of length dz against two half steps.  The field advances only when accepted.
+    int try_step(double dz, bool* accepted, double* prop) {
+        const double dz2 = 0.5 * dz, dz4 = 0.25 * dz;
+        int rc = pmx_field_broadcast(ust, u);
+        if (rc == PMX_OK) rc = pmx_field_broadcast(uh, u);
+        if (rc == PMX_OK) rc = nl(u, dz2);
+        if (rc == PMX_OK) rc = lstep(u, dz);
+        if (rc == PMX_OK) rc = nl(u, dz2);
+        if (rc == PMX_OK) rc = nl(uh, dz4);
+        if (rc == PMX_OK) rc = lstep(uh, dz2);
+        if (rc == PMX_OK) rc = nl(uh, dz2);
+        if (rc == PMX_OK) rc = lstep(uh, dz2);
+        if (rc == PMX_OK) rc = nl(uh, dz4);
+        double md2 = 0.0;
+        if (rc == PMX_OK) rc = pmx_field_maxdiff2(c, u, uh, &md2);
+        if (rc != PMX_OK) return rc;
+        const double est_err = sqrt(md2) / dz;
+        *prop = safety * sqrt(err_tol / est_err) * dz;
+        if (est_err > err_tol) {                           // reject the step
+            ++nrej;
+            *accepted = false;
+            return pmx_field_broadcast(u, ust);
+        }
+        *accepted = true;
+        return pmx_field_lincomb(c, u, 4.0 / 3.0, uh, 1.0 / 3.0, u);   // Richardson extrapolation
+    }
+};
+}  // namespace
+
+extern "C" int pmx_scalar_adaptive_run(pmx_ctx* c, const pmx_fiber_desc* d, double ltol, double safety, int32_t first_only,
+                                       pmx_field* io, pmx_fiber_result* out) {
+    if (!c || !d || !io) return set_err(c, PMX_ERR_INVALID, "pmx_scalar_adaptive_run: null argument");
+    if (!d->scalar_field || d->fls[1])
+        return set_err(c, PMX_ERR_INVALID, "adaptive step available in absence of polarization effects");   // fiber.m:372-374
+    if (d->batch != 1) return set_err(c, PMX_ERR_UNSUPPORTED, "the local-error adaptive step takes one realization per call");
+    if (d->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "the local-error adaptive step runs in FP64 only");
+    if (!(ltol > 0) || !(safety > 0)) return set_err(c, PMX_ERR_INVALID, "ltol and the safety factor must be > 0");
+    if (d->nfc > PMX_MAX_NFC) return set_err(c, PMX_ERR_UNSUPPORTED, "nfc=%d outside [1,%d]", d->nfc, PMX_MAX_NFC);
+    LocalErrorStepper st;
+    int rc = st.init(c, d, io, ltol, safety);
+    if (rc != PMX_OK) return rc;
+    double dz = 0.0, umax[PMX_MAX_NFC];
+    rc = st.first_step(&dz, umax);
+    if (rc != PMX_OK) return rc;
+    double firstdz = dz;
+    int ncycle = 1;
+    if (!first_only) {                                     // scalar_a_ssfm, fiber.m:664-678
+        double zdone = 0.0;
+        while (zdone < d->length) {
+            if (zdone + dz > d->length) dz = d->length - zdone;
+            bool ok = false;
+            double prop = 0.0;
+            rc = st.try_step(dz, &ok, &prop);
+            if (rc != PMX_OK) return rc;
+            if (ok) {
+                zdone = zdone + dz;
+                ++ncycle;
+            }
+            dz = prop;
+            if (dz > d->dzmaxt) dz = d->dzmaxt;
+            if (ncycle + st.nrej > 10000000) return set_err(c, PMX_ERR_NUMERIC, "adaptive step loop did not terminate");
+        }
+    } else {                                               // scalar_ssfm with tolflag == 1, fiber.m:588-611
+        if (d->alphalin == 0.0)
+            return set_err(c, PMX_ERR_INVALID, "x.dphiadapt needs attenuation: fiber.m:607 divides (1-exp(-alpha*zdone)) by "
+                                               "(1-exp(-alpha*dzini))");
+        double dphimaxt = d->dphimaxt;
+        if (dz >= d->dzmaxt) {                             // :589-597
+            double maxpow = 0.0;
+            for (int k = 0; k < d->nfc; ++k) maxpow = (k == 0) ? d->gam[k] * umax[k] : std::max(maxpow, d->gam[k] * umax[k]);
+            dphimaxt = maxpow * (1.0 - exp(-d->alphalin * dz)) / d->alphalin;
+        }
+        const double dzini = dz;
+        double zdone = 0.0;
+        while (zdone == 0.0) {                             // :600-603
+            bool ok = false;
+            double prop = 0.0;
+            rc = st.try_step(dz, &ok, &prop);
+            if (rc != PMX_OK) return rc;
+            if (ok) zdone = zdone + dz;
+            dz = prop;
+            if (st.nrej > 100000) return set_err(c, PMX_ERR_NUMERIC, "adaptive first step did not converge");
+        }
+        if (dz > d->dzmaxt) dz = d->dzmaxt;                // :604
+        dphimaxt = dphimaxt * (1.0 - exp(-d->alphalin * zdone)) / (1.0 - exp(-d->alphalin * dzini));   // :607
+        pmx_fiber_desc rest = *d;
+        rest.dphimaxt = dphimaxt;
+        rest.z_start = zdone;
+        rest.dz_first = dz;
+        pmx_plan* plan = nullptr;
+        rc = pmx_plan_create(c, &rest, &plan);
+        double fdz = 0.0;
+        int32_t ncyc = 0, ntot = 0, status = 0;
+        pmx_fiber_result r = {&fdz, &ncyc, &ntot, &status, nullptr, nullptr, 0};
+        if (rc == PMX_OK) rc = pmx_fiber_exec(plan, st.u, &r);
+        std::string keep = c->error;
+        pmx_plan_destroy(plan);
+        if (rc != PMX_OK) {
+            c->error = keep;
+            g_tls_error = keep;
+            return rc;
+        }
+        firstdz = zdone;                                   // :609-611: the adaptive step counts as one
+        ncycle = ncyc + 1;
+    }
+    pmx_field h = *io;
+    std::vector<double> ybuf;
+    if (h.layout == PMX_PLANAR) {                          // the download wants all four planes; Y is discarded
+        ybuf.resize((size_t)2 * d->nfc * d->nfft);
+        if (!h.xi) return set_err(c, PMX_ERR_INVALID, "planar output needs xr and xi");
+        h.yr = ybuf.data();
+        h.yi = ybuf.data() + (size_t)d->nfc * d->nfft;
+    } else {
+        ybuf.resize((size_t)2 * d->nfc * d->nfft);
+        h.yr = ybuf.data();
+    }
+    rc = pmx_field_download(st.u, &h, 0, 1);
+    if (rc != PMX_OK) return rc;
+    if (out) {
+        if (out->firstdz) out->firstdz[0] = firstdz;
+        if (out->ncycle) out->ncycle[0] = ncycle;
+        if (out->ntot) out->ntot[0] = 0;
+        if (out->status) out->status[0] = PMX_OK;
+    }
+    return PMX_OK;
+}

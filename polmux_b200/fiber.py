@@ -239,7 +239,7 @@ def apply_side_effects(s: FiberSetup):
 LAST = {}  # firstdz / ncycle / schedule of the most recent fiber(), what the reference prints to simul_out
 
 
-def _nextstep_host(dzmax, phimax, gam, alphalin, umax):
+def _nextstep_host(dzmax, phimax, gam, alphalin, umax):   # (kept for host-side checks; the library has its own)
     """nextstep (fiber.m:693-715) from the per-column maxima of |u|^2."""
     with np.errstate(divide='ignore', invalid='ignore'):
         pmax = np.max(np.asarray(gam, dtype=np.float64) * np.asarray(umax, dtype=np.float64))
@@ -251,130 +251,21 @@ def _nextstep_host(dzmax, phimax, gam, alphalin, umax):
         return float(dzmax) if step > dzmax else float(step)
 
 
-class _LocalErrorStepper:
-    """adaptssfm (fiber.m:938-1010) on a resident scalar field: one symmetric step of length dz against two half steps,
-    local error max|u - uh|/dz, Richardson extrapolation 4/3*uh - 1/3*u on acceptance.  nl_step + attenuation
-    (pmx_scalar_nl_exec), lin_step (a one-step plan whose length is set per call), the error norm and the
-    extrapolation run on the device; the accept/reject logic is host code as in the reference."""
-
-    def __init__(self, s: FiberSetup, ctx: _lib.Context, disp_mode=None):
-        G = GSTATE
-        n, nfc = s.nfft, s.nfc
-        self.s, self.ctx = s, ctx
-        fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]
-        self.u = _lib.DeviceField(ctx, n, nfc, 1)
-        self.uh = _lib.DeviceField(ctx, n, nfc, 1)
-        self.ustack = _lib.DeviceField(ctx, n, nfc, 1)
-        self.u.upload(fx, None)
-        # lin_step(betat*dz, u) = ifft(fft(u).*fastexp(-betat*dz)): a one-step plan of the same dispersion, no loss
-        lin = FiberSetup(nfft=n, nfc=nfc, fls=(s.fls[0], 0, 0, 0), dphimaxt=math.inf, dzmaxt=s.length, length=s.length,
-                         alphalin=0.0, gam=s.gam, betat=s.betat, db1=s.db1, manakov=False, nplates=1, brf=s.brf,
-                         isv=False, isy=False, b1=s.b1, dch=s.dch, scalars=s.scalars)
-        desc, keep = setup_to_desc(lin, disp_mode=disp_mode)
-        self.plan = _lib.Plan(ctx, desc, keep)
-        self.gam = np.asarray(s.gam, dtype=np.float64)
-        self.nrej = 0
-
-    def _nl(self, f, dz):                                                   # nl_step + u*exp(-halfalpha*dz)
-        a = self.s.alphalin
-        leff = dz if a == 0 else (1 - math.exp(-a * dz)) / a
-        _lib.scalar_nl_exec(self.ctx, f, self.gam, leff, math.exp(-0.5 * a * dz), bool(self.s.fls[2]), bool(self.s.fls[3]))
-
-    def _lin(self, f, dz):
-        self.plan.set_length(dz)
-        self.plan.execute(f)
-
-    def first_step(self):
-        """nextstep on the incoming field -> (dz, per-column max |u|^2)"""
-        umax = _lib.field_max_power(self.ctx, self.u)[0]
-        return _nextstep_host(self.s.dzmaxt, self.s.dphimaxt, self.gam, self.s.alphalin, umax), umax
-
-    def try_step(self, dz):
-        """-> (accepted, proposed next step).  The field advances by dz only when the step is accepted."""
-        u, uh, ustack = self.u, self.uh, self.ustack
-        dz2, dz4 = 0.5 * dz, 0.25 * dz                                      # adaptssfm :966-1009
-        ustack.broadcast_from(u)
-        uh.broadcast_from(u)
-        self._nl(u, dz2)
-        self._lin(u, dz)
-        self._nl(u, dz2)
-        self._nl(uh, dz4)
-        self._lin(uh, dz2)
-        self._nl(uh, dz2)
-        self._lin(uh, dz2)
-        self._nl(uh, dz4)
-        est_err = math.sqrt(_lib.field_maxdiff2(self.ctx, u, uh)) / dz
-        with np.errstate(divide='ignore'):
-            prop = self.s.trg['safety'] * float(np.sqrt(np.float64(self.s.trg['err']) / np.float64(est_err))) * dz
-        if est_err > self.s.trg['err']:                                     # reject the step
-            u.broadcast_from(ustack)
-            self.nrej += 1
-            return False, prop
-        _lib.field_lincomb(self.ctx, u, 4.0 / 3.0, uh, 1.0 / 3.0, u)        # accept: Richardson extrapolation
-        return True, prop
-
-    def close(self):
-        self.plan.close()
-        for f in (self.uh, self.ustack, self.u):
-            f.close()
-
-
-def _scalar_a_ssfm(s: FiberSetup, ctx: _lib.Context, disp_mode=None):
-    """scalar_a_ssfm (fiber.m:639-679): symmetric SSFM with every step chosen from the local error."""
+def _scalar_adaptive(s: FiberSetup, ctx: _lib.Context, disp_mode=None):
+    """The local-error adaptive dispatches of the scalar path -- scalar_a_ssfm / adaptssfm (x.ltol, fiber.m:639-679,
+    938-1010) and scalar_ssfm with x.dphiadapt (tolflag 1, :588-611) -- through pmx_scalar_adaptive_run: the
+    accept/reject loop is host logic inside the library, nl_step, lin_step, the error norm and the Richardson
+    combination run on the resident field.  -> (firstdz, ncycle)"""
+    import ctypes
     G = GSTATE
-    st = _LocalErrorStepper(s, ctx, disp_mode)
-    ncycle = 1                                                              # :664-668
-    dz, _ = st.first_step()
-    firstdz, zdone = dz, 0.0
-    while zdone < s.length:                                                 # :670-678
-        if zdone + dz > s.length:
-            dz = s.length - zdone
-        accepted, prop = st.try_step(dz)
-        if accepted:
-            zdone = zdone + dz
-            ncycle += 1
-        dz = prop
-        if dz > s.dzmaxt:
-            dz = s.dzmaxt
-    gx, _ = st.u.download()
-    G.FIELDX = np.ascontiguousarray(gx[0].T)
-    st.close()
-    return firstdz, ncycle
-
-
-def _scalar_dphiadapt_ssfm(s: FiberSetup, ctx: _lib.Context, disp_mode=None):
-    """scalar_ssfm with tolflag == 1 (x.dphiadapt, fiber.m:588-611): the first step is found by the local-error
-    method, the nonlinear phase per step is recalibrated from it (:607) and the remaining fiber runs through the
-    device loop, resumed at zprop = zdone + dz with the step the adaptive method proposed."""
-    G = GSTATE
-    if s.alphalin == 0:
-        raise ValueError('x.dphiadapt needs attenuation: fiber.m:607 divides (1-exp(-alpha*zdone)) by (1-exp(-alpha*dzini))')
-    st = _LocalErrorStepper(s, ctx, disp_mode)
-    dz, umax = st.first_step()
-    dphimaxt = s.dphimaxt
-    if dz >= s.dzmaxt:                                                      # :589-597
-        maxpow = float(np.max(st.gam * umax))
-        dphimaxt = maxpow * (1 - math.exp(-s.alphalin * dz)) / s.alphalin
-    dzini, zdone = dz, 0.0
-    while zdone == 0:                                                       # :600-603
-        accepted, prop = st.try_step(dz)
-        if accepted:
-            zdone = zdone + dz
-        dz = prop
-    if dz > s.dzmaxt:                                                       # :604
-        dz = s.dzmaxt
-    dphimaxt = dphimaxt * (1 - math.exp(-s.alphalin * zdone)) / (1 - math.exp(-s.alphalin * dzini))   # :607
-    rest = dataclasses.replace(s, dphimaxt=dphimaxt, tolflag=0, trg=None)
-    desc, keep = setup_to_desc(rest, disp_mode=disp_mode, z_start=zdone, dz_first=dz)
-    plan = _lib.Plan(ctx, desc, keep)
-    try:
-        res = plan.execute(st.u)
-    finally:
-        plan.close()
-    gx, _ = st.u.download()
-    G.FIELDX = np.ascontiguousarray(gx[0].T)
-    st.close()
-    return zdone, int(res.ncycle[0]) + 1                                    # :609-611: the adaptive step counts as one
+    desc, keep = setup_to_desc(s, disp_mode=disp_mode)
+    fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]          # [1][nfc][nfft]
+    io = _lib.complex_field(fx, None)
+    res = _lib.Result(1)
+    ctx.check(ctx.lib.pmx_scalar_adaptive_run(ctx.h, ctypes.byref(desc), float(s.trg['err']), float(s.trg['safety']),
+                                              1 if s.tolflag == 1 else 0, ctypes.byref(io), ctypes.byref(res.c)))
+    G.FIELDX = np.ascontiguousarray(fx[0].T)
+    return float(res.firstdz[0]), int(res.ncycle[0])
 
 
 def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional[_lib.Context] = None,
@@ -396,7 +287,7 @@ def fiber(x, flag: str, rng: Optional[np.random.Generator] = None, ctx: Optional
     if s.tolflag == 2 or (s.tolflag == 1 and not s.isv):                    # :375-380, :386-387
         if (precision or PRECISION) != 'f64':
             raise NotImplementedError('the local-error adaptive step runs in FP64 only')
-        firstdz, ncycle = (_scalar_a_ssfm if s.tolflag == 2 else _scalar_dphiadapt_ssfm)(s, ctx, disp_mode)
+        firstdz, ncycle = _scalar_adaptive(s, ctx, disp_mode)
         apply_side_effects(s)
         LAST.clear()
         LAST.update(firstdz=firstdz, ncycle=ncycle, ntot=0)
