@@ -619,7 +619,10 @@ class _Continue(Exception):
 
 class Interp:
     def __init__(self, path, rng=None):
+        # path: one directory, or a list searched in order (an earlier directory shadows a later one, like the
+        # interpreter's path); self.builtins: per-instance functions (e.g. a MEX gateway) looked up before BUILTINS
         self.path = path
+        self.builtins = {}
         self.rng = rng if rng is not None else np.random.default_rng(0)
         self.globals = {}
         self.files = {}       # file base name -> {func name: ast}
@@ -630,8 +633,13 @@ class Interp:
     def load(self, name):
         if name in self.files:
             return self.files[name]
-        fn = os.path.join(self.path, name + '.m')
-        if not os.path.exists(fn):
+        fn = None
+        for d in ([self.path] if isinstance(self.path, str) else list(self.path)):
+            cand = os.path.join(d, name + '.m')
+            if os.path.exists(cand):
+                fn = cand
+                break
+        if fn is None:
             return None
         src = open(fn, encoding='latin-1').read()
         funcs = Parser(tokenize(src), name + '.m').parse_file()
@@ -646,6 +654,8 @@ class Interp:
     def call(self, name, args, nargout=1, local_funcs=None):
         if local_funcs and name in local_funcs and name != '__main__':
             return self.run_function(local_funcs[name], args, nargout, local_funcs)
+        if name in self.builtins:
+            return self.builtins[name](self, args, nargout)
         table = self.load(name)
         if table is not None:
             return self.run_function(table['__main__'], args, nargout, table)

@@ -1,0 +1,208 @@
+"""matlab/fiber.m and matlab/ampliflat.m -- the thin M front-ends that replace the toolbox's fiber.m on the path --
+executed by the mini M interpreter (oracle/mini_m).
+
+CPU (here, where /root/reference exists): the front-end with an oracle-backed ssfm_mex reproduces the goldens the
+interpreted ORIGINAL fiber.m produced (same plate draws from the same rand stream, same DELAY / DISP, same brf, same
+simul_out text), with create_field.m / reset_all.m taken from the reference tree -- i.e. the scripts' calls run
+unchanged with matlab/ first on the path.
+GPU: the same front-end with the real gateway (mexFunction of mex/ssfm_mex.c through the mex.h stand-in) against the
+goldens, including C1 at its full size, the resident span loop fiber(); ampliflat(); and the FP32 option."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle.fiber_oracle as orc
+from oracle.mini_m.interp import Interp, MStruct, MError, from_m, to_m
+from polmux_b200 import synth
+import mex_bridge
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+MDIR = os.path.join(ROOT, 'matlab')
+REF = '/root/reference'
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, '*.npz')))
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'create_field.m')), reason='reference tree not present')
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    return z, json.loads(str(z['meta']))
+
+
+def globals_from_python(it, nsymb, nt, nch, rate, pavg, fx, fy, lams=None):
+    """GSTATE / CONSTANTS as reset_all.m + create_field.m leave them (for runs without the reference tree)."""
+    n = nsymb * nt
+    it.globals['CONSTANTS'] = MStruct({'CLIGHT': to_m(orc.CLIGHT), 'HPLANCK': to_m(orc.HPLANCK),
+                                       'ECHARGE': to_m(orc.ECHARGE), 'KBOLTZMANN': to_m(orc.KBOLTZMANN)})
+    fn = np.fft.fftshift(-nt / 2.0 + np.arange(n) / nsymb).reshape(1, -1)
+    npol = 2 if fy is not None else 1
+    it.globals['GSTATE'] = MStruct({
+        'NSYMB': to_m(nsymb), 'NT': to_m(nt), 'NCH': to_m(nch), 'FN': fn, 'SYMBOLRATE': to_m(rate),
+        'LAMBDA': (synth.wdm_lambdas(nch) if lams is None else lams).reshape(1, -1),
+        'POWER': np.full((1, nch), float(pavg)), 'FIELDX': np.array(fx), 'FIELDY': np.zeros((0, 0)) if fy is None else np.array(fy),
+        'DELAY': np.zeros((npol, nch)), 'DISP': np.zeros((npol, nch)), 'PRINT': np.array([[False]]), 'DIR': 'sim'})
+    it.globals['PMXOPT'] = np.zeros((0, 0))
+
+
+def tx_through_reference(it, m, z):
+    it.call('reset_all', [to_m(m['nsymb']), to_m(m['nt']), to_m(m['nch'])], 0)
+    G = it.globals['GSTATE'].copy()
+    G['SYMBOLRATE'] = to_m(m['rate'])
+    G['LAMBDA'] = to_m(synth.wdm_lambdas(m['nch']).reshape(1, -1))
+    G['POWER'] = to_m(np.full((1, m['nch']), float(m['pavg'])))
+    it.globals['GSTATE'] = G
+    it.globals['PMXOPT'] = np.zeros((0, 0))
+    args = [m['ftype'], to_m(z['in_ex']), to_m(z['in_ey']) if m['two_pol'] else np.zeros((0, 0)), MStruct({'power': 'average'})]
+    it.call('create_field', args, 0)
+
+
+@needs_ref
+@pytest.mark.parametrize('scalmode', [0, 1])
+@pytest.mark.parametrize('name', CASES)
+def test_front_end_reproduces_the_interpreted_original(name, scalmode):
+    """matlab/fiber.m (first on the path) + the reference's reset_all.m / create_field.m + an oracle-backed ssfm_mex
+    == the interpreted original fiber.m: fields <= 1e-13, DELAY / DISP, the brf struct and its plate draws"""
+    z, m = load(name)
+    calls = []
+    it = Interp([MDIR, REF], rng=np.random.Generator(np.random.PCG64(m['seed'])))
+    it.builtins['ssfm_mex'] = mex_bridge.oracle_gateway(calls)
+    tx_through_reference(it, m, z)
+    it.globals['PMXOPT'] = MStruct({'scalar': to_m(float(scalmode))})
+    want_brf = 'brf_theta' in z.files
+    res = it.call('fiber', [to_m(m['fiber']), m['flag']], 1 if want_brf else 0)
+    G = it.globals['GSTATE']
+    if z['out_FIELDY'].size:
+        err = orc.rel_l2(G['FIELDX'], G['FIELDY'], z['out_FIELDX'], z['out_FIELDY'])
+    else:
+        err = float(np.linalg.norm(G['FIELDX'] - z['out_FIELDX']) / np.linalg.norm(z['out_FIELDX']))
+        assert np.size(G['FIELDY']) == 0
+    assert err < 1e-13, err
+    np.testing.assert_allclose(G['DELAY'], z['out_DELAY'], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(G['DISP'], z['out_DISP'], rtol=1e-13, atol=1e-13)
+    assert len(calls) == 1 and calls[0]['scalar_field'] == (0.0 if m['two_pol'] or m['fiber'].get('dgd') else 1.0)
+    if want_brf:
+        brf = from_m(res[0])
+        for k in ('db0', 'theta', 'epsilon'):
+            np.testing.assert_array_equal(np.asarray(brf[k]).ravel(), z['brf_' + k])
+        np.testing.assert_allclose(np.asarray(brf['betat']), z['brf_betat'], rtol=1e-15, atol=0)
+        np.testing.assert_allclose(np.asarray(brf['db1']), z['brf_db1'], rtol=1e-15, atol=0)
+        assert float(np.asarray(brf['lcorr']).ravel()[0]) == float(z['brf_lcorr'][0])
+
+
+@needs_ref
+@pytest.mark.parametrize('name', sorted(os.path.basename(p)[len('simul_out_'):-5] for p in
+                                        glob.glob(os.path.join(GOLD, 'simul_out_*.json'))))
+def test_front_end_prints_the_same_summary(name):
+    """GSTATE.PRINT: the block matlab/fiber.m appends to simul_out is character-identical to the original's"""
+    m = json.load(open(os.path.join(GOLD, 'simul_out_%s.json' % name)))
+    ex, ey, _, _ = synth.pdm_qpsk(m['nsymb'], m['nt'], m['nch'])
+    it = Interp([MDIR, REF], rng=np.random.Generator(np.random.PCG64(m['seed'])))
+    it.builtins['ssfm_mex'] = mex_bridge.oracle_gateway()
+    tx_through_reference(it, m, {'in_ex': ex, 'in_ey': ey})
+    G = it.globals['GSTATE'].copy()
+    G['PRINT'] = to_m(True)
+    G['DIR'] = 'sim'
+    it.globals['GSTATE'] = G
+    it.printed = []
+    it.call('fiber', [to_m(m['fiber']), m['flag']], 0)
+    assert ''.join(it.printed) == m['text']
+
+
+@needs_ref
+def test_front_end_errors_like_the_original():
+    it = Interp([MDIR, REF])
+    it.builtins['ssfm_mex'] = mex_bridge.oracle_gateway()
+    z, m = load('scalar_gs')
+    tx_through_reference(it, m, z)
+    with pytest.raises(MError, match='wrong flag'):
+        it.call('fiber', [to_m(m['fiber']), 'abcd'], 0)
+    with pytest.raises(MError, match='only for channels separated'):
+        it.call('fiber', [to_m(m['fiber']), 'g--x'], 0)
+    with pytest.raises(MError, match='Missing DGD'):
+        it.call('fiber', [to_m(m['fiber']), 'gps-'], 0)
+    z, m = load('cnlse_nopmd')
+    tx_through_reference(it, m, z)
+    with pytest.raises(MError, match='absence of polarization'):
+        it.call('fiber', [to_m(dict(m['fiber'], ltol=1e-6)), 'g-s-'], 0)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _gpu_interp(seed):
+    it = Interp([MDIR], rng=np.random.Generator(np.random.PCG64(seed)))
+    gw = mex_bridge.real_gateway()
+    it.builtins['ssfm_mex'] = gw
+    return it, gw
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['manakov_100plates_80km', 'cnlse_10plates_100km', 'sep3_manakov', 'pmf_single', 'scalar_gs',
+                                  'scalar_sep3_gsx', 'scalar_ltol_gs', 'scalar_dphiadapt_sep3_gsx', 'cnlse_nopmd'])
+def test_interpreted_front_end_on_the_device(name):
+    """matlab/fiber.m interpreted, its ssfm_mex the compiled gateway on the GPU: all three dispatches (matrix_ssfm,
+    scalar_ssfm, scalar_a_ssfm) against the interpreted original's goldens, FP64 <= 1e-10"""
+    z, m = load(name)
+    it, gw = _gpu_interp(m['seed'])
+    two = m['two_pol']
+    globals_from_python(it, m['nsymb'], m['nt'], m['nch'], m['rate'], m['pavg'], z['tx_FIELDX'],
+                        z['tx_FIELDY'] if two else None)
+    it.call('fiber', [to_m(m['fiber']), m['flag']], 0)
+    G = it.globals['GSTATE']
+    if z['out_FIELDY'].size:
+        err = orc.rel_l2(G['FIELDX'], G['FIELDY'], z['out_FIELDX'], z['out_FIELDY'])
+    else:
+        err = float(np.linalg.norm(G['FIELDX'] - z['out_FIELDX']) / np.linalg.norm(z['out_FIELDX']))
+    assert err < 1e-10, err
+    np.testing.assert_allclose(G['DELAY'], z['out_DELAY'], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(G['DISP'], z['out_DISP'], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_interpreted_front_end_c1_full_size_and_resident_span_loop():
+    """C1 at its full size through the interpreted front-end against the interpreted original; then the script loop
+    `fiber(x,flag); ampliflat(G,'gain',opt);` three times: the field is uploaded once (the gateway keeps it in HBM and
+    recognises the arrays it handed back), every call still returns its arrays to the interpreter, and the result
+    equals the same loop with PMXOPT.resident = false bit for bit; FP32 option within 1e-5 (Manakov golden)"""
+    import polmux_b200 as pmx
+    z = np.load(os.path.join(GOLD, 'big', 'c1_cnlse_10plates_100km_2e16.npz'))
+    m = json.loads(str(z['meta']))
+    ex, ey, _, _ = synth.pdm_qpsk(m['nsymb'], m['nt'], 1)
+    pmx.reset_all(m['nsymb'], m['nt'], 1)
+    P = pmx.GSTATE
+    P.SYMBOLRATE, P.POWER, P.LAMBDA = m['rate'], np.array([float(m['pavg'])]), synth.wdm_lambdas(1)
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    tx_x, tx_y = np.array(P.FIELDX), np.array(P.FIELDY)
+    it, gw = _gpu_interp(m['seed'])
+    globals_from_python(it, m['nsymb'], m['nt'], 1, m['rate'], m['pavg'], tx_x, tx_y)
+    it.call('fiber', [to_m(m['fiber']), 'gps-'], 0)
+    G = it.globals['GSTATE']
+    assert orc.rel_l2(G['FIELDX'], G['FIELDY'], z['out_FIELDX'], z['out_FIELDY']) < 1e-10
+    # span loop, resident and per-call
+    fib = dict(m['fiber'], length=2e4)
+    outs = {}
+    for resident in (1.0, 0.0):
+        it, gw = _gpu_interp(5)
+        globals_from_python(it, m['nsymb'], m['nt'], 1, m['rate'], m['pavg'], tx_x, tx_y)
+        it.globals['PMXOPT'] = MStruct({'resident': to_m(resident)})
+        s0 = gw.stats()
+        for k in range(3):
+            it.call('fiber', [to_m(fib), 'gps-'], 0)
+            it.call('ampliflat', [to_m(4.0), 'gain', MStruct({'f': to_m(5.0)})], 0)
+        s1 = gw.stats()
+        G = it.globals['GSTATE']
+        outs[resident] = (np.array(G['FIELDX']), np.array(G['FIELDY']))
+        up, down, hits = (s1[k] - s0[k] for k in ('uploads', 'downloads', 'resident_hits'))
+        assert down == 6
+        assert (up, hits) == ((1, 5) if resident else (6, 0))
+    assert np.array_equal(outs[1.0][0], outs[0.0][0]) and np.array_equal(outs[1.0][1], outs[0.0][1])
+    # FP32 option of the front-end (PMXOPT.precision = 'f32'), on the Manakov golden: within the mode's 1e-5
+    z, m = load('manakov_100plates_80km')
+    it, gw = _gpu_interp(m['seed'])
+    globals_from_python(it, m['nsymb'], m['nt'], 1, m['rate'], m['pavg'], z['tx_FIELDX'], z['tx_FIELDY'])
+    it.globals['PMXOPT'] = MStruct({'precision': 'f32'})
+    it.call('fiber', [to_m(m['fiber']), m['flag']], 0)
+    G = it.globals['GSTATE']
+    err = orc.rel_l2(G['FIELDX'], G['FIELDY'], z['out_FIELDX'], z['out_FIELDY'])
+    assert 1e-9 < err < 1e-5, err
