@@ -153,6 +153,15 @@ if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'c1':     # only the full-size C1 case
         run_c1_case()
         sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'small':  # only the small-field cases
+        run_case('small_ex06_gsx_2e10', 32, 32, 1, 'unique', fib(length=1e5, dphimax=3e-3), 'g-sx', two_pol=False,
+                 want_brf=False, rate=10.0, pavg=4.0)
+        run_case('small_ex10_sep5_gsx_2e11', 64, 32, 5, 'sepfields', fib(length=1e5, dphimax=3e-3), 'g-sx', two_pol=False,
+                 want_brf=False, rate=10.0, pavg=4.0)
+        run_case('small_2pol_cnlse_2e9', 32, 16, 1, 'unique', fib(length=5e4, dgd=0.5, nplates=10, manakov='no'), 'gps-')
+        run_case('small_sep3_manakov_2e8', 16, 16, 3, 'sepfields', fib(length=4e4, dgd=0.3, nplates=8, manakov='yes',
+                                                                        slope=0.057), 'gps-')
+        sys.exit(0)
     run_case('lin_gvd_2pol', 256, 16, 1, 'unique', fib(length=1e5), 'g---', want_brf=True)
     run_case('lin_pmd_20plates', 256, 16, 1, 'unique', fib(length=8e4, dgd=0.5, nplates=20), 'gp--')
     run_case('cnlse_10plates_100km', 256, 16, 1, 'unique', fib(length=1e5, dgd=1.0, nplates=10, manakov='no'), 'gps-',
@@ -179,6 +188,15 @@ if __name__ == '__main__':
              want_brf=False)
     run_case('scalar_dphiadapt_sep3_gsx', 256, 16, 3, 'sepfields', fib(length=3e4, ltol=2e-6, dphiadapt=True, slope=0.057),
              'g-sx', two_pol=False, want_brf=False)
+    # the sizes of the reference's own scalar-path scripts: ex06_ber.m:14-16 (32 x 32 = 2^10 samples, one channel) and
+    # ex10_wdm.m:22-24 (64 x 32 = 2^11 samples, five separate channels with XPM), transmission fiber of ex10_wdm.m:44-52
+    run_case('small_ex06_gsx_2e10', 32, 32, 1, 'unique', fib(length=1e5, dphimax=3e-3), 'g-sx', two_pol=False, want_brf=False,
+             rate=10.0, pavg=4.0)
+    run_case('small_ex10_sep5_gsx_2e11', 64, 32, 5, 'sepfields', fib(length=1e5, dphimax=3e-3), 'g-sx', two_pol=False,
+             want_brf=False, rate=10.0, pavg=4.0)
+    run_case('small_2pol_cnlse_2e9', 32, 16, 1, 'unique', fib(length=5e4, dgd=0.5, nplates=10, manakov='no'), 'gps-')
+    run_case('small_sep3_manakov_2e8', 16, 16, 3, 'sepfields', fib(length=4e4, dgd=0.3, nplates=8, manakov='yes', slope=0.057),
+             'gps-')
     # the summary block of fiber.m:392-456 (GSTATE.PRINT)
     run_print_case('manakov', 256, 16, 1, 'unique', fib(length=8e4, dgd=0.1, nplates=100, manakov='yes'), 'gps-')
     run_print_case('wdm3_pmf', 128, 64, 3, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],

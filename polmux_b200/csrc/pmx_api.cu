@@ -227,6 +227,7 @@ struct pmx_plan {
     int* trace_ntrunk = nullptr;
     int trace_cap = 0;
     bool single_step;
+    bool onchip = false;   // nfft <= 4096: the single-launch kernel of small fields (pmx_onchip.cuh)
 };
 
 static int set_err(pmx_ctx* ctx, int code, const char* fmt, ...) {
@@ -741,9 +742,16 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     if (d->precision != PMX_F64 && d->precision != PMX_F32)
         return set_err(c, PMX_ERR_INVALID, "unknown precision %d", d->precision);
     const int lg = ilog2_exact(d->nfft);
-    if (lg < 12 || lg > 24)
-        return set_err(c, PMX_ERR_UNSUPPORTED, "nfft=%lld: this build handles powers of two from 2^12 to 2^24",
+    if (lg < 6 || lg > 24)
+        return set_err(c, PMX_ERR_UNSUPPORTED, "nfft=%lld: this build handles powers of two from 2^6 to 2^24",
                        (long long)d->nfft);
+    // Fields of up to 4096 samples run in the single-launch on-chip kernel (one CTA per column, the columns of a
+    // realization in one thread-block cluster): at most 8 columns.  PMX_NO_ONCHIP=1 sends 2^12 through the three passes.
+    const bool no_onchip = getenv("PMX_NO_ONCHIP") && atoi(getenv("PMX_NO_ONCHIP"));
+    const bool onchip = lg <= 12 && d->nfc <= 8 && !(no_onchip && lg == 12);
+    if (lg < 12 && !onchip)
+        return set_err(c, PMX_ERR_UNSUPPORTED, "nfft=%lld (< 2^12) with nfc=%d: small fields take at most 8 columns",
+                       (long long)d->nfft, d->nfc);
     if (d->nfc < 1 || d->nfc > PMX_MAX_NFC)
         return set_err(c, PMX_ERR_UNSUPPORTED, "nfc=%d outside [1,%d]", d->nfc, PMX_MAX_NFC);
     if (d->batch < 1) return set_err(c, PMX_ERR_INVALID, "batch must be >= 1");
@@ -775,17 +783,30 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
     p->ctx = c;
     p->d = *d;
     p->d.gam = p->d.db0 = p->d.theta = p->d.epsilon = p->d.betat = p->d.db1 = p->d.beta1 = p->d.beta2 = nullptr;
-    p->log2N1 = split_log2N1(lg);
+    p->onchip = onchip;
+    p->log2N1 = onchip ? 0 : split_log2N1(lg);   // on-chip: one transform of the full length, bins in natural order
     p->log2N2 = lg - p->log2N1;
     p->N1 = 1 << p->log2N1;
     p->N2 = 1 << p->log2N2;
-    p->tA = pmx_get_table(p->N1, d->precision);
+    p->tA = pmx_get_table(onchip ? p->N2 : p->N1, d->precision);
     p->tB = pmx_get_table(p->N2, d->precision);
     if (!p->tA || !p->tB) {
         delete p;
         return set_err(c, PMX_ERR_UNSUPPORTED, "no kernel built for FFT factors %d x %d", 1 << (lg / 2), 1 << (lg - lg / 2));
     }
+    if (onchip) {
+        const int key = p->tB->L + 65536 * p->tB->precision + (1 << 20);
+        if (!c->setup_done.count(key)) {
+            cudaError_t e = p->tB->onchip_setup();
+            if (e != cudaSuccess) {
+                delete p;
+                return set_err(c, PMX_ERR_CUDA, "on-chip kernel setup (L=%d) failed: %s", (int)d->nfft, cudaGetErrorString(e));
+            }
+            c->setup_done[key] = pmx_ctx::Occ();
+        }
+    }
     for (const PmxLaunchTable* t : {p->tA, p->tB}) {
+        if (onchip) break;
         if (!c->setup_done.count(t->L + 65536 * t->precision)) {
             pmx_ctx::Occ o;
             cudaError_t e = t->setup(&o.a, &o.b, &o.c);
@@ -969,16 +990,17 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     pa.batch = batch;
     pa.dbg = g_dbg;
     pa.pkg = p->pkg;
-    const void *tw4A, *tw4B;
-    rc = get_four_tw(c, p->d.nfft, p->tA, p->N2, &tw4A);  // pass A: one row per column n2, W_N^(n2*k1), k1 < N1
-    if (rc) return rc;
-    rc = get_four_tw(c, p->d.nfft, p->tB, p->N1, &tw4B);  // pass B: one row per k1, W_N^(k1*n2), n2 < N2
-    if (rc) return rc;
-    const void *twA, *twB;
-    rc = get_stage_tw(c, p->tA, &twA);
-    if (rc) return rc;
-    rc = get_stage_tw(c, p->tB, &twB);
-    if (rc) return rc;
+    const void *tw4A = nullptr, *tw4B = nullptr, *twA = nullptr, *twB = nullptr;
+    if (!p->onchip) {
+        rc = get_four_tw(c, p->d.nfft, p->tA, p->N2, &tw4A);  // pass A: one row per column n2, W_N^(n2*k1), k1 < N1
+        if (rc) return rc;
+        rc = get_four_tw(c, p->d.nfft, p->tB, p->N1, &tw4B);  // pass B: one row per k1, W_N^(k1*n2), n2 < N2
+        if (rc) return rc;
+        rc = get_stage_tw(c, p->tA, &twA);
+        if (rc) return rc;
+        rc = get_stage_tw(c, p->tB, &twB);
+        if (rc) return rc;
+    }
     PassParams pA = pa, pB = pa;
     pA.tw_stage = twA;
     pB.tw_stage = twB;
@@ -987,6 +1009,44 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
 
     CK(c, cudaMemsetAsync(p->ctl, 0, (size_t)batch * sizeof(StepCtl), c->stream));
     CK(c, cudaMemsetAsync(p->pkg, 0, (size_t)batch * sizeof(StepPkg), c->stream));
+    // what the caller gets back, from the control blocks read into h_ctl
+    auto collect = [&]() -> int {
+        int worst = PMX_OK;
+        for (int b = 0; b < batch; ++b) {
+            const StepCtl& s = c->h_ctl[b];
+            int st = (s.state == PMX_ST_ERROR) ? s.err : PMX_OK;
+            if (st != PMX_OK && worst == PMX_OK) worst = st;
+            if (out) {
+                if (out->firstdz) out->firstdz[b] = s.firstdz;
+                if (out->ncycle) out->ncycle[b] = s.ncycle;
+                if (out->ntot) out->ntot[b] = s.ntot + s.ntrunk - s.nmem;
+                if (out->status) out->status[b] = st;
+            }
+        }
+        if (p->trace_cap && out) {
+            CK(c, cudaMemcpy(out->trace_dz, p->trace_dz, (size_t)batch * p->trace_cap * sizeof(double), cudaMemcpyDeviceToHost));
+            CK(c, cudaMemcpy(out->trace_ntrunk, p->trace_ntrunk, (size_t)batch * p->trace_cap * sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        if (worst == PMX_ERR_PLATE_INDEX)
+            return set_err(c, worst, "trunk counter exceeded nplates=%d (the reference raises an index error at fiber.m:910 "
+                                     "for this length/nplates pair)", p->d.nplates);
+        if (worst != PMX_OK) return set_err(c, worst, "NaN/Inf met in the step control");
+        return PMX_OK;
+    };
+    if (p->onchip) {   // small field: the whole loop of every realization in one launch
+        PassParams q = pa;
+        rc = get_stage_tw(c, p->tB, &q.tw_stage);
+        if (rc) return rc;
+        q.N1 = 1;
+        q.N2 = (int)p->d.nfft;
+        q.log2N1 = fld->log2N1;   // layout of the resident column (transposed for 2^12, natural below)
+        q.log2N2 = fld->log2N2;
+        CK(c, p->tB->onchip(nfc, batch, c->stream, q, p->fc));
+        c->launches += 1;
+        CK(c, cudaMemcpyAsync(c->h_ctl, p->ctl, (size_t)batch * sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return collect();
+    }
     {
         dim3 g(148 * 2, batch * nfc);
         ProfScope ps(c, 3);
@@ -1132,27 +1192,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
         }
         chunk = (int)std::min(32.0, std::max(1.0, ceil(0.85 * est)));
     }
-    int worst = PMX_OK;
-    for (int b = 0; b < batch; ++b) {
-        const StepCtl& s = c->h_ctl[b];
-        int st = (s.state == PMX_ST_ERROR) ? s.err : PMX_OK;
-        if (st != PMX_OK && worst == PMX_OK) worst = st;
-        if (out) {
-            if (out->firstdz) out->firstdz[b] = s.firstdz;
-            if (out->ncycle) out->ncycle[b] = s.ncycle;
-            if (out->ntot) out->ntot[b] = s.ntot + s.ntrunk - s.nmem;
-            if (out->status) out->status[b] = st;
-        }
-    }
-    if (p->trace_cap && out) {
-        CK(c, cudaMemcpy(out->trace_dz, p->trace_dz, (size_t)batch * p->trace_cap * sizeof(double), cudaMemcpyDeviceToHost));
-        CK(c, cudaMemcpy(out->trace_ntrunk, p->trace_ntrunk, (size_t)batch * p->trace_cap * sizeof(int), cudaMemcpyDeviceToHost));
-    }
-    if (worst == PMX_ERR_PLATE_INDEX)
-        return set_err(c, worst, "trunk counter exceeded nplates=%d (the reference raises an index error at fiber.m:910 "
-                                 "for this length/nplates pair)", p->d.nplates);
-    if (worst != PMX_OK) return set_err(c, worst, "NaN/Inf met in the step control");
-    return PMX_OK;
+    return collect();
 }
 
 extern "C" int pmx_fiber_run(pmx_ctx* c, const pmx_fiber_desc* d, pmx_field* io, pmx_fiber_result* out) {

@@ -175,26 +175,20 @@ __device__ __forceinline__ void pmx_block_max(unsigned long long key, void* scra
     }
 }
 
-// Step control, one CTA per realization: thread 0 runs nextstep + checkstep for the step about to run
-// (first: fiber.m:512; afterwards :534-536) from the per-column maxima the previous kernel left, then the
-// CTA writes the step package the pass kernels fetch with their tiles.
-static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst f, int first) {
-    const int b = blockIdx.x;
-    StepCtl* c = &p.ctl[b];
-    StepPkg* g = &p.pkg[b];
-    __shared__ int s_go;
-    if (p.pdl) {
-        pmx_pdl_launch_dependents();
-        pmx_pdl_wait();
-    }
+// nextstep + checkstep for the step about to run and the step package of the realization, by all threads of a CTA
+// (thread 0 runs the scalar logic, everybody copies).  c, g: the realization's control block and package (global
+// memory for the pass kernels, shared memory in the single-CTA kernel of small fields).  -> false when the realization
+// has no further step.
+__device__ __forceinline__ bool pmx_ctl_step(StepCtl* c, StepPkg* g, const PassParams& p, const FiberConst& f, int first, int b,
+                                             int* s_go) {
     if (threadIdx.x == 0) {
         const int go = first || c->state < PMX_ST_DONE;
         if (go) pmx_ctl_next(c, f, first != 0, b, p.trace_dz, p.trace_ntrunk);
         g->state = c->state;
-        s_go = go && c->state < PMX_ST_DONE;
+        *s_go = go && c->state < PMX_ST_DONE;
     }
     __syncthreads();
-    if (!s_go) return;
+    if (!*s_go) return false;
     const int ntrunk = c->ntrunk, n_first = c->n_first;
     const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + n_first;
     if (threadIdx.x == 0) {
@@ -220,27 +214,41 @@ static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst
         g->n_first = n_first;
         g->bmode = f.pmd ? c->bmode : (c->bmode & PMX_BM_NL_SMALL);
     }
-    if (!f.pmd || ntrunk <= 0) return;
-    if (threadIdx.x >= 32 && threadIdx.x < 40) {  // entry matrix
-        const int i = threadIdx.x - 32;
-        double v = (i == 0 || i == 6) ? 1.0 : 0.0;
-        if (c->bmode & PMX_BM_ENTRY_R) {  // R^H: element (r,cc) = conj(R(cc,r))
-            const int r = i >> 2, cc = (i >> 1) & 1, im = i & 1;
-            v = (&plg[0].r11r)[(cc * 2 + r) * 2 + im];
-            if (im) v = -v;
-        } else if (c->bmode & PMX_BM_ENTRY_C) {
-            v = (&plg[-1].c11r)[i];
+    if (!f.pmd || ntrunk <= 0) return true;
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+        if (i < 8) {  // entry matrix
+            double v = (i == 0 || i == 6) ? 1.0 : 0.0;
+            if (c->bmode & PMX_BM_ENTRY_R) {  // R^H: element (r,cc) = conj(R(cc,r))
+                const int r = i >> 2, cc = (i >> 1) & 1, im = i & 1;
+                v = (&plg[0].r11r)[(cc * 2 + r) * 2 + im];
+                if (im) v = -v;
+            } else if (c->bmode & PMX_BM_ENTRY_C) {
+                v = (&plg[-1].c11r)[i];
+            }
+            g->E[i] = v;
+        } else {      // exit matrix
+            g->X[i - 8] = (&plg[ntrunk - 1].r11r)[i - 8];
         }
-        g->E[i] = v;
-    } else if (threadIdx.x >= 40 && threadIdx.x < 48) {  // exit matrix
-        const int i = threadIdx.x - 40;
-        g->X[i] = (&plg[ntrunk - 1].r11r)[i];
     }
     constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
     const int n = (ntrunk < PMX_PKG_PLATES ? ntrunk : PMX_PKG_PLATES) * PLD;
     const double* src = reinterpret_cast<const double*>(plg);
     double* dst = reinterpret_cast<double*>(g->plates);
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    return true;
+}
+
+// Step control, one CTA per realization: nextstep + checkstep for the step about to run (first: fiber.m:512; afterwards
+// :534-536) from the per-column maxima the previous kernel left, and the step package the pass kernels fetch with
+// their tiles.
+static __global__ void __launch_bounds__(128) pmx_k_ctl(PassParams p, FiberConst f, int first) {
+    const int b = blockIdx.x;
+    __shared__ int s_go;
+    if (p.pdl) {
+        pmx_pdl_launch_dependents();
+        pmx_pdl_wait();
+    }
+    pmx_ctl_step(&p.ctl[b], &p.pkg[b], p, f, first, b, &s_go);
 }
 
 // ---------------------------------------------------------------------------
@@ -422,6 +430,60 @@ static __global__ void __launch_bounds__(256) pmx_k_xpm_sum(PassParams p, FiberC
 }
 
 // ---------------------------------------------------------------------------
+// The nonlinear step on the eight samples a thread holds: matrix_nl_step (fiber.m:827-851, Manakov or CNLSE) or, on
+// the scalar path, nl_step (:786-803; with the 'x' flag y[q].x must hold sum_j |u_j|^2 of the sample).
+__device__ __forceinline__ void pmx_nl_step(cpx (&x)[8], cpx (&y)[8], const StepPkg* st, const FiberConst& f, int col) {
+    if (f.scalar_field) {  // nl_step (fiber.m:786-803): u .* fastexp(-gam.*pow*leff), Y absent
+        if (f.spm || f.xpm) {
+            const real ngam = (real)(-f.gam[col]), leff = (real)st->leff;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                real pw = R_ADD(R_MUL(x[q].x, x[q].x), R_MUL(x[q].y, x[q].y));
+                if (f.xpm) {  // y.x holds sum(pow,2) of this sample (pmx_k_xpm_sum)
+                    const real two_s = R_MUL((real)2, y[q].x);
+                    pw = f.spm ? R_ADD(two_s, -pw) : R_MUL((real)2, R_ADD(y[q].x, -pw));
+                }
+                x[q] = cmul(x[q], pmx_cis_r(R_MUL(R_MUL(ngam, pw), leff)));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[q] = mkc((real)0, (real)0);
+    } else if (f.spm) {
+        const real gamleff = (real)__dmul_rn(f.gam[col], st->leff);
+        const real ngl = -gamleff;
+        const bool nl_small = (st->bmode & PMX_BM_NL_SMALL) != 0;  // uniform for the tile
+        cpx e[8];
+        if (nl_small) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) e[q] = pmx_cis_small(R_MUL(ngl, power_ref(x[q], y[q])));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) e[q] = pmx_cis_r(R_MUL(ngl, power_ref(x[q], y[q])));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            x[q] = cmul(x[q], e[q]);
+            y[q] = cmul(y[q], e[q]);
+        }
+        if (!f.manakov) {  // CNLSE: rotation by gamleff*s3/3 around the third Stokes axis (:841-851)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const real s3 = (real)2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
+                const real a3 = R_MUL(gamleff, s3) / (real)3.0;
+                e[q] = nl_small ? pmx_cis_small(a3) : pmx_cis_r(a3);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const cpx ux = x[q], uy = y[q];
+                const real cs = e[q].x, sn = e[q].y;
+                x[q] = mkc(cs * ux.x + sn * uy.x, cs * ux.y + sn * uy.y);
+                y[q] = mkc(cs * uy.x - sn * ux.x, cs * uy.y - sn * ux.y);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Tile walk shared by the three passes (persistent CTAs): tile -> (realization-column bc, group inside it),
 // serpentine direction, skipping finished realizations.
 struct PmxWalk {
@@ -536,55 +598,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
 #endif
         PMX_T_MARK(2)
-        // ---- nonlinear step, fiber.m:832-851
-        if (f.scalar_field) {  // nl_step (fiber.m:786-803): u .* fastexp(-gam.*pow*leff), Y absent
-            if (f.spm || f.xpm) {
-                const real ngam = (real)(-f.gam[col]), leff = (real)st->leff;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    real pw = R_ADD(R_MUL(x[q].x, x[q].x), R_MUL(x[q].y, x[q].y));
-                    if (f.xpm) {  // y.x holds sum(pow,2) of this sample (pmx_k_xpm_sum)
-                        const real two_s = R_MUL((real)2, y[q].x);
-                        pw = f.spm ? R_ADD(two_s, -pw) : R_MUL((real)2, R_ADD(y[q].x, -pw));
-                    }
-                    x[q] = cmul(x[q], pmx_cis_r(R_MUL(R_MUL(ngam, pw), leff)));
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) y[q] = mkc((real)0, (real)0);
-        } else if (f.spm) {
-            const real gamleff = (real)__dmul_rn(f.gam[col], st->leff);
-            const real ngl = -gamleff;
-            const bool nl_small = (st->bmode & PMX_BM_NL_SMALL) != 0;  // uniform for the tile
-            cpx e[8];
-            if (nl_small) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) e[q] = pmx_cis_small(R_MUL(ngl, power_ref(x[q], y[q])));
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) e[q] = pmx_cis_r(R_MUL(ngl, power_ref(x[q], y[q])));
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                x[q] = cmul(x[q], e[q]);
-                y[q] = cmul(y[q], e[q]);
-            }
-            if (!f.manakov) {  // CNLSE: rotation by gamleff*s3/3 around the third Stokes axis (:841-851)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const real s3 = (real)2.0 * (x[q].x * y[q].y - x[q].y * y[q].x);
-                    const real a3 = R_MUL(gamleff, s3) / (real)3.0;
-                    e[q] = nl_small ? pmx_cis_small(a3) : pmx_cis_r(a3);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const cpx ux = x[q], uy = y[q];
-                    const real cs = e[q].x, sn = e[q].y;
-                    x[q] = mkc(cs * ux.x + sn * uy.x, cs * ux.y + sn * uy.y);
-                    y[q] = mkc(cs * uy.x - sn * ux.x, cs * uy.y - sn * ux.y);
-                }
-            }
-        }
+        pmx_nl_step(x, y, st, f, col);   // ---- nonlinear step, fiber.m:832-851
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
@@ -737,6 +751,234 @@ __device__ __forceinline__ void pmx_b_common(cpx (&x)[8], cpx (&y)[8], cpx E, cp
 }
 #endif
 
+// ---------------------------------------------------------------------------
+// The linear step on the eight bins a thread holds after a forward transform (matrix_step, fiber.m:907-933, and
+// lin_step on the scalar path): entry basis change, the step's trunks, exit basis change, common phase.  The bins
+// are k = k1 + N1*(t + q*T) (q = 0..7) of a length-N spectrum: pass B calls it with the four-step split of the
+// field, the single-CTA kernel of small fields with N1 = 1, k1 = 0.  All threads of the CTA must call it together
+// (steps with more trunks than the package holds reload plate chunks behind __syncthreads).
+//   scr / scr_stride : the thread's pre-evaluated phasors (pmx_b_pre), FP64 scalar dispersion mode
+//   schunk           : shared buffer of PMX_PKG_PLATES plates
+template <bool SC, bool PRE>
+__device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const StepPkg* st, const FiberConst& f,
+                                                const PassParams& p, const cpx* scr, int scr_stride, PlateConst* schunk,
+                                                int b, int col, int k1, int t, int T, size_t N, double fn0, double fn4,
+                                                double dfn, bool any_full) {
+    constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
+    const int ntrunk = st->ntrunk, bmode = st->bmode;
+    (void)scr;
+    (void)scr_stride;
+    (void)fn0;
+    (void)dfn;
+        const double dz_cur = st->dz_cur;
+#ifndef PMX_F32
+        // scalar phase common to both polarizations collected over the trunks: conj(Bacc) * conj(Gacc)^j
+        cpx Bacc = mkc(1.0, 0.0), Gacc = mkc(1.0, 0.0);
+#endif
+        if (f.pmd) {
+            const double lcorr = f.lcorr, dzb_first = st->dzb_first, dzb_last = st->dzb_last;
+            if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
+            // whole trunks share exp(-i*db1/2) per bin
+            double d1[(SC) ? 1 : 8];
+            cpx e1[(SC) ? 1 : 8];
+            // scalar mode: phases of the step's first / last trunk at the thread's lowest bin; db1 is linear
+            // in omega, so the other bins follow by a geometric progression (pmx_b_diag)
+#ifdef PMX_F32
+            cpx pf0, pl0, pf4, pl4;  // FP32: g^4 in float would cost 2e-7 of phase per trunk; evaluate both base bins
+            // FP32: the whole-trunk factor exp(-i*db1/2) of a bin is the same for every whole trunk of the
+            // step, so a float-rounded copy (or a float progression) would repeat the SAME phase error in
+            // each of up to nplates factors.  It is kept in double; each trunk's exp(-i*(db1+db0)/2) is
+            // formed in double and rounded once, which makes the per-trunk errors independent.
+            double2 Ed[8];
+#else
+            cpx E0b, pfb, plb, pprev = mkc(1.0, 0.0);
+#endif
+            if constexpr (SC) {
+#ifdef PMX_F32
+                const double d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
+                const double d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
+                if (any_full) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;
+                        pmx_sincos_fast(-0.5 * __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn)), &Ed[q].y, &Ed[q].x);
+                    }
+                }
+                // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
+                // independent and interleave
+                const double db0f = st->plates[0].db0, db0l = st->db0_last;
+                pf0 = pmx_cis(-(0.5 * (d10 + db0f) * dzb_first / lcorr));
+                pl0 = pmx_cis(-(0.5 * (d10 + db0l) * dzb_last / lcorr));
+                pf4 = pmx_cis(-(0.5 * (d14 + db0f) * dzb_first / lcorr));
+                pl4 = pmx_cis(-(0.5 * (d14 + db0l) * dzb_last / lcorr));
+#else
+                E0b = scr[3 * scr_stride];
+                pfb = scr[4 * scr_stride];
+                plb = scr[5 * scr_stride];
+#endif
+            } else {
+                const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
+                if (any_full) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+#ifdef PMX_F32
+                        pmx_sincos_fast(-0.5 * d1[q], &Ed[q].y, &Ed[q].x);
+#else
+                        e1[q] = pmx_cis(-0.5 * d1[q]);
+#endif
+                    }
+                }
+            }
+            for (int k0 = 0; k0 < ntrunk; k0 += PMX_PKG_PLATES) {
+                const PlateConst* pl = st->plates;
+                if (k0 > 0) {  // more trunks than the package holds (one-step 'gp--' runs): next chunk
+                    __syncthreads();
+                    const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + st->n_first + k0;
+                    const int n = ((ntrunk - k0) < PMX_PKG_PLATES ? (ntrunk - k0) : PMX_PKG_PLATES) * PLD;
+                    const double* s_ = reinterpret_cast<const double*>(plg);
+                    double* d_ = reinterpret_cast<double*>(schunk);
+                    for (int i = threadIdx.x; i < n; i += blockDim.x) d_[i] = __ldg(&s_[i]);
+                    __syncthreads();
+                    pl = schunk;
+                }
+                const int kend = (ntrunk - k0) < PMX_PKG_PLATES ? ntrunk : k0 + PMX_PKG_PLATES;
+                for (int k = k0; k < kend; ++k) {
+                    const PlateConst& P = pl[k - k0];
+                    const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
+                    if constexpr (SC) {
+#ifdef PMX_F32
+                        if (dzb == lcorr) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const cpx e = mkc((real)(Ed[q].x * P.h0r - Ed[q].y * P.h0i), (real)(Ed[q].x * P.h0i + Ed[q].y * P.h0r));
+                                x[q] = cmul(x[q], e);
+                                y[q] = cmulc(y[q], e);
+                            }
+                            if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);
+                            continue;
+                        }
+                        {   // partial trunk: bins 1..3 are e0*g^q, bins 5..7 e4*g^(q-4)
+                            const cpx e0 = (k == 0) ? pf0 : pl0, e4 = (k == 0) ? pf4 : pl4;
+                            const cpx g = (k == 0) ? mkc((real)st->gpf_r, (real)st->gpf_i) : mkc((real)st->gpl_r, (real)st->gpl_i);
+                            const cpx g2 = cmul(g, g);
+                            const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
+                            const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
+                            x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
+                            x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
+                            x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
+                            x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
+                            x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
+                            x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
+                            x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
+                            x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
+                        }
+#else
+                        {
+                            cpx b, g, g2, g4;
+                            if (dzb == lcorr) {  // whole trunk: exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
+                                b = cmul(E0b, mkc(P.h0r, P.h0i));
+                                g = mkc(f.g1r, f.g1i);
+                                g2 = mkc(f.g2r, f.g2i);
+                                g4 = mkc(f.g4r, f.g4i);
+                            } else if (k == 0) {  // partial trunk (first or last of the step)
+                                b = pfb;
+                                g = mkc(st->gpf_r, st->gpf_i);
+                                g2 = mkc(st->gpf2[0], st->gpf2[1]);
+                                g4 = mkc(st->gpf4[0], st->gpf4[1]);
+                            } else {
+                                b = plb;
+                                g = mkc(st->gpl_r, st->gpl_i);
+                                g2 = mkc(st->gpl2[0], st->gpl2[1]);
+                                g4 = mkc(st->gpl4[0], st->gpl4[1]);
+                            }
+                            b = cmul(b, pprev);          // left phase of the boundary matrix just applied
+                            Bacc = cmul(Bacc, b);
+                            Gacc = cmul(Gacc, g);
+                            pmx_b_diag2(x, cmul(b, b), g2, g4);
+                            if (k < ntrunk - 1) {        // basis change matR(n+1)' * matR(n) = diag(p, p*) * K
+                                pmx_b_applyK(x, y, P.ka, P.kbr, P.kbi);
+                                pprev = mkc(P.pr, P.pi);
+                            }
+                            continue;
+                        }
+#endif
+                    } else {
+                        if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
+                            const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+#ifdef PMX_F32
+                                const cpx e = mkc((real)(Ed[q].x * P.h0r - Ed[q].y * P.h0i), (real)(Ed[q].x * P.h0i + Ed[q].y * P.h0r));
+                                (void)h0;
+#else
+                                const cpx e = cmul(e1[q], h0);
+#endif
+                                x[q] = cmul(x[q], e);
+                                y[q] = cmulc(y[q], e);
+                            }
+                        } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const cpx e = pmx_cis(-(0.5 * (d1[q] + P.db0) * dzb / lcorr));
+                                x[q] = cmul(x[q], e);
+                                y[q] = cmulc(y[q], e);
+                            }
+                        }
+                    }
+                    if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);  // basis change matR(n+1)' * matR(n)
+                }
+            }
+            if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
+        }
+#ifndef PMX_F32
+        if constexpr (PRE) {  // common phase exp(-i*betat*sum(dzb)) (:924,927-928) times the trunks' common scalar
+            // at the anchor bin (j = 4) the collected scalar is conj(Bacc * Gacc^4)
+            const cpx G2 = cmul(Gacc, Gacc);
+            const cpx S4 = cmul(Bacc, cmul(G2, G2));
+            if (f.gvd_any)
+                pmx_b_common(x, y, cmulc(scr[0 * scr_stride], S4), cmulc(scr[1 * scr_stride], Gacc),
+                             scr[2 * scr_stride], mkc(st->gd3_r, st->gd3_i));
+            else if (f.pmd)
+                pmx_b_common(x, y, cconj(S4), cconj(Gacc), mkc(1.0, 0.0), mkc(1.0, 0.0));
+        } else
+#endif
+#ifdef PMX_EXP_NO_COMMON
+        if (false) {
+#else
+        if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
+#endif
+            {
+                double a[8];
+                if constexpr (SC) {  // betat regenerated per bin (:355-356)
+                    const double b1 = f.beta1[col], b2 = f.beta2[col];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
+                        const double w = __dmul_rn(f.w0, fn);
+                        const double w2 = __dmul_rn(w, w);
+                        double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
+                        bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
+                        a[q] = -(bt * dz_cur);
+                    }
+                } else {
+                    const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
+                }
+                cpx e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) e[q] = pmx_cis(a[q]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    x[q] = cmul(x[q], e[q]);
+                    y[q] = cmul(y[q], e[q]);
+                }
+            }
+        }
+}
+
 template <typename R, int L, int G, bool PF, bool SC>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
@@ -759,7 +1001,6 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);      // [0]: tile, [1]: step package
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
     const size_t N = (size_t)p.N1 * p.N2;
-    constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
     PmxWalk wk;
     wk.ltpb = p.log2N1 - pmx_ilog2(G);
     wk.tpb_mask = (1 << wk.ltpb) - 1;
@@ -816,7 +1057,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         cpx x[8], y[8];
         PMX_T_MARK(0)
         pmx_mbar_wait(mbar + 1, phase);
-        const int ntrunk = st->ntrunk, bmode = st->bmode;
+        const int ntrunk = st->ntrunk;
         // Scalar dispersion mode: a thread's bins are k = k1 + N1*(t + q*T): q < 4 on the positive-frequency side,
         // q >= 4 on the negative one, equally spaced by domega; bin 4 lies four spacings BELOW bin 0.
         const long long kb = (long long)k1 + (long long)p.N1 * t;
@@ -857,213 +1098,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
 #else
             if (ntrunk > 0) {
 #endif
-                const double dz_cur = st->dz_cur;
-#ifndef PMX_F32
-                // scalar phase common to both polarizations collected over the trunks: conj(Bacc) * conj(Gacc)^j
-                cpx Bacc = mkc(1.0, 0.0), Gacc = mkc(1.0, 0.0);
-#endif
-                if (f.pmd) {
-                    const double lcorr = f.lcorr, dzb_first = st->dzb_first, dzb_last = st->dzb_last;
-                    if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
-                    // whole trunks share exp(-i*db1/2) per bin
-                    double d1[(SC) ? 1 : 8];
-                    cpx e1[(SC) ? 1 : 8];
-                    // scalar mode: phases of the step's first / last trunk at the thread's lowest bin; db1 is linear
-                    // in omega, so the other bins follow by a geometric progression (pmx_b_diag)
-#ifdef PMX_F32
-                    cpx pf0, pl0, pf4, pl4;  // FP32: g^4 in float would cost 2e-7 of phase per trunk; evaluate both base bins
-                    // FP32: the whole-trunk factor exp(-i*db1/2) of a bin is the same for every whole trunk of the
-                    // step, so a float-rounded copy (or a float progression) would repeat the SAME phase error in
-                    // each of up to nplates factors.  It is kept in double; each trunk's exp(-i*(db1+db0)/2) is
-                    // formed in double and rounded once, which makes the per-trunk errors independent.
-                    double2 Ed[8];
-#else
-                    cpx E0b, pfb, plb, pprev = mkc(1.0, 0.0);
-#endif
-                    if constexpr (SC) {
-#ifdef PMX_F32
-                        const double d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
-                        const double d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
-                        if (any_full) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;
-                                pmx_sincos_fast(-0.5 * __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn)), &Ed[q].y, &Ed[q].x);
-                            }
-                        }
-                        // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
-                        // independent and interleave
-                        const double db0f = st->plates[0].db0, db0l = st->db0_last;
-                        pf0 = pmx_cis(-(0.5 * (d10 + db0f) * dzb_first / lcorr));
-                        pl0 = pmx_cis(-(0.5 * (d10 + db0l) * dzb_last / lcorr));
-                        pf4 = pmx_cis(-(0.5 * (d14 + db0f) * dzb_first / lcorr));
-                        pl4 = pmx_cis(-(0.5 * (d14 + db0l) * dzb_last / lcorr));
-#else
-                        E0b = scr[3 * S::THREADS];
-                        pfb = scr[4 * S::THREADS];
-                        plb = scr[5 * S::THREADS];
-#endif
-                    } else {
-                        const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) d1[q] = __ldg(&d1p[t + q * T]);
-                        if (any_full) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-#ifdef PMX_F32
-                                pmx_sincos_fast(-0.5 * d1[q], &Ed[q].y, &Ed[q].x);
-#else
-                                e1[q] = pmx_cis(-0.5 * d1[q]);
-#endif
-                            }
-                        }
-                    }
-                    for (int k0 = 0; k0 < ntrunk; k0 += PMX_PKG_PLATES) {
-                        const PlateConst* pl = st->plates;
-                        if (k0 > 0) {  // more trunks than the package holds (one-step 'gp--' runs): next chunk
-                            __syncthreads();
-                            const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + st->n_first + k0;
-                            const int n = ((ntrunk - k0) < PMX_PKG_PLATES ? (ntrunk - k0) : PMX_PKG_PLATES) * PLD;
-                            const double* s_ = reinterpret_cast<const double*>(plg);
-                            double* d_ = reinterpret_cast<double*>(schunk);
-                            for (int i = threadIdx.x; i < n; i += blockDim.x) d_[i] = __ldg(&s_[i]);
-                            __syncthreads();
-                            pl = schunk;
-                        }
-                        const int kend = (ntrunk - k0) < PMX_PKG_PLATES ? ntrunk : k0 + PMX_PKG_PLATES;
-                        for (int k = k0; k < kend; ++k) {
-                            const PlateConst& P = pl[k - k0];
-                            const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
-                            if constexpr (SC) {
-#ifdef PMX_F32
-                                if (dzb == lcorr) {
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const cpx e = mkc((real)(Ed[q].x * P.h0r - Ed[q].y * P.h0i), (real)(Ed[q].x * P.h0i + Ed[q].y * P.h0r));
-                                        x[q] = cmul(x[q], e);
-                                        y[q] = cmulc(y[q], e);
-                                    }
-                                    if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);
-                                    continue;
-                                }
-                                {   // partial trunk: bins 1..3 are e0*g^q, bins 5..7 e4*g^(q-4)
-                                    const cpx e0 = (k == 0) ? pf0 : pl0, e4 = (k == 0) ? pf4 : pl4;
-                                    const cpx g = (k == 0) ? mkc((real)st->gpf_r, (real)st->gpf_i) : mkc((real)st->gpl_r, (real)st->gpl_i);
-                                    const cpx g2 = cmul(g, g);
-                                    const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
-                                    const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
-                                    x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
-                                    x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
-                                    x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
-                                    x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
-                                    x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
-                                    x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
-                                    x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
-                                    x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
-                                }
-#else
-                                {
-                                    cpx b, g, g2, g4;
-                                    if (dzb == lcorr) {  // whole trunk: exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
-                                        b = cmul(E0b, mkc(P.h0r, P.h0i));
-                                        g = mkc(f.g1r, f.g1i);
-                                        g2 = mkc(f.g2r, f.g2i);
-                                        g4 = mkc(f.g4r, f.g4i);
-                                    } else if (k == 0) {  // partial trunk (first or last of the step)
-                                        b = pfb;
-                                        g = mkc(st->gpf_r, st->gpf_i);
-                                        g2 = mkc(st->gpf2[0], st->gpf2[1]);
-                                        g4 = mkc(st->gpf4[0], st->gpf4[1]);
-                                    } else {
-                                        b = plb;
-                                        g = mkc(st->gpl_r, st->gpl_i);
-                                        g2 = mkc(st->gpl2[0], st->gpl2[1]);
-                                        g4 = mkc(st->gpl4[0], st->gpl4[1]);
-                                    }
-                                    b = cmul(b, pprev);          // left phase of the boundary matrix just applied
-                                    Bacc = cmul(Bacc, b);
-                                    Gacc = cmul(Gacc, g);
-                                    pmx_b_diag2(x, cmul(b, b), g2, g4);
-                                    if (k < ntrunk - 1) {        // basis change matR(n+1)' * matR(n) = diag(p, p*) * K
-                                        pmx_b_applyK(x, y, P.ka, P.kbr, P.kbi);
-                                        pprev = mkc(P.pr, P.pi);
-                                    }
-                                    continue;
-                                }
-#endif
-                            } else {
-                                if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
-                                    const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-#ifdef PMX_F32
-                                        const cpx e = mkc((real)(Ed[q].x * P.h0r - Ed[q].y * P.h0i), (real)(Ed[q].x * P.h0i + Ed[q].y * P.h0r));
-                                        (void)h0;
-#else
-                                        const cpx e = cmul(e1[q], h0);
-#endif
-                                        x[q] = cmul(x[q], e);
-                                        y[q] = cmulc(y[q], e);
-                                    }
-                                } else {  // partial trunk: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const cpx e = pmx_cis(-(0.5 * (d1[q] + P.db0) * dzb / lcorr));
-                                        x[q] = cmul(x[q], e);
-                                        y[q] = cmulc(y[q], e);
-                                    }
-                                }
-                            }
-                            if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);  // basis change matR(n+1)' * matR(n)
-                        }
-                    }
-                    if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
-                }
-#ifndef PMX_F32
-                if constexpr (PRE) {  // common phase exp(-i*betat*sum(dzb)) (:924,927-928) times the trunks' common scalar
-                    // at the anchor bin (j = 4) the collected scalar is conj(Bacc * Gacc^4)
-                    const cpx G2 = cmul(Gacc, Gacc);
-                    const cpx S4 = cmul(Bacc, cmul(G2, G2));
-                    if (f.gvd_any)
-                        pmx_b_common(x, y, cmulc(scr[0 * S::THREADS], S4), cmulc(scr[1 * S::THREADS], Gacc),
-                                     scr[2 * S::THREADS], mkc(st->gd3_r, st->gd3_i));
-                    else if (f.pmd)
-                        pmx_b_common(x, y, cconj(S4), cconj(Gacc), mkc(1.0, 0.0), mkc(1.0, 0.0));
-                } else
-#endif
-#ifdef PMX_EXP_NO_COMMON
-                if (false) {
-#else
-                if (f.gvd_any) {  // common phase exp(-i*betat*sum(dzb))  (:924,927-928)
-#endif
-                    {
-                        double a[8];
-                        if constexpr (SC) {  // betat regenerated per bin (:355-356)
-                            const double b1 = f.beta1[col], b2 = f.beta2[col];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;  // exact
-                                const double w = __dmul_rn(f.w0, fn);
-                                const double w2 = __dmul_rn(w, w);
-                                double bt = __dadd_rn(__dmul_rn(w, b1), __dmul_rn(__dmul_rn(0.5, w2), b2));
-                                bt = __dadd_rn(bt, __dmul_rn(__dmul_rn(w2, w), f.b30_6));
-                                a[q] = -(bt * dz_cur);
-                            }
-                        } else {
-                            const double* bt = p.betat_p + (size_t)col * N + (size_t)k1 * p.N2;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) a[q] = -(__ldg(&bt[t + q * T]) * dz_cur);
-                        }
-                        cpx e[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) e[q] = pmx_cis(a[q]);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            x[q] = cmul(x[q], e[q]);
-                            y[q] = cmul(y[q], e[q]);
-                        }
-                    }
-                }
+                pmx_linear_bins<SC, PRE>(x, y, st, f, p, scr, S::THREADS, schunk, b, col, k1, t, T, N, fn0, fn4, dfn, any_full);
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {

@@ -28,6 +28,11 @@ struct PmxLaunchTable {
     void (*fill_tw4)(void* tab, int rows, double two_over_N, cudaStream_t s);
     // scalar XPM: sum over the columns of |u|^2 per sample, written to the Y slot of every column (grid.y = realizations)
     void (*xpm_sum)(dim3 grid, cudaStream_t s, const PassParams& p, const FiberConst& f);
+    // small fields (nfft == L <= 4096): the whole fiber in one launch, one CTA per realization-column, the nfc CTAs of a
+    // realization in one thread-block cluster (pmx_onchip.cuh)
+    size_t smemOnchip;
+    cudaError_t (*onchip_setup)();
+    cudaError_t (*onchip)(int nfc, int batch, cudaStream_t s, const PassParams& p, const FiberConst& f);
 };
 
 const PmxLaunchTable* pmx_get_table(int L, int precision = 0);  // nullptr if L is not built

@@ -1,6 +1,7 @@
 // Instantiates the pass kernels for one in-CTA FFT length (-DPMX_L=<L>) in one precision
 // (FP64, or FP32 with -DPMX_F32) and exports their launchers through a PmxLaunchTable.
 #include "pmx_kernels.cuh"
+#include "pmx_onchip.cuh"
 #include "pmx_launch.h"
 
 #ifndef PMX_L
@@ -97,6 +98,30 @@ void fill_tw4(void* tab, int rows, double two_over_N, cudaStream_t s) {
     pmx_k_fill_tw4<<<blocks, 256, 0, s>>>(reinterpret_cast<cpx*>(tab), rows, PmxTw4<L>::LO, PmxTw4<L>::PER, PmxTw4<L>::PER,
                                           two_over_N);
 }
+// ---- single-CTA kernel of small fields
+using SO = OnchipSmem<L>;
+constexpr int ONCHIP_THREADS = (L / 8) < 32 ? 32 : (L / 8);
+cudaError_t onchip_setup() {
+    cudaError_t e = cudaFuncSetAttribute(pmx_k_onchip<real, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SO::TOTAL);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pmx_k_onchip<real, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SO::TOTAL);
+}
+cudaError_t onchip(int nfc, int batch, cudaStream_t s, const PassParams& p, const FiberConst& f) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nfc, batch);
+    cfg.blockDim = dim3(ONCHIP_THREADS);
+    cfg.dynamicSmemBytes = SO::TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;   // the columns of a realization exchange maxima / powers through DSMEM
+    at[0].val.clusterDim.x = nfc;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = nfc > 1 ? 1 : 0;
+    if (f.disp_scalar) return cudaLaunchKernelEx(&cfg, pmx_k_onchip<real, L, true>, p, f);
+    return cudaLaunchKernelEx(&cfg, pmx_k_onchip<real, L, false>, p, f);
+}
 }  // namespace
 
 #define PMX_CAT2(a, b) a##b
@@ -109,4 +134,4 @@ void fill_tw4(void* tab, int rows, double two_over_N, cudaStream_t s) {
 extern const PmxLaunchTable PMX_TABLE_NAME = {
     L, GAC, GB, PFAC ? 1 : 0, PFB ? 1 : 0, SA::THREADS, SB::THREADS, (size_t)SA::TOTAL, (size_t)SB::TOTAL,
     pmx_tw_total(L), pmx_tw_layout(L), PmxTw4<L>::LO, PmxTw4<L>::PER, PMX_PRECISION, (int)sizeof(cpx),
-    setup, passA, passB, passC, init_max, fill_tw4, xpm_sum};
+    setup, passA, passB, passC, init_max, fill_tw4, xpm_sum, (size_t)SO::TOTAL, onchip_setup, onchip};

@@ -74,7 +74,7 @@ def test_oracle_matches_reference_source(name):
         assert orc.rel_l2(gs.FIELDX, gs.FIELDY, z['amp_FIELDX'], z['amp_FIELDY']) < 1e-14
 
 
-VECTOR_CASES = [c for c in CASES if not c.startswith('scalar_')]
+VECTOR_CASES = [c for c in CASES if load(c)[1]['two_pol']]
 
 
 @pytest.mark.gpu
@@ -96,7 +96,7 @@ def test_cuda_matches_reference_source(name):
         assert orc.rel_l2(G.FIELDX, G.FIELDY, z['amp_FIELDX'], z['amp_FIELDY']) < 1e-10
 
 
-SCALAR_CASES = [c for c in CASES if c.startswith('scalar_')]
+SCALAR_CASES = [c for c in CASES if not load(c)[1]['two_pol']]
 
 
 @pytest.mark.gpu

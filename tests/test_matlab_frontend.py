@@ -139,7 +139,8 @@ def _gpu_interp(seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['manakov_100plates_80km', 'cnlse_10plates_100km', 'sep3_manakov', 'pmf_single', 'scalar_gs',
-                                  'scalar_sep3_gsx', 'scalar_ltol_gs', 'scalar_dphiadapt_sep3_gsx', 'cnlse_nopmd'])
+                                  'scalar_sep3_gsx', 'scalar_ltol_gs', 'scalar_dphiadapt_sep3_gsx', 'cnlse_nopmd',
+                                  'small_ex06_gsx_2e10', 'small_ex10_sep5_gsx_2e11', 'small_2pol_cnlse_2e9'])
 def test_interpreted_front_end_on_the_device(name):
     """matlab/fiber.m interpreted, its ssfm_mex the compiled gateway on the GPU: all three dispatches (matrix_ssfm,
     scalar_ssfm, scalar_a_ssfm) against the interpreted original's goldens, FP64 <= 1e-10"""
