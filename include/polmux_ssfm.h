@@ -205,6 +205,11 @@ int pmx_ampliflat_exec(pmx_ctx* ctx, pmx_devfield* f, double gain, const double*
  * asepol = 1 (X), 2 (Y), 3 (both = pmx_ampliflat_exec). */
 int pmx_ampliflat_exec_pol(pmx_ctx* ctx, pmx_devfield* f, double gain, const double* sigma,
                            const double* noise_host, uint64_t seed, int32_t asepol);
+/* ... for a batch whose first realization has the global index realization0: the generator is keyed by
+ * (seed, realization0 + b, column, sample), so the noise of a realization does not depend on how a Monte-Carlo run
+ * groups or shards its realizations. */
+int pmx_ampliflat_exec_at(pmx_ctx* ctx, pmx_devfield* f, double gain, const double* sigma, const double* noise_host,
+                          uint64_t seed, int32_t asepol, uint64_t realization0);
 
 /* ---- span loop: nspan x [ fiber ; ampliflat ] without returning to the host ---------------
  * The loop every multi-span script of the reference writes around its in-line devices
@@ -223,6 +228,8 @@ typedef struct pmx_link_desc {
     const double* noise;     /* NULL: device generator keyed by seeds[k]; else HOST [nspan][batch][2*nfc][nfft]   */
                              /* complex standard normals, options.noise of span k (ampliflat.m:123-129)            */
     const uint64_t* seeds;   /* [nspan] ASE seed of every span, or NULL: seed k                                   */
+    uint64_t realization0;   /* global index of the batch's first realization (device generator key, see          */
+                             /* pmx_ampliflat_exec_at); 0 for a stand-alone link                                   */
 } pmx_link_desc;
 /* Resident form.  out (may be NULL): arrays of nspan*batch entries, span-major ([k*batch + b]); no trace. */
 int pmx_link_exec(pmx_plan* plan, pmx_devfield* f, const pmx_link_desc* link, pmx_fiber_result* out);
@@ -261,6 +268,38 @@ int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pa
  * counts_dev: DEVICE pointer to [batch] int64 (e.g. the NCCL send buffer), overwritten. */
 int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t nsymb, int32_t nt,
                    int64_t* counts_dev);
+
+/* ---- Monte-Carlo over independent realizations on the GPUs of one node (BASELINE config C5) ------------------------
+ * The `while cond` loop of ex20_coherent_polmux.m:131-181 with its realizations sharded over several GPUs from ONE
+ * process: contiguous realization groups per GPU (rank g owns [g*nreal/ndev, (g+1)*nreal/ndev)), one host thread and
+ * one context per GPU, every realization = nspan x [fiber ; ampliflat] on the resident batch, optionally the ideal
+ * linear equaliser (GVD and PMD of every span undone with the known plates, cf. inverse_pmd.m:100-124), then the
+ * error counter (pmx_qpsk_count) writing into the rank's slice of a zero-initialised [nreal] int64 vector and ONE
+ * ncclAllReduce(sum) over NVLink.  NCCL is bound at run time (libnccl.so.2); with a single GPU it is optional.
+ * The caller replays ber_estimate's recursion (ber_estimate.m:121-127) over counts[] in realization order. */
+typedef struct pmx_mc_desc {
+    int32_t ndev;                /* GPUs of this node to shard over                                          */
+    const int32_t* device_ids;   /* [ndev]                                                                   */
+    int32_t nreal;               /* realizations in total                                                     */
+    int32_t batch;               /* realizations resident per GPU at a time                                   */
+    int32_t nspan;
+    int32_t equalize;            /* 1: ideal linear equaliser before the decision                             */
+    const double* db0;           /* [nspan][nreal][nplates] plate draws (fiber.m:274-276), host; NULL without 'p' */
+    const double* theta;
+    const double* epsilon;
+    double gain;                 /* linear power gain of the amplifier after every span; 0: none              */
+    const double* sigma;         /* [nfc] ASE sigma per column or NULL                                        */
+    uint64_t ase_seed;           /* span k uses the seed ((ase_seed & 0xffffff) << 40) + (k << 32), keyed by the     */
+                                 /* global realization index (pmx_ampliflat_exec_at)                          */
+    const uint8_t* sym;          /* [2][nsymb] transmitted QPSK symbol indices (pmx_qpsk_count)               */
+    int32_t nsymb, nt;
+} pmx_mc_desc;
+/* fiber: the span's fiber (batch / plate_sets / plates are taken from mc); tx: HOST Tx field of one realization;
+ * counts: [nreal] bit errors per realization; sa_steps (may be NULL): sum over all realizations of nfft*nfc*ncycle;
+ * errbuf (may be NULL): message of the first failure. */
+int pmx_mc_run(const pmx_fiber_desc* fiber, const pmx_mc_desc* mc, const pmx_field* tx, int64_t* counts,
+               int64_t* sa_steps, char* errbuf, int32_t errlen);
+int pmx_mc_nccl_available(void);
 
 /* ---- building blocks of the local-error adaptive step (scalar path only) -------------------------
  * scalar_a_ssfm / adaptssfm, fiber.m:639-679,938-1010: one symmetric step against two half steps, local error

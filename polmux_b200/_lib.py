@@ -30,7 +30,8 @@ EXPORTS = [
     'pmx_ctx_launch_count', 'pmx_ampliflat_exec', 'pmx_count_errors', 'pmx_ctx_profile',
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
-    'pmx_host_is_pinned', 'pmx_scalar_adaptive_run',
+    'pmx_host_is_pinned', 'pmx_scalar_adaptive_run', 'pmx_mc_run', 'pmx_mc_nccl_available',
+    'pmx_ampliflat_exec_at',
 ]
 
 
@@ -67,9 +68,17 @@ class FiberResult(C.Structure):
                 ('trace_dz', _dp), ('trace_ntrunk', _ip), ('trace_cap', C.c_int32)]
 
 
+class McDesc(C.Structure):
+    _fields_ = [('ndev', C.c_int32), ('device_ids', C.POINTER(C.c_int32)), ('nreal', C.c_int32), ('batch', C.c_int32),
+                ('nspan', C.c_int32), ('equalize', C.c_int32), ('db0', _dp), ('theta', _dp), ('epsilon', _dp),
+                ('gain', C.c_double), ('sigma', _dp), ('ase_seed', C.c_uint64), ('sym', C.POINTER(C.c_uint8)),
+                ('nsymb', C.c_int32), ('nt', C.c_int32)]
+
+
 class LinkDesc(C.Structure):
     _fields_ = [('nspan', C.c_int32), ('plate_sets', C.c_int32), ('db0', _dp), ('theta', _dp), ('epsilon', _dp),
-                ('gain', C.c_double), ('sigma', _dp), ('noise', _dp), ('seeds', C.POINTER(C.c_uint64))]
+                ('gain', C.c_double), ('sigma', _dp), ('noise', _dp), ('seeds', C.POINTER(C.c_uint64)),
+                ('realization0', C.c_uint64)]
 
 
 _lib = None
@@ -114,6 +123,8 @@ def load():
     lib.pmx_plan_set_plates.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     lib.pmx_fiber_exec.argtypes = [vp, vp, C.POINTER(FiberResult)]
     lib.pmx_host_is_pinned.argtypes = [vp]
+    lib.pmx_mc_run.argtypes = [C.POINTER(FiberDesc), C.POINTER(McDesc), C.POINTER(Field), C.POINTER(C.c_int64),
+                               C.POINTER(C.c_int64), C.c_char_p, C.c_int32]
     lib.pmx_scalar_adaptive_run.argtypes = [vp, C.POINTER(FiberDesc), C.c_double, C.c_double, C.c_int32, C.POINTER(Field),
                                             C.POINTER(FiberResult)]
     lib.pmx_ampliflat_exec.argtypes = [vp, vp, C.c_double, _dp, _dp, C.c_uint64]
@@ -386,12 +397,13 @@ class Plan:
             pass
 
 
-def make_link(nspan, gain=0.0, sigma=None, plates=None, plate_sets=1, noise=None, seeds=None):
+def make_link(nspan, gain=0.0, sigma=None, plates=None, plate_sets=1, noise=None, seeds=None, first=0):
     """-> (LinkDesc, keep-alive dict).  plates: (db0, theta, epsilon) each [nspan][plate_sets][nplates] or None;
     noise: [nspan][batch][2*nfc][nfft] complex128 or None; seeds: [nspan] ints or None."""
     keep = {}
     l = LinkDesc()
     l.nspan, l.plate_sets, l.gain = int(nspan), int(plate_sets), float(gain)
+    l.realization0 = int(first)          # global index of the batch's first realization (ASE generator key)
     if plates is not None:
         for name, a in zip(('db0', 'theta', 'epsilon'), plates):
             keep[name] = _f64(a).reshape(-1)

@@ -1250,6 +1250,8 @@ struct AmpParams {
     int nfc, batch;
     int l1, l2;        // field layout: time sample n1*N2 + n2 at n2*N1 + n1 (log2 N1, log2 N2; 0/0 = natural order)
     int asepol;        // bit 0: ASE on X, bit 1: ASE on Y (options.onepol, ampliflat.m:107-118)
+    unsigned b0;       // global index of the batch's first realization: the generator is keyed by the realization, so a
+                       // Monte-Carlo run draws the same noise however its realizations are grouped or sharded
 };
 
 template <typename T2>  // the gain and the noise are evaluated in double in both field precisions
@@ -1267,7 +1269,7 @@ __global__ void __launch_bounds__(256) pmx_k_ampliflat(AmpParams a) {
                 ny = a.noise[((size_t)b * 2 * a.nfc + a.nfc + col) * a.N + n];
             } else {
                 uint32_t r[4];
-                philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)col, (uint32_t)b, (uint32_t)a.seed,
+                philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)col, (uint32_t)b + a.b0, (uint32_t)a.seed,
                               (uint32_t)(a.seed >> 32), r);
                 nx = pmx_cnormal(r[0], r[1]);
                 ny = pmx_cnormal(r[2], r[3]);
@@ -1288,6 +1290,10 @@ extern "C" int pmx_ampliflat_exec(pmx_ctx* c, pmx_devfield* f, double gain, cons
 }
 extern "C" int pmx_ampliflat_exec_pol(pmx_ctx* c, pmx_devfield* f, double gain, const double* sigma,
                                       const double* noise_host, uint64_t seed, int32_t asepol) {
+    return pmx_ampliflat_exec_at(c, f, gain, sigma, noise_host, seed, asepol, 0);
+}
+extern "C" int pmx_ampliflat_exec_at(pmx_ctx* c, pmx_devfield* f, double gain, const double* sigma, const double* noise_host,
+                                     uint64_t seed, int32_t asepol, uint64_t realization0) {
     if (!c || !f) return set_err(c, PMX_ERR_INVALID, "pmx_ampliflat_exec: null argument");
     if (!(gain > 0)) return set_err(c, PMX_ERR_INVALID, "gain must be > 0");
     CK(c, cudaSetDevice(c->device));
@@ -1299,6 +1305,7 @@ extern "C" int pmx_ampliflat_exec_pol(pmx_ctx* c, pmx_devfield* f, double gain, 
     if (asepol < 1 || asepol > 3) return set_err(c, PMX_ERR_INVALID, "asepol must be 1 (X), 2 (Y) or 3 (both)");
     a.asepol = asepol;
     a.seed = seed;
+    a.b0 = (unsigned)realization0;
     a.N = (size_t)f->nfft;
     a.nfc = f->nfc;
     a.batch = f->batch;
@@ -1452,9 +1459,9 @@ extern "C" int pmx_link_exec(pmx_plan* p, pmx_devfield* f, const pmx_link_desc* 
         rc = pmx_fiber_exec(p, f, &r);
         if (rc != PMX_OK) return rc;
         if (l->gain > 0) {
-            rc = pmx_ampliflat_exec(c, f, l->gain, l->sigma ? l->sigma : zeros.data(),
-                                    l->noise ? l->noise + (size_t)k * noise_span : nullptr,
-                                    l->seeds ? l->seeds[k] : (uint64_t)k);
+            rc = pmx_ampliflat_exec_at(c, f, l->gain, l->sigma ? l->sigma : zeros.data(),
+                                       l->noise ? l->noise + (size_t)k * noise_span : nullptr,
+                                       l->seeds ? l->seeds[k] : (uint64_t)k, 3, l->realization0);
             if (rc != PMX_OK) return rc;
         }
     }

@@ -75,14 +75,17 @@ class Link:
                                                         for k in range(self.nspan)])
         link, keep = _lib.make_link(
             self.nspan, self.gain, self.sigma, plates=[np.stack([pl[i] for pl in self.plates]) for i in range(3)],
-            plate_sets=self.batch, noise=noise, seeds=[self.ase_seed(ase_seed, k) for k in range(self.nspan)])
+            plate_sets=self.batch, noise=noise, seeds=[self.ase_seed(ase_seed, k) for k in range(self.nspan)],
+            first=self.first)
         res = self.plan.link_exec(field, link, keep)            # the span loop runs inside the library
         ncyc = res.ncycle.reshape(self.nspan, self.batch)
         self.ncycles = [ncyc[k].copy() for k in range(self.nspan)]
         return int(ncyc.sum()) * n * self.setup.nfc
 
     def ase_seed(self, ase_seed: int, span: int) -> int:
-        return ((int(ase_seed) & 0xffffff) << 40) + (span << 32) + self.first
+        # (the device generator is keyed by the global realization index, pmx_link_desc.realization0: the noise of a
+        # realization does not depend on how the run groups or shards its realizations)
+        return ((int(ase_seed) & 0xffffff) << 40) + (span << 32)
 
     def equalize(self, field: _lib.DeviceField):
         """Ideal linear equaliser: undo GVD and PMD of every span, last span first.  One linear
@@ -219,3 +222,39 @@ def run_mc(ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt
         return r.run(ase_seed)
     finally:
         r.close()
+
+
+def run_mc_native(setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int, gain_db: float, nf_db: float,
+                  nreal: int, batch: int, devices=(0,), ase_seed: int = 1, equalize: bool = True):
+    """The same Monte-Carlo job through pmx_mc_run: one process, one host thread and one context per GPU of `devices`,
+    the integer all-reduce done with NCCL inside the library (no torch.distributed).  Plate draws as run_mc's.
+    -> (counts [nreal] int64, Sa*steps over all realizations)"""
+    import ctypes as C
+    lib = _lib.load()
+    np_ = setup.nplates
+    pl = np.empty((3, nspan, nreal, np_))
+    for k in range(nspan):
+        for r in range(nreal):
+            d = draw_plates(plate_seed(r, k), np_)
+            for i in range(3):
+                pl[i, k, r] = d[i]
+    desc, keep = setup_to_desc(setup, batch=1)
+    gain = 10 ** (gain_db * 0.1)
+    sigma = np.ascontiguousarray(ase_sigma(gain, nf_db, setup.nfc), dtype=np.float64)
+    devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+    symb = np.ascontiguousarray(sym, dtype=np.uint8).reshape(2, nsymb)
+    m = _lib.McDesc()
+    m.ndev, m.device_ids, m.nreal, m.batch, m.nspan, m.equalize = len(devices), devs, int(nreal), int(batch), int(nspan), int(equalize)
+    m.db0, m.theta, m.epsilon = (pl[i].ctypes.data_as(_lib._dp) for i in range(3))
+    m.gain, m.sigma, m.ase_seed = gain, sigma.ctypes.data_as(_lib._dp), int(ase_seed)
+    m.sym, m.nsymb, m.nt = symb.ctypes.data_as(C.POINTER(C.c_uint8)), int(nsymb), int(nt)
+    fx = np.ascontiguousarray(np.asarray(tx_x, dtype=np.complex128).T)[None]
+    fy = np.ascontiguousarray(np.asarray(tx_y, dtype=np.complex128).T)[None]
+    io = _lib.complex_field(fx, fy)
+    counts = np.zeros(nreal, dtype=np.int64)
+    sa = C.c_int64(0)
+    err = C.create_string_buffer(512)
+    rc = lib.pmx_mc_run(C.byref(desc), C.byref(m), C.byref(io), counts.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(sa), err, 512)
+    if rc != 0:
+        raise _lib.PolmuxError(rc, err.value.decode(errors='replace'))
+    return counts, int(sa.value)

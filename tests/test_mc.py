@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 import oracle.fiber_oracle as orc
-from polmux_b200 import mc
+import polmux_b200 as pmx
+from polmux_b200 import mc, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = '/root/reference'
@@ -177,3 +178,36 @@ def test_mc_counts_match_oracle(ctx):
         want.append(errs)
     assert got.tolist() == want
     assert min(want) > 0
+
+
+@pytest.mark.gpu
+def test_native_mc_run_matches_the_torch_driven_path(ctx):
+    """pmx_mc_run (the Monte-Carlo job behind the C ABI: host threads + contexts + NCCL bound at run time inside the
+    library) gives the error counts of mc.run_mc bit for bit, on one GPU and -- when the box has more -- sharded over
+    two with the counts all-reduced by NCCL"""
+    from polmux_b200 import _lib
+    from polmux_b200.fiber import fiber_setup
+    nsymb, nt, nspan, nreal, batch = 1 << 10, 16, 3, 6, 2
+    ex, ey, sx, sy = synth.pdm_qpsk(nsymb, nt, 1)
+    pmx.reset_all(nsymb, nt, 1)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.LAMBDA, G.POWER = 28.0, np.array([1550.0]), np.array([8.0])
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    fib = dict(synth.SMF)
+    fib.update(length=8e4, dgd=0.1, nplates=20, manakov='yes')
+    setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
+    sym = np.stack([sx[:, 0], sy[:, 0]]).astype(np.uint8)
+    ref, sa_ref = mc.run_mc(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 16.0, 18.0, nreal, batch, ase_seed=5)
+    got, sa = mc.run_mc_native(setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 16.0, 18.0, nreal, batch,
+                               devices=(0,), ase_seed=5)
+    assert np.array_equal(got, ref) and sa == sa_ref and ref.sum() > 0
+    assert _lib.load().pmx_mc_nccl_available() == 1
+    # the ASE generator is keyed by the global realization index: another grouping of the same realizations, same counts
+    got3, _ = mc.run_mc_native(setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 16.0, 18.0, nreal, 3,
+                               devices=(0,), ase_seed=5)
+    assert np.array_equal(got3, ref)
+    import torch
+    if torch.cuda.device_count() >= 2:
+        got2, sa2 = mc.run_mc_native(setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 16.0, 18.0, nreal, batch,
+                                     devices=(0, 1), ase_seed=5)
+        assert np.array_equal(got2, ref) and sa2 == sa_ref
