@@ -230,6 +230,8 @@ typedef struct pmx_link_desc {
     const uint64_t* seeds;   /* [nspan] ASE seed of every span, or NULL: seed k                                   */
     uint64_t realization0;   /* global index of the batch's first realization (device generator key, see          */
                              /* pmx_ampliflat_exec_at); 0 for a stand-alone link                                   */
+    int32_t asepol;          /* 0 or 3: ASE on both polarizations; 1: X only, 2: Y only (options.onepol,           */
+    int32_t reserved;        /* ampliflat.m:107-118)                                                               */
 } pmx_link_desc;
 /* Resident form.  out (may be NULL): arrays of nspan*batch entries, span-major ([k*batch + b]); no trace. */
 int pmx_link_exec(pmx_plan* plan, pmx_devfield* f, const pmx_link_desc* link, pmx_fiber_result* out);

@@ -78,7 +78,7 @@ class McDesc(C.Structure):
 class LinkDesc(C.Structure):
     _fields_ = [('nspan', C.c_int32), ('plate_sets', C.c_int32), ('db0', _dp), ('theta', _dp), ('epsilon', _dp),
                 ('gain', C.c_double), ('sigma', _dp), ('noise', _dp), ('seeds', C.POINTER(C.c_uint64)),
-                ('realization0', C.c_uint64)]
+                ('realization0', C.c_uint64), ('asepol', C.c_int32), ('reserved', C.c_int32)]
 
 
 _lib = None
@@ -397,13 +397,14 @@ class Plan:
             pass
 
 
-def make_link(nspan, gain=0.0, sigma=None, plates=None, plate_sets=1, noise=None, seeds=None, first=0):
+def make_link(nspan, gain=0.0, sigma=None, plates=None, plate_sets=1, noise=None, seeds=None, first=0, asepol=3):
     """-> (LinkDesc, keep-alive dict).  plates: (db0, theta, epsilon) each [nspan][plate_sets][nplates] or None;
     noise: [nspan][batch][2*nfc][nfft] complex128 or None; seeds: [nspan] ints or None."""
     keep = {}
     l = LinkDesc()
     l.nspan, l.plate_sets, l.gain = int(nspan), int(plate_sets), float(gain)
     l.realization0 = int(first)          # global index of the batch's first realization (ASE generator key)
+    l.asepol = int(asepol)               # 1: ASE on X only, 2: on Y only, 3: both (options.onepol)
     if plates is not None:
         for name, a in zip(('db0', 'theta', 'epsilon'), plates):
             keep[name] = _f64(a).reshape(-1)

@@ -1461,7 +1461,7 @@ extern "C" int pmx_link_exec(pmx_plan* p, pmx_devfield* f, const pmx_link_desc* 
         if (l->gain > 0) {
             rc = pmx_ampliflat_exec_at(c, f, l->gain, l->sigma ? l->sigma : zeros.data(),
                                        l->noise ? l->noise + (size_t)k * noise_span : nullptr,
-                                       l->seeds ? l->seeds[k] : (uint64_t)k, 3, l->realization0);
+                                       l->seeds ? l->seeds[k] : (uint64_t)k, l->asepol ? l->asepol : 3, l->realization0);
             if (rc != PMX_OK) return rc;
         }
     }

@@ -65,14 +65,6 @@ struct __align__(16) StepCtl {
     int nmem;          // fiber.m:742,748
     int n_first;       // 0-based plate index of trunk k=1:  ntot + 1 - nmem - 1
     int bmode;         // PMX_BM_* : which constant basis changes pass B applies around the trunk product
-    // scalar dispersion mode: per-bin-step factors exp(-i*0.5*dgdrms*domega*dzb/lcorr) of the
-    // first / last (partial) trunk of the step, domega = spacing of a thread's bins
-    double gpf_r, gpf_i, gpl_r, gpl_i;
-    // scalar dispersion mode: exp(-i*dz*b30*domega^3), the constant third difference of the common phase
-    // -betat*dz over a thread's equally spaced bins (pass B builds exp(-i*betat*dz) of its bins by a difference
-    // recurrence from three evaluations instead of one sincos per bin)
-    double gd3_r, gd3_i;
-    double gpf2[2], gpf4[2], gpl2[2], gpl4[2];   // squares and fourth powers of gpf / gpl
     // reduction scratch for nextstep
     unsigned long long umax_bits[PMX_MAX_NFC];  // max over n of |ux|^2+|uy|^2, per column
     unsigned int pad_ticket;

@@ -116,26 +116,7 @@ __device__ __forceinline__ void pmx_ctl_next(StepCtl* c, const FiberConst& f, bo
         c->bmode = PMX_BM_ENTRY_R | PMX_BM_EXIT_R;
     // largest nonlinear phase of the step: gam*leff*max|u|^2 (the CNLSE rotation angle is at most a third of it)
     if (f.spm && !f.xpm && pmax * c->leff < 0.015625) c->bmode |= PMX_BM_NL_SMALL;
-    if (f.disp_scalar && f.pmd) {
-        double s, cs;
-        const double af = -(0.5 * f.dgdrms * f.domega * dzb_first / lcorr), al = -(0.5 * f.dgdrms * f.domega * dzb_last / lcorr);
-        sincos(af, &s, &cs);
-        c->gpf_r = cs;
-        c->gpf_i = s;
-        sincos(al, &s, &cs);
-        c->gpl_r = cs;
-        c->gpl_i = s;
-        sincos(2.0 * af, &c->gpf2[1], &c->gpf2[0]);
-        sincos(4.0 * af, &c->gpf4[1], &c->gpf4[0]);
-        sincos(2.0 * al, &c->gpl2[1], &c->gpl2[0]);
-        sincos(4.0 * al, &c->gpl4[1], &c->gpl4[0]);
-    }
-    if (f.disp_scalar && f.gvd_any) {  // third difference of -betat*dz over bins spaced by domega: -dz*b30*domega^3
-        double s, cs;
-        sincos(-(dz_cur * (6.0 * f.b30_6) * f.domega * f.domega * f.domega), &s, &cs);
-        c->gd3_r = cs;
-        c->gd3_i = s;
-    }
+    // (the per-step phasors gpf, gpl, their powers and gd3 are evaluated by pmx_ctl_step, one thread each)
     if (ntrunk > 0 && (c->ntot + ntrunk - nmem > f.nplates || c->n_first < 0)) {
         c->state = PMX_ST_ERROR;  // brf.theta(n) index error in the reference (fiber.m:910)
         c->err = -4;              // PMX_ERR_PLATE_INDEX
@@ -191,25 +172,30 @@ __device__ __forceinline__ bool pmx_ctl_step(StepCtl* c, StepPkg* g, const PassP
     if (!*s_go) return false;
     const int ntrunk = c->ntrunk, n_first = c->n_first;
     const PlateConst* plg = p.plates + (f.plate_sets > 1 ? (size_t)b * f.nplates : 0) + n_first;
+    // Scalar dispersion mode: the step's phasors, one thread each (seven independent evaluations instead of a serial
+    // chain on thread 0): per-bin-step factors exp(-i*0.5*dgdrms*domega*dzb/lcorr) of the first / last (partial) trunk
+    // with their squares and fourth powers, and exp(-i*dz*b30*domega^3), the third difference of the common phase.
+    if (f.disp_scalar && threadIdx.x >= 8 && threadIdx.x < 15) {
+        const int k = threadIdx.x - 8;
+        const double af = -(0.5 * f.dgdrms * f.domega * c->dzb_first / f.lcorr), al = -(0.5 * f.dgdrms * f.domega * c->dzb_last / f.lcorr);
+        const double a3 = -(c->dz_cur * (6.0 * f.b30_6) * f.domega * f.domega * f.domega);
+        const double arg = (k == 0) ? af : (k == 1) ? al : (k == 2) ? 2.0 * af : (k == 3) ? 4.0 * af : (k == 4) ? 2.0 * al
+                         : (k == 5) ? 4.0 * al : a3;
+        double sn, cs;
+        pmx_sincos_fast(arg, &sn, &cs);
+        double* dst = (k == 0) ? &g->gpf_r : (k == 1) ? &g->gpl_r : (k == 2) ? g->gpf2 : (k == 3) ? g->gpf4 : (k == 4) ? g->gpl2
+                    : (k == 5) ? g->gpl4 : &g->gd3_r;
+        const bool on = (k == 6) ? (f.gvd_any != 0) : (f.pmd != 0);
+        dst[0] = on ? cs : 0.0;
+        dst[1] = on ? sn : 0.0;
+    }
     if (threadIdx.x == 0) {
         g->dz_cur = c->dz_cur;
         g->leff = c->leff;
         g->scale = c->scale;
         g->dzb_first = c->dzb_first;
         g->dzb_last = c->dzb_last;
-        g->gpf_r = c->gpf_r;
-        g->gpf_i = c->gpf_i;
-        g->gpl_r = c->gpl_r;
-        g->gpl_i = c->gpl_i;
         g->db0_last = (f.pmd && ntrunk > 0) ? plg[ntrunk - 1].db0 : 0.0;
-        g->gd3_r = c->gd3_r;
-        g->gd3_i = c->gd3_i;
-        for (int i = 0; i < 2; ++i) {
-            g->gpf2[i] = c->gpf2[i];
-            g->gpf4[i] = c->gpf4[i];
-            g->gpl2[i] = c->gpl2[i];
-            g->gpl4[i] = c->gpl4[i];
-        }
         g->ntrunk = ntrunk;
         g->n_first = n_first;
         g->bmode = f.pmd ? c->bmode : (c->bmode & PMX_BM_NL_SMALL);

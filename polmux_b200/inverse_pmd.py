@@ -19,8 +19,11 @@ from .gstate import GSTATE
 
 def inverse_pmd(brf, options=None, ctx=None):
     G = GSTATE
-    if options:
-        raise NotImplementedError('inverse_pmd options (mat, theta; inverse_pmd.m:73-89) are not built')
+    options = dict(options or {})
+    unknown = set(options) - {'gvd'}
+    if unknown:
+        raise NotImplementedError('inverse_pmd options %s (inverse_pmd.m:73-89) are not built' % sorted(unknown))
+    keep_gvd = str(options.get('gvd', 'yes')) != 'no'          # options.gvd = 'no': PMD only (inverse_pmd.m:79,135)
     brfs = [brf] if isinstance(brf, dict) else list(brf)
     nfr, nfc = G.field_shape()
     if nfc != 1:
@@ -36,7 +39,7 @@ def inverse_pmd(brf, options=None, ctx=None):
         db0 = np.asarray(b['db0'], dtype=np.float64).ravel()
         ntr = th.size
         length = float(b['lcorr']) * ntr
-        betat = -np.asarray(b['betat'], dtype=np.float64).reshape(n, 1)
+        betat = -np.asarray(b['betat'], dtype=np.float64).reshape(n, 1) * (1.0 if keep_gvd else 0.0)
         db1 = -np.asarray(b['db1'], dtype=np.float64).reshape(n, 1)
         inv = FiberSetup(nfft=n, nfc=1, fls=(1, 1, 0, 0), dphimaxt=math.inf, dzmaxt=length, length=length,
                          alphalin=0.0, gam=np.zeros(1), betat=betat, db1=db1, manakov=False, nplates=ntr,

@@ -34,8 +34,12 @@ def link(x, flag: str, nspan: int, gain_db: Optional[float] = None, options=None
     if nspan < 1:
         raise ValueError('nspan must be at least 1')
     options = dict(options or {})
-    if 'onepol' in options:
-        raise NotImplementedError('link: options.onepol goes through ampliflat() (pmx_link_desc carries no polarization mask)')
+    asepol = 3
+    if 'onepol' in options:                                                              # ampliflat.m:107-118
+        pol = str(options['onepol']).lower()
+        if pol not in ('asex', 'asey'):
+            raise ValueError("ONEPOL, if exists, must be 'asex' or 'asey'")
+        asepol = 1 if pol == 'asex' else 2
     setups = [fiber_setup(x, flag, rng) for _ in range(nspan)]          # one plate draw per span, in call order
     s = setups[0]
     if not (s.isv and G.has_y()):
@@ -62,7 +66,7 @@ def link(x, flag: str, nspan: int, gain_db: Optional[float] = None, options=None
     else:
         seeds = [int(seed) + k for k in range(nspan)]
     ldesc, lkeep = _lib.make_link(nspan, gain, sigma, plates=plates, plate_sets=1, noise=noise,
-                                  seeds=seeds)
+                                  seeds=seeds, asepol=asepol)
     fx = np.ascontiguousarray(np.asarray(G.FIELDX, dtype=np.complex128).T)[None]             # [1][nfc][nfft]
     fy = np.ascontiguousarray(np.asarray(G.FIELDY, dtype=np.complex128).T)[None]
     io = _lib.complex_field(fx, fy)

@@ -319,3 +319,34 @@ def test_ampliflat_default_calls_draw_fresh_noise():
     assert np.array_equal(outs[0][0][0], outs[1][0][0]) and np.array_equal(outs[0][1][1], outs[1][1][1])
     d = outs[0][0][0] - outs[0][1][0]
     assert abs(np.vdot(d, d).real / d.size) > 0
+
+
+def test_inverse_pmd_gvd_no_and_link_onepol():
+    """inverse_pmd(brf, options.gvd = 'no') (inverse_pmd.m:79,135) undoes the PMD only: what is left is the pure GVD of
+    the fiber, ifft(fft(u) .* exp(-i*betat*L)); link(..., options.onepol) equals the loop of fiber() / ampliflat() calls"""
+    make_tx(1 << 9, 16)
+    G = pmx.GSTATE
+    tx_x, tx_y = np.array(G.FIELDX), np.array(G.FIELDY)
+    fib = base_fiber(length=5e4, dgd=0.6, nplates=15, alphadB=0.0)
+    brf = pmx.fiber(fib, 'gp--', rng=np.random.Generator(np.random.PCG64(11)))
+    pmx.inverse_pmd(brf, {'gvd': 'no'})
+    ph = np.exp(-1j * brf['betat'][:, 0] * fib['length'])
+    rx = np.fft.ifft(np.fft.fft(tx_x[:, 0]) * ph)
+    ry = np.fft.ifft(np.fft.fft(tx_y[:, 0]) * ph)
+    assert rel_l2(G.FIELDX[:, 0], G.FIELDY[:, 0], rx, ry) < 1e-9
+    with pytest.raises(NotImplementedError):
+        pmx.inverse_pmd(brf, {'mat': np.eye(2)})
+    # link with ASE on one polarization
+    fib = base_fiber(length=2e4, dgd=0.2, nplates=8, manakov='yes')
+    outs = []
+    for use_link in (True, False):
+        make_tx(1 << 9, 16)
+        rng = np.random.Generator(np.random.PCG64(3))
+        if use_link:
+            pmx.link(fib, 'gps-', 2, 6.0, {'f': 5.0, 'onepol': 'asey'}, rng=rng, seed=40)
+        else:
+            for k in range(2):
+                pmx.fiber(fib, 'gps-', rng=rng)
+                pmx.ampliflat(6.0, 'gain', {'f': 5.0, 'onepol': 'asey'}, seed=40 + k)
+        outs.append((np.array(pmx.GSTATE.FIELDX), np.array(pmx.GSTATE.FIELDY)))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
