@@ -1,0 +1,173 @@
+"""NumPy restatement of the blind DSP core of the reference's coherent receiver (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module; the product never does.
+
+Reference code followed (all under /root/reference):
+  cmaadaptivefilter.m:33-55 (C twin cmaadaptivefilter.c:57-91)   constant-modulus 2x2 FIR update, sample by sample
+  dsp4cohdec.m:353-427   cmapolardemux: initial taps, circular extension, passes until the taps move < 5e-5
+  dsp4cohdec.m:320-345   vitvit: M-th power, circular moving average of 2k+1 samples, (unwrapped) angle / M
+  dsp4cohdec.m:241-283   carrier recovery: frequency from s.*conj(shift(s)) (navg = freqavg), phase (navg = phasavg)
+  samp2pat.m:60-67       'coherent': first_bit = |phase| <= pi/2, second_bit = phase > 0
+  pat_decoder.m:68-82    'dqpsk' with binary patterns: pat2stars (pat2stars.m:51-63), conj(s).*shift(s,1),
+                         stars2pat (stars2pat.m:28-41), both bits inverted
+  ex20_coherent_polmux.m:168-176   X/Y swap test, ber_estimate.m:118 error count
+
+PARITY PINNING: tests/test_dsp_oracle.py executes the reference's own cmaadaptivefilter.m, samp2pat.m,
+pat_decoder.m (+ pat2stars.m, stars2pat.m, fastshift.m) and the sub-functions vitvit / cmapolardemux of
+dsp4cohdec.m with the mini interpreter (oracle/mini_m) on seeded inputs and compares them with this file.
+
+NOT restated (and not built): the front-end of receiver_cohmix.m (optical / electrical filters, LO mixing),
+mygeteyeinfo's timing search and the toolbox function `decimate` (dsp4cohdec.m:176-184, not in the tree): the
+chain here starts from one complex sample per symbol and polarization.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def errorfuncma(x, m):
+    """cmaadaptivefilter.m:54-55: E = X.*(M - abs(X).^2)"""
+    return x * (m - np.abs(x) ** 2)
+
+
+def cma_adaptive_filter(xx, h1, h2, mu, R):
+    """cmaadaptivefilter.m:33-52.  xx: [L+ntap-1, 2] circularly extended input; h1, h2: [ntap, 2].
+    -> (Y [L,2], h1, h2).  Sums in the interpreter's order: columns first, then across the two columns."""
+    xx = np.asarray(xx, dtype=np.complex128)
+    h1 = np.array(h1, dtype=np.complex128)
+    h2 = np.array(h2, dtype=np.complex128)
+    ntap = h1.shape[0]
+    L = xx.shape[0] - ntap + 1
+    y = np.zeros((L, 2), dtype=np.complex128)
+    for k in range(L):
+        w = xx[k:k + ntap, :]
+        y1 = np.sum(np.sum(w * h1, axis=0))
+        y2 = np.sum(np.sum(w * h2, axis=0))
+        y[k, 0], y[k, 1] = y1, y2
+        h1 = h1 + mu * errorfuncma(y1, R[0]) * np.conj(w)
+        h2 = h2 + mu * errorfuncma(y2, R[1]) * np.conj(w)
+    return y, h1, h2
+
+
+def cma_polar_demux(x, mu=1 / 6000, taps=7, R=(1.0, 1.0), phizero=0.0, max_passes=None):
+    """cmapolardemux (dsp4cohdec.m:353-427) for two transmitted polarizations.  -> (y [L,2], passes run)"""
+    x = np.asarray(x, dtype=np.complex128)
+    half = taps // 2
+    M = np.array([[math.cos(phizero), math.sin(phizero)], [-math.sin(phizero), math.cos(phizero)]], dtype=np.complex128)
+    h1 = np.zeros((taps, 2), dtype=np.complex128)
+    h2 = np.zeros((taps, 2), dtype=np.complex128)
+    h1[half, :] = M[0, :]          # hzero(halftaps+1,:,:) = M; h1 = squeeze(hzero(:,1,:))
+    h2[half, :] = M[1, :]
+    ext = np.concatenate([x[len(x) - half:], x, x[:half]]) if half else x
+    L = len(x)
+    repetitions = 50 * math.ceil(1.0 / (L * mu))
+    if max_passes is not None:
+        repetitions = min(repetitions, max_passes + 1)
+    c, conv, y = 1, False, None
+    while not conv and c < repetitions:
+        h1o, h2o = h1.copy(), h2.copy()
+        y, h1n, h2n = cma_adaptive_filter(ext, h1, h2, mu, R)
+        if np.any(h1n) or np.any(h2n):
+            h1, h2 = h1n, h2n
+        if max(np.max(np.abs(h1o - h1)), np.max(np.abs(h2o - h2))) < 5e-5:
+            conv = True
+        c += 1
+    return y, c - 1
+
+
+def circ_moving_average(s, k):
+    """The smoothing of vitvit (dsp4cohdec.m:329-340): ifft(fft(s).*fft(ones(N,1)/N, L)), N = 2k+1, i.e. the circular
+    causal average out(n) = mean(s(n-N+1 .. n)).  Evaluated directly (the transform pair is an implementation detail of
+    the interpreter code; the two agree to rounding)."""
+    s = np.asarray(s, dtype=np.complex128)
+    L, N = s.shape[0], 2 * k + 1
+    if N >= L:
+        reps = math.ceil(N / L)
+        long = np.concatenate([s] * reps)
+        return circ_moving_average_exact(long, N)[:L]
+    return circ_moving_average_exact(s, N)
+
+
+def circ_moving_average_exact(s, N):
+    L = s.shape[0]
+    out = np.zeros_like(s)
+    for j in range(N):
+        out += np.roll(s, j, axis=0)
+    return out / N
+
+
+def vitvit(s, P, M, k, applyunwrap):
+    """dsp4cohdec.m:320-345"""
+    s = np.asarray(s, dtype=np.complex128)
+    if P == M:
+        s = s ** P
+    else:
+        s = np.abs(s) ** P * np.exp(1j * np.angle(s ** M))
+    if k > 0:
+        s = circ_moving_average(s, k)
+    if applyunwrap:
+        return np.unwrap(np.angle(s), axis=0) / M
+    return np.angle(s) / M
+
+
+def carrier_recovery(signals, modorder=2, freqavg=500, phasavg=3, poworder=2):
+    """dsp4cohdec.m:241-283 -> Phases = angle(Signals .* Carrier), [L, npol]"""
+    s = np.asarray(signals, dtype=np.complex128)
+    M = 2 ** modorder
+    off = math.pi / 4 if modorder > 1 else 0.0
+    if freqavg:
+        om = np.cumsum(vitvit(s * np.conj(np.roll(s, 1, axis=0)), M, M, freqavg, False), axis=0)
+        closest = om[0] + np.round((om[-1] - om[0]) / 2 / math.pi) * 2 * math.pi
+        ratio = closest / om[-1]
+        om = (om - om[0]) * ratio + om[0]
+        demod = s * np.exp(-1j * om)
+        theta = vitvit(demod, poworder, M, phasavg, True)
+        carrier = np.exp(1j * (-om - theta + off))
+    else:
+        theta = vitvit(s, poworder, M, phasavg, True)
+        carrier = np.exp(1j * (-theta + off))
+    return np.angle(s * carrier)
+
+
+def samp2pat_coherent(phase):
+    """samp2pat.m:60-67 -> [first_bit second_bit] per polarization, [L, 2*npol] of 0/1"""
+    phase = np.asarray(phase, dtype=np.float64)
+    second = phase > 0
+    first = np.abs(phase) <= math.pi / 2
+    cols = []
+    for p in range(phase.shape[1]):
+        cols += [first[:, p], second[:, p]]
+    return np.stack(cols, axis=1).astype(np.uint8)
+
+
+def pat_decoder_dqpsk_binary(patmat):
+    """pat_decoder(patmat,'dqpsk',struct('binary',true)) (pat_decoder.m:68-82) -> (pat [L], patmat [L,2])"""
+    patmat = np.asarray(patmat).astype(np.int64)
+    stars = np.zeros(patmat.shape[0], dtype=np.complex128)            # pat2stars.m:51-63
+    a, b = patmat[:, 0], patmat[:, 1]
+    stars[(a == 0) & (b == 0)] = 1
+    stars[(a == 0) & (b == 1)] = 1j
+    stars[(a == 1) & (b == 1)] = -1
+    stars[(a == 1) & (b == 0)] = -1j
+    r = np.conj(stars) * np.roll(stars, 1)                             # conj(stars_t).*fastshift(stars_t,1)
+    pat = np.zeros(len(r), dtype=np.int64)                             # stars2pat.m:28-41
+    pm = np.zeros((len(r), 2), dtype=np.int64)
+    for val, p, bits in ((1, 0, (0, 0)), (1j, 1, (0, 1)), (-1, 3, (1, 1)), (-1j, 2, (1, 0))):
+        m = r == val
+        pat[m] = p
+        pm[m, 0], pm[m, 1] = bits
+    return 3 - pat, 1 - pm                                             # pat = 3-pat; patmat = ~patmat
+
+
+def count_errors_dqpsk(phases_rx, tx_phase):
+    """Decision + differential decoding + X/Y swap test + error count (ex20_coherent_polmux.m:160-178,
+    ber_estimate.m:118).  phases_rx: [L,2] recovered phases; tx_phase: [L,2] phases of the transmitted symbols."""
+    hat = samp2pat_coherent(phases_rx)
+    ref = samp2pat_coherent(tx_phase)
+    hx, hy = pat_decoder_dqpsk_binary(hat[:, 0:2])[1], pat_decoder_dqpsk_binary(hat[:, 2:4])[1]
+    rx, ry = pat_decoder_dqpsk_binary(ref[:, 0:2])[1], pat_decoder_dqpsk_binary(ref[:, 2:4])[1]
+    if np.sum(rx != hy) < np.sum(rx != hx):
+        hx, hy = hy, hx
+    return int(np.sum(rx != hx) + np.sum(ry != hy))

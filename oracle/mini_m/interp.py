@@ -676,6 +676,11 @@ class Interp:
             self.exec_block(body, ws)
         except _Return:
             pass
+        if outs and outs[-1] == 'varargout':      # function varargout = f(...): the cell's elements are the outputs
+            va = ws.get('varargout')
+            head = [ws.get(o) for o in outs[:-1]]
+            tail = list(va) if isinstance(va, MCell) else []
+            return (head + tail)[:max(nargout, 1)]
         res = []
         for k, o in enumerate(outs[:max(nargout, 1)]):
             if o in ws['__globals__']:
@@ -836,9 +841,27 @@ class Interp:
         base = np.zeros((0, 0)) if cur is None else cur
         if isinstance(base, str):
             base = arr(base)
+        if isinstance(base, np.ndarray) and base.ndim == 3:
+            return self.index_assign(base, step[2], val, ws)
         return self.index_assign(arr(base), step[2], val, ws)
 
+    def _sel3(self, a, idx_nodes, ws):
+        sel = []
+        for d, node in enumerate(idx_nodes):
+            if node[0] == 'all':
+                sel.append(np.arange(a.shape[d]))
+            else:
+                ix = arr(self.eval(node, ws, end_ctx=(a, d, 3)))
+                sel.append(np.real(ix).astype(np.int64).flatten('F') - 1)
+        return sel
+
     def index_assign(self, a, idx_nodes, val, ws):
+        if isinstance(a, np.ndarray) and a.ndim == 3 and len(idx_nodes) == 3:   # minimal 3-D support (zeros(a,b,c))
+            v = num(val)
+            out = a.astype(np.complex128) if np.iscomplexobj(v) and not np.iscomplexobj(a) else a.copy()
+            sel = self._sel3(out, idx_nodes, ws)
+            out[np.ix_(*sel)] = v.flat[0] if v.size == 1 else np.reshape(v, tuple(len(q) for q in sel), order='F')
+            return out
         v = num(val) if not isinstance(val, str) else arr(val)
         if np.iscomplexobj(v) and not np.iscomplexobj(a):
             a = a.astype(np.complex128)
@@ -1005,6 +1028,8 @@ class Interp:
         raise MError('cannot evaluate %s' % k)
 
     def index(self, base, idx_nodes, ws):
+        if isinstance(base, np.ndarray) and base.ndim == 3 and len(idx_nodes) == 3:
+            return base[np.ix_(*self._sel3(base, idx_nodes, ws))]
         if isinstance(base, MCell):
             i = arr(self.eval(idx_nodes[0], ws, end_ctx=(base, 0, 1)))
             return MCell([base[int(j) - 1] for j in i.flatten()])
@@ -1214,8 +1239,19 @@ def _log10(it, a, n):
 
 _simple('mod', lambda x, y: np.where(num(y) == 0, num(x), np.mod(num(x), np.where(num(y) == 0, 1, num(y)))))
 _simple('complex', lambda x, y: num(x).astype(np.float64) + 1j * num(y).astype(np.float64))
-_simple('fft', lambda x, *r: sfft.fft(num(x), axis=(1 if num(x).shape[0] == 1 else 0)))
-_simple('ifft', lambda x, *r: sfft.ifft(num(x), axis=(1 if num(x).shape[0] == 1 else 0)))
+def _fftn(fn):
+    # fft(x) / fft(x, n): along the first non-singleton dimension, zero-padded or truncated to n points
+    def f(x, *r):
+        a = num(x)
+        n = int(scalar(r[0])) if r and arr(r[0]).size else None
+        return fn(a, n=n, axis=(1 if a.shape[0] == 1 else 0))
+    return f
+
+
+_simple('fft', _fftn(sfft.fft))
+_simple('ifft', _fftn(sfft.ifft))
+_simple('unwrap', lambda x: np.unwrap(num(x), axis=(1 if num(x).shape[0] == 1 else 0)))
+_simple('cumsum', lambda x: np.cumsum(num(x), axis=(1 if num(x).shape[0] == 1 else 0)))
 _simple('fftshift', lambda x: np.fft.fftshift(num(x), axes=(1 if num(x).shape[0] == 1 else 0)))
 _simple('flipud', lambda x: num(x)[::-1, :])
 _simple('fliplr', lambda x: num(x)[:, ::-1])
@@ -1241,7 +1277,26 @@ _simple('isfield', lambda s, f: np.array([[isinstance(s, MStruct) and f in s]]))
 _simple('num2str', lambda x, *r: ('%g' % np.real(scalar(x))))
 _simple('struct', lambda *a: MStruct({a[i]: a[i + 1] for i in range(0, len(a), 2)}))
 _simple('nargchk', lambda *a: np.zeros((0, 0)))
-_simple('squeeze', lambda x: num(x))
+def _squeeze(x):
+    a = np.asarray(x)
+    if a.ndim <= 2:
+        return num(x)
+    b = np.squeeze(a)
+    return b if b.ndim == 2 else (b.reshape(-1, 1) if b.ndim == 1 else b.reshape(1, 1) if b.ndim == 0 else b)
+
+
+_simple('squeeze', _squeeze)
+
+
+def _sort(x, *r):
+    a = num(x)
+    out = np.sort(a, axis=(1 if a.shape[0] == 1 else 0))
+    if r and isinstance(r[-1], str) and r[-1].lower() == 'descend':
+        out = out[::-1] if a.shape[0] != 1 else out[:, ::-1]
+    return out
+
+
+_simple('sort', _sort)
 _simple('tic', lambda: np.zeros((0, 0)))
 
 for _n, _v in [('pi', math.pi), ('Inf', math.inf), ('inf', math.inf), ('NaN', math.nan), ('nan', math.nan),
