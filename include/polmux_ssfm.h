@@ -271,6 +271,40 @@ int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pa
 int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t nsymb, int32_t nt,
                    int64_t* counts_dev);
 
+/* ---- blind DSP core of the coherent receiver + error count ------------------------------------------------------
+ * What dsp4cohdec.m does between its decimator and its outputs, for a dual-polarization QPSK field already compensated
+ * for chromatic dispersion, on one complex sample per symbol (the sample at time index k*nt of symbol k) normalised to
+ * unit mean power:
+ *   cmapolardemux   constant-modulus 2x2 FIR polarization demultiplexer: cmaadaptivefilter.m:33-55 (C twin
+ *                   cmaadaptivefilter.c:57-91) passed over the block until the taps move by less than 5e-5
+ *                   (dsp4cohdec.m:353-427), taps initialised to the rotation by phizero
+ *   carrier         frequency from (s.*conj(shift(s))).^4 averaged over 2*freqavg+1 symbols, cumulated and cleaned to
+ *                   the block's circularity; phase by Viterbi & Viterbi with 2*phasavg+1 symbols (vitvit,
+ *                   dsp4cohdec.m:241-283, 320-345)
+ *   decision        samp2pat 'coherent' (samp2pat.m:60-67), differential decoding pat_decoder 'dqpsk'
+ *                   (pat_decoder.m:68-82), X/Y swap test and error count (ex20_coherent_polmux.m:168-176,
+ *                   ber_estimate.m:118)
+ * Neither the waveplates nor the transmitted symbols enter the processing; ref_patmat is only counted against.
+ * Not built: the front-end of receiver_cohmix.m (filters, LO mixing), mygeteyeinfo's timing search and the toolbox
+ * decimator of dsp4cohdec.m:176-184. */
+typedef struct pmx_dsp_desc {
+    int32_t nsymb, nt;        /* symbols per block, samples per symbol                                   */
+    int32_t apply_cma;        /* p.applypol with p.polmethod = 'cma'                                      */
+    int32_t taps;             /* p.cmaparams.taps (odd, <= 15)                                            */
+    double mu;                /* p.cmaparams.mu                                                           */
+    double R[2];              /* p.cmaparams.R                                                            */
+    double phizero;           /* p.cmaparams.phizero                                                      */
+    int32_t max_passes;       /* 0: the reference's bound 50*ceil(1/(L*mu)) - 1                           */
+    int32_t modorder;         /* p.modorder (2 = QPSK)                                                    */
+    int32_t freqavg, phasavg; /* p.freqavg, p.phasavg                                                     */
+    int32_t poworder;         /* p.poworder                                                               */
+} pmx_dsp_desc;
+/* ref_patmat: HOST [nsymb][4] bytes, the differentially decoded transmitted pattern [x1 x2 y1 y2] (pat_decoder of the
+ * transmitted bits); counts_dev: DEVICE [batch] int64 (e.g. the NCCL send buffer); passes_host (may be NULL): [batch]
+ * passes the demultiplexer ran. */
+int pmx_dsp_count(pmx_ctx* ctx, pmx_devfield* f, const pmx_dsp_desc* dsp, const uint8_t* ref_patmat, int64_t* counts_dev,
+                  int32_t* passes_host);
+
 /* ---- Monte-Carlo over independent realizations on the GPUs of one node (BASELINE config C5) ------------------------
  * The `while cond` loop of ex20_coherent_polmux.m:131-181 with its realizations sharded over several GPUs from ONE
  * process: contiguous realization groups per GPU (rank g owns [g*nreal/ndev, (g+1)*nreal/ndev)), one host thread and

@@ -31,7 +31,7 @@ EXPORTS = [
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
     'pmx_host_is_pinned', 'pmx_scalar_adaptive_run', 'pmx_mc_run', 'pmx_mc_nccl_available',
-    'pmx_ampliflat_exec_at',
+    'pmx_ampliflat_exec_at', 'pmx_dsp_count',
 ]
 
 
@@ -66,6 +66,12 @@ class Field(C.Structure):
 class FiberResult(C.Structure):
     _fields_ = [('firstdz', _dp), ('ncycle', _ip), ('ntot', _ip), ('status', _ip),
                 ('trace_dz', _dp), ('trace_ntrunk', _ip), ('trace_cap', C.c_int32)]
+
+
+class DspDesc(C.Structure):
+    _fields_ = [('nsymb', C.c_int32), ('nt', C.c_int32), ('apply_cma', C.c_int32), ('taps', C.c_int32), ('mu', C.c_double),
+                ('R', C.c_double * 2), ('phizero', C.c_double), ('max_passes', C.c_int32), ('modorder', C.c_int32),
+                ('freqavg', C.c_int32), ('phasavg', C.c_int32), ('poworder', C.c_int32)]
 
 
 class McDesc(C.Structure):
@@ -123,6 +129,7 @@ def load():
     lib.pmx_plan_set_plates.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     lib.pmx_fiber_exec.argtypes = [vp, vp, C.POINTER(FiberResult)]
     lib.pmx_host_is_pinned.argtypes = [vp]
+    lib.pmx_dsp_count.argtypes = [vp, vp, C.POINTER(DspDesc), C.POINTER(C.c_uint8), vp, C.POINTER(C.c_int32)]
     lib.pmx_mc_run.argtypes = [C.POINTER(FiberDesc), C.POINTER(McDesc), C.POINTER(Field), C.POINTER(C.c_int64),
                                C.POINTER(C.c_int64), C.c_char_p, C.c_int32]
     lib.pmx_scalar_adaptive_run.argtypes = [vp, C.POINTER(FiberDesc), C.c_double, C.c_double, C.c_int32, C.POINTER(Field),

@@ -1592,6 +1592,305 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
 }
 
 // ---------------------------------------------------------------------------
+// Blind DSP core of the reference's coherent receiver on the device (pmx_dsp_count): one complex sample per symbol and
+// polarization -> constant-modulus 2x2 FIR polarization demultiplexer (cmaadaptivefilter.m:33-55 inside the
+// convergence loop of cmapolardemux, dsp4cohdec.m:353-427) -> carrier frequency and phase by Viterbi & Viterbi
+// (vitvit, dsp4cohdec.m:320-345, 241-283) -> decision (samp2pat.m:60-67) -> differential decoding
+// (pat_decoder.m:68-82) -> X/Y swap test and error count (ex20_coherent_polmux.m:168-176, ber_estimate.m:118).
+// Nothing here knows the waveplates or the transmitted symbols; the caller hands in the decoded reference pattern to
+// count against.  The adaptive filter and the scans are sequential in the symbol index by definition: they run as a few
+// threads per realization, all realizations of the batch in parallel.  FP64.
+#define PMX_DSP_MAX_TAPS 15
+
+// sig[(b*2 + pol)*L + k] = field sample at the centre of symbol k, divided by sqrt(mean |s|^2 over both polarizations)
+__global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t N, int l1, int l2, int nsymb, int nt,
+                                                        cpx* sig) {
+    __shared__ double red[256];
+    const int b = blockIdx.x;
+    const cpx* fld = field + (size_t)b * N * 2;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
+        const size_t m = pmx_mem_index((size_t)k * nt, l1, l2);
+        const cpx x = fld[2 * m], y = fld[2 * m + 1];
+        acc += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {   // fixed tree: the same result on every run
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double inv = 1.0 / sqrt(red[0] / (2.0 * nsymb));
+    for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
+        const size_t m = pmx_mem_index((size_t)k * nt, l1, l2);
+        const cpx x = fld[2 * m], y = fld[2 * m + 1];
+        sig[((size_t)b * 2 + 0) * nsymb + k] = make_double2(x.x * inv, x.y * inv);
+        sig[((size_t)b * 2 + 1) * nsymb + k] = make_double2(y.x * inv, y.y * inv);
+    }
+}
+
+// cmapolardemux: thread 0 of a CTA runs filter 1 (h1 -> Y1), thread 1 filter 2; sums in the interpreter's order
+// (column by column, then across the two columns), products and sums rounded separately.
+__global__ void __launch_bounds__(32) pmx_k_dsp_cma(const cpx* sig, cpx* out, int L, int taps, double mu, double r1, double r2,
+                                                    double phizero, int repetitions, int* passes) {
+    const int b = blockIdx.x, f = threadIdx.x;   // f: which of the two filters
+    if (f >= 2) return;
+    const cpx* x0 = sig + (size_t)b * 2 * L;      // column 0 (X)
+    const cpx* x1 = x0 + L;                       // column 1 (Y)
+    cpx* y = out + ((size_t)b * 2 + f) * L;
+    const int half = taps / 2;
+    const double R = f == 0 ? r1 : r2;
+    cpx h[2][PMX_DSP_MAX_TAPS], ho[2][PMX_DSP_MAX_TAPS];
+    for (int j = 0; j < taps; ++j) h[0][j] = h[1][j] = make_double2(0.0, 0.0);
+    // hzero(halftaps+1,:,:) = M = [cos sin; -sin cos]; filter f takes row f
+    h[0][half] = make_double2(f == 0 ? cos(phizero) : -sin(phizero), 0.0);
+    h[1][half] = make_double2(f == 0 ? sin(phizero) : cos(phizero), 0.0);
+    int c = 1;
+    bool conv = false;
+    while (!conv && c < repetitions) {
+        for (int j = 0; j < taps; ++j) {
+            ho[0][j] = h[0][j];
+            ho[1][j] = h[1][j];
+        }
+        for (int k = 0; k < L; ++k) {
+            cpx s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
+            cpx w0[PMX_DSP_MAX_TAPS], w1[PMX_DSP_MAX_TAPS];
+            for (int j = 0; j < taps; ++j) {   // extendedx(k + j) = x(k + j - half) circularly
+                int i = k + j - half;
+                i = i < 0 ? i + L : (i >= L ? i - L : i);
+                w0[j] = x0[i];
+                w1[j] = x1[i];
+                const cpx p0 = make_double2(__dadd_rn(__dmul_rn(w0[j].x, h[0][j].x), -__dmul_rn(w0[j].y, h[0][j].y)),
+                                            __dadd_rn(__dmul_rn(w0[j].x, h[0][j].y), __dmul_rn(w0[j].y, h[0][j].x)));
+                const cpx p1 = make_double2(__dadd_rn(__dmul_rn(w1[j].x, h[1][j].x), -__dmul_rn(w1[j].y, h[1][j].y)),
+                                            __dadd_rn(__dmul_rn(w1[j].x, h[1][j].y), __dmul_rn(w1[j].y, h[1][j].x)));
+                s0 = make_double2(__dadd_rn(s0.x, p0.x), __dadd_rn(s0.y, p0.y));
+                s1 = make_double2(__dadd_rn(s1.x, p1.x), __dadd_rn(s1.y, p1.y));
+            }
+            const cpx yk = make_double2(__dadd_rn(s0.x, s1.x), __dadd_rn(s0.y, s1.y));
+            y[k] = yk;
+            // incr = mu .* errorfuncma(Y, R) .* conj(xx):  E = Y .* (R - abs(Y).^2)
+            const double a = hypot(yk.x, yk.y), g = __dadd_rn(R, -__dmul_rn(a, a));
+            const cpx e = make_double2(__dmul_rn(mu, __dmul_rn(yk.x, g)), __dmul_rn(mu, __dmul_rn(yk.y, g)));
+            for (int j = 0; j < taps; ++j) {
+                h[0][j] = make_double2(__dadd_rn(h[0][j].x, __dadd_rn(__dmul_rn(e.x, w0[j].x), __dmul_rn(e.y, w0[j].y))),
+                                       __dadd_rn(h[0][j].y, __dadd_rn(__dmul_rn(e.y, w0[j].x), -__dmul_rn(e.x, w0[j].y))));
+                h[1][j] = make_double2(__dadd_rn(h[1][j].x, __dadd_rn(__dmul_rn(e.x, w1[j].x), __dmul_rn(e.y, w1[j].y))),
+                                       __dadd_rn(h[1][j].y, __dadd_rn(__dmul_rn(e.y, w1[j].x), -__dmul_rn(e.x, w1[j].y))));
+            }
+        }
+        // (the reference keeps the old taps when the new ones are all zero: any(any(h_new)), dsp4cohdec.m:404-407)
+        double moved = 0.0, nz = 0.0;
+        for (int j = 0; j < taps; ++j)
+            for (int p = 0; p < 2; ++p) {
+                moved = fmax(moved, hypot(ho[p][j].x - h[p][j].x, ho[p][j].y - h[p][j].y));
+                nz = fmax(nz, fmax(fabs(h[p][j].x), fabs(h[p][j].y)));
+            }
+        const double moved_o = __shfl_xor_sync(0x3u, moved, 1), nz_o = __shfl_xor_sync(0x3u, nz, 1);
+        if (fmax(nz, nz_o) == 0.0) {
+            for (int j = 0; j < taps; ++j) {
+                h[0][j] = ho[0][j];
+                h[1][j] = ho[1][j];
+            }
+            moved = 0.0;
+        } else {
+            moved = fmax(moved, moved_o);
+        }
+        if (moved < 5e-5) conv = true;
+        ++c;
+    }
+    if (f == 0 && passes) passes[b] = c - 1;
+}
+
+// Carrier recovery of one (realization, polarization) stream by one thread: frequency estimate (navg = freqavg) ->
+// cumulated phase omega, cleaned to match the circularity -> demodulation -> Viterbi & Viterbi phase (navg = phasavg,
+// unwrapped) -> phases = angle(s .* fastexp(-omega - theta + pi/4)).  w1, w2: complex scratch of L entries, om: real.
+__device__ __forceinline__ cpx pmx_cpow_int(cpx a, int n) {   // a^n, n >= 1, by repeated multiplication
+    cpx r = a;
+    for (int i = 1; i < n; ++i) r = make_double2(r.x * a.x - r.y * a.y, r.x * a.y + r.y * a.x);
+    return r;
+}
+__device__ void pmx_circ_avg(const cpx* in, cpx* out, int L, int k) {   // out(n) = mean(in(n-N+1 .. n)), N = 2k+1, circular
+    const int N = 2 * k + 1;
+    const double invN = 1.0 / N;
+    // every output from its own N terms would cost L*N; a running sum is re-seeded every 4096 outputs to bound its drift
+    cpx run = make_double2(0.0, 0.0);
+    for (int n = 0; n < L; ++n) {
+        if ((n & 4095) == 0) {
+            run = make_double2(0.0, 0.0);
+            for (int j = 0; j < N; ++j) {
+                int i = (n - j) % L;
+                i = i < 0 ? i + L : i;
+                run.x += in[i].x;
+                run.y += in[i].y;
+            }
+        } else {
+            int i0 = (n - N) % L;
+            i0 = i0 < 0 ? i0 + L : i0;
+            run.x += in[n].x - in[i0].x;
+            run.y += in[n].y - in[i0].y;
+        }
+        out[n] = make_double2(run.x * invN, run.y * invN);
+    }
+}
+__global__ void __launch_bounds__(32) pmx_k_dsp_carrier(const cpx* sig, cpx* w1, cpx* w2, double* om, double* phases, int L,
+                                                        int M, int freqavg, int phasavg, int P, double offset) {
+    const int s_id = blockIdx.x;   // one (realization, polarization) stream per CTA, thread 0 works
+    if (threadIdx.x != 0) return;
+    const cpx* s = sig + (size_t)s_id * L;
+    cpx* a = w1 + (size_t)s_id * L;
+    cpx* bq = w2 + (size_t)s_id * L;
+    double* omg = om + (size_t)s_id * L;
+    double* ph = phases + (size_t)s_id * L;
+    const double TWO_PI = 6.283185307179586476925286766559;
+    if (freqavg > 0) {
+        for (int n = 0; n < L; ++n) {   // (s .* conj(fastshift(s,1))).^M
+            const cpx p = s[n], q = s[n == 0 ? L - 1 : n - 1];
+            a[n] = pmx_cpow_int(make_double2(p.x * q.x + p.y * q.y, p.y * q.x - p.x * q.y), M);
+        }
+        pmx_circ_avg(a, bq, L, freqavg);
+        double acc = 0.0;
+        for (int n = 0; n < L; ++n) {   // omega = cumsum(angle(.)/M)
+            acc += atan2(bq[n].y, bq[n].x) / M;
+            omg[n] = acc;
+        }
+        const double o0 = omg[0], oe = omg[L - 1];
+        const double closest = o0 + rint((oe - o0) / 2 / 3.14159265358979323846) * 2 * 3.14159265358979323846;
+        const double ratio = closest / oe;
+        for (int n = 0; n < L; ++n) omg[n] = (omg[n] - o0) * ratio + o0;
+    } else {
+        for (int n = 0; n < L; ++n) omg[n] = 0.0;
+    }
+    for (int n = 0; n < L; ++n) {   // demodulate, then abs(s).^P .* fastexp(angle(s.^M))  (or s.^P when P == M)
+        double sn, cs;
+        sincos(-omg[n], &sn, &cs);
+        const cpx d = make_double2(s[n].x * cs - s[n].y * sn, s[n].x * sn + s[n].y * cs);
+        const cpx dm = pmx_cpow_int(d, M);
+        if (P == M) {
+            a[n] = dm;
+        } else {
+            const double mag = pow(hypot(d.x, d.y), (double)P), ang = atan2(dm.y, dm.x);
+            sincos(ang, &sn, &cs);
+            a[n] = make_double2(mag * cs, mag * sn);
+        }
+    }
+    const cpx* sm = a;
+    if (phasavg > 0) {
+        pmx_circ_avg(a, bq, L, phasavg);
+        sm = bq;
+    }
+    double prev = 0.0, unw = 0.0;
+    for (int n = 0; n < L; ++n) {   // theta = unwrap(angle(.))/M;  phases = angle(s .* fastexp(-omega - theta + offset))
+        const double ang = atan2(sm[n].y, sm[n].x);
+        if (n == 0) {
+            unw = ang;
+        } else {
+            double dd = ang - prev;
+            dd -= TWO_PI * rint(dd / TWO_PI);
+            if (fabs(ang - prev) <= 3.14159265358979323846) dd = ang - prev;   // numpy.unwrap: jumps below pi stay
+            unw += dd;
+        }
+        prev = ang;
+        const double arg = -omg[n] - unw / M + offset;
+        double sn, cs;
+        sincos(arg, &sn, &cs);
+        ph[n] = atan2(s[n].x * sn + s[n].y * cs, s[n].x * cs - s[n].y * sn);
+    }
+}
+
+// decision + differential decoding + the four error sums of the swap test: acc[b*4 + {xx, xy, yy, yx}]
+__device__ __forceinline__ int pmx_star_of(double phase) {   // samp2pat 'coherent' bits -> pat2stars (binary) quadrant
+    const int first = fabs(phase) <= 1.57079632679489661923 ? 1 : 0, second = phase > 0 ? 1 : 0;
+    // [0 0] -> 1 (0), [0 1] -> i (1), [1 1] -> -1 (2), [1 0] -> -i (3): index = multiples of pi/2
+    return first == 0 ? (second == 0 ? 0 : 1) : (second == 1 ? 2 : 3);
+}
+__global__ void __launch_bounds__(256) pmx_k_dsp_decide(const double* phases, const uint8_t* ref, int L, unsigned long long* acc) {
+    const int b = blockIdx.y;
+    const double* px = phases + (size_t)b * 2 * L;
+    const double* py = px + L;
+    unsigned long long e[4] = {0, 0, 0, 0};
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+        const int km = k == 0 ? L - 1 : k - 1;
+        int bits[2][2];
+        for (int p = 0; p < 2; ++p) {
+            const double* q = p ? py : px;
+            // stars_r = conj(stars_t(k)) .* stars_t(k-1): quadrant difference; stars2pat then inverts both bits
+            const int d = (pmx_star_of(q[km]) - pmx_star_of(q[k])) & 3;
+            const int m0 = (d == 2 || d == 3) ? 1 : 0, m1 = (d == 1 || d == 2) ? 1 : 0;
+            bits[p][0] = 1 - m0;
+            bits[p][1] = 1 - m1;
+        }
+        const uint8_t* r = ref + (size_t)k * 4;   // decoded reference pattern [x1 x2 y1 y2]
+        e[0] += (r[0] != bits[0][0]) + (r[1] != bits[0][1]);
+        e[1] += (r[0] != bits[1][0]) + (r[1] != bits[1][1]);
+        e[2] += (r[2] != bits[1][0]) + (r[3] != bits[1][1]);
+        e[3] += (r[2] != bits[0][0]) + (r[3] != bits[0][1]);
+    }
+    for (int i = 0; i < 4; ++i) {
+        for (int o = 16; o > 0; o >>= 1) e[i] += __shfl_xor_sync(0xffffffffu, e[i], o);
+        if ((threadIdx.x & 31) == 0 && e[i]) atomicAdd(&acc[(size_t)b * 4 + i], e[i]);
+    }
+}
+__global__ void pmx_k_dsp_final(const unsigned long long* acc, int batch, unsigned long long* counts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const unsigned long long xx = acc[b * 4], xy = acc[b * 4 + 1], yy = acc[b * 4 + 2], yx = acc[b * 4 + 3];
+    counts[b] = (xy < xx) ? xy + yx : xx + yy;   // ex20_coherent_polmux.m:168-173: swap when Y decodes the X pattern better
+}
+
+extern "C" int pmx_dsp_count(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const uint8_t* ref_patmat, int64_t* counts_dev,
+                             int32_t* passes_host) {
+    if (!c || !f || !d || !ref_patmat || !counts_dev) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: null argument");
+    if (f->nfc != 1) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_dsp_count: single-column ('unique') fields only");
+    if (f->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_dsp_count: FP64 fields only");
+    if ((int64_t)d->nsymb * d->nt != f->nfft) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: nsymb*nt must equal nfft");
+    if (d->taps < 1 || d->taps > PMX_DSP_MAX_TAPS || !(d->taps & 1))
+        return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: taps must be odd, 1..%d", PMX_DSP_MAX_TAPS);
+    if (d->modorder != 2) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_dsp_count: QPSK (modorder 2) only");
+    if (!(d->mu > 0)) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: mu must be > 0");
+    CK(c, cudaSetDevice(c->device));
+    const int L = d->nsymb, B = f->batch;
+    const size_t n = (size_t)B * 2 * L;
+    cpx *sig = nullptr, *y = nullptr, *w1 = nullptr, *w2 = nullptr;
+    double *om = nullptr, *ph = nullptr;
+    uint8_t* dref = nullptr;
+    unsigned long long* acc = nullptr;
+    int* dpass = nullptr;
+    CK(c, cudaMallocAsync(&sig, n * sizeof(cpx), c->stream));
+    CK(c, cudaMallocAsync(&y, n * sizeof(cpx), c->stream));
+    CK(c, cudaMallocAsync(&w1, n * sizeof(cpx), c->stream));
+    CK(c, cudaMallocAsync(&w2, n * sizeof(cpx), c->stream));
+    CK(c, cudaMallocAsync(&om, n * sizeof(double), c->stream));
+    CK(c, cudaMallocAsync(&ph, n * sizeof(double), c->stream));
+    CK(c, cudaMallocAsync(&dref, (size_t)L * 4, c->stream));
+    CK(c, cudaMallocAsync(&acc, (size_t)B * 4 * sizeof(unsigned long long), c->stream));
+    CK(c, cudaMallocAsync(&dpass, (size_t)B * sizeof(int), c->stream));
+    CK(c, cudaMemcpyAsync(dref, ref_patmat, (size_t)L * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(acc, 0, (size_t)B * 4 * sizeof(unsigned long long), c->stream));
+    CK(c, cudaMemsetAsync(dpass, 0, (size_t)B * sizeof(int), c->stream));
+    pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sig);
+    const cpx* stream_in = sig;
+    if (d->apply_cma) {
+        const int rep = d->max_passes > 0 ? d->max_passes + 1 : 50 * (int)ceil(1.0 / ((double)L * d->mu));
+        pmx_k_dsp_cma<<<B, 32, 0, c->stream>>>(sig, y, L, d->taps, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass);
+        stream_in = y;
+        c->launches++;
+    }
+    pmx_k_dsp_carrier<<<2 * B, 32, 0, c->stream>>>(stream_in, w1, w2, om, ph, L, 1 << d->modorder, d->freqavg, d->phasavg,
+                                                   d->poworder, d->modorder > 1 ? 0.78539816339744830962 : 0.0);
+    dim3 g((unsigned)std::min((L + 255) / 256, 64), B);
+    pmx_k_dsp_decide<<<g, 256, 0, c->stream>>>(ph, dref, L, acc);
+    pmx_k_dsp_final<<<(B + 127) / 128, 128, 0, c->stream>>>(acc, B, (unsigned long long*)counts_dev);
+    c->launches += 4;
+    CK(c, cudaGetLastError());
+    if (passes_host) CK(c, cudaMemcpyAsync(passes_host, dpass, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    for (void* q : {(void*)sig, (void*)y, (void*)w1, (void*)w2, (void*)om, (void*)ph, (void*)dref, (void*)acc, (void*)dpass})
+        CK(c, cudaFreeAsync(q, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));   // ref_patmat / passes_host are host buffers of the caller
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
 // building blocks of the local-error adaptive step (scalar path, fiber.m:639-679,938-1010); FP64
 __global__ void __launch_bounds__(256) pmx_k_scalar_nl(cpx* field, size_t N, int nfc, const double* gam /*[nfc], device*/,
                                                        double leff, double atten, int spm, int xpm) {

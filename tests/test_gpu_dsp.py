@@ -1,0 +1,83 @@
+"""-m gpu: the blind DSP core on the device (pmx_dsp_count) against the DSP oracle (oracle/dsp_oracle.py, itself pinned
+on the reference's M source by tests/test_dsp_oracle.py): a PDM-QPSK field through a fiber with PMD and an amplifier
+with ASE, chromatic dispersion compensated, then CMA + Viterbi & Viterbi + differential decision.  Integer error
+counts and the number of CMA passes must be equal."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle.dsp_oracle as dsp_orc
+import polmux_b200 as pmx
+from polmux_b200 import _lib, dsp, synth
+from common import base_fiber
+
+pytestmark = pytest.mark.gpu
+
+
+def _received_field(nsymb, nt, nf_db, seed, dgd=0.3, length=4e4, batch=2):
+    """-> (ctx, DeviceField with `batch` realizations after fiber + amplifier + CD compensation, symbols)"""
+    import torch  # noqa: F401  (device buffer for the counts)
+    ex, ey, sx, sy = synth.pdm_qpsk(nsymb, nt, 1)
+    pmx.reset_all(nsymb, nt, 1)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.LAMBDA, G.POWER = 28.0, np.array([1550.0]), np.array([1.0])
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    ctx = _lib.default_context()
+    n = nsymb * nt
+    fld = _lib.DeviceField(ctx, n, 1, batch)
+    xs, ys = [], []
+    for b in range(batch):
+        pmx.create_field('unique', ex, ey, {'power': 'average'})
+        G.DELAY, G.DISP = np.zeros((2, 1)), np.zeros((2, 1))
+        pmx.fiber(base_fiber(length=length, dgd=dgd, nplates=20, manakov='yes'), 'gps-',
+                  rng=np.random.Generator(np.random.PCG64(seed + b)))
+        pmx.ampliflat(0.2 * length * 1e-3, 'gain', {'f': nf_db}, seed=seed + 100 + b)
+        pmx.fiber(base_fiber(length=length, disp=-17.0, alphadB=0.0), 'g---')          # dispersion compensation
+        xs.append(np.ascontiguousarray(np.array(G.FIELDX).T))
+        ys.append(np.ascontiguousarray(np.array(G.FIELDY).T))
+    fld.upload(np.stack(xs), np.stack(ys))
+    return ctx, fld, np.stack(xs)[:, 0, :], np.stack(ys)[:, 0, :], sx[:, 0], sy[:, 0]
+
+
+@pytest.mark.parametrize('nf_db,expect_errors', [(5.0, False), (33.0, True)])
+def test_dsp_count_matches_the_oracle(nf_db, expect_errors):
+    import torch
+    nsymb, nt, batch = 1 << 11, 16, 2
+    ctx, fld, hx, hy, sx, sy = _received_field(nsymb, nt, nf_db, seed=50, batch=batch)
+    params = dict(taps=7, mu=1 / 2000, freqavg=200, phasavg=3, poworder=2)
+    ref = dsp.reference_pattern(sx, sy)
+    counts = torch.zeros(batch, dtype=torch.int64, device='cuda')
+    passes = dsp.dsp_count(ctx, fld, nsymb, nt, ref, counts.data_ptr(), **params)
+    got = counts.cpu().numpy()
+    tx_phase = np.stack([np.angle((2.0 * (s & 1) - 1) + 1j * (2.0 * ((s >> 1) & 1) - 1)) for s in (sx, sy)], axis=1)
+    for b in range(batch):
+        s = np.stack([hx[b, ::nt], hy[b, ::nt]], axis=1)
+        s = s / math.sqrt(np.mean(np.abs(s) ** 2))
+        y, npass = dsp_orc.cma_polar_demux(s, mu=params['mu'], taps=params['taps'])
+        ph = dsp_orc.carrier_recovery(y, 2, params['freqavg'], params['phasavg'], params['poworder'])
+        want = dsp_orc.count_errors_dqpsk(ph, tx_phase)
+        assert int(passes[b]) == npass and npass >= 1
+        assert int(got[b]) == want
+        assert (want > 0) == expect_errors
+    # the product's reference pattern is the oracle's decoding of the transmitted phases
+    o = dsp_orc.samp2pat_coherent(tx_phase)
+    np.testing.assert_array_equal(ref[:, 0:2], dsp_orc.pat_decoder_dqpsk_binary(o[:, 0:2])[1])
+    np.testing.assert_array_equal(ref[:, 2:4], dsp_orc.pat_decoder_dqpsk_binary(o[:, 2:4])[1])
+    fld.close()
+
+
+def test_dsp_count_without_polarization_demultiplexer_and_argument_checks():
+    import torch
+    nsymb, nt = 1 << 10, 16
+    ctx, fld, hx, hy, sx, sy = _received_field(nsymb, nt, 5.0, seed=60, dgd=0.0, batch=1)
+    counts = torch.zeros(1, dtype=torch.int64, device='cuda')
+    ref = dsp.reference_pattern(sx, sy)
+    dsp.dsp_count(ctx, fld, nsymb, nt, ref, counts.data_ptr(), applypol=False, freqavg=100)
+    s = np.stack([hx[0, ::nt], hy[0, ::nt]], axis=1)
+    s = s / math.sqrt(np.mean(np.abs(s) ** 2))
+    tx_phase = np.stack([np.angle((2.0 * (q & 1) - 1) + 1j * (2.0 * ((q >> 1) & 1) - 1)) for q in (sx, sy)], axis=1)
+    assert int(counts[0]) == dsp_orc.count_errors_dqpsk(dsp_orc.carrier_recovery(s, 2, 100, 3, 2), tx_phase)
+    with pytest.raises(_lib.PolmuxError):
+        dsp.dsp_count(ctx, fld, nsymb, nt, ref, counts.data_ptr(), taps=4)
+    fld.close()
