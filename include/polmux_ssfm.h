@@ -259,7 +259,7 @@ int pmx_count_errors(pmx_ctx* ctx, const uint8_t* pat_hat_dev, const uint8_t* pa
                      int32_t batch, int64_t* counts_dev);
 
 /* ---- minimal coherent decision + error count for Monte-Carlo runs -------------------------
- * Not the reference's dsp4cohdec.m: a data-aided stand-in used only to turn a propagated (and
+ * Not the reference's dsp4cohdec.m (its blind DSP core is pmx_dsp_count below): a data-aided stand-in used only to turn a propagated (and
  * linearly equalised, see polmux_b200/mc.py) PDM-QPSK field into the INTEGER error count that
  * ber_estimate.m:118 feeds its recursion with.  Per realization and polarization:
  *   r_k = field[k*nt]                                 symbol-centre sample (samp2pat.m:60-67)

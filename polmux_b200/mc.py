@@ -109,6 +109,23 @@ class Link:
             self._inv.set_plates(-db0[:, ::-1], th[:, ::-1], ep[:, ::-1], plate_sets=self.batch)
             self._inv.execute(field)
 
+    def cd_compensate(self, field: _lib.DeviceField):
+        """What a blind receiver knows: the accumulated chromatic dispersion of the link (dsp4cohdec's p.applydcf,
+        dsp4cohdec.m:200-210, as an all-pass filter): one linear step with the dispersion of all spans negated.  The PMD
+        stays in the field for the polarization demultiplexer."""
+        s = self.setup
+        if getattr(self, '_cd', None) is None:
+            sc = dict(s.scalars)
+            sc.update(b30=-sc['b30'], dgdrms=0.0, beta1=-np.asarray(sc['beta1']), beta2=-np.asarray(sc['beta2']))
+            total = s.length * self.nspan
+            inv = FiberSetup(nfft=s.nfft, nfc=s.nfc, fls=(s.fls[0], 0, 0, 0), dphimaxt=math.inf, dzmaxt=total, length=total,
+                             alphalin=0.0, gam=s.gam, betat=-s.betat, db1=np.zeros_like(s.db1), manakov=False, nplates=1,
+                             brf={'db0': np.zeros(1), 'theta': np.zeros(1), 'epsilon': np.zeros(1)}, isv=True, isy=True,
+                             b1=s.b1, dch=s.dch, scalars=sc)
+            desc, keep = setup_to_desc(inv, batch=self.batch, plate_sets=1)
+            self._cd = _lib.Plan(self.ctx, desc, keep)
+        self._cd.execute(field)
+
 
 # ------------------------------------------------------------------------------------------
 @dataclass
@@ -178,8 +195,16 @@ class McRunner:
     integer all-reduce."""
 
     def __init__(self, ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int,
-                 gain_db: float, nf_db: float, nreal: int, batch: int, rank: int = 0, world: int = 1):
+                 gain_db: float, nf_db: float, nreal: int, batch: int, rank: int = 0, world: int = 1,
+                 receiver: str = 'genie', dsp_params=None):
+        """receiver: 'genie' -- ideal linear equaliser from the known plates + data-aided decision (pmx_qpsk_count);
+        'blind' -- chromatic dispersion compensated, then the DSP core of dsp4cohdec (CMA polarization demultiplexer,
+        Viterbi & Viterbi carrier recovery, differential decision: pmx_dsp_count, polmux_b200/dsp.py)"""
         import torch
+        from . import dsp as _dsp
+        self.receiver, self.dsp_params = receiver, dict(dsp_params or {})
+        self.ref_patmat = _dsp.reference_pattern(np.asarray(sym)[0], np.asarray(sym)[1]) if receiver == 'blind' else None
+        self.passes = []
         self.ctx, self.setup, self.sym, self.nsymb, self.nt = ctx, setup, sym, nsymb, nt
         self.nreal, self.batch, self.rank, self.world = nreal, batch, rank, world
         self.r0, self.r1 = shard(nreal, rank, world)
@@ -202,8 +227,14 @@ class McRunner:
             self.link.retarget(g0)
             self.work.broadcast_from(self.tx)
             sa_steps += self.link.run(self.work, ase_seed)
-            self.link.equalize(self.work)
-            _lib.qpsk_count(self.ctx, self.work, self.sym, self.nsymb, self.nt, self.buf.data_ptr())   # writes the send buffer
+            if self.receiver == 'blind':
+                from . import dsp as _dsp
+                self.link.cd_compensate(self.work)
+                self.passes.append(_dsp.dsp_count(self.ctx, self.work, self.nsymb, self.nt, self.ref_patmat,
+                                                  self.buf.data_ptr(), **self.dsp_params))
+            else:
+                self.link.equalize(self.work)
+                _lib.qpsk_count(self.ctx, self.work, self.sym, self.nsymb, self.nt, self.buf.data_ptr())   # writes the send buffer
             self.ctx.sync()
             self.local[g0 - self.r0:g0 - self.r0 + nb] = self.buf[:nb]
         counts = allreduce_counts(self.local, self.r0, self.nreal)

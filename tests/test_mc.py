@@ -211,3 +211,31 @@ def test_native_mc_run_matches_the_torch_driven_path(ctx):
         got2, sa2 = mc.run_mc_native(setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 16.0, 18.0, nreal, batch,
                                      devices=(0, 1), ase_seed=5)
         assert np.array_equal(got2, ref) and sa2 == sa_ref
+
+
+@pytest.mark.gpu
+def test_mc_with_the_blind_receiver(ctx):
+    """McRunner(receiver='blind'): link -> dispersion compensation -> CMA + Viterbi & Viterbi + differential decision
+    (pmx_dsp_count) instead of the genie equaliser; at a comfortable OSNR both receivers count (almost) no errors, and
+    the blind one does not read the plates"""
+    from polmux_b200.fiber import fiber_setup
+    nsymb, nt, nspan, nreal, batch = 1 << 11, 16, 2, 4, 2
+    ex, ey, sx, sy = synth.pdm_qpsk(nsymb, nt, 1)
+    pmx.reset_all(nsymb, nt, 1)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.LAMBDA, G.POWER = 28.0, np.array([1550.0]), np.array([1.0])
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    fib = dict(synth.SMF)
+    fib.update(length=4e4, dgd=0.3, nplates=20, manakov='yes')
+    setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
+    sym = np.stack([sx[:, 0], sy[:, 0]]).astype(np.uint8)
+    out = {}
+    for rec in ('genie', 'blind'):
+        r = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 8.0, 5.0, nreal, batch, receiver=rec,
+                        dsp_params=dict(mu=1 / 2000, freqavg=200))
+        out[rec], _ = r.run(ase_seed=9)
+        if rec == 'blind':
+            assert len(r.passes) == nreal // batch and all(p.min() >= 1 for p in r.passes)
+        r.close()
+    assert out['genie'].sum() == 0
+    assert out['blind'].sum() <= 8          # differential decoding doubles isolated errors; none expected here
