@@ -171,6 +171,12 @@ struct CtaFFT {
     // x[q], y[q] hold element t + q*T on entry and on exit (natural order).  tw: shared-memory
     // copy of the per-L stage table.
     __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t, const cpx* tw) {
+        run(x, y, sx, sy, t, tw, [] {});
+    }
+    // on_free(): called by every thread as soon as the exchange buffer has been read for the last time (before the last
+    // butterfly stage), so that a caller whose next tile lands in that buffer can issue its load that much earlier
+    template <typename F>
+    __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t, const cpx* tw, F&& on_free) {
         constexpr int NB = 8 / R0;
         // ---- first stage
         if constexpr (R0 == 8) {
@@ -188,7 +194,10 @@ struct CtaFFT {
                 }
             }
         }
-        if constexpr (R0 == L) return;
+        if constexpr (R0 == L) {
+            on_free();
+            return;
+        }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const int j0 = (t + b * T) * R0;
@@ -206,6 +215,7 @@ struct CtaFFT {
                 pmx_ex_ld(sx, sy, pmx_sw(t + q * T), x[q], y[q]);
             }
             __syncthreads();  // everyone has read the exchange buffer: free for the next stage / the caller
+            if (ns * 8 >= L) on_free();
             // ---- radix-8 stage with ns sub-transforms done
             const int k = t & (ns - 1);
             {
@@ -283,6 +293,10 @@ template <typename R>
 struct CtaFFT<R, 1024> {
     static constexpr int L = 1024, T = 128;
     __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t, const cpx* tw) {
+        run(x, y, sx, sy, t, tw, [] {});
+    }
+    template <typename F>
+    __device__ __forceinline__ static void run(cpx (&x)[8], cpx (&y)[8], cpx* sx, cpx* sy, int t, const cpx* tw, F&& on_free) {
         // ---- stage A: radix 8, no twiddles; butterfly j = t, inputs t + r*128, outputs 8*t + r
         dft8<false>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         dft8<false>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
@@ -314,6 +328,7 @@ struct CtaFFT<R, 1024> {
             y[q] = sy[o];
         }
         __syncthreads();  // everyone has read the exchange buffer: free for the caller
+        on_free();
         // ---- stage C: radix 8, Ns = 128: twiddles W_1024^(t*r), natural-order output t + r*128
         {
             const cpx* tc = tw + 15 * 8;

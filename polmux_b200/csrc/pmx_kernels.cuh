@@ -588,10 +588,19 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
+#if defined(PMX_AC_LDG) || defined(PMX_AC_LATE_ISSUE)
         CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
 #ifndef PMX_AC_LDG
         if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);  // the exchange buffer is free again
+#endif
+#else
+        // the next tile lands in the exchange buffer: its load goes out as soon as the last exchange is read, under the
+        // last butterfly stage and the store
+        CtaFFT<R, L>::run(x, y, sx, sy, t, stw, [&] {
+            if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+        });
+        PMX_T_MARK(4)
 #endif
         // four-step twiddle W_N^(n2*k1), k1 = t + q*T, from the row's two-level table; straight to HBM (the row is
         // contiguous: 32 lanes x 32 B per store instruction)
@@ -1254,10 +1263,17 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_C(G*(L / 8), PF))
         cpx* sx = work + rl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
         PMX_T_MARK(3)
+#if defined(PMX_AC_LDG) || defined(PMX_AC_LATE_ISSUE)
         CtaFFT<R, L>::run(x, y, sx, sy, t, stw);
         PMX_T_MARK(4)
 #ifndef PMX_AC_LDG
         if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+#endif
+#else
+        CtaFFT<R, L>::run(x, y, sx, sy, t, stw, [&] {
+            if (!PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
+        });
+        PMX_T_MARK(4)
 #endif
         {
             cpx* base = reinterpret_cast<cpx*>(p.field) + ((size_t)bc * N + (size_t)(row0 + rl) * L) * 2;
