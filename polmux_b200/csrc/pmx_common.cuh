@@ -32,6 +32,22 @@ __host__ __device__ __forceinline__ cpx mkc(real a, real b) { return make_double
 
 #define PMX_MAX_NFC 16
 
+// Debug builds (make EXTRA=-DPMX_DEBUG, `make debug`): index checks in the tile walks and the bin arithmetic; the
+// compute-sanitizer is not available on the pool, these traps stand in for its bounds checks.
+#ifdef PMX_DEBUG
+#include <cstdio>
+#define PMX_ASSERT(cond)                                                                                  \
+    do {                                                                                                  \
+        if (!(cond)) {                                                                                    \
+            printf("PMX_ASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                     \
+            __trap();                                                                                     \
+        }                                                                                                 \
+    } while (0)
+#else
+#define PMX_ASSERT(cond) ((void)0)
+#endif
+
 enum { PMX_ST_RUN = 0, PMX_ST_LAST = 1, PMX_ST_DONE = 2, PMX_ST_ERROR = 3 };
 // Basis bookkeeping of the PMD product.  The reference goes laboratory -> PSP basis of the first trunk at the
 // start of every linear step and back at its end (fiber.m:920-921,931-932).  When the nonlinear step is a

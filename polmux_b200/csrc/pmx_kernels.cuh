@@ -558,6 +558,8 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         const int tt = wk.phys(tile), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
+        PMX_ASSERT(tt >= 0 && tt < total && bc < p.batch * f.nfc && b < p.batch && col < f.nfc && b * f.nfc + col == bc);
+        PMX_ASSERT(row0 + G <= p.N2 && L == p.N1);
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
         const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
         const cpx* gtab = reinterpret_cast<const cpx*>(aux + S::PKG_BYTES);
@@ -761,6 +763,8 @@ __device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const 
                                                 double dfn, bool any_full) {
     constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
     const int ntrunk = st->ntrunk, bmode = st->bmode;
+    PMX_ASSERT((size_t)k1 + (size_t)p.N1 * (size_t)(t + 7 * T) < N && ntrunk >= 0 && st->n_first >= 0 &&
+               st->n_first + ntrunk <= f.nplates);
     (void)scr;
     (void)scr_stride;
     (void)fn0;
@@ -1046,6 +1050,8 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         int b, col;
         pmx_split_bc(bc, f, b, col);
         const int k1 = c0 + cl;
+        PMX_ASSERT(tt >= 0 && tt < total && bc < p.batch * f.nfc && b < p.batch && col < f.nfc && b * f.nfc + col == bc);
+        PMX_ASSERT(k1 < p.N1 && L == p.N2);
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
         const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
         const int next = live(tile + gridDim.x);
@@ -1221,6 +1227,8 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_C(G*(L / 8), PF))
         const int tt = wk.phys(tile), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
         int b, col;
         pmx_split_bc(bc, f, b, col);
+        PMX_ASSERT(tt >= 0 && tt < total && bc < p.batch * f.nfc && b < p.batch && col < f.nfc && b * f.nfc + col == bc);
+        PMX_ASSERT(row0 + G <= p.N2 && L == p.N1);
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
         const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
         const cpx* gtab = reinterpret_cast<const cpx*>(aux + S::PKG_BYTES);

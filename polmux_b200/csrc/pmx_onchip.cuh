@@ -79,6 +79,7 @@ __global__ void __launch_bounds__((L / 8) < 32 ? 32 : (L / 8), 1) pmx_k_onchip(P
     cpx* fld = reinterpret_cast<cpx*>(p.field) + (size_t)(b * f.nfc + col) * N * 2;
     // position of time sample n in the resident column (transposed four-step layout for 2^12, natural order below)
     auto mem = [&](int n) { return (size_t)(((n & ((1 << p.log2N2) - 1)) << p.log2N1) + (n >> p.log2N2)); };
+    PMX_ASSERT(col < f.nfc && b < p.batch && mem(L - 1) < N && (int)blockDim.x >= T && (int)gridDim.x == f.nfc);
 
     pmx_load_stage_tw<L>(stw, p.tw_stage);
     for (int i = t; i < (int)(sizeof(StepCtl) / 4); i += blockDim.x) reinterpret_cast<int*>(c)[i] = 0;
