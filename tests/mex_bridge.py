@@ -118,6 +118,22 @@ def oracle_gateway(log=None):
 
     def call(it, a, nargout):
         cmd = a[0]
+        if cmd == 'ampliflat':                             # [ux,uy] = ssfm_mex('ampliflat', ux, uy, gain, sigma, noise, asepol, opt)
+            ux, uy, gain, sigma, noise, asepol = a[1:7]
+            g = float(np.asarray(gain).ravel()[0])
+            sg = np.asarray(sigma, dtype=np.float64).reshape(1, -1)
+            ox, oy = np.asarray(ux) * math.sqrt(g), np.asarray(uy) * math.sqrt(g)
+            nz = np.asarray(noise)
+            nfc = ox.shape[1]
+            if np.any(sg) and nz.size == 2 * ox.size:      # options.noise (ampliflat.m:123-129)
+                pol = int(np.asarray(asepol).ravel()[0])
+                if pol & 1:
+                    ox = ox + sg * nz[:, :nfc]
+                if pol & 2:
+                    oy = oy + sg * nz[:, nfc:]
+            elif np.any(sg):
+                raise NotImplementedError('the oracle-backed gateway takes injected noise only')
+            return [ox, oy][:max(nargout, 1)]
         if cmd != 'fiber':
             raise NotImplementedError(cmd)
         ux, uy, betat, db1, P, gam, fls, plates, scal = a[1:10]

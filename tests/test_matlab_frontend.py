@@ -129,6 +129,62 @@ def test_front_end_errors_like_the_original():
         it.call('fiber', [to_m(dict(m['fiber'], ltol=1e-6)), 'g-s-'], 0)
 
 
+@needs_ref
+@pytest.mark.parametrize('script', ['Run_my_PDM_QPSK', 'ex24_pmd', 'ex06_ber'])
+def test_script_call_sequences_run_unchanged(script):
+    """The in-line device calls of the reference's scripts, verbatim, with matlab/ first on the path against the toolbox
+    alone: Run_my_PDM_QPSK.m:117-122 (create_field('sepfields',...); fiber(fib,'g---')), ex24_pmd.m:78-100 (a PMF given by
+    scalar db0/theta/epsilon: fiber(tx,'gp--'); ampliflat(Gerbio,'gain')) and the span loop of ex06_ber.m:110-115
+    (fiber(tx,'g-sx'); fiber(comp,'g-sx'); ampliflat(Gerbio,'gain',ampli) with injected noise)"""
+    out = {}
+    for path in ([REF], [MDIR, REF]):
+        it = Interp(path, rng=np.random.Generator(np.random.PCG64(3)))
+        if len(path) == 2:
+            it.builtins['ssfm_mex'] = mex_bridge.oracle_gateway()
+        it.globals['PMXOPT'] = np.zeros((0, 0))
+        if script == 'Run_my_PDM_QPSK':
+            nsymb, nt, nch = 64, 16, 1
+            ex, ey, _, _ = synth.pdm_qpsk(nsymb, nt, nch)
+            fib = dict(length=1e3, alphadB=0.2, aeff=80.0, n2=2.7e-20, **{'lambda': 1550.0}, disp=17.0, slope=0.0, dphimax=5e-3,
+                       dzmax=2e4, dgd=1.0, nplates=10.0, manakov='no')
+            calls = [('create_field', ['sepfields', to_m(ex), to_m(ey), MStruct({'power': 'average'})]),
+                     ('fiber', [to_m(fib), 'g---'])]
+        elif script == 'ex24_pmd':
+            nsymb, nt, nch = 32, 32, 1
+            ex, _, _, _ = synth.pdm_qpsk(nsymb, nt, nch)
+            tx = dict(length=1e5, alphadB=0.2, aeff=80.0, n2=2.7e-20, **{'lambda': 1550.0}, disp=17.0, slope=0.0, dphimax=5e-3,
+                      dzmax=2e4, db0=0.0, theta=np.pi / 4, epsilon=np.pi / 4, dgd=0.5, nplates=20.0)
+            calls = [('create_field', ['unique', to_m(ex), to_m(np.zeros_like(ex))]),
+                     ('fiber', [to_m(tx), 'gp--']), ('ampliflat', [to_m(20.0), 'gain'])]
+        else:
+            nsymb, nt, nch = 32, 32, 1
+            ex, _, _, _ = synth.pdm_qpsk(nsymb, nt, nch)
+            tx = dict(length=1e5, alphadB=0.2, aeff=80.0, n2=2.7e-20, **{'lambda': 1550.0}, disp=17.0, slope=0.0, dphimax=3e-3,
+                      dzmax=2e4)
+            comp = dict(tx, length=1.7e4, alphadB=0.6, aeff=20.0, disp=-100.0)
+            g = np.random.Generator(np.random.PCG64(8))
+            calls = [('create_field', ['unique', to_m(ex), np.zeros((0, 0)), MStruct({'power': 'average'})])]
+            for k in range(2):
+                noise = g.standard_normal((nsymb * nt, 2)) + 1j * g.standard_normal((nsymb * nt, 2))
+                calls += [('fiber', [to_m(tx), 'g-sx']), ('fiber', [to_m(comp), 'g-sx']),
+                          ('ampliflat', [to_m(30.2), 'gain', MStruct({'f': to_m(6.0), 'noise': noise})])]
+        it.call('reset_all', [to_m(nsymb), to_m(nt), to_m(nch)], 0)
+        G = it.globals['GSTATE'].copy()
+        G['SYMBOLRATE'], G['LAMBDA'], G['POWER'] = to_m(10.0), to_m(np.array([[1550.0]])), to_m(np.array([[4.0]]))
+        it.globals['GSTATE'] = G
+        for name, args in calls:
+            it.call(name, args, 0)
+        G = it.globals['GSTATE']
+        out[len(path)] = (np.array(G['FIELDX']), np.array(G['FIELDY']), np.array(G['DELAY']), np.array(G['DISP']))
+    a, b = out[1], out[2]
+    assert a[0].shape == b[0].shape and a[1].shape == b[1].shape
+    assert np.linalg.norm(a[0] - b[0]) <= 1e-13 * np.linalg.norm(a[0])
+    if a[1].size:
+        assert np.linalg.norm(a[1] - b[1]) <= 1e-13 * max(np.linalg.norm(a[1]), 1e-300) + 1e-18
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(b[3], a[3], rtol=1e-13, atol=1e-13)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _gpu_interp(seed):
     it = Interp([MDIR], rng=np.random.Generator(np.random.PCG64(seed)))
