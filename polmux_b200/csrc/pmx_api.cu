@@ -1629,77 +1629,85 @@ __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t
     }
 }
 
-// cmapolardemux: thread 0 of a CTA runs filter 1 (h1 -> Y1), thread 1 filter 2; sums in the interpreter's order
-// (column by column, then across the two columns), products and sums rounded separately.
-__global__ void __launch_bounds__(32) pmx_k_dsp_cma(const cpx* sig, cpx* out, int L, int taps, double mu, double r1, double r2,
+// cmapolardemux: four threads per realization, one per (filter, input column): thread (f, p) keeps the taps h_f(:, p),
+// forms the column sum sum_j xx(k+j, p) * h_f(j, p) in the interpreter's order (products and sums rounded separately,
+// j ascending), the two column sums of a filter are added through a shuffle (column 0 + column 1, as sum(sum(.)) does),
+// and each thread updates its own taps.  The same arithmetic as one thread per filter, half the dependent chain.
+// (TAPS is a template parameter so that the taps and the input window live in registers)
+template <int TAPS>
+__global__ void __launch_bounds__(32) pmx_k_dsp_cma(const cpx* sig, cpx* out, int L, double mu, double r1, double r2,
                                                     double phizero, int repetitions, int* passes) {
-    const int b = blockIdx.x, f = threadIdx.x;   // f: which of the two filters
-    if (f >= 2) return;
-    const cpx* x0 = sig + (size_t)b * 2 * L;      // column 0 (X)
-    const cpx* x1 = x0 + L;                       // column 1 (Y)
+    constexpr int taps = TAPS;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (lane >= 4) return;
+    const int f = lane >> 1, p = lane & 1;          // filter, input column
+    const cpx* xin = sig + ((size_t)b * 2 + p) * L;
     cpx* y = out + ((size_t)b * 2 + f) * L;
     const int half = taps / 2;
     const double R = f == 0 ? r1 : r2;
-    cpx h[2][PMX_DSP_MAX_TAPS], ho[2][PMX_DSP_MAX_TAPS];
-    for (int j = 0; j < taps; ++j) h[0][j] = h[1][j] = make_double2(0.0, 0.0);
-    // hzero(halftaps+1,:,:) = M = [cos sin; -sin cos]; filter f takes row f
-    h[0][half] = make_double2(f == 0 ? cos(phizero) : -sin(phizero), 0.0);
-    h[1][half] = make_double2(f == 0 ? sin(phizero) : cos(phizero), 0.0);
+    cpx h[TAPS], ho[TAPS];
+#pragma unroll
+    for (int j = 0; j < taps; ++j) h[j] = make_double2(0.0, 0.0);
+    // hzero(halftaps+1,:,:) = M = [cos sin; -sin cos]; filter f takes row f, this thread its entry p
+    h[half] = make_double2(f == 0 ? (p == 0 ? cos(phizero) : sin(phizero)) : (p == 0 ? -sin(phizero) : cos(phizero)), 0.0);
     int c = 1;
     bool conv = false;
     while (!conv && c < repetitions) {
-        for (int j = 0; j < taps; ++j) {
-            ho[0][j] = h[0][j];
-            ho[1][j] = h[1][j];
+#pragma unroll
+        for (int j = 0; j < taps; ++j) ho[j] = h[j];
+        cpx w[TAPS];   // sliding window extendedx(k .. k+taps-1) = x(k - half .. k + half) circularly
+#pragma unroll
+        for (int j = 1; j < taps; ++j) {
+            int i = j - 1 - half;
+            i = i < 0 ? i + L : i;
+            w[j] = xin[i % L];
         }
         for (int k = 0; k < L; ++k) {
-            cpx s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-            cpx w0[PMX_DSP_MAX_TAPS], w1[PMX_DSP_MAX_TAPS];
-            for (int j = 0; j < taps; ++j) {   // extendedx(k + j) = x(k + j - half) circularly
-                int i = k + j - half;
-                i = i < 0 ? i + L : (i >= L ? i - L : i);
-                w0[j] = x0[i];
-                w1[j] = x1[i];
-                const cpx p0 = make_double2(__dadd_rn(__dmul_rn(w0[j].x, h[0][j].x), -__dmul_rn(w0[j].y, h[0][j].y)),
-                                            __dadd_rn(__dmul_rn(w0[j].x, h[0][j].y), __dmul_rn(w0[j].y, h[0][j].x)));
-                const cpx p1 = make_double2(__dadd_rn(__dmul_rn(w1[j].x, h[1][j].x), -__dmul_rn(w1[j].y, h[1][j].y)),
-                                            __dadd_rn(__dmul_rn(w1[j].x, h[1][j].y), __dmul_rn(w1[j].y, h[1][j].x)));
-                s0 = make_double2(__dadd_rn(s0.x, p0.x), __dadd_rn(s0.y, p0.y));
-                s1 = make_double2(__dadd_rn(s1.x, p1.x), __dadd_rn(s1.y, p1.y));
+            cpx s = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j + 1 < taps; ++j) w[j] = w[j + 1];
+            {
+                int i = k + half;
+                w[taps - 1] = xin[i >= L ? i - L : i];
             }
-            const cpx yk = make_double2(__dadd_rn(s0.x, s1.x), __dadd_rn(s0.y, s1.y));
-            y[k] = yk;
+#pragma unroll
+            for (int j = 0; j < taps; ++j) {
+                const cpx q = make_double2(__dadd_rn(__dmul_rn(w[j].x, h[j].x), -__dmul_rn(w[j].y, h[j].y)),
+                                           __dadd_rn(__dmul_rn(w[j].x, h[j].y), __dmul_rn(w[j].y, h[j].x)));
+                s = make_double2(__dadd_rn(s.x, q.x), __dadd_rn(s.y, q.y));
+            }
+            const double ox = __shfl_xor_sync(0xfu, s.x, 1), oy = __shfl_xor_sync(0xfu, s.y, 1);
+            const cpx yk = p == 0 ? make_double2(__dadd_rn(s.x, ox), __dadd_rn(s.y, oy))     // column 0 + column 1
+                                  : make_double2(__dadd_rn(ox, s.x), __dadd_rn(oy, s.y));
+            if (p == 0) y[k] = yk;
             // incr = mu .* errorfuncma(Y, R) .* conj(xx):  E = Y .* (R - abs(Y).^2)
             const double a = hypot(yk.x, yk.y), g = __dadd_rn(R, -__dmul_rn(a, a));
             const cpx e = make_double2(__dmul_rn(mu, __dmul_rn(yk.x, g)), __dmul_rn(mu, __dmul_rn(yk.y, g)));
-            for (int j = 0; j < taps; ++j) {
-                h[0][j] = make_double2(__dadd_rn(h[0][j].x, __dadd_rn(__dmul_rn(e.x, w0[j].x), __dmul_rn(e.y, w0[j].y))),
-                                       __dadd_rn(h[0][j].y, __dadd_rn(__dmul_rn(e.y, w0[j].x), -__dmul_rn(e.x, w0[j].y))));
-                h[1][j] = make_double2(__dadd_rn(h[1][j].x, __dadd_rn(__dmul_rn(e.x, w1[j].x), __dmul_rn(e.y, w1[j].y))),
-                                       __dadd_rn(h[1][j].y, __dadd_rn(__dmul_rn(e.y, w1[j].x), -__dmul_rn(e.x, w1[j].y))));
-            }
+#pragma unroll
+            for (int j = 0; j < taps; ++j)
+                h[j] = make_double2(__dadd_rn(h[j].x, __dadd_rn(__dmul_rn(e.x, w[j].x), __dmul_rn(e.y, w[j].y))),
+                                    __dadd_rn(h[j].y, __dadd_rn(__dmul_rn(e.y, w[j].x), -__dmul_rn(e.x, w[j].y))));
         }
         // (the reference keeps the old taps when the new ones are all zero: any(any(h_new)), dsp4cohdec.m:404-407)
         double moved = 0.0, nz = 0.0;
-        for (int j = 0; j < taps; ++j)
-            for (int p = 0; p < 2; ++p) {
-                moved = fmax(moved, hypot(ho[p][j].x - h[p][j].x, ho[p][j].y - h[p][j].y));
-                nz = fmax(nz, fmax(fabs(h[p][j].x), fabs(h[p][j].y)));
-            }
-        const double moved_o = __shfl_xor_sync(0x3u, moved, 1), nz_o = __shfl_xor_sync(0x3u, nz, 1);
-        if (fmax(nz, nz_o) == 0.0) {
-            for (int j = 0; j < taps; ++j) {
-                h[0][j] = ho[0][j];
-                h[1][j] = ho[1][j];
-            }
+#pragma unroll
+        for (int j = 0; j < taps; ++j) {
+            moved = fmax(moved, hypot(ho[j].x - h[j].x, ho[j].y - h[j].y));
+            nz = fmax(nz, fmax(fabs(h[j].x), fabs(h[j].y)));
+        }
+        for (int o = 1; o < 4; o <<= 1) {   // over both filters and both columns
+            moved = fmax(moved, __shfl_xor_sync(0xfu, moved, o));
+            nz = fmax(nz, __shfl_xor_sync(0xfu, nz, o));
+        }
+        if (nz == 0.0) {
+#pragma unroll
+            for (int j = 0; j < taps; ++j) h[j] = ho[j];
             moved = 0.0;
-        } else {
-            moved = fmax(moved, moved_o);
         }
         if (moved < 5e-5) conv = true;
         ++c;
     }
-    if (f == 0 && passes) passes[b] = c - 1;
+    if (lane == 0 && passes) passes[b] = c - 1;
 }
 
 // Carrier recovery of one (realization, polarization) stream by one thread: frequency estimate (navg = freqavg) ->
@@ -1872,7 +1880,12 @@ extern "C" int pmx_dsp_count(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d,
     const cpx* stream_in = sig;
     if (d->apply_cma) {
         const int rep = d->max_passes > 0 ? d->max_passes + 1 : 50 * (int)ceil(1.0 / ((double)L * d->mu));
-        pmx_k_dsp_cma<<<B, 32, 0, c->stream>>>(sig, y, L, d->taps, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass);
+        switch (d->taps) {
+#define PMX_CMA_CASE(T) case T: pmx_k_dsp_cma<T><<<B, 32, 0, c->stream>>>(sig, y, L, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass); break;
+            PMX_CMA_CASE(1) PMX_CMA_CASE(3) PMX_CMA_CASE(5) PMX_CMA_CASE(7) PMX_CMA_CASE(9) PMX_CMA_CASE(11) PMX_CMA_CASE(13)
+            PMX_CMA_CASE(15)
+#undef PMX_CMA_CASE
+        }
         stream_in = y;
         c->launches++;
     }
