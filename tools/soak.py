@@ -1,5 +1,8 @@
 """Stress run over sizes, batches, flags and precisions: every execute must return, with finite fields and a sane
-step count (looks for hangs / races in the persistent kernels, not for accuracy -- the tests do that).
+step count (looks for hangs / races in the persistent kernels), and the FP32 result must agree with the FP64 one to
+1e-4 -- the two precisions take different code paths through the per-bin physics (FP64: difference recurrence, K-form
+boundary matrices, common-scalar extraction; FP32: per-bin phasors, plain matrices), so their agreement over all sizes,
+column counts, flags and batches is an independent cross-check of both.
 Usage: python tools/soak.py [repeats]"""
 import os, sys, time
 import numpy as np
@@ -14,11 +17,11 @@ REP = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 ctx = _lib.Context(0)
 t00 = time.time()
 nrun = 0
-for lg in (12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22):
-    nsymb, nt = 1 << (lg - 4), 16
+for lg in (6, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22):
+    nsymb, nt = 1 << (lg - 3), 8
     N = nsymb * nt
-    for nch, ftype in ((1, 'unique'), (3, 'sepfields')):
-        if nch == 3 and lg > 18:
+    for nch, ftype in ((1, 'unique'), (3, 'sepfields'), (8, 'sepfields')):
+        if (nch == 3 and lg > 18) or (nch == 8 and lg > 12):
             continue
         ex, ey, _, _ = synth.pdm_qpsk(nsymb, nt, nch)
         pmx.reset_all(nsymb, nt, nch)
@@ -31,6 +34,7 @@ for lg in (12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22):
             setup = fiber_setup(fib, flag, rng=np.random.Generator(np.random.PCG64(lg)))
             nfc = setup.nfc
             for batch in ((1, 3, 8) if lg <= 20 else (1, 2)):
+                fields = {}
                 for prec in ('f64', 'f32'):
                     pc = _lib.PMX_F64 if prec == 'f64' else _lib.PMX_F32
                     d = [mc.draw_plates(7 + b, setup.nplates) for b in range(batch)]
@@ -50,7 +54,15 @@ for lg in (12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22):
                     if not ok:
                         print('BAD', lg, nch, flag, man, batch, prec, res.ncycle.tolist(), flush=True)
                         sys.exit(1)
+                    fields[prec] = (x, y)
                     plan.close()
                     del work, tx
-    print('N=2^%d ok (%d executes so far, %.0f s)' % (lg, nrun, time.time() - t00), flush=True)
+                a, b = fields['f64'], fields['f32']
+                err = np.sqrt((np.abs(a[0] - b[0]) ** 2).sum() + (np.abs(a[1] - b[1]) ** 2).sum()) / np.sqrt(
+                    (np.abs(a[0]) ** 2).sum() + (np.abs(a[1]) ** 2).sum())
+                worst = max(globals().get('worst', 0.0), err)
+                if err > 1e-4:
+                    print('FP32/FP64 DISAGREE', lg, nch, flag, man, batch, err, flush=True)
+                    sys.exit(1)
+    print('N=2^%d ok (%d executes so far, %.0f s; largest FP32-FP64 rel-L2 %.1e)' % (lg, nrun, time.time() - t00, worst), flush=True)
 print('soak passed: %d executes' % nrun, flush=True)
