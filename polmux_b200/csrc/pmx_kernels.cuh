@@ -282,13 +282,9 @@ struct PmxTw4 {
 
 #define PMX_LIVE_CAP 64    // realizations whose done-flags a CTA caches in shared memory
 
-// Pass B, FP64: per-thread phasors that depend on the tile's bins and the step only (not on the field) are evaluated
-// BEFORE the CTA waits for its tile and parked here while the forward transform needs the registers.
-#ifdef PMX_F32
-#define PMX_B_SCR 0
-#else
+// Pass B: per-thread phasors (double2 in both builds) that depend on the tile's bins and the step only (not on the
+// field) are evaluated BEFORE the CTA waits for its tile and parked here while the forward transform needs the registers.
 #define PMX_B_SCR 6
-#endif
 
 // Shared-memory plan of a pass CTA working on G rows (pass B) or G columns (passes A, C) of
 // length L.  PF: the next tile is prefetched by TMA into its own landing buffer while the
@@ -310,7 +306,7 @@ struct PassSmem {
     static constexpr int AUX_OFF = TW_OFF + ((pmx_tw_total(L) * (int)sizeof(cpx) + 15) / 16) * 16;
     static constexpr int PLATE_OFF = AUX_OFF + 2 * AUX_BYTES;               // pass B: chunks of trunks beyond the package
     static constexpr int SCR_OFF = PLATE_OFF + ((KIND == 1) ? PMX_PKG_PLATES * (int)sizeof(PlateConst) : 0);
-    static constexpr int SCR_BYTES = (KIND == 1) ? PMX_B_SCR * THREADS * (int)sizeof(cpx) : 0;   // [PMX_B_SCR][THREADS]
+    static constexpr int SCR_BYTES = (KIND == 1) ? PMX_B_SCR * THREADS * (int)sizeof(double2) : 0;   // [PMX_B_SCR][THREADS]
     static constexpr int RED_OFF = SCR_OFF + SCR_BYTES;
     static constexpr int LIVE_OFF = RED_OFF + 32 * 8;
     static constexpr int MBAR_OFF = LIVE_OFF + PMX_LIVE_CAP;
@@ -647,22 +643,33 @@ __device__ __forceinline__ void pmx_apply2x2(cpx (&x)[8], cpx (&y)[8], const dou
     }
 }
 
-// FP64, scalar dispersion mode: what a thread of pass B knows about its eight bins before the field arrives.
+// Scalar dispersion mode: what a thread of pass B knows about its eight bins before the field arrives.
 // The bins k = k1 + N1*(t + q*T) are equally spaced in frequency; in rising order they are q = 4..7 (negative
 // frequencies) then q = 0..3, so with j = (q + 4) & 7 the angular frequency is wb + j*domega.
+// The phasors below are DOUBLE in both builds (phases reach 1e3..1e5 rad and progressions over a step's trunks must not
+// repeat a float rounding error): they are rounded to the field's precision where they meet the data.
+typedef double2 dcpx;
+__device__ __forceinline__ dcpx dmk(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ dcpx dmul(dcpx a, dcpx b) { return dmk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ dcpx dmulc(dcpx a, dcpx b) { return dmk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a*conj(b)
+__device__ __forceinline__ dcpx dcis(double a) {
+    dcpx e;
+    pmx_sincos_fast(a, &e.y, &e.x);
+    return e;
+}
+__device__ __forceinline__ cpx pmx_to_cpx(dcpx e) { return mkc((real)e.x, (real)e.y); }
 struct PmxBPre {
-    cpx E, D1, D2;    // common phase exp(i*phi(j)), phi = -betat*dz: value, first and second difference at j = 4
-    cpx E0, pf, pl;   // exp(-i*db1/2) (whole trunks), first / last trunk phasor (partial trunks), all at j = 0
+    dcpx E, D1, D2;    // common phase exp(i*phi(j)), phi = -betat*dz: value, first and second difference at j = 4
+    dcpx E0, pf, pl;   // exp(-i*db1/2) (whole trunks), first / last trunk phasor (partial trunks), all at j = 0
 };
 
-#ifndef PMX_F32
 // phi(w) = -dz*(b1*w + b2/2*w^2 + b30/6*w^3) at w = wc; its forward differences over the bin spacing d are evaluated
 // from their closed forms (no cancellation):
 //   D1 = phi(w+d) - phi(w)   = -dz*d*(b1 + b2*(w + d/2) + b30_6*(3*w*(w + d) + d*d))
 //   D2 = D1(w+d) - D1(w)     = -dz*d*d*(b2 + 6*b30_6*(w + d))
 //   D3                        = -dz*6*b30_6*d^3          (per step: StepPkg.gd3)
 // The six phasors go straight to the thread's scratch slots scr[slot*stride] (PmxBPre order).
-__device__ __forceinline__ void pmx_b_pre(cpx* scr, int stride, const StepPkg* st, const FiberConst& f, int col, double fnb,
+__device__ __forceinline__ void pmx_b_pre(dcpx* scr, int stride, const StepPkg* st, const FiberConst& f, int col, double fnb,
                                           double fnc, bool any_full) {
     const double wb = __dmul_rn(f.w0, fnb);   // lowest bin (j = 0): base of the trunk phasor progressions
     if (f.gvd_any) {
@@ -674,16 +681,16 @@ __device__ __forceinline__ void pmx_b_pre(cpx* scr, int stride, const StepPkg* s
         const double ndzd = -(dz * d);
         const double a1 = ndzd * (b1 + fma(b2, fma(0.5, d, wc), f.b30_6 * fma(3.0 * wc, wc + d, d * d)));
         const double a2 = ndzd * d * fma(6.0 * f.b30_6, wc + d, b2);
-        scr[0 * stride] = pmx_cis(-(bt * dz));
-        scr[1 * stride] = pmx_cis(a1);
-        scr[2 * stride] = pmx_cis(a2);
+        scr[0 * stride] = dcis(-(bt * dz));
+        scr[1 * stride] = dcis(a1);
+        scr[2 * stride] = dcis(a2);
     }
     if (f.pmd) {
         const double d1b = __dmul_rn(f.dgdrms, wb);  // db1 = dgdrms*omega (:358)
-        scr[3 * stride] = any_full ? pmx_cis(-0.5 * d1b) : mkc(1.0, 0.0);
+        scr[3 * stride] = any_full ? dcis(-0.5 * d1b) : dmk(1.0, 0.0);
         // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925)
-        scr[4 * stride] = pmx_cis(-(0.5 * (d1b + st->plates[0].db0) * st->dzb_first / f.lcorr));
-        scr[5 * stride] = pmx_cis(-(0.5 * (d1b + st->db0_last) * st->dzb_last / f.lcorr));
+        scr[4 * stride] = dcis(-(0.5 * (d1b + st->plates[0].db0) * st->dzb_first / f.lcorr));
+        scr[5 * stride] = dcis(-(0.5 * (d1b + st->db0_last) * st->dzb_last / f.lcorr));
     }
 }
 
@@ -691,22 +698,24 @@ __device__ __forceinline__ void pmx_b_pre(cpx* scr, int stride, const StepPkg* s
 // linear in omega).  Written as conj(e) * diag(e^2, 1): the scalar conj(e) is common to both polarizations and is
 // collected over the trunks of the step in closed form (conj(prod b) * conj(prod g)^j, folded into the common-phase
 // recurrence), so a trunk multiplies ONE polarization by e(j)^2 = b2 * g2^j.  Two interleaved chains (even / odd j)
-// advanced by g4 = g2^2: three phasors live at a time.
-__device__ __forceinline__ void pmx_b_diag2(cpx (&x)[8], cpx b2, cpx g2, cpx g4) {
-    cpx ea = b2, eo = cmul(b2, g2);
+// advanced by g4 = g2^2: three phasors live at a time.  (FP32 fields: the chains run in double and every phasor is
+// rounded once where it is applied, so the trunks of a step do not repeat one rounding error.)
+__device__ __forceinline__ void pmx_b_diag2(cpx (&x)[8], dcpx b2, dcpx g2, dcpx g4) {
+    dcpx ea = b2, eo = dmul(b2, g2);
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
         const int qa = (j + 4) & 7, qo = (j + 5) & 7;
-        x[qa] = cmul(x[qa], ea);
-        x[qo] = cmul(x[qo], eo);
+        x[qa] = cmul(x[qa], pmx_to_cpx(ea));
+        x[qo] = cmul(x[qo], pmx_to_cpx(eo));
         if (j < 6) {
-            ea = cmul(ea, g4);
-            eo = cmul(eo, g4);
+            ea = dmul(ea, g4);
+            eo = dmul(eo, g4);
         }
     }
 }
 // u <- [ka kb; -conj(kb) ka] * u, ka real: 12 FMAs per bin
-__device__ __forceinline__ void pmx_b_applyK(cpx (&x)[8], cpx (&y)[8], double ka, double kbr, double kbi) {
+__device__ __forceinline__ void pmx_b_applyK(cpx (&x)[8], cpx (&y)[8], double ka_, double kbr_, double kbi_) {
+    const real ka = (real)ka_, kbr = (real)kbr_, kbi = (real)kbi_;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const cpx a = x[q], b = y[q];
@@ -720,33 +729,37 @@ __device__ __forceinline__ void pmx_b_applyK(cpx (&x)[8], cpx (&y)[8], double ka
 //   downwards  E(j-1) = E(j)*conj(D1(j-1)), D1(j-1) = D1(j)*conj(D2(j-1)), D2(j-1) = D2(j)*conj(D3)
 // three evaluations + 18 complex products instead of eight evaluations; a rounding error of the first / second
 // difference is amplified by at most 4 / 6 (binomials of the distance to the anchor).
-__device__ __forceinline__ void pmx_b_common(cpx (&x)[8], cpx (&y)[8], cpx E, cpx D1, cpx D2, cpx D3) {
-    x[0] = cmul(x[0], E);
-    y[0] = cmul(y[0], E);
+__device__ __forceinline__ void pmx_b_common(cpx (&x)[8], cpx (&y)[8], dcpx E, dcpx D1, dcpx D2, dcpx D3) {
+    {
+        const cpx e0 = pmx_to_cpx(E);
+        x[0] = cmul(x[0], e0);
+        y[0] = cmul(y[0], e0);
+    }
     {   // j = 5, 6, 7  <->  q = 1, 2, 3
-        cpx e = E, d1 = D1, d2 = D2;
+        dcpx e = E, d1 = D1, d2 = D2;
 #pragma unroll
         for (int q = 1; q < 4; ++q) {
-            e = cmul(e, d1);
-            x[q] = cmul(x[q], e);
-            y[q] = cmul(y[q], e);
-            if (q < 3) d1 = cmul(d1, d2);
-            if (q < 2) d2 = cmul(d2, D3);
+            e = dmul(e, d1);
+            const cpx ef = pmx_to_cpx(e);
+            x[q] = cmul(x[q], ef);
+            y[q] = cmul(y[q], ef);
+            if (q < 3) d1 = dmul(d1, d2);
+            if (q < 2) d2 = dmul(d2, D3);
         }
     }
     {   // j = 3, 2, 1, 0  <->  q = 7, 6, 5, 4
-        cpx e = E, d1 = D1, d2 = D2;
+        dcpx e = E, d1 = D1, d2 = D2;
 #pragma unroll
         for (int q = 7; q >= 4; --q) {
-            d2 = cmulc(d2, D3);
-            d1 = cmulc(d1, d2);
-            e = cmulc(e, d1);
-            x[q] = cmul(x[q], e);
-            y[q] = cmul(y[q], e);
+            d2 = dmulc(d2, D3);
+            d1 = dmulc(d1, d2);
+            e = dmulc(e, d1);
+            const cpx ef = pmx_to_cpx(e);
+            x[q] = cmul(x[q], ef);
+            y[q] = cmul(y[q], ef);
         }
     }
 }
-#endif
 
 // ---------------------------------------------------------------------------
 // The linear step on the eight bins a thread holds after a forward transform (matrix_step, fiber.m:907-933, and
@@ -754,11 +767,11 @@ __device__ __forceinline__ void pmx_b_common(cpx (&x)[8], cpx (&y)[8], cpx E, cp
 // are k = k1 + N1*(t + q*T) (q = 0..7) of a length-N spectrum: pass B calls it with the four-step split of the
 // field, the single-CTA kernel of small fields with N1 = 1, k1 = 0.  All threads of the CTA must call it together
 // (steps with more trunks than the package holds reload plate chunks behind __syncthreads).
-//   scr / scr_stride : the thread's pre-evaluated phasors (pmx_b_pre), FP64 scalar dispersion mode
+//   scr / scr_stride : the thread's pre-evaluated phasors (pmx_b_pre, double2), scalar dispersion mode
 //   schunk           : shared buffer of PMX_PKG_PLATES plates
 template <bool SC, bool PRE>
 __device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const StepPkg* st, const FiberConst& f,
-                                                const PassParams& p, const cpx* scr, int scr_stride, PlateConst* schunk,
+                                                const PassParams& p, const dcpx* scr, int scr_stride, PlateConst* schunk,
                                                 int b, int col, int k1, int t, int T, size_t N, double fn0, double fn4,
                                                 double dfn, bool any_full) {
     constexpr int PLD = (int)(sizeof(PlateConst) / sizeof(double));
@@ -770,51 +783,27 @@ __device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const 
     (void)fn0;
     (void)dfn;
         const double dz_cur = st->dz_cur;
-#ifndef PMX_F32
         // scalar phase common to both polarizations collected over the trunks: conj(Bacc) * conj(Gacc)^j
-        cpx Bacc = mkc(1.0, 0.0), Gacc = mkc(1.0, 0.0);
-#endif
+        dcpx Bacc = dmk(1.0, 0.0), Gacc = dmk(1.0, 0.0);
         if (f.pmd) {
             const double lcorr = f.lcorr, dzb_first = st->dzb_first, dzb_last = st->dzb_last;
             if (bmode & (PMX_BM_ENTRY_R | PMX_BM_ENTRY_C)) pmx_apply2x2(x, y, st->E);  // (:920-921)
-            // whole trunks share exp(-i*db1/2) per bin
+            // vector dispersion mode: db1 of the thread's bins; whole trunks share exp(-i*db1/2) per bin.  (FP32: that
+            // factor is kept in double and each trunk's exp(-i*(db1+db0)/2) is formed in double and rounded once,
+            // otherwise the same float-rounded phasor would repeat its phase error in up to nplates factors.)
             double d1[(SC) ? 1 : 8];
+#ifdef PMX_F32
+            double2 Ed[(SC) ? 1 : 8];
+#else
             cpx e1[(SC) ? 1 : 8];
-            // scalar mode: phases of the step's first / last trunk at the thread's lowest bin; db1 is linear
-            // in omega, so the other bins follow by a geometric progression (pmx_b_diag)
-#ifdef PMX_F32
-            cpx pf0, pl0, pf4, pl4;  // FP32: g^4 in float would cost 2e-7 of phase per trunk; evaluate both base bins
-            // FP32: the whole-trunk factor exp(-i*db1/2) of a bin is the same for every whole trunk of the
-            // step, so a float-rounded copy (or a float progression) would repeat the SAME phase error in
-            // each of up to nplates factors.  It is kept in double; each trunk's exp(-i*(db1+db0)/2) is
-            // formed in double and rounded once, which makes the per-trunk errors independent.
-            double2 Ed[8];
-#else
-            cpx E0b, pfb, plb, pprev = mkc(1.0, 0.0);
 #endif
+            // scalar dispersion mode: phasors of the step's whole / first / last trunk at the thread's lowest bin (from
+            // the pre-phase); db1 is linear in omega, so the other bins follow by a geometric progression (pmx_b_diag2)
+            dcpx E0b = dmk(1.0, 0.0), pfb = E0b, plb = E0b, pprev = E0b;
             if constexpr (SC) {
-#ifdef PMX_F32
-                const double d10 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn0));  // db1 = dgdrms*omega (:358)
-                const double d14 = __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn4));
-                if (any_full) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const double fn = (q < 4) ? fn0 + (double)q * dfn : fn4 + (double)(q - 4) * dfn;
-                        pmx_sincos_fast(-0.5 * __dmul_rn(f.dgdrms, __dmul_rn(f.w0, fn)), &Ed[q].y, &Ed[q].x);
-                    }
-                }
-                // partial trunks: deltabeta = 0.5*(db1+db0)*dzb/lcorr  (:925); the four evaluations are
-                // independent and interleave
-                const double db0f = st->plates[0].db0, db0l = st->db0_last;
-                pf0 = pmx_cis(-(0.5 * (d10 + db0f) * dzb_first / lcorr));
-                pl0 = pmx_cis(-(0.5 * (d10 + db0l) * dzb_last / lcorr));
-                pf4 = pmx_cis(-(0.5 * (d14 + db0f) * dzb_first / lcorr));
-                pl4 = pmx_cis(-(0.5 * (d14 + db0l) * dzb_last / lcorr));
-#else
                 E0b = scr[3 * scr_stride];
                 pfb = scr[4 * scr_stride];
                 plb = scr[5 * scr_stride];
-#endif
             } else {
                 const double* d1p = p.db1_p + (size_t)col * N + (size_t)k1 * p.N2;
 #pragma unroll
@@ -847,62 +836,32 @@ __device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const 
                     const PlateConst& P = pl[k - k0];
                     const double dzb = (k == 0) ? dzb_first : ((k == ntrunk - 1) ? dzb_last : lcorr);
                     if constexpr (SC) {
-#ifdef PMX_F32
-                        if (dzb == lcorr) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const cpx e = mkc((real)(Ed[q].x * P.h0r - Ed[q].y * P.h0i), (real)(Ed[q].x * P.h0i + Ed[q].y * P.h0r));
-                                x[q] = cmul(x[q], e);
-                                y[q] = cmulc(y[q], e);
-                            }
-                            if (k < ntrunk - 1) pmx_apply2x2(x, y, &P.c11r);
-                            continue;
+                        dcpx bb, g, g2, g4;
+                        if (dzb == lcorr) {  // whole trunk: exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
+                            bb = dmul(E0b, dmk(P.h0r, P.h0i));
+                            g = dmk(f.g1r, f.g1i);
+                            g2 = dmk(f.g2r, f.g2i);
+                            g4 = dmk(f.g4r, f.g4i);
+                        } else if (k == 0) {  // partial trunk (first or last of the step)
+                            bb = pfb;
+                            g = dmk(st->gpf_r, st->gpf_i);
+                            g2 = dmk(st->gpf2[0], st->gpf2[1]);
+                            g4 = dmk(st->gpf4[0], st->gpf4[1]);
+                        } else {
+                            bb = plb;
+                            g = dmk(st->gpl_r, st->gpl_i);
+                            g2 = dmk(st->gpl2[0], st->gpl2[1]);
+                            g4 = dmk(st->gpl4[0], st->gpl4[1]);
                         }
-                        {   // partial trunk: bins 1..3 are e0*g^q, bins 5..7 e4*g^(q-4)
-                            const cpx e0 = (k == 0) ? pf0 : pl0, e4 = (k == 0) ? pf4 : pl4;
-                            const cpx g = (k == 0) ? mkc((real)st->gpf_r, (real)st->gpf_i) : mkc((real)st->gpl_r, (real)st->gpl_i);
-                            const cpx g2 = cmul(g, g);
-                            const cpx e01 = cmul(e0, g), e02 = cmul(e0, g2), e41 = cmul(e4, g), e42 = cmul(e4, g2);
-                            const cpx e03 = cmul(e01, g2), e43 = cmul(e41, g2);
-                            x[0] = cmul(x[0], e0);   y[0] = cmulc(y[0], e0);
-                            x[4] = cmul(x[4], e4);   y[4] = cmulc(y[4], e4);
-                            x[1] = cmul(x[1], e01);  y[1] = cmulc(y[1], e01);
-                            x[5] = cmul(x[5], e41);  y[5] = cmulc(y[5], e41);
-                            x[2] = cmul(x[2], e02);  y[2] = cmulc(y[2], e02);
-                            x[6] = cmul(x[6], e42);  y[6] = cmulc(y[6], e42);
-                            x[3] = cmul(x[3], e03);  y[3] = cmulc(y[3], e03);
-                            x[7] = cmul(x[7], e43);  y[7] = cmulc(y[7], e43);
+                        bb = dmul(bb, pprev);        // left phase of the boundary matrix just applied
+                        Bacc = dmul(Bacc, bb);
+                        Gacc = dmul(Gacc, g);
+                        pmx_b_diag2(x, dmul(bb, bb), g2, g4);
+                        if (k < ntrunk - 1) {        // basis change matR(n+1)' * matR(n) = diag(p, p*) * K
+                            pmx_b_applyK(x, y, P.ka, P.kbr, P.kbi);
+                            pprev = dmk(P.pr, P.pi);
                         }
-#else
-                        {
-                            cpx b, g, g2, g4;
-                            if (dzb == lcorr) {  // whole trunk: exp(-i*0.5*(db1+db0)) = exp(-i*db1/2) * exp(-i*db0/2)
-                                b = cmul(E0b, mkc(P.h0r, P.h0i));
-                                g = mkc(f.g1r, f.g1i);
-                                g2 = mkc(f.g2r, f.g2i);
-                                g4 = mkc(f.g4r, f.g4i);
-                            } else if (k == 0) {  // partial trunk (first or last of the step)
-                                b = pfb;
-                                g = mkc(st->gpf_r, st->gpf_i);
-                                g2 = mkc(st->gpf2[0], st->gpf2[1]);
-                                g4 = mkc(st->gpf4[0], st->gpf4[1]);
-                            } else {
-                                b = plb;
-                                g = mkc(st->gpl_r, st->gpl_i);
-                                g2 = mkc(st->gpl2[0], st->gpl2[1]);
-                                g4 = mkc(st->gpl4[0], st->gpl4[1]);
-                            }
-                            b = cmul(b, pprev);          // left phase of the boundary matrix just applied
-                            Bacc = cmul(Bacc, b);
-                            Gacc = cmul(Gacc, g);
-                            pmx_b_diag2(x, cmul(b, b), g2, g4);
-                            if (k < ntrunk - 1) {        // basis change matR(n+1)' * matR(n) = diag(p, p*) * K
-                                pmx_b_applyK(x, y, P.ka, P.kbr, P.kbi);
-                                pprev = mkc(P.pr, P.pi);
-                            }
-                            continue;
-                        }
-#endif
+                        continue;
                     } else {
                         if (dzb == lcorr) {  // whole trunk: exp(-i*db1/2) * exp(-i*db0/2)
                             const cpx h0 = mkc((real)P.h0r, (real)P.h0i);
@@ -931,18 +890,16 @@ __device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const 
             }
             if (bmode & PMX_BM_EXIT_R) pmx_apply2x2(x, y, st->X);  // back to the laboratory basis (:931-932)
         }
-#ifndef PMX_F32
         if constexpr (PRE) {  // common phase exp(-i*betat*sum(dzb)) (:924,927-928) times the trunks' common scalar
             // at the anchor bin (j = 4) the collected scalar is conj(Bacc * Gacc^4)
-            const cpx G2 = cmul(Gacc, Gacc);
-            const cpx S4 = cmul(Bacc, cmul(G2, G2));
+            const dcpx G2 = dmul(Gacc, Gacc);
+            const dcpx S4 = dmul(Bacc, dmul(G2, G2));
             if (f.gvd_any)
-                pmx_b_common(x, y, cmulc(scr[0 * scr_stride], S4), cmulc(scr[1 * scr_stride], Gacc),
-                             scr[2 * scr_stride], mkc(st->gd3_r, st->gd3_i));
+                pmx_b_common(x, y, dmulc(scr[0 * scr_stride], S4), dmulc(scr[1 * scr_stride], Gacc),
+                             scr[2 * scr_stride], dmk(st->gd3_r, st->gd3_i));
             else if (f.pmd)
-                pmx_b_common(x, y, cconj(S4), cconj(Gacc), mkc(1.0, 0.0), mkc(1.0, 0.0));
+                pmx_b_common(x, y, dmk(S4.x, -S4.y), dmk(Gacc.x, -Gacc.y), dmk(1.0, 0.0), dmk(1.0, 0.0));
         } else
-#endif
 #ifdef PMX_EXP_NO_COMMON
         if (false) {
 #else
@@ -983,11 +940,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_k_passB(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 1>;
     constexpr int T = L / 8, SA = PMX_SA_BYTES, PITCH = G * SA, MASK = PITCH / 16 - 1;
-#ifdef PMX_F32
-    constexpr bool PRE = false;
-#else
-    constexpr bool PRE = SC;   // FP64 scalar dispersion mode: data-independent phasors before the tile wait
-#endif
+    constexpr bool PRE = SC;   // scalar dispersion mode: data-independent phasors before the tile wait
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* sm = pmx_checked1024(smraw);
     unsigned char* in = sm;
@@ -995,7 +948,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     cpx* stw = reinterpret_cast<cpx*>(sm + S::TW_OFF);
     unsigned char* aux0 = sm + S::AUX_OFF;
     PlateConst* schunk = reinterpret_cast<PlateConst*>(sm + S::PLATE_OFF);
-    cpx* scr = reinterpret_cast<cpx*>(sm + S::SCR_OFF) + threadIdx.x;   // [slot][THREADS]
+    dcpx* scr = reinterpret_cast<dcpx*>(sm + S::SCR_OFF) + threadIdx.x;   // [slot][THREADS]
     unsigned char* sdone = sm + S::LIVE_OFF;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + S::MBAR_OFF);      // [0]: tile, [1]: step package
     const int cl = threadIdx.x % G, t = threadIdx.x / G;
@@ -1066,11 +1019,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         const double fn0 = (double)kb * f.inv_nsymb;
         const double fn4 = (double)(kb + (long long)p.N1 * 4 * T - (long long)N) * f.inv_nsymb;
         const bool any_full = (ntrunk > 2) || (st->dzb_first == f.lcorr) || (st->dzb_last == f.lcorr);
-#ifndef PMX_F32
         if constexpr (PRE) {
             if (ntrunk > 0) pmx_b_pre(scr, S::THREADS, st, f, col, fn4, fn0, any_full);
         }
-#endif
         PMX_T_MARK(7)
         pmx_mbar_wait(mbar, phase);
         phase ^= 1u;

@@ -25,7 +25,7 @@ struct OnchipSmem {
     static constexpr int WORK_BYTES = 2 * L * (int)sizeof(cpx);   // exchange buffer (and, before a step, XPM powers)
     static constexpr int TW_OFF = WORK_BYTES;
     static constexpr int SCR_OFF = TW_OFF + R16(pmx_tw_total(L) * (int)sizeof(cpx));
-    static constexpr int PKG_OFF = SCR_OFF + PMX_B_SCR * T * (int)sizeof(cpx);
+    static constexpr int PKG_OFF = SCR_OFF + PMX_B_SCR * T * (int)sizeof(double2);
     static constexpr int PLATE_OFF = PKG_OFF + (int)sizeof(StepPkg);
     static constexpr int CTL_OFF = PLATE_OFF + PMX_PKG_PLATES * (int)sizeof(PlateConst);
     static constexpr int RED_OFF = CTL_OFF + R16((int)sizeof(StepCtl));
@@ -56,11 +56,7 @@ template <typename R, int L, bool SC>
 __global__ void __launch_bounds__((L / 8) < 32 ? 32 : (L / 8), 1) pmx_k_onchip(PassParams p, FiberConst f) {
     using S = OnchipSmem<L>;
     constexpr int T = L / 8;
-#ifdef PMX_F32
-    constexpr bool PRE = false;
-#else
     constexpr bool PRE = SC;
-#endif
     extern __shared__ __align__(16) unsigned char smo[];
     cpx* work = reinterpret_cast<cpx*>(smo);
     cpx* stw = reinterpret_cast<cpx*>(smo + S::TW_OFF);
@@ -73,7 +69,7 @@ __global__ void __launch_bounds__((L / 8) < 32 ? 32 : (L / 8), 1) pmx_k_onchip(P
     const int col = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     const bool live = t < T;   // (L = 64, 128: the CTA is padded to one warp)
     const int tt = live ? t : 0;   // (padding threads shadow thread 0: same loads, same values, same stores)
-    cpx* scr = reinterpret_cast<cpx*>(smo + S::SCR_OFF) + tt;
+    dcpx* scr = reinterpret_cast<dcpx*>(smo + S::SCR_OFF) + tt;
     cg::cluster_group cluster = cg::this_cluster();
     const size_t N = L;
     cpx* fld = reinterpret_cast<cpx*>(p.field) + (size_t)(b * f.nfc + col) * N * 2;
@@ -116,11 +112,9 @@ __global__ void __launch_bounds__((L / 8) < 32 ? 32 : (L / 8), 1) pmx_k_onchip(P
         first = 0;
         const int ntrunk = st->ntrunk;
         const bool any_full = (ntrunk > 2) || (st->dzb_first == f.lcorr) || (st->dzb_last == f.lcorr);
-#ifndef PMX_F32
         if constexpr (PRE) {
             if (ntrunk > 0) pmx_b_pre(scr, T, st, f, col, fn4, fn0, any_full);
         }
-#endif
         // ---- scalar path with the 'x' flag: sum over the columns of |u|^2 per sample, left to right (fiber.m:793-799)
         if (f.xpm) {
             real* pw = reinterpret_cast<real*>(work);
