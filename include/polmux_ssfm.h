@@ -359,6 +359,9 @@ int pmx_scalar_adaptive_run(pmx_ctx* ctx, const pmx_fiber_desc* desc, double lto
                             pmx_field* io, pmx_fiber_result* out);
 int pmx_plan_set_length(pmx_plan* plan, double length);
 int pmx_field_max_power(pmx_ctx* ctx, pmx_devfield* f, double* umax);
+/* pavg[b*nfc+c] = mean_n |ux|^2 + |uy|^2: the average power avg_power.m:63-76 returns for a separate-channel field
+ * (ampliflat's 'fixpower' gain, ampliflat.m:65-72). */
+int pmx_field_mean_power(pmx_ctx* ctx, pmx_devfield* f, double* pavg);
 int pmx_field_maxdiff2(pmx_ctx* ctx, pmx_devfield* a, pmx_devfield* b, double* out);
 int pmx_field_lincomb(pmx_ctx* ctx, pmx_devfield* dst, double ca, pmx_devfield* a, double cb, pmx_devfield* b);
 

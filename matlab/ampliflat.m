@@ -1,7 +1,8 @@
 function ampliflat(x, atype, options)
 %AMPLIFLAT  Flat-gain optical amplifier with ASE noise (drop-in front-end, device side).
-%   AMPLIFLAT(X,'gain',OPTIONS) keeps the contract of the toolbox's ampliflat.m for the 'gain' type:
-%   the field in GSTATE.FIELDX / FIELDY is multiplied by sqrt(10^(X/10)) and, with OPTIONS.f [dB],
+%   AMPLIFLAT(X,ATYPE,OPTIONS) keeps the contract of the toolbox's ampliflat.m: the field in
+%   GSTATE.FIELDX / FIELDY is multiplied by sqrt(gain), gain = 10^(X/10) for ATYPE 'gain' and
+%   X/avg_power(midch,'abs') for 'fixpower' (separate channels only), and, with OPTIONS.f [dB],
 %   complex Gaussian noise of the amplifier's ASE is added on both polarizations (OPTIONS.onepol =
 %   'asex' | 'asey' restricts it to one; OPTIONS.noise injects the noise samples, Nfft x 2*nfc).
 %   The arithmetic runs through the MEX gateway on the field the previous in-line device left in HBM,
@@ -11,11 +12,18 @@ function ampliflat(x, atype, options)
 
 global CONSTANTS GSTATE PMXOPT
 
-if ~strcmp(lower(atype), 'gain')
-    error('this front-end implements the ''gain'' amplifier type only');
-end
 ncol = size(GSTATE.FIELDX, 2);
-gain = 10^(x * 0.1);
+switch lower(atype)
+    case 'gain'
+        gain = 10^(x * 0.1);
+    case 'fixpower'
+        if ncol ~= GSTATE.NCH
+            error(['''fixpower'' works', ' only for channels separated']);
+        end
+        gain = x / avg_power(ceil(ncol / 2), 'abs');   % (the toolbox's own avg_power, on the write-through copy)
+    otherwise
+        error('wrong string atype');
+end
 sigma = zeros(1, ncol);
 asepol = 3;
 noise = [];

@@ -633,9 +633,10 @@ def scalar_a_ssfm(u, betat, dzmaxt, dphimaxt, gam, alphalin, nfft, nfc, lf, trg,
 
 
 # --------------------------------------------------------------------------
-def ampliflat_sigma(gs: GState, gain_db: float, f_db: float, nfc: int):
-    """ampliflat.m:62,91-106: linear gain and ASE sigma [sqrt(mW)] per column."""
-    gain = 10 ** (gain_db * 0.1)
+def ampliflat_sigma(gs: GState, gain_db: float, f_db: float, nfc: int, gain=None):
+    """ampliflat.m:62,91-106: linear gain (10^(gain_db/10) unless given) and ASE sigma [sqrt(mW)] per column."""
+    if gain is None:
+        gain = 10 ** (gain_db * 0.1)
     if f_db is None or math.isinf(f_db):
         return gain, np.zeros(nfc)
     flin = 10 ** (f_db * 0.1)
@@ -649,11 +650,41 @@ def ampliflat_sigma(gs: GState, gain_db: float, f_db: float, nfc: int):
     return gain, sigma
 
 
-def ampliflat(gs: GState, gain_db: float, f_db: Optional[float] = None, noise=None, onepol=None):
-    """ampliflat.m:61-148, atype='gain'.  ``noise`` is options.noise: [N, 2*nfc]
-    complex standard normals (X columns first, then Y), :123-129; ``onepol``: 'asex' / 'asey' (:107-118)."""
+def avg_power_abs(gs: GState, ich: int) -> float:
+    """avg_power(ich,'abs') for separate channels (avg_power.m:63,83-86,90-98,110-132 with nfc == NCH: ndfn = 0,
+    ndfnl = ndfnr = Nfft/2, no filter): E = sum |fft(FIELD(:,ich))|^2 / Nfft^2, X plus Y."""
+    nfft, nfc = gs.FIELDX.shape
+    if ich > gs.NCH:
+        raise ValueError('The channel does not exist')
+    if nfc != gs.NCH:
+        raise NotImplementedError('avg_power: separate channels only')
+    h = nfft // 2
+
+    def one(col):
+        x = np.fft.fft(np.asarray(col, dtype=np.complex128))
+        return (np.sum(np.abs(x[:h]) ** 2) + np.sum(np.abs(x[nfft - h:]) ** 2)) / nfft ** 2
+
+    e = one(gs.FIELDX[:, ich - 1])
+    if gs.FIELDY is not None:
+        e = e + one(gs.FIELDY[:, ich - 1])
+    return float(e)
+
+
+def ampliflat(gs: GState, gain_db: float, f_db: Optional[float] = None, noise=None, onepol=None, atype='gain'):
+    """ampliflat.m:61-148.  atype 'gain': gain_db [dB]; 'fixpower': gain_db is the output power [mW] of the middle
+    channel (:65-72).  ``noise`` is options.noise: [N, 2*nfc] complex standard normals (X columns first, then Y),
+    :123-129; ``onepol``: 'asex' / 'asey' (:107-118)."""
     nfr, nfc = gs.FIELDX.shape
-    gain, sigma = ampliflat_sigma(gs, gain_db, f_db, nfc)
+    atype = atype.lower()
+    if atype == 'gain':
+        gain, sigma = ampliflat_sigma(gs, gain_db, f_db, nfc)
+    elif atype == 'fixpower':
+        if nfc != gs.NCH:
+            raise ValueError("'fixpower' works only for channels separated")
+        gain = gain_db / avg_power_abs(gs, math.ceil(nfc / 2))
+        gain, sigma = ampliflat_sigma(gs, 10 * math.log10(gain), f_db, nfc, gain=gain)
+    else:
+        raise ValueError('wrong string atype')
     R = np.dtype(gs.real).type
     sg = R(math.sqrt(gain))
     gs.FIELDX = gs.FIELDX * sg

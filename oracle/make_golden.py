@@ -84,7 +84,7 @@ def run_case(name, nsymb, nt, nch, ftype, fib, flag, seed=1000, rate=28.0, pavg=
         nfc = post['FIELDX'].shape[1]
         noise = (g.standard_normal((n, 2 * nfc)) + 1j * g.standard_normal((n, 2 * nfc)))
         opt = MStruct({'f': to_m(amp['f']), 'noise': to_m(noise)})
-        it.call('ampliflat', [to_m(amp['gain']), 'gain', opt], 0)
+        it.call('ampliflat', [to_m(amp['gain']), amp.get('atype', 'gain'), opt], 0)   # ('fixpower': gain = mW)
         a = snapshot(it)
         data.update(amp_noise=noise, amp_FIELDX=a['FIELDX'], amp_FIELDY=a['FIELDY'])
         meta['amp'] = amp
@@ -117,6 +117,16 @@ def fib(**kw):
     f = dict(SMF)
     f.update(kw)
     return f
+
+
+def fixpower_cases():
+    """ampliflat(x,'fixpower',options): output power of the middle channel = x [mW], through the interpreted ampliflat.m
+    and avg_power.m; separate channels, two polarizations and the scalar (FIELDY empty) field"""
+    run_case('fixpower_sep3_manakov', 64, 16, 3, 'sepfields', fib(length=4e4, dgd=0.3, nplates=8, manakov='yes',
+                                                                  slope=0.057), 'gps-',
+             amp={'gain': 1.5, 'f': 5.0, 'atype': 'fixpower'})
+    run_case('fixpower_scalar_sep3_gsx', 64, 16, 3, 'sepfields', fib(length=3e4, slope=0.057), 'g-sx', two_pol=False,
+             want_brf=False, amp={'gain': 0.8, 'f': 6.0, 'atype': 'fixpower'})
 
 
 def run_c1_case(name='c1_cnlse_10plates_100km_2e16'):
@@ -152,6 +162,9 @@ def run_c1_case(name='c1_cnlse_10plates_100km_2e16'):
 if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'c1':     # only the full-size C1 case
         run_c1_case()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'fixpower':  # only ampliflat(x,'fixpower',...) (ampliflat.m:65-72 + avg_power.m)
+        fixpower_cases()
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == 'small':  # only the small-field cases
         run_case('small_ex06_gsx_2e10', 32, 32, 1, 'unique', fib(length=1e5, dphimax=3e-3), 'g-sx', two_pol=False,
@@ -202,4 +215,5 @@ if __name__ == '__main__':
     run_print_case('wdm3_pmf', 128, 64, 3, 'unique', fib(length=3e4, dgd=0.7, db0=[1.1, -0.4, 2.0], theta=[0.3, -0.9, 1.2],
                                                          epsilon=[0.1, 0.5, -0.3], manakov='no', slope=0.057), 'gps-', pavg=1.0)
     run_print_case('scalar_sep3_ltol', 256, 16, 3, 'sepfields', fib(length=2e4, ltol=2e-6, slope=0.057), 'g-sx', two_pol=False)
+    fixpower_cases()
     run_c1_case()

@@ -31,7 +31,7 @@ EXPORTS = [
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
     'pmx_host_is_pinned', 'pmx_scalar_adaptive_run', 'pmx_mc_run', 'pmx_mc_nccl_available',
-    'pmx_ampliflat_exec_at', 'pmx_dsp_count',
+    'pmx_ampliflat_exec_at', 'pmx_dsp_count', 'pmx_field_mean_power',
 ]
 
 
@@ -141,6 +141,7 @@ def load():
     lib.pmx_scalar_nl_exec.argtypes = [vp, vp, _dp, C.c_double, C.c_double, C.c_int32, C.c_int32]
     lib.pmx_plan_set_length.argtypes = [vp, C.c_double]
     lib.pmx_field_max_power.argtypes = [vp, vp, _dp]
+    lib.pmx_field_mean_power.argtypes = [vp, vp, _dp]
     lib.pmx_field_maxdiff2.argtypes = [vp, vp, vp, _dp]
     lib.pmx_field_lincomb.argtypes = [vp, vp, C.c_double, vp, C.c_double, vp]
     lib.pmx_field_mux.argtypes = [vp, C.POINTER(Field), C.c_int32, C.POINTER(C.c_int64), _dp, C.POINTER(C.c_int64),
@@ -149,6 +150,13 @@ def load():
     lib.pmx_link_run.argtypes = [vp, C.POINTER(FiberDesc), C.POINTER(LinkDesc), C.POINTER(Field), C.POINTER(FiberResult)]
     _lib = lib
     return lib
+
+
+def field_mean_power(ctx, field):
+    """-> [batch, nfc] mean |ux|^2 + |uy|^2 (pmx_field_mean_power)"""
+    out = np.zeros((field.batch, field.nfc), dtype=np.float64)
+    ctx.check(ctx.lib.pmx_field_mean_power(ctx.h, field.h, out.ctypes.data_as(_dp)))
+    return out
 
 
 def host_is_pinned(a) -> bool:

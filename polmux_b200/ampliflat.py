@@ -25,6 +25,24 @@ def ase_sigma(gain: float, f_db, nfc: int) -> np.ndarray:
     return np.sqrt(flin / 4 * CONSTANTS.HPLANCK * CONSTANTS.CLIGHT / lam * (gain - 1) * G.NT * G.SYMBOLRATE * 1e21)
 
 
+def _avg_power_abs(G, ctx, ch):
+    """avg_power(ch,'abs') for separate channels (avg_power.m:63-76: no filter, every bin counted): the mean over the
+    samples of |FIELDX(:,ch)|^2 + |FIELDY(:,ch)|^2, reduced on the device where the field lives."""
+    if G.has_y():
+        fld, hx, hy = G.take_device(ctx)
+        try:
+            return float(_lib.field_mean_power(ctx, fld)[0, ch - 1])
+        finally:
+            G.restore_host(fld, hx, hy)          # (untouched: back as it was, resident or host)
+    nfr, nfc = G.field_shape()
+    fld = _lib.DeviceField(ctx, nfr, nfc, 1)
+    try:
+        fld.upload(G.FIELDX, np.zeros_like(G.FIELDX))
+        return float(_lib.field_mean_power(ctx, fld)[0, ch - 1])
+    finally:
+        fld.close()
+
+
 def ampliflat(x, atype='gain', options=None, ctx=None, seed=None):
     """ampliflat(x,'gain',options) on GSTATE.FIELDX/FIELDY, like the reference.
 
@@ -33,8 +51,9 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=None):
     default) takes the next value of the global stream (gstate.seed(k) = randn('state',k)), so successive calls add
     independent noise as the reference's randn does (ampliflat.m:132-135)."""
     G = GSTATE
-    if atype.lower() != 'gain':
-        raise NotImplementedError("ampliflat: only atype 'gain' is built (ampliflat.m:61-63)")
+    atype = atype.lower()
+    if atype not in ('gain', 'fixpower'):
+        raise ValueError('wrong string atype')                                   # ampliflat.m:74-75
     options = dict(options or {})
     asepol = 3
     if 'onepol' in options:                                                  # ampliflat.m:107-118
@@ -43,9 +62,14 @@ def ampliflat(x, atype='gain', options=None, ctx=None, seed=None):
             raise ValueError("ONEPOL, if exists, must be 'asex' or 'asey'")
         asepol = 1 if pol == 'asex' else 2
     nfr, nfc = G.field_shape()
-    gain = 10 ** (x * 0.1)
-    sigma = ase_sigma(gain, options.get('f'), nfc) if options else np.zeros(nfc)
+    if atype == 'fixpower' and nfc != G.NCH:
+        raise ValueError("'fixpower' works only for channels separated")         # ampliflat.m:66,70-71
     ctx = ctx or _lib.default_context()
+    if atype == 'gain':
+        gain = 10 ** (x * 0.1)                                                   # ampliflat.m:62-63
+    else:                                                                        # ampliflat.m:65-69
+        gain = x / _avg_power_abs(G, ctx, math.ceil(nfc / 2))                    # gain = x/avg_power(midch,'abs')
+    sigma = ase_sigma(gain, options.get('f'), nfc) if options else np.zeros(nfc)
     noise = None
     if seed is None:
         seed = gstate.next_ase_seed() if np.any(sigma) and 'noise' not in options else 0

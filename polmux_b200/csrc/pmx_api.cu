@@ -2002,6 +2002,61 @@ extern "C" int pmx_field_max_power(pmx_ctx* c, pmx_devfield* f, double* umax) {
     return PMX_OK;
 }
 
+// mean over the samples of |x|^2 + |y|^2 per realization-column (avg_power.m:63-76 for a separate-channel field: the
+// spectral sum over all bins divided by Nfft^2 is the time average, by Parseval).  Two stages with fixed summation
+// trees -- CTA (chunk, column) writes one partial, thread 0 of a second launch adds the partials left to right -- so the
+// result is the same on every run.  E = double2 or float2 elements; the sum is taken in double either way.
+template <typename E>
+__global__ void __launch_bounds__(256) pmx_k_mean_power(const E* field, size_t N, double* part) {
+    __shared__ double red[256];
+    const E* fld = field + (size_t)blockIdx.y * N * 2;
+    const size_t per = (N + gridDim.x - 1) / gridDim.x;
+    const size_t n0 = blockIdx.x * per, n1 = n0 + per < N ? n0 + per : N;
+    double acc = 0.0;
+    for (size_t n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+        const E x = fld[2 * n], y = fld[2 * n + 1];
+        acc += ((double)x.x * x.x + (double)x.y * x.y) + ((double)y.x * y.x + (double)y.y * y.y);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void pmx_k_mean_power_fin(const double* part, int nchunk, size_t N, int nbc, double* out) {
+    const int bc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bc >= nbc) return;
+    double acc = 0.0;
+    for (int i = 0; i < nchunk; ++i) acc += part[(size_t)bc * nchunk + i];
+    out[bc] = acc / (double)N;
+}
+
+extern "C" int pmx_field_mean_power(pmx_ctx* c, pmx_devfield* f, double* pavg) {
+    if (!c || !f || !pavg) return set_err(c, PMX_ERR_INVALID, "pmx_field_mean_power: null argument");
+    CK(c, cudaSetDevice(c->device));
+    const int nbc = f->batch * f->nfc;
+    const int nchunk = (int)std::max<size_t>(1, std::min<size_t>(((size_t)f->nfft + 4095) / 4096, (148 * 8 + nbc - 1) / nbc));
+    double* d = nullptr;
+    CK(c, cudaMallocAsync(&d, ((size_t)nbc * nchunk + nbc) * sizeof(double), c->stream));
+    dim3 g(nchunk, nbc);
+    if (f->precision == PMX_F32)
+        pmx_k_mean_power<float2><<<g, 256, 0, c->stream>>>(reinterpret_cast<const float2*>(f->data), (size_t)f->nfft, d);
+    else
+        pmx_k_mean_power<double2><<<g, 256, 0, c->stream>>>(reinterpret_cast<const double2*>(f->data), (size_t)f->nfft, d);
+    pmx_k_mean_power_fin<<<(nbc + 127) / 128, 128, 0, c->stream>>>(d, nchunk, (size_t)f->nfft, nbc, d + (size_t)nbc * nchunk);
+    c->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(pavg, d + (size_t)nbc * nchunk, nbc * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaFreeAsync(d, c->stream);
+    CK(c, e);
+    CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
 __global__ void __launch_bounds__(256) pmx_k_maxdiff2(const cpx* a, const cpx* b, size_t n_sa, unsigned long long* out) {
     unsigned long long vmax = 0ull;
     for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_sa; n += (size_t)gridDim.x * blockDim.x) {

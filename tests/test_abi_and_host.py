@@ -239,3 +239,18 @@ def test_link_descriptor_checks():
         _lib.make_link(3, 2.0, [0.1], plates=[np.zeros(10)] * 3)
     l0, _ = _lib.make_link(2)
     assert not l0.db0 and not l0.sigma and not l0.seeds and l0.gain == 0.0
+
+
+def test_ampliflat_argument_errors_like_the_reference():
+    """ampliflat.m:65-75: unknown atype; 'fixpower' on a field that is not one column per channel (raised on the host,
+    before any device call)"""
+    import polmux_b200 as pmx
+    pmx.reset_all(16, 8, 3)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.LAMBDA, G.POWER = 10.0, np.array([1549.6, 1550.0, 1550.4]), np.ones(3)
+    G.FIELDX = np.ones((128, 1), dtype=np.complex128)
+    G.FIELDY = np.ones((128, 1), dtype=np.complex128)
+    with pytest.raises(ValueError, match='wrong string atype'):
+        pmx.ampliflat(3.0, 'boost')
+    with pytest.raises(ValueError, match='only for channels separated'):
+        pmx.ampliflat(1.0, 'fixpower')

@@ -90,6 +90,12 @@ def test_front_end_reproduces_the_interpreted_original(name, scalmode):
         np.testing.assert_allclose(np.asarray(brf['betat']), z['brf_betat'], rtol=1e-15, atol=0)
         np.testing.assert_allclose(np.asarray(brf['db1']), z['brf_db1'], rtol=1e-15, atol=0)
         assert float(np.asarray(brf['lcorr']).ravel()[0]) == float(z['brf_lcorr'][0])
+    if 'amp_FIELDX' in z.files:    # matlab/ampliflat.m ('gain' and 'fixpower', the latter through the toolbox's avg_power.m)
+        a = m['amp']
+        opt = MStruct({'f': to_m(a['f']), 'noise': to_m(z['amp_noise'])})
+        it.call('ampliflat', [to_m(a['gain']), a.get('atype', 'gain'), opt], 0)
+        G = it.globals['GSTATE']
+        assert orc.rel_l2(G['FIELDX'], G['FIELDY'], z['amp_FIELDX'], z['amp_FIELDY']) < 1e-13
 
 
 @needs_ref
@@ -123,6 +129,13 @@ def test_front_end_errors_like_the_original():
         it.call('fiber', [to_m(m['fiber']), 'g--x'], 0)
     with pytest.raises(MError, match='Missing DGD'):
         it.call('fiber', [to_m(m['fiber']), 'gps-'], 0)
+    with pytest.raises(MError, match='wrong string atype'):
+        it.call('ampliflat', [to_m(3.0), 'boost'], 0)
+    z3, m3 = load('wdm3_unique_manakov')         # three channels in one 'unique' field
+    tx_through_reference(it, m3, z3)
+    with pytest.raises(MError, match='only for channels separated'):
+        it.call('ampliflat', [to_m(1.0), 'fixpower'], 0)
+    tx_through_reference(it, m, z)
     z, m = load('cnlse_nopmd')
     tx_through_reference(it, m, z)
     with pytest.raises(MError, match='absence of polarization'):
@@ -196,7 +209,8 @@ def _gpu_interp(seed):
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['manakov_100plates_80km', 'cnlse_10plates_100km', 'sep3_manakov', 'pmf_single', 'scalar_gs',
                                   'scalar_sep3_gsx', 'scalar_ltol_gs', 'scalar_dphiadapt_sep3_gsx', 'cnlse_nopmd',
-                                  'small_ex06_gsx_2e10', 'small_ex10_sep5_gsx_2e11', 'small_2pol_cnlse_2e9'])
+                                  'small_ex06_gsx_2e10', 'small_ex10_sep5_gsx_2e11', 'small_2pol_cnlse_2e9',
+                                  'fixpower_sep3_manakov', 'fixpower_scalar_sep3_gsx'])
 def test_interpreted_front_end_on_the_device(name):
     """matlab/fiber.m interpreted, its ssfm_mex the compiled gateway on the GPU: all three dispatches (matrix_ssfm,
     scalar_ssfm, scalar_a_ssfm) against the interpreted original's goldens, FP64 <= 1e-10"""
@@ -214,6 +228,21 @@ def test_interpreted_front_end_on_the_device(name):
     assert err < 1e-10, err
     np.testing.assert_allclose(G['DELAY'], z['out_DELAY'], rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(G['DISP'], z['out_DISP'], rtol=1e-13, atol=1e-13)
+    if 'amp' in m:
+        # matlab/ampliflat.m, 'fixpower' included.  It calls the toolbox's avg_power.m, which is not on the GPU box: the
+        # test stands in for it with the oracle's restatement (pinned on the interpreted avg_power.m by test_golden)
+        def avg_power(it_, a, nargout):
+            Gm = it_.globals['GSTATE']
+            gs = orc.reset_all(m['nsymb'], m['nt'], m['nch'])
+            gs.FIELDX, fy = np.asarray(Gm['FIELDX']), np.asarray(Gm['FIELDY'])
+            gs.FIELDY = fy if fy.size else None
+            assert a[1] == 'abs'
+            return [to_m(orc.avg_power_abs(gs, int(np.asarray(a[0]).ravel()[0])))]
+        it.builtins['avg_power'] = avg_power
+        opt = MStruct({'f': to_m(m['amp']['f']), 'noise': to_m(z['amp_noise'])})
+        it.call('ampliflat', [to_m(m['amp']['gain']), m['amp'].get('atype', 'gain'), opt], 0)
+        G = it.globals['GSTATE']
+        assert orc.rel_l2(G['FIELDX'], G['FIELDY'], z['amp_FIELDX'], z['amp_FIELDY']) < 1e-10
 
 
 @pytest.mark.gpu
