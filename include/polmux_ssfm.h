@@ -365,6 +365,29 @@ int pmx_field_mean_power(pmx_ctx* ctx, pmx_devfield* f, double* pavg);
 int pmx_field_maxdiff2(pmx_ctx* ctx, pmx_devfield* a, pmx_devfield* b, double* out);
 int pmx_field_lincomb(pmx_ctx* ctx, pmx_devfield* dst, double ca, pmx_devfield* a, double cb, pmx_devfield* b);
 
+/* ---- inverse_pmd.m: the PMD matrix of a chain of fibers, and a constant Jones matrix on the field -------------------
+ * One fiber of the chain as fiber() returns it in its brf struct (inverse_pmd.m:9-17). */
+typedef struct pmx_brf {
+    int32_t ntrunk;        /* length(brf.theta) */
+    int32_t reserved;
+    double lcorr;          /* trunk length [m] */
+    const double* db0;     /* [ntrunk] */
+    const double* theta;   /* [ntrunk] */
+    const double* epsilon; /* [ntrunk] */
+    const double* betat;   /* [nfft]  scalar phase per metre (brf.betat) */
+    const double* db1;     /* [nfft]  differential phase per trunk (brf.db1) */
+} pmx_brf;
+/* U(:,:,n) and Uinv(:,:,n) of inverse_pmd.m:73-131 evaluated on the device, one thread per frequency, in the
+ * interpreter's order of operations (update_U keeps the first row and completes it to [a b; -b* a*], :152-161).
+ * mat: options.mat as 8 doubles (m11 re, im, m12, m21, m22), or NULL; gvd = 0 is options.gvd = 'no'.
+ * U, Uinv: [nfft][2][2] complex128 in the interpreter's column-major order (element (i,j,n) at i + 2j + 4n); either
+ * may be NULL. */
+int pmx_pmd_matrix(pmx_ctx* ctx, int64_t nfft, int32_t nfiber, const pmx_brf* brf, const double* mat, int32_t gvd,
+                   double* U, double* Uinv);
+/* [ux; uy] <- J [ux; uy] for every sample of every column; j = 8 doubles, row-major (j11 re, im, j12, j21, j22).  The
+ * change of reference system options.mat of inverse_pmd.m:87-89 commutes with the transforms, so it is applied in time. */
+int pmx_field_jones(pmx_ctx* ctx, pmx_devfield* f, const double* j);
+
 #ifdef __cplusplus
 }
 #endif

@@ -707,8 +707,10 @@ def ampliflat(gs: GState, gain_db: float, f_db: Optional[float] = None, noise=No
 
 
 # --------------------------------------------------------------------------
-def inverse_pmd_matrix(brf_list, nfft):
-    """inverse_pmd.m:91-131: U(omega) of a chain of fibers and its inverse (no options)."""
+def inverse_pmd_matrix(brf_list, nfft, mat=None, gvd=True):
+    """inverse_pmd.m:73-131: U(omega) of a chain of fibers and its inverse.  ``mat`` is options.mat (a change of the
+    reference system, applied first, :87-89 -- update_U keeps its first row only and completes it to the form
+    [a b; -b* a*], :158-161); ``gvd`` False is options.gvd = 'no' (:79,124-128)."""
     u = np.zeros((2, 2, nfft), dtype=np.complex128)
     u[0, 0, :] = 1
     u[1, 1, :] = 1
@@ -724,6 +726,8 @@ def inverse_pmd_matrix(brf_list, nfft):
         return un
 
     one = np.ones(nfft)
+    if mat is not None:
+        u = update(one, one, np.asarray(mat, dtype=np.complex128), u)
     for brf in brf_list:
         th, ep, db0 = brf['theta'], brf['epsilon'], brf['db0']
         db1 = brf['db1'][:, 0]
@@ -738,21 +742,29 @@ def inverse_pmd_matrix(brf_list, nfft):
             u = update(l1, 1 / l1, m2.conj().T @ m1, u)
         u = update(one, one, _mat_r(th[-1], ep[-1], np.float64), u)
         allgvd = allgvd + brf['betat'][:, 0] * brf['lcorr'] * ntr
-    u = u * fastexp(-allgvd)[None, None, :]
+    if gvd:
+        u = u * fastexp(-allgvd)[None, None, :]
     uinv = np.empty_like(u)
     uinv[0, 0], uinv[0, 1] = np.conj(u[0, 0]), np.conj(u[1, 0])
     uinv[1, 0], uinv[1, 1] = np.conj(u[0, 1]), np.conj(u[1, 1])
     return uinv, u
 
 
-def inverse_pmd(gs: GState, brf_list):
-    """inverse_pmd.m:133-141: apply Uinv to the field (single column)."""
+def inverse_pmd(gs: GState, brf_list, options=None):
+    """inverse_pmd.m:60-141 (single column) -> (Uinv, U), both [2, 2, Nfft].  The field is transformed when
+    options.apply is absent -- or equal to 'n', the one value the test at :135 lets through; any other value,
+    the documented 'no' included, leaves the field alone."""
+    if gs.FIELDX.shape[1] > 1:
+        raise ValueError('inverse_pmd can be used only with a unique field.')
+    options = options or {}
     nfft = gs.NSYMB * gs.NT
-    uinv, _ = inverse_pmd_matrix(brf_list, nfft)
-    fx, fy = fft(gs.FIELDX)[:, 0], fft(gs.FIELDY)[:, 0]
-    gs.FIELDX = ifft((uinv[0, 0] * fx + uinv[0, 1] * fy)[:, None])
-    gs.FIELDY = ifft((uinv[1, 0] * fx + uinv[1, 1] * fy)[:, None])
-    gs.DISP = np.zeros((2, gs.NCH))
+    uinv, u = inverse_pmd_matrix(brf_list, nfft, mat=options.get('mat'), gvd=options.get('gvd') != 'no')
+    if 'apply' not in options or options['apply'] == 'n':
+        fx, fy = fft(gs.FIELDX)[:, 0], fft(gs.FIELDY)[:, 0]
+        gs.FIELDX = ifft((uinv[0, 0] * fx + uinv[0, 1] * fy)[:, None])
+        gs.FIELDY = ifft((uinv[1, 0] * fx + uinv[1, 1] * fy)[:, None])
+        gs.DISP = np.zeros((2, gs.NCH))
+    return uinv, u
 
 
 def count_errors(pat_hat, pat) -> int:

@@ -17,7 +17,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.mini_m.interp import Interp, MStruct, from_m, to_m  # noqa: E402
+from oracle.mini_m.interp import Interp, MCell, MStruct, from_m, to_m  # noqa: E402
 from polmux_b200 import synth  # noqa: E402
 
 REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
@@ -129,6 +129,43 @@ def fixpower_cases():
              want_brf=False, amp={'gain': 0.8, 'f': 6.0, 'atype': 'fixpower'})
 
 
+def inverse_pmd_cases(name='invpmd_two_fibers'):
+    """inverse_pmd.m interpreted, after two fibers 'gp--' (5 and 8 plates): without options, with options.mat +
+    options.gvd = 'no', and with options.apply = 'no' (matrices only) -> tests/golden/invpmd/<name>.npz"""
+    nsymb, nt, seed = 64, 8, 1000
+    it = new_interp(seed)
+    ex, ey = tx_through_reference(it, nsymb, nt, 1, 28.0, 2.0, 'unique', True)
+    brfs = []
+    for f in (fib(length=2e4, dgd=0.5, nplates=5), fib(length=3e4, dgd=0.8, nplates=8, disp=4.0)):
+        brfs.append(it.call('fiber', [to_m(f), 'gp--'], 1)[0])
+    after = snapshot(it)
+    mat = np.array([[0.6, 0.8j], [0.8j, 0.6]]) * np.exp(0.3j)     # unitary, det != 1
+    data = {'in_ex': ex, 'in_ey': ey, 'prop_FIELDX': after['FIELDX'], 'prop_FIELDY': after['FIELDY'], 'mat': mat}
+    for k, b in enumerate(brfs):
+        bb = from_m(b)
+        for key in ('db0', 'theta', 'epsilon'):
+            data['brf%d_%s' % (k, key)] = np.asarray(bb[key]).ravel()
+        data['brf%d_lcorr' % k] = np.asarray(bb['lcorr']).ravel()
+        data['brf%d_betat' % k] = np.asarray(bb['betat'])
+        data['brf%d_db1' % k] = np.asarray(bb['db1'])
+    variants = {'plain': None, 'mat_nogvd': MStruct({'mat': to_m(mat), 'gvd': 'no'}), 'noapply': MStruct({'apply': 'no'}),
+                'apply_n': MStruct({'apply': 'n', 'mat': to_m(mat)})}
+    for tag, opt in variants.items():
+        G = it.globals['GSTATE'].copy()
+        G['FIELDX'], G['FIELDY'] = np.array(after['FIELDX']), np.array(after['FIELDY'])
+        G['DISP'] = np.array(after['DISP'])
+        it.globals['GSTATE'] = G
+        args = [MCell(brfs)] + ([opt] if opt is not None else [])
+        uinv, u = it.call('inverse_pmd', args, 2)
+        o = snapshot(it)
+        data.update({tag + '_Uinv': np.asarray(uinv), tag + '_U': np.asarray(u), tag + '_FIELDX': o['FIELDX'],
+                     tag + '_FIELDY': o['FIELDY'], tag + '_DISP': o['DISP']})
+    data['meta'] = np.array(json.dumps({'name': name, 'nsymb': nsymb, 'nt': nt, 'seed': seed, 'rate': 28.0, 'pavg': 2.0}))
+    os.makedirs(os.path.join(OUT, 'invpmd'), exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, 'invpmd', name + '.npz'), **data)
+    print('%-28s N=%-6d variants=%s' % (name, nsymb * nt, list(variants)))
+
+
 def run_c1_case(name='c1_cnlse_10plates_100km_2e16'):
     """BASELINE config C1 at its full size (Run_my_PDM_QPSK: 2^12 symbols x 16 samples = 2^16 samples, 28 GBaud, 100 km SMF,
     'gps-' CNLSE, 10 plates, x.dgd = 1.0 -- the value Run_my_PDM_QPSK.m:46 evaluates to) through the interpreted
@@ -162,6 +199,9 @@ def run_c1_case(name='c1_cnlse_10plates_100km_2e16'):
 if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'c1':     # only the full-size C1 case
         run_c1_case()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'invpmd':    # only inverse_pmd.m with its options
+        inverse_pmd_cases()
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == 'fixpower':  # only ampliflat(x,'fixpower',...) (ampliflat.m:65-72 + avg_power.m)
         fixpower_cases()
@@ -216,4 +256,5 @@ if __name__ == '__main__':
                                                          epsilon=[0.1, 0.5, -0.3], manakov='no', slope=0.057), 'gps-', pavg=1.0)
     run_print_case('scalar_sep3_ltol', 256, 16, 3, 'sepfields', fib(length=2e4, ltol=2e-6, slope=0.057), 'g-sx', two_pol=False)
     fixpower_cases()
+    inverse_pmd_cases()
     run_c1_case()

@@ -552,6 +552,8 @@ def arr(x):
             return x.reshape(1, 1)
         if x.ndim == 1:
             return x.reshape(1, -1)
+        if x.ndim == 3:        # (minimal 3-D support: element-wise operations, conj, unary minus, squeeze)
+            return x
         raise MError('N-d arrays are not supported')
     if isinstance(x, (bool, np.bool_)):
         return np.array([[bool(x)]])
@@ -841,7 +843,7 @@ class Interp:
         base = np.zeros((0, 0)) if cur is None else cur
         if isinstance(base, str):
             base = arr(base)
-        if isinstance(base, np.ndarray) and base.ndim == 3:
+        if (isinstance(base, np.ndarray) and base.ndim == 3) or len(step[2]) == 3:
             return self.index_assign(base, step[2], val, ws)
         return self.index_assign(arr(base), step[2], val, ws)
 
@@ -856,10 +858,24 @@ class Interp:
         return sel
 
     def index_assign(self, a, idx_nodes, val, ws):
-        if isinstance(a, np.ndarray) and a.ndim == 3 and len(idx_nodes) == 3:   # minimal 3-D support (zeros(a,b,c))
-            v = num(val)
+        if len(idx_nodes) == 3:   # minimal 3-D support: A(i,j,k) = v on a 3-D array, or creating / growing one
+            v = np.asarray(val) if isinstance(val, np.ndarray) and val.ndim == 3 else num(val)
+            a = np.asarray(a)
+            if a.ndim < 3:
+                a = a.reshape(a.shape + (1,)) if a.size else np.zeros((0, 0, 0), dtype=a.dtype)
             out = a.astype(np.complex128) if np.iscomplexobj(v) and not np.iscomplexobj(a) else a.copy()
-            sel = self._sel3(out, idx_nodes, ws)
+            sel = []
+            for d, node in enumerate(idx_nodes):
+                if node[0] == 'all':       # ':' on a dimension that does not exist yet takes its extent from the value
+                    sel.append(np.arange(out.shape[d] if out.shape[d] else (v.size if v.ndim < 3 else v.shape[d])))
+                else:
+                    ix = arr(self.eval(node, ws, end_ctx=(out, d, 3)))
+                    sel.append(np.real(ix).astype(np.int64).flatten('F') - 1)
+            need = tuple(max(out.shape[d], int(sel[d].max()) + 1 if sel[d].size else 0) for d in range(3))
+            if need != out.shape:
+                grown = np.zeros(need, dtype=out.dtype)
+                grown[:out.shape[0], :out.shape[1], :out.shape[2]] = out
+                out = grown
             out[np.ix_(*sel)] = v.flat[0] if v.size == 1 else np.reshape(v, tuple(len(q) for q in sel), order='F')
             return out
         v = num(val) if not isinstance(val, str) else arr(val)

@@ -31,7 +31,7 @@ EXPORTS = [
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
     'pmx_host_is_pinned', 'pmx_scalar_adaptive_run', 'pmx_mc_run', 'pmx_mc_nccl_available',
-    'pmx_ampliflat_exec_at', 'pmx_dsp_count', 'pmx_field_mean_power',
+    'pmx_ampliflat_exec_at', 'pmx_dsp_count', 'pmx_field_mean_power', 'pmx_pmd_matrix', 'pmx_field_jones',
 ]
 
 
@@ -79,6 +79,11 @@ class McDesc(C.Structure):
                 ('nspan', C.c_int32), ('equalize', C.c_int32), ('db0', _dp), ('theta', _dp), ('epsilon', _dp),
                 ('gain', C.c_double), ('sigma', _dp), ('ase_seed', C.c_uint64), ('sym', C.POINTER(C.c_uint8)),
                 ('nsymb', C.c_int32), ('nt', C.c_int32)]
+
+
+class BrfDesc(C.Structure):
+    _fields_ = [('ntrunk', C.c_int32), ('reserved', C.c_int32), ('lcorr', C.c_double), ('db0', _dp), ('theta', _dp),
+                ('epsilon', _dp), ('betat', _dp), ('db1', _dp)]
 
 
 class LinkDesc(C.Structure):
@@ -142,6 +147,8 @@ def load():
     lib.pmx_plan_set_length.argtypes = [vp, C.c_double]
     lib.pmx_field_max_power.argtypes = [vp, vp, _dp]
     lib.pmx_field_mean_power.argtypes = [vp, vp, _dp]
+    lib.pmx_pmd_matrix.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(BrfDesc), _dp, C.c_int32, _dp, _dp]
+    lib.pmx_field_jones.argtypes = [vp, vp, _dp]
     lib.pmx_field_maxdiff2.argtypes = [vp, vp, vp, _dp]
     lib.pmx_field_lincomb.argtypes = [vp, vp, C.c_double, vp, C.c_double, vp]
     lib.pmx_field_mux.argtypes = [vp, C.POINTER(Field), C.c_int32, C.POINTER(C.c_int64), _dp, C.POINTER(C.c_int64),
@@ -150,6 +157,40 @@ def load():
     lib.pmx_link_run.argtypes = [vp, C.POINTER(FiberDesc), C.POINTER(LinkDesc), C.POINTER(Field), C.POINTER(FiberResult)]
     _lib = lib
     return lib
+
+
+def pmd_matrix(ctx, nfft, brfs, mat=None, gvd=True, want_u=True, want_uinv=True):
+    """-> (Uinv, U), each [2, 2, nfft] complex128 or None (pmx_pmd_matrix; inverse_pmd.m:73-131)"""
+    keep, descs = [], (BrfDesc * len(brfs))()
+    for d, b in zip(descs, brfs):
+        arrs = {k: np.ascontiguousarray(np.asarray(b[k], dtype=np.float64).ravel()) for k in ('db0', 'theta', 'epsilon', 'betat', 'db1')}
+        if arrs['betat'].size != nfft or arrs['db1'].size != nfft:
+            raise ValueError('brf.betat / brf.db1 must have one value per frequency')
+        if not (arrs['db0'].size == arrs['theta'].size == arrs['epsilon'].size):
+            raise ValueError('brf.db0 / theta / epsilon must have one value per trunk')
+        keep.append(arrs)
+        d.ntrunk, d.lcorr = arrs['theta'].size, float(np.asarray(b['lcorr']).ravel()[0])
+        for k, a in arrs.items():
+            setattr(d, k, a.ctypes.data_as(_dp))
+    m = None
+    if mat is not None:
+        mm = np.asarray(mat, dtype=np.complex128)
+        if mm.shape != (2, 2):
+            raise ValueError('options.mat must be a [2,2] matrix')
+        m = np.ascontiguousarray(mm.reshape(4)).view(np.float64)
+    u = np.zeros((nfft, 2, 2), dtype=np.complex128) if want_u else None          # memory order of U(2,2,Nfft)
+    ui = np.zeros((nfft, 2, 2), dtype=np.complex128) if want_uinv else None
+    ctx.check(ctx.lib.pmx_pmd_matrix(ctx.h, nfft, len(brfs), descs, None if m is None else m.ctypes.data_as(_dp),
+                                     1 if gvd else 0, None if u is None else u.ctypes.data_as(_dp),
+                                     None if ui is None else ui.ctypes.data_as(_dp)))
+    tr = lambda a: None if a is None else a.transpose(2, 1, 0)                   # [n][j][i] -> (i, j, n)
+    return tr(ui), tr(u)
+
+
+def field_jones(ctx, field, jones):
+    """[ux; uy] <- J [ux; uy] on the device field (pmx_field_jones)"""
+    j = np.ascontiguousarray(np.asarray(jones, dtype=np.complex128).reshape(4)).view(np.float64)
+    ctx.check(ctx.lib.pmx_field_jones(ctx.h, field.h, j.ctypes.data_as(_dp)))
 
 
 def field_mean_power(ctx, field):

@@ -2121,6 +2121,183 @@ extern "C" int pmx_field_lincomb(pmx_ctx* c, pmx_devfield* dst, double ca, pmx_d
 }
 
 // ---------------------------------------------------------------------------
+// inverse_pmd.m:73-131 on the device.  update_U (:152-161) only ever propagates the first row (a, b) of U -- the second
+// is rebuilt as (-b*, a*) after every update -- so the state is two complex numbers per frequency.
+struct cplx {
+    double re, im;
+};
+static inline cplx cmulh(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+static inline cplx cconjh(cplx a) { return {a.re, -a.im}; }
+static inline cplx caddh(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+// getmatR (inverse_pmd.m:164-168): (cos(theta)*sig0 - sin(theta)*sig3i) * complex(cos(eps)*sig0, sin(eps)*sig2)
+static void get_mat_r(double theta, double eps, cplx m[4]) {
+    const double c = std::cos(theta), s = std::sin(theta), ce = std::cos(eps), se = std::sin(eps);
+    const cplx rt[4] = {{c, 0}, {-s, 0}, {s, 0}, {c, 0}};
+    const cplx re[4] = {{ce, 0}, {0, se}, {0, se}, {ce, 0}};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) m[2 * i + j] = caddh(cmulh(rt[2 * i], re[j]), cmulh(rt[2 * i + 1], re[2 + j]));
+}
+
+// one fiber: ab <- first row of (R_last * prod_k D_k R_k' R_(k-1) * D_1 R_1') * [a b; -b* a*]; allgvd += betat*lcorr*ntrunk
+__global__ void __launch_bounds__(128) pmx_k_pmd_update(double2* ab, double* allgvd, const double* db1, const double* betat,
+                                                         const double2* rows, const double* db0, int ntrunk, double lcorr,
+                                                         size_t nfft) {
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nfft) return;
+    double2 a = ab[2 * n], b = ab[2 * n + 1];
+    const double d1 = db1[n];
+    for (int k = 0; k <= ntrunk; ++k) {
+        double2 t11 = rows[2 * k], t12 = rows[2 * k + 1];
+        if (k < ntrunk) {   // l1 = fastexp(-deltabeta), deltabeta = 0.5*(db1 + db0(k)) (:95-97,115-118); the last update has l1 = 1
+            double sn, cs;
+            sincos(-(0.5 * (d1 + db0[k])), &sn, &cs);
+            const double2 l1 = make_double2(cs, sn);
+            t11 = make_double2(l1.x * t11.x - l1.y * t11.y, l1.x * t11.y + l1.y * t11.x);
+            t12 = make_double2(l1.x * t12.x - l1.y * t12.y, l1.x * t12.y + l1.y * t12.x);
+        }
+        const double2 u21 = make_double2(-b.x, b.y), u22 = make_double2(a.x, -a.y);
+        const double2 na = make_double2((t11.x * a.x - t11.y * a.y) + (t12.x * u21.x - t12.y * u21.y),
+                                        (t11.x * a.y + t11.y * a.x) + (t12.x * u21.y + t12.y * u21.x));
+        const double2 nb = make_double2((t11.x * b.x - t11.y * b.y) + (t12.x * u22.x - t12.y * u22.y),
+                                        (t11.x * b.y + t11.y * b.x) + (t12.x * u22.y + t12.y * u22.x));
+        a = na;
+        b = nb;
+    }
+    ab[2 * n] = a;
+    ab[2 * n + 1] = b;
+    allgvd[n] += betat[n] * lcorr * (double)ntrunk;
+}
+
+// U = Hgvd .* [a b; -b* a*], Uinv = U' (inverse_pmd.m:123-131), written in the interpreter's column-major [2][2][nfft]
+__global__ void __launch_bounds__(128) pmx_k_pmd_finish(const double2* ab, const double* allgvd, int gvd, size_t nfft,
+                                                         double2* U, double2* Uinv) {
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nfft) return;
+    const double2 a = ab[2 * n], b = ab[2 * n + 1];
+    double2 u[4] = {a, make_double2(-b.x, b.y), b, make_double2(a.x, -a.y)};   // (1,1) (2,1) (1,2) (2,2)
+    if (gvd) {
+        double sn, cs;
+        sincos(-allgvd[n], &sn, &cs);
+        for (int i = 0; i < 4; ++i) u[i] = make_double2(cs * u[i].x - sn * u[i].y, cs * u[i].y + sn * u[i].x);
+    }
+    if (U)
+        for (int i = 0; i < 4; ++i) U[4 * n + i] = u[i];
+    if (Uinv) {
+        Uinv[4 * n + 0] = make_double2(u[0].x, -u[0].y);   // Uinv(1,1) = conj(U(1,1))
+        Uinv[4 * n + 1] = make_double2(u[2].x, -u[2].y);   // Uinv(2,1) = conj(U(1,2))
+        Uinv[4 * n + 2] = make_double2(u[1].x, -u[1].y);   // Uinv(1,2) = conj(U(2,1))
+        Uinv[4 * n + 3] = make_double2(u[3].x, -u[3].y);
+    }
+}
+
+extern "C" int pmx_pmd_matrix(pmx_ctx* c, int64_t nfft, int32_t nfiber, const pmx_brf* brf, const double* mat, int32_t gvd,
+                              double* U, double* Uinv) {
+    if (!c || !brf || nfiber < 1 || nfft < 1) return set_err(c, PMX_ERR_INVALID, "pmx_pmd_matrix: bad arguments");
+    for (int f = 0; f < nfiber; ++f)
+        if (brf[f].ntrunk < 1 || !brf[f].db0 || !brf[f].theta || !brf[f].epsilon || !brf[f].betat || !brf[f].db1)
+            return set_err(c, PMX_ERR_INVALID, "pmx_pmd_matrix: fiber %d of the chain is incomplete", f);
+    CK(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)nfft;
+    int maxtr = 0;
+    for (int f = 0; f < nfiber; ++f) maxtr = std::max(maxtr, brf[f].ntrunk);
+    // one allocation: ab [2N] double2, allgvd [N], db1 [N], betat [N], rows [2(maxtr+1)] double2, db0 [maxtr], U, Uinv [4N] double2
+    const size_t bytes = 2 * N * 16 + 3 * N * 8 + 2 * (size_t)(maxtr + 1) * 16 + (size_t)maxtr * 8 + 8 * N * 16;
+    unsigned char* d = nullptr;
+    CK(c, cudaMallocAsync(&d, bytes, c->stream));
+    double2* ab = reinterpret_cast<double2*>(d);
+    double2* dU = ab + 2 * N;
+    double2* dUinv = dU + 4 * N;
+    double2* drows = dUinv + 4 * N;
+    double* dgvd = reinterpret_cast<double*>(drows + 2 * (size_t)(maxtr + 1));
+    double* ddb1 = dgvd + N;
+    double* dbetat = ddb1 + N;
+    double* ddb0 = dbetat + N;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) {
+        if (e == cudaSuccess) e = r;
+    };
+    // U = eye, or the first row of options.mat (update_U with l1 = l2 = 1, inverse_pmd.m:87-89)
+    std::vector<cplx> init(2 * N);
+    const cplx a0 = mat ? cplx{mat[0], mat[1]} : cplx{1.0, 0.0}, b0 = mat ? cplx{mat[2], mat[3]} : cplx{0.0, 0.0};
+    for (size_t n = 0; n < N; ++n) {
+        init[2 * n] = a0;
+        init[2 * n + 1] = b0;
+    }
+    step(cudaMemcpyAsync(ab, init.data(), 2 * N * 16, cudaMemcpyHostToDevice, c->stream));
+    step(cudaMemsetAsync(dgvd, 0, N * 8, c->stream));
+    std::vector<cplx> rows;
+    const unsigned grid = (unsigned)((N + 127) / 128);
+    for (int f = 0; f < nfiber && e == cudaSuccess; ++f) {
+        const pmx_brf& b = brf[f];
+        rows.assign(2 * (size_t)(b.ntrunk + 1), cplx{0, 0});
+        cplx m1[4], m2[4];
+        get_mat_r(b.theta[0], b.epsilon[0], m1);
+        rows[0] = cconjh(m1[0]);                         // matR' : first row = conj of the first column
+        rows[1] = cconjh(m1[2]);
+        for (int k = 1; k < b.ntrunk; ++k) {             // matR2' * matR1 (:100-102)
+            get_mat_r(b.theta[k - 1], b.epsilon[k - 1], m1);
+            get_mat_r(b.theta[k], b.epsilon[k], m2);
+            for (int j = 0; j < 2; ++j) rows[2 * k + j] = caddh(cmulh(cconjh(m2[0]), m1[j]), cmulh(cconjh(m2[2]), m1[2 + j]));
+        }
+        get_mat_r(b.theta[b.ntrunk - 1], b.epsilon[b.ntrunk - 1], m1);
+        rows[2 * b.ntrunk] = m1[0];
+        rows[2 * b.ntrunk + 1] = m1[1];
+        step(cudaMemcpyAsync(drows, rows.data(), rows.size() * 16, cudaMemcpyHostToDevice, c->stream));
+        step(cudaMemcpyAsync(ddb0, b.db0, (size_t)b.ntrunk * 8, cudaMemcpyHostToDevice, c->stream));
+        step(cudaMemcpyAsync(ddb1, b.db1, N * 8, cudaMemcpyHostToDevice, c->stream));
+        step(cudaMemcpyAsync(dbetat, b.betat, N * 8, cudaMemcpyHostToDevice, c->stream));
+        pmx_k_pmd_update<<<grid, 128, 0, c->stream>>>(ab, dgvd, ddb1, dbetat, drows, ddb0, b.ntrunk, b.lcorr, N);
+        c->launches++;
+        step(cudaGetLastError());
+        step(cudaStreamSynchronize(c->stream));          // rows / the caller's arrays are pageable host memory reused next turn
+    }
+    if (e == cudaSuccess) {
+        pmx_k_pmd_finish<<<grid, 128, 0, c->stream>>>(ab, dgvd, gvd ? 1 : 0, N, U ? dU : nullptr, Uinv ? dUinv : nullptr);
+        c->launches++;
+        step(cudaGetLastError());
+        if (U) step(cudaMemcpyAsync(U, dU, 4 * N * 16, cudaMemcpyDeviceToHost, c->stream));
+        if (Uinv) step(cudaMemcpyAsync(Uinv, dUinv, 4 * N * 16, cudaMemcpyDeviceToHost, c->stream));
+    }
+    cudaFreeAsync(d, c->stream);
+    cudaError_t es = cudaStreamSynchronize(c->stream);
+    CK(c, e);
+    CK(c, es);
+    return PMX_OK;
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) pmx_k_jones(E* field, size_t n_sa, double j0, double j1, double j2, double j3, double j4,
+                                                    double j5, double j6, double j7) {
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_sa; n += (size_t)gridDim.x * blockDim.x) {
+        const E x = field[2 * n], y = field[2 * n + 1];
+        const double xr = x.x, xi = x.y, yr = y.x, yi = y.y;
+        E ox, oy;
+        ox.x = (j0 * xr - j1 * xi) + (j2 * yr - j3 * yi);
+        ox.y = (j0 * xi + j1 * xr) + (j2 * yi + j3 * yr);
+        oy.x = (j4 * xr - j5 * xi) + (j6 * yr - j7 * yi);
+        oy.y = (j4 * xi + j5 * xr) + (j6 * yi + j7 * yr);
+        field[2 * n] = ox;
+        field[2 * n + 1] = oy;
+    }
+}
+
+extern "C" int pmx_field_jones(pmx_ctx* c, pmx_devfield* f, const double* j) {
+    if (!c || !f || !j) return set_err(c, PMX_ERR_INVALID, "pmx_field_jones: null argument");
+    CK(c, cudaSetDevice(c->device));
+    const size_t n_sa = (size_t)f->batch * f->nfc * f->nfft;
+    const unsigned grid = (unsigned)std::min<size_t>((n_sa + 255) / 256, 148 * 8);
+    if (f->precision == PMX_F32)
+        pmx_k_jones<float2><<<grid, 256, 0, c->stream>>>(reinterpret_cast<float2*>(f->data), n_sa, j[0], j[1], j[2], j[3], j[4],
+                                                         j[5], j[6], j[7]);
+    else
+        pmx_k_jones<double2><<<grid, 256, 0, c->stream>>>(reinterpret_cast<double2*>(f->data), n_sa, j[0], j[1], j[2], j[3],
+                                                          j[4], j[5], j[6], j[7]);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Local-error adaptive step on the scalar path: scalar_a_ssfm / adaptssfm (fiber.m:639-679, 938-1010) and the
 // x.dphiadapt variant of scalar_ssfm (fiber.m:588-611).  The accept/reject logic is host code as in the reference;
 // nl_step + attenuation, lin_step, the error norm and the Richardson combination run on the resident field.

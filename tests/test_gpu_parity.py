@@ -334,8 +334,16 @@ def test_inverse_pmd_gvd_no_and_link_onepol():
     rx = np.fft.ifft(np.fft.fft(tx_x[:, 0]) * ph)
     ry = np.fft.ifft(np.fft.fft(tx_y[:, 0]) * ph)
     assert rel_l2(G.FIELDX[:, 0], G.FIELDY[:, 0], rx, ry) < 1e-9
-    with pytest.raises(NotImplementedError):
-        pmx.inverse_pmd(brf, {'mat': np.eye(2)})
+    with pytest.raises(ValueError, match='unknown options'):
+        pmx.inverse_pmd(brf, {'theta': 0.1})
+    # options.mat = a rotation: inverting with it and then rotating back by hand equals the plain inversion
+    c, s_ = np.cos(0.4), np.sin(0.4)
+    before = (np.array(G.FIELDX), np.array(G.FIELDY))
+    G.FIELDX, G.FIELDY = tx_x.copy(), tx_y.copy()
+    brf = pmx.fiber(fib, 'gp--', rng=np.random.Generator(np.random.PCG64(11)))
+    pmx.inverse_pmd(brf, {'gvd': 'no', 'mat': np.array([[c, s_], [-s_, c]])})
+    bx, by = c * G.FIELDX + s_ * G.FIELDY, -s_ * G.FIELDX + c * G.FIELDY
+    assert rel_l2(bx, by, before[0], before[1]) < 1e-12
     # link with ASE on one polarization
     fib = base_fiber(length=2e4, dgd=0.2, nplates=8, manakov='yes')
     outs = []
