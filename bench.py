@@ -47,10 +47,10 @@ NSPAN, SPAN_KM, NPLATES, DGD = 10, 80.0, 100, 0.1
 GAIN_DB, NF_DB = 16.0, 5.0
 ALG_BYTES_PER_SA_STEP = 192.0   # 3 passes x (read + write) x 32 B   
 # dram__bytes_read.sum + dram__bytes_write.sum per Sa of a launch, from the ncu --set full capture summarised in
-# profiles/r1_ncu_v17_summary.txt (batch 16 in two groups: 8 realizations of 2^20 Sa per launch): pass A
-# (271.3+209.3) MB, B (268.8+218.4) MB, C (271.2+211.9) MB  ->  bytes per Sa; below the 64 algorithmic bytes because
+# profiles/r2_ncu_final_summary.txt (batch 16 in two groups: 8 realizations of 2^20 Sa per launch): pass A
+# (271.2+208.7) MB, B (269.3+217.5) MB, C (271.2+208.9) MB  ->  bytes per Sa; below the 64 algorithmic bytes because
 # part of the traffic is served by the L2
-NCU_DRAM_BYTES_PER_SA = {'passA': 480.6e6 / (8 << 20), 'passB': 487.2e6 / (8 << 20), 'passC': 483.1e6 / (8 << 20)}
+NCU_DRAM_BYTES_PER_SA = {'passA': 479.9e6 / (8 << 20), 'passB': 486.8e6 / (8 << 20), 'passC': 480.0e6 / (8 << 20)}
 CPU_SAMPLE_KM = SPAN_KM         # bounded CPU sample: span 1 of the link in full (80 km, 100 plates): 15-30 s per core
 # FP64 work of one whole trunk on one Sa (both polarizations of a bin) as pass B executes it: phasor progression 1 complex
 # product, phasor on one polarization 1 complex product (2 mul + 2 fma each), boundary matrix 4 mul + 8 fma
@@ -357,7 +357,7 @@ def main():
         ach = alg_bytes / (pms[dom] * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'kernel': names[dom], 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                 'frac': ach / peak, 'traffic': NCU_DRAM_BYTES_PER_SA[names[dom]] * prof_sa_steps / float(pn[dom]),
-                'traffic_source': 'ncu --set full, profiles/r1_ncu_v17_summary.txt, scaled to the Sa of a launch',
+                'traffic_source': 'ncu --set full, profiles/r2_ncu_final_summary.txt, scaled to the Sa of a launch',
                 'peak_source': peak_src,
                 'bytes_per_launch': alg_bytes / float(pn[dom]), 'ms_per_launch': pms[dom] / float(pn[dom]),
                 'launches_timed': int(pn[dom]),

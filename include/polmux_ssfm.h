@@ -78,7 +78,7 @@ void* pmx_ctx_stream(pmx_ctx* ctx);
  */
 typedef struct pmx_fiber_desc {
     int64_t nfft;        /* rows of FIELDX = NSYMB*NT (fiber.m:133); power of two, 2^6..2^24 */
-    int32_t nfc;         /* columns of FIELDX (fiber.m:132): <= 16; <= 8 for nfft <= 2^12 (on-chip) */
+    int32_t nfc;         /* columns of FIELDX (fiber.m:132): <= 64; <= 8 for nfft < 2^12 (on-chip: one cluster) */
     int32_t batch;       /* independent realizations propagated by one call (>=1)            */
     int32_t precision;   /* pmx_precision                                                     */
     int32_t manakov;     /* strcmp(manakov,'yes')   fiber.m:499                               */

@@ -12,7 +12,7 @@ static void (*g_at_exit)(void) = NULL;
 mxArray *mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity flag)
 {
     mxArray *a = (mxArray *)calloc(1, sizeof *a);
-    size_t cnt = m * n ? m * n : 1;
+    size_t cnt = m * n != 0 ? m * n : 1;
     a->m = m;
     a->n = n;
     a->pr = (double *)calloc(cnt, sizeof(double));

@@ -58,6 +58,8 @@
 #include <math.h>
 #include <string.h>
 #include "mex.h"
+
+#define PMX_MEX_MAX_NFC 64 /* the library's limit on field columns (polmux_ssfm.h: pmx_fiber_desc.nfc) */
 #include "polmux_ssfm.h"
 
 static pmx_ctx *g_ctx = NULL; /* one device context for the life of the MEX file */
@@ -94,7 +96,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     pmx_field io;
     pmx_fiber_result res;
     pmx_link_desc lk;
-    double gam_buf[16], beta_buf[32], sigma_buf[16];
+    double gam_buf[PMX_MEX_MAX_NFC], beta_buf[2 * PMX_MEX_MAX_NFC], sigma_buf[PMX_MEX_MAX_NFC];
     double *firstdz;
     int32_t *ncycle, *ntot, *status;
     uint64_t *seeds;
@@ -116,8 +118,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
     n = nfft * nfc;
     if (n == 0)
         mexErrMsgTxt("ssfm_mex: empty x field.");
-    if (nfc > 16)
-        mexErrMsgTxt("ssfm_mex: at most 16 field columns.");
+    if (nfc > PMX_MEX_MAX_NFC)
+        mexErrMsgTxt("ssfm_mex: at most 64 field columns.");
     if (mxGetNumberOfElements(prhs[1]) != 0 && (mxGetM(prhs[1]) != nfft || mxGetN(prhs[1]) != nfc))
         mexErrMsgTxt("ssfm_mex: ux and uy must have the same size.");
     if ((size_t)mxGetScalar(prhs[8]) != nfc)
@@ -398,7 +400,7 @@ static void cmd_fiber(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
     pmx_fiber_result res;
     pmx_plan *plan = NULL;
     pmx_devfield *f;
-    double gam_buf[16], beta_buf[32], firstdz = 0.0;
+    double gam_buf[PMX_MEX_MAX_NFC], beta_buf[2 * PMX_MEX_MAX_NFC], firstdz = 0.0;
     const double *P, *pl;
     int32_t ncycle = 0, ntot = 0, status = 0;
     size_t nfft, nfc, n, k, np;
@@ -414,8 +416,8 @@ static void cmd_fiber(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
     n = nfft * nfc;
     if (n == 0)
         mexErrMsgTxt("ssfm_mex: empty x field.");
-    if (nfc > 16)
-        mexErrMsgTxt("ssfm_mex: at most 16 field columns.");
+    if (nfc > PMX_MEX_MAX_NFC)
+        mexErrMsgTxt("ssfm_mex: at most 64 field columns.");
     has_y = mxGetNumberOfElements(prhs[2]) != 0;
     if (has_y && (mxGetM(prhs[2]) != nfft || mxGetN(prhs[2]) != nfc))
         mexErrMsgTxt("ssfm_mex: ux and uy must have the same size.");
@@ -537,7 +539,7 @@ static void cmd_fiber(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
 static void cmd_ampliflat(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 {
     /* prhs: 'ampliflat', ux, uy, gain, sigma, noise, asepol, opt */
-    double sigma_buf[16], *nz = NULL;
+    double sigma_buf[PMX_MEX_MAX_NFC], *nz = NULL;
     const mxArray *opt = nrhs > 7 ? prhs[7] : NULL;
     pmx_devfield *f;
     size_t nfft, nfc, n, k, c;
@@ -550,7 +552,7 @@ static void cmd_ampliflat(int nlhs, mxArray *plhs[], int nrhs, const mxArray *pr
     nfft = mxGetM(prhs[1]);
     nfc = mxGetN(prhs[1]);
     n = nfft * nfc;
-    if (n == 0 || nfc > 16)
+    if (n == 0 || nfc > PMX_MEX_MAX_NFC)
         mexErrMsgTxt("ssfm_mex: bad x field.");
     if (mxGetNumberOfElements(prhs[4]) != nfc)
         mexErrMsgTxt("ssfm_mex: sigma must have one entry per field column.");

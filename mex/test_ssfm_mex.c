@@ -19,8 +19,8 @@
 static mxArray *vec(FILE *f, size_t m, size_t n, int cplx)
 {
     mxArray *a = mxCreateDoubleMatrix(m, n, cplx ? mxCOMPLEX : mxREAL);
-    if (m * n && fread(a->pr, sizeof(double), m * n, f) != m * n) exit(3);
-    if (cplx && m * n && fread(a->pi, sizeof(double), m * n, f) != m * n) exit(3);
+    if (m * n != 0 && fread(a->pr, sizeof(double), m * n, f) != m * n) exit(3);
+    if (cplx && m * n != 0 && fread(a->pi, sizeof(double), m * n, f) != m * n) exit(3);
     return a;
 }
 static mxArray *scal(double v)

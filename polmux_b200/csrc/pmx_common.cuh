@@ -30,7 +30,7 @@ __host__ __device__ __forceinline__ cpx mkc(real a, real b) { return make_double
 #endif
 #define PMX_SA_BYTES (4 * (int)sizeof(real))
 
-#define PMX_MAX_NFC 16
+#define PMX_MAX_NFC 64
 
 // Debug builds (make EXTRA=-DPMX_DEBUG, `make debug`): index checks in the tile walks and the bin arithmetic; the
 // compute-sanitizer is not available on the pool, these traps stand in for its bounds checks.

@@ -91,6 +91,16 @@ def test_sepfields_two_columns():
     check_schedule(gs)
 
 
+@pytest.mark.parametrize('nch,flag,man', [(24, 'gps-', 'yes'), (40, 'gps-', 'no'), (64, 'gp--', 'no')])
+def test_sepfields_many_columns(nch, flag, man):
+    """more separate channels than a dense WDM comb of the reference's scripts (up to the library's 64 columns): per-column
+    constants, the step control's max over all the columns"""
+    fib = base_fiber(length=2e4, dgd=0.3, nplates=10, manakov=man, slope=0.057)
+    err, gs, _, _ = run_both(1 << 8, 16, fib, flag, nch=nch, ftype='sepfields', pavg=0.5)
+    assert err < TOL
+    check_schedule(gs)
+
+
 def test_energy_ratio():
     """every sub-step is unitary except exp(-alpha dz): sum|u|^2 out/in = exp(-alpha L)."""
     fib = base_fiber(length=8e4, dgd=0.1, nplates=100, manakov='yes')
