@@ -285,8 +285,10 @@ int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t ns
  *                   (pat_decoder.m:68-82), X/Y swap test and error count (ex20_coherent_polmux.m:168-176,
  *                   ber_estimate.m:118)
  * Neither the waveplates nor the transmitted symbols enter the processing; ref_patmat is only counted against.
- * Not built: the front-end of receiver_cohmix.m (filters, LO mixing), mygeteyeinfo's timing search and the toolbox
- * decimator of dsp4cohdec.m:176-184. */
+ * The front-end of receiver_cohmix.m is pmx_filter_create / pmx_field_modulate / pmx_cohmix_exec below.  Not built:
+ * mygeteyeinfo's pattern-correlation timing search (the 'theory' delay of dsp4cohdec.m:490-503 enters as sample_shift) and
+ * the decimator of dsp4cohdec.m:176-184 -- `decimate` is a Signal Processing Toolbox function that is not in the
+ * reference tree; the currents are sampled at the symbol centres without its anti-alias FIR. */
 typedef struct pmx_dsp_desc {
     int32_t nsymb, nt;        /* symbols per block, samples per symbol                                   */
     int32_t apply_cma;        /* p.applypol with p.polmethod = 'cma'                                      */
@@ -298,6 +300,10 @@ typedef struct pmx_dsp_desc {
     int32_t modorder;         /* p.modorder (2 = QPSK)                                                    */
     int32_t freqavg, phasavg; /* p.freqavg, p.phasavg                                                     */
     int32_t poworder;         /* p.poworder                                                               */
+    int32_t sample_shift;     /* symbol k is sampled at time index k*nt + sample_shift (circular): 0 for a field; for the
+                               * receiver's currents round(delay*NT), the shift dsp4cohdec.m:167-169 undoes            */
+    double peak;              /* samples are divided by peak = 4*sqrt(GSTATE.POWER(ich)) (dsp4cohdec.m:226-227);
+                               * 0: normalise the block to unit mean power instead                                     */
 } pmx_dsp_desc;
 /* ref_patmat: HOST [nsymb][4] bytes, the differentially decoded transmitted pattern [x1 x2 y1 y2] (pat_decoder of the
  * transmitted bits); counts_dev: DEVICE [batch] int64 (e.g. the NCCL send buffer); passes_host (may be NULL): [batch]
@@ -362,8 +368,33 @@ int pmx_field_max_power(pmx_ctx* ctx, pmx_devfield* f, double* umax);
 /* pavg[b*nfc+c] = mean_n |ux|^2 + |uy|^2: the average power avg_power.m:63-76 returns for a separate-channel field
  * (ampliflat's 'fixpower' gain, ampliflat.m:65-72). */
 int pmx_field_mean_power(pmx_ctx* ctx, pmx_devfield* f, double* pavg);
+/* the two polarizations apart: px, py [batch*nfc] (x.avgebx / x.avgeby of receiver_cohmix.m:174-175,233-234) */
+int pmx_field_mean_power_xy(pmx_ctx* ctx, pmx_devfield* f, double* px, double* py);
 int pmx_field_maxdiff2(pmx_ctx* ctx, pmx_devfield* a, pmx_devfield* b, double* out);
 int pmx_field_lincomb(pmx_ctx* ctx, pmx_devfield* dst, double ca, pmx_devfield* a, double cb, pmx_devfield* b);
+
+/* ---- linear filters: ifft(fft(u) .* H) -----------------------------------------------------------------------------
+ * The building block of the toolbox's filter devices and receivers (receiver_cohmix.m:169,180,231,302: optical band-pass
+ * and electrical low-pass filters given by myfilter.m as a vector over GSTATE.FN).  The plan runs the same three passes
+ * as a linear fiber step with H(k) as the per-bin factor; pmx_fiber_exec(plan, f, NULL) filters both polarizations of
+ * every column and realization of f in place.  H: [hcols][nfft] complex128 (re, im interleaved), in the order of
+ * GSTATE.FN (FFT order); hcols = 1 (one filter for every column) or nfc.  Destroy with pmx_plan_destroy. */
+int pmx_filter_create(pmx_ctx* ctx, int64_t nfft, int32_t nfc, int32_t batch, int32_t precision, const double* H,
+                      int32_t hcols, pmx_plan** out);
+
+/* ---- front-end of the coherent receiver: receiver_cohmix.m -----------------------------------------------------------
+ *   x.sigx = GSTATE.FIELDX(:,nch) (a copy, :133-137)            pmx_field_copy_cols
+ *   x.sigx = fft(x.sigx); x.sigx = x.sigx(nind)  (:171-172)     pmx_field_modulate (the shift by ndfn bins, in time)
+ *   x.sigx = x.sigx .* Hf; ifft  (:169,176,240-241)             filter plan with Hf = fastexp(-betat_post) .* myfilter(...)
+ *   LO, four mixer outputs, photodiodes  (:178-290)             pmx_cohmix_exec
+ *   Iric = real(ifft(fft(Iric) .* Hf))  (:293-302)              filter plan with the Hermitian part of the low-pass Hf
+ * pmx_field_copy_cols: count realization-columns of src, starting at src_bc, to dst starting at dst_bc (device to device).
+ * pmx_field_modulate : u(n) <- u(n)*exp(+i*2*pi*m*n/nfft), both polarizations of every column.
+ * pmx_cohmix_exec    : in place, per polarization s -> I_a + i*I_b with (I_a, I_b) = (I1 - I2, I3 - I4) (balanced) or
+ *                      (I1, I3); Elo(n) = lo_ecw * fastexp(lo_detune*(n+1) + lo_phase[n]); lo_phase: HOST [nfft] or NULL. */
+int pmx_field_copy_cols(pmx_devfield* dst, int32_t dst_bc, const pmx_devfield* src, int32_t src_bc, int32_t count);
+int pmx_field_modulate(pmx_ctx* ctx, pmx_devfield* f, int64_t m);
+int pmx_cohmix_exec(pmx_ctx* ctx, pmx_devfield* f, double lo_ecw, double lo_detune, const double* lo_phase, int32_t balanced);
 
 /* ---- inverse_pmd.m: the PMD matrix of a chain of fibers, and a constant Jones matrix on the field -------------------
  * One fiber of the chain as fiber() returns it in its brf struct (inverse_pmd.m:9-17). */

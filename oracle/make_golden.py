@@ -166,6 +166,70 @@ def inverse_pmd_cases(name='invpmd_two_fibers'):
     print('%-28s N=%-6d variants=%s' % (name, nsymb * nt, list(variants)))
 
 
+def rx_cases():
+    """receiver_cohmix.m (+ myfilter.m, evaldelay.m) interpreted -> tests/golden/rx/*.npz: separate channels with two
+    polarizations; three channels in one field with post-compensation, LO detuning and phase noise; one polarization with
+    single photodiodes; back-to-back"""
+    os.makedirs(os.path.join(OUT, 'rx'), exist_ok=True)
+    g = np.random.Generator(np.random.PCG64(77))
+    cases = {
+        'rx_sep3_2pol': dict(nsymb=64, nt=16, nch=3, ftype='sepfields', two_pol=True, ich=2,
+                             x={'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65, 'lopower': 0.0}),
+        'rx_unique3_post': dict(nsymb=64, nt=64, nch=3, ftype='unique', two_pol=True, ich=3,
+                                x={'oftype': 'supergauss', 'oord': 2, 'obw': 1.6, 'eftype': 'butt2', 'ebw': 0.7, 'lopower': 3.0,
+                                   'lodetuning': 3.2e9, 'dpost': -340.0, 'slopez': 1.5, 'lambda': 1550.0, 'lophasenoise': 'PN'}),
+        'rx_unique3_mid': dict(nsymb=64, nt=64, nch=3, ftype='unique', two_pol=True, ich=2,
+                               x={'oftype': 'butt4', 'obw': 1.8, 'eftype': 'rc2', 'ebw': 0.8}),
+        'rx_scalar_normal': dict(nsymb=128, nt=8, nch=1, ftype='unique', two_pol=False, ich=1,
+                                 x={'oftype': 'butt6', 'obw': 2.0, 'eftype': 'butt4', 'ebw': 0.75, 'pdtype': 'normal',
+                                    'lopower': -2.0}),
+        'rx_b2b': dict(nsymb=64, nt=16, nch=1, ftype='unique', two_pol=True, ich=1,
+                       x={'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65, 'b2b': 'b2b', 'dpost': 100.0,
+                          'slopez': 0.0, 'lambda': 1550.0}),
+    }
+    for name, c in cases.items():
+        it = new_interp(1000)
+        n = c['nsymb'] * c['nt']
+        ex, ey = tx_through_reference(it, c['nsymb'], c['nt'], c['nch'], 28.0, 2.0, c['ftype'], c['two_pol'])
+        it.call('fiber', [to_m(fib(length=1.5e4)), 'g-s-' if c['two_pol'] else 'g-s-'], 0)
+        pre = snapshot(it)
+        xs = dict(c['x'])
+        pn = None
+        if xs.get('lophasenoise') == 'PN':
+            pn = np.cumsum(0.02 * g.standard_normal(n))
+            xs['lophasenoise'] = pn.reshape(-1, 1)
+        xm = MStruct({k: (v if isinstance(v, str) else to_m(v)) for k, v in xs.items()})
+        iric, xo = it.call('receiver_cohmix', [to_m(float(c['ich'])), xm], 2)
+        post = snapshot(it)
+        assert np.array_equal(post['FIELDX'], pre['FIELDX'])          # GSTATE is left unchanged
+        G = it.globals['GSTATE']
+        data = {'FIELDX': pre['FIELDX'], 'FIELDY': pre['FIELDY'], 'DELAY': pre['DELAY'], 'POWER': pre['POWER'],
+                'FIELDX_TX': np.array(G['FIELDX_TX']),
+                'FIELDY_TX': np.array(G['FIELDY_TX']) if np.size(G['FIELDY_TX']) else np.zeros((0, 0)),
+                'Iric': np.asarray(iric), 'avgebx': np.asarray(xo['avgebx']).ravel(),
+                'avgeby': np.asarray(xo['avgeby']).ravel() if 'avgeby' in xo else np.zeros(0),
+                'post_delay': np.asarray(xo['post_delay'], dtype=np.float64).ravel()}
+        if pn is not None:
+            data['lophasenoise'] = pn
+        meta = {k: v for k, v in c.items() if k != 'x'}
+        meta.update(name=name, rate=28.0, pavg=2.0, seed=1000, x={k: v for k, v in c['x'].items()})
+        data['meta'] = np.array(json.dumps(meta))
+        np.savez_compressed(os.path.join(OUT, 'rx', name + '.npz'), **data)
+        print('%-28s N=%-6d Iric %s  |Iric|=%.6e' % (name, n, np.shape(iric), np.linalg.norm(np.asarray(iric))))
+    # myfilter.m / evaldelay.m over a frequency grid, every filter type
+    it = new_interp(1)
+    f = np.fft.fftshift(-8 + np.arange(512) / 32.0).reshape(1, -1)
+    out = {'f': f.ravel()}
+    for ft, bw, od in (('movavg', 0.9, 0), ('gauss', 0.95, 0), ('gauss_off', 0.95, 0.3), ('butt2', 0.7, 0), ('butt4', 0.7, 0),
+                       ('butt6', 0.7, 0), ('ideal', 1.1, 0), ('bessel5', 0.65, 0), ('rc1', 0.8, 0), ('rc2', 0.8, 0),
+                       ('supergauss', 0.9, 3)):
+        out['H_' + ft] = np.asarray(it.call('myfilter', [ft, to_m(f), to_m(bw), to_m(float(od))], 1)[0]).ravel()
+        out['D_' + ft] = np.asarray(it.call('evaldelay', [ft, to_m(bw)], 1)[0], dtype=np.float64).ravel()
+        out['P_' + ft] = np.array([bw, od], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, 'rx', 'myfilter_all.npz'), **out)
+    print('myfilter_all: %d filter types' % (len(out) // 3))
+
+
 def run_c1_case(name='c1_cnlse_10plates_100km_2e16'):
     """BASELINE config C1 at its full size (Run_my_PDM_QPSK: 2^12 symbols x 16 samples = 2^16 samples, 28 GBaud, 100 km SMF,
     'gps-' CNLSE, 10 plates, x.dgd = 1.0 -- the value Run_my_PDM_QPSK.m:46 evaluates to) through the interpreted
@@ -199,6 +263,9 @@ def run_c1_case(name='c1_cnlse_10plates_100km_2e16'):
 if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'c1':     # only the full-size C1 case
         run_c1_case()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'rx':        # only the receiver front-end
+        rx_cases()
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == 'invpmd':    # only inverse_pmd.m with its options
         inverse_pmd_cases()
@@ -257,4 +324,5 @@ if __name__ == '__main__':
     run_print_case('scalar_sep3_ltol', 256, 16, 3, 'sepfields', fib(length=2e4, ltol=2e-6, slope=0.057), 'g-sx', two_pol=False)
     fixpower_cases()
     inverse_pmd_cases()
+    rx_cases()
     run_c1_case()

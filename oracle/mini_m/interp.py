@@ -837,6 +837,18 @@ class Interp:
                 base.append(np.zeros((0, 0)))
             base[idx] = self._assign_chain(base[idx], chain[1:], val, ws)
             return base
+        # C(k) = {v}: paren-indexed assignment of a cell into a cell (varargout(2) = {x})
+        if isinstance(val, MCell) and len(chain) == 1 and len(step[2]) == 1 and (cur is None or isinstance(cur, MCell) or
+                                                                                  (isinstance(cur, np.ndarray) and cur.size == 0)):
+            base = MCell(cur) if isinstance(cur, MCell) else MCell()
+            idx = np.real(arr(self.eval(step[2][0], ws, end_ctx=(base, 0, 1)))).astype(np.int64).flatten() - 1
+            if len(val) not in (1, len(idx)):
+                raise MError('C(I) = {..}: number of elements must agree')
+            for n, i in enumerate(idx):
+                while len(base) <= i:
+                    base.append(np.zeros((0, 0)))
+                base[int(i)] = val[n if len(val) > 1 else 0]
+            return base
         # numeric indexed assignment
         if len(chain) > 1:
             raise MError('nested indexed assignment is not supported')
@@ -1289,6 +1301,17 @@ _simple('find', lambda x: (lambda p, a: (p.reshape(1, -1) if a.shape[0] == 1 els
 _simple('repmat', lambda x, m, n=None: np.tile(num(x), (int(scalar(m)), int(scalar(n if n is not None else m)))))
 _simple('circshift', lambda x, k: np.roll(num(x), int(scalar(k)), axis=(1 if num(x).shape[0] == 1 else 0)))
 _simple('fieldnames', lambda s: MCell(list(s.keys())))
+def _rmfield(st, f):
+    out = MStruct(st)
+    if f not in out:
+        raise MError("rmfield: no field '%s'" % f)
+    del out[f]
+    return out
+
+
+_simple('rmfield', _rmfield)
+# sinc is a toolbox function that is not in the reference tree (myfilter.m:80 calls it): sin(pi*x)/(pi*x), 1 at x = 0
+_simple('sinc', lambda x: np.sinc(num(x)))
 _simple('isfield', lambda s, f: np.array([[isinstance(s, MStruct) and f in s]]))
 _simple('num2str', lambda x, *r: ('%g' % np.real(scalar(x))))
 _simple('struct', lambda *a: MStruct({a[i]: a[i + 1] for i in range(0, len(a), 2)}))

@@ -31,7 +31,8 @@ EXPORTS = [
     'pmx_ctx_profile_read', 'pmx_qpsk_count', 'pmx_scalar_nl_exec', 'pmx_plan_set_length', 'pmx_field_max_power',
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
     'pmx_host_is_pinned', 'pmx_scalar_adaptive_run', 'pmx_mc_run', 'pmx_mc_nccl_available',
-    'pmx_ampliflat_exec_at', 'pmx_dsp_count', 'pmx_field_mean_power', 'pmx_pmd_matrix', 'pmx_field_jones',
+    'pmx_ampliflat_exec_at', 'pmx_dsp_count', 'pmx_field_mean_power', 'pmx_pmd_matrix', 'pmx_field_jones', 'pmx_filter_create', 'pmx_field_copy_cols', 'pmx_field_modulate',
+    'pmx_cohmix_exec', 'pmx_field_mean_power_xy',
 ]
 
 
@@ -71,7 +72,8 @@ class FiberResult(C.Structure):
 class DspDesc(C.Structure):
     _fields_ = [('nsymb', C.c_int32), ('nt', C.c_int32), ('apply_cma', C.c_int32), ('taps', C.c_int32), ('mu', C.c_double),
                 ('R', C.c_double * 2), ('phizero', C.c_double), ('max_passes', C.c_int32), ('modorder', C.c_int32),
-                ('freqavg', C.c_int32), ('phasavg', C.c_int32), ('poworder', C.c_int32)]
+                ('freqavg', C.c_int32), ('phasavg', C.c_int32), ('poworder', C.c_int32), ('sample_shift', C.c_int32),
+                ('peak', C.c_double)]
 
 
 class McDesc(C.Structure):
@@ -147,8 +149,13 @@ def load():
     lib.pmx_plan_set_length.argtypes = [vp, C.c_double]
     lib.pmx_field_max_power.argtypes = [vp, vp, _dp]
     lib.pmx_field_mean_power.argtypes = [vp, vp, _dp]
+    lib.pmx_field_mean_power_xy.argtypes = [vp, vp, _dp, _dp]
     lib.pmx_pmd_matrix.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(BrfDesc), _dp, C.c_int32, _dp, _dp]
     lib.pmx_field_jones.argtypes = [vp, vp, _dp]
+    lib.pmx_field_copy_cols.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int32]
+    lib.pmx_field_modulate.argtypes = [vp, vp, C.c_int64]
+    lib.pmx_cohmix_exec.argtypes = [vp, vp, C.c_double, C.c_double, _dp, C.c_int32]
+    lib.pmx_filter_create.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int32, C.POINTER(vp)]
     lib.pmx_field_maxdiff2.argtypes = [vp, vp, vp, _dp]
     lib.pmx_field_lincomb.argtypes = [vp, vp, C.c_double, vp, C.c_double, vp]
     lib.pmx_field_mux.argtypes = [vp, C.POINTER(Field), C.c_int32, C.POINTER(C.c_int64), _dp, C.POINTER(C.c_int64),
@@ -187,6 +194,25 @@ def pmd_matrix(ctx, nfft, brfs, mat=None, gvd=True, want_u=True, want_uinv=True)
     return tr(ui), tr(u)
 
 
+def field_copy_cols(dst, dst_bc, src, src_bc, count=1):
+    """count realization-columns of src (from src_bc) -> dst (from dst_bc), device to device"""
+    dst.ctx.check(dst.ctx.lib.pmx_field_copy_cols(dst.h, int(dst_bc), src.h, int(src_bc), int(count)))
+
+
+def field_modulate(ctx, field, m):
+    """u(n) <- u(n) * exp(+i*2*pi*m*n/nfft) (pmx_field_modulate)"""
+    ctx.check(ctx.lib.pmx_field_modulate(ctx.h, field.h, int(m)))
+
+
+def cohmix_exec(ctx, field, lo_ecw=1.0, lo_detune=0.0, lo_phase=None, balanced=True):
+    """LO mixing + photodetection in place (pmx_cohmix_exec): each polarization becomes I_a + i*I_b"""
+    ph = None if lo_phase is None else np.ascontiguousarray(np.asarray(lo_phase, dtype=np.float64).ravel())
+    if ph is not None and ph.size != field.nfft:
+        raise ValueError('Incompatible vector.')                               # receiver_cohmix.m:203-205
+    ctx.check(ctx.lib.pmx_cohmix_exec(ctx.h, field.h, float(lo_ecw), float(lo_detune),
+                                      None if ph is None else ph.ctypes.data_as(_dp), 1 if balanced else 0))
+
+
 def field_jones(ctx, field, jones):
     """[ux; uy] <- J [ux; uy] on the device field (pmx_field_jones)"""
     j = np.ascontiguousarray(np.asarray(jones, dtype=np.complex128).reshape(4)).view(np.float64)
@@ -198,6 +224,14 @@ def field_mean_power(ctx, field):
     out = np.zeros((field.batch, field.nfc), dtype=np.float64)
     ctx.check(ctx.lib.pmx_field_mean_power(ctx.h, field.h, out.ctypes.data_as(_dp)))
     return out
+
+
+def field_mean_power_xy(ctx, field):
+    """-> (mean |ux|^2, mean |uy|^2), each [batch, nfc] (pmx_field_mean_power_xy)"""
+    px = np.zeros((field.batch, field.nfc), dtype=np.float64)
+    py = np.zeros_like(px)
+    ctx.check(ctx.lib.pmx_field_mean_power_xy(ctx.h, field.h, px.ctypes.data_as(_dp), py.ctypes.data_as(_dp)))
+    return px, py
 
 
 def host_is_pinned(a) -> bool:
@@ -451,6 +485,23 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+class Filter(Plan):
+    """u <- ifft(fft(u) .* H) on a device field (pmx_filter_create).  H: [nfft] or [nfft, nfc] complex, in the order of
+    GSTATE.FN; one column filters every field column alike."""
+
+    def __init__(self, ctx: Context, nfft, nfc, H, batch=1, precision=PMX_F64):
+        hh = np.asarray(H, dtype=np.complex128)
+        hh = hh.reshape(nfft, -1) if hh.ndim > 1 else hh.reshape(nfft, 1)
+        if hh.shape[1] not in (1, nfc):
+            raise ValueError('H must have one column, or one per field column')
+        self.ctx, self.desc, self.keep = ctx, None, None
+        hc = np.ascontiguousarray(hh.T)                       # [hcols][nfft]
+        h = C.c_void_p()
+        ctx.check(ctx.lib.pmx_filter_create(ctx.h, int(nfft), int(nfc), int(batch), int(precision),
+                                            hc.ctypes.data_as(_dp), hc.shape[0], C.byref(h)))
+        self.h = h
 
 
 def make_link(nspan, gain=0.0, sigma=None, plates=None, plate_sets=1, noise=None, seeds=None, first=0, asepol=3):

@@ -220,6 +220,8 @@ struct pmx_plan {
     const PmxLaunchTable* tB;  // pass B   (L = N2)
     double* betat_p = nullptr;
     double* db1_p = nullptr;
+    double2* hfilt = nullptr;      // linear-filter plans: H per bin, permuted like betat_p
+    long long hfilt_stride = 0;
     PlateConst* plates = nullptr;
     StepCtl* ctl = nullptr;
     StepPkg* pkg = nullptr;  // [batch] step packages written by pmx_k_ctl
@@ -728,6 +730,7 @@ extern "C" void pmx_plan_destroy(pmx_plan* p) {
     cudaStream_t st = p->ctx->stream;
     if (p->betat_p) cudaFreeAsync(p->betat_p, st);
     if (p->db1_p) cudaFreeAsync(p->db1_p, st);
+    if (p->hfilt) cudaFreeAsync(p->hfilt, st);
     if (p->plates) cudaFreeAsync(p->plates, st);
     if (p->ctl) cudaFreeAsync(p->ctl, st);
     if (p->pkg) cudaFreeAsync(p->pkg, st);
@@ -930,6 +933,70 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
 }
 
 // ---------------------------------------------------------------------------
+// A linear filter as a plan: one step of a fiber without dispersion, birefringence, nonlinearity or loss whose per-bin
+// factor is the caller's H instead of exp(-i*betat*dz).  pmx_fiber_exec on it is u <- ifft(fft(u) .* H).
+__global__ void __launch_bounds__(256) pmx_k_permute_c(const double2* __restrict__ src, double2* __restrict__ dst, int log2N1,
+                                                       int log2N2, int ncol) {
+    const size_t N = (size_t)1 << (log2N1 + log2N2), total = N * ncol;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t col = i >> (log2N1 + log2N2), o = i & (N - 1);
+        const size_t k1 = o >> log2N2, k2 = o & (((size_t)1 << log2N2) - 1);
+        dst[i] = src[col * N + k1 + (k2 << log2N1)];
+    }
+}
+
+extern "C" int pmx_filter_create(pmx_ctx* c, int64_t nfft, int32_t nfc, int32_t batch, int32_t precision, const double* H,
+                                 int32_t hcols, pmx_plan** out) {
+    if (!c || !H || !out) return set_err(c, PMX_ERR_INVALID, "pmx_filter_create: null argument");
+    *out = nullptr;
+    if (nfc < 1 || (hcols != 1 && hcols != nfc))
+        return set_err(c, PMX_ERR_INVALID, "pmx_filter_create: H must have one column, or one per field column");
+    if (nfft < 1) return set_err(c, PMX_ERR_INVALID, "pmx_filter_create: nfft");
+    const std::vector<double> zeros((size_t)nfft * nfc, 0.0), gam((size_t)nfc, 0.0);
+    const double zero1 = 0.0;
+    pmx_fiber_desc d;
+    memset(&d, 0, sizeof d);
+    d.nfft = nfft;
+    d.nfc = nfc;
+    d.batch = batch;
+    d.precision = precision;
+    d.length = d.dzmaxt = 1.0;
+    d.dphimaxt = INFINITY;
+    d.gam = gam.data();
+    d.fls[0] = 1;                       // 'g---': exactly one linear step
+    d.nplates = d.plate_sets = 1;
+    d.db0 = d.theta = d.epsilon = &zero1;
+    d.betat = zeros.data();
+    d.disp_mode = PMX_DISP_VECTOR;
+    d.nsymb = (int32_t)std::min<int64_t>(nfft, INT32_MAX);
+    d.nt = 1;
+    d.symbolrate = 1.0;
+    pmx_plan* p = nullptr;
+    int rc = pmx_plan_create(c, &d, &p);
+    if (rc) return rc;
+    const size_t n = (size_t)nfft * hcols;
+    double2* raw = nullptr;
+    cudaError_t e = cudaMallocAsync(&p->hfilt, n * sizeof(double2), c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&raw, n * sizeof(double2), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(raw, H, n * sizeof(double2), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        pmx_k_permute_c<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, c->stream>>>(raw, p->hfilt, p->log2N1,
+                                                                                                   p->log2N2, hcols);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (raw) cudaFreeAsync(raw, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // the caller's H may go away
+    if (e != cudaSuccess) {
+        pmx_plan_destroy(p);
+        return set_err(c, PMX_ERR_CUDA, "pmx_filter_create: %s", cudaGetErrorString(e));
+    }
+    p->hfilt_stride = hcols > 1 ? (long long)nfft : 0;
+    *out = p;
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
 static int ensure_hctl(pmx_ctx* c, int batch) {
     if (c->h_ctl_cap < batch) {
         if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -980,6 +1047,8 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     pa.ctl = p->ctl;
     pa.betat_p = p->betat_p;
     pa.db1_p = p->db1_p;
+    pa.hfilt = p->hfilt;
+    pa.hfilt_stride = p->hfilt_stride;
     pa.plates = p->plates;
     pa.trace_dz = p->trace_dz;
     pa.trace_ntrunk = p->trace_ntrunk;
@@ -1602,30 +1671,43 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
 // threads per realization, all realizations of the batch in parallel.  FP64.
 #define PMX_DSP_MAX_TAPS 15
 
-// sig[(b*2 + pol)*L + k] = field sample at the centre of symbol k, divided by sqrt(mean |s|^2 over both polarizations)
+// sig[(b*2 + pol)*L + k] = field sample at time index k*nt + shift (circular): the centre of symbol k for a field, the
+// centre delayed by the receiver's filters for its currents (fastshift(Irx, round(-delay*NT)), dsp4cohdec.m:167-169);
+// divided by `peak` (dsp4cohdec.m:226-227) or, with peak = 0, by sqrt(mean |s|^2 over both polarizations)
 __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t N, int l1, int l2, int nsymb, int nt,
-                                                        cpx* sig) {
+                                                        long long shift, double peak, cpx* sig) {
     __shared__ double red[256];
     const int b = blockIdx.x;
     const cpx* fld = field + (size_t)b * N * 2;
-    double acc = 0.0;
-    for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
-        const size_t m = pmx_mem_index((size_t)k * nt, l1, l2);
-        const cpx x = fld[2 * m], y = fld[2 * m + 1];
-        acc += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
-    }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {   // fixed tree: the same result on every run
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    auto at = [&](int k) { return pmx_mem_index((size_t)(((long long)k * nt + shift) & (long long)(N - 1)), l1, l2); };
+    double inv;
+    if (peak > 0.0) {
+        inv = 1.0 / peak;
+    } else {
+        double acc = 0.0;
+        for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
+            const size_t m = at(k);
+            const cpx x = fld[2 * m], y = fld[2 * m + 1];
+            acc += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
+        }
+        red[threadIdx.x] = acc;
         __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {   // fixed tree: the same result on every run
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        inv = 1.0 / sqrt(red[0] / (2.0 * nsymb));
     }
-    const double inv = 1.0 / sqrt(red[0] / (2.0 * nsymb));
     for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
-        const size_t m = pmx_mem_index((size_t)k * nt, l1, l2);
+        const size_t m = at(k);
         const cpx x = fld[2 * m], y = fld[2 * m + 1];
-        sig[((size_t)b * 2 + 0) * nsymb + k] = make_double2(x.x * inv, x.y * inv);
-        sig[((size_t)b * 2 + 1) * nsymb + k] = make_double2(y.x * inv, y.y * inv);
+        if (peak > 0.0) {   // Signals/peak: a division in the reference
+            sig[((size_t)b * 2 + 0) * nsymb + k] = make_double2(x.x / peak, x.y / peak);
+            sig[((size_t)b * 2 + 1) * nsymb + k] = make_double2(y.x / peak, y.y / peak);
+        } else {
+            sig[((size_t)b * 2 + 0) * nsymb + k] = make_double2(x.x * inv, x.y * inv);
+            sig[((size_t)b * 2 + 1) * nsymb + k] = make_double2(y.x * inv, y.y * inv);
+        }
     }
 }
 
@@ -1876,7 +1958,11 @@ extern "C" int pmx_dsp_count(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d,
     CK(c, cudaMemcpyAsync(dref, ref_patmat, (size_t)L * 4, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemsetAsync(acc, 0, (size_t)B * 4 * sizeof(unsigned long long), c->stream));
     CK(c, cudaMemsetAsync(dpass, 0, (size_t)B * sizeof(int), c->stream));
-    pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sig);
+    {
+        const long long N = (long long)f->nfft;
+        const long long sh = (((long long)d->sample_shift % N) + N) % N;
+        pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sh, d->peak, sig);
+    }
     const cpx* stream_in = sig;
     if (d->apply_cma) {
         const int rep = d->max_passes > 0 ? d->max_passes + 1 : 50 * (int)ceil(1.0 / ((double)L * d->mu));
@@ -2008,52 +2094,76 @@ extern "C" int pmx_field_max_power(pmx_ctx* c, pmx_devfield* f, double* umax) {
 // result is the same on every run.  E = double2 or float2 elements; the sum is taken in double either way.
 template <typename E>
 __global__ void __launch_bounds__(256) pmx_k_mean_power(const E* field, size_t N, double* part) {
-    __shared__ double red[256];
+    __shared__ double redx[256], redy[256];
     const E* fld = field + (size_t)blockIdx.y * N * 2;
     const size_t per = (N + gridDim.x - 1) / gridDim.x;
     const size_t n0 = blockIdx.x * per, n1 = n0 + per < N ? n0 + per : N;
-    double acc = 0.0;
+    double ax = 0.0, ay = 0.0;
     for (size_t n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
         const E x = fld[2 * n], y = fld[2 * n + 1];
-        acc += ((double)x.x * x.x + (double)x.y * x.y) + ((double)y.x * y.x + (double)y.y * y.y);
+        ax += (double)x.x * x.x + (double)x.y * x.y;
+        ay += (double)y.x * y.x + (double)y.y * y.y;
     }
-    red[threadIdx.x] = acc;
+    redx[threadIdx.x] = ax;
+    redy[threadIdx.x] = ay;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        if (threadIdx.x < o) {
+            redx[threadIdx.x] += redx[threadIdx.x + o];
+            redy[threadIdx.x] += redy[threadIdx.x + o];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = red[0];
+    if (threadIdx.x == 0) {
+        part[2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x)] = redx[0];
+        part[2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + 1] = redy[0];
+    }
 }
 
+// out[0..nbc) = mean |x|^2, out[nbc..2nbc) = mean |y|^2
 __global__ void pmx_k_mean_power_fin(const double* part, int nchunk, size_t N, int nbc, double* out) {
     const int bc = blockIdx.x * blockDim.x + threadIdx.x;
     if (bc >= nbc) return;
-    double acc = 0.0;
-    for (int i = 0; i < nchunk; ++i) acc += part[(size_t)bc * nchunk + i];
-    out[bc] = acc / (double)N;
+    double ax = 0.0, ay = 0.0;
+    for (int i = 0; i < nchunk; ++i) {
+        ax += part[2 * ((size_t)bc * nchunk + i)];
+        ay += part[2 * ((size_t)bc * nchunk + i) + 1];
+    }
+    out[bc] = ax / (double)N;
+    out[nbc + bc] = ay / (double)N;
 }
 
-extern "C" int pmx_field_mean_power(pmx_ctx* c, pmx_devfield* f, double* pavg) {
-    if (!c || !f || !pavg) return set_err(c, PMX_ERR_INVALID, "pmx_field_mean_power: null argument");
+extern "C" int pmx_field_mean_power_xy(pmx_ctx* c, pmx_devfield* f, double* px, double* py) {
+    if (!c || !f || !px || !py) return set_err(c, PMX_ERR_INVALID, "pmx_field_mean_power: null argument");
     CK(c, cudaSetDevice(c->device));
     const int nbc = f->batch * f->nfc;
     const int nchunk = (int)std::max<size_t>(1, std::min<size_t>(((size_t)f->nfft + 4095) / 4096, (148 * 8 + nbc - 1) / nbc));
     double* d = nullptr;
-    CK(c, cudaMallocAsync(&d, ((size_t)nbc * nchunk + nbc) * sizeof(double), c->stream));
+    CK(c, cudaMallocAsync(&d, (2 * (size_t)nbc * nchunk + 2 * nbc) * sizeof(double), c->stream));
+    double* dout = d + 2 * (size_t)nbc * nchunk;
     dim3 g(nchunk, nbc);
     if (f->precision == PMX_F32)
         pmx_k_mean_power<float2><<<g, 256, 0, c->stream>>>(reinterpret_cast<const float2*>(f->data), (size_t)f->nfft, d);
     else
         pmx_k_mean_power<double2><<<g, 256, 0, c->stream>>>(reinterpret_cast<const double2*>(f->data), (size_t)f->nfft, d);
-    pmx_k_mean_power_fin<<<(nbc + 127) / 128, 128, 0, c->stream>>>(d, nchunk, (size_t)f->nfft, nbc, d + (size_t)nbc * nchunk);
+    pmx_k_mean_power_fin<<<(nbc + 127) / 128, 128, 0, c->stream>>>(d, nchunk, (size_t)f->nfft, nbc, dout);
     c->launches += 2;
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(pavg, d + (size_t)nbc * nchunk, nbc * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(px, dout, nbc * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(py, dout + nbc, nbc * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     cudaFreeAsync(d, c->stream);
     CK(c, e);
     CK(c, cudaStreamSynchronize(c->stream));
+    return PMX_OK;
+}
+
+extern "C" int pmx_field_mean_power(pmx_ctx* c, pmx_devfield* f, double* pavg) {
+    if (!c || !f || !pavg) return set_err(c, PMX_ERR_INVALID, "pmx_field_mean_power: null argument");
+    const int nbc = f->batch * f->nfc;
+    std::vector<double> px(nbc), py(nbc);
+    int rc = pmx_field_mean_power_xy(c, f, px.data(), py.data());
+    if (rc) return rc;
+    for (int i = 0; i < nbc; ++i) pavg[i] = px[i] + py[i];   // E = Ex + Ey (avg_power.m:131)
     return PMX_OK;
 }
 
@@ -2294,6 +2404,127 @@ extern "C" int pmx_field_jones(pmx_ctx* c, pmx_devfield* f, const double* j) {
                                                           j[4], j[5], j[6], j[7]);
     c->launches++;
     CK(c, cudaGetLastError());
+    return PMX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Front-end of the coherent receiver (receiver_cohmix.m): copies of field columns, the channel's frequency shift, LO
+// mixing + photodetection.  The two filters in between are filter plans (pmx_filter_create).
+extern "C" int pmx_field_copy_cols(pmx_devfield* dst, int32_t dst_bc, const pmx_devfield* src, int32_t src_bc, int32_t count) {
+    if (!dst || !src) return set_err(nullptr, PMX_ERR_INVALID, "null field");
+    pmx_ctx* c = dst->ctx;
+    if (dst->nfft != src->nfft || dst->precision != src->precision)
+        return set_err(c, PMX_ERR_INVALID, "pmx_field_copy_cols: length or precision mismatch");
+    if (count < 0 || dst_bc < 0 || src_bc < 0 || dst_bc + count > dst->batch * dst->nfc || src_bc + count > src->batch * src->nfc)
+        return set_err(c, PMX_ERR_INVALID, "pmx_field_copy_cols: column range outside the field");
+    CK(c, cudaSetDevice(c->device));
+    const size_t col = (size_t)src->nfft * 2 * src->cbytes();
+    CK(c, cudaMemcpyAsync((char*)dst->data + (size_t)dst_bc * col, (const char*)src->data + (size_t)src_bc * col, (size_t)count * col,
+                          cudaMemcpyDeviceToDevice, c->stream));
+    return PMX_OK;
+}
+
+// time index of the sample stored at position pos of a column
+__device__ __forceinline__ size_t pmx_time_index(size_t pos, int l1, int l2) {
+    return ((pos & (((size_t)1 << l1) - 1)) << l2) + (pos >> l1);
+}
+
+// u(n) <- u(n) * exp(+i*2*pi*m*n/N): the spectrum moves up by m bins (x.sigx(nind), receiver_cohmix.m:93,172)
+template <typename E>
+__global__ void __launch_bounds__(256) pmx_k_modulate(E* field, size_t N, int l1, int l2, long long m) {
+    E* fld = field + (size_t)blockIdx.y * N * 2;
+    for (size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pos < N; pos += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long r = ((unsigned long long)m * (unsigned long long)pmx_time_index(pos, l1, l2)) & (N - 1);  // m*n mod N
+        double sn, cs;
+        sincospi(2.0 * (double)r / (double)N, &sn, &cs);
+        const E x = fld[2 * pos], y = fld[2 * pos + 1];
+        E ox, oy;
+        ox.x = (double)x.x * cs - (double)x.y * sn;
+        ox.y = (double)x.x * sn + (double)x.y * cs;
+        oy.x = (double)y.x * cs - (double)y.y * sn;
+        oy.y = (double)y.x * sn + (double)y.y * cs;
+        fld[2 * pos] = ox;
+        fld[2 * pos + 1] = oy;
+    }
+}
+
+extern "C" int pmx_field_modulate(pmx_ctx* c, pmx_devfield* f, int64_t m) {
+    if (!c || !f) return set_err(c, PMX_ERR_INVALID, "pmx_field_modulate: null argument");
+    CK(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)f->nfft;
+    const long long mm = ((m % (long long)N) + (long long)N) % (long long)N;
+    dim3 g((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), f->batch * f->nfc);
+    if (f->precision == PMX_F32)
+        pmx_k_modulate<float2><<<g, 256, 0, c->stream>>>(reinterpret_cast<float2*>(f->data), N, f->log2N1, f->log2N2, mm);
+    else
+        pmx_k_modulate<double2><<<g, 256, 0, c->stream>>>(reinterpret_cast<double2*>(f->data), N, f->log2N1, f->log2N2, mm);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return PMX_OK;
+}
+
+// The four mixer outputs and the photocurrents of one polarization (receiver_cohmix.m:253-277), as the interpreter forms
+// them: E1 = j*s + j*lo, E2 = s - lo, E3 = j*s - lo, E4 = -s + j*lo, I_k = real(E_k .* conj(E_k)); balanced detection
+// returns (I1 - I2, I3 - I4), single photodiodes (I1, I3).  The pair is stored as one complex sample.
+__device__ __forceinline__ double2 pmx_mix_pd(double sr, double si, double lr, double li, int balanced) {
+    const double e1r = -si - li, e1i = sr + lr;
+    const double e3r = -si - lr, e3i = sr - li;
+    const double i1 = e1r * e1r + e1i * e1i, i3 = e3r * e3r + e3i * e3i;
+    if (!balanced) return make_double2(i1, i3);
+    const double e2r = sr - lr, e2i = si - li;
+    const double e4r = -sr - li, e4i = -si + lr;
+    const double i2 = e2r * e2r + e2i * e2i, i4 = e4r * e4r + e4i * e4i;
+    return make_double2(i1 - i2, i3 - i4);
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) pmx_k_cohmix(E* field, size_t N, int l1, int l2, double ecw, double detune,
+                                                     const double* lophase, int balanced) {
+    E* fld = field + (size_t)blockIdx.y * N * 2;
+    for (size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pos < N; pos += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = pmx_time_index(pos, l1, l2);
+        // Elo = LO_Ecw * fastexp(LO_Detuning + LO_PhaseNoise), LO_Detuning = 2*pi*kdet/Nfft*(1:Nfft)' (:200,219)
+        const double ph = (detune != 0.0 ? detune * (double)(n + 1) : 0.0) + (lophase ? lophase[n] : 0.0);
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        const double lr = ecw * cs, li = ecw * sn;
+        const E x = fld[2 * pos], y = fld[2 * pos + 1];
+        const double2 zx = pmx_mix_pd(x.x, x.y, lr, li, balanced), zy = pmx_mix_pd(y.x, y.y, lr, li, balanced);
+        E ox, oy;
+        ox.x = zx.x; ox.y = zx.y; oy.x = zy.x; oy.y = zy.y;
+        fld[2 * pos] = ox;
+        fld[2 * pos + 1] = oy;
+    }
+}
+
+extern "C" int pmx_cohmix_exec(pmx_ctx* c, pmx_devfield* f, double lo_ecw, double lo_detune, const double* lo_phase,
+                               int32_t balanced) {
+    if (!c || !f) return set_err(c, PMX_ERR_INVALID, "pmx_cohmix_exec: null argument");
+    CK(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)f->nfft;
+    double* dph = nullptr;
+    if (lo_phase) {
+        CK(c, cudaMallocAsync(&dph, N * sizeof(double), c->stream));
+        cudaError_t e = cudaMemcpyAsync(dph, lo_phase, N * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(dph, c->stream);
+            CK(c, e);
+        }
+    }
+    dim3 g((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), f->batch * f->nfc);
+    if (f->precision == PMX_F32)
+        pmx_k_cohmix<float2><<<g, 256, 0, c->stream>>>(reinterpret_cast<float2*>(f->data), N, f->log2N1, f->log2N2, lo_ecw,
+                                                         lo_detune, dph, balanced ? 1 : 0);
+    else
+        pmx_k_cohmix<double2><<<g, 256, 0, c->stream>>>(reinterpret_cast<double2*>(f->data), N, f->log2N1, f->log2N2, lo_ecw,
+                                                          lo_detune, dph, balanced ? 1 : 0);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (dph) {
+        cudaFreeAsync(dph, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // lo_phase is the caller's pageable memory
+    }
+    CK(c, e);
     return PMX_OK;
 }
 

@@ -143,6 +143,8 @@ struct PassParams {
     const void* tw_stage;   // cpx: in-CTA FFT stage twiddles for this L
     const double* betat_p;  // [nfc][N1][N2] permuted so that bin k1 + N1*k2 sits at k1*N2 + k2
     const double* db1_p;    // same layout
+    const double2* hfilt;   // linear-filter plans (pmx_filter_create): the per-bin factor H, same layout; else null
+    long long hfilt_stride; // N when every column has its own H, 0 when they share one
     const PlateConst* plates;  // [plate_sets][nplates]
     StepPkg* pkg;           // [batch]
     const void* tw4;        // cpx: four-step twiddle rows for this pass: [rows][PmxTw4<L>::PER], see pmx_kernels.cuh

@@ -782,6 +782,19 @@ __device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const 
     (void)scr_stride;
     (void)fn0;
     (void)dfn;
+    if constexpr (!SC) {
+        if (p.hfilt) {   // a linear filter: u(k) <- H(k) * u(k) from the plan's table, the product taken in double
+            const double2* h = p.hfilt + (size_t)col * (size_t)p.hfilt_stride + (size_t)k1 * p.N2;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double2 e = __ldg(&h[t + q * T]);
+                const double xr = x[q].x, xi = x[q].y, yr = y[q].x, yi = y[q].y;
+                x[q] = mkc((real)(xr * e.x - xi * e.y), (real)(xr * e.y + xi * e.x));
+                y[q] = mkc((real)(yr * e.x - yi * e.y), (real)(yr * e.y + yi * e.x));
+            }
+            return;
+        }
+    }
         const double dz_cur = st->dz_cur;
         // scalar phase common to both polarizations collected over the trunks: conj(Bacc) * conj(Gacc)^j
         dcpx Bacc = dmk(1.0, 0.0), Gacc = dmk(1.0, 0.0);
