@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 
 DEFAULTS = dict(applypol=True, taps=7, mu=1 / 6000, R=(1.0, 1.0), phizero=0.0, max_passes=0, modorder=2, freqavg=500,
-                phasavg=3, poworder=2)
+                phasavg=3, poworder=2, sample_shift=0, peak=0.0)
 
 
 def reference_pattern(sym_x, sym_y):
@@ -32,7 +32,8 @@ def reference_pattern(sym_x, sym_y):
 
 
 def dsp_count(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, ref_patmat, counts_dev_ptr: int, **params):
-    """Error counts of every realization of `field` (CD already compensated) into a device int64 buffer.
+    """Error counts of every realization of `field` (CD already compensated) into a device int64 buffer.  sample_shift /
+    peak: the receiver's currents are sampled at k*nt + sample_shift and divided by peak (0: unit mean power).
     -> passes the polarization demultiplexer ran, per realization."""
     p = dict(DEFAULTS)
     p.update(params)
@@ -40,6 +41,7 @@ def dsp_count(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, r
     d.nsymb, d.nt, d.apply_cma, d.taps, d.mu = int(nsymb), int(nt), int(bool(p['applypol'])), int(p['taps']), float(p['mu'])
     d.R[0], d.R[1], d.phizero, d.max_passes = float(p['R'][0]), float(p['R'][1]), float(p['phizero']), int(p['max_passes'])
     d.modorder, d.freqavg, d.phasavg, d.poworder = int(p['modorder']), int(p['freqavg']), int(p['phasavg']), int(p['poworder'])
+    d.sample_shift, d.peak = int(p['sample_shift']), float(p['peak'])
     ref = np.ascontiguousarray(ref_patmat, dtype=np.uint8).reshape(nsymb, 4)
     passes = np.zeros(field.batch, dtype=np.int32)
     ctx.check(ctx.lib.pmx_dsp_count(ctx.h, field.h, C.byref(d), ref.ctypes.data_as(C.POINTER(C.c_uint8)),

@@ -196,14 +196,32 @@ class McRunner:
 
     def __init__(self, ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int,
                  gain_db: float, nf_db: float, nreal: int, batch: int, rank: int = 0, world: int = 1,
-                 receiver: str = 'genie', dsp_params=None):
+                 receiver: str = 'genie', dsp_params=None, rx_params=None, ich: int = 1):
         """receiver: 'genie' -- ideal linear equaliser from the known plates + data-aided decision (pmx_qpsk_count);
         'blind' -- chromatic dispersion compensated, then the DSP core of dsp4cohdec (CMA polarization demultiplexer,
-        Viterbi & Viterbi carrier recovery, differential decision: pmx_dsp_count, polmux_b200/dsp.py)"""
+        Viterbi & Viterbi carrier recovery, differential decision: pmx_dsp_count, polmux_b200/dsp.py);
+        'cohmix' -- chromatic dispersion compensated, the front-end of receiver_cohmix.m for channel `ich` (optical
+        filter, LO mixing, photodiodes, low-pass filter; rx_params = its x struct, polmux_b200/receiver.py), the
+        currents sampled at the symbol centres delayed by the filters' 'theory' delay (dsp4cohdec.m:490-503) and
+        divided by 4*sqrt(POWER(ich)) (dsp4cohdec.m:226-227), then the same DSP core"""
         import torch
         from . import dsp as _dsp
         self.receiver, self.dsp_params = receiver, dict(dsp_params or {})
-        self.ref_patmat = _dsp.reference_pattern(np.asarray(sym)[0], np.asarray(sym)[1]) if receiver == 'blind' else None
+        if receiver not in ('genie', 'blind', 'cohmix'):
+            raise ValueError("receiver must be 'genie', 'blind' or 'cohmix'")
+        self.ref_patmat = _dsp.reference_pattern(np.asarray(sym)[0], np.asarray(sym)[1]) if receiver != 'genie' else None
+        self.rx = None
+        if receiver == 'cohmix':
+            from . import receiver as _rx
+            from .gstate import GSTATE
+            x = dict(rx_params or {'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65})   # ex20_coherent_polmux.m:47-50
+            S = _rx.CohmixSetup(ich, x, GSTATE, nfc=setup.nfc)
+            delay = _rx.evaldelay(x['oftype'], x['obw'] * 0.5) + _rx.evaldelay(x['eftype'], x['ebw']) + S.x['post_delay']
+            self.rx = dict(S=S, ich=ich, shift=int(round(delay * nt)),
+                           peak=4.0 * math.sqrt(float(np.asarray(GSTATE.POWER).ravel()[ich - 1])),
+                           fo=_lib.Filter(ctx, setup.nfft, 1, S.hf_opt, batch=batch),
+                           fe=_lib.Filter(ctx, setup.nfft, 1, _rx.hermitian_part(S.hf_el), batch=batch),
+                           col=_lib.DeviceField(ctx, setup.nfft, 1, batch) if setup.nfc > 1 else None)
         self.passes = []
         self.ctx, self.setup, self.sym, self.nsymb, self.nt = ctx, setup, sym, nsymb, nt
         self.nreal, self.batch, self.rank, self.world = nreal, batch, rank, world
@@ -232,6 +250,22 @@ class McRunner:
                 self.link.cd_compensate(self.work)
                 self.passes.append(_dsp.dsp_count(self.ctx, self.work, self.nsymb, self.nt, self.ref_patmat,
                                                   self.buf.data_ptr(), **self.dsp_params))
+            elif self.receiver == 'cohmix':
+                from . import dsp as _dsp
+                R, S = self.rx, self.rx['S']
+                self.link.cd_compensate(self.work)
+                cur = self.work
+                if R['col'] is not None:                            # the channel's column of every realization
+                    cur = R['col']
+                    for b in range(self.batch):
+                        _lib.field_copy_cols(cur, b, self.work, b * self.setup.nfc + S.nch - 1, 1)
+                if S.ndfn:
+                    _lib.field_modulate(self.ctx, cur, S.ndfn)
+                R['fo'].execute(cur)
+                _lib.cohmix_exec(self.ctx, cur, S.ecw, S.detune, S.lophase, S.balanced)
+                R['fe'].execute(cur)
+                self.passes.append(_dsp.dsp_count(self.ctx, cur, self.nsymb, self.nt, self.ref_patmat, self.buf.data_ptr(),
+                                                  sample_shift=R['shift'], peak=R['peak'], **self.dsp_params))
             else:
                 self.link.equalize(self.work)
                 _lib.qpsk_count(self.ctx, self.work, self.sym, self.nsymb, self.nt, self.buf.data_ptr())   # writes the send buffer
@@ -243,6 +277,10 @@ class McRunner:
     def close(self):
         for f in (self.work, self.tx):
             f.close()
+        if self.rx:
+            for k in ('fo', 'fe', 'col'):
+                if self.rx[k] is not None:
+                    self.rx[k].close()
 
 
 def run_mc(ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int, gain_db: float,

@@ -28,6 +28,7 @@ def _received_field(nsymb, nt, nf_db, seed, dgd=0.3, length=4e4, batch=2):
     fld = _lib.DeviceField(ctx, n, 1, batch)
     xs, ys = [], []
     for b in range(batch):
+        G.POWER = np.array([1.0])          # (create_field rewrites POWER: every realization starts from the same one)
         pmx.create_field('unique', ex, ey, {'power': 'average'})
         G.DELAY, G.DISP = np.zeros((2, 1)), np.zeros((2, 1))
         pmx.fiber(base_fiber(length=length, dgd=dgd, nplates=20, manakov='yes'), 'gps-',
@@ -80,4 +81,56 @@ def test_dsp_count_without_polarization_demultiplexer_and_argument_checks():
     assert int(counts[0]) == dsp_orc.count_errors_dqpsk(dsp_orc.carrier_recovery(s, 2, 100, 3, 2), tx_phase)
     with pytest.raises(_lib.PolmuxError):
         dsp.dsp_count(ctx, fld, nsymb, nt, ref, counts.data_ptr(), taps=4)
+    fld.close()
+
+
+@pytest.mark.parametrize('nf_db', [5.0, 38.0])
+def test_receiver_front_end_plus_dsp_chain_matches_the_oracles(nf_db):
+    """the whole receive chain of McRunner(receiver='cohmix') on the device -- optical filter, LO (detuned, with phase
+    noise), photodiodes, low-pass filter, sampling at the delayed symbol centres, /peak, CMA, Viterbi & Viterbi, decision --
+    against oracle/receiver_oracle.py followed by oracle/dsp_oracle.py on the same received fields: equal error counts"""
+    import torch
+    import oracle.receiver_oracle as rxo
+    from polmux_b200 import receiver as rx
+    nsymb, nt, batch = 1 << 11, 16, 2
+    ctx, fld, hx, hy, sx, sy = _received_field(nsymb, nt, nf_db, seed=70, batch=batch)
+    n = nsymb * nt
+    G = pmx.GSTATE
+    pn = np.cumsum(2e-3 * np.random.Generator(np.random.PCG64(4)).standard_normal(n))
+    x = {'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65, 'lopower': 0.0, 'lodetuning': 4.0e7,
+         'lophasenoise': pn - np.arange(n) / (n - 1) * pn[-1]}
+    S = rx.CohmixSetup(1, x, G, nfc=1)
+    shift = int(round((rx.evaldelay('gauss', 0.95) + rx.evaldelay('bessel5', 0.65)) * nt))
+    peak = 4.0 * math.sqrt(float(G.POWER[0]))
+    assert shift == round(0.3863 / 0.65 * nt)
+    fo = _lib.Filter(ctx, n, 1, S.hf_opt, batch=batch)
+    fe = _lib.Filter(ctx, n, 1, rx.hermitian_part(S.hf_el), batch=batch)
+    fo.execute(fld)
+    _lib.cohmix_exec(ctx, fld, S.ecw, S.detune, S.lophase, S.balanced)
+    fe.execute(fld)
+    params = dict(taps=7, mu=1 / 2000, freqavg=200, phasavg=3, poworder=2)
+    ref = dsp.reference_pattern(sx, sy)
+    counts = torch.zeros(batch, dtype=torch.int64, device='cuda')
+    passes = dsp.dsp_count(ctx, fld, nsymb, nt, ref, counts.data_ptr(), sample_shift=shift, peak=peak, **params)
+    got = counts.cpu().numpy()
+    tx_phase = np.stack([np.angle((2.0 * (s & 1) - 1) + 1j * (2.0 * ((s >> 1) & 1) - 1)) for s in (sx, sy)], axis=1)
+
+    class GS:
+        pass
+    for b in range(batch):
+        gs = GS()
+        for k in ('FN', 'LAMBDA', 'SYMBOLRATE', 'NSYMB', 'NT', 'NCH', 'POWER'):
+            setattr(gs, k, getattr(G, k))
+        gs.FIELDX, gs.FIELDY = hx[b][:, None], hy[b][:, None]
+        iric, _ = rxo.receiver_cohmix(gs, 1, x)
+        idx = (np.arange(nsymb) * nt + shift) % n
+        s = np.stack([iric[idx, 0] + 1j * iric[idx, 1], iric[idx, 2] + 1j * iric[idx, 3]], axis=1) / peak
+        y, npass = dsp_orc.cma_polar_demux(s, mu=params['mu'], taps=params['taps'])
+        ph = dsp_orc.carrier_recovery(y, 2, params['freqavg'], params['phasavg'], params['poworder'])
+        want = dsp_orc.count_errors_dqpsk(ph, tx_phase)
+        assert int(passes[b]) == npass
+        assert int(got[b]) == want
+        assert (want > 0) == (nf_db > 20)
+    fo.close()
+    fe.close()
     fld.close()

@@ -230,12 +230,14 @@ def test_mc_with_the_blind_receiver(ctx):
     setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
     sym = np.stack([sx[:, 0], sy[:, 0]]).astype(np.uint8)
     out = {}
-    for rec in ('genie', 'blind'):
+    for rec in ('genie', 'blind', 'cohmix'):
         r = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 8.0, 5.0, nreal, batch, receiver=rec,
                         dsp_params=dict(mu=1 / 2000, freqavg=200))
         out[rec], _ = r.run(ase_seed=9)
-        if rec == 'blind':
+        if rec != 'genie':
             assert len(r.passes) == nreal // batch and all(p.min() >= 1 for p in r.passes)
         r.close()
     assert out['genie'].sum() == 0
     assert out['blind'].sum() <= 8          # differential decoding doubles isolated errors; none expected here
+    # the full front-end of receiver_cohmix (gauss 1.9 / bessel5 0.65, ex20_coherent_polmux.m:47-50) in front of the same DSP
+    assert out['cohmix'].sum() <= 8
