@@ -395,6 +395,25 @@ int pmx_filter_create(pmx_ctx* ctx, int64_t nfft, int32_t nfc, int32_t batch, in
 int pmx_field_copy_cols(pmx_devfield* dst, int32_t dst_bc, const pmx_devfield* src, int32_t src_bc, int32_t count);
 int pmx_field_modulate(pmx_ctx* ctx, pmx_devfield* f, int64_t m);
 int pmx_cohmix_exec(pmx_ctx* ctx, pmx_devfield* f, double lo_ecw, double lo_detune, const double* lo_phase, int32_t balanced);
+/* The same on host buffers in one call (what the MEX gateway binds for matlab/receiver_cohmix.m): sig = the channel's
+ * column(s) x.sigx / x.sigy in time, one realization; iric: [nfft][2 or 4] column-major, as receiver_cohmix returns it;
+ * avgeb (may be NULL): [2] = sum |X(band)|^2 / Nfft^2 of the two polarizations (x.avgebx, x.avgeby before the division by
+ * GSTATE.POWER).  hf_el is myfilter(x.eftype, ...) as the reference builds it (its Hermitian part is taken inside). */
+typedef struct pmx_cohmix_desc {
+    int64_t nfft;
+    int32_t precision;       /* pmx_precision of the device arithmetic */
+    int32_t two_pol;         /* ~isempty(GSTATE.FIELDY) */
+    int32_t balanced;        /* ~strcmp(x.pdtype,'normal') (:264-268) */
+    int32_t reserved;
+    int64_t ndfn;            /* spectrum shift in bins (:87-89); 0 for separate channels */
+    int64_t ndfnl, ndfnr;    /* the channel's band for avgeb (:90-110) */
+    const double* hf_opt;    /* [nfft] complex: fastexp(-betat) .* myfilter(x.oftype,...) (:166-169) */
+    const double* hf_el;     /* [nfft] complex: myfilter(x.eftype,...) (:293) */
+    double lo_ecw;           /* LO_Ecw (:215-219) */
+    double lo_detune;        /* 2*pi*kdet/Nfft (:187-200) */
+    const double* lo_phase;  /* [nfft] LO_PhaseNoise or NULL (:201-214) */
+} pmx_cohmix_desc;
+int pmx_cohmix_run(pmx_ctx* ctx, const pmx_cohmix_desc* d, const pmx_field* sig, double* iric, double* avgeb);
 
 /* ---- inverse_pmd.m: the PMD matrix of a chain of fibers, and a constant Jones matrix on the field -------------------
  * One fiber of the chain as fiber() returns it in its brf struct (inverse_pmd.m:9-17). */

@@ -587,6 +587,85 @@ static void cmd_ampliflat(int nlhs, mxArray *plhs[], int nrhs, const mxArray *pr
     release(f, nfft, nfc, precision, 1, resident, nlhs, plhs);
 }
 
+/* complex mxArray (split storage) -> interleaved re,im in a fresh mxArray-owned buffer of 2*n doubles */
+static double *interleave(const mxArray *a, size_t n, mxArray **owner)
+{
+    const double *re = mxGetPr(a), *im = mxGetPi(a);
+    double *out;
+    size_t k;
+    *owner = mxCreateDoubleMatrix(2 * n, 1, mxREAL);
+    out = mxGetPr(*owner);
+    for (k = 0; k < n; k++) {
+        out[2 * k] = re[k];
+        out[2 * k + 1] = im ? im[k] : 0.0;
+    }
+    return out;
+}
+
+static void cmd_cohmix(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+{
+    /* [Iric,avgeb] = ssfm_mex('cohmix', sigx, sigy, Hopt, Hel, lo, lophase, band, opt)
+     *   sigx, sigy : the channel's column of GSTATE.FIELDX / FIELDY (sigy empty: one polarization)
+     *   Hopt, Hel  : Nfft x 1 filter responses over GSTATE.FN (receiver_cohmix.m:169,293)
+     *   lo         : [LO_Ecw, 2*pi*kdet/Nfft, balanced]      lophase : Nfft x 1 or []
+     *   band       : [ndfn, ndfnl, ndfnr]                     opt     : [0, precision] */
+    pmx_cohmix_desc d;
+    pmx_field sig;
+    mxArray *o1 = NULL, *o2 = NULL;
+    const mxArray *opt = nrhs > 8 ? prhs[8] : NULL;
+    size_t nfft;
+    double avgeb[2] = {0.0, 0.0};
+    int rc, two;
+
+    if (nrhs < 8 || nrhs > 9 || nlhs > 2)
+        mexErrMsgTxt("[Iric,avgeb] = ssfm_mex('cohmix',sigx,sigy,Hopt,Hel,lo,lophase,band[,opt]): wrong number of arguments.");
+    nfft = mxGetNumberOfElements(prhs[1]);
+    two = mxGetNumberOfElements(prhs[2]) == nfft;
+    if (nfft == 0 || (!two && mxGetNumberOfElements(prhs[2]) != 0))
+        mexErrMsgTxt("ssfm_mex: sigx must be a column of Nfft samples and sigy the same, or empty.");
+    if (mxGetNumberOfElements(prhs[3]) != nfft || mxGetNumberOfElements(prhs[4]) != nfft)
+        mexErrMsgTxt("ssfm_mex: the filter responses must have Nfft elements.");
+    if (mxGetNumberOfElements(prhs[5]) != 3 || mxGetNumberOfElements(prhs[7]) != 3)
+        mexErrMsgTxt("ssfm_mex: lo = [Ecw, detuning, balanced], band = [ndfn, ndfnl, ndfnr].");
+    if (mxGetNumberOfElements(prhs[6]) != 0 && mxGetNumberOfElements(prhs[6]) != nfft)
+        mexErrMsgTxt("Incompatible vector."); /* receiver_cohmix.m:204 */
+    memset(&d, 0, sizeof d);
+    d.nfft = (int64_t)nfft;
+    d.precision = opt_at(opt, 1, 0.0) != 0.0 ? PMX_F32 : PMX_F64;
+    d.two_pol = two;
+    d.hf_opt = interleave(prhs[3], nfft, &o1);
+    d.hf_el = interleave(prhs[4], nfft, &o2);
+    d.lo_ecw = mxGetPr(prhs[5])[0];
+    d.lo_detune = mxGetPr(prhs[5])[1];
+    d.balanced = mxGetPr(prhs[5])[2] != 0.0;
+    d.lo_phase = mxGetNumberOfElements(prhs[6]) ? mxGetPr(prhs[6]) : NULL;
+    d.ndfn = (int64_t)mxGetPr(prhs[7])[0];
+    d.ndfnl = (int64_t)mxGetPr(prhs[7])[1];
+    d.ndfnr = (int64_t)mxGetPr(prhs[7])[2];
+    memset(&sig, 0, sizeof sig);
+    sig.layout = PMX_PLANAR;
+    sig.xr = mxGetPr(prhs[1]);
+    sig.xi = mxGetPi(prhs[1]);
+    if (two) {
+        sig.yr = mxGetPr(prhs[2]);
+        sig.yi = mxGetPi(prhs[2]);
+    }
+    plhs[0] = mxCreateDoubleMatrix(nfft, two ? 4 : 2, mxREAL);
+    ensure_ctx();
+    rc = pmx_cohmix_run(g_ctx, &d, &sig, mxGetPr(plhs[0]), nlhs > 1 ? avgeb : NULL);
+    mxDestroyArray(o1);
+    mxDestroyArray(o2);
+    if (rc != PMX_OK)
+        fail("ssfm_mex: cohmix failed");
+    if (nlhs > 1) {
+        plhs[1] = mxCreateDoubleMatrix(1, 2, mxREAL);
+        mxGetPr(plhs[1])[0] = avgeb[0];
+        mxGetPr(plhs[1])[1] = avgeb[1];
+    }
+    g_stats[0] += 1.0; /* one upload of the column, one download of the currents */
+    g_stats[1] += 1.0;
+}
+
 static void command(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 {
     char cmd[32];
@@ -596,12 +675,14 @@ static void command(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         cmd_fiber(nlhs, plhs, nrhs, prhs);
     } else if (!strcmp(cmd, "ampliflat")) {
         cmd_ampliflat(nlhs, plhs, nrhs, prhs);
+    } else if (!strcmp(cmd, "cohmix")) {
+        cmd_cohmix(nlhs, plhs, nrhs, prhs);
     } else if (!strcmp(cmd, "reset")) {
         drop_resident();
     } else if (!strcmp(cmd, "stats")) {
         plhs[0] = mxCreateDoubleMatrix(1, 3, mxREAL);
         memcpy(mxGetPr(plhs[0]), g_stats, sizeof g_stats);
     } else {
-        mexErrMsgTxt("ssfm_mex: unknown command (fiber, ampliflat, reset, stats).");
+        mexErrMsgTxt("ssfm_mex: unknown command (fiber, ampliflat, cohmix, reset, stats).");
     }
 }

@@ -2528,6 +2528,73 @@ extern "C" int pmx_cohmix_exec(pmx_ctx* c, pmx_devfield* f, double lo_ecw, doubl
     return PMX_OK;
 }
 
+// The whole sample work of receiver_cohmix.m on host buffers, for callers that are not the Python mirror (the MEX gateway)
+extern "C" int pmx_cohmix_run(pmx_ctx* c, const pmx_cohmix_desc* d, const pmx_field* sig, double* iric, double* avgeb) {
+    if (!c || !d || !sig || !iric) return set_err(c, PMX_ERR_INVALID, "pmx_cohmix_run: null argument");
+    if (!d->hf_opt || !d->hf_el) return set_err(c, PMX_ERR_INVALID, "pmx_cohmix_run: both filter responses are required");
+    const size_t N = (size_t)d->nfft;
+    pmx_devfield *f = nullptr, *tmp = nullptr;
+    pmx_plan *fo = nullptr, *fe = nullptr, *fb = nullptr;
+    int rc = pmx_field_create(c, d->nfft, 1, 1, d->precision, &f);
+    if (rc == PMX_OK) rc = pmx_field_upload(f, sig, 0, 1);
+    if (rc == PMX_OK && d->ndfn) rc = pmx_field_modulate(c, f, d->ndfn);
+    if (rc == PMX_OK && avgeb) {   // energy of the channel's band before the optical filter (receiver_cohmix.m:174-175,233-234)
+        const bool all = d->ndfnl + d->ndfnr >= d->nfft;
+        pmx_devfield* src = f;
+        if (!all) {
+            std::vector<double> band(2 * N, 0.0);
+            for (size_t k = 0; k < N; ++k)
+                if ((int64_t)k < d->ndfnl || (int64_t)k >= d->nfft - d->ndfnr) band[2 * k] = 1.0;
+            rc = pmx_field_create(c, d->nfft, 1, 1, d->precision, &tmp);
+            if (rc == PMX_OK) rc = pmx_field_copy_cols(tmp, 0, f, 0, 1);
+            if (rc == PMX_OK) rc = pmx_filter_create(c, d->nfft, 1, 1, d->precision, band.data(), 1, &fb);
+            if (rc == PMX_OK) rc = pmx_fiber_exec(fb, tmp, nullptr);
+            src = tmp;
+        }
+        if (rc == PMX_OK) rc = pmx_field_mean_power_xy(c, src, &avgeb[0], &avgeb[1]);
+    }
+    if (rc == PMX_OK) rc = pmx_filter_create(c, d->nfft, 1, 1, d->precision, d->hf_opt, 1, &fo);
+    if (rc == PMX_OK) rc = pmx_fiber_exec(fo, f, nullptr);
+    if (rc == PMX_OK) rc = pmx_cohmix_exec(c, f, d->lo_ecw, d->lo_detune, d->lo_phase, d->balanced);
+    if (rc == PMX_OK) {
+        // real(ifft(fft(I) .* H)) of a real I is ifft(fft(I) .* Hh), Hh(k) = (H(k) + conj(H(-k)))/2: the two currents of a
+        // polarization ride one complex transform
+        std::vector<double> hh(2 * N);
+        for (size_t k = 0; k < N; ++k) {
+            const size_t m = (N - k) & (N - 1);
+            hh[2 * k] = 0.5 * (d->hf_el[2 * k] + d->hf_el[2 * m]);
+            hh[2 * k + 1] = 0.5 * (d->hf_el[2 * k + 1] - d->hf_el[2 * m + 1]);
+        }
+        rc = pmx_filter_create(c, d->nfft, 1, 1, d->precision, hh.data(), 1, &fe);
+    }
+    if (rc == PMX_OK) rc = pmx_fiber_exec(fe, f, nullptr);
+    if (rc == PMX_OK) {   // Iric = [I_x Q_x I_y Q_y], column-major: the planar download
+        pmx_field out;
+        memset(&out, 0, sizeof out);
+        out.layout = PMX_PLANAR;
+        out.xr = iric;
+        out.xi = iric + N;
+        std::vector<double> scratch;
+        if (d->two_pol) {
+            out.yr = iric + 2 * N;
+            out.yi = iric + 3 * N;
+        } else {
+            scratch.resize(2 * N);
+            out.yr = scratch.data();
+            out.yi = scratch.data() + N;
+        }
+        rc = pmx_field_download(f, &out, 0, 1);
+    }
+    std::string keep = c->error;
+    pmx_plan_destroy(fo);
+    pmx_plan_destroy(fe);
+    pmx_plan_destroy(fb);
+    pmx_field_destroy(f);
+    pmx_field_destroy(tmp);
+    if (rc != PMX_OK) c->error = keep;
+    return rc;
+}
+
 // ---------------------------------------------------------------------------
 // Local-error adaptive step on the scalar path: scalar_a_ssfm / adaptssfm (fiber.m:639-679, 938-1010) and the
 // x.dphiadapt variant of scalar_ssfm (fiber.m:588-611).  The accept/reject logic is host code as in the reference;

@@ -134,6 +134,27 @@ def oracle_gateway(log=None):
             elif np.any(sg):
                 raise NotImplementedError('the oracle-backed gateway takes injected noise only')
             return [ox, oy][:max(nargout, 1)]
+        if cmd == 'cohmix':    # [Iric,avgeb] = ssfm_mex('cohmix', sigx, sigy, Hopt, Hel, lo, lophase, band, opt)
+            sigx, sigy, hopt, hel, lo, lophase, band = a[1:8]
+            n = np.size(sigx)
+            ecw, det, balanced = [float(v) for v in np.asarray(lo).ravel()]
+            ndfn, ndfnl, ndfnr = [int(v) for v in np.asarray(band).ravel()]
+            nind = np.mod(np.arange(1, n + 1) - ndfn - 1, n)
+            elo = ecw * np.exp(1j * (det * np.arange(1, n + 1) + (np.asarray(lophase).ravel() if np.size(lophase) else 0.0)))
+            hopt, hel = np.asarray(hopt).ravel(), np.asarray(hel).ravel()
+            cols, avg = [], []
+            for sg in (sigx, sigy):
+                if not np.size(sg):
+                    avg.append(0.0)
+                    continue
+                sp = np.fft.fft(np.asarray(sg).ravel())[nind]
+                avg.append((np.sum(np.abs(sp[:ndfnl]) ** 2) + np.sum(np.abs(sp[n - ndfnr:]) ** 2)) / n ** 2)
+                t = np.fft.ifft(sp * hopt)
+                e = [1j * t + 1j * elo, t - elo, 1j * t - elo, -t + 1j * elo]
+                i = [np.real(v * np.conj(v)) for v in e]
+                pair = [i[0] - i[1], i[2] - i[3]] if balanced else [i[0], i[2]]
+                cols += [np.real(np.fft.ifft(np.fft.fft(c) * hel)) for c in pair]
+            return [np.stack(cols, axis=1), np.array([avg])][:max(nargout, 1)]
         if cmd != 'fiber':
             raise NotImplementedError(cmd)
         ux, uy, betat, db1, P, gam, fls, plates, scal = a[1:10]

@@ -198,6 +198,56 @@ def test_script_call_sequences_run_unchanged(script):
     np.testing.assert_allclose(b[3], a[3], rtol=1e-13, atol=1e-13)
 
 
+# ---- matlab/receiver_cohmix.m
+RXGOLD = os.path.join(GOLD, 'rx')
+RXCASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(RXGOLD, 'rx_*.npz')))
+
+
+def _rx_case(name):
+    z = np.load(os.path.join(RXGOLD, name + '.npz'))
+    m = json.loads(str(z['meta']))
+    x = dict(m['x'])
+    if x.get('lophasenoise') == 'PN':
+        x['lophasenoise'] = z['lophasenoise'].reshape(-1, 1)
+    return z, m, MStruct({k: (v if isinstance(v, str) else to_m(v)) for k, v in x.items()})
+
+
+def _rx_globals(it, z, m):
+    globals_from_python(it, m['nsymb'], m['nt'], m['nch'], m['rate'], m['pavg'], z['FIELDX'],
+                        z['FIELDY'] if z['FIELDY'].size else None)
+    G = it.globals['GSTATE']
+    G['POWER'] = z['POWER'].reshape(1, -1)
+    G['FIELDX_TX'] = np.array(z['FIELDX_TX'])
+    G['FIELDY_TX'] = np.array(z['FIELDY_TX']) if z['FIELDY_TX'].size else np.zeros((0, 0))
+
+
+def _rx_check(it, z, m, x, tol):
+    before = np.array(it.globals['GSTATE']['FIELDX'])
+    iric, xo = it.call('receiver_cohmix', [to_m(float(m['ich'])), x], 2)
+    assert np.shape(iric) == z['Iric'].shape
+    assert np.linalg.norm(np.asarray(iric) - z['Iric']) <= tol * np.linalg.norm(z['Iric'])
+    assert abs(float(np.asarray(xo['avgebx']).ravel()[0]) / float(z['avgebx'][0]) - 1) < tol
+    if z['avgeby'].size:
+        assert abs(float(np.asarray(xo['avgeby']).ravel()[0]) / float(z['avgeby'][0]) - 1) < tol
+    pd = float(np.asarray(xo['post_delay'], dtype=np.float64).ravel()[0])
+    assert abs(pd - float(z['post_delay'][0])) <= 1e-13 * max(1.0, abs(pd))
+    assert np.array_equal(np.asarray(it.globals['GSTATE']['FIELDX']), before)      # GSTATE is left unchanged
+    one = it.call('receiver_cohmix', [to_m(float(m['ich'])), x], 1)[0]
+    assert np.array_equal(np.asarray(one), np.asarray(iric))
+
+
+@needs_ref
+@pytest.mark.parametrize('name', RXCASES)
+def test_receiver_front_end_reproduces_the_interpreted_original(name):
+    """matlab/receiver_cohmix.m (first on the path) + the toolbox's myfilter.m / fastexp.m + an oracle-backed ssfm_mex
+    == the interpreted original receiver_cohmix.m: currents, avgebx / avgeby, post_delay"""
+    z, m, x = _rx_case(name)
+    it = Interp([MDIR, REF])
+    it.builtins['ssfm_mex'] = mex_bridge.oracle_gateway()
+    _rx_globals(it, z, m)
+    _rx_check(it, z, m, x, 1e-13)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _gpu_interp(seed):
     it = Interp([MDIR], rng=np.random.Generator(np.random.PCG64(seed)))
@@ -243,6 +293,22 @@ def test_interpreted_front_end_on_the_device(name):
         it.call('ampliflat', [to_m(m['amp']['gain']), m['amp'].get('atype', 'gain'), opt], 0)
         G = it.globals['GSTATE']
         assert orc.rel_l2(G['FIELDX'], G['FIELDY'], z['amp_FIELDX'], z['amp_FIELDY']) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', RXCASES)
+def test_interpreted_receiver_front_end_on_the_device(name):
+    """matlab/receiver_cohmix.m interpreted, its ssfm_mex('cohmix', ...) the compiled gateway on the GPU (pmx_cohmix_run),
+    against the interpreted original's goldens, FP64 <= 1e-10.  myfilter.m / fastexp.m belong to the toolbox, which is
+    not on the GPU box: the test stands in for them with the oracle's restatement (pinned by test_receiver_oracle)."""
+    import oracle.receiver_oracle as rxo
+    z, m, x = _rx_case(name)
+    it, gw = _gpu_interp(0)
+    it.builtins['myfilter'] = lambda it_, a, nargout: [rxo.myfilter(a[0], np.asarray(a[1]), float(np.asarray(a[2]).ravel()[0]),
+                                                                   float(np.asarray(a[3]).ravel()[0]) if len(a) > 3 else 0).reshape(-1, 1)]
+    it.builtins['fastexp'] = lambda it_, a, nargout: [np.cos(np.asarray(a[0])) + 1j * np.sin(np.asarray(a[0]))]
+    _rx_globals(it, z, m)
+    _rx_check(it, z, m, x, 1e-10)
 
 
 @pytest.mark.gpu
