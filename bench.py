@@ -58,6 +58,10 @@ CPU_SAMPLE_KM = SPAN_KM         # bounded CPU sample: span 1 of the link in full
 FLOPS_PER_SA_TRUNK = 32.0
 FP64_INSTR_PER_SA_TRUNK = 20.0
 FP64_FMA_PER_CLK_SM = 64.0      # measured: tools/ubench/fp64_rate.cu, 63.9 DFMA/clk/SM on this B200
+# FP64 instructions (DFMA + DADD + DMUL) per Sa of a launch, from the same ncu capture: sm__pipe_fp64_cycles_active x 2 warp
+# instructions per active cycle and SM x 32 threads / (Sa per SM); pass B also counted instruction by instruction on the
+# source page (214.6).  The FP64-pipe floor of a pass = this / (64 per clock and SM x 148 SMs x SM clock).
+NCU_FP64_INSTR_PER_SA = {'passA': 94.9, 'passB': 214.6, 'passC': 82.8}
 
 
 def fiber_params(length_m, nplates):
@@ -535,6 +539,15 @@ def main():
 
     if rank == 0:
         sampler.join(timeout=2)
+        clk = sampler.summary()
+        if roof and clk.get('sm_mhz'):
+            # the second ceiling of the dominant pass on this part: 64 FP64 instructions per clock and SM
+            fl = NCU_FP64_INSTR_PER_SA[roof['kernel']] / (FP64_FMA_PER_CLK_SM * 148 * clk['sm_mhz'] * 1e6)   # s per Sa
+            t_sa = 64.0 / (roof['achieved'] * 1e9)
+            roof['fp64_pipe'] = {'instr_per_sa': NCU_FP64_INSTR_PER_SA[roof['kernel']], 'floor_ps_per_sa': fl * 1e12,
+                                 'hbm_floor_ps_per_sa': 64.0 / (roof['peak'] * 1e9) * 1e12, 'measured_ps_per_sa': t_sa * 1e12,
+                                 'frac_of_fp64_floor': fl / t_sa,
+                                 'note': 'FP64 pipe floor at the SM clock sampled during the run; above the HBM floor for pass B'}
         line = {'metric': 'ssfm_gsa_steps_per_s', 'value': value, 'unit': 'GSa*steps/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / max(args.steps, 1),
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
