@@ -10,10 +10,11 @@ larger than the 126 MB L2.
 
   value  Sum(N * ncycle) / time, fields resident in HBM, timed with CUDA events on the
          library's stream, max over ranks
-  e2e    the same metric through the reference-facing calls on HOST buffers (pinned): GSTATE.FIELDX/Y
-         assigned from host arrays, fiber(x,'gps-') + ampliflat() per span, GSTATE.FIELDX/Y read back --
-         H2D of the Tx field and D2H of the Rx field inside every step (e2e_per_call: H2D and D2H inside
-         every fiber()/ampliflat() call)
+  e2e    the same step (the batch of realizations, ten spans) through the C-ABI call pmx_link_run on HOST buffers
+         (pinned): plan and device field created, H2D of every realization's field, the spans, D2H, all inside
+         the timed call.  e2e.script_flow: one realization through the reference's own script calls --
+         GSTATE.FIELDX/Y assigned from host arrays, fiber(x,'gps-') + ampliflat() per span, GSTATE.FIELDX/Y
+         read back (e2e_per_call: H2D and D2H inside every fiber()/ampliflat() call)
   roofline      dominant pass kernel: 64 algorithmic bytes per live Sa and step / its device time
                 (CUDA events around every launch of one extra, profiled link pass)
   mc            Monte-Carlo BER leg (BASELINE config C5): --mc-realizations (default 1024) realizations of the C2 link
@@ -515,10 +516,61 @@ def main():
 
         per_field = N * 32
         ne2e = max(2, args.steps)
-        e2e = {'value': e2e_leg(True, ne2e), 'unit': 'GSa*steps/s',
-               'h2d_bytes_per_step': per_field, 'd2h_bytes_per_step': per_field,
-               'api': "GSTATE.FIELDX/Y <- pinned host field; 10 x [fiber(x,'gps-'); ampliflat(G,'gain',opt)]; read "
-                      "GSTATE.FIELDX/Y (field resident in HBM between the calls), 1 realization per rank"}
+        e2e_script = {'value': e2e_leg(True, ne2e), 'unit': 'GSa*steps/s',
+                      'h2d_bytes_per_step': per_field, 'd2h_bytes_per_step': per_field,
+                      'api': "GSTATE.FIELDX/Y <- pinned host field; 10 x [fiber(x,'gps-'); ampliflat(G,'gain',opt)]; read "
+                             "GSTATE.FIELDX/Y (field resident in HBM between the calls), 1 realization per rank"}
+
+        # the step of `value` (B realizations x 10 spans) through the C-ABI call on HOST buffers: pmx_link_run creates the
+        # plan and the device field, uploads the B fields, loops the spans, downloads the B fields and frees everything
+        import ctypes as _C
+        bx = torch.empty((B, 1, N), dtype=torch.complex128).pin_memory()
+        by = torch.empty((B, 1, N), dtype=torch.complex128).pin_memory()
+        txr, tyr = np.ascontiguousarray(txx.T), np.ascontiguousarray(txy.T)       # [1][N]
+        lk = mc.Link(ctx, setup, NSPAN, B, GAIN_DB, NF_DB, first_realization=rank * B)   # (plate draws and sigma only)
+        desc_b, keep_b = setup_to_desc(setup, batch=B, plate_sets=B, db0=lk.plates[0][0], theta=lk.plates[0][1],
+                                       epsilon=lk.plates[0][2])
+
+        def e2e_batched(sid):
+            hx, hy = bx.numpy(), by.numpy()
+            hx[...] = txr[None]
+            hy[...] = tyr[None]
+            ldesc, lkeep = _lib.make_link(NSPAN, lk.gain, lk.sigma,
+                                          plates=[np.stack([pl[i] for pl in lk.plates]) for i in range(3)], plate_sets=B,
+                                          seeds=[lk.ase_seed(sid, k) for k in range(NSPAN)], first=rank * B)
+            io = _lib.complex_field(hx, hy)
+            res = _lib.Result(NSPAN * B)
+            ctx.sync()
+            t0 = time.perf_counter()
+            ctx.check(ctx.lib.pmx_link_run(ctx.h, _C.byref(desc_b), _C.byref(ldesc), _C.byref(io), _C.byref(res.c)))
+            dt = time.perf_counter() - t0
+            assert np.isfinite(hx[B - 1, 0, 0]) and not np.array_equal(hx[0, 0, :8], txr[0, :8])
+            return int(res.ncycle.sum()) * N, dt
+
+        for w in range(2):
+            e2e_batched(w)
+        barrier()
+        sa_b, dt_b = 0, 0.0
+        for k in range(ne2e):
+            a, b_ = e2e_batched(10 + k)
+            sa_b += a
+            dt_b += b_
+        tt = torch.tensor([dt_b, float(sa_b)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            a = tt.clone()
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b_ = tt.clone()
+            dist.all_reduce(b_, op=dist.ReduceOp.SUM)
+            v_b = float(b_[1]) / float(a[0]) / 1e9
+        else:
+            v_b = sa_b / dt_b / 1e9
+        e2e = {'value': v_b, 'unit': 'GSa*steps/s', 'h2d_bytes_per_step': B * per_field, 'd2h_bytes_per_step': B * per_field,
+               'api': 'pmx_link_run(ctx, fiber desc, link desc, HOST fields, result) -- the C-ABI call: %d realizations per '
+                      'rank in pinned host buffers, plan + device field created, H2D, 10 x [fiber ; ampliflat], D2H, all '
+                      'inside the timed call (wall clock)' % B,
+               'script_flow': e2e_script}
+        lk.plan.close()
+        del bx, by
         # a stateless gateway: fiber() and ampliflat() each copy the field up and down
         e2e_pc = {'value': e2e_leg(False, 2), 'unit': 'GSa*steps/s',
                   'h2d_bytes_per_step': NSPAN * 2 * per_field, 'd2h_bytes_per_step': NSPAN * 2 * per_field,
