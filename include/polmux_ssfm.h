@@ -310,6 +310,10 @@ typedef struct pmx_dsp_desc {
  * passes the demultiplexer ran. */
 int pmx_dsp_count(pmx_ctx* ctx, pmx_devfield* f, const pmx_dsp_desc* dsp, const uint8_t* ref_patmat, int64_t* counts_dev,
                   int32_t* passes_host);
+/* The same processing up to the outputs of dsp4cohdec itself (dsp4cohdec.m:284-287): Phases = angle(Signals .* Carrier)
+ * and Amplitudes = abs(Signals) per symbol, HOST [batch][2][nsymb] each (amps may be NULL) -- what samp2pat / pat_decoder
+ * of a script take next (ex20_coherent_polmux.m:151-161). */
+int pmx_dsp_phases(pmx_ctx* ctx, pmx_devfield* f, const pmx_dsp_desc* dsp, double* phases, double* amps, int32_t* passes_host);
 
 /* ---- Monte-Carlo over independent realizations on the GPUs of one node (BASELINE config C5) ------------------------
  * The `while cond` loop of ex20_coherent_polmux.m:131-181 with its realizations sharded over several GPUs from ONE

@@ -32,7 +32,7 @@ EXPORTS = [
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
     'pmx_host_is_pinned', 'pmx_scalar_adaptive_run', 'pmx_mc_run', 'pmx_mc_nccl_available',
     'pmx_ampliflat_exec_at', 'pmx_dsp_count', 'pmx_field_mean_power', 'pmx_pmd_matrix', 'pmx_field_jones', 'pmx_filter_create', 'pmx_field_copy_cols', 'pmx_field_modulate',
-    'pmx_cohmix_exec', 'pmx_field_mean_power_xy', 'pmx_cohmix_run',
+    'pmx_cohmix_exec', 'pmx_field_mean_power_xy', 'pmx_cohmix_run', 'pmx_dsp_phases',
 ]
 
 
@@ -136,6 +136,7 @@ def load():
     lib.pmx_plan_set_plates.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     lib.pmx_fiber_exec.argtypes = [vp, vp, C.POINTER(FiberResult)]
     lib.pmx_host_is_pinned.argtypes = [vp]
+    lib.pmx_dsp_phases.argtypes = [vp, vp, C.POINTER(DspDesc), _dp, _dp, C.POINTER(C.c_int32)]
     lib.pmx_dsp_count.argtypes = [vp, vp, C.POINTER(DspDesc), C.POINTER(C.c_uint8), vp, C.POINTER(C.c_int32)]
     lib.pmx_mc_run.argtypes = [C.POINTER(FiberDesc), C.POINTER(McDesc), C.POINTER(Field), C.POINTER(C.c_int64),
                                C.POINTER(C.c_int64), C.c_char_p, C.c_int32]

@@ -1928,16 +1928,23 @@ __global__ void pmx_k_dsp_final(const unsigned long long* acc, int batch, unsign
     counts[b] = (xy < xx) ? xy + yx : xx + yy;   // ex20_coherent_polmux.m:168-173: swap when Y decodes the X pattern better
 }
 
-extern "C" int pmx_dsp_count(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const uint8_t* ref_patmat, int64_t* counts_dev,
-                             int32_t* passes_host) {
-    if (!c || !f || !d || !ref_patmat || !counts_dev) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: null argument");
-    if (f->nfc != 1) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_dsp_count: single-column ('unique') fields only");
-    if (f->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_dsp_count: FP64 fields only");
-    if ((int64_t)d->nsymb * d->nt != f->nfft) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: nsymb*nt must equal nfft");
+// |s| of every sample (Amplitudes = abs(Signals), dsp4cohdec.m:286)
+__global__ void __launch_bounds__(256) pmx_k_dsp_abs(const cpx* s, size_t n, double* out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = hypot(s[i].x, s[i].y);
+}
+
+// sampler, polarization demultiplexer, carrier recovery; then either the decision + count (ref_patmat, counts_dev) or the
+// phases / amplitudes handed back to the host (phases, amps: [batch][2][nsymb])
+static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const uint8_t* ref_patmat, int64_t* counts_dev,
+                    double* phases, double* amps, int32_t* passes_host, const char* who) {
+    if (f->nfc != 1) return set_err(c, PMX_ERR_UNSUPPORTED, "%s: single-column ('unique') fields only", who);
+    if (f->precision != PMX_F64) return set_err(c, PMX_ERR_UNSUPPORTED, "%s: FP64 fields only", who);
+    if ((int64_t)d->nsymb * d->nt != f->nfft) return set_err(c, PMX_ERR_INVALID, "%s: nsymb*nt must equal nfft", who);
     if (d->taps < 1 || d->taps > PMX_DSP_MAX_TAPS || !(d->taps & 1))
-        return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: taps must be odd, 1..%d", PMX_DSP_MAX_TAPS);
-    if (d->modorder != 2) return set_err(c, PMX_ERR_UNSUPPORTED, "pmx_dsp_count: QPSK (modorder 2) only");
-    if (!(d->mu > 0)) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: mu must be > 0");
+        return set_err(c, PMX_ERR_INVALID, "%s: taps must be odd, 1..%d", who, PMX_DSP_MAX_TAPS);
+    if (d->modorder != 2) return set_err(c, PMX_ERR_UNSUPPORTED, "%s: QPSK (modorder 2) only", who);
+    if (!(d->mu > 0)) return set_err(c, PMX_ERR_INVALID, "%s: mu must be > 0", who);
     CK(c, cudaSetDevice(c->device));
     const int L = d->nsymb, B = f->batch;
     const size_t n = (size_t)B * 2 * L;
@@ -1955,7 +1962,7 @@ extern "C" int pmx_dsp_count(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d,
     CK(c, cudaMallocAsync(&dref, (size_t)L * 4, c->stream));
     CK(c, cudaMallocAsync(&acc, (size_t)B * 4 * sizeof(unsigned long long), c->stream));
     CK(c, cudaMallocAsync(&dpass, (size_t)B * sizeof(int), c->stream));
-    CK(c, cudaMemcpyAsync(dref, ref_patmat, (size_t)L * 4, cudaMemcpyHostToDevice, c->stream));
+    if (ref_patmat) CK(c, cudaMemcpyAsync(dref, ref_patmat, (size_t)L * 4, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemsetAsync(acc, 0, (size_t)B * 4 * sizeof(unsigned long long), c->stream));
     CK(c, cudaMemsetAsync(dpass, 0, (size_t)B * sizeof(int), c->stream));
     {
@@ -1977,16 +1984,38 @@ extern "C" int pmx_dsp_count(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d,
     }
     pmx_k_dsp_carrier<<<2 * B, 32, 0, c->stream>>>(stream_in, w1, w2, om, ph, L, 1 << d->modorder, d->freqavg, d->phasavg,
                                                    d->poworder, d->modorder > 1 ? 0.78539816339744830962 : 0.0);
-    dim3 g((unsigned)std::min((L + 255) / 256, 64), B);
-    pmx_k_dsp_decide<<<g, 256, 0, c->stream>>>(ph, dref, L, acc);
-    pmx_k_dsp_final<<<(B + 127) / 128, 128, 0, c->stream>>>(acc, B, (unsigned long long*)counts_dev);
-    c->launches += 4;
+    c->launches += 2;
+    if (counts_dev) {
+        dim3 g((unsigned)std::min((L + 255) / 256, 64), B);
+        pmx_k_dsp_decide<<<g, 256, 0, c->stream>>>(ph, dref, L, acc);
+        pmx_k_dsp_final<<<(B + 127) / 128, 128, 0, c->stream>>>(acc, B, (unsigned long long*)counts_dev);
+        c->launches += 2;
+    }
     CK(c, cudaGetLastError());
+    if (phases) CK(c, cudaMemcpyAsync(phases, ph, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (amps) {   // the carrier is a pure phase: abs(Signals .* Carrier) = abs(Signals)
+        pmx_k_dsp_abs<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, c->stream>>>(stream_in, n, om);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        CK(c, cudaMemcpyAsync(amps, om, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
     if (passes_host) CK(c, cudaMemcpyAsync(passes_host, dpass, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     for (void* q : {(void*)sig, (void*)y, (void*)w1, (void*)w2, (void*)om, (void*)ph, (void*)dref, (void*)acc, (void*)dpass})
         CK(c, cudaFreeAsync(q, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));   // ref_patmat / passes_host are host buffers of the caller
+    CK(c, cudaStreamSynchronize(c->stream));   // ref_patmat / phases / passes_host are host buffers of the caller
     return PMX_OK;
+}
+
+extern "C" int pmx_dsp_count(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const uint8_t* ref_patmat, int64_t* counts_dev,
+                             int32_t* passes_host) {
+    if (!c || !f || !d || !ref_patmat || !counts_dev) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_count: null argument");
+    return dsp_core(c, f, d, ref_patmat, counts_dev, nullptr, nullptr, passes_host, "pmx_dsp_count");
+}
+
+extern "C" int pmx_dsp_phases(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, double* phases, double* amps,
+                              int32_t* passes_host) {
+    if (!c || !f || !d || !phases) return set_err(c, PMX_ERR_INVALID, "pmx_dsp_phases: null argument");
+    return dsp_core(c, f, d, nullptr, nullptr, phases, amps, passes_host, "pmx_dsp_phases");
 }
 
 // ---------------------------------------------------------------------------

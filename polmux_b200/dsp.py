@@ -31,10 +31,7 @@ def reference_pattern(sym_x, sym_y):
     return np.ascontiguousarray(np.stack(out, axis=1), dtype=np.uint8)
 
 
-def dsp_count(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, ref_patmat, counts_dev_ptr: int, **params):
-    """Error counts of every realization of `field` (CD already compensated) into a device int64 buffer.  sample_shift /
-    peak: the receiver's currents are sampled at k*nt + sample_shift and divided by peak (0: unit mean power).
-    -> passes the polarization demultiplexer ran, per realization."""
+def _desc(nsymb, nt, params):
     p = dict(DEFAULTS)
     p.update(params)
     d = _lib.DspDesc()
@@ -42,6 +39,72 @@ def dsp_count(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, r
     d.R[0], d.R[1], d.phizero, d.max_passes = float(p['R'][0]), float(p['R'][1]), float(p['phizero']), int(p['max_passes'])
     d.modorder, d.freqavg, d.phasavg, d.poworder = int(p['modorder']), int(p['freqavg']), int(p['phasavg']), int(p['poworder'])
     d.sample_shift, d.peak = int(p['sample_shift']), float(p['peak'])
+    return d
+
+
+def dsp_phases(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, want_amplitudes=True, **params):
+    """-> (Phases, Amplitudes, passes): [batch, nsymb, 2] each, what dsp4cohdec returns (pmx_dsp_phases)."""
+    d = _desc(nsymb, nt, params)
+    ph = np.zeros((field.batch, 2, nsymb), dtype=np.float64)
+    am = np.zeros_like(ph) if want_amplitudes else None
+    passes = np.zeros(field.batch, dtype=np.int32)
+    ctx.check(ctx.lib.pmx_dsp_phases(ctx.h, field.h, C.byref(d), ph.ctypes.data_as(_lib._dp),
+                                     None if am is None else am.ctypes.data_as(_lib._dp),
+                                     passes.ctypes.data_as(C.POINTER(C.c_int32))))
+    tr = lambda a: None if a is None else np.ascontiguousarray(a.transpose(0, 2, 1))
+    return tr(ph), tr(am), passes
+
+
+def dsp4cohdec(ich, pat, x, p, ctx=None):
+    """[Phases, Amplitudes] = dsp4cohdec(ich, pat, x, p) -- dsp4cohdec.m:1, for a two-polarization QPSK field, on the device:
+    receiver_cohmix (polmux_b200/receiver.py), the shift by the receiver's delay (:167-169), one sample per symbol,
+    normalisation by 4*sqrt(POWER(ich)) (:226-227), polarization demultiplexer (p.applypol, 'cma'), carrier recovery
+    (p.freqavg / phasavg / poworder).  -> (Phases [nsymb, 2], Amplitudes [nsymb, 2]).
+    Differences stated in DESIGN.md: x.delay must be 'theory' (the pattern-correlation search of mygeteyeinfo is not
+    built, so `pat` only tells the number of polarizations and worsteyeop is not returned), the decimator (`decimate`, a
+    Signal Processing Toolbox function outside the reference tree) is replaced by plain sampling at the symbol centres;
+    p.applyadc / applydcf / applynlr and the 'easi' / 'singlepol' demultiplexers raise."""
+    from . import receiver as _rx
+    from .gstate import GSTATE as G
+    if x.get('rec', 'coherent') != 'coherent':
+        raise ValueError("Flag X.rec must be 'coherent'")                       # dsp4cohdec.m:143
+    for k in ('applyadc', 'applydcf', 'applynlr'):
+        if p.get(k):
+            raise NotImplementedError('dsp4cohdec: p.%s is not built' % k)
+    if p.get('applypol') and str(p.get('polmethod', 'cma')).lower() != 'cma':
+        raise NotImplementedError("dsp4cohdec: polarization demultiplexer '%s' is not built" % p.get('polmethod'))
+    if x.get('delay') != 'theory':
+        raise NotImplementedError("dsp4cohdec: x.delay = 'theory' only (the pattern-correlation timing search is not built)")
+    if not G.has_y() or np.ndim(pat) < 2 or np.shape(pat)[1] == 1:
+        raise NotImplementedError('dsp4cohdec: two-polarization fields and patterns only')
+    if int(p.get('modorder', 2)) != 2:
+        raise NotImplementedError('dsp4cohdec: QPSK (modorder 2) only')
+    ctx = ctx or _lib.default_context()
+    col, S, xo = _rx.front_end(ich, x, ctx)
+    try:
+        if 'b2b' in x:
+            avgdelay = 0.0                                                      # mygeteyeinfo, dsp4cohdec.m:491-493
+        else:
+            dl = np.asarray(G.DELAY, dtype=np.float64)
+            avgdelay = 0.5 * (dl[0, ich - 1] + dl[1, ich - 1])
+        delay = avgdelay + _rx.evaldelay(xo['oftype'], xo['obw'] * 0.5) + _rx.evaldelay(xo['eftype'], xo['ebw']) + xo['post_delay']
+        cma = dict(p.get('cmaparams') or {})
+        params = dict(applypol=bool(p.get('applypol')), taps=int(cma.get('taps', 7)), mu=float(cma.get('mu', 1 / 6000)),
+                      R=tuple(cma.get('R', (1.0, 1.0))), phizero=float(cma.get('phizero', 0.0)),
+                      modorder=2, freqavg=int(p.get('freqavg', 500)), phasavg=int(p.get('phasavg', 3)),
+                      poworder=int(p.get('poworder', 2)), sample_shift=int(round(delay * G.NT)),
+                      peak=4.0 * math.sqrt(float(np.asarray(G.POWER).ravel()[ich - 1])))
+        ph, am, _ = dsp_phases(ctx, col, G.NSYMB, G.NT, **params)
+    finally:
+        col.close()
+    return ph[0], am[0]
+
+
+def dsp_count(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, ref_patmat, counts_dev_ptr: int, **params):
+    """Error counts of every realization of `field` (CD already compensated) into a device int64 buffer.  sample_shift /
+    peak: the receiver's currents are sampled at k*nt + sample_shift and divided by peak (0: unit mean power).
+    -> passes the polarization demultiplexer ran, per realization."""
+    d = _desc(nsymb, nt, params)
     ref = np.ascontiguousarray(ref_patmat, dtype=np.uint8).reshape(nsymb, 4)
     passes = np.zeros(field.batch, dtype=np.int32)
     ctx.check(ctx.lib.pmx_dsp_count(ctx.h, field.h, C.byref(d), ref.ctypes.data_as(C.POINTER(C.c_uint8)),

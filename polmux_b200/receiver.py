@@ -170,14 +170,14 @@ class CohmixSetup:
         self.balanced = not (x.get('pdtype') == 'normal')                     # :264-268
 
 
-def receiver_cohmix(ich, x, ctx=None, nargout=1, randn=None):
-    """Iric = receiver_cohmix(ich, x): the photocurrents of channel ich, [Nfft, 2] (X: in-phase, quadrature) or
-    [Nfft, 4] (X, then Y) -- receiver_cohmix.m:1.  With nargout = 2 also returns x with avgebx / avgeby / post_delay."""
+def front_end(ich, x, ctx, want_energy=False, randn=None):
+    """The device part of receiver_cohmix: -> (DeviceField [1][1][Nfft] whose X / Y slots hold I + i*Q of the two
+    polarizations' currents, CohmixSetup, x updated).  The caller closes the field."""
     G = GSTATE
-    ctx = ctx or _lib.default_context()
     nfr, nfc = G.field_shape()
     S = CohmixSetup(ich, x, G, nfc, randn)
     isy = G.has_y()
+    xo = S.x
     col = _lib.DeviceField(ctx, S.nfft, 1, 1)
     try:
         if S.b2b:                                                            # the transmitted field (:124-128, 224-229)
@@ -196,8 +196,7 @@ def receiver_cohmix(ich, x, ctx=None, nargout=1, randn=None):
             col.upload(np.asarray(G.FIELDX)[:, S.nch - 1:S.nch], None)
         if S.ndfn:
             _lib.field_modulate(ctx, col, S.ndfn)
-        xo = S.x
-        if nargout >= 2:   # normalised average energy per bit in the channel's band, before the optical filter (:174-175,233-234)
+        if want_energy:   # normalised average energy per bit in the channel's band, before the optical filter (:174-175,233-234)
             band = np.zeros(S.nfft)
             band[:S.ndfnl] = 1
             band[S.nfft - S.ndfnr:] = 1
@@ -211,13 +210,12 @@ def receiver_cohmix(ich, x, ctx=None, nargout=1, randn=None):
                     finally:
                         f_.close()
                 px, py = _lib.field_mean_power_xy(ctx, tmp)
-                pw = (px[0, 0], py[0, 0])
             finally:
                 tmp.close()
             pch = float(np.asarray(G.POWER).ravel()[ich - 1])
-            xo['avgebx'] = pw[0] / pch
+            xo['avgebx'] = px[0, 0] / pch
             if isy:
-                xo['avgeby'] = pw[1] / pch
+                xo['avgeby'] = py[0, 0] / pch
         fo = _lib.Filter(ctx, S.nfft, 1, S.hf_opt)
         try:
             fo.execute(col)
@@ -229,6 +227,19 @@ def receiver_cohmix(ich, x, ctx=None, nargout=1, randn=None):
             fe.execute(col)
         finally:
             fe.close()
+    except Exception:
+        col.close()
+        raise
+    return col, S, xo
+
+
+def receiver_cohmix(ich, x, ctx=None, nargout=1, randn=None):
+    """Iric = receiver_cohmix(ich, x): the photocurrents of channel ich, [Nfft, 2] (X: in-phase, quadrature) or
+    [Nfft, 4] (X, then Y) -- receiver_cohmix.m:1.  With nargout = 2 also returns x with avgebx / avgeby / post_delay."""
+    ctx = ctx or _lib.default_context()
+    isy = GSTATE.has_y()
+    col, S, xo = front_end(ich, x, ctx, want_energy=nargout >= 2, randn=randn)
+    try:
         zx, zy = col.download()
     finally:
         col.close()

@@ -134,3 +134,51 @@ def test_receiver_front_end_plus_dsp_chain_matches_the_oracles(nf_db):
     fo.close()
     fe.close()
     fld.close()
+
+
+def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
+    """polmux_b200.dsp.dsp4cohdec(ich, pat, x, p) -- the reference's call (ex20_coherent_polmux.m:151), x.delay = 'theory':
+    Phases / Amplitudes equal those of oracle/receiver_oracle.py + oracle/dsp_oracle.py (<= 1e-9 rad away from the +-pi
+    cut), and samp2pat / pat_decoder on them give the counts the device counter gives"""
+    import oracle.receiver_oracle as rxo
+    nsymb, nt = 1 << 11, 16
+    n = nsymb * nt
+    ex, ey, sx, sy = synth.pdm_qpsk(nsymb, nt, 1)
+    pmx.reset_all(nsymb, nt, 1)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.LAMBDA, G.POWER = 28.0, np.array([1550.0]), np.array([1.0])
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    pmx.fiber(base_fiber(length=4e4, dgd=0.3, nplates=20, manakov='yes', disp=0.0), 'gps-',
+              rng=np.random.Generator(np.random.PCG64(81)))
+    pmx.ampliflat(8.0, 'gain', {'f': 30.0}, seed=5)
+    x = {'rec': 'coherent', 'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65, 'lopower': 0.0, 'delay': 'theory'}
+    p = {'sps': nt, 'workatbaudrate': True, 'applyadc': False, 'applydcf': False, 'applynlr': False, 'applypol': True,
+         'polmethod': 'cma', 'cmaparams': {'R': (1.0, 1.0), 'mu': 1 / 2000, 'taps': 7, 'txpolars': 2, 'phizero': 0.0},
+         'modorder': 2, 'freqavg': 200, 'phasavg': 3, 'poworder': 2}
+    pat = np.stack([sx[:, 0], sy[:, 0]], axis=1)
+    hx, hy = np.array(G.FIELDX), np.array(G.FIELDY)
+    delay0 = float(0.5 * (G.DELAY[0, 0] + G.DELAY[1, 0]))
+    phases, amps = dsp.dsp4cohdec(1, pat, x, p)
+    assert phases.shape == (nsymb, 2) and amps.shape == (nsymb, 2)
+
+    class GS:
+        pass
+    gs = GS()
+    for k in ('FN', 'LAMBDA', 'SYMBOLRATE', 'NSYMB', 'NT', 'NCH', 'POWER'):
+        setattr(gs, k, getattr(G, k))
+    gs.FIELDX, gs.FIELDY = hx, hy
+    iric, xo = rxo.receiver_cohmix(gs, 1, x)
+    shift = int(round((delay0 + rxo.evaldelay('gauss', 0.95) + rxo.evaldelay('bessel5', 0.65) + xo['post_delay']) * nt))
+    idx = (np.arange(nsymb) * nt + shift) % n
+    s = np.stack([iric[idx, 0] + 1j * iric[idx, 1], iric[idx, 2] + 1j * iric[idx, 3]], axis=1) / (4 * math.sqrt(float(G.POWER[0])))
+    y, _ = dsp_orc.cma_polar_demux(s, mu=1 / 2000, taps=7)
+    want = dsp_orc.carrier_recovery(y, 2, 200, 3, 2)
+    np.testing.assert_allclose(amps, np.abs(y), rtol=1e-9, atol=1e-12)
+    away = np.abs(np.abs(want) - math.pi) > 1e-6
+    np.testing.assert_allclose(phases[away], want[away], rtol=0, atol=1e-9)
+    tx_phase = np.stack([np.angle((2.0 * (q & 1) - 1) + 1j * (2.0 * ((q >> 1) & 1) - 1)) for q in (sx[:, 0], sy[:, 0])], axis=1)
+    assert dsp_orc.count_errors_dqpsk(phases, tx_phase) == dsp_orc.count_errors_dqpsk(want, tx_phase)
+    with pytest.raises(NotImplementedError, match='theory'):
+        dsp.dsp4cohdec(1, pat, dict(x, delay='estimate'), p)
+    with pytest.raises(NotImplementedError, match='applydcf'):
+        dsp.dsp4cohdec(1, pat, x, dict(p, applydcf=True))
