@@ -1792,66 +1792,172 @@ __global__ void __launch_bounds__(32) pmx_k_dsp_cma(const cpx* sig, cpx* out, in
     if (lane == 0 && passes) passes[b] = c - 1;
 }
 
-// Carrier recovery of one (realization, polarization) stream by one thread: frequency estimate (navg = freqavg) ->
+// The same filter with one lane per (filter, input column, tap) -- 4*TAPS <= 32 lanes of one warp: every lane forms ONE
+// product and updates ONE tap, the products of a (filter, column) group are fetched by shuffles and added in the
+// interpreter's order (tap index ascending, then column 0 + column 1) by all its lanes alike.  A quarter of the issued
+// FP64 instructions of the four-lane form (every warp instruction costs the same whether 4 or 28 lanes are active).
+// |Y|^2 is taken as re^2 + im^2 (the reference squares abs(Y): the two differ in the last bits only).
+template <int TAPS>
+__global__ void __launch_bounds__(32) pmx_k_dsp_cma_w(const cpx* sig, cpx* out, int L, double mu, double r1, double r2,
+                                                      double phizero, int repetitions, int* passes) {
+    static_assert(4 * TAPS <= 32, "one warp");
+    constexpr int taps = TAPS, NL = 4 * TAPS;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const bool act = lane < NL;
+    const int l = act ? lane : 0;                      // (idle lanes shadow lane 0 and never store)
+    const int f = l / (2 * taps), p = (l / taps) & 1, j = l % taps;
+    const unsigned full = 0xffffffffu;
+    const cpx* xin = sig + ((size_t)b * 2 + p) * L;
+    cpx* y = out + ((size_t)b * 2 + f) * L;
+    const int half = taps / 2, base = l - j, other = base + (p ? -taps : taps);
+    const double R = f == 0 ? r1 : r2;
+    // hzero(halftaps+1,:,:) = M = [cos sin; -sin cos]; filter f takes row f, column p its entry
+    cpx h = make_double2(j == half ? (f == 0 ? (p == 0 ? cos(phizero) : sin(phizero)) : (p == 0 ? -sin(phizero) : cos(phizero))) : 0.0, 0.0);
+    int c = 1;
+    bool conv = false;
+    auto at = [&](int i) { i %= L; return xin[i < 0 ? i + L : i]; };
+    while (!conv && c < repetitions) {
+        const cpx ho = h;
+        // window of symbol k: w_j = x(k - half + j), circular; lane j holds w_j of symbol k - 1 before the shift
+        cpx w = at(-1 - half + j);
+        cpx nxt = at(half);                            // the sample entering at k = 0 (lane taps-1 uses it)
+        for (int k = 0; k < L; ++k) {
+            const double wx = __shfl_down_sync(full, w.x, 1), wy = __shfl_down_sync(full, w.y, 1);
+            w = (j == taps - 1) ? nxt : make_double2(wx, wy);
+            {
+                const int i = k + 1 + half;
+                nxt = xin[i >= L ? i - L : i];         // for the next symbol: its latency hides behind this one
+            }
+            const cpx q = make_double2(__dadd_rn(__dmul_rn(w.x, h.x), -__dmul_rn(w.y, h.y)),
+                                       __dadd_rn(__dmul_rn(w.x, h.y), __dmul_rn(w.y, h.x)));
+            cpx sacc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int jj = 0; jj < taps; ++jj)
+                sacc = make_double2(__dadd_rn(sacc.x, __shfl_sync(full, q.x, base + jj)), __dadd_rn(sacc.y, __shfl_sync(full, q.y, base + jj)));
+            const double ox = __shfl_sync(full, sacc.x, other), oy = __shfl_sync(full, sacc.y, other);
+            const cpx yk = p == 0 ? make_double2(__dadd_rn(sacc.x, ox), __dadd_rn(sacc.y, oy))     // column 0 + column 1
+                                  : make_double2(__dadd_rn(ox, sacc.x), __dadd_rn(oy, sacc.y));
+            if (act && p == 0 && j == 0) y[k] = yk;
+            // incr = mu .* errorfuncma(Y, R) .* conj(xx):  E = Y .* (R - abs(Y).^2)
+            const double g = __dadd_rn(R, -__dadd_rn(__dmul_rn(yk.x, yk.x), __dmul_rn(yk.y, yk.y)));
+            const cpx e = make_double2(__dmul_rn(mu, __dmul_rn(yk.x, g)), __dmul_rn(mu, __dmul_rn(yk.y, g)));
+            h = make_double2(__dadd_rn(h.x, __dadd_rn(__dmul_rn(e.x, w.x), __dmul_rn(e.y, w.y))),
+                             __dadd_rn(h.y, __dadd_rn(__dmul_rn(e.y, w.x), -__dmul_rn(e.x, w.y))));
+        }
+        // (the reference keeps the old taps when the new ones are all zero: any(any(h_new)), dsp4cohdec.m:404-407)
+        double moved = act ? hypot(ho.x - h.x, ho.y - h.y) : 0.0, nz = act ? fmax(fabs(h.x), fabs(h.y)) : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {   // over both filters, both columns and all taps
+            moved = fmax(moved, __shfl_xor_sync(full, moved, o));
+            nz = fmax(nz, __shfl_xor_sync(full, nz, o));
+        }
+        if (nz == 0.0) {
+            h = ho;
+            moved = 0.0;
+        }
+        if (moved < 5e-5) conv = true;
+        ++c;
+    }
+    if (lane == 0 && passes) passes[b] = c - 1;
+}
+
+// Carrier recovery of one (realization, polarization) stream by one CTA: frequency estimate (navg = freqavg) ->
 // cumulated phase omega, cleaned to match the circularity -> demodulation -> Viterbi & Viterbi phase (navg = phasavg,
 // unwrapped) -> phases = angle(s .* fastexp(-omega - theta + pi/4)).  w1, w2: complex scratch of L entries, om: real.
+// Every thread owns a contiguous chunk of the symbols; the two running quantities (cumsum of the frequency estimate,
+// unwrap of the phase) are block-wide scans: the unwrap as an exact integer count of 2*pi jumps.
 __device__ __forceinline__ cpx pmx_cpow_int(cpx a, int n) {   // a^n, n >= 1, by repeated multiplication
     cpx r = a;
     for (int i = 1; i < n; ++i) r = make_double2(r.x * a.x - r.y * a.y, r.x * a.y + r.y * a.x);
     return r;
 }
-__device__ void pmx_circ_avg(const cpx* in, cpx* out, int L, int k) {   // out(n) = mean(in(n-N+1 .. n)), N = 2k+1, circular
+// out(n) = mean(in(n-N+1 .. n)), N = 2k+1, circular, for n in [n0, n1): a running sum seeded from its own N terms
+__device__ __forceinline__ void pmx_circ_avg_chunk(const cpx* in, cpx* out, int L, int k, int n0, int n1) {
+    if (n0 >= n1) return;
     const int N = 2 * k + 1;
     const double invN = 1.0 / N;
-    // every output from its own N terms would cost L*N; a running sum is re-seeded every 4096 outputs to bound its drift
     cpx run = make_double2(0.0, 0.0);
-    for (int n = 0; n < L; ++n) {
-        if ((n & 4095) == 0) {
-            run = make_double2(0.0, 0.0);
-            for (int j = 0; j < N; ++j) {
-                int i = (n - j) % L;
-                i = i < 0 ? i + L : i;
-                run.x += in[i].x;
-                run.y += in[i].y;
-            }
-        } else {
-            int i0 = (n - N) % L;
-            i0 = i0 < 0 ? i0 + L : i0;
-            run.x += in[n].x - in[i0].x;
-            run.y += in[n].y - in[i0].y;
-        }
+    for (int j = 0; j < N; ++j) {
+        int i = (n0 - j) % L;
+        i = i < 0 ? i + L : i;
+        run.x += in[i].x;
+        run.y += in[i].y;
+    }
+    out[n0] = make_double2(run.x * invN, run.y * invN);
+    for (int n = n0 + 1; n < n1; ++n) {
+        int i0 = (n - N) % L;
+        i0 = i0 < 0 ? i0 + L : i0;
+        run.x += in[n].x - in[i0].x;
+        run.y += in[n].y - in[i0].y;
         out[n] = make_double2(run.x * invN, run.y * invN);
     }
 }
-__global__ void __launch_bounds__(32) pmx_k_dsp_carrier(const cpx* sig, cpx* w1, cpx* w2, double* om, double* phases, int L,
-                                                        int M, int freqavg, int phasavg, int P, double offset) {
-    const int s_id = blockIdx.x;   // one (realization, polarization) stream per CTA, thread 0 works
-    if (threadIdx.x != 0) return;
+// exclusive scan of one value per thread over the CTA (blockDim.x <= 1024); every thread gets its offset and the total
+template <typename T>
+__device__ __forceinline__ T pmx_block_exscan(T v, T* sh /*[32]*/, T* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    __syncthreads();   // sh may still be read from a previous scan
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    T woff = 0, tot = 0;
+    for (int w = 0; w < nwarp; ++w) {
+        if (w < warp) woff += sh[w];
+        tot += sh[w];
+    }
+    *total = tot;
+    return woff + inc - v;
+}
+#define PMX_CARRIER_THREADS 1024
+__global__ void __launch_bounds__(PMX_CARRIER_THREADS) pmx_k_dsp_carrier(const cpx* sig, cpx* w1, cpx* w2, double* om,
+                                                                         double* phases, int L, int M, int freqavg, int phasavg,
+                                                                         int P, double offset) {
+    __shared__ double shd[32];
+    __shared__ long long shl[32];
+    __shared__ double s_o0, s_oe;
+    const int s_id = blockIdx.x;   // one (realization, polarization) stream per CTA
     const cpx* s = sig + (size_t)s_id * L;
     cpx* a = w1 + (size_t)s_id * L;
     cpx* bq = w2 + (size_t)s_id * L;
     double* omg = om + (size_t)s_id * L;
     double* ph = phases + (size_t)s_id * L;
-    const double TWO_PI = 6.283185307179586476925286766559;
+    const double TWO_PI = 6.283185307179586476925286766559, PI = 3.14159265358979323846;
+    const int chunk = (L + blockDim.x - 1) / blockDim.x;
+    const int n0 = min(L, (int)threadIdx.x * chunk), n1 = min(L, n0 + chunk);
     if (freqavg > 0) {
-        for (int n = 0; n < L; ++n) {   // (s .* conj(fastshift(s,1))).^M
+        for (int n = threadIdx.x; n < L; n += blockDim.x) {   // (s .* conj(fastshift(s,1))).^M
             const cpx p = s[n], q = s[n == 0 ? L - 1 : n - 1];
             a[n] = pmx_cpow_int(make_double2(p.x * q.x + p.y * q.y, p.y * q.x - p.x * q.y), M);
         }
-        pmx_circ_avg(a, bq, L, freqavg);
+        __syncthreads();
+        pmx_circ_avg_chunk(a, bq, L, freqavg, n0, n1);
         double acc = 0.0;
-        for (int n = 0; n < L; ++n) {   // omega = cumsum(angle(.)/M)
+        for (int n = n0; n < n1; ++n) {   // omega = cumsum(angle(.)/M): local sums, then the offsets of the chunks
             acc += atan2(bq[n].y, bq[n].x) / M;
             omg[n] = acc;
         }
-        const double o0 = omg[0], oe = omg[L - 1];
-        const double closest = o0 + rint((oe - o0) / 2 / 3.14159265358979323846) * 2 * 3.14159265358979323846;
+        double total;
+        const double off = pmx_block_exscan<double>(acc, shd, &total);
+        for (int n = n0; n < n1; ++n) omg[n] += off;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_o0 = omg[0];
+            s_oe = omg[L - 1];
+        }
+        __syncthreads();
+        const double o0 = s_o0, oe = s_oe;
+        const double closest = o0 + rint((oe - o0) / 2 / PI) * 2 * PI;
         const double ratio = closest / oe;
-        for (int n = 0; n < L; ++n) omg[n] = (omg[n] - o0) * ratio + o0;
+        for (int n = threadIdx.x; n < L; n += blockDim.x) omg[n] = (omg[n] - o0) * ratio + o0;
     } else {
-        for (int n = 0; n < L; ++n) omg[n] = 0.0;
+        for (int n = threadIdx.x; n < L; n += blockDim.x) omg[n] = 0.0;
     }
-    for (int n = 0; n < L; ++n) {   // demodulate, then abs(s).^P .* fastexp(angle(s.^M))  (or s.^P when P == M)
+    __syncthreads();
+    for (int n = threadIdx.x; n < L; n += blockDim.x) {   // demodulate, then abs(s).^P .* fastexp(angle(s.^M))  (or s.^P when P == M)
         double sn, cs;
         sincos(-omg[n], &sn, &cs);
         const cpx d = make_double2(s[n].x * cs - s[n].y * sn, s[n].x * sn + s[n].y * cs);
@@ -1864,23 +1970,30 @@ __global__ void __launch_bounds__(32) pmx_k_dsp_carrier(const cpx* sig, cpx* w1,
             a[n] = make_double2(mag * cs, mag * sn);
         }
     }
+    __syncthreads();
     const cpx* sm = a;
     if (phasavg > 0) {
-        pmx_circ_avg(a, bq, L, phasavg);
+        pmx_circ_avg_chunk(a, bq, L, phasavg, n0, n1);
         sm = bq;
+        __syncthreads();
     }
-    double prev = 0.0, unw = 0.0;
-    for (int n = 0; n < L; ++n) {   // theta = unwrap(angle(.))/M;  phases = angle(s .* fastexp(-omega - theta + offset))
+    // theta = unwrap(angle(.))/M: unwrap(n) = angle(n) - 2*pi*(number of upward minus downward jumps up to n), jumps where
+    // the step between neighbours exceeds pi (numpy.unwrap / the interpreter's unwrap)
+    long long local = 0;
+    for (int n = n0; n < n1; ++n) {
+        if (n == 0) continue;
+        const double dd = atan2(sm[n].y, sm[n].x) - atan2(sm[n - 1].y, sm[n - 1].x);
+        if (fabs(dd) > PI) local += (long long)rint(dd / TWO_PI);
+    }
+    long long totl;
+    long long jumps = pmx_block_exscan<long long>(local, shl, &totl);
+    for (int n = n0; n < n1; ++n) {   // phases = angle(s .* fastexp(-omega - theta + offset))
         const double ang = atan2(sm[n].y, sm[n].x);
-        if (n == 0) {
-            unw = ang;
-        } else {
-            double dd = ang - prev;
-            dd -= TWO_PI * rint(dd / TWO_PI);
-            if (fabs(ang - prev) <= 3.14159265358979323846) dd = ang - prev;   // numpy.unwrap: jumps below pi stay
-            unw += dd;
+        if (n > 0) {
+            const double dd = ang - atan2(sm[n - 1].y, sm[n - 1].x);
+            if (fabs(dd) > PI) jumps += (long long)rint(dd / TWO_PI);
         }
-        prev = ang;
+        const double unw = ang - TWO_PI * (double)jumps;
         const double arg = -omg[n] - unw / M + offset;
         double sn, cs;
         sincos(arg, &sn, &cs);
@@ -1975,14 +2088,16 @@ static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const ui
         const int rep = d->max_passes > 0 ? d->max_passes + 1 : 50 * (int)ceil(1.0 / ((double)L * d->mu));
         switch (d->taps) {
 #define PMX_CMA_CASE(T) case T: pmx_k_dsp_cma<T><<<B, 32, 0, c->stream>>>(sig, y, L, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass); break;
-            PMX_CMA_CASE(1) PMX_CMA_CASE(3) PMX_CMA_CASE(5) PMX_CMA_CASE(7) PMX_CMA_CASE(9) PMX_CMA_CASE(11) PMX_CMA_CASE(13)
+#define PMX_CMA_WARP(T) case T: pmx_k_dsp_cma_w<T><<<B, 32, 0, c->stream>>>(sig, y, L, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass); break;
+            PMX_CMA_WARP(1) PMX_CMA_WARP(3) PMX_CMA_WARP(5) PMX_CMA_WARP(7) PMX_CMA_CASE(9) PMX_CMA_CASE(11) PMX_CMA_CASE(13)
             PMX_CMA_CASE(15)
 #undef PMX_CMA_CASE
+#undef PMX_CMA_WARP
         }
         stream_in = y;
         c->launches++;
     }
-    pmx_k_dsp_carrier<<<2 * B, 32, 0, c->stream>>>(stream_in, w1, w2, om, ph, L, 1 << d->modorder, d->freqavg, d->phasavg,
+    pmx_k_dsp_carrier<<<2 * B, PMX_CARRIER_THREADS, 0, c->stream>>>(stream_in, w1, w2, om, ph, L, 1 << d->modorder, d->freqavg, d->phasavg,
                                                    d->poworder, d->modorder > 1 ? 0.78539816339744830962 : 0.0);
     c->launches += 2;
     if (counts_dev) {
