@@ -455,7 +455,28 @@ def main():
                            'plans and a warm-up group outside',
                  'errors_total': int(counts.sum()), 'bits_per_realization': 4 * NSYMB, 'avgber': rep['avgber'],
                  'count_reduce': 'all_reduce(int64[%d], sum) over %d rank(s), backend %s'
-                                 % (nreal, world, 'nccl' if world > 1 else 'none (single rank)')}
+                                 % (nreal, world, 'nccl' if world > 1 else 'none (single rank)'),
+                 'receiver': 'genie: ideal linear equaliser from the known plates + data-aided decision'}
+        # the same job with the reference's receive chain behind the link (receiver_cohmix front-end, sampler, CMA
+        # polarization demultiplexer, Viterbi & Viterbi, differential decision), on a bounded number of realizations
+        nrx = max(B * world, min(nreal, 8 * B * world if world == 1 else 4 * B * world))
+        rxr = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nrx, B, rank, world,
+                          receiver='cohmix')
+        rxr.work.broadcast_from(rxr.tx)
+        rxr.link.cd_compensate(rxr.work)               # builds the compensation plan outside the clock
+        barrier()
+        t0 = time.perf_counter()
+        rxc, _ = rxr.run(ase_seed=7)
+        barrier()
+        tdx = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tdx, op=dist.ReduceOp.MAX)
+        npass = [int(p.max()) for p in rxr.passes]
+        rxr.close()
+        mcres['receiver_chain'] = {'receiver': "cohmix: receiver_cohmix front-end (gauss 1.9 / bessel5 0.65) + sampler + CMA + "
+                                               'Viterbi & Viterbi + differential decision, all on the device',
+                                   'realizations': nrx, 'seconds': float(tdx[0]), 'realizations_per_s': nrx / float(tdx[0]),
+                                   'errors_total': int(rxc.sum()), 'cma_passes_max_rank0': max(npass) if npass else 0}
 
     # ---- e2e: the reference's own script flow on HOST buffers (one realization, all spans):
     #   GSTATE.FIELDX/FIELDY <- pinned host arrays; for each span fiber(x,'gps-'), ampliflat(G,'gain',opt); read the
