@@ -49,9 +49,9 @@ GAIN_DB, NF_DB = 16.0, 5.0
 ALG_BYTES_PER_SA_STEP = 192.0   # 3 passes x (read + write) x 32 B   
 # dram__bytes_read.sum + dram__bytes_write.sum per Sa of a launch, from the ncu --set full capture summarised in
 # profiles/r2_ncu_final_summary.txt (batch 16 in two groups: 8 realizations of 2^20 Sa per launch): pass A
-# (271.2+208.7) MB, B (269.3+217.5) MB, C (271.2+208.9) MB  ->  bytes per Sa; below the 64 algorithmic bytes because
+# (271.3+209.2) MB, B (269.5+219.7) MB, C (271.2+208.7) MB  ->  bytes per Sa; below the 64 algorithmic bytes because
 # part of the traffic is served by the L2
-NCU_DRAM_BYTES_PER_SA = {'passA': 479.9e6 / (8 << 20), 'passB': 486.8e6 / (8 << 20), 'passC': 480.0e6 / (8 << 20)}
+NCU_DRAM_BYTES_PER_SA = {'passA': 480.5e6 / (8 << 20), 'passB': 489.1e6 / (8 << 20), 'passC': 480.0e6 / (8 << 20)}
 CPU_SAMPLE_KM = SPAN_KM         # bounded CPU sample: span 1 of the link in full (80 km, 100 plates): 15-30 s per core
 # FP64 work of one whole trunk on one Sa (both polarizations of a bin) as pass B executes it: phasor progression 1 complex
 # product, phasor on one polarization 1 complex product (2 mul + 2 fma each), boundary matrix 4 mul + 8 fma
@@ -476,7 +476,12 @@ def main():
         mcres['receiver_chain'] = {'receiver': "cohmix: receiver_cohmix front-end (gauss 1.9 / bessel5 0.65) + sampler + CMA + "
                                                'Viterbi & Viterbi + differential decision, all on the device',
                                    'realizations': nrx, 'seconds': float(tdx[0]), 'realizations_per_s': nrx / float(tdx[0]),
-                                   'errors_total': int(rxc.sum()), 'cma_passes_max_rank0': max(npass) if npass else 0}
+                                   'errors_total': int(rxc.sum()), 'cma_passes_max_rank0': max(npass) if npass else 0,
+                                   # a constant-modulus demultiplexer started from the identity can lock both outputs on the
+                                   # same polarization (the reference's cmapolardemux does the same; its scripts run with
+                                   # applypol = false): those realizations count about half the bits of one polarization
+                                   'cma_singular_realizations': int((rxc > NSYMB // 2).sum()),
+                                   'errors_without_singular': int(rxc[rxc <= NSYMB // 2].sum())}
 
     # ---- e2e: the reference's own script flow on HOST buffers (one realization, all spans):
     #   GSTATE.FIELDX/FIELDY <- pinned host arrays; for each span fiber(x,'gps-'), ampliflat(G,'gain',opt); read the
