@@ -323,6 +323,20 @@ int pmx_dsp_phases(pmx_ctx* ctx, pmx_devfield* f, const pmx_dsp_desc* dsp, doubl
  * error counter (pmx_qpsk_count) writing into the rank's slice of a zero-initialised [nreal] int64 vector and ONE
  * ncclAllReduce(sum) over NVLink.  NCCL is bound at run time (libnccl.so.2); with a single GPU it is optional.
  * The caller replays ber_estimate's recursion (ber_estimate.m:121-127) over counts[] in realization order. */
+/* The reference's receive chain behind the link of a Monte-Carlo job (ex20_coherent_polmux.m:151-176): receiver_cohmix's
+ * front-end, the sampler and the DSP core, per resident batch.  hf_opt already carries whatever all-pass compensation the
+ * receiver applies (x.dpost, receiver_cohmix.m:139-166, or p.applydcf).  Single-column ('unique') FP64 fields. */
+typedef struct pmx_mc_receiver {
+    const double* hf_opt;      /* [nfft] complex: post fiber .* optical filter                              */
+    const double* hf_el;       /* [nfft] complex: low-pass filter as myfilter returns it                    */
+    double lo_ecw, lo_detune;  /* local oscillator (pmx_cohmix_exec)                                        */
+    const double* lo_phase;    /* [nfft] or NULL                                                            */
+    int32_t balanced;
+    int32_t reserved;
+    pmx_dsp_desc dsp;          /* sampler (sample_shift, peak), demultiplexer, carrier recovery             */
+    const uint8_t* ref_patmat; /* [nsymb][4] decoded transmitted pattern (pmx_dsp_count)                    */
+} pmx_mc_receiver;
+
 typedef struct pmx_mc_desc {
     int32_t ndev;                /* GPUs of this node to shard over                                          */
     const int32_t* device_ids;   /* [ndev]                                                                   */
@@ -339,6 +353,7 @@ typedef struct pmx_mc_desc {
                                  /* global realization index (pmx_ampliflat_exec_at)                          */
     const uint8_t* sym;          /* [2][nsymb] transmitted QPSK symbol indices (pmx_qpsk_count)               */
     int32_t nsymb, nt;
+    const pmx_mc_receiver* rx;   /* NULL: the data-aided counter above; else the reference's receive chain     */
 } pmx_mc_desc;
 /* fiber: the span's fiber (batch / plate_sets / plates are taken from mc); tx: HOST Tx field of one realization;
  * counts: [nreal] bit errors per realization; sa_steps (may be NULL): sum over all realizations of nfft*nfc*ncycle;

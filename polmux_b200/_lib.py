@@ -76,11 +76,16 @@ class DspDesc(C.Structure):
                 ('peak', C.c_double)]
 
 
+class McReceiver(C.Structure):
+    _fields_ = [('hf_opt', _dp), ('hf_el', _dp), ('lo_ecw', C.c_double), ('lo_detune', C.c_double), ('lo_phase', _dp),
+                ('balanced', C.c_int32), ('reserved', C.c_int32), ('dsp', DspDesc), ('ref_patmat', C.POINTER(C.c_uint8))]
+
+
 class McDesc(C.Structure):
     _fields_ = [('ndev', C.c_int32), ('device_ids', C.POINTER(C.c_int32)), ('nreal', C.c_int32), ('batch', C.c_int32),
                 ('nspan', C.c_int32), ('equalize', C.c_int32), ('db0', _dp), ('theta', _dp), ('epsilon', _dp),
                 ('gain', C.c_double), ('sigma', _dp), ('ase_seed', C.c_uint64), ('sym', C.POINTER(C.c_uint8)),
-                ('nsymb', C.c_int32), ('nt', C.c_int32)]
+                ('nsymb', C.c_int32), ('nt', C.c_int32), ('rx', C.POINTER(McReceiver))]
 
 
 class BrfDesc(C.Structure):

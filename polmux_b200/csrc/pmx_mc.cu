@@ -66,7 +66,7 @@ struct Worker {
 // realizations [r0, r1) on one device
 void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, const pmx_mc_desc& m, const pmx_field& tx) {
     pmx_devfield *ftx = nullptr, *work = nullptr;
-    pmx_plan *plan = nullptr, *inv = nullptr;
+    pmx_plan *plan = nullptr, *inv = nullptr, *fo = nullptr, *fe = nullptr;
     int64_t* tmp = nullptr;
     const int B = m.batch, np = fd.nplates, nspan = m.nspan, nfc = fd.nfc;
     const size_t span_stride = (size_t)m.nreal * np;
@@ -145,6 +145,22 @@ void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, con
             }
             MC_CK(pmx_plan_create(w.ctx, &e, &inv));
         }
+        if (m.rx) {   // the receive chain's two filter plans (receiver_cohmix.m:169,293), for the resident batch
+            if (nfc != 1 || fd.precision != PMX_F64 || !m.rx->hf_opt || !m.rx->hf_el || !m.rx->ref_patmat) {
+                w.rc = PMX_ERR_UNSUPPORTED;
+                w.err = "the receive chain takes single-column FP64 fields, both filter responses and the reference pattern";
+                goto done;
+            }
+            MC_CK(pmx_filter_create(w.ctx, fd.nfft, 1, B, PMX_F64, m.rx->hf_opt, 1, &fo));
+            std::vector<double> hh(2 * (size_t)fd.nfft);   // Hermitian part: two real currents on one complex transform
+            const size_t N = (size_t)fd.nfft;
+            for (size_t k = 0; k < N; ++k) {
+                const size_t mk = (N - k) & (N - 1);
+                hh[2 * k] = 0.5 * (m.rx->hf_el[2 * k] + m.rx->hf_el[2 * mk]);
+                hh[2 * k + 1] = 0.5 * (m.rx->hf_el[2 * k + 1] - m.rx->hf_el[2 * mk + 1]);
+            }
+            MC_CK(pmx_filter_create(w.ctx, fd.nfft, 1, B, PMX_F64, hh.data(), 1, &fe));
+        }
         for (int g0 = r0; g0 < r1; g0 += B) {
             const int nb = std::min(B, r1 - g0);
             if (g0 != r0) gather(g0);
@@ -182,7 +198,14 @@ void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, con
                 }
             }
             // the error counter writes the group's counts; they land in this rank's slice of the NCCL send buffer
-            MC_CK(pmx_qpsk_count(w.ctx, work, m.sym, m.nsymb, m.nt, tmp));
+            if (m.rx) {
+                MC_CK(pmx_fiber_exec(fo, work, nullptr));
+                MC_CK(pmx_cohmix_exec(w.ctx, work, m.rx->lo_ecw, m.rx->lo_detune, m.rx->lo_phase, m.rx->balanced));
+                MC_CK(pmx_fiber_exec(fe, work, nullptr));
+                MC_CK(pmx_dsp_count(w.ctx, work, &m.rx->dsp, m.rx->ref_patmat, tmp, nullptr));
+            } else {
+                MC_CK(pmx_qpsk_count(w.ctx, work, m.sym, m.nsymb, m.nt, tmp));
+            }
             if (cudaMemcpyAsync(w.counts_dev + g0, tmp, (size_t)nb * sizeof(int64_t), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
                 w.rc = PMX_ERR_CUDA;
                 w.err = "count copy failed";
@@ -193,6 +216,8 @@ void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, con
     }
 done:
     if (tmp) cudaFree(tmp);
+    pmx_plan_destroy(fo);
+    pmx_plan_destroy(fe);
     pmx_plan_destroy(inv);
     pmx_plan_destroy(plan);
     pmx_field_destroy(work);

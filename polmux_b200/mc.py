@@ -294,9 +294,13 @@ def run_mc(ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt
 
 
 def run_mc_native(setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int, gain_db: float, nf_db: float,
-                  nreal: int, batch: int, devices=(0,), ase_seed: int = 1, equalize: bool = True):
+                  nreal: int, batch: int, devices=(0,), ase_seed: int = 1, equalize: bool = True, receiver=None,
+                  dsp_params=None, ich: int = 1):
     """The same Monte-Carlo job through pmx_mc_run: one process, one host thread and one context per GPU of `devices`,
     the integer all-reduce done with NCCL inside the library (no torch.distributed).  Plate draws as run_mc's.
+    receiver: None -- the data-aided counter (with `equalize`); a dict = the x struct of receiver_cohmix -- the reference's
+    receive chain (front-end, sampler, DSP core with dsp_params) behind the link, its optical response carrying the
+    compensation of the link's chromatic dispersion (as x.dpost / p.applydcf would).
     -> (counts [nreal] int64, Sa*steps over all realizations)"""
     import ctypes as C
     lib = _lib.load()
@@ -317,6 +321,30 @@ def run_mc_native(setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan
     m.db0, m.theta, m.epsilon = (pl[i].ctypes.data_as(_lib._dp) for i in range(3))
     m.gain, m.sigma, m.ase_seed = gain, sigma.ctypes.data_as(_lib._dp), int(ase_seed)
     m.sym, m.nsymb, m.nt = symb.ctypes.data_as(C.POINTER(C.c_uint8)), int(nsymb), int(nt)
+    rxkeep = None
+    if receiver is not None:
+        from . import dsp as _dsp
+        from . import receiver as _rx
+        from .gstate import GSTATE
+        S = _rx.CohmixSetup(ich, receiver, GSTATE, nfc=setup.nfc)
+        x = S.x
+        delay = _rx.evaldelay(x['oftype'], x['obw'] * 0.5) + _rx.evaldelay(x['eftype'], x['ebw']) + x['post_delay']
+        p = dict(dsp_params or {})
+        p.update(sample_shift=int(round(delay * nt)), peak=4.0 * math.sqrt(float(np.asarray(GSTATE.POWER).ravel()[ich - 1])))
+        ph = np.asarray(setup.betat, dtype=np.float64)[:, 0] * (setup.length * nspan)      # the link's all-pass phase, undone
+        hopt = np.ascontiguousarray(S.hf_opt * (np.cos(ph) + 1j * np.sin(ph)))
+        hel = np.ascontiguousarray(np.asarray(S.hf_el, dtype=np.complex128))
+        ref = np.ascontiguousarray(_dsp.reference_pattern(np.asarray(sym)[0], np.asarray(sym)[1]), dtype=np.uint8)
+        lop = None if S.lophase is None else np.ascontiguousarray(S.lophase, dtype=np.float64)
+        rx = _lib.McReceiver()
+        rx.hf_opt, rx.hf_el = hopt.ctypes.data_as(_lib._dp), hel.ctypes.data_as(_lib._dp)
+        rx.lo_ecw, rx.lo_detune, rx.balanced = float(S.ecw), float(S.detune), int(S.balanced)
+        rx.lo_phase = None if lop is None else lop.ctypes.data_as(_lib._dp)
+        rx.dsp = _dsp._desc(nsymb, nt, p)
+        rx.ref_patmat = ref.ctypes.data_as(C.POINTER(C.c_uint8))
+        rxkeep = (hopt, hel, ref, lop, rx)
+        m.rx = C.pointer(rx)
+        m.equalize = 0
     fx = np.ascontiguousarray(np.asarray(tx_x, dtype=np.complex128).T)[None]
     fy = np.ascontiguousarray(np.asarray(tx_y, dtype=np.complex128).T)[None]
     io = _lib.complex_field(fx, fy)

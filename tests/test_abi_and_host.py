@@ -37,7 +37,8 @@ def test_struct_layout_matches_header(tmp_path):
     """compile a probe against the header with gcc: sizes and field offsets equal the ctypes mirror"""
     import subprocess
     structs = {'pmx_fiber_desc': _lib.FiberDesc, 'pmx_field': _lib.Field, 'pmx_fiber_result': _lib.FiberResult,
-               'pmx_link_desc': _lib.LinkDesc}
+               'pmx_link_desc': _lib.LinkDesc, 'pmx_dsp_desc': _lib.DspDesc, 'pmx_mc_desc': _lib.McDesc,
+               'pmx_mc_receiver': _lib.McReceiver, 'pmx_brf': _lib.BrfDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "polmux_ssfm.h"', 'int main(void){']
     for cname, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

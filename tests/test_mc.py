@@ -241,3 +241,32 @@ def test_mc_with_the_blind_receiver(ctx):
     assert out['blind'].sum() <= 8          # differential decoding doubles isolated errors; none expected here
     # the full front-end of receiver_cohmix (gauss 1.9 / bessel5 0.65, ex20_coherent_polmux.m:47-50) in front of the same DSP
     assert out['cohmix'].sum() <= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nf_db', [5.0, 37.0])
+def test_native_mc_run_with_the_receive_chain(ctx, nf_db):
+    """pmx_mc_run with pmx_mc_desc.rx (receiver_cohmix front-end + sampler + DSP core inside the library's Monte-Carlo
+    job) against McRunner(receiver='cohmix') driving the same pieces from Python: equal counts per realization"""
+    from polmux_b200.fiber import fiber_setup
+    nsymb, nt, nspan, nreal, batch = 1 << 11, 16, 2, 5, 2
+    ex, ey, sx, sy = synth.pdm_qpsk(nsymb, nt, 1)
+    pmx.reset_all(nsymb, nt, 1)
+    G = pmx.GSTATE
+    G.SYMBOLRATE, G.LAMBDA, G.POWER = 28.0, np.array([1550.0]), np.array([1.0])
+    pmx.create_field('unique', ex, ey, {'power': 'average'})
+    fib = dict(synth.SMF)
+    fib.update(length=4e4, dgd=0.3, nplates=20, manakov='yes')
+    setup = fiber_setup(fib, 'gps-', rng=np.random.Generator(np.random.PCG64(0)))
+    sym = np.stack([sx[:, 0], sy[:, 0]]).astype(np.uint8)
+    x = {'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65, 'lopower': 0.0}
+    dspp = dict(mu=1 / 2000, freqavg=200)
+    r = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 8.0, nf_db, nreal, batch, receiver='cohmix',
+                    dsp_params=dspp, rx_params=x)
+    want, sa = r.run(ase_seed=9)
+    r.close()
+    got, sa2 = mc.run_mc_native(setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 8.0, nf_db, nreal, batch, devices=(0,),
+                                ase_seed=9, receiver=x, dsp_params=dspp)
+    assert sa2 == sa
+    assert np.array_equal(got, want), (got, want)
+    assert (want.sum() > 0) == (nf_db > 20)
