@@ -275,6 +275,7 @@ int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t ns
  * What dsp4cohdec.m does between its decimator and its outputs, for a dual-polarization QPSK field already compensated
  * for chromatic dispersion, on one complex sample per symbol (the sample at time index k*nt of symbol k) normalised to
  * unit mean power:
+ *   easipolardemux  (optional, before or instead of the CMA) EASI source separation with one 2x2 tap
  *   cmapolardemux   constant-modulus 2x2 FIR polarization demultiplexer: cmaadaptivefilter.m:33-55 (C twin
  *                   cmaadaptivefilter.c:57-91) passed over the block until the taps move by less than 5e-5
  *                   (dsp4cohdec.m:353-427), taps initialised to the rotation by phizero
@@ -304,6 +305,13 @@ typedef struct pmx_dsp_desc {
                                * receiver's currents round(delay*NT), the shift dsp4cohdec.m:167-169 undoes            */
     double peak;              /* samples are divided by peak = 4*sqrt(GSTATE.POWER(ich)) (dsp4cohdec.m:226-227);
                                * 0: normalise the block to unit mean power instead                                     */
+    /* p.polmethod = 'easi' (apply_easi = 1, apply_cma = 0) or 'combo' (both: EASI first, dsp4cohdec.m:236-241):
+     * easipolardemux / easiadaptivefilter (dsp4cohdec.m:428-482, easiadaptivefilter.m:28-61), one 2x2 tap */
+    int32_t apply_easi;
+    int32_t easi_max_passes;  /* 0: the reference's bound 20*ceil(1/(L*mu)) - 1                                        */
+    double easi_mu;           /* p.easiparams.mu                                                                       */
+    double easi_phizero;      /* p.easiparams.phizero                                                                  */
+    int32_t* easi_passes;     /* HOST [batch] output: passes the EASI stage ran; may be NULL                           */
 } pmx_dsp_desc;
 /* ref_patmat: HOST [nsymb][4] bytes, the differentially decoded transmitted pattern [x1 x2 y1 y2] (pat_decoder of the
  * transmitted bits); counts_dev: DEVICE [batch] int64 (e.g. the NCCL send buffer); passes_host (may be NULL): [batch]

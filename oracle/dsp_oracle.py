@@ -5,6 +5,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this mod
 Reference code followed (all under /root/reference):
   cmaadaptivefilter.m:33-55 (C twin cmaadaptivefilter.c:57-91)   constant-modulus 2x2 FIR update, sample by sample
   dsp4cohdec.m:353-427   cmapolardemux: initial taps, circular extension, passes until the taps move < 5e-5
+  easiadaptivefilter.m:28-61 (C twin easiadaptivefilter.c)   EASI source separation, one 2x2 tap: Y = H*x,
+                         H <- (I - mu*E(Y))*H with the nonlinear error matrix E (errorfun, :55-61)
+  dsp4cohdec.m:428-482   easipolardemux: initial rotation, passes until the taps move < 5e-5 (at most 20*ceil(1/(L*mu)) - 1)
   dsp4cohdec.m:320-345   vitvit: M-th power, circular moving average of 2k+1 samples, (unwrapped) angle / M
   dsp4cohdec.m:241-283   carrier recovery: frequency from s.*conj(shift(s)) (navg = freqavg), phase (navg = phasavg)
   samp2pat.m:60-67       'coherent': first_bit = |phase| <= pi/2, second_bit = phase > 0
@@ -12,8 +15,8 @@ Reference code followed (all under /root/reference):
                          stars2pat (stars2pat.m:28-41), both bits inverted
   ex20_coherent_polmux.m:168-176   X/Y swap test, ber_estimate.m:118 error count
 
-PARITY PINNING: tests/test_dsp_oracle.py executes the reference's own cmaadaptivefilter.m, samp2pat.m,
-pat_decoder.m (+ pat2stars.m, stars2pat.m, fastshift.m) and the sub-functions vitvit / cmapolardemux of
+PARITY PINNING: tests/test_dsp_oracle.py executes the reference's own cmaadaptivefilter.m, easiadaptivefilter.m, samp2pat.m,
+pat_decoder.m (+ pat2stars.m, stars2pat.m, fastshift.m) and the sub-functions vitvit / cmapolardemux / easipolardemux of
 dsp4cohdec.m with the mini interpreter (oracle/mini_m) on seeded inputs and compares them with this file.
 
 NOT restated (and not built): the front-end of receiver_cohmix.m (optical / electrical filters, LO mixing),
@@ -69,6 +72,63 @@ def cma_polar_demux(x, mu=1 / 6000, taps=7, R=(1.0, 1.0), phizero=0.0, max_passe
     while not conv and c < repetitions:
         h1o, h2o = h1.copy(), h2.copy()
         y, h1n, h2n = cma_adaptive_filter(ext, h1, h2, mu, R)
+        if np.any(h1n) or np.any(h2n):
+            h1, h2 = h1n, h2n
+        if max(np.max(np.abs(h1o - h1)), np.max(np.abs(h2o - h2))) < 5e-5:
+            conv = True
+        c += 1
+    return y, c - 1
+
+
+def easi_errorfun(a, b, lam):
+    """errorfun of easiadaptivefilter.m:55-61 -> E [2,2] (the products are a*b, not a*conj(b), as the reference writes them)"""
+    na, nb = abs(a) ** 2, abs(b) ** 2
+    d1 = 1 + lam * (na + nb)
+    d2 = 1 + lam * (a * abs(a) + b * abs(b))
+    e = np.empty((2, 2), dtype=np.complex128)
+    e[0, 0] = (na - 1) / d1
+    e[0, 1] = (a * b) / d1 + (a * b * (na - nb)) / d2
+    e[1, 0] = (a * b) / d1 + (a * b * (nb - na)) / d2
+    e[1, 1] = (nb - 1) / d1
+    return e
+
+
+def easi_adaptive_filter(xx, h1, h2, mu):
+    """easiadaptivefilter.m:28-51 for one tap: xx [L,2]; h1, h2 [1,2] (rows of the separation matrix).
+    -> (Y [L,2], h1, h2)"""
+    xx = np.asarray(xx, dtype=np.complex128)
+    h1 = np.array(h1, dtype=np.complex128).reshape(1, 2)
+    h2 = np.array(h2, dtype=np.complex128).reshape(1, 2)
+    L = xx.shape[0]
+    y = np.zeros((L, 2), dtype=np.complex128)
+    for k in range(L):
+        w = xx[k:k + 1, :]
+        y1 = np.sum(np.sum(w * h1))
+        y2 = np.sum(np.sum(w * h2))
+        y[k, 0], y[k, 1] = y1, y2
+        e = easi_errorfun(y1, y2, mu)
+        h11 = (1 - mu * e[0, 0]) * h1[:, 0] + (-mu * e[0, 1]) * h2[:, 0]
+        h12 = (1 - mu * e[0, 0]) * h1[:, 1] + (-mu * e[0, 1]) * h2[:, 1]
+        h21 = (-mu * e[1, 0]) * h1[:, 0] + (1 - mu * e[1, 1]) * h2[:, 0]
+        h22 = (-mu * e[1, 0]) * h1[:, 1] + (1 - mu * e[1, 1]) * h2[:, 1]
+        h1 = np.stack([h11, h12], axis=1)
+        h2 = np.stack([h21, h22], axis=1)
+    return y, h1, h2
+
+
+def easi_polar_demux(x, mu=1 / 6000, phizero=0.0, max_passes=None):
+    """easipolardemux (dsp4cohdec.m:428-482) for two transmitted polarizations.  -> (y [L,2], passes run)"""
+    x = np.asarray(x, dtype=np.complex128)
+    M = np.array([[math.cos(phizero), math.sin(phizero)], [-math.sin(phizero), math.cos(phizero)]], dtype=np.complex128)
+    h1, h2 = M[0:1, :].copy(), M[1:2, :].copy()
+    L = len(x)
+    repetitions = 20 * math.ceil(1.0 / (L * mu))
+    if max_passes is not None:
+        repetitions = min(repetitions, max_passes + 1)
+    c, conv, y = 1, False, None
+    while not conv and c < repetitions:
+        h1o, h2o = h1.copy(), h2.copy()
+        y, h1n, h2n = easi_adaptive_filter(x, h1, h2, mu)
         if np.any(h1n) or np.any(h2n):
             h1, h2 = h1n, h2n
         if max(np.max(np.abs(h1o - h1)), np.max(np.abs(h2o - h2))) < 5e-5:

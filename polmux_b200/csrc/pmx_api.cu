@@ -1860,6 +1860,88 @@ __global__ void __launch_bounds__(32) pmx_k_dsp_cma_w(const cpx* sig, cpx* out, 
     if (lane == 0 && passes) passes[b] = c - 1;
 }
 
+// easipolardemux (dsp4cohdec.m:428-482) around easiadaptivefilter.m:28-61 for its single 2x2 tap: Y = H*x, then
+// H <- (I - mu*E(Y))*H with errorfun's E (:55-61; its products are a*b as written there).  Sequential in the symbol index;
+// one thread per realization, products and sums rounded separately as the interpreter does.
+struct dc2 { double x, y; };
+__device__ __forceinline__ double2 pmx_cm(double2 a, double2 b) {   // a*b, no contraction
+    return make_double2(__dadd_rn(__dmul_rn(a.x, b.x), -__dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ double2 pmx_cdiv(double2 a, double2 b) {   // a/b
+    const double d = __dadd_rn(__dmul_rn(b.x, b.x), __dmul_rn(b.y, b.y));
+    return make_double2(__ddiv_rn(__dadd_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), d),
+                        __ddiv_rn(__dadd_rn(__dmul_rn(a.y, b.x), -__dmul_rn(a.x, b.y)), d));
+}
+__global__ void __launch_bounds__(32) pmx_k_dsp_easi(const cpx* sig, cpx* out, int L, double mu, double phizero, int repetitions,
+                                                     int* passes) {
+    const int b = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const cpx* x1 = sig + ((size_t)b * 2 + 0) * L;
+    const cpx* x2 = sig + ((size_t)b * 2 + 1) * L;
+    cpx* y1o = out + ((size_t)b * 2 + 0) * L;
+    cpx* y2o = out + ((size_t)b * 2 + 1) * L;
+    // hzero(1,:,:) = M = [cos sin; -sin cos]; h1 = its first row, h2 its second
+    double2 h11 = make_double2(cos(phizero), 0.0), h12 = make_double2(sin(phizero), 0.0);
+    double2 h21 = make_double2(-sin(phizero), 0.0), h22 = make_double2(cos(phizero), 0.0);
+    int c = 1;
+    bool conv = false;
+    while (!conv && c < repetitions) {
+        const double2 o11 = h11, o12 = h12, o21 = h21, o22 = h22;
+        double2 nx1 = x1[0], nx2 = x2[0];
+        for (int k = 0; k < L; ++k) {
+            const double2 a1 = nx1, a2 = nx2;
+            if (k + 1 < L) {
+                nx1 = x1[k + 1];
+                nx2 = x2[k + 1];
+            }
+            const double2 p1 = pmx_cm(a1, h11), p2 = pmx_cm(a2, h12), q1 = pmx_cm(a1, h21), q2 = pmx_cm(a2, h22);
+            const double2 ya = make_double2(__dadd_rn(p1.x, p2.x), __dadd_rn(p1.y, p2.y));
+            const double2 yb = make_double2(__dadd_rn(q1.x, q2.x), __dadd_rn(q1.y, q2.y));
+            y1o[k] = ya;
+            y2o[k] = yb;
+            const double aa = sqrt(__dadd_rn(__dmul_rn(ya.x, ya.x), __dmul_rn(ya.y, ya.y)));
+            const double ab = sqrt(__dadd_rn(__dmul_rn(yb.x, yb.x), __dmul_rn(yb.y, yb.y)));
+            const double na = __dmul_rn(aa, aa), nb = __dmul_rn(ab, ab);
+            const double d1 = __dadd_rn(1.0, __dmul_rn(mu, __dadd_rn(na, nb)));
+            const double2 d2 = make_double2(__dadd_rn(1.0, __dmul_rn(mu, __dadd_rn(__dmul_rn(ya.x, aa), __dmul_rn(yb.x, ab)))),
+                                            __dmul_rn(mu, __dadd_rn(__dmul_rn(ya.y, aa), __dmul_rn(yb.y, ab))));
+            const double2 pab = pmx_cm(ya, yb);
+            const double2 t = make_double2(__ddiv_rn(pab.x, d1), __ddiv_rn(pab.y, d1));
+            const double dn = __dadd_rn(na, -nb);
+            const double2 u = pmx_cdiv(make_double2(__dmul_rn(pab.x, dn), __dmul_rn(pab.y, dn)), d2);
+            const double e11 = __ddiv_rn(__dadd_rn(na, -1.0), d1), e22 = __ddiv_rn(__dadd_rn(nb, -1.0), d1);
+            const double2 e12 = make_double2(__dadd_rn(t.x, u.x), __dadd_rn(t.y, u.y));
+            const double2 e21 = make_double2(__dadd_rn(t.x, -u.x), __dadd_rn(t.y, -u.y));
+            // h11 = (1-mu*E11)*h1(1) + (-mu*E12)*h2(1), ... (easiadaptivefilter.m:40-43)
+            const double g1 = __dadd_rn(1.0, -__dmul_rn(mu, e11)), g2 = __dadd_rn(1.0, -__dmul_rn(mu, e22));
+            const double2 m12 = make_double2(-__dmul_rn(mu, e12.x), -__dmul_rn(mu, e12.y));
+            const double2 m21 = make_double2(-__dmul_rn(mu, e21.x), -__dmul_rn(mu, e21.y));
+            const double2 r1 = pmx_cm(m12, h21), r2 = pmx_cm(m12, h22), r3 = pmx_cm(m21, h11), r4 = pmx_cm(m21, h12);
+            const double2 n11 = make_double2(__dadd_rn(__dmul_rn(g1, h11.x), r1.x), __dadd_rn(__dmul_rn(g1, h11.y), r1.y));
+            const double2 n12 = make_double2(__dadd_rn(__dmul_rn(g1, h12.x), r2.x), __dadd_rn(__dmul_rn(g1, h12.y), r2.y));
+            const double2 n21 = make_double2(__dadd_rn(r3.x, __dmul_rn(g2, h21.x)), __dadd_rn(r3.y, __dmul_rn(g2, h21.y)));
+            const double2 n22 = make_double2(__dadd_rn(r4.x, __dmul_rn(g2, h22.x)), __dadd_rn(r4.y, __dmul_rn(g2, h22.y)));
+            h11 = n11;
+            h12 = n12;
+            h21 = n21;
+            h22 = n22;
+        }
+        const double nz = fmax(fmax(fmax(fabs(h11.x), fabs(h11.y)), fmax(fabs(h12.x), fabs(h12.y))),
+                               fmax(fmax(fabs(h21.x), fabs(h21.y)), fmax(fabs(h22.x), fabs(h22.y))));
+        if (nz == 0.0) {   // any(any(h_new)): all-zero taps are not taken over (dsp4cohdec.m:470-473)
+            h11 = o11;
+            h12 = o12;
+            h21 = o21;
+            h22 = o22;
+        }
+        const double moved = fmax(fmax(hypot(o11.x - h11.x, o11.y - h11.y), hypot(o12.x - h12.x, o12.y - h12.y)),
+                                  fmax(hypot(o21.x - h21.x, o21.y - h21.y), hypot(o22.x - h22.x, o22.y - h22.y)));
+        if (moved < 5e-5) conv = true;
+        ++c;
+    }
+    if (passes) passes[b] = c - 1;
+}
+
 // Carrier recovery of one (realization, polarization) stream by one CTA: frequency estimate (navg = freqavg) ->
 // cumulated phase omega, cleaned to match the circularity -> demodulation -> Viterbi & Viterbi phase (navg = phasavg,
 // unwrapped) -> phases = angle(s .* fastexp(-omega - theta + pi/4)).  w1, w2: complex scratch of L entries, om: real.
@@ -2084,17 +2166,35 @@ static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const ui
         pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sh, d->peak, sig);
     }
     const cpx* stream_in = sig;
+    cpx* stage_out = y;
+    int* dpass_easi = nullptr;
+    if (d->apply_easi) {   // 'easi' / first half of 'combo' (dsp4cohdec.m:234-241)
+        if (!(d->easi_mu > 0)) {
+            for (void* q : {(void*)sig, (void*)y, (void*)w1, (void*)w2, (void*)om, (void*)ph, (void*)dref, (void*)acc, (void*)dpass})
+                cudaFreeAsync(q, c->stream);
+            return set_err(c, PMX_ERR_INVALID, "%s: easi_mu must be > 0", who);
+        }
+        CK(c, cudaMallocAsync(&dpass_easi, (size_t)B * sizeof(int), c->stream));
+        CK(c, cudaMemsetAsync(dpass_easi, 0, (size_t)B * sizeof(int), c->stream));
+        const int rep = d->easi_max_passes > 0 ? d->easi_max_passes + 1 : 20 * (int)ceil(1.0 / ((double)L * d->easi_mu));
+        pmx_k_dsp_easi<<<B, 32, 0, c->stream>>>(sig, y, L, d->easi_mu, d->easi_phizero, rep, dpass_easi);
+        c->launches++;
+        stream_in = y;
+        stage_out = sig;
+    }
     if (d->apply_cma) {
         const int rep = d->max_passes > 0 ? d->max_passes + 1 : 50 * (int)ceil(1.0 / ((double)L * d->mu));
+        const cpx* cin = stream_in;
+        cpx* cout_ = stage_out;
         switch (d->taps) {
-#define PMX_CMA_CASE(T) case T: pmx_k_dsp_cma<T><<<B, 32, 0, c->stream>>>(sig, y, L, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass); break;
-#define PMX_CMA_WARP(T) case T: pmx_k_dsp_cma_w<T><<<B, 32, 0, c->stream>>>(sig, y, L, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass); break;
+#define PMX_CMA_CASE(T) case T: pmx_k_dsp_cma<T><<<B, 32, 0, c->stream>>>(cin, cout_, L, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass); break;
+#define PMX_CMA_WARP(T) case T: pmx_k_dsp_cma_w<T><<<B, 32, 0, c->stream>>>(cin, cout_, L, d->mu, d->R[0], d->R[1], d->phizero, rep, dpass); break;
             PMX_CMA_WARP(1) PMX_CMA_WARP(3) PMX_CMA_WARP(5) PMX_CMA_WARP(7) PMX_CMA_CASE(9) PMX_CMA_CASE(11) PMX_CMA_CASE(13)
             PMX_CMA_CASE(15)
 #undef PMX_CMA_CASE
 #undef PMX_CMA_WARP
         }
-        stream_in = y;
+        stream_in = stage_out;
         c->launches++;
     }
     pmx_k_dsp_carrier<<<2 * B, PMX_CARRIER_THREADS, 0, c->stream>>>(stream_in, w1, w2, om, ph, L, 1 << d->modorder, d->freqavg, d->phasavg,
@@ -2115,8 +2215,11 @@ static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const ui
         CK(c, cudaMemcpyAsync(amps, om, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
     if (passes_host) CK(c, cudaMemcpyAsync(passes_host, dpass, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    for (void* q : {(void*)sig, (void*)y, (void*)w1, (void*)w2, (void*)om, (void*)ph, (void*)dref, (void*)acc, (void*)dpass})
-        CK(c, cudaFreeAsync(q, c->stream));
+    if (dpass_easi && d->easi_passes)
+        CK(c, cudaMemcpyAsync(d->easi_passes, dpass_easi, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    for (void* q : {(void*)sig, (void*)y, (void*)w1, (void*)w2, (void*)om, (void*)ph, (void*)dref, (void*)acc, (void*)dpass,
+                    (void*)dpass_easi})
+        if (q) CK(c, cudaFreeAsync(q, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));   // ref_patmat / phases / passes_host are host buffers of the caller
     return PMX_OK;
 }

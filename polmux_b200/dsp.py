@@ -13,7 +13,8 @@ import numpy as np
 from . import _lib
 
 DEFAULTS = dict(applypol=True, taps=7, mu=1 / 6000, R=(1.0, 1.0), phizero=0.0, max_passes=0, modorder=2, freqavg=500,
-                phasavg=3, poworder=2, sample_shift=0, peak=0.0)
+                phasavg=3, poworder=2, sample_shift=0, peak=0.0, applyeasi=False, easi_mu=1 / 6000, easi_phizero=0.0,
+                easi_max_passes=0)
 
 
 def reference_pattern(sym_x, sym_y):
@@ -31,7 +32,7 @@ def reference_pattern(sym_x, sym_y):
     return np.ascontiguousarray(np.stack(out, axis=1), dtype=np.uint8)
 
 
-def _desc(nsymb, nt, params):
+def _desc(nsymb, nt, params, easi_passes=None):
     p = dict(DEFAULTS)
     p.update(params)
     d = _lib.DspDesc()
@@ -39,12 +40,17 @@ def _desc(nsymb, nt, params):
     d.R[0], d.R[1], d.phizero, d.max_passes = float(p['R'][0]), float(p['R'][1]), float(p['phizero']), int(p['max_passes'])
     d.modorder, d.freqavg, d.phasavg, d.poworder = int(p['modorder']), int(p['freqavg']), int(p['phasavg']), int(p['poworder'])
     d.sample_shift, d.peak = int(p['sample_shift']), float(p['peak'])
+    d.apply_easi, d.easi_mu, d.easi_phizero = int(bool(p['applyeasi'])), float(p['easi_mu']), float(p['easi_phizero'])
+    d.easi_max_passes = int(p['easi_max_passes'])
+    if easi_passes is not None:
+        d.easi_passes = easi_passes.ctypes.data_as(C.POINTER(C.c_int32))
     return d
 
 
-def dsp_phases(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, want_amplitudes=True, **params):
+def dsp_phases(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, want_amplitudes=True, easi_passes_out=None,
+               **params):
     """-> (Phases, Amplitudes, passes): [batch, nsymb, 2] each, what dsp4cohdec returns (pmx_dsp_phases)."""
-    d = _desc(nsymb, nt, params)
+    d = _desc(nsymb, nt, params, easi_passes_out)
     ph = np.zeros((field.batch, 2, nsymb), dtype=np.float64)
     am = np.zeros_like(ph) if want_amplitudes else None
     passes = np.zeros(field.batch, dtype=np.int32)
@@ -63,7 +69,7 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
     Differences stated in DESIGN.md: x.delay must be 'theory' (the pattern-correlation search of mygeteyeinfo is not
     built, so `pat` only tells the number of polarizations and worsteyeop is not returned), the decimator (`decimate`, a
     Signal Processing Toolbox function outside the reference tree) is replaced by plain sampling at the symbol centres;
-    p.applyadc / applydcf / applynlr and the 'easi' / 'singlepol' demultiplexers raise."""
+    p.applyadc / applydcf / applynlr and the 'singlepol' demultiplexer raise ('cma', 'easi' and 'combo' are built)."""
     from . import receiver as _rx
     from .gstate import GSTATE as G
     if x.get('rec', 'coherent') != 'coherent':
@@ -71,8 +77,11 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
     for k in ('applyadc', 'applydcf', 'applynlr'):
         if p.get(k):
             raise NotImplementedError('dsp4cohdec: p.%s is not built' % k)
-    if p.get('applypol') and str(p.get('polmethod', 'cma')).lower() != 'cma':
-        raise NotImplementedError("dsp4cohdec: polarization demultiplexer '%s' is not built" % p.get('polmethod'))
+    method = str(p.get('polmethod', 'cma')).lower()
+    if p.get('applypol') and method not in ('cma', 'easi', 'combo'):
+        if method == 'singlepol':
+            raise NotImplementedError("dsp4cohdec: polarization demultiplexer 'singlepol' is not built")
+        raise ValueError('Unknown Polar Rotation method.')                      # dsp4cohdec.m:242-243
     if x.get('delay') != 'theory':
         raise NotImplementedError("dsp4cohdec: x.delay = 'theory' only (the pattern-correlation timing search is not built)")
     if not G.has_y() or np.ndim(pat) < 2 or np.shape(pat)[1] == 1:
@@ -89,7 +98,11 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
             avgdelay = 0.5 * (dl[0, ich - 1] + dl[1, ich - 1])
         delay = avgdelay + _rx.evaldelay(xo['oftype'], xo['obw'] * 0.5) + _rx.evaldelay(xo['eftype'], xo['ebw']) + xo['post_delay']
         cma = dict(p.get('cmaparams') or {})
-        params = dict(applypol=bool(p.get('applypol')), taps=int(cma.get('taps', 7)), mu=float(cma.get('mu', 1 / 6000)),
+        easi = dict(p.get('easiparams') or {})
+        on = bool(p.get('applypol'))
+        params = dict(applypol=on and method in ('cma', 'combo'), applyeasi=on and method in ('easi', 'combo'),
+                      easi_mu=float(easi.get('mu', 1 / 6000)), easi_phizero=float(easi.get('phizero', 0.0)),
+                      taps=int(cma.get('taps', 7)), mu=float(cma.get('mu', 1 / 6000)),
                       R=tuple(cma.get('R', (1.0, 1.0))), phizero=float(cma.get('phizero', 0.0)),
                       modorder=2, freqavg=int(p.get('freqavg', 500)), phasavg=int(p.get('phasavg', 3)),
                       poworder=int(p.get('poworder', 2)), sample_shift=int(round(delay * G.NT)),
@@ -100,11 +113,14 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
     return ph[0], am[0]
 
 
-def dsp_count(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, ref_patmat, counts_dev_ptr: int, **params):
+def dsp_count(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, ref_patmat, counts_dev_ptr: int,
+              easi_passes_out=None, **params):
     """Error counts of every realization of `field` (CD already compensated) into a device int64 buffer.  sample_shift /
     peak: the receiver's currents are sampled at k*nt + sample_shift and divided by peak (0: unit mean power).
-    -> passes the polarization demultiplexer ran, per realization."""
-    d = _desc(nsymb, nt, params)
+    applyeasi / easi_mu / easi_phizero: EASI before (polmethod 'combo') or instead of (applypol=False: 'easi') the CMA;
+    easi_passes_out: int32 [batch] array that receives the passes of that stage.
+    -> passes the CMA polarization demultiplexer ran, per realization."""
+    d = _desc(nsymb, nt, params, easi_passes_out)
     ref = np.ascontiguousarray(ref_patmat, dtype=np.uint8).reshape(nsymb, 4)
     passes = np.zeros(field.batch, dtype=np.int32)
     ctx.check(ctx.lib.pmx_dsp_count(ctx.h, field.h, C.byref(d), ref.ctypes.data_as(C.POINTER(C.c_uint8)),

@@ -61,6 +61,28 @@ def test_cmapolardemux_matches_reference_source():
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-11)
 
 
+def test_easiadaptivefilter_matches_reference_source():
+    x, _ = _signals(200, 5, rot=0.5)
+    h1 = np.array([[1.0, 0.2j]])
+    h2 = np.array([[-0.2j, 1.0]])
+    it = Interp(REF)
+    y, a, b = it.call('easiadaptivefilter', [x, h1, h2, to_m(1), to_m(1 / 300), to_m(1)], 3)
+    yo, ao, bo = dsp.easi_adaptive_filter(x, h1, h2, 1 / 300)
+    np.testing.assert_allclose(yo, y, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(ao, a, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(bo, b, rtol=0, atol=1e-13)
+
+
+def test_easipolardemux_matches_reference_source():
+    x, _ = _signals(300, 6, rot=0.6)
+    it = Interp(REF)
+    params = MStruct({'mu': to_m(1 / 300), 'txpolars': to_m(2), 'phizero': to_m(0.1)})
+    ref = _local(it, 'easipolardemux', [x, params])[0]
+    got, passes = dsp.easi_polar_demux(x, mu=1 / 300, phizero=0.1)
+    assert passes >= 2
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-11)
+
+
 def test_decision_and_differential_decoding_match_reference_source():
     g = np.random.Generator(np.random.PCG64(4))
     phase = g.uniform(-np.pi, np.pi, (64, 2))

@@ -182,3 +182,34 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
         dsp.dsp4cohdec(1, pat, dict(x, delay='estimate'), p)
     with pytest.raises(NotImplementedError, match='applydcf'):
         dsp.dsp4cohdec(1, pat, x, dict(p, applydcf=True))
+
+
+@pytest.mark.parametrize('method', ['easi', 'combo'])
+def test_easi_and_combo_demultiplexers_match_the_oracle(method):
+    """p.polmethod = 'easi' / 'combo' (dsp4cohdec.m:234-241): EASI source separation (easipolardemux around
+    easiadaptivefilter.m) alone or in front of the CMA, on the device against oracle/dsp_oracle.py: equal counts and pass
+    counts of both stages"""
+    import torch
+    nsymb, nt, batch = 1 << 11, 16, 2
+    ctx, fld, hx, hy, sx, sy = _received_field(nsymb, nt, 26.0, seed=90, dgd=0.5, batch=batch)
+    params = dict(taps=7, mu=1 / 2000, freqavg=200, phasavg=3, poworder=2, applyeasi=True, easi_mu=1 / 1500, easi_phizero=0.05,
+                  applypol=(method == 'combo'))
+    ref = dsp.reference_pattern(sx, sy)
+    counts = torch.zeros(batch, dtype=torch.int64, device='cuda')
+    ep = np.zeros(batch, dtype=np.int32)
+    passes = dsp.dsp_count(ctx, fld, nsymb, nt, ref, counts.data_ptr(), easi_passes_out=ep, **params)
+    got = counts.cpu().numpy()
+    tx_phase = np.stack([np.angle((2.0 * (s & 1) - 1) + 1j * (2.0 * ((s >> 1) & 1) - 1)) for s in (sx, sy)], axis=1)
+    for b in range(batch):
+        s = np.stack([hx[b, ::nt], hy[b, ::nt]], axis=1)
+        s = s / math.sqrt(np.mean(np.abs(s) ** 2))
+        y, ne = dsp_orc.easi_polar_demux(s, mu=1 / 1500, phizero=0.05)
+        nc = 0
+        if method == 'combo':
+            y, nc = dsp_orc.cma_polar_demux(y, mu=params['mu'], taps=params['taps'])
+        ph = dsp_orc.carrier_recovery(y, 2, params['freqavg'], params['phasavg'], params['poworder'])
+        want = dsp_orc.count_errors_dqpsk(ph, tx_phase)
+        assert int(ep[b]) == ne and ne >= 1
+        assert int(passes[b]) == nc
+        assert int(got[b]) == want
+    fld.close()
