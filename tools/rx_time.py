@@ -56,13 +56,16 @@ print('per batch of %d: link %.1f ms, CD compensation %.2f ms, optical filter %.
       'low-pass filter %.2f ms' % (B, t_link * 1e3, t_cd * 1e3, t_fo * 1e3, t_mix * 1e3, t_fe * 1e3), flush=True)
 keep.close()
 r.close()
-for rec in ('genie', 'blind', 'cohmix'):
+for rec, dp in (('genie', None), ('blind', None), ('cohmix', None), ('cohmix', dict(applyeasi=True)),
+                ('cohmix', dict(applyeasi=True, applypol=False))):
     r = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, bench.NSPAN, bench.GAIN_DB, bench.NF_DB, nreal, B,
-                    receiver=rec)
+                    receiver=rec, dsp_params=dp)
     r.run(ase_seed=3)
     t0 = time.perf_counter()
     counts, _ = r.run(ase_seed=3)
     dt = time.perf_counter() - t0
-    print('%s receiver: %d realizations in %.2f s = %.1f realizations/s, errors %s' % (
-        rec, nreal, dt, nreal / dt, counts.tolist()[:8]), flush=True)
+    tag = rec + ('' if not dp else (' (combo: EASI + CMA)' if dp.get('applypol', True) else ' (EASI)'))
+    print('%s receiver: %d realizations in %.2f s = %.1f realizations/s, errors in total %d, realizations with more than '
+          'NSYMB/2 errors %d, first counts %s' % (tag, nreal, dt, nreal / dt, int(counts.sum()), int((counts > NSYMB // 2).sum()),
+                                                    counts.tolist()[:8]), flush=True)
     r.close()
