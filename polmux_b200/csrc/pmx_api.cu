@@ -1680,6 +1680,7 @@ __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t
     const int b = blockIdx.x;
     const cpx* fld = field + (size_t)b * N * 2;
     auto at = [&](int k) { return pmx_mem_index((size_t)(((long long)k * nt + shift) & (long long)(N - 1)), l1, l2); };
+    PMX_ASSERT(shift >= 0 && (size_t)shift < N && (size_t)nsymb * nt == N && at(nsymb - 1) < N);
     double inv;
     if (peak > 0.0) {
         inv = 1.0 / peak;
@@ -1822,6 +1823,7 @@ __global__ void __launch_bounds__(32) pmx_k_dsp_cma_w(const cpx* sig, cpx* out, 
         cpx w = at(-1 - half + j);
         cpx nxt = at(half);                            // the sample entering at k = 0 (lane taps-1 uses it)
         for (int k = 0; k < L; ++k) {
+            PMX_ASSERT(base >= 0 && base + taps <= NL && other >= 0 && other + taps <= NL && (base % taps) == 0);
             const double wx = __shfl_down_sync(full, w.x, 1), wy = __shfl_down_sync(full, w.y, 1);
             w = (j == taps - 1) ? nxt : make_double2(wx, wy);
             {
@@ -2010,6 +2012,7 @@ __global__ void __launch_bounds__(PMX_CARRIER_THREADS) pmx_k_dsp_carrier(const c
     const double TWO_PI = 6.283185307179586476925286766559, PI = 3.14159265358979323846;
     const int chunk = (L + blockDim.x - 1) / blockDim.x;
     const int n0 = min(L, (int)threadIdx.x * chunk), n1 = min(L, n0 + chunk);
+    PMX_ASSERT(n0 <= n1 && n1 <= L && (threadIdx.x + 1 < blockDim.x || n1 == L));
     if (freqavg > 0) {
         for (int n = threadIdx.x; n < L; n += blockDim.x) {   // (s .* conj(fastshift(s,1))).^M
             const cpx p = s[n], q = s[n == 0 ? L - 1 : n - 1];
@@ -2681,6 +2684,7 @@ template <typename E>
 __global__ void __launch_bounds__(256) pmx_k_modulate(E* field, size_t N, int l1, int l2, long long m) {
     E* fld = field + (size_t)blockIdx.y * N * 2;
     for (size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pos < N; pos += (size_t)gridDim.x * blockDim.x) {
+        PMX_ASSERT(pmx_time_index(pos, l1, l2) < N && m >= 0 && (unsigned long long)m < N && ((size_t)1 << (l1 + l2)) == N);
         const unsigned long long r = ((unsigned long long)m * (unsigned long long)pmx_time_index(pos, l1, l2)) & (N - 1);  // m*n mod N
         double sn, cs;
         sincospi(2.0 * (double)r / (double)N, &sn, &cs);
@@ -2730,6 +2734,7 @@ __global__ void __launch_bounds__(256) pmx_k_cohmix(E* field, size_t N, int l1, 
     E* fld = field + (size_t)blockIdx.y * N * 2;
     for (size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pos < N; pos += (size_t)gridDim.x * blockDim.x) {
         const size_t n = pmx_time_index(pos, l1, l2);
+        PMX_ASSERT(n < N && pmx_mem_index(n, l1, l2) == pos);
         // Elo = LO_Ecw * fastexp(LO_Detuning + LO_PhaseNoise), LO_Detuning = 2*pi*kdet/Nfft*(1:Nfft)' (:200,219)
         const double ph = (detune != 0.0 ? detune * (double)(n + 1) : 0.0) + (lophase ? lophase[n] : 0.0);
         double sn, cs;

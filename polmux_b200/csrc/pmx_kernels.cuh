@@ -785,6 +785,7 @@ __device__ __forceinline__ void pmx_linear_bins(cpx (&x)[8], cpx (&y)[8], const 
     if constexpr (!SC) {
         if (p.hfilt) {   // a linear filter: u(k) <- H(k) * u(k) from the plan's table, the product taken in double
             const double2* h = p.hfilt + (size_t)col * (size_t)p.hfilt_stride + (size_t)k1 * p.N2;
+            PMX_ASSERT((size_t)k1 * p.N2 + (size_t)(t + 7 * T) < N && (p.hfilt_stride == 0 || (size_t)p.hfilt_stride == N));
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const double2 e = __ldg(&h[t + q * T]);
