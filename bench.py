@@ -458,12 +458,11 @@ def main():
                                  % (nreal, world, 'nccl' if world > 1 else 'none (single rank)'),
                  'receiver': 'genie: ideal linear equaliser from the known plates + data-aided decision'}
         # the same job with the reference's receive chain behind the link (receiver_cohmix front-end, sampler, CMA
-        # polarization demultiplexer, Viterbi & Viterbi, differential decision), on a bounded number of realizations
+        # polarization demultiplexer, Viterbi & Viterbi, differential decision), on a bounded number of realizations; the
+        # chain of a group runs on its own stream beside the propagation of the next group (plans created by McRunner)
         nrx = max(B * world, min(nreal, 8 * B * world if world == 1 else 4 * B * world))
         rxr = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, NSPAN, GAIN_DB, NF_DB, nrx, B, rank, world,
                           receiver='cohmix')
-        rxr.work.broadcast_from(rxr.tx)
-        rxr.link.cd_compensate(rxr.work)               # builds the compensation plan outside the clock
         barrier()
         t0 = time.perf_counter()
         rxc, _ = rxr.run(ase_seed=7)

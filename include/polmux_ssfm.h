@@ -176,7 +176,9 @@ void pmx_plan_destroy(pmx_plan* plan);
 int pmx_plan_set_plates(pmx_plan* plan, int32_t plate_sets, const double* db0, const double* theta,
                         const double* epsilon);
 /* The SSFM loop on a resident field (asynchronous wrt. the host except for the
- * step-control polling; returns after the fiber is complete). */
+ * step-control polling; returns after the fiber is complete).  The field may belong to another context of the same
+ * device (contexts are streams: a receive chain can work on one batch beside the propagation of the next); the caller
+ * orders the two. */
 int pmx_fiber_exec(pmx_plan* plan, pmx_devfield* f, pmx_fiber_result* out);
 /* Total kernel launches issued by this ctx so far (bench `gpu_launches`). */
 int64_t pmx_ctx_launch_count(const pmx_ctx* ctx);

@@ -1010,7 +1010,10 @@ static int ensure_hctl(pmx_ctx* c, int batch) {
 extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* out) {
     if (!p || !fld) return set_err(nullptr, PMX_ERR_INVALID, "pmx_fiber_exec: null argument");
     pmx_ctx* c = p->ctx;
-    if (fld->ctx != c) return set_err(c, PMX_ERR_INVALID, "field and plan belong to different contexts");
+    // a field may be worked on by a plan of another context of the SAME device (a second stream, e.g. a receive chain running
+    // beside the next group's propagation): the caller orders the two streams (every call here returns synchronised)
+    if (fld->ctx != c && fld->ctx->device != c->device)
+        return set_err(c, PMX_ERR_INVALID, "field and plan belong to contexts on different devices");
     if (fld->precision != p->d.precision)
         return set_err(c, PMX_ERR_INVALID, "field precision %d does not match the plan's %d", fld->precision, p->d.precision);
     if (fld->nfft != p->d.nfft || fld->nfc != p->d.nfc || fld->batch != p->d.batch)

@@ -109,22 +109,32 @@ class Link:
             self._inv.set_plates(-db0[:, ::-1], th[:, ::-1], ep[:, ::-1], plate_sets=self.batch)
             self._inv.execute(field)
 
+    def cd_plan(self, ctx=None):
+        """the plan of cd_compensate() on `ctx` (default: the link's own context; a receive chain that runs beside the next
+        group's propagation keeps its plans on a context -- a stream -- of its own)"""
+        if ctx is None or ctx is self.ctx:
+            if getattr(self, '_cd', None) is None:
+                self._cd = self._make_cd_plan(self.ctx)
+            return self._cd
+        return self._make_cd_plan(ctx)
+
+    def _make_cd_plan(self, ctx):
+        s = self.setup
+        sc = dict(s.scalars)
+        sc.update(b30=-sc['b30'], dgdrms=0.0, beta1=-np.asarray(sc['beta1']), beta2=-np.asarray(sc['beta2']))
+        total = s.length * self.nspan
+        inv = FiberSetup(nfft=s.nfft, nfc=s.nfc, fls=(s.fls[0], 0, 0, 0), dphimaxt=math.inf, dzmaxt=total, length=total,
+                         alphalin=0.0, gam=s.gam, betat=-s.betat, db1=np.zeros_like(s.db1), manakov=False, nplates=1,
+                         brf={'db0': np.zeros(1), 'theta': np.zeros(1), 'epsilon': np.zeros(1)}, isv=True, isy=True,
+                         b1=s.b1, dch=s.dch, scalars=sc)
+        desc, keep = setup_to_desc(inv, batch=self.batch, plate_sets=1)
+        return _lib.Plan(ctx, desc, keep)
+
     def cd_compensate(self, field: _lib.DeviceField):
         """What a blind receiver knows: the accumulated chromatic dispersion of the link (dsp4cohdec's p.applydcf,
         dsp4cohdec.m:200-210, as an all-pass filter): one linear step with the dispersion of all spans negated.  The PMD
         stays in the field for the polarization demultiplexer."""
-        s = self.setup
-        if getattr(self, '_cd', None) is None:
-            sc = dict(s.scalars)
-            sc.update(b30=-sc['b30'], dgdrms=0.0, beta1=-np.asarray(sc['beta1']), beta2=-np.asarray(sc['beta2']))
-            total = s.length * self.nspan
-            inv = FiberSetup(nfft=s.nfft, nfc=s.nfc, fls=(s.fls[0], 0, 0, 0), dphimaxt=math.inf, dzmaxt=total, length=total,
-                             alphalin=0.0, gam=s.gam, betat=-s.betat, db1=np.zeros_like(s.db1), manakov=False, nplates=1,
-                             brf={'db0': np.zeros(1), 'theta': np.zeros(1), 'epsilon': np.zeros(1)}, isv=True, isy=True,
-                             b1=s.b1, dch=s.dch, scalars=sc)
-            desc, keep = setup_to_desc(inv, batch=self.batch, plate_sets=1)
-            self._cd = _lib.Plan(self.ctx, desc, keep)
-        self._cd.execute(field)
+        self.cd_plan().execute(field)
 
 
 # ------------------------------------------------------------------------------------------
@@ -196,91 +206,124 @@ class McRunner:
 
     def __init__(self, ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int,
                  gain_db: float, nf_db: float, nreal: int, batch: int, rank: int = 0, world: int = 1,
-                 receiver: str = 'genie', dsp_params=None, rx_params=None, ich: int = 1):
+                 receiver: str = 'genie', dsp_params=None, rx_params=None, ich: int = 1, pipeline: bool = True):
         """receiver: 'genie' -- ideal linear equaliser from the known plates + data-aided decision (pmx_qpsk_count);
         'blind' -- chromatic dispersion compensated, then the DSP core of dsp4cohdec (CMA polarization demultiplexer,
         Viterbi & Viterbi carrier recovery, differential decision: pmx_dsp_count, polmux_b200/dsp.py);
         'cohmix' -- chromatic dispersion compensated, the front-end of receiver_cohmix.m for channel `ich` (optical
         filter, LO mixing, photodiodes, low-pass filter; rx_params = its x struct, polmux_b200/receiver.py), the
         currents sampled at the symbol centres delayed by the filters' 'theory' delay (dsp4cohdec.m:490-503) and
-        divided by 4*sqrt(POWER(ich)) (dsp4cohdec.m:226-227), then the same DSP core"""
+        divided by 4*sqrt(POWER(ich)) (dsp4cohdec.m:226-227), then the same DSP core.
+        pipeline: run the receive chain of a group beside the propagation of the next one (same counts either way)"""
         import torch
         from . import dsp as _dsp
         self.receiver, self.dsp_params = receiver, dict(dsp_params or {})
         if receiver not in ('genie', 'blind', 'cohmix'):
             raise ValueError("receiver must be 'genie', 'blind' or 'cohmix'")
         self.ref_patmat = _dsp.reference_pattern(np.asarray(sym)[0], np.asarray(sym)[1]) if receiver != 'genie' else None
-        self.rx = None
-        if receiver == 'cohmix':
-            from . import receiver as _rx
-            from .gstate import GSTATE
-            x = dict(rx_params or {'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65})   # ex20_coherent_polmux.m:47-50
-            S = _rx.CohmixSetup(ich, x, GSTATE, nfc=setup.nfc)
-            delay = _rx.evaldelay(x['oftype'], x['obw'] * 0.5) + _rx.evaldelay(x['eftype'], x['ebw']) + S.x['post_delay']
-            self.rx = dict(S=S, ich=ich, shift=int(round(delay * nt)),
-                           peak=4.0 * math.sqrt(float(np.asarray(GSTATE.POWER).ravel()[ich - 1])),
-                           fo=_lib.Filter(ctx, setup.nfft, 1, S.hf_opt, batch=batch),
-                           fe=_lib.Filter(ctx, setup.nfft, 1, _rx.hermitian_part(S.hf_el), batch=batch),
-                           col=_lib.DeviceField(ctx, setup.nfft, 1, batch) if setup.nfc > 1 else None)
         self.passes = []
         self.ctx, self.setup, self.sym, self.nsymb, self.nt = ctx, setup, sym, nsymb, nt
         self.nreal, self.batch, self.rank, self.world = nreal, batch, rank, world
         self.r0, self.r1 = shard(nreal, rank, world)
         self.dev = torch.device('cuda', ctx.device)
         self.local = torch.zeros(max(self.r1 - self.r0, 0), dtype=torch.int64, device=self.dev)
-        self.buf = torch.zeros(batch, dtype=torch.int64, device=self.dev)
         self.tx = _lib.DeviceField(ctx, setup.nfft, setup.nfc, 1)
         self.tx.upload(tx_x, tx_y)
-        self.work = _lib.DeviceField(ctx, setup.nfft, setup.nfc, batch)
         self.link = Link(ctx, setup, nspan, batch, gain_db, nf_db, self.r0)
+        # The genie receiver works in place on the link's stream.  The reference's receive chain is mostly one warp per
+        # realization (the adaptive filter is sequential in the symbol index) and leaves the GPU idle: it runs on a context
+        # -- a stream -- of its own, in a host thread, beside the propagation of the NEXT group; two work fields alternate.
+        self.pipelined = pipeline and receiver != 'genie'
+        nslot = 2 if self.pipelined else 1
+        self.works = [_lib.DeviceField(ctx, setup.nfft, setup.nfc, batch) for _ in range(nslot)]
+        self.bufs = [torch.zeros(batch, dtype=torch.int64, device=self.dev) for _ in range(nslot)]
+        self.work, self.buf = self.works[0], self.bufs[0]
+        self.rx = None
+        if receiver != 'genie':
+            self.rxctx = _lib.Context(ctx.device) if self.pipelined else ctx
+            self.rx = dict(cd=self.link.cd_plan(self.rxctx), S=None)
+            if receiver == 'cohmix':
+                from . import receiver as _rx
+                from .gstate import GSTATE
+                x = dict(rx_params or {'oftype': 'gauss', 'obw': 1.9, 'eftype': 'bessel5', 'ebw': 0.65})   # ex20_coherent_polmux.m:47-50
+                S = _rx.CohmixSetup(ich, x, GSTATE, nfc=setup.nfc)
+                delay = _rx.evaldelay(x['oftype'], x['obw'] * 0.5) + _rx.evaldelay(x['eftype'], x['ebw']) + S.x['post_delay']
+                self.rx.update(S=S, ich=ich, shift=int(round(delay * nt)),
+                               peak=4.0 * math.sqrt(float(np.asarray(GSTATE.POWER).ravel()[ich - 1])),
+                               fo=_lib.Filter(self.rxctx, setup.nfft, 1, S.hf_opt, batch=batch),
+                               fe=_lib.Filter(self.rxctx, setup.nfft, 1, _rx.hermitian_part(S.hf_el), batch=batch),
+                               col=_lib.DeviceField(self.rxctx, setup.nfft, 1, batch) if setup.nfc > 1 else None)
+
+    def _receive(self, work, buf, g0, nb):
+        """the receive chain of one propagated group, on the receiver's context; -> the group's counts land in self.local"""
+        from . import dsp as _dsp
+        R, c = self.rx, self.rxctx
+        R['cd'].execute(work)
+        cur, extra = work, {}
+        if self.receiver == 'cohmix':
+            S = R['S']
+            if R['col'] is not None:                                # the channel's column of every realization
+                cur = R['col']
+                for b in range(self.batch):
+                    _lib.field_copy_cols(cur, b, work, b * self.setup.nfc + S.nch - 1, 1)
+            if S.ndfn:
+                _lib.field_modulate(c, cur, S.ndfn)
+            R['fo'].execute(cur)
+            _lib.cohmix_exec(c, cur, S.ecw, S.detune, S.lophase, S.balanced)
+            R['fe'].execute(cur)
+            extra = dict(sample_shift=R['shift'], peak=R['peak'])
+        extra.update(self.dsp_params)
+        passes = _dsp.dsp_count(c, cur, self.nsymb, self.nt, self.ref_patmat, buf.data_ptr(), **extra)   # (synchronises)
+        self.local[g0 - self.r0:g0 - self.r0 + nb] = buf[:nb]
+        return passes
 
     def run(self, ase_seed: int = 1):
         """-> (counts [nreal] int64 on the host, Sa*steps done by this rank)"""
         import torch
         sa_steps = 0
         self.local.zero_()
-        for g0 in range(self.r0, self.r1, self.batch):
-            torch.cuda.synchronize(self.dev)                         # torch's stream and the library's are independent
-            nb = min(self.batch, self.r1 - g0)
-            self.link.retarget(g0)
-            self.work.broadcast_from(self.tx)
-            sa_steps += self.link.run(self.work, ase_seed)
-            if self.receiver == 'blind':
-                from . import dsp as _dsp
-                self.link.cd_compensate(self.work)
-                self.passes.append(_dsp.dsp_count(self.ctx, self.work, self.nsymb, self.nt, self.ref_patmat,
-                                                  self.buf.data_ptr(), **self.dsp_params))
-            elif self.receiver == 'cohmix':
-                from . import dsp as _dsp
-                R, S = self.rx, self.rx['S']
-                self.link.cd_compensate(self.work)
-                cur = self.work
-                if R['col'] is not None:                            # the channel's column of every realization
-                    cur = R['col']
-                    for b in range(self.batch):
-                        _lib.field_copy_cols(cur, b, self.work, b * self.setup.nfc + S.nch - 1, 1)
-                if S.ndfn:
-                    _lib.field_modulate(self.ctx, cur, S.ndfn)
-                R['fo'].execute(cur)
-                _lib.cohmix_exec(self.ctx, cur, S.ecw, S.detune, S.lophase, S.balanced)
-                R['fe'].execute(cur)
-                self.passes.append(_dsp.dsp_count(self.ctx, cur, self.nsymb, self.nt, self.ref_patmat, self.buf.data_ptr(),
-                                                  sample_shift=R['shift'], peak=R['peak'], **self.dsp_params))
-            else:
-                self.link.equalize(self.work)
-                _lib.qpsk_count(self.ctx, self.work, self.sym, self.nsymb, self.nt, self.buf.data_ptr())   # writes the send buffer
-            self.ctx.sync()
-            self.local[g0 - self.r0:g0 - self.r0 + nb] = self.buf[:nb]
+        pool, pending = None, None
+        if self.pipelined:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(max_workers=1)
+        try:
+            for gi, g0 in enumerate(range(self.r0, self.r1, self.batch)):
+                nb = min(self.batch, self.r1 - g0)
+                work, buf = self.works[gi % len(self.works)], self.bufs[gi % len(self.bufs)]
+                if self.receiver == 'genie':
+                    torch.cuda.synchronize(self.dev)                 # torch's stream and the library's are independent
+                self.link.retarget(g0)
+                work.broadcast_from(self.tx)
+                sa_steps += self.link.run(work, ase_seed)            # (returns when the group is propagated)
+                if self.receiver == 'genie':
+                    self.link.equalize(work)
+                    _lib.qpsk_count(self.ctx, work, self.sym, self.nsymb, self.nt, buf.data_ptr())   # writes the send buffer
+                    self.ctx.sync()
+                    self.local[g0 - self.r0:g0 - self.r0 + nb] = buf[:nb]
+                elif pool is None:
+                    self.passes.append(self._receive(work, buf, g0, nb))
+                else:
+                    if pending is not None:                          # the other slot's receive chain ran beside this link
+                        self.passes.append(pending.result())
+                    pending = pool.submit(self._receive, work, buf, g0, nb)
+            if pending is not None:
+                self.passes.append(pending.result())
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True)
+        torch.cuda.synchronize(self.dev)
         counts = allreduce_counts(self.local, self.r0, self.nreal)
         return counts.cpu().numpy(), sa_steps
 
     def close(self):
-        for f in (self.work, self.tx):
+        for f in self.works + [self.tx]:
             f.close()
         if self.rx:
             for k in ('fo', 'fe', 'col'):
-                if self.rx[k] is not None:
+                if self.rx.get(k) is not None:
                     self.rx[k].close()
+            if self.pipelined:
+                self.rx['cd'].close()
 
 
 def run_mc(ctx: _lib.Context, setup: FiberSetup, tx_x, tx_y, sym, nsymb: int, nt: int, nspan: int, gain_db: float,

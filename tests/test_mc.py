@@ -236,6 +236,17 @@ def test_mc_with_the_blind_receiver(ctx):
         out[rec], _ = r.run(ase_seed=9)
         if rec != 'genie':
             assert len(r.passes) == nreal // batch and all(p.min() >= 1 for p in r.passes)
+            # the chain beside the next group's propagation (default) or after its own link: the same counts
+            q = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 8.0, 30.0, nreal + 1, batch, receiver=rec,
+                            dsp_params=dict(mu=1 / 2000, freqavg=200), pipeline=False)
+            seq, _ = q.run(ase_seed=9)
+            q.close()
+            q = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, nsymb, nt, nspan, 8.0, 30.0, nreal + 1, batch, receiver=rec,
+                            dsp_params=dict(mu=1 / 2000, freqavg=200))
+            par, _ = q.run(ase_seed=9)
+            par2, _ = q.run(ase_seed=9)
+            q.close()
+            assert q.pipelined and np.array_equal(seq, par) and np.array_equal(par, par2)
         r.close()
     assert out['genie'].sum() == 0
     assert out['blind'].sum() <= 8          # differential decoding doubles isolated errors; none expected here

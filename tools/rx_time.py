@@ -32,7 +32,7 @@ def timed(fn, n=1):
 
 
 r = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, bench.NSPAN, bench.GAIN_DB, bench.NF_DB, B, B,
-                receiver='cohmix')
+                receiver='cohmix', pipeline=False)
 r.link.retarget(0)
 r.work.broadcast_from(r.tx)
 t_link = timed(lambda: r.link.run(r.work, 3))
@@ -56,15 +56,17 @@ print('per batch of %d: link %.1f ms, CD compensation %.2f ms, optical filter %.
       'low-pass filter %.2f ms' % (B, t_link * 1e3, t_cd * 1e3, t_fo * 1e3, t_mix * 1e3, t_fe * 1e3), flush=True)
 keep.close()
 r.close()
-for rec, dp in (('genie', None), ('blind', None), ('cohmix', None), ('cohmix', dict(applyeasi=True)),
-                ('cohmix', dict(applyeasi=True, applypol=False))):
+for rec, dp, pipe in (('genie', None, True), ('blind', None, False), ('blind', None, True), ('cohmix', None, False),
+                      ('cohmix', None, True), ('cohmix', dict(applyeasi=True), True),
+                      ('cohmix', dict(applyeasi=True, applypol=False), True)):
     r = mc.McRunner(ctx, setup, G.FIELDX_TX, G.FIELDY_TX, sym, NSYMB, NT, bench.NSPAN, bench.GAIN_DB, bench.NF_DB, nreal, B,
-                    receiver=rec, dsp_params=dp)
+                    receiver=rec, dsp_params=dp, pipeline=pipe)
     r.run(ase_seed=3)
     t0 = time.perf_counter()
     counts, _ = r.run(ase_seed=3)
     dt = time.perf_counter() - t0
-    tag = rec + ('' if not dp else (' (combo: EASI + CMA)' if dp.get('applypol', True) else ' (EASI)'))
+    tag = rec + ('' if not dp else (' (combo: EASI + CMA)' if dp.get('applypol', True) else ' (EASI)')) + \
+        ('' if rec == 'genie' else (', chain beside the next link' if pipe else ', chain after the link'))
     print('%s receiver: %d realizations in %.2f s = %.1f realizations/s, errors in total %d, realizations with more than '
           'NSYMB/2 errors %d, first counts %s' % (tag, nreal, dt, nreal / dt, int(counts.sum()), int((counts > NSYMB // 2).sum()),
                                                     counts.tolist()[:8]), flush=True)
