@@ -7,6 +7,7 @@ B200 is visible, every compute entry point raises ``PolmuxError``.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import os
 
 import numpy as np
@@ -299,6 +300,9 @@ class Context:
             self.h = None
 
     def __del__(self):
+        # at interpreter shutdown objects die in no particular order (a context before its plans): leave them to the process exit
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
@@ -449,6 +453,9 @@ class DeviceField:
             self.h = None
 
     def __del__(self):
+        # at interpreter shutdown objects die in no particular order (a context before its plans): leave them to the process exit
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
@@ -488,6 +495,9 @@ class Plan:
             self.h = None
 
     def __del__(self):
+        # at interpreter shutdown objects die in no particular order (a context before its plans): leave them to the process exit
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
