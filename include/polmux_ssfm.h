@@ -314,6 +314,8 @@ typedef struct pmx_dsp_desc {
     double easi_mu;           /* p.easiparams.mu                                                                       */
     double easi_phizero;      /* p.easiparams.phizero                                                                  */
     int32_t* easi_passes;     /* HOST [batch] output: passes the EASI stage ran; may be NULL                           */
+    double nlr_alpha;         /* p.applynlr ? p.nlralpha : 0 -- NLRotation (dsp4cohdec.m:219-221,308-315), applied to the
+                               * sampled signals before the division by peak                                            */
 } pmx_dsp_desc;
 /* ref_patmat: HOST [nsymb][4] bytes, the differentially decoded transmitted pattern [x1 x2 y1 y2] (pat_decoder of the
  * transmitted bits); counts_dev: DEVICE [batch] int64 (e.g. the NCCL send buffer); passes_host (may be NULL): [batch]
@@ -424,6 +426,9 @@ int pmx_filter_create(pmx_ctx* ctx, int64_t nfft, int32_t nfc, int32_t batch, in
 int pmx_field_copy_cols(pmx_devfield* dst, int32_t dst_bc, const pmx_devfield* src, int32_t src_bc, int32_t count);
 int pmx_field_modulate(pmx_ctx* ctx, pmx_devfield* f, int64_t m);
 int pmx_cohmix_exec(pmx_ctx* ctx, pmx_devfield* f, double lo_ecw, double lo_detune, const double* lo_phase, int32_t balanced);
+/* p.applyadc (dsp4cohdec.m:157-162) on the currents a front-end left in f: per realization M = max |I| over its samples and
+ * currents, I <- round((I + M)/2/M*2^bits)*2*M/2^bits - M.  FP64 fields. */
+int pmx_field_quantize(pmx_ctx* ctx, pmx_devfield* f, int32_t bits);
 /* The same on host buffers in one call (what the MEX gateway binds for matlab/receiver_cohmix.m): sig = the channel's
  * column(s) x.sigx / x.sigy in time, one realization; iric: [nfft][2 or 4] column-major, as receiver_cohmix returns it;
  * avgeb (may be NULL): [2] = sum |X(band)|^2 / Nfft^2 of the two polarizations (x.avgebx, x.avgeby before the division by

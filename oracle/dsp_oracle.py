@@ -7,6 +7,8 @@ Reference code followed (all under /root/reference):
   dsp4cohdec.m:353-427   cmapolardemux: initial taps, circular extension, passes until the taps move < 5e-5
   easiadaptivefilter.m:28-61 (C twin easiadaptivefilter.c)   EASI source separation, one 2x2 tap: Y = H*x,
                          H <- (I - mu*E(Y))*H with the nonlinear error matrix E (errorfun, :55-61)
+  dsp4cohdec.m:157-162   ADC emulation: round((Irx + M)/2./M*2^bits)*2.*M/2^bits - M, M = max(max(abs(Irx)))
+  dsp4cohdec.m:308-315   NLRotation: Phases + alpha*(sum(|s|^2,2) - mean), on the sampled signals before the normalisation
   dsp4cohdec.m:428-482   easipolardemux: initial rotation, passes until the taps move < 5e-5 (at most 20*ceil(1/(L*mu)) - 1)
   dsp4cohdec.m:320-345   vitvit: M-th power, circular moving average of 2k+1 samples, (unwrapped) angle / M
   dsp4cohdec.m:241-283   carrier recovery: frequency from s.*conj(shift(s)) (navg = freqavg), phase (navg = phasavg)
@@ -135,6 +137,25 @@ def easi_polar_demux(x, mu=1 / 6000, phizero=0.0, max_passes=None):
             conv = True
         c += 1
     return y, c - 1
+
+
+def adc_quantize(irx, bits):
+    """dsp4cohdec.m:159-161 (round = half away from zero, as the interpreter's)"""
+    irx = np.asarray(irx, dtype=np.float64)
+    m = np.max(np.abs(irx))
+    v = (irx + m) / 2 / m * 2 ** bits
+    r = np.sign(v) * np.floor(np.abs(v) + 0.5)
+    return r * 2 * m / 2 ** bits - m
+
+
+def nl_rotation(s, alpha):
+    """NLRotation, dsp4cohdec.m:308-315"""
+    s = np.asarray(s, dtype=np.complex128)
+    phases, amps = np.angle(s), np.abs(s)
+    asq = np.sum(amps * amps, axis=1)
+    dp = asq - np.mean(asq)
+    phases = phases + (alpha * dp)[:, None] * np.ones((1, s.shape[1]))
+    return amps * (np.cos(phases) + 1j * np.sin(phases))
 
 
 def circ_moving_average(s, k):

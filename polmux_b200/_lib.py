@@ -33,7 +33,7 @@ EXPORTS = [
     'pmx_field_maxdiff2', 'pmx_field_lincomb', 'pmx_link_exec', 'pmx_link_run', 'pmx_field_mux', 'pmx_ampliflat_exec_pol',
     'pmx_host_is_pinned', 'pmx_scalar_adaptive_run', 'pmx_mc_run', 'pmx_mc_nccl_available',
     'pmx_ampliflat_exec_at', 'pmx_dsp_count', 'pmx_field_mean_power', 'pmx_pmd_matrix', 'pmx_field_jones', 'pmx_filter_create', 'pmx_field_copy_cols', 'pmx_field_modulate',
-    'pmx_cohmix_exec', 'pmx_field_mean_power_xy', 'pmx_cohmix_run', 'pmx_dsp_phases',
+    'pmx_cohmix_exec', 'pmx_field_mean_power_xy', 'pmx_cohmix_run', 'pmx_dsp_phases', 'pmx_field_quantize',
 ]
 
 
@@ -75,7 +75,7 @@ class DspDesc(C.Structure):
                 ('R', C.c_double * 2), ('phizero', C.c_double), ('max_passes', C.c_int32), ('modorder', C.c_int32),
                 ('freqavg', C.c_int32), ('phasavg', C.c_int32), ('poworder', C.c_int32), ('sample_shift', C.c_int32),
                 ('peak', C.c_double), ('apply_easi', C.c_int32), ('easi_max_passes', C.c_int32), ('easi_mu', C.c_double),
-                ('easi_phizero', C.c_double), ('easi_passes', C.POINTER(C.c_int32))]
+                ('easi_phizero', C.c_double), ('easi_passes', C.POINTER(C.c_int32)), ('nlr_alpha', C.c_double)]
 
 
 class McReceiver(C.Structure):
@@ -162,6 +162,7 @@ def load():
     lib.pmx_field_jones.argtypes = [vp, vp, _dp]
     lib.pmx_field_copy_cols.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int32]
     lib.pmx_field_modulate.argtypes = [vp, vp, C.c_int64]
+    lib.pmx_field_quantize.argtypes = [vp, vp, C.c_int32]
     lib.pmx_cohmix_exec.argtypes = [vp, vp, C.c_double, C.c_double, _dp, C.c_int32]
     lib.pmx_filter_create.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int32, C.POINTER(vp)]
     lib.pmx_field_maxdiff2.argtypes = [vp, vp, vp, _dp]
@@ -205,6 +206,11 @@ def pmd_matrix(ctx, nfft, brfs, mat=None, gvd=True, want_u=True, want_uinv=True)
 def field_copy_cols(dst, dst_bc, src, src_bc, count=1):
     """count realization-columns of src (from src_bc) -> dst (from dst_bc), device to device"""
     dst.ctx.check(dst.ctx.lib.pmx_field_copy_cols(dst.h, int(dst_bc), src.h, int(src_bc), int(count)))
+
+
+def field_quantize(ctx, field, bits):
+    """ADC with `bits` bits on the currents in `field` (pmx_field_quantize, dsp4cohdec.m:157-162)"""
+    ctx.check(ctx.lib.pmx_field_quantize(ctx.h, field.h, int(bits)))
 
 
 def field_modulate(ctx, field, m):

@@ -1678,39 +1678,61 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
 // centre delayed by the receiver's filters for its currents (fastshift(Irx, round(-delay*NT)), dsp4cohdec.m:167-169);
 // divided by `peak` (dsp4cohdec.m:226-227) or, with peak = 0, by sqrt(mean |s|^2 over both polarizations)
 __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t N, int l1, int l2, int nsymb, int nt,
-                                                        long long shift, double peak, cpx* sig) {
+                                                        long long shift, double peak, double nlr_alpha, cpx* sig) {
     __shared__ double red[256];
     const int b = blockIdx.x;
     const cpx* fld = field + (size_t)b * N * 2;
+    cpx* sx = sig + ((size_t)b * 2 + 0) * nsymb;
+    cpx* sy = sig + ((size_t)b * 2 + 1) * nsymb;
     auto at = [&](int k) { return pmx_mem_index((size_t)(((long long)k * nt + shift) & (long long)(N - 1)), l1, l2); };
     PMX_ASSERT(shift >= 0 && (size_t)shift < N && (size_t)nsymb * nt == N && at(nsymb - 1) < N);
-    double inv;
-    if (peak > 0.0) {
-        inv = 1.0 / peak;
-    } else {
-        double acc = 0.0;
-        for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
-            const size_t m = at(k);
-            const cpx x = fld[2 * m], y = fld[2 * m + 1];
-            acc += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
-        }
-        red[threadIdx.x] = acc;
+    auto block_sum = [&](double v) {   // fixed tree: the same result on every run
         __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {   // fixed tree: the same result on every run
+        red[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
             if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
             __syncthreads();
         }
-        inv = 1.0 / sqrt(red[0] / (2.0 * nsymb));
-    }
+        return red[0];
+    };
+    double acc = 0.0;
     for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
         const size_t m = at(k);
         const cpx x = fld[2 * m], y = fld[2 * m + 1];
-        if (peak > 0.0) {   // Signals/peak: a division in the reference
-            sig[((size_t)b * 2 + 0) * nsymb + k] = make_double2(x.x / peak, x.y / peak);
-            sig[((size_t)b * 2 + 1) * nsymb + k] = make_double2(y.x / peak, y.y / peak);
-        } else {
-            sig[((size_t)b * 2 + 0) * nsymb + k] = make_double2(x.x * inv, x.y * inv);
-            sig[((size_t)b * 2 + 1) * nsymb + k] = make_double2(y.x * inv, y.y * inv);
+        sx[k] = x;
+        sy[k] = y;
+        acc += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
+    }
+    if (nlr_alpha != 0.0) {
+        // NLRotation (dsp4cohdec.m:308-315), before the normalisation as in the reference: Phases + alpha*(Asquare - mean(Asquare)),
+        // Asquare = |s_x|^2 + |s_y|^2 of the symbol
+        double asq = 0.0;
+        for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
+            const double ax = hypot(sx[k].x, sx[k].y), ay = hypot(sy[k].x, sy[k].y);
+            asq += ax * ax + ay * ay;
+        }
+        const double mean = block_sum(asq) / (double)nsymb;
+        for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
+            const double ax = hypot(sx[k].x, sx[k].y), ay = hypot(sy[k].x, sy[k].y);
+            const double dp = nlr_alpha * ((ax * ax + ay * ay) - mean);
+            double sn, cs;
+            sincos(atan2(sx[k].y, sx[k].x) + dp, &sn, &cs);
+            sx[k] = make_double2(ax * cs, ax * sn);
+            sincos(atan2(sy[k].y, sy[k].x) + dp, &sn, &cs);
+            sy[k] = make_double2(ay * cs, ay * sn);
+        }
+    }
+    if (peak > 0.0) {   // Signals/peak: a division in the reference (dsp4cohdec.m:226-227)
+        for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
+            sx[k] = make_double2(sx[k].x / peak, sx[k].y / peak);
+            sy[k] = make_double2(sy[k].x / peak, sy[k].y / peak);
+        }
+    } else {
+        const double inv = 1.0 / sqrt(block_sum(acc) / (2.0 * nsymb));
+        for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
+            sx[k] = make_double2(sx[k].x * inv, sx[k].y * inv);
+            sy[k] = make_double2(sy[k].x * inv, sy[k].y * inv);
         }
     }
 }
@@ -2169,7 +2191,8 @@ static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const ui
     {
         const long long N = (long long)f->nfft;
         const long long sh = (((long long)d->sample_shift % N) + N) % N;
-        pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sh, d->peak, sig);
+        pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sh, d->peak, d->nlr_alpha,
+                                                  sig);
     }
     const cpx* stream_in = sig;
     cpx* stage_out = y;
@@ -2779,6 +2802,48 @@ extern "C" int pmx_cohmix_exec(pmx_ctx* c, pmx_devfield* f, double lo_ecw, doubl
         cudaFreeAsync(dph, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // lo_phase is the caller's pageable memory
     }
+    CK(c, e);
+    return PMX_OK;
+}
+
+// ADC with a finite number of bits (dsp4cohdec.m:157-162) on the currents of a realization: M = max over its samples and
+// currents of |I|, then I <- round((I + M)/2/M*2^bits)*2*M/2^bits - M, the interpreter's order of operations
+__global__ void __launch_bounds__(256) pmx_k_adc_max(const cpx* field, size_t n_cpx, unsigned long long* out) {
+    const cpx* fld = field + (size_t)blockIdx.y * n_cpx;
+    unsigned long long vmax = 0ull;
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_cpx; n += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = pmx_pow_key(fmax(fabs(fld[n].x), fabs(fld[n].y)));
+        vmax = k > vmax ? k : vmax;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, vmax, o);
+        vmax = other > vmax ? other : vmax;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(&out[blockIdx.y], vmax);
+}
+__global__ void __launch_bounds__(256) pmx_k_adc_quant(cpx* field, size_t n_cpx, const double* maxv, double levels) {
+    cpx* fld = field + (size_t)blockIdx.y * n_cpx;
+    const double M = maxv[blockIdx.y];
+    auto q = [&](double v) { return round((v + M) / 2 / M * levels) * 2 * M / levels - M; };
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_cpx; n += (size_t)gridDim.x * blockDim.x)
+        fld[n] = make_double2(q(fld[n].x), q(fld[n].y));
+}
+
+extern "C" int pmx_field_quantize(pmx_ctx* c, pmx_devfield* f, int32_t bits) {
+    int rc = need_f64(c, f, "pmx_field_quantize");
+    if (rc) return rc;
+    if (bits < 1 || bits > 52) return set_err(c, PMX_ERR_INVALID, "pmx_field_quantize: bits must be 1..52");
+    CK(c, cudaSetDevice(c->device));
+    const size_t n_cpx = (size_t)f->nfc * f->nfft * 2;
+    unsigned long long* d = nullptr;
+    CK(c, cudaMallocAsync(&d, f->batch * sizeof(unsigned long long), c->stream));
+    CK(c, cudaMemsetAsync(d, 0, f->batch * sizeof(unsigned long long), c->stream));
+    dim3 g((unsigned)std::min<size_t>((n_cpx + 255) / 256, 148 * 4), f->batch);
+    pmx_k_adc_max<<<g, 256, 0, c->stream>>>(f->data, n_cpx, d);
+    pmx_k_adc_quant<<<g, 256, 0, c->stream>>>(f->data, n_cpx, reinterpret_cast<const double*>(d), ldexp(1.0, bits));   // key == bit pattern
+    c->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d, c->stream);
     CK(c, e);
     return PMX_OK;
 }

@@ -14,7 +14,7 @@ from . import _lib
 
 DEFAULTS = dict(applypol=True, taps=7, mu=1 / 6000, R=(1.0, 1.0), phizero=0.0, max_passes=0, modorder=2, freqavg=500,
                 phasavg=3, poworder=2, sample_shift=0, peak=0.0, applyeasi=False, easi_mu=1 / 6000, easi_phizero=0.0,
-                easi_max_passes=0)
+                easi_max_passes=0, nlr_alpha=0.0)
 
 
 def reference_pattern(sym_x, sym_y):
@@ -42,6 +42,7 @@ def _desc(nsymb, nt, params, easi_passes=None):
     d.sample_shift, d.peak = int(p['sample_shift']), float(p['peak'])
     d.apply_easi, d.easi_mu, d.easi_phizero = int(bool(p['applyeasi'])), float(p['easi_mu']), float(p['easi_phizero'])
     d.easi_max_passes = int(p['easi_max_passes'])
+    d.nlr_alpha = float(p['nlr_alpha'])
     if easi_passes is not None:
         d.easi_passes = easi_passes.ctypes.data_as(C.POINTER(C.c_int32))
     return d
@@ -69,14 +70,13 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
     Differences stated in DESIGN.md: x.delay must be 'theory' (the pattern-correlation search of mygeteyeinfo is not
     built, so `pat` only tells the number of polarizations and worsteyeop is not returned), the decimator (`decimate`, a
     Signal Processing Toolbox function outside the reference tree) is replaced by plain sampling at the symbol centres;
-    p.applyadc / applydcf / applynlr and the 'singlepol' demultiplexer raise ('cma', 'easi' and 'combo' are built)."""
+    p.applydcf and the 'singlepol' demultiplexer raise (p.applyadc, p.applynlr, 'cma', 'easi' and 'combo' are built)."""
     from . import receiver as _rx
     from .gstate import GSTATE as G
     if x.get('rec', 'coherent') != 'coherent':
         raise ValueError("Flag X.rec must be 'coherent'")                       # dsp4cohdec.m:143
-    for k in ('applyadc', 'applydcf', 'applynlr'):
-        if p.get(k):
-            raise NotImplementedError('dsp4cohdec: p.%s is not built' % k)
+    if p.get('applydcf'):   # (a post-compensating all-pass fiber is available through x.dpost, receiver_cohmix.m:139-166)
+        raise NotImplementedError('dsp4cohdec: p.applydcf is not built')
     method = str(p.get('polmethod', 'cma')).lower()
     if p.get('applypol') and method not in ('cma', 'easi', 'combo'):
         if method == 'singlepol':
@@ -91,6 +91,8 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
     ctx = ctx or _lib.default_context()
     col, S, xo = _rx.front_end(ich, x, ctx)
     try:
+        if p.get('applyadc'):                                                   # dsp4cohdec.m:157-162
+            _lib.field_quantize(ctx, col, int(p['adcbits']))
         if 'b2b' in x:
             avgdelay = 0.0                                                      # mygeteyeinfo, dsp4cohdec.m:491-493
         else:
@@ -106,6 +108,7 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
                       R=tuple(cma.get('R', (1.0, 1.0))), phizero=float(cma.get('phizero', 0.0)),
                       modorder=2, freqavg=int(p.get('freqavg', 500)), phasavg=int(p.get('phasavg', 3)),
                       poworder=int(p.get('poworder', 2)), sample_shift=int(round(delay * G.NT)),
+                      nlr_alpha=float(p['nlralpha']) if p.get('applynlr') else 0.0,
                       peak=4.0 * math.sqrt(float(np.asarray(G.POWER).ravel()[ich - 1])))
         ph, am, _ = dsp_phases(ctx, col, G.NSYMB, G.NT, **params)
     finally:

@@ -273,6 +273,8 @@ class McRunner:
             R['fe'].execute(cur)
             extra = dict(sample_shift=R['shift'], peak=R['peak'])
         extra.update(self.dsp_params)
+        if extra.pop('adcbits', None):                              # p.applyadc (dsp4cohdec.m:157-162)
+            _lib.field_quantize(c, cur, int(self.dsp_params['adcbits']))
         passes = _dsp.dsp_count(c, cur, self.nsymb, self.nt, self.ref_patmat, buf.data_ptr(), **extra)   # (synchronises)
         self.local[g0 - self.r0:g0 - self.r0 + nb] = buf[:nb]
         return passes

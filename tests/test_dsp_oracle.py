@@ -83,6 +83,32 @@ def test_easipolardemux_matches_reference_source():
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-11)
 
 
+def test_nlrotation_matches_reference_source():
+    x, _ = _signals(128, 7)
+    x = x * (1 + 0.3 * np.random.Generator(np.random.PCG64(8)).standard_normal((128, 1)))
+    it = Interp(REF)
+    ref = _local(it, 'NLRotation', [x, to_m(0.37)])[0]
+    np.testing.assert_allclose(dsp.nl_rotation(x, 0.37), ref, rtol=0, atol=1e-14)
+
+
+def test_adc_emulation_matches_reference_source():
+    """the ADC lines of dsp4cohdec.m sit in its main body: they are cut out of the file as text and executed"""
+    import re
+    from oracle.mini_m.interp import Parser, tokenize
+    src = open(os.path.join(REF, 'dsp4cohdec.m'), encoding='latin-1').read()
+    m = re.search(r"if p\.applyadc(.*?)\nend", src, re.S)
+    assert m and 'round' in m.group(1)
+    fn = 'function Irx = adcwrap(Irx, p)\n' + m.group(1) + '\n'
+    f = Parser(tokenize(fn), 'adcwrap.m').parse_file()[0]
+    it = Interp(REF)
+    irx = np.random.Generator(np.random.PCG64(9)).standard_normal((200, 4)) * 3.0
+    for bits in (3, 5, 8):
+        ref = it.run_function(f, [irx, MStruct({'adcbits': to_m(bits)})], 1, {'adcwrap': f})[0]
+        got = dsp.adc_quantize(irx, bits)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-15)
+        assert len(np.unique(np.round(got, 12))) <= 2 ** bits + 1
+
+
 def test_decision_and_differential_decoding_match_reference_source():
     g = np.random.Generator(np.random.PCG64(4))
     phase = g.uniform(-np.pi, np.pi, (64, 2))

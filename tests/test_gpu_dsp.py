@@ -182,6 +182,19 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
         dsp.dsp4cohdec(1, pat, dict(x, delay='estimate'), p)
     with pytest.raises(NotImplementedError, match='applydcf'):
         dsp.dsp4cohdec(1, pat, x, dict(p, applydcf=True))
+    # p.applyadc (5 bits) and p.applynlr: the same chain with the oracle's ADC on the currents and NLRotation on the sampled,
+    # not yet normalised signals
+    p2 = dict(p, applyadc=True, adcbits=5, applynlr=True, nlralpha=0.02)
+    ph2, am2 = dsp.dsp4cohdec(1, pat, x, p2)
+    iq = dsp_orc.adc_quantize(iric, 5)
+    s2 = np.stack([iq[idx, 0] + 1j * iq[idx, 1], iq[idx, 2] + 1j * iq[idx, 3]], axis=1)
+    s2 = dsp_orc.nl_rotation(s2, 0.02) / (4 * math.sqrt(float(G.POWER[0])))
+    y2, _ = dsp_orc.cma_polar_demux(s2, mu=1 / 2000, taps=7)
+    want2 = dsp_orc.carrier_recovery(y2, 2, 200, 3, 2)
+    np.testing.assert_allclose(am2, np.abs(y2), rtol=1e-9, atol=1e-12)
+    away = np.abs(np.abs(want2) - math.pi) > 1e-6
+    np.testing.assert_allclose(ph2[away], want2[away], rtol=0, atol=1e-9)
+    assert not np.allclose(am2, amps)
 
 
 @pytest.mark.parametrize('method', ['easi', 'combo'])
