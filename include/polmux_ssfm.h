@@ -338,7 +338,8 @@ int pmx_dsp_phases(pmx_ctx* ctx, pmx_devfield* f, const pmx_dsp_desc* dsp, doubl
  * The caller replays ber_estimate's recursion (ber_estimate.m:121-127) over counts[] in realization order. */
 /* The reference's receive chain behind the link of a Monte-Carlo job (ex20_coherent_polmux.m:151-176): receiver_cohmix's
  * front-end, the sampler and the DSP core, per resident batch.  hf_opt already carries whatever all-pass compensation the
- * receiver applies (x.dpost, receiver_cohmix.m:139-166, or p.applydcf).  Single-column ('unique') FP64 fields. */
+ * receiver applies (x.dpost, receiver_cohmix.m:139-166, or p.applydcf).  Single-column ('unique') FP64 fields.  The chain of
+ * a group runs on a context (stream) and host thread of its own beside the propagation of the next group. */
 typedef struct pmx_mc_receiver {
     const double* hf_opt;      /* [nfft] complex: post fiber .* optical filter                              */
     const double* hf_el;       /* [nfft] complex: low-pass filter as myfilter returns it                    */

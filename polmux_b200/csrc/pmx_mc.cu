@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -65,9 +66,12 @@ struct Worker {
 
 // realizations [r0, r1) on one device
 void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, const pmx_mc_desc& m, const pmx_field& tx) {
-    pmx_devfield *ftx = nullptr, *work = nullptr;
+    pmx_devfield *ftx = nullptr, *work = nullptr, *work2 = nullptr;
     pmx_plan *plan = nullptr, *inv = nullptr, *fo = nullptr, *fe = nullptr;
-    int64_t* tmp = nullptr;
+    pmx_ctx* rxctx = nullptr;   // the receive chain's own context (stream): it runs beside the next group's propagation
+    int64_t *tmp = nullptr, *tmp2 = nullptr;
+    std::future<int> pending;
+    std::string rxerr;
     const int B = m.batch, np = fd.nplates, nspan = m.nspan, nfc = fd.nfc;
     const size_t span_stride = (size_t)m.nreal * np;
     std::vector<double> pl[3], ipl[3], nb1, nb2, nbt, ndb1;
@@ -151,7 +155,22 @@ void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, con
                 w.err = "the receive chain takes single-column FP64 fields, both filter responses and the reference pattern";
                 goto done;
             }
-            MC_CK(pmx_filter_create(w.ctx, fd.nfft, 1, B, PMX_F64, m.rx->hf_opt, 1, &fo));
+            if (pmx_ctx_create(&rxctx, dev) != PMX_OK) {
+                w.rc = PMX_ERR_CUDA;
+                w.err = std::string("pmx_ctx_create (receive chain): ") + pmx_last_error(nullptr);
+                goto done;
+            }
+            MC_CK(pmx_field_create(w.ctx, fd.nfft, nfc, B, fd.precision, &work2));
+            if (cudaMalloc(&tmp2, (size_t)B * sizeof(int64_t)) != cudaSuccess) {
+                w.rc = PMX_ERR_CUDA;
+                w.err = "count buffers: out of device memory";
+                goto done;
+            }
+            if (pmx_filter_create(rxctx, fd.nfft, 1, B, PMX_F64, m.rx->hf_opt, 1, &fo) != PMX_OK) {
+                w.rc = PMX_ERR_CUDA;
+                w.err = std::string("pmx_filter_create: ") + pmx_last_error(rxctx);
+                goto done;
+            }
             std::vector<double> hh(2 * (size_t)fd.nfft);   // Hermitian part: two real currents on one complex transform
             const size_t N = (size_t)fd.nfft;
             for (size_t k = 0; k < N; ++k) {
@@ -159,12 +178,18 @@ void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, con
                 hh[2 * k] = 0.5 * (m.rx->hf_el[2 * k] + m.rx->hf_el[2 * mk]);
                 hh[2 * k + 1] = 0.5 * (m.rx->hf_el[2 * k + 1] - m.rx->hf_el[2 * mk + 1]);
             }
-            MC_CK(pmx_filter_create(w.ctx, fd.nfft, 1, B, PMX_F64, hh.data(), 1, &fe));
+            if (pmx_filter_create(rxctx, fd.nfft, 1, B, PMX_F64, hh.data(), 1, &fe) != PMX_OK) {
+                w.rc = PMX_ERR_CUDA;
+                w.err = std::string("pmx_filter_create: ") + pmx_last_error(rxctx);
+                goto done;
+            }
         }
-        for (int g0 = r0; g0 < r1; g0 += B) {
+        for (int g0 = r0, gi = 0; g0 < r1; g0 += B, ++gi) {
             const int nb = std::min(B, r1 - g0);
+            pmx_devfield* const cur = (m.rx && (gi & 1)) ? work2 : work;   // two work fields alternate under the receive chain
+            int64_t* const ctmp = (m.rx && (gi & 1)) ? tmp2 : tmp;
             if (g0 != r0) gather(g0);
-            MC_CK(pmx_field_broadcast(work, ftx));
+            MC_CK(pmx_field_broadcast(cur, ftx));
             for (int k = 0; k < nspan; ++k)   // the seed convention of polmux_b200.mc.Link.ase_seed
                 seeds[k] = ((m.ase_seed & 0xffffffull) << 40) + ((uint64_t)k << 32);
             pmx_link_desc l;
@@ -181,7 +206,7 @@ void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, con
             pmx_fiber_result res;
             memset(&res, 0, sizeof res);
             res.ncycle = ncyc.data();
-            MC_CK(pmx_link_exec(plan, work, &l, &res));
+            MC_CK(pmx_link_exec(plan, cur, &l, &res));
             for (int k = 0; k < nspan; ++k)
                 for (int b = 0; b < nb; ++b) w.sa_steps += (long long)ncyc[(size_t)k * B + b] * fd.nfft * nfc;
             if (inv) {
@@ -194,34 +219,64 @@ void run_shard(Worker& w, int dev, int r0, int r1, const pmx_fiber_desc& fd, con
                             ipl[2][t] = pl[2][s];
                         }
                     MC_CK(pmx_plan_set_plates(inv, B, ipl[0].data(), ipl[1].data(), ipl[2].data()));
-                    MC_CK(pmx_fiber_exec(inv, work, nullptr));
+                    MC_CK(pmx_fiber_exec(inv, cur, nullptr));
                 }
             }
             // the error counter writes the group's counts; they land in this rank's slice of the NCCL send buffer
             if (m.rx) {
-                MC_CK(pmx_fiber_exec(fo, work, nullptr));
-                MC_CK(pmx_cohmix_exec(w.ctx, work, m.rx->lo_ecw, m.rx->lo_detune, m.rx->lo_phase, m.rx->balanced));
-                MC_CK(pmx_fiber_exec(fe, work, nullptr));
-                MC_CK(pmx_dsp_count(w.ctx, work, &m.rx->dsp, m.rx->ref_patmat, tmp, nullptr));
-            } else {
-                MC_CK(pmx_qpsk_count(w.ctx, work, m.sym, m.nsymb, m.nt, tmp));
+                // the previous group's chain ran beside this group's link; now this group's chain starts beside the next link
+                if (pending.valid() && pending.get() != PMX_OK) {
+                    w.rc = PMX_ERR_CUDA;
+                    w.err = rxerr;
+                    goto done;
+                }
+                int64_t* const dst = w.counts_dev + g0;
+                pending = std::async(std::launch::async, [=, &m, &rxerr]() -> int {
+                    int rc = pmx_fiber_exec(fo, cur, nullptr);
+                    if (rc == PMX_OK) rc = pmx_cohmix_exec(rxctx, cur, m.rx->lo_ecw, m.rx->lo_detune, m.rx->lo_phase, m.rx->balanced);
+                    if (rc == PMX_OK) rc = pmx_fiber_exec(fe, cur, nullptr);
+                    if (rc == PMX_OK) rc = pmx_dsp_count(rxctx, cur, &m.rx->dsp, m.rx->ref_patmat, ctmp, nullptr);
+                    if (rc == PMX_OK) {
+                        cudaStream_t rs = (cudaStream_t)pmx_ctx_stream(rxctx);
+                        if (cudaMemcpyAsync(dst, ctmp, (size_t)nb * sizeof(int64_t), cudaMemcpyDeviceToDevice, rs) != cudaSuccess ||
+                            cudaStreamSynchronize(rs) != cudaSuccess) {
+                            rxerr = "count copy failed";
+                            return PMX_ERR_CUDA;
+                        }
+                    } else {
+                        rxerr = std::string("receive chain: ") + pmx_last_error(rxctx);
+                    }
+                    return rc;
+                });
+                continue;
             }
-            if (cudaMemcpyAsync(w.counts_dev + g0, tmp, (size_t)nb * sizeof(int64_t), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            // the error counter writes the group's counts; they land in this rank's slice of the NCCL send buffer
+            MC_CK(pmx_qpsk_count(w.ctx, cur, m.sym, m.nsymb, m.nt, ctmp));
+            if (cudaMemcpyAsync(w.counts_dev + g0, ctmp, (size_t)nb * sizeof(int64_t), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
                 w.rc = PMX_ERR_CUDA;
                 w.err = "count copy failed";
                 goto done;
             }
         }
+        if (pending.valid() && pending.get() != PMX_OK) {
+            w.rc = PMX_ERR_CUDA;
+            w.err = rxerr;
+            goto done;
+        }
         MC_CK(pmx_ctx_sync(w.ctx));
     }
 done:
+    if (pending.valid()) pending.wait();   // (an error path: the chain must not outlive its buffers)
     if (tmp) cudaFree(tmp);
+    if (tmp2) cudaFree(tmp2);
     pmx_plan_destroy(fo);
     pmx_plan_destroy(fe);
     pmx_plan_destroy(inv);
     pmx_plan_destroy(plan);
     pmx_field_destroy(work);
+    pmx_field_destroy(work2);
     pmx_field_destroy(ftx);
+    if (rxctx) pmx_ctx_destroy(rxctx);
 }
 }  // namespace
 
