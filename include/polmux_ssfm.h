@@ -317,6 +317,9 @@ typedef struct pmx_dsp_desc {
     int32_t* easi_passes;     /* HOST [batch] output: passes the EASI stage ran; may be NULL                           */
     double nlr_alpha;         /* p.applynlr ? p.nlralpha : 0 -- NLRotation (dsp4cohdec.m:219-221,308-315), applied to the
                                * sampled signals before the division by peak                                            */
+    const double* dcf_h;      /* p.applydcf: HOST [nsymb] complex Hfilt of DispCompFilter (dsp4cohdec.m:289-297) applied to the
+                               * sampled signals, ifft(fft(Signals).*Hfilt) (:198-210), before the rotation above; or NULL;
+                               * nsymb must then be a power of two >= 64                                                  */
 } pmx_dsp_desc;
 /* ref_patmat: HOST [nsymb][4] bytes, the differentially decoded transmitted pattern [x1 x2 y1 y2] (pat_decoder of the
  * transmitted bits); counts_dev: DEVICE [batch] int64 (e.g. the NCCL send buffer); passes_host (may be NULL): [batch]

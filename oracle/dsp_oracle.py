@@ -8,6 +8,8 @@ Reference code followed (all under /root/reference):
   easiadaptivefilter.m:28-61 (C twin easiadaptivefilter.c)   EASI source separation, one 2x2 tap: Y = H*x,
                          H <- (I - mu*E(Y))*H with the nonlinear error matrix E (errorfun, :55-61)
   dsp4cohdec.m:157-162   ADC emulation: round((Irx + M)/2./M*2^bits)*2.*M/2^bits - M, M = max(max(abs(Irx)))
+  dsp4cohdec.m:198-210,289-297   digital dispersion compensation: DispCompFilter (ideal all-pass response, impulse response
+                         truncated to FilterLength+1 taps, the delay taken out again) and ifft(fft(Signals).*Hfilt)
   dsp4cohdec.m:308-315   NLRotation: Phases + alpha*(sum(|s|^2,2) - mean), on the sampled signals before the normalisation
   dsp4cohdec.m:428-482   easipolardemux: initial rotation, passes until the taps move < 5e-5 (at most 20*ceil(1/(L*mu)) - 1)
   dsp4cohdec.m:320-345   vitvit: M-th power, circular moving average of 2k+1 samples, (unwrapped) angle / M
@@ -137,6 +139,26 @@ def easi_polar_demux(x, mu=1 / 6000, phizero=0.0, max_passes=None):
             conv = True
         c += 1
     return y, c - 1
+
+
+def disp_comp_filter(beta2l, bw, n, flen):
+    """DispCompFilter, dsp4cohdec.m:289-297 -> Hfilt [n]"""
+    freq = -bw / 2 + np.arange(n) * (bw / n)              # ( -B/2 : B/N : B/2*(N-2)/N )
+    freq = np.fft.ifftshift(freq)
+    delay = 2 * math.pi * freq / bw * (flen / 2)
+    argum = (2 * math.pi * freq) ** 2 * beta2l / 2 - delay
+    h = np.cos(argum) + 1j * np.sin(argum)
+    b = np.fft.ifft(h)[:int(flen) + 1]
+    return np.fft.fft(b, n) * (np.cos(delay) + 1j * np.sin(delay))
+
+
+def apply_dcf(signals, dispersion, lam, baudrate, ndispsym, workatbaudrate=True):
+    """dsp4cohdec.m:198-210"""
+    beta2l = -dispersion * lam ** 2 / 2 / math.pi / 299792458.0 * 1e-21
+    sps = 1 + (0 if workatbaudrate else 1)
+    s = np.asarray(signals, dtype=np.complex128)
+    h = disp_comp_filter(beta2l, sps * baudrate, s.shape[0], ndispsym * sps)
+    return np.fft.ifft(np.fft.fft(s, axis=0) * h[:, None], axis=0)
 
 
 def adc_quantize(irx, bits):

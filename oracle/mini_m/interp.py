@@ -1281,6 +1281,7 @@ _simple('ifft', _fftn(sfft.ifft))
 _simple('unwrap', lambda x: np.unwrap(num(x), axis=(1 if num(x).shape[0] == 1 else 0)))
 _simple('cumsum', lambda x: np.cumsum(num(x), axis=(1 if num(x).shape[0] == 1 else 0)))
 _simple('fftshift', lambda x: np.fft.fftshift(num(x), axes=(1 if num(x).shape[0] == 1 else 0)))
+_simple('ifftshift', lambda x: np.fft.ifftshift(num(x), axes=(1 if num(x).shape[0] == 1 else 0)))
 _simple('flipud', lambda x: num(x)[::-1, :])
 _simple('fliplr', lambda x: num(x)[:, ::-1])
 _simple('isempty', lambda x: np.array([[(len(x) == 0) if isinstance(x, (str, MCell, MStruct)) else arr(x).size == 0]]))

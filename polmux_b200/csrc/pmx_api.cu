@@ -1678,7 +1678,7 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
 // centre delayed by the receiver's filters for its currents (fastshift(Irx, round(-delay*NT)), dsp4cohdec.m:167-169);
 // divided by `peak` (dsp4cohdec.m:226-227) or, with peak = 0, by sqrt(mean |s|^2 over both polarizations)
 __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t N, int l1, int l2, int nsymb, int nt,
-                                                        long long shift, double peak, double nlr_alpha, cpx* sig) {
+                                                        long long shift, double peak, double nlr_alpha, int raw, cpx* sig) {
     __shared__ double red[256];
     const int b = blockIdx.x;
     const cpx* fld = field + (size_t)b * N * 2;
@@ -1704,6 +1704,7 @@ __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t
         sy[k] = y;
         acc += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
     }
+    if (raw) return;   // the samples as they are: a dispersion-compensating filter comes first (dsp4cohdec.m:198-210)
     if (nlr_alpha != 0.0) {
         // NLRotation (dsp4cohdec.m:308-315), before the normalisation as in the reference: Phases + alpha*(Asquare - mean(Asquare)),
         // Asquare = |s_x|^2 + |s_y|^2 of the symbol
@@ -2157,6 +2158,19 @@ __global__ void __launch_bounds__(256) pmx_k_dsp_abs(const cpx* s, size_t n, dou
         out[i] = hypot(s[i].x, s[i].y);
 }
 
+// the two sampled streams of a realization as the two polarizations of a field of L samples (field layout)
+__global__ void __launch_bounds__(256) pmx_k_dsp_pack(const cpx* sig, int L, int l1, int l2, cpx* field) {
+    const int b = blockIdx.y;
+    const cpx* sx = sig + ((size_t)b * 2 + 0) * L;
+    const cpx* sy = sig + ((size_t)b * 2 + 1) * L;
+    cpx* fld = field + (size_t)b * L * 2;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+        const size_t m = pmx_mem_index((size_t)k, l1, l2);
+        fld[2 * m] = sx[k];
+        fld[2 * m + 1] = sy[k];
+    }
+}
+
 // sampler, polarization demultiplexer, carrier recovery; then either the decision + count (ref_patmat, counts_dev) or the
 // phases / amplitudes handed back to the host (phases, amps: [batch][2][nsymb])
 static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const uint8_t* ref_patmat, int64_t* counts_dev,
@@ -2192,7 +2206,35 @@ static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const ui
         const long long N = (long long)f->nfft;
         const long long sh = (((long long)d->sample_shift % N) + N) % N;
         pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sh, d->peak, d->nlr_alpha,
-                                                  sig);
+                                                  d->dcf_h ? 1 : 0, sig);
+    }
+    if (d->dcf_h) {
+        // p.applydcf: Signals = ifft(fft(Signals) .* Hfilt) on the sampled signals (dsp4cohdec.m:198-210), before the
+        // non-linear rotation and the normalisation.  The two streams of a realization become the polarizations of a field
+        // of nsymb samples, a filter plan does the rest; the sampler then runs again over that field (one sample per symbol).
+        pmx_devfield* tf = nullptr;
+        pmx_plan* fp = nullptr;
+        int rc = pmx_field_create(c, L, 1, B, PMX_F64, &tf);
+        if (rc == PMX_OK) rc = pmx_filter_create(c, L, 1, B, PMX_F64, d->dcf_h, 1, &fp);
+        if (rc == PMX_OK) {
+            pmx_k_dsp_pack<<<dim3((unsigned)std::min((L + 255) / 256, 64), B), 256, 0, c->stream>>>(sig, L, tf->log2N1, tf->log2N2, tf->data);
+            c->launches++;
+            rc = pmx_fiber_exec(fp, tf, nullptr);
+        }
+        if (rc == PMX_OK) {
+            pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(tf->data, (size_t)L, tf->log2N1, tf->log2N2, L, 1, 0, d->peak, d->nlr_alpha, 0, sig);
+            c->launches++;
+            if (cudaGetLastError() != cudaSuccess) rc = set_err(c, PMX_ERR_CUDA, "%s: dispersion-compensation kernels failed", who);
+        }
+        std::string keep = c->error;
+        pmx_plan_destroy(fp);
+        pmx_field_destroy(tf);
+        if (rc != PMX_OK) {
+            c->error = keep;
+            for (void* q : {(void*)sig, (void*)y, (void*)w1, (void*)w2, (void*)om, (void*)ph, (void*)dref, (void*)acc, (void*)dpass})
+                cudaFreeAsync(q, c->stream);
+            return rc;
+        }
     }
     const cpx* stream_in = sig;
     cpx* stage_out = y;

@@ -14,7 +14,7 @@ from . import _lib
 
 DEFAULTS = dict(applypol=True, taps=7, mu=1 / 6000, R=(1.0, 1.0), phizero=0.0, max_passes=0, modorder=2, freqavg=500,
                 phasavg=3, poworder=2, sample_shift=0, peak=0.0, applyeasi=False, easi_mu=1 / 6000, easi_phizero=0.0,
-                easi_max_passes=0, nlr_alpha=0.0)
+                easi_max_passes=0, nlr_alpha=0.0, dcf_h=None)
 
 
 def reference_pattern(sym_x, sym_y):
@@ -32,6 +32,17 @@ def reference_pattern(sym_x, sym_y):
     return np.ascontiguousarray(np.stack(out, axis=1), dtype=np.uint8)
 
 
+def disp_comp_filter(beta2l, bw, n, flen):
+    """Hfilt = DispCompFilter(Beta2L, B, N, FilterLength), dsp4cohdec.m:289-297: the all-pass response of the dispersion to
+    undo, its impulse response truncated to FilterLength + 1 taps, the filter's delay taken out again.  Host set-up (a
+    filter design: two length-N transforms, once per receiver), like the evaluation of myfilter."""
+    freq = np.fft.ifftshift(-bw / 2 + np.arange(n) * (bw / n))
+    delay = 2 * math.pi * freq / bw * (flen / 2)
+    argum = (2 * math.pi * freq) ** 2 * beta2l / 2 - delay
+    b = np.fft.ifft(np.cos(argum) + 1j * np.sin(argum))[:int(flen) + 1]
+    return np.fft.fft(b, n) * (np.cos(delay) + 1j * np.sin(delay))
+
+
 def _desc(nsymb, nt, params, easi_passes=None):
     p = dict(DEFAULTS)
     p.update(params)
@@ -43,6 +54,12 @@ def _desc(nsymb, nt, params, easi_passes=None):
     d.apply_easi, d.easi_mu, d.easi_phizero = int(bool(p['applyeasi'])), float(p['easi_mu']), float(p['easi_phizero'])
     d.easi_max_passes = int(p['easi_max_passes'])
     d.nlr_alpha = float(p['nlr_alpha'])
+    if p['dcf_h'] is not None:
+        h = np.ascontiguousarray(np.asarray(p['dcf_h'], dtype=np.complex128).ravel())
+        if h.size != int(nsymb):
+            raise ValueError('dcf_h: one response value per symbol')
+        d._keep_dcf = h                                   # (the descriptor keeps the array alive)
+        d.dcf_h = h.ctypes.data_as(_lib._dp)
     if easi_passes is not None:
         d.easi_passes = easi_passes.ctypes.data_as(C.POINTER(C.c_int32))
     return d
@@ -62,6 +79,13 @@ def dsp_phases(ctx: _lib.Context, field: _lib.DeviceField, nsymb: int, nt: int, 
     return tr(ph), tr(am), passes
 
 
+def _dcf_response(p, G):
+    """dsp4cohdec.m:198-207 at one sample per symbol (p.workatbaudrate)"""
+    from .gstate import CONSTANTS
+    beta2l = -p['dispersion'] * p['lambda'] ** 2 / 2 / math.pi / CONSTANTS.CLIGHT * 1e-21
+    return disp_comp_filter(beta2l, float(p['baudrate']), int(G.NSYMB), int(p['ndispsym']))
+
+
 def dsp4cohdec(ich, pat, x, p, ctx=None):
     """[Phases, Amplitudes] = dsp4cohdec(ich, pat, x, p) -- dsp4cohdec.m:1, for a two-polarization QPSK field, on the device:
     receiver_cohmix (polmux_b200/receiver.py), the shift by the receiver's delay (:167-169), one sample per symbol,
@@ -70,13 +94,14 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
     Differences stated in DESIGN.md: x.delay must be 'theory' (the pattern-correlation search of mygeteyeinfo is not
     built, so `pat` only tells the number of polarizations and worsteyeop is not returned), the decimator (`decimate`, a
     Signal Processing Toolbox function outside the reference tree) is replaced by plain sampling at the symbol centres;
-    p.applydcf and the 'singlepol' demultiplexer raise (p.applyadc, p.applynlr, 'cma', 'easi' and 'combo' are built)."""
+    the 'singlepol' demultiplexer raises; p.applyadc, p.applydcf (with p.workatbaudrate), p.applynlr, 'cma', 'easi' and 'combo' are built."""
     from . import receiver as _rx
     from .gstate import GSTATE as G
     if x.get('rec', 'coherent') != 'coherent':
         raise ValueError("Flag X.rec must be 'coherent'")                       # dsp4cohdec.m:143
-    if p.get('applydcf'):   # (a post-compensating all-pass fiber is available through x.dpost, receiver_cohmix.m:139-166)
-        raise NotImplementedError('dsp4cohdec: p.applydcf is not built')
+    if p.get('applydcf') and not p.get('workatbaudrate'):
+        raise NotImplementedError('dsp4cohdec: p.applydcf at two samples per symbol needs the decimator (not built); '
+                                  'set p.workatbaudrate, or compensate with x.dpost')
     method = str(p.get('polmethod', 'cma')).lower()
     if p.get('applypol') and method not in ('cma', 'easi', 'combo'):
         if method == 'singlepol':
@@ -109,6 +134,7 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
                       modorder=2, freqavg=int(p.get('freqavg', 500)), phasavg=int(p.get('phasavg', 3)),
                       poworder=int(p.get('poworder', 2)), sample_shift=int(round(delay * G.NT)),
                       nlr_alpha=float(p['nlralpha']) if p.get('applynlr') else 0.0,
+                      dcf_h=_dcf_response(p, G) if p.get('applydcf') else None,
                       peak=4.0 * math.sqrt(float(np.asarray(G.POWER).ravel()[ich - 1])))
         ph, am, _ = dsp_phases(ctx, col, G.NSYMB, G.NT, **params)
     finally:

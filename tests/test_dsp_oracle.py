@@ -83,6 +83,16 @@ def test_easipolardemux_matches_reference_source():
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-11)
 
 
+def test_dispcompfilter_matches_reference_source():
+    it = Interp(REF)
+    beta2l = -800.0 * 1550.0 ** 2 / 2 / np.pi / 299792458.0 * 1e-21
+    for n, flen in ((256, 16), (512, 32)):
+        ref = np.asarray(_local(it, 'DispCompFilter', [to_m(beta2l), to_m(28e9), to_m(n), to_m(flen)])[0]).ravel()
+        got = dsp.disp_comp_filter(beta2l, 28e9, n, flen)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+        assert abs(np.abs(got).mean() - 1) < 0.2          # close to an all-pass response
+
+
 def test_nlrotation_matches_reference_source():
     x, _ = _signals(128, 7)
     x = x * (1 + 0.3 * np.random.Generator(np.random.PCG64(8)).standard_normal((128, 1)))

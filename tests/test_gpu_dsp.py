@@ -181,7 +181,7 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
     with pytest.raises(NotImplementedError, match='theory'):
         dsp.dsp4cohdec(1, pat, dict(x, delay='estimate'), p)
     with pytest.raises(NotImplementedError, match='applydcf'):
-        dsp.dsp4cohdec(1, pat, x, dict(p, applydcf=True))
+        dsp.dsp4cohdec(1, pat, x, dict(p, applydcf=True, workatbaudrate=False))
     # p.applyadc (5 bits) and p.applynlr: the same chain with the oracle's ADC on the currents and NLRotation on the sampled,
     # not yet normalised signals
     p2 = dict(p, applyadc=True, adcbits=5, applynlr=True, nlralpha=0.02)
@@ -195,6 +195,18 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
     away = np.abs(np.abs(want2) - math.pi) > 1e-6
     np.testing.assert_allclose(ph2[away], want2[away], rtol=0, atol=1e-9)
     assert not np.allclose(am2, amps)
+    # p.applydcf at one sample per symbol: the truncated-FIR dispersion compensation of DispCompFilter on the sampled signals
+    p3 = dict(p, applydcf=True, dispersion=300.0, ndispsym=16, baudrate=28e9)
+    p3['lambda'] = 1550.0
+    ph3, am3 = dsp.dsp4cohdec(1, pat, x, p3)
+    s3 = np.stack([iric[idx, 0] + 1j * iric[idx, 1], iric[idx, 2] + 1j * iric[idx, 3]], axis=1)
+    s3 = dsp_orc.apply_dcf(s3, 300.0, 1550.0, 28e9, 16) / (4 * math.sqrt(float(G.POWER[0])))
+    y3, _ = dsp_orc.cma_polar_demux(s3, mu=1 / 2000, taps=7)
+    want3 = dsp_orc.carrier_recovery(y3, 2, 200, 3, 2)
+    np.testing.assert_allclose(am3, np.abs(y3), rtol=1e-8, atol=1e-11)
+    away = np.abs(np.abs(want3) - math.pi) > 1e-6
+    np.testing.assert_allclose(ph3[away], want3[away], rtol=0, atol=1e-8)
+    assert not np.allclose(am3, amps)
 
 
 @pytest.mark.parametrize('method', ['easi', 'combo'])
