@@ -292,7 +292,7 @@ int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t ns
  * mygeteyeinfo's pattern-correlation timing search (the 'theory' delay of dsp4cohdec.m:490-503 enters as sample_shift) and
  * the decimator of dsp4cohdec.m:176-184 -- `decimate` is a Signal Processing Toolbox function that is not in the
  * reference tree; the currents are sampled at the symbol centres without its anti-alias FIR.  p.applyadc is
- * pmx_field_quantize on the currents, p.applynlr the desc's nlr_alpha. */
+ * pmx_field_quantize on the currents, p.applynlr the desc's nlr_alpha, p.applydcf (one sample per symbol) its dcf_h. */
 typedef struct pmx_dsp_desc {
     int32_t nsymb, nt;        /* symbols per block, samples per symbol                                   */
     int32_t apply_cma;        /* p.applypol with p.polmethod = 'cma'                                      */
