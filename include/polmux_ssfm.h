@@ -290,8 +290,9 @@ int pmx_qpsk_count(pmx_ctx* ctx, pmx_devfield* f, const uint8_t* sym, int32_t ns
  * Neither the waveplates nor the transmitted symbols enter the processing; ref_patmat is only counted against.
  * The front-end of receiver_cohmix.m is pmx_filter_create / pmx_field_modulate / pmx_cohmix_exec below.  Not built:
  * mygeteyeinfo's pattern-correlation timing search (the 'theory' delay of dsp4cohdec.m:490-503 enters as sample_shift) and
- * the decimator of dsp4cohdec.m:176-184 -- `decimate` is a Signal Processing Toolbox function that is not in the
- * reference tree; the currents are sampled at the symbol centres without its anti-alias FIR.  p.applyadc is
+ * a pinned decimator (dsp4cohdec.m:176-184) -- `decimate` is a Signal Processing Toolbox function that is not in the
+ * reference tree; the currents are sampled at the symbol centres, optionally behind an anti-alias FIR the caller designs
+ * (decim_taps).  p.applyadc is
  * pmx_field_quantize on the currents, p.applynlr the desc's nlr_alpha, p.applydcf (one sample per symbol) its dcf_h. */
 typedef struct pmx_dsp_desc {
     int32_t nsymb, nt;        /* symbols per block, samples per symbol                                   */
@@ -320,6 +321,13 @@ typedef struct pmx_dsp_desc {
     const double* dcf_h;      /* p.applydcf: HOST [nsymb] complex Hfilt of DispCompFilter (dsp4cohdec.m:289-297) applied to the
                                * sampled signals, ifft(fft(Signals).*Hfilt) (:198-210), before the rotation above; or NULL;
                                * nsymb must then be a power of two >= 64                                                  */
+    /* The decimator's anti-alias FIR in front of the sampling (dsp4cohdec.m:176-184: decimate(I, r, 16, 'fir')).  `decimate`
+     * and `fir1` belong to the Signal Processing Toolbox, not to the reference tree: the caller designs the taps (the host
+     * mirror restates the toolbox's PUBLISHED algorithm -- Hamming-windowed sinc, unit DC gain, group delay compensated;
+     * parity unpinned) and the sampler evaluates filter(b,1,I) at the sampling instants only, circularly. */
+    int32_t decim_ntaps;      /* 0 / 1: plain sampling; else odd, <= 65                                                  */
+    int32_t reserved2;
+    const double* decim_taps; /* HOST [decim_ntaps]                                                                      */
 } pmx_dsp_desc;
 /* ref_patmat: HOST [nsymb][4] bytes, the differentially decoded transmitted pattern [x1 x2 y1 y2] (pat_decoder of the
  * transmitted bits); counts_dev: DEVICE [batch] int64 (e.g. the NCCL send buffer); passes_host (may be NULL): [batch]

@@ -23,9 +23,10 @@ PARITY PINNING: tests/test_dsp_oracle.py executes the reference's own cmaadaptiv
 pat_decoder.m (+ pat2stars.m, stars2pat.m, fastshift.m) and the sub-functions vitvit / cmapolardemux / easipolardemux of
 dsp4cohdec.m with the mini interpreter (oracle/mini_m) on seeded inputs and compares them with this file.
 
-NOT restated (and not built): the front-end of receiver_cohmix.m (optical / electrical filters, LO mixing),
-mygeteyeinfo's timing search and the toolbox function `decimate` (dsp4cohdec.m:176-184, not in the tree): the
-chain here starts from one complex sample per symbol and polarization.
+The front-end of receiver_cohmix.m is restated in oracle/receiver_oracle.py.  NOT restated: mygeteyeinfo's timing
+search.  PARITY UNPINNED for one function: `decimate_fir` below stands in for the toolbox functions decimate / fir1
+(dsp4cohdec.m:176-184; Signal Processing Toolbox, not in the reference tree, no golden vector): it restates their
+published description and is checked against the product's own design only.
 """
 from __future__ import annotations
 
@@ -139,6 +140,22 @@ def easi_polar_demux(x, mu=1 / 6000, phizero=0.0, max_passes=None):
             conv = True
         c += 1
     return y, c - 1
+
+
+def decimate_fir(x, r, order=16):
+    """decimate(x, r, order, 'fir') after the toolbox's published description, PARITY UNPINNED: b = fir1(order, 1/r)
+    (Hamming-windowed sinc, unit DC gain), filter(b, 1, x), every r-th sample from the group delay order/2 on; circular
+    at the ends (the toolbox mirrors the record there).  x: [N] or [N, ncol] -> [N/r, ...]"""
+    n = np.arange(order + 1)
+    wn = 1.0 / r
+    ideal = np.where(n == order / 2.0, wn, np.sin(math.pi * wn * (n - order / 2.0)) / (math.pi * (n - order / 2.0) + (n == order / 2.0)))
+    b = ideal * (0.54 - 0.46 * np.cos(2 * math.pi * n / order))
+    b = b / np.sum(b)
+    x = np.asarray(x)
+    y = np.zeros(x.shape, dtype=np.result_type(x.dtype, np.float64))
+    for j in range(order + 1):
+        y = y + b[j] * np.roll(x, j - order // 2, axis=0)     # filter(b,1,x)(m + order/2) = sum_j b(j) x(m + order/2 - j)
+    return y[::r]
 
 
 def disp_comp_filter(beta2l, bw, n, flen):

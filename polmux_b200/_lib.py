@@ -75,7 +75,7 @@ class DspDesc(C.Structure):
                 ('R', C.c_double * 2), ('phizero', C.c_double), ('max_passes', C.c_int32), ('modorder', C.c_int32),
                 ('freqavg', C.c_int32), ('phasavg', C.c_int32), ('poworder', C.c_int32), ('sample_shift', C.c_int32),
                 ('peak', C.c_double), ('apply_easi', C.c_int32), ('easi_max_passes', C.c_int32), ('easi_mu', C.c_double),
-                ('easi_phizero', C.c_double), ('easi_passes', C.POINTER(C.c_int32)), ('nlr_alpha', C.c_double), ('dcf_h', _dp)]
+                ('easi_phizero', C.c_double), ('easi_passes', C.POINTER(C.c_int32)), ('nlr_alpha', C.c_double), ('dcf_h', _dp), ('decim_ntaps', C.c_int32), ('reserved2', C.c_int32), ('decim_taps', _dp)]
 
 
 class McReceiver(C.Structure):

@@ -1677,8 +1677,14 @@ extern "C" int pmx_qpsk_count(pmx_ctx* c, pmx_devfield* f, const uint8_t* sym, i
 // sig[(b*2 + pol)*L + k] = field sample at time index k*nt + shift (circular): the centre of symbol k for a field, the
 // centre delayed by the receiver's filters for its currents (fastshift(Irx, round(-delay*NT)), dsp4cohdec.m:167-169);
 // divided by `peak` (dsp4cohdec.m:226-227) or, with peak = 0, by sqrt(mean |s|^2 over both polarizations)
+#define PMX_DECIM_MAX_TAPS 65
+struct DecimTaps {   // the decimator's low-pass FIR (decimate(...,'fir'), dsp4cohdec.m:176-184); n <= 1: none
+    int n;
+    double h[PMX_DECIM_MAX_TAPS];
+};
 __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t N, int l1, int l2, int nsymb, int nt,
-                                                        long long shift, double peak, double nlr_alpha, int raw, cpx* sig) {
+                                                        long long shift, double peak, double nlr_alpha, int raw, DecimTaps fir,
+                                                        cpx* sig) {
     __shared__ double red[256];
     const int b = blockIdx.x;
     const cpx* fld = field + (size_t)b * N * 2;
@@ -1698,8 +1704,27 @@ __global__ void __launch_bounds__(256) pmx_k_dsp_sample(const cpx* field, size_t
     };
     double acc = 0.0;
     for (int k = threadIdx.x; k < nsymb; k += blockDim.x) {
-        const size_t m = at(k);
-        const cpx x = fld[2 * m], y = fld[2 * m + 1];
+        cpx x, y;
+        if (fir.n > 1) {
+            // filter(b,1,I) read at the sampling instant plus the filter's group delay (n-1)/2, as decimate compensates
+            // it: sum_j b(j) * I(c + (n-1)/2 - j), circular
+            const long long c0 = (long long)k * nt + shift + (fir.n - 1) / 2;
+            double xr = 0.0, xi = 0.0, yr = 0.0, yi = 0.0;
+            for (int j = 0; j < fir.n; ++j) {
+                const size_t m = pmx_mem_index((size_t)((c0 - j) & (long long)(N - 1)), l1, l2);
+                const cpx u = fld[2 * m], v = fld[2 * m + 1];
+                xr += fir.h[j] * u.x;
+                xi += fir.h[j] * u.y;
+                yr += fir.h[j] * v.x;
+                yi += fir.h[j] * v.y;
+            }
+            x = make_double2(xr, xi);
+            y = make_double2(yr, yi);
+        } else {
+            const size_t m = at(k);
+            x = fld[2 * m];
+            y = fld[2 * m + 1];
+        }
         sx[k] = x;
         sy[k] = y;
         acc += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
@@ -2205,8 +2230,19 @@ static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const ui
     {
         const long long N = (long long)f->nfft;
         const long long sh = (((long long)d->sample_shift % N) + N) % N;
+        DecimTaps fir;
+        fir.n = 0;
+        if (d->decim_ntaps > 1 && d->decim_taps) {
+            if (d->decim_ntaps > PMX_DECIM_MAX_TAPS || !(d->decim_ntaps & 1)) {
+                for (void* q : {(void*)sig, (void*)y, (void*)w1, (void*)w2, (void*)om, (void*)ph, (void*)dref, (void*)acc, (void*)dpass})
+                    cudaFreeAsync(q, c->stream);
+                return set_err(c, PMX_ERR_INVALID, "%s: decim_ntaps must be odd, <= %d", who, PMX_DECIM_MAX_TAPS);
+            }
+            fir.n = d->decim_ntaps;
+            for (int j = 0; j < fir.n; ++j) fir.h[j] = d->decim_taps[j];
+        }
         pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(f->data, (size_t)f->nfft, f->log2N1, f->log2N2, L, d->nt, sh, d->peak, d->nlr_alpha,
-                                                  d->dcf_h ? 1 : 0, sig);
+                                                  d->dcf_h ? 1 : 0, fir, sig);
     }
     if (d->dcf_h) {
         // p.applydcf: Signals = ifft(fft(Signals) .* Hfilt) on the sampled signals (dsp4cohdec.m:198-210), before the
@@ -2222,7 +2258,9 @@ static int dsp_core(pmx_ctx* c, pmx_devfield* f, const pmx_dsp_desc* d, const ui
             rc = pmx_fiber_exec(fp, tf, nullptr);
         }
         if (rc == PMX_OK) {
-            pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(tf->data, (size_t)L, tf->log2N1, tf->log2N2, L, 1, 0, d->peak, d->nlr_alpha, 0, sig);
+            DecimTaps none;
+            none.n = 0;
+            pmx_k_dsp_sample<<<B, 256, 0, c->stream>>>(tf->data, (size_t)L, tf->log2N1, tf->log2N2, L, 1, 0, d->peak, d->nlr_alpha, 0, none, sig);
             c->launches++;
             if (cudaGetLastError() != cudaSuccess) rc = set_err(c, PMX_ERR_CUDA, "%s: dispersion-compensation kernels failed", who);
         }

@@ -14,7 +14,7 @@ from . import _lib
 
 DEFAULTS = dict(applypol=True, taps=7, mu=1 / 6000, R=(1.0, 1.0), phizero=0.0, max_passes=0, modorder=2, freqavg=500,
                 phasavg=3, poworder=2, sample_shift=0, peak=0.0, applyeasi=False, easi_mu=1 / 6000, easi_phizero=0.0,
-                easi_max_passes=0, nlr_alpha=0.0, dcf_h=None)
+                easi_max_passes=0, nlr_alpha=0.0, dcf_h=None, decim_taps=None)
 
 
 def reference_pattern(sym_x, sym_y):
@@ -30,6 +30,19 @@ def reference_pattern(sym_x, sym_y):
         m0, m1 = ((d == 2) | (d == 3)).astype(np.uint8), ((d == 1) | (d == 2)).astype(np.uint8)   # stars2pat
         out += [1 - m0, 1 - m1]                                                                   # patmat = ~patmat
     return np.ascontiguousarray(np.stack(out, axis=1), dtype=np.uint8)
+
+
+def fir1_lowpass(order, wn):
+    """The low-pass design decimate(x, r, order, 'fir') asks fir1 for, fir1(order, 1/r) -- Signal Processing Toolbox functions
+    that are NOT in the reference tree (dsp4cohdec.m:176-184 calls decimate).  Restated from the toolbox's published
+    description: ideal low-pass impulse response wn*sinc(wn*(n - order/2)), Hamming window 0.54 - 0.46*cos(2*pi*n/order),
+    scaled to unit gain at DC; decimate filters in one direction and takes every r-th sample from the filter's group delay
+    on, i.e. a zero-phase FIR read at the sampling instants.  PARITY UNPINNED: no toolbox source and no golden vector
+    exist here; decimate's mirror extension at the two ends of the record is replaced by the circular one of the rest
+    of the chain."""
+    n = np.arange(order + 1)
+    h = wn * np.sinc(wn * (n - order / 2.0)) * (0.54 - 0.46 * np.cos(2 * math.pi * n / order))
+    return h / h.sum()
 
 
 def disp_comp_filter(beta2l, bw, n, flen):
@@ -60,6 +73,10 @@ def _desc(nsymb, nt, params, easi_passes=None):
             raise ValueError('dcf_h: one response value per symbol')
         d._keep_dcf = h                                   # (the descriptor keeps the array alive)
         d.dcf_h = h.ctypes.data_as(_lib._dp)
+    if p['decim_taps'] is not None:
+        t = np.ascontiguousarray(np.asarray(p['decim_taps'], dtype=np.float64).ravel())
+        d._keep_taps = t
+        d.decim_ntaps, d.decim_taps = int(t.size), t.ctypes.data_as(_lib._dp)
     if easi_passes is not None:
         d.easi_passes = easi_passes.ctypes.data_as(C.POINTER(C.c_int32))
     return d
@@ -86,19 +103,22 @@ def _dcf_response(p, G):
     return disp_comp_filter(beta2l, float(p['baudrate']), int(G.NSYMB), int(p['ndispsym']))
 
 
-def dsp4cohdec(ich, pat, x, p, ctx=None):
+def dsp4cohdec(ich, pat, x, p, ctx=None, decimator='fir'):
     """[Phases, Amplitudes] = dsp4cohdec(ich, pat, x, p) -- dsp4cohdec.m:1, for a two-polarization QPSK field, on the device:
     receiver_cohmix (polmux_b200/receiver.py), the shift by the receiver's delay (:167-169), one sample per symbol,
     normalisation by 4*sqrt(POWER(ich)) (:226-227), polarization demultiplexer (p.applypol, 'cma'), carrier recovery
     (p.freqavg / phasavg / poworder).  -> (Phases [nsymb, 2], Amplitudes [nsymb, 2]).
     Differences stated in DESIGN.md: x.delay must be 'theory' (the pattern-correlation search of mygeteyeinfo is not
-    built, so `pat` only tells the number of polarizations and worsteyeop is not returned), the decimator (`decimate`, a
-    Signal Processing Toolbox function outside the reference tree) is replaced by plain sampling at the symbol centres;
+    built, so `pat` only tells the number of polarizations and worsteyeop is not returned); the decimator (`decimate`, a
+    Signal Processing Toolbox function outside the reference tree) is restated from its published description
+    (decimator='fir': fir1_lowpass(16, 1/NT) read at the symbol centres, parity unpinned) or left out (decimator='sample');
     the 'singlepol' demultiplexer raises; p.applyadc, p.applydcf (with p.workatbaudrate), p.applynlr, 'cma', 'easi' and 'combo' are built."""
     from . import receiver as _rx
     from .gstate import GSTATE as G
     if x.get('rec', 'coherent') != 'coherent':
         raise ValueError("Flag X.rec must be 'coherent'")                       # dsp4cohdec.m:143
+    if decimator not in ('fir', 'sample'):
+        raise ValueError("decimator must be 'fir' or 'sample'")
     if p.get('applydcf') and not p.get('workatbaudrate'):
         raise NotImplementedError('dsp4cohdec: p.applydcf at two samples per symbol needs the decimator (not built); '
                                   'set p.workatbaudrate, or compensate with x.dpost')
@@ -135,6 +155,7 @@ def dsp4cohdec(ich, pat, x, p, ctx=None):
                       poworder=int(p.get('poworder', 2)), sample_shift=int(round(delay * G.NT)),
                       nlr_alpha=float(p['nlralpha']) if p.get('applynlr') else 0.0,
                       dcf_h=_dcf_response(p, G) if p.get('applydcf') else None,
+                      decim_taps=fir1_lowpass(16, 1.0 / G.NT) if decimator == 'fir' else None,
                       peak=4.0 * math.sqrt(float(np.asarray(G.POWER).ravel()[ich - 1])))
         ph, am, _ = dsp_phases(ctx, col, G.NSYMB, G.NT, **params)
     finally:

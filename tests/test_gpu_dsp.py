@@ -158,7 +158,7 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
     pat = np.stack([sx[:, 0], sy[:, 0]], axis=1)
     hx, hy = np.array(G.FIELDX), np.array(G.FIELDY)
     delay0 = float(0.5 * (G.DELAY[0, 0] + G.DELAY[1, 0]))
-    phases, amps = dsp.dsp4cohdec(1, pat, x, p)
+    phases, amps = dsp.dsp4cohdec(1, pat, x, p, decimator='sample')
     assert phases.shape == (nsymb, 2) and amps.shape == (nsymb, 2)
 
     class GS:
@@ -185,7 +185,7 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
     # p.applyadc (5 bits) and p.applynlr: the same chain with the oracle's ADC on the currents and NLRotation on the sampled,
     # not yet normalised signals
     p2 = dict(p, applyadc=True, adcbits=5, applynlr=True, nlralpha=0.02)
-    ph2, am2 = dsp.dsp4cohdec(1, pat, x, p2)
+    ph2, am2 = dsp.dsp4cohdec(1, pat, x, p2, decimator='sample')
     iq = dsp_orc.adc_quantize(iric, 5)
     s2 = np.stack([iq[idx, 0] + 1j * iq[idx, 1], iq[idx, 2] + 1j * iq[idx, 3]], axis=1)
     s2 = dsp_orc.nl_rotation(s2, 0.02) / (4 * math.sqrt(float(G.POWER[0])))
@@ -198,7 +198,7 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
     # p.applydcf at one sample per symbol: the truncated-FIR dispersion compensation of DispCompFilter on the sampled signals
     p3 = dict(p, applydcf=True, dispersion=300.0, ndispsym=16, baudrate=28e9)
     p3['lambda'] = 1550.0
-    ph3, am3 = dsp.dsp4cohdec(1, pat, x, p3)
+    ph3, am3 = dsp.dsp4cohdec(1, pat, x, p3, decimator='sample')
     s3 = np.stack([iric[idx, 0] + 1j * iric[idx, 1], iric[idx, 2] + 1j * iric[idx, 3]], axis=1)
     s3 = dsp_orc.apply_dcf(s3, 300.0, 1550.0, 28e9, 16) / (4 * math.sqrt(float(G.POWER[0])))
     y3, _ = dsp_orc.cma_polar_demux(s3, mu=1 / 2000, taps=7)
@@ -207,6 +207,18 @@ def test_dsp4cohdec_returns_the_oracles_phases_and_amplitudes():
     away = np.abs(np.abs(want3) - math.pi) > 1e-6
     np.testing.assert_allclose(ph3[away], want3[away], rtol=0, atol=1e-8)
     assert not np.allclose(am3, amps)
+    # the default: the decimator's anti-alias FIR (fir1(16, 1/NT), restated from the toolbox's published description)
+    # in front of the sampling
+    ph4, am4 = dsp.dsp4cohdec(1, pat, x, p)
+    dec = dsp_orc.decimate_fir(np.roll(iric, -shift, axis=0), nt)
+    s4 = np.stack([dec[:, 0] + 1j * dec[:, 1], dec[:, 2] + 1j * dec[:, 3]], axis=1) / (4 * math.sqrt(float(G.POWER[0])))
+    y4, _ = dsp_orc.cma_polar_demux(s4, mu=1 / 2000, taps=7)
+    want4 = dsp_orc.carrier_recovery(y4, 2, 200, 3, 2)
+    np.testing.assert_allclose(am4, np.abs(y4), rtol=1e-9, atol=1e-12)
+    away = np.abs(np.abs(want4) - math.pi) > 1e-6
+    np.testing.assert_allclose(ph4[away], want4[away], rtol=0, atol=1e-9)
+    assert not np.allclose(am4, amps)
+    assert dsp_orc.count_errors_dqpsk(ph4, tx_phase) <= dsp_orc.count_errors_dqpsk(phases, tx_phase)   # less noise behind the FIR
 
 
 @pytest.mark.parametrize('method', ['easi', 'combo'])
