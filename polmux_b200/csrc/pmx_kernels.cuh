@@ -985,15 +985,30 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     };
     // The step package travels on its own mbarrier: it is a few KB out of the L2 and lands long before the tile, so
     // the threads can evaluate everything that does not depend on the field while the tile is still in flight.
-    auto issue = [&](int tl, int buf) {  // one thread
+    // (PMX_B_EARLY_PKG: the next tile's package is fetched while the current tile is still being worked on -- its buffer and
+    // its barrier are free from the moment every thread has picked up the current one -- so that the data-independent
+    // phasors of the next tile start the moment the tile's store has been issued, under the tile load)
+    auto issue_pkg = [&](int tl, int buf) {  // one thread
         pmx_fence_proxy_async();
-        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb;
         int b_, col_;
         pmx_split_bc(bc, f, b_, col_);
         pmx_mbar_expect_tx(mbar + 1, S::PKG_BYTES);
         pmx_bulk_load(aux0 + buf * S::AUX_BYTES, &p.pkg[b_], S::PKG_BYTES, mbar + 1);
+    };
+    auto issue_tile = [&](int tl) {  // one thread
+        pmx_fence_proxy_async();
+        const int tt = wk.phys(tl), bc = tt >> wk.ltpb, c0 = (tt & wk.tpb_mask) * G;
         pmx_mbar_expect_tx(mbar, S::TILE_BYTES);
         for (int r0 = 0; r0 < L; r0 += 256) pmx_tma_load_3d(in + r0 * PITCH, &tmap, c0 * 4, r0, p.bc0 + bc, mbar);
+    };
+    auto issue = [&](int tl, int buf) {  // one thread
+#ifndef PMX_B_EARLY_PKG
+        issue_pkg(tl, buf);
+#else
+        (void)buf;
+#endif
+        issue_tile(tl);
     };
     if (threadIdx.x == 0) {
         pmx_mbar_init(mbar, 1);
@@ -1008,6 +1023,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
     pmx_cache_live(sdone, p);
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;
+#ifdef PMX_B_EARLY_PKG
+    if (threadIdx.x == 0 && tile < total) issue_pkg(tile, 0);
+#endif
     if (threadIdx.x == 0 && tile < total) issue(tile, 0);
     pmx_stagger(p);
     uint32_t phase = 0;
@@ -1044,6 +1062,9 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB_B(G*(L / 8), PF))
         for (int q = 0; q < 8; ++q) lds_sa(in, pmx_swz<MASK>((uint32_t)((t + q * T) * PITCH + cl * SA)), x[q], y[q]);
         if (threadIdx.x == 0) pmx_tma_wait_read();  // previous tile's store has left the exchange buffer
         __syncthreads();
+#ifdef PMX_B_EARLY_PKG
+        if (threadIdx.x == 0 && next < total) issue_pkg(next, (it + 1) & 1);   // every thread is past this tile's package wait
+#endif
         if (PF && threadIdx.x == 0 && next < total) issue(next, (it + 1) & 1);
         cpx* sx = work + cl * PmxSmem<L, G>::STRIDE;
         cpx* sy = sx + L;
