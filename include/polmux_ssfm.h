@@ -484,6 +484,12 @@ int pmx_pmd_matrix(pmx_ctx* ctx, int64_t nfft, int32_t nfiber, const pmx_brf* br
 /* [ux; uy] <- J [ux; uy] for every sample of every column; j = 8 doubles, row-major (j11 re, im, j12, j21, j22).  The
  * change of reference system options.mat of inverse_pmd.m:87-89 commutes with the transforms, so it is applied in time. */
 int pmx_field_jones(pmx_ctx* ctx, pmx_devfield* f, const double* j);
+/* inverse_pmd(brf, options) on host buffers in one call (the gateway's 'invpmd', matlab/inverse_pmd.m): the chain's inverse as
+ * reversed / negated single-step runs of the SSFM passes on the device (inverse_pmd.m:91-141), options.mat as a constant
+ * Jones matrix (:87-89), gvd = 0 for options.gvd = 'no', apply = 0 to leave the field alone (:135); U / Uinv as
+ * pmx_pmd_matrix returns them, or NULL.  io: one realization, one column, both polarizations. */
+int pmx_inverse_pmd_run(pmx_ctx* ctx, int64_t nfft, int32_t nfiber, const pmx_brf* brf, const double* mat, int32_t gvd,
+                        int32_t apply, pmx_field* io, double* U, double* Uinv);
 
 #ifdef __cplusplus
 }

@@ -666,6 +666,98 @@ static void cmd_cohmix(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[
     g_stats[1] += 1.0;
 }
 
+static void cmd_invpmd(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+{
+    /* [ux,uy,Uinv4,U4] = ssfm_mex('invpmd', ux, uy, plates, ntr, lcorr, betat, db1, mat, flags)
+     *   plates : sum(ntr) x 3 = [db0 theta epsilon] of the fibers one after the other      ntr, lcorr : 1 x nfiber
+     *   betat, db1 : Nfft x nfiber (brf{k}.betat, brf{k}.db1)      mat : 2 x 2 (options.mat) or []
+     *   flags  : [gvd apply]          Uinv4, U4 : 4 x Nfft, column n = [M11; M21; M12; M22] at GSTATE.FN(n) */
+    pmx_brf brf[64];
+    pmx_field io;
+    mxArray *wu = NULL, *wi = NULL;
+    double matbuf[8], *U = NULL, *Ui = NULL;
+    const double *pl;
+    size_t nfft, nfib, k, n, row = 0, tot;
+    int gvd, apply, rc;
+
+    if (nrhs != 10 || nlhs < 2 || nlhs > 4)
+        mexErrMsgTxt("[ux,uy,Uinv4,U4] = ssfm_mex('invpmd',ux,uy,plates,ntr,lcorr,betat,db1,mat,flags): wrong number of arguments.");
+    nfft = mxGetM(prhs[1]);
+    nfib = mxGetNumberOfElements(prhs[4]);
+    if (mxGetN(prhs[1]) != 1)
+        mexErrMsgTxt("inverse_pmd can be used only with a unique field."); /* inverse_pmd.m:63 */
+    if (nfib < 1 || nfib > 64 || mxGetNumberOfElements(prhs[5]) != nfib || mxGetM(prhs[6]) != nfft || mxGetN(prhs[6]) != nfib ||
+        mxGetM(prhs[7]) != nfft || mxGetN(prhs[7]) != nfib || mxGetN(prhs[3]) != 3 || mxGetNumberOfElements(prhs[9]) != 2)
+        mexErrMsgTxt("ssfm_mex: invpmd: inconsistent fiber tables.");
+    tot = mxGetM(prhs[3]);
+    pl = mxGetPr(prhs[3]);
+    for (k = 0; k < nfib; k++) {
+        memset(&brf[k], 0, sizeof brf[k]);
+        brf[k].ntrunk = (int32_t)mxGetPr(prhs[4])[k];
+        brf[k].lcorr = mxGetPr(prhs[5])[k];
+        if (brf[k].ntrunk < 1 || row + (size_t)brf[k].ntrunk > tot)
+            mexErrMsgTxt("ssfm_mex: invpmd: plates and ntr disagree.");
+        brf[k].db0 = pl + row;
+        brf[k].theta = pl + tot + row;
+        brf[k].epsilon = pl + 2 * tot + row;
+        brf[k].betat = mxGetPr(prhs[6]) + k * nfft;
+        brf[k].db1 = mxGetPr(prhs[7]) + k * nfft;
+        row += (size_t)brf[k].ntrunk;
+    }
+    if (mxGetNumberOfElements(prhs[8]) == 4) { /* row-major re,im of the column-major 2 x 2 */
+        const double *re = mxGetPr(prhs[8]), *im = mxGetPi(prhs[8]);
+        static const int order[4] = {0, 2, 1, 3};
+        for (k = 0; k < 4; k++) {
+            matbuf[2 * k] = re[order[k]];
+            matbuf[2 * k + 1] = im ? im[order[k]] : 0.0;
+        }
+    } else if (mxGetNumberOfElements(prhs[8]) != 0) {
+        mexErrMsgTxt("ssfm_mex: invpmd: options.mat must be 2 x 2.");
+    }
+    gvd = mxGetPr(prhs[9])[0] != 0.0;
+    apply = mxGetPr(prhs[9])[1] != 0.0;
+    plhs[0] = mxCreateDoubleMatrix(nfft, 1, mxCOMPLEX);
+    plhs[1] = mxCreateDoubleMatrix(nfft, 1, mxCOMPLEX);
+    memcpy(mxGetPr(plhs[0]), mxGetPr(prhs[1]), nfft * sizeof(double));
+    if (mxGetPi(prhs[1])) memcpy(mxGetPi(plhs[0]), mxGetPi(prhs[1]), nfft * sizeof(double));
+    memcpy(mxGetPr(plhs[1]), mxGetPr(prhs[2]), nfft * sizeof(double));
+    if (mxGetPi(prhs[2])) memcpy(mxGetPi(plhs[1]), mxGetPi(prhs[2]), nfft * sizeof(double));
+    memset(&io, 0, sizeof io);
+    io.layout = PMX_PLANAR;
+    io.xr = mxGetPr(plhs[0]);
+    io.xi = mxGetPi(plhs[0]);
+    io.yr = mxGetPr(plhs[1]);
+    io.yi = mxGetPi(plhs[1]);
+    if (nlhs > 2) {
+        wi = mxCreateDoubleMatrix(8 * nfft, 1, mxREAL);
+        Ui = mxGetPr(wi);
+    }
+    if (nlhs > 3) {
+        wu = mxCreateDoubleMatrix(8 * nfft, 1, mxREAL);
+        U = mxGetPr(wu);
+    }
+    ensure_ctx();
+    rc = pmx_inverse_pmd_run(g_ctx, (int64_t)nfft, (int32_t)nfib, brf, mxGetNumberOfElements(prhs[8]) == 4 ? matbuf : NULL, gvd,
+                             apply, &io, U, Ui);
+    if (rc != PMX_OK) {
+        if (wi) mxDestroyArray(wi);
+        if (wu) mxDestroyArray(wu);
+        fail("ssfm_mex: invpmd failed");
+    }
+    for (k = 2; k < (size_t)nlhs; k++) { /* interleaved [nfft][4] -> split storage 4 x nfft */
+        const double *src = (k == 2) ? Ui : U;
+        plhs[k] = mxCreateDoubleMatrix(4, nfft, mxCOMPLEX);
+        for (n = 0; n < 4 * nfft; n++) {
+            mxGetPr(plhs[k])[n] = src[2 * n];
+            mxGetPi(plhs[k])[n] = src[2 * n + 1];
+        }
+    }
+    if (wi) mxDestroyArray(wi);
+    if (wu) mxDestroyArray(wu);
+    g_stats[0] += apply ? 1.0 : 0.0;
+    g_stats[1] += apply ? 1.0 : 0.0;
+}
+
 static void command(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
 {
     char cmd[32];
@@ -677,12 +769,14 @@ static void command(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         cmd_ampliflat(nlhs, plhs, nrhs, prhs);
     } else if (!strcmp(cmd, "cohmix")) {
         cmd_cohmix(nlhs, plhs, nrhs, prhs);
+    } else if (!strcmp(cmd, "invpmd")) {
+        cmd_invpmd(nlhs, plhs, nrhs, prhs);
     } else if (!strcmp(cmd, "reset")) {
         drop_resident();
     } else if (!strcmp(cmd, "stats")) {
         plhs[0] = mxCreateDoubleMatrix(1, 3, mxREAL);
         memcpy(mxGetPr(plhs[0]), g_stats, sizeof g_stats);
     } else {
-        mexErrMsgTxt("ssfm_mex: unknown command (fiber, ampliflat, cohmix, reset, stats).");
+        mexErrMsgTxt("ssfm_mex: unknown command (fiber, ampliflat, cohmix, invpmd, reset, stats).");
     }
 }

@@ -1300,6 +1300,18 @@ _simple('logical', lambda x: arr(x) != 0)
 _simple('find', lambda x: (lambda p, a: (p.reshape(1, -1) if a.shape[0] == 1 else p.reshape(-1, 1)))(
     np.flatnonzero(arr(x).flatten('F') != 0).astype(np.float64) + 1, arr(x)))
 _simple('repmat', lambda x, m, n=None: np.tile(num(x), (int(scalar(m)), int(scalar(n if n is not None else m)))))
+def _reshape(x, *dims):
+    a = np.asarray(x) if isinstance(x, np.ndarray) and x.ndim == 3 else num(x)
+    if len(dims) == 1:
+        dims = tuple(np.real(arr(dims[0])).astype(int).ravel())
+    else:
+        dims = tuple(int(scalar(d)) for d in dims)
+    if len(dims) < 2 or len(dims) > 3 or int(np.prod(dims)) != a.size:
+        raise MError('reshape: the number of elements must not change')
+    return np.reshape(a, dims, order='F')
+
+
+_simple('reshape', _reshape)
 _simple('circshift', lambda x, k: np.roll(num(x), int(scalar(k)), axis=(1 if num(x).shape[0] == 1 else 0)))
 _simple('fieldnames', lambda s: MCell(list(s.keys())))
 def _rmfield(st, f):

@@ -2763,6 +2763,82 @@ extern "C" int pmx_field_jones(pmx_ctx* c, pmx_devfield* f, const double* j) {
     return PMX_OK;
 }
 
+// inverse_pmd(brf, options) on host buffers (what the MEX gateway binds for matlab/inverse_pmd.m): inv(U) of a chain is the
+// linear step of every fiber taken backwards -- plates in reverse order, db0, db1 and betat negated, no loss -- one
+// single-step run of the SSFM passes per fiber on the resident field, then the constant Jones matrix of options.mat;
+// U / Uinv from pmx_pmd_matrix.  apply = 0: the field is left alone (io may be NULL).
+extern "C" int pmx_inverse_pmd_run(pmx_ctx* c, int64_t nfft, int32_t nfiber, const pmx_brf* brf, const double* mat, int32_t gvd,
+                                   int32_t apply, pmx_field* io, double* U, double* Uinv) {
+    if (!c || !brf || nfiber < 1) return set_err(c, PMX_ERR_INVALID, "pmx_inverse_pmd_run: bad arguments");
+    if (apply && !io) return set_err(c, PMX_ERR_INVALID, "pmx_inverse_pmd_run: a field is required when it is to be transformed");
+    int rc = PMX_OK;
+    if (U || Uinv) rc = pmx_pmd_matrix(c, nfft, nfiber, brf, mat, gvd, U, Uinv);
+    if (rc != PMX_OK || !apply) return rc;
+    const size_t N = (size_t)nfft;
+    pmx_devfield* f = nullptr;
+    rc = pmx_field_create(c, nfft, 1, 1, PMX_F64, &f);
+    if (rc == PMX_OK) rc = pmx_field_upload(f, io, 0, 1);
+    std::vector<double> nbt(N), ndb1(N), rdb0, rth, rep;
+    const double gam0 = 0.0;
+    for (int k = nfiber - 1; k >= 0 && rc == PMX_OK; --k) {
+        const pmx_brf& b = brf[k];
+        if (b.ntrunk < 1 || !b.db0 || !b.theta || !b.epsilon || !b.betat || !b.db1) {
+            rc = set_err(c, PMX_ERR_INVALID, "pmx_inverse_pmd_run: fiber %d of the chain is incomplete", k);
+            break;
+        }
+        const int nt = b.ntrunk;
+        rdb0.resize(nt);
+        rth.resize(nt);
+        rep.resize(nt);
+        for (int n = 0; n < nt; ++n) {
+            rdb0[n] = -b.db0[nt - 1 - n];
+            rth[n] = b.theta[nt - 1 - n];
+            rep[n] = b.epsilon[nt - 1 - n];
+        }
+        for (size_t n = 0; n < N; ++n) {
+            nbt[n] = gvd ? -b.betat[n] : 0.0;
+            ndb1[n] = -b.db1[n];
+        }
+        pmx_fiber_desc d;
+        memset(&d, 0, sizeof d);
+        d.nfft = nfft;
+        d.nfc = 1;
+        d.batch = 1;
+        d.precision = PMX_F64;
+        d.length = d.dzmaxt = b.lcorr * nt;
+        d.dphimaxt = INFINITY;
+        d.gam = &gam0;
+        d.fls[0] = 1;
+        d.fls[1] = 1;
+        d.nplates = nt;
+        d.plate_sets = 1;
+        d.db0 = rdb0.data();
+        d.theta = rth.data();
+        d.epsilon = rep.data();
+        d.betat = nbt.data();
+        d.db1 = ndb1.data();
+        d.disp_mode = PMX_DISP_VECTOR;
+        d.nsymb = (int32_t)std::min<int64_t>(nfft, INT32_MAX);
+        d.nt = 1;
+        d.symbolrate = 1.0;
+        pmx_plan* p = nullptr;
+        rc = pmx_plan_create(c, &d, &p);
+        if (rc == PMX_OK) rc = pmx_fiber_exec(p, f, nullptr);
+        std::string keep = c->error;
+        pmx_plan_destroy(p);
+        if (rc != PMX_OK) c->error = keep;
+    }
+    if (rc == PMX_OK && mat) {   // U = chain * [m11 m12; -m12* m11*]  ->  Uinv = [m11* -m12; m12* m11] * chain'
+        const double j[8] = {mat[0], -mat[1], -mat[2], -mat[3], mat[2], -mat[3], mat[0], mat[1]};
+        rc = pmx_field_jones(c, f, j);
+    }
+    if (rc == PMX_OK) rc = pmx_field_download(f, io, 0, 1);
+    std::string keep = c->error;
+    pmx_field_destroy(f);
+    if (rc != PMX_OK) c->error = keep;
+    return rc;
+}
+
 // ---------------------------------------------------------------------------
 // Front-end of the coherent receiver (receiver_cohmix.m): copies of field columns, the channel's frequency shift, LO
 // mixing + photodetection.  The two filters in between are filter plans (pmx_filter_create).

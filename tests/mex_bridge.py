@@ -134,6 +134,26 @@ def oracle_gateway(log=None):
             elif np.any(sg):
                 raise NotImplementedError('the oracle-backed gateway takes injected noise only')
             return [ox, oy][:max(nargout, 1)]
+        if cmd == 'invpmd':    # [ux,uy,Uinv4,U4] = ssfm_mex('invpmd', ux, uy, plates, ntr, lcorr, betat, db1, mat, flags)
+            ux, uy, plates, ntr, lcorr, betat, db1, mat, flags = a[1:10]
+            plates = np.asarray(plates, dtype=np.float64)
+            ntr = [int(v) for v in np.asarray(ntr).ravel()]
+            lc = [float(v) for v in np.asarray(lcorr).ravel()]
+            brfs, row = [], 0
+            for k, nt in enumerate(ntr):
+                brfs.append({'db0': plates[row:row + nt, 0], 'theta': plates[row:row + nt, 1], 'epsilon': plates[row:row + nt, 2],
+                             'betat': np.asarray(betat)[:, k:k + 1], 'db1': np.asarray(db1)[:, k:k + 1], 'lcorr': lc[k]})
+                row += nt
+            gvd, apply = [bool(v) for v in np.asarray(flags).ravel()]
+            n = np.asarray(ux).shape[0]
+            uinv, u = orc.inverse_pmd_matrix(brfs, n, mat=(np.asarray(mat) if np.size(mat) else None), gvd=gvd)
+            ox, oy = np.asarray(ux), np.asarray(uy)
+            if apply:
+                fx, fy = np.fft.fft(ox[:, 0]), np.fft.fft(oy[:, 0])
+                ox = np.fft.ifft(uinv[0, 0] * fx + uinv[0, 1] * fy)[:, None]
+                oy = np.fft.ifft(uinv[1, 0] * fx + uinv[1, 1] * fy)[:, None]
+            four = lambda m: np.reshape(m, (4, n), order='F')      # column n = [M11; M21; M12; M22]
+            return [ox, oy, four(uinv), four(u)][:max(nargout, 1)]
         if cmd == 'cohmix':    # [Iric,avgeb] = ssfm_mex('cohmix', sigx, sigy, Hopt, Hel, lo, lophase, band, opt)
             sigx, sigy, hopt, hel, lo, lophase, band = a[1:8]
             n = np.size(sigx)

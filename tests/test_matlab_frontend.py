@@ -248,6 +248,44 @@ def test_receiver_front_end_reproduces_the_interpreted_original(name):
     _rx_check(it, z, m, x, 1e-13)
 
 
+# ---- matlab/inverse_pmd.m
+INVGOLD = os.path.join(GOLD, 'invpmd', 'invpmd_two_fibers.npz')
+INVVARIANTS = {'plain': None, 'mat_nogvd': {'mat': 'MAT', 'gvd': 'no'}, 'noapply': {'apply': 'no'}, 'apply_n': {'apply': 'n', 'mat': 'MAT'}}
+
+
+def _inv_run(it, tag):
+    from oracle.mini_m.interp import MCell
+    z = np.load(INVGOLD)
+    m = json.loads(str(z['meta']))
+    globals_from_python(it, m['nsymb'], m['nt'], 1, m['rate'], m['pavg'], z['prop_FIELDX'], z['prop_FIELDY'])
+    it.globals['GSTATE']['DISP'] = np.ones((2, 1))
+    brfs = MCell([MStruct({k: (to_m(float(z['brf%d_%s' % (f, k)][0])) if k == 'lcorr' else np.array(z['brf%d_%s' % (f, k)], dtype=np.float64).reshape(-1, 1) if k in ('db0', 'theta', 'epsilon') else np.array(z['brf%d_%s' % (f, k)]))
+                           for k in ('db0', 'theta', 'epsilon', 'lcorr', 'betat', 'db1')}) for f in range(2)])
+    opt = INVVARIANTS[tag]
+    args = [brfs] + ([MStruct({k: (to_m(z['mat']) if v == 'MAT' else v) for k, v in opt.items()})] if opt else [])
+    uinv, u = it.call('inverse_pmd', args, 2)
+    return z, np.asarray(uinv), np.asarray(u), it.globals['GSTATE']
+
+
+def _inv_check(z, tag, uinv, u, G, tol):
+    assert uinv.shape == z[tag + '_Uinv'].shape and u.shape == uinv.shape
+    np.testing.assert_allclose(uinv, z[tag + '_Uinv'], rtol=0, atol=tol)
+    np.testing.assert_allclose(u, z[tag + '_U'], rtol=0, atol=tol)
+    assert orc.rel_l2(G['FIELDX'], G['FIELDY'], z[tag + '_FIELDX'], z[tag + '_FIELDY']) < tol
+    applied = tag != 'noapply'
+    np.testing.assert_array_equal(np.asarray(G['DISP']), np.zeros((2, 1)) if applied else np.ones((2, 1)))
+
+
+@needs_ref
+@pytest.mark.parametrize('tag', list(INVVARIANTS))
+def test_inverse_pmd_front_end_reproduces_the_interpreted_original(tag):
+    """matlab/inverse_pmd.m + an oracle-backed ssfm_mex('invpmd', ...) == the interpreted original inverse_pmd.m with every option"""
+    it = Interp([MDIR, REF])
+    it.builtins['ssfm_mex'] = mex_bridge.oracle_gateway()
+    z, uinv, u, G = _inv_run(it, tag)
+    _inv_check(z, tag, uinv, u, G, 1e-12)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _gpu_interp(seed):
     it = Interp([MDIR], rng=np.random.Generator(np.random.PCG64(seed)))
@@ -309,6 +347,15 @@ def test_interpreted_receiver_front_end_on_the_device(name):
     it.builtins['fastexp'] = lambda it_, a, nargout: [np.cos(np.asarray(a[0])) + 1j * np.sin(np.asarray(a[0]))]
     _rx_globals(it, z, m)
     _rx_check(it, z, m, x, 1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', list(INVVARIANTS))
+def test_interpreted_inverse_pmd_front_end_on_the_device(tag):
+    """matlab/inverse_pmd.m interpreted, its ssfm_mex('invpmd', ...) the compiled gateway on the GPU (pmx_inverse_pmd_run)"""
+    it, gw = _gpu_interp(0)
+    z, uinv, u, G = _inv_run(it, tag)
+    _inv_check(z, tag, uinv, u, G, 1e-10)
 
 
 @pytest.mark.gpu
