@@ -871,7 +871,7 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
             any = any || d->beta1[k] != 0.0 || d->beta2[k] != 0.0;
         }
         f.gvd_any = any ? 1 : 0;
-        cudaError_t e = cudaMallocAsync(&p->ctl, (size_t)d->batch * sizeof(StepCtl), c->stream);
+        cudaError_t e = cudaMallocAsync(&p->ctl, 2 * (size_t)d->batch * sizeof(StepCtl), c->stream);
         if (e == cudaSuccess) e = cudaMallocAsync(&p->pkg, (size_t)d->batch * sizeof(StepPkg), c->stream);
         if (e != cudaSuccess) {
             pmx_plan_destroy(p);
@@ -912,7 +912,7 @@ extern "C" int pmx_plan_create(pmx_ctx* c, const pmx_fiber_desc* d, pmx_plan** o
                 }
             }
         }
-        if (e == cudaSuccess) e = cudaMallocAsync(&p->ctl, (size_t)d->batch * sizeof(StepCtl), c->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&p->ctl, 2 * (size_t)d->batch * sizeof(StepCtl), c->stream);
         if (e == cudaSuccess) e = cudaMallocAsync(&p->pkg, (size_t)d->batch * sizeof(StepPkg), c->stream);
         if (raw) cudaFreeAsync(raw, c->stream);
         if (d_any) cudaFreeAsync(d_any, c->stream);
@@ -1079,7 +1079,7 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
     pA.tw4 = tw4A;
     pB.tw4 = tw4B;
 
-    CK(c, cudaMemsetAsync(p->ctl, 0, (size_t)batch * sizeof(StepCtl), c->stream));
+    CK(c, cudaMemsetAsync(p->ctl, 0, 2 * (size_t)batch * sizeof(StepCtl), c->stream));   // ([1]: the second block of the fused control)
     CK(c, cudaMemsetAsync(p->pkg, 0, (size_t)batch * sizeof(StepPkg), c->stream));
     // what the caller gets back, from the control blocks read into h_ctl
     auto collect = [&]() -> int {
@@ -1119,14 +1119,26 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
         CK(c, cudaStreamSynchronize(c->stream));
         return collect();
     }
+    // A batch of one (the reference-style fiber() call) has nothing to overlap the step-control kernel with: pass A then
+    // runs the control itself (pmx_k_passA<..., FUSED>), three dependent launches per step instead of four.
+    // Every CTA of that pass A repeats the (scalar, 2-3 us) control, so it pays while the pass is a single round of CTAs --
+    // fields of up to 2^19 samples; measured at 2^16: 31.9 -> 27.9 us per step, at 2^20 (1024 CTAs in two rounds) -3 %.
+    static const int fused_env = getenv("PMX_FUSED_CTL") ? atoi(getenv("PMX_FUSED_CTL")) : 1;
+    const bool fused = fused_env && batch == 1 && !p->fc.xpm && !c->profile &&
+                       (long)(p->N2 / p->tA->gAC) * nfc <= (long)c->sm_count * c->setup_done[p->N1 + 65536 * p->d.precision].a;
     {
         dim3 g(148 * 2, batch * nfc);
         ProfScope ps(c, 3);
         p->tA->init_max(g, c->stream, pa, p->fc);
-        pmx_k_ctl<<<batch, 128, 0, c->stream>>>(pa, p->fc, 1);
-        c->launches += 2;
+        c->launches += 1;
+        if (!fused) {
+            pmx_k_ctl<<<batch, 128, 0, c->stream>>>(pa, p->fc, 1);
+            c->launches += 1;
+        }
         CK(c, cudaGetLastError());
     }
+    int par = 0;          // fused control: the block the next pass A reads
+    int fused_first = 1;
     if (!fld->has_maps) return set_err(c, PMX_ERR_INVALID, "field has no tensor maps (unsupported nfft)");
     const pmx_ctx::Occ oA = c->setup_done[p->N1 + 65536 * p->d.precision], oB = c->setup_done[p->N2 + 65536 * p->d.precision];
     // Realization groups.  The batch is split into groups that run on their own streams with full-size persistent
@@ -1212,10 +1224,25 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
                     p->tA->xpm_sum(dim3((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), G.nb), G.st, G.pA, G.fc);
                     c->launches++;
                 }
+                if (fused) {   // pass A reads block `par`, writes block `par ^ 1`; pass C gathers the maxima in the new one
+                    G.pA.ctl = p->ctl + par;
+                    G.pA.ctl_out = p->ctl + (par ^ 1);
+                    G.pA.first = fused_first;
+                }
                 { ProfScope ps(c, 0); CK(c, p->tA->passA(G.gA, G.st, G.pA, G.fc, fld->map_rows)); }
                 G.pB.reverse = serp ? (rev[gi] ^= 1) : 0;
                 { ProfScope ps(c, 1); CK(c, p->tB->passB(G.gB, G.st, G.pB, G.fc, fld->map_cols)); }
                 G.pA.reverse = serp ? (rev[gi] ^= 1) : 0;
+                if (fused) {
+                    PassParams pC = G.pA;
+                    pC.ctl = p->ctl + (par ^ 1);
+                    pC.ctl_out = nullptr;
+                    CK(c, p->tA->passC(G.gC, G.st, pC, G.fc, fld->map_rows));
+                    par ^= 1;
+                    fused_first = 0;
+                    c->launches += 3;
+                    continue;
+                }
                 { ProfScope ps(c, 2); CK(c, p->tA->passC(G.gC, G.st, G.pA, G.fc, fld->map_rows)); }
                 if (use_pdl) {
                     cudaLaunchConfig_t cfg = {};
@@ -1241,11 +1268,13 @@ extern "C" int pmx_fiber_exec(pmx_plan* p, pmx_devfield* fld, pmx_fiber_result* 
             CK(c, cudaEventRecord(c->ev_join[g - 1], c->gstream[g - 1]));
             CK(c, cudaStreamWaitEvent(c->stream, c->ev_join[g - 1], 0));
         }
-        CK(c, cudaMemcpyAsync(c->h_ctl, p->ctl, (size_t)batch * sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(c->h_ctl, p->ctl + (fused ? par : 0), (size_t)batch * sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         bool all_done = true;
+        // (fused control: no kernel follows the last step's passes to turn LAST into DONE; LAST at the end of a chunk --
+        // every later launch of the chunk having found the fiber finished -- means the same)
         for (int b = 0; b < batch; ++b)
-            if (c->h_ctl[b].state < PMX_ST_DONE) all_done = false;
+            if (c->h_ctl[b].state < (fused ? PMX_ST_LAST : PMX_ST_DONE)) all_done = false;
         if (all_done) break;
         if (total_steps > 10000000) return set_err(c, PMX_ERR_NUMERIC, "step loop did not terminate");
         // Size the next chunk from what is left: steps beyond the last one of every realization are launches that

@@ -140,6 +140,8 @@ struct FiberConst {
 struct PassParams {
     void* field;            // cpx [batch*nfc][N][2] in the precision of the launch
     StepCtl* ctl;           // [batch]
+    StepCtl* ctl_out;       // fused step control (pass A, a batch of one): the control block the step writes; ctl is read
+    int first;              // fused step control: this launch runs the first step of the fiber
     const void* tw_stage;   // cpx: in-CTA FFT stage twiddles for this L
     const double* betat_p;  // [nfc][N1][N2] permuted so that bin k1 + N1*k2 sits at k1*N2 + k2
     const double* db1_p;    // same layout

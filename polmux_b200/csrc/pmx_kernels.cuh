@@ -484,7 +484,13 @@ struct PmxWalk {
 //
 // pass A: G adjacent rows per tile, thread (t fastest, rl).  Persistent CTAs walk the tile list
 // (tile = realization-column bc, row group); finished realizations are skipped.
-template <typename R, int L, int G, bool PF>
+// FUSED (a batch of ONE realization, the reference-style fiber() call): there is no step-control kernel between pass C
+// and pass A.  Every CTA of pass A runs nextstep + checkstep itself from the control block the previous step left
+// (deterministic scalar code: all CTAs arrive at the same package), under its first tile load; CTA 0 writes the new
+// control block -- into the OTHER of two blocks, so that no CTA reads what another writes -- and the package passes B
+// and C fetch.  One dependent launch per step less.
+#define PMX_FUSED_BYTES (((int)sizeof(StepCtl) + 15) / 16 * 16 + ((int)sizeof(StepPkg) + 15) / 16 * 16 + 16)
+template <typename R, int L, int G, bool PF, bool FUSED = false>
 __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
     pmx_k_passA(PassParams p, FiberConst f, const __grid_constant__ CUtensorMap tmap) {
     using S = PassSmem<L, G, PF, 0>;
@@ -543,12 +549,47 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         pmx_pdl_launch_dependents();
         pmx_pdl_wait();
     }
-    pmx_cache_live(sdone, p);
+    const StepPkg* fpkg = nullptr;
+    if constexpr (FUSED) {
+        for (int i = threadIdx.x; i < PMX_LIVE_CAP; i += blockDim.x) sdone[i] = 0;   // (one realization; decided below)
+    } else {
+        pmx_cache_live(sdone, p);
+    }
     __syncthreads();
     int tile = live(blockIdx.x), it = 0;
     if (threadIdx.x == 0 && tile < total) issue(tile, 0);
-    pmx_stagger(p);
     uint32_t phase = 0;
+    if constexpr (FUSED) {
+        constexpr int CB = ((int)sizeof(StepCtl) + 15) / 16 * 16, PB = ((int)sizeof(StepPkg) + 15) / 16 * 16;
+        unsigned char* fz = sm + ((S::TOTAL + 15) / 16) * 16;
+        StepCtl* sc = reinterpret_cast<StepCtl*>(fz);
+        StepPkg* sp = reinterpret_cast<StepPkg*>(fz + CB);
+        int* s_go = reinterpret_cast<int*>(fz + CB + PB);
+        PMX_ASSERT(p.batch == 1 && p.ctl_out != nullptr && p.ctl_out != p.ctl);
+        for (int i = threadIdx.x; i < (int)(sizeof(StepCtl) / 4); i += blockDim.x)
+            reinterpret_cast<int*>(sc)[i] = reinterpret_cast<const int*>(p.ctl)[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(StepPkg) / 4); i += blockDim.x) reinterpret_cast<int*>(sp)[i] = 0;
+        __syncthreads();
+        PassParams q = p;
+        if (blockIdx.x != 0) {   // the schedule trace is written once
+            q.trace_dz = nullptr;
+            q.trace_ntrunk = nullptr;
+        }
+        const bool go = pmx_ctl_step(sc, sp, q, f, p.first, 0, s_go);
+        __syncthreads();
+        if (blockIdx.x == 0) {
+            for (int i = threadIdx.x; i < (int)(sizeof(StepCtl) / 4); i += blockDim.x)
+                reinterpret_cast<int*>(p.ctl_out)[i] = reinterpret_cast<const int*>(sc)[i];
+            for (int i = threadIdx.x; i < (int)(sizeof(StepPkg) / 4); i += blockDim.x)
+                reinterpret_cast<int*>(p.pkg)[i] = reinterpret_cast<const int*>(sp)[i];
+        }
+        if (!go) {   // the fiber is finished: nothing to do (the tile already asked for must still land)
+            if (tile < total) pmx_mbar_wait(mbar, phase);
+            return;
+        }
+        fpkg = sp;
+    }
+    pmx_stagger(p);
     PMX_T_DECL
     while (tile < total) {
         const int tt = wk.phys(tile), bc = tt >> wk.ltpb, row0 = (tt & wk.tpb_mask) * G;
@@ -557,7 +598,7 @@ __global__ void __launch_bounds__(G*(L / 8), PMX_MINB(G*(L / 8), PF))
         PMX_ASSERT(tt >= 0 && tt < total && bc < p.batch * f.nfc && b < p.batch && col < f.nfc && b * f.nfc + col == bc);
         PMX_ASSERT(row0 + G <= p.N2 && L == p.N1);
         const unsigned char* aux = aux0 + (it & 1) * S::AUX_BYTES;
-        const StepPkg* st = reinterpret_cast<const StepPkg*>(aux);
+        const StepPkg* st = FUSED ? fpkg : reinterpret_cast<const StepPkg*>(aux);
         const cpx* gtab = reinterpret_cast<const cpx*>(aux + S::PKG_BYTES);
         const int next = live(tile + gridDim.x);
         cpx x[8], y[8];

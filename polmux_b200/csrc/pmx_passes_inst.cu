@@ -55,6 +55,11 @@ cudaError_t setup(int* ctasA, int* ctasB, int* ctasC) {
     };
     e = prep(pmx_k_passA<real, L, GAC, PFAC>, SA::TOTAL, SA::THREADS, ctasA);
     if (e != cudaSuccess) return e;
+    {
+        int dummy = 0;
+        e = prep(pmx_k_passA<real, L, GAC, PFAC, true>, ((SA::TOTAL + 15) / 16) * 16 + PMX_FUSED_BYTES, SA::THREADS, &dummy);
+        if (e != cudaSuccess) return e;
+    }
     e = prep(pmx_k_passB<real, L, GB, PFB, false>, SB::TOTAL, SB::THREADS, ctasB);
     if (e != cudaSuccess) return e;
     e = prep(pmx_k_passB<real, L, GB, PFB, true>, SB::TOTAL, SB::THREADS, ctasB);
@@ -77,6 +82,8 @@ cudaError_t launch(K kern, int gx, int threads, int smem, cudaStream_t s, const 
     return cudaLaunchKernelEx(&cfg, kern, p, f, m);
 }
 cudaError_t passA(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
+    if (p.ctl_out)   // fused step control (a batch of one)
+        return launch(pmx_k_passA<real, L, GAC, PFAC, true>, gx, SA::THREADS, ((SA::TOTAL + 15) / 16) * 16 + PMX_FUSED_BYTES, s, p, f, m);
     return launch(pmx_k_passA<real, L, GAC, PFAC>, gx, SA::THREADS, SA::TOTAL, s, p, f, m);
 }
 cudaError_t passB(int gx, cudaStream_t s, const PassParams& p, const FiberConst& f, const CUtensorMap& m) {
